@@ -1,0 +1,213 @@
+/* lfb200.h -- C ABI of the B200-native lens-flare ghost engine (liblfb200.so).
+ *
+ * The reference (aatifjiwani/lens-flare) has no plugin/FFI boundary: its ghost
+ * path is a set of C++ members and file-scope functions in namespace CGL.  This
+ * header is the seam a maintainer cuts at: each
+ * entry point names the reference interface it replaces (file:line relative to
+ * the reference tree).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Threading: like the reference (raytraced_renderer.cpp:303-311 calls the path
+ * once per render on the caller's thread) an engine is used by one thread at a
+ * time.  All calls are blocking unless the name ends in _device/_async.
+ * Errors: int status, 0 = LFB_OK, negative = failure; lfb_last_error() returns a
+ * thread-local message.  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with LFB_ERR_NO_DEVICE.
+ */
+#ifndef LFB200_H
+#define LFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFB_ABI_VERSION 1
+#define LFB_MAX_SURFACES 16
+#define LFB_MAX_LAMBDA 64
+
+typedef struct lfb_engine lfb_engine;
+
+enum lfb_status {
+  LFB_OK = 0,
+  LFB_ERR_INVALID = -1,   /* bad argument */
+  LFB_ERR_NO_DEVICE = -2, /* no CUDA device / driver: the engine never falls back to the CPU */
+  LFB_ERR_CUDA = -3,      /* a CUDA runtime call failed (message has the CUDA error string) */
+  LFB_ERR_STATE = -4,     /* lens or aperture not set yet */
+  LFB_ERR_NOMEM = -5
+};
+
+/* Rendering modes.
+ * REF_QUADS      bit-faithful PathTracer::generate_ghost_buffer (pathtracer.cpp:714-762):
+ *                two marginal rays per ghost through the reference's ABCD chain
+ *                (:588-689), ghost quad (:433-508) and textured-triangle raster (:305-410).
+ * PARAXIAL_GRID  N x N ray bundle per ghost pushed through the SAME ABCD matrices
+ *                (per ray, both meridional axes), aperture-mask lookup at every
+ *                stop crossing, splat on the sensor.
+ * EXACT_GRID     N x N ray bundle traced through the real prescription: sphere/plane
+ *                intersection, vector Snell refraction with n(lambda), Fresnel +
+ *                quarter-wave coating reflectance (physics absent from the reference,
+ *                SURVEY.md 8a row a13), aperture lookup, splat. */
+enum lfb_mode { LFB_MODE_REF_QUADS = 0, LFB_MODE_PARAXIAL_GRID = 1, LFB_MODE_EXACT_GRID = 2 };
+
+/* Ghost pair sets.  REF13 = what generate_ghost_buffer draws (both reflections on the
+ * same side of the stop, pathtracer.cpp:735-762); ALL = every i<j of non-stop surfaces
+ * (28 for the built-in lens). */
+enum lfb_pairset { LFB_PAIRS_REF = 0, LFB_PAIRS_ALL = 1 };
+
+/* Output element of lfb_render_ghosts.  F64x3 with stride 24 or 32 is the in-memory
+ * layout of the reference's HDRImageBuffer::data (util/image.h:239; sizeof(Vector3D)
+ * is 24, or 32 when the reference is built with -mavx, CGL/include/CGL/vector3D.h:30-43). */
+enum lfb_elem { LFB_F32x3 = 0, LFB_F64x3 = 1 };
+
+enum lfb_precision { LFB_FP32 = 0, LFB_FP64 = 1 };
+enum lfb_splat { LFB_SPLAT_NEAREST = 0, LFB_SPLAT_BILINEAR = 1 };
+
+/* Per-ray flags reported by lfb_dump_rays. */
+enum lfb_ray_flags {
+  LFB_RAY_OK = 0,
+  LFB_RAY_MISSED = 1,      /* no intersection with a surface */
+  LFB_RAY_VIGNETTED = 2,   /* outside a surface's clear semi-aperture */
+  LFB_RAY_TIR = 4,         /* total internal reflection at a refracting surface */
+  LFB_RAY_STOPPED = 8,     /* aperture mask was 0 (or outside the mask) at a stop crossing */
+  LFB_RAY_OFF_SENSOR = 16  /* landed outside the W x H sensor */
+};
+
+/* The lens prescription: replaces the file-scope globals of pathtracer.cpp:539-556
+ * (Ts, red/green/blue_refr, curvatures) and the constants 14.5 (:737), 11.6/-11.5
+ * (:621-625).  ior[l][k] is the index AFTER surface k at wavelength l (the medium
+ * before surface 0 is air, 1.0, as in create_Rs_for_color :560-566). */
+typedef struct lfb_lens {
+  int32_t n_surfaces;                       /* <= LFB_MAX_SURFACES */
+  int32_t stop_index;                       /* surface index of the aperture stop */
+  int32_t n_lambda;                         /* <= LFB_MAX_LAMBDA */
+  int32_t reserved0;
+  float curvature[LFB_MAX_SURFACES];        /* c = 1/R, 0 for planes */
+  float thickness[LFB_MAX_SURFACES];        /* axial distance after surface k (last: to the sensor) */
+  float semi_aperture[LFB_MAX_SURFACES];    /* clear radius of each element (EXACT_GRID vignetting) */
+  float coating_lambda0_nm[LFB_MAX_SURFACES]; /* quarter-wave design wavelength; 0 = uncoated */
+  float ior[LFB_MAX_LAMBDA][LFB_MAX_SURFACES];
+  float lambda_nm[LFB_MAX_LAMBDA];
+  float rgb_weight[LFB_MAX_LAMBDA][3];      /* how wavelength l adds into R,G,B */
+  double entrance_half_height;              /* 14.5: half-side of the entrance ray grid */
+  double stop_half_height;                  /* 11.6: the aperture mask spans [-h,h]^2 at the stop */
+  double stop_half_height_neg;              /* 11.5: the reference's asymmetric re-aim height for r<0 */
+} lfb_lens;
+
+/* One light.  Replaces PathTracer::axis_ray / angle_to_sun / flare_radiance
+ * (pathtracer.h:131-135), which find_sun_pos (pathtracer.cpp:32-64) fills for the
+ * single sun of the reference. */
+typedef struct lfb_light {
+  double ns_x, ns_y;  /* normalised screen position in [0,1]^2 (axis_ray) */
+  float theta;        /* ray angle in the meridional plane, radians (angle_to_sun) */
+  float radiance[3];
+} lfb_light;
+
+typedef struct lfb_params {
+  int32_t mode;            /* enum lfb_mode */
+  int32_t pair_set;        /* enum lfb_pairset */
+  int32_t include_direct;  /* grid modes: also trace the unreflected path */
+  int32_t grid_n;          /* grid modes: N rays per axis per ghost */
+  int32_t width, height;   /* sensor size in pixels (sampleBuffer.w/h, pathtracer.cpp:720) */
+  int32_t precision;       /* enum lfb_precision (grid modes) */
+  int32_t splat;           /* enum lfb_splat (grid modes) */
+  int32_t fixed_point_bits; /* sensor accumulators are u64 fixed point with this many fractional bits; 0 -> 40 */
+  int32_t physical_backward; /* PARAXIAL_GRID only: 0 = the reference's R^-1 on backward legs
+                                (pathtracer.cpp:607-608), 1 = physically consistent backward refraction */
+  int32_t shard_index, shard_count; /* this engine renders jobs q with q % shard_count == shard_index
+                                       of the LPT-ordered (light x pair x lambda) job list; 0,0 -> all */
+  float px_per_unit;       /* sensor pixels per lens unit; 0 -> 0.4 (pathtracer.cpp:457-463) */
+  float reserved[3];
+} lfb_params;
+
+/* Per-ray record of lfb_dump_rays (parity instrument). */
+typedef struct lfb_ray_hit {
+  double x_s, y_s;    /* sensor-plane position, lens units, local (meridional, sagittal) frame */
+  double x_ap, y_ap;  /* position at the LAST stop crossing */
+  double px, py;      /* continuous pixel position on the sensor */
+  double weight;      /* scalar weight before the light's radiance and rgb_weight */
+  uint32_t flags;     /* enum lfb_ray_flags */
+  uint32_t pad;
+} lfb_ray_hit;
+
+/* Per-ghost record of lfb_ref_ghosts (REF_QUADS introspection). */
+typedef struct lfb_ref_ghost {
+  int32_t i, j, colour, pad;
+  double r1, r2;          /* sensor heights of the +/-entrance marginal rays (trace_ray_auto_*) */
+  float verts[4][2];      /* ul, ll, ur, lr screen-space vertices of draw_ghost */
+  float scale, shift;
+} lfb_ref_ghost;
+
+/* ---- lifecycle -------------------------------------------------------- */
+int lfb_abi_version(void);
+/* One engine per CUDA device (one process per GPU under torchrun; a C++ host may
+ * create several).  device_id < 0 -> current device. */
+int lfb_create(lfb_engine** out, int device_id);
+void lfb_destroy(lfb_engine* e);
+const char* lfb_last_error(void);
+
+/* ---- inputs ----------------------------------------------------------- */
+/* Fills `lens` with the reference's built-in prescription (pathtracer.cpp:539-556)
+ * for n_lambda = 3 (the reference's R,G,B index tables) or, for other n_lambda,
+ * wavelengths uniform on [400,700] nm with a 3-term Cauchy fit through the R,G,B
+ * anchors at 650/550/450 nm.  coating_lambda0_nm > 0 coats every glass surface. */
+int lfb_builtin_lens(lfb_lens* lens, int n_lambda, float coating_lambda0_nm);
+int lfb_set_lens(lfb_engine* e, const lfb_lens* lens);
+/* Replaces Camera::ghost_aperture_texture (camera.h:175, filled by
+ * CameraApertureTexture::init, camera.h:26-83): row-major y*w+x, values in [0,1]. */
+int lfb_set_aperture(lfb_engine* e, const float* texels, int w, int h);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* Replaces PathTracer::generate_ghost_buffer (pathtracer.cpp:714-762).  Renders all
+ * ghosts of all lights into `out` (host memory; pageable or pinned), pixel (x,y) at
+ * byte offset (x + y*width)*out_stride_bytes holding 3 floats or 3 doubles.
+ * additive = 0 overwrites (the reference clears first, :719-720), 1 adds. */
+int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_lights,
+                      const lfb_params* params, void* out, size_t out_stride_bytes,
+                      int out_elem, int additive);
+
+/* Parity instrument: trace the N x N grid of one ghost (i, j, lambda) of one light
+ * and return every ray's record (grid modes only).  i = j = -1 selects the direct path. */
+int lfb_dump_rays(lfb_engine* e, const lfb_light* light, const lfb_params* params,
+                  int i, int j, int lambda, lfb_ray_hit* out, size_t cap);
+
+/* REF_QUADS introspection: the ghosts the device set up for the last REF_QUADS frame
+ * (trace_ray_auto_* results and draw_ghost vertices). Returns the count or <0. */
+int lfb_ref_ghosts(lfb_engine* e, lfb_ref_ghost* out, int cap);
+
+/* ---- device-resident API (multi-GPU sharding, benchmarking) ------------- */
+/* Sensor accumulators: width*height*3 u64 fixed-point sums, owned by the caller. */
+size_t lfb_accum_bytes(int width, int height);
+/* The engine's CUDA stream (cudaStream_t) so callers can order work / record events. */
+void* lfb_stream(lfb_engine* e);
+/* Zero the accumulators, trace + splat this shard's ghosts (grid modes), all on the
+ * engine stream; returns without synchronising.  accum_dev is a device pointer. */
+int lfb_render_ghosts_device(lfb_engine* e, const lfb_light* lights, int n_lights,
+                             const lfb_params* params, void* accum_dev, int clear_first);
+/* accum (u64 fixed point) -> packed F32x3 / F64x3 pixels in device memory. */
+int lfb_finalize_device(lfb_engine* e, const void* accum_dev, const lfb_params* params,
+                        void* out_dev, size_t out_stride_bytes, int out_elem);
+int lfb_sync(lfb_engine* e);
+
+/* ---- accounting --------------------------------------------------------- */
+/* Ray-surface interactions (I(i,j) = 2(j-i) + n_surfaces + 1 per ray,
+ * n_surfaces + 1 for the direct path) and rays this shard traces for one frame. */
+int lfb_count_work(const lfb_lens* lens, const lfb_params* params, int n_lights,
+                   double* rays, double* interactions, int* jobs);
+/* The (light, i, j, lambda) jobs this shard renders, in launch order (host-only; no
+ * device needed).  out holds cap rows of 4 ints; returns the job count (may exceed cap). */
+int lfb_list_jobs(const lfb_lens* lens, const lfb_params* params, int n_lights,
+                  int32_t* out, int cap);
+/* Kernels launched by this engine since creation, and the device time (ms, CUDA
+ * events on the engine stream) of the trace/splat and raster kernels of the last frame. */
+int lfb_stats(lfb_engine* e, uint64_t* kernel_launches, float* last_trace_ms, float* last_frame_ms);
+
+/* ---- pinned host memory helpers ---------------------------------------- */
+void* lfb_host_alloc(size_t bytes);  /* cudaHostAlloc; NULL on failure */
+void lfb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFB200_H */

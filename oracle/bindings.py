@@ -1,0 +1,263 @@
+"""ctypes bindings for the two CPU oracles -- TEST INFRASTRUCTURE ONLY.
+
+  RefOracle   oracle/_ref/libref_oracle.so : the UNMODIFIED reference sources compiled by
+              oracle/Makefile (present here and, as a built file, on the GPU box).
+  PortOracle  oracle/_build/liblf_oracle.so: the C restatement oracle/lf_oracle.c.
+
+Only tests/, tools/make_golden.py, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs import this module; nothing under lens_flare_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libref_oracle.so")
+PORT_SO = os.path.join(HERE, "_build", "liblf_oracle.so")
+
+MAX_SURFACES = 16
+MAX_LAMBDA = 64
+
+
+class Lens(C.Structure):
+    _fields_ = [
+        ("n_surfaces", C.c_int32), ("stop_index", C.c_int32), ("n_lambda", C.c_int32), ("reserved0", C.c_int32),
+        ("curvature", C.c_float * MAX_SURFACES), ("thickness", C.c_float * MAX_SURFACES),
+        ("semi_aperture", C.c_float * MAX_SURFACES), ("coating_lambda0_nm", C.c_float * MAX_SURFACES),
+        ("ior", (C.c_float * MAX_SURFACES) * MAX_LAMBDA), ("lambda_nm", C.c_float * MAX_LAMBDA),
+        ("rgb_weight", (C.c_float * 3) * MAX_LAMBDA),
+        ("entrance_half_height", C.c_double), ("stop_half_height", C.c_double),
+        ("stop_half_height_neg", C.c_double),
+    ]
+
+
+class Light(C.Structure):
+    _fields_ = [("ns_x", C.c_double), ("ns_y", C.c_double), ("theta", C.c_float), ("radiance", C.c_float * 3)]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("pair_set", C.c_int32), ("include_direct", C.c_int32), ("grid_n", C.c_int32),
+        ("width", C.c_int32), ("height", C.c_int32), ("precision", C.c_int32), ("splat", C.c_int32),
+        ("fixed_point_bits", C.c_int32), ("physical_backward", C.c_int32),
+        ("shard_index", C.c_int32), ("shard_count", C.c_int32),
+        ("px_per_unit", C.c_float), ("reserved", C.c_float * 3),
+    ]
+
+
+RAY_HIT_DTYPE = np.dtype([("x_s", "f8"), ("y_s", "f8"), ("x_ap", "f8"), ("y_ap", "f8"), ("px", "f8"),
+                          ("py", "f8"), ("weight", "f8"), ("flags", "u4"), ("pad", "u4")])
+REF_GHOST_DTYPE = np.dtype([("i", "i4"), ("j", "i4"), ("colour", "i4"), ("pad", "i4"), ("r1", "f8"),
+                            ("r2", "f8"), ("verts", "f4", (4, 2)), ("scale", "f4"), ("shift", "f4")])
+
+MODE_REF_QUADS, MODE_PARAXIAL_GRID, MODE_EXACT_GRID = 0, 1, 2
+PAIRS_REF, PAIRS_ALL = 0, 1
+F32x3, F64x3 = 0, 1
+FP32, FP64 = 0, 1
+SPLAT_NEAREST, SPLAT_BILINEAR = 0, 1
+RAY_MISSED, RAY_VIGNETTED, RAY_TIR, RAY_STOPPED, RAY_OFF_SENSOR = 1, 2, 4, 8, 16
+
+
+def make_light(ns_x, ns_y, theta=None, radiance=(1.0, 1.0, 1.0)):
+    """theta=None -> the reference's angle_to_sun = atan(ns_y/ns_x) (pathtracer.cpp:50)."""
+    lt = Light()
+    lt.ns_x, lt.ns_y = ns_x, ns_y
+    lt.theta = float(np.float32(np.arctan(ns_y / ns_x))) if theta is None else theta
+    lt.radiance[:] = radiance
+    return lt
+
+
+def make_params(mode, width, height, grid_n=0, pair_set=PAIRS_REF, precision=FP32, splat=SPLAT_BILINEAR,
+                include_direct=0, physical_backward=0, bits=0, px_per_unit=0.0, shard=(0, 0)):
+    p = Params()
+    p.mode, p.pair_set, p.include_direct, p.grid_n = mode, pair_set, include_direct, grid_n
+    p.width, p.height, p.precision, p.splat = width, height, precision, splat
+    p.fixed_point_bits, p.physical_backward = bits, physical_backward
+    p.shard_index, p.shard_count = shard
+    p.px_per_unit = px_per_unit
+    return p
+
+
+def lights_array(lights):
+    arr = (Light * len(lights))()
+    for k, lt in enumerate(lights):
+        arr[k] = lt
+    return arr
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def build(which=("port", "ref")):
+    """Compile the oracles (ref only when /root/reference is present)."""
+    ref_root = os.environ.get("LFB_REFERENCE", "/root/reference")
+    for w in which:
+        if w == "ref" and not os.path.isdir(ref_root):
+            continue
+        subprocess.run(["make", "-s", "-C", HERE, w, f"REF={ref_root}"], check=True)
+
+
+class RefOracle:
+    """The compiled reference (oracle/_ref)."""
+
+    def __init__(self, path=REF_SO):
+        self.lib = L = C.CDLL(path)
+        L.ref_trace.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.ref_generate_ghost_buffer.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_double, C.c_double, C.c_float, C.POINTER(C.c_double)]
+        L.ref_time_ghost_buffer.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                            C.c_double, C.c_float, C.c_int, C.POINTER(C.c_double)]
+        L.ref_time_ghost_buffer.restype = C.c_double
+        L.ref_time_trace_grid.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double)]
+        L.ref_time_trace_grid.restype = C.c_double
+        L.ref_load_aperture.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ref_find_sun_pos.argtypes = [C.POINTER(C.c_double)] * 2 + [C.c_double, C.c_double] + \
+            [C.POINTER(C.c_double)] * 4 + [C.POINTER(C.c_float)]
+        L.ref_starburst.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                    C.POINTER(C.c_double), C.c_double, C.c_double, C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double)]
+
+    def sizeof_vector3d(self):
+        return self.lib.ref_sizeof_vector3d()
+
+    def prescription(self):
+        t, l, rr, rg, rb = (np.zeros((9, 4)) for _ in range(5))
+        curv = np.zeros(10, np.float32)
+        n = np.zeros((3, 9), np.float32)
+        self.lib.ref_prescription(_dp(t), _dp(l), _dp(rr), _dp(rg), _dp(rb), _fp(curv), _fp(n[0]), _fp(n[1]), _fp(n[2]))
+        return dict(T=t, L=l, R=[rr, rg, rb], curvature=curv, ior=n)
+
+    def trace(self, which, r, theta, i, j, colour):
+        out = (C.c_double * 2)()
+        self.lib.ref_trace(which, r, theta, i, j, colour, out)
+        return out[0], out[1]
+
+    def generate_ghost_buffer(self, tex, W, H, ns_x, ns_y, angle):
+        tex = np.ascontiguousarray(tex, np.float32)
+        out = np.zeros((H, W, 3))
+        rc = self.lib.ref_generate_ghost_buffer(_fp(tex), tex.shape[1], tex.shape[0], W, H, ns_x, ns_y, angle, _dp(out))
+        assert rc == 0
+        return out
+
+    def time_ghost_buffer(self, tex, W, H, ns_x, ns_y, angle, reps):
+        tex = np.ascontiguousarray(tex, np.float32)
+        cs = C.c_double()
+        s = self.lib.ref_time_ghost_buffer(_fp(tex), tex.shape[1], tex.shape[0], W, H, ns_x, ns_y, angle, reps, C.byref(cs))
+        return s, cs.value
+
+    def time_trace_grid(self, N, theta, ncol, pairset, nthreads):
+        cs, rays = C.c_double(), C.c_double()
+        s = self.lib.ref_time_trace_grid(N, theta, ncol, pairset, nthreads, C.byref(cs), C.byref(rays))
+        return s, rays.value, cs.value
+
+    def load_aperture(self, path):
+        out = np.zeros(4096 * 4096 // 16, np.float32)
+        w, h, tot = C.c_int(), C.c_int(), C.c_double()
+        bbox = (C.c_int * 4)()
+        rc = self.lib.ref_load_aperture(path.encode(), _fp(out), out.size, C.byref(w), C.byref(h), C.byref(tot), bbox)
+        assert rc == 0
+        return out[: w.value * h.value].reshape(h.value, w.value).copy(), tot.value, tuple(bbox)
+
+    def find_sun_pos(self, c2w, cam_pos, hfov, vfov, light_pos, light_dir, radiance=(1, 1, 1)):
+        a = [np.ascontiguousarray(v, np.float64) for v in (c2w, cam_pos, light_pos, light_dir, radiance)]
+        ns = np.zeros(2)
+        ang = C.c_float()
+        n = self.lib.ref_find_sun_pos(_dp(a[0]), _dp(a[1]), hfov, vfov, _dp(a[2]), _dp(a[3]), _dp(a[4]), _dp(ns), C.byref(ang))
+        return n, ns[0], ns[1], ang.value
+
+    def starburst(self, tex, W, H, fo, radiance, flare_radius, flare_intensity, xs, ys):
+        tex = np.ascontiguousarray(tex, np.float32)
+        xs = np.ascontiguousarray(xs, np.int32)
+        ys = np.ascontiguousarray(ys, np.int32)
+        rad = np.ascontiguousarray(radiance, np.float64)
+        out = np.zeros((xs.size, 6))
+        self.lib.ref_starburst(_fp(tex), tex.shape[1], tex.shape[0], W, H, fo[0], fo[1], _dp(rad), flare_radius,
+                               flare_intensity, xs.ctypes.data_as(C.POINTER(C.c_int)),
+                               ys.ctypes.data_as(C.POINTER(C.c_int)), xs.size, _dp(out))
+        return out
+
+
+class PortOracle:
+    """The C restatement (oracle/lf_oracle.c)."""
+
+    def __init__(self, path=PORT_SO):
+        self.lib = L = C.CDLL(path)
+        LP, LiP, PP = C.POINTER(Lens), C.POINTER(Light), C.POINTER(Params)
+        L.lfo_builtin_lens.argtypes = [LP, C.c_int, C.c_float]
+        L.lfo_prescription.argtypes = [LP, C.c_int] + [C.POINTER(C.c_double)] * 3
+        L.lfo_trace_ray_auto.argtypes = [LP, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.lfo_generate_ghost_buffer.argtypes = [LP, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                                C.c_double, C.c_float, C.POINTER(C.c_double), C.c_void_p, C.c_int]
+        L.lfo_paraxial_system.argtypes = [LP, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.lfo_trace_grid.argtypes = [LP, C.POINTER(C.c_float), C.c_int, C.c_int, LiP, PP, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.lfo_render.argtypes = [LP, C.POINTER(C.c_float), C.c_int, C.c_int, LiP, C.c_int, PP, C.POINTER(C.c_double), C.c_void_p]
+        L.lfo_reflectance.argtypes = [C.c_double] * 5
+        L.lfo_reflectance.restype = C.c_double
+        L.lfo_time_render.argtypes = [LP, C.POINTER(C.c_float), C.c_int, C.c_int, LiP, C.c_int, PP, C.c_int, C.POINTER(C.c_double)]
+        L.lfo_time_render.restype = C.c_double
+
+    def builtin_lens(self, n_lambda=3, coating_lambda0_nm=0.0):
+        lens = Lens()
+        assert self.lib.lfo_builtin_lens(C.byref(lens), n_lambda, coating_lambda0_nm) == 0
+        return lens
+
+    def prescription(self, lens, lam):
+        t, l, r = (np.zeros((lens.n_surfaces, 4)) for _ in range(3))
+        self.lib.lfo_prescription(C.byref(lens), lam, _dp(t), _dp(l), _dp(r))
+        return t, l, r
+
+    def trace_ray_auto(self, lens, lam, which, r, theta, i, j):
+        out = (C.c_double * 2)()
+        self.lib.lfo_trace_ray_auto(C.byref(lens), lam, which, r, theta, i, j, out)
+        return out[0], out[1]
+
+    def generate_ghost_buffer(self, lens, tex, W, H, ns_x, ns_y, angle, want_ghosts=False):
+        tex = np.ascontiguousarray(tex, np.float32)
+        out = np.zeros((H, W, 3))
+        cap = 64 * lens.n_lambda
+        ghosts = np.zeros(cap, REF_GHOST_DTYPE)
+        n = self.lib.lfo_generate_ghost_buffer(C.byref(lens), _fp(tex), tex.shape[1], tex.shape[0], W, H, ns_x, ns_y,
+                                               angle, _dp(out), ghosts.ctypes.data, cap)
+        return (out, ghosts[:n]) if want_ghosts else out
+
+    def paraxial_system(self, lens, lam, i, j, physical_backward=0):
+        cross = np.zeros((3, 4))
+        full = np.zeros(4)
+        nc = self.lib.lfo_paraxial_system(C.byref(lens), lam, i, j, physical_backward, _dp(cross), _dp(full))
+        return cross[:nc], full
+
+    def trace_grid(self, lens, tex, light, params, i, j, lam):
+        tex = np.ascontiguousarray(tex, np.float32)
+        out = np.zeros(params.grid_n * params.grid_n, RAY_HIT_DTYPE)
+        rc = self.lib.lfo_trace_grid(C.byref(lens), _fp(tex), tex.shape[1], tex.shape[0], C.byref(light), C.byref(params),
+                                     i, j, lam, out.ctypes.data)
+        assert rc == 0
+        return out
+
+    def render(self, lens, tex, lights, params, want_accum=False):
+        tex = np.ascontiguousarray(tex, np.float32)
+        out = np.zeros((params.height, params.width, 3))
+        acc = np.zeros((params.height, params.width, 3), np.int64) if want_accum else None
+        rc = self.lib.lfo_render(C.byref(lens), _fp(tex), tex.shape[1], tex.shape[0], lights_array(lights), len(lights),
+                                 C.byref(params), _dp(out), acc.ctypes.data if want_accum else None)
+        assert rc == 0
+        return (out, acc) if want_accum else out
+
+    def reflectance(self, n0, n2, cos0, lambda0, lam):
+        return self.lib.lfo_reflectance(n0, n2, cos0, lambda0, lam)
+
+    def time_render(self, lens, tex, lights, params, nthreads):
+        tex = np.ascontiguousarray(tex, np.float32)
+        cs = C.c_double()
+        s = self.lib.lfo_time_render(C.byref(lens), _fp(tex), tex.shape[1], tex.shape[0], lights_array(lights),
+                                     len(lights), C.byref(params), nthreads, C.byref(cs))
+        return s, cs.value

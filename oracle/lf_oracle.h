@@ -1,0 +1,73 @@
+/* oracle/lf_oracle.h -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * CPU restatement (C99, double precision) of the lens-flare ghost path, used as
+ * the checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.
+ * Parity status:
+ *   - lfo_prescription / lfo_trace_ray_auto / lfo_generate_ghost_buffer restate
+ *     the reference (src/pathtracer/pathtracer.cpp) and are PINNED bit-for-bit
+ *     against the compiled reference (oracle/_ref, built by oracle/Makefile) and
+ *     against tests/golden/ (vectors produced by tools/make_golden.py from it).
+ *   - lfo_paraxial_system (PARAXIAL_GRID) is pinned against the reference's
+ *     trace_ray_auto_before/after per ray (<= 1e-9 lens units).
+ *   - the EXACT_GRID physics (sphere/plane intersection, vector Snell, Fresnel,
+ *     quarter-wave coating) does not exist in the reference (its BSDF::refract /
+ *     reflect / Fresnel are empty stubs, advanced_bsdf.cpp:52-169): PARITY
+ *     UNPINNED by the reference; it is pinned by analytic invariants instead
+ *     (tests/test_oracle_physics.py).
+ * Struct definitions are shared with the product header include/lfb200.h.
+ */
+#ifndef LF_ORACLE_H
+#define LF_ORACLE_H
+#include "../include/lfb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* pathtracer.cpp:539-556 as data (+ Cauchy n(lambda) when n_lambda != 3). */
+int lfo_builtin_lens(lfb_lens* lens, int n_lambda, float coating_lambda0_nm);
+
+/* pathtracer.cpp:511-586: T_k, L_k, R_k(lambda) as (m00,m01,m10,m11) per surface. */
+void lfo_prescription(const lfb_lens* lens, int lambda, double* t, double* l, double* r);
+
+/* pathtracer.cpp:588-641 (which=0, trace_ray_auto_before) / :643-689 (which=1, _after). */
+void lfo_trace_ray_auto(const lfb_lens* lens, int lambda, int which, float r, float theta,
+                        int i, int j, double out[2]);
+
+/* pathtracer.cpp:714-762 incl. draw_ghost :433-508, shift_vertex :412-430,
+ * rasterize_textured_triangle :346-410, fill_textured_pixel :305-343.
+ * out = W*H*3 doubles.  ghosts (optional, cap rows) receives the per-ghost records. */
+int lfo_generate_ghost_buffer(const lfb_lens* lens, const float* tex, int tw, int th,
+                              int W, int H, double axis_x, double axis_y, float angle_to_sun,
+                              double* out, lfb_ref_ghost* ghosts, int cap);
+
+/* Per-ghost ABCD system for PARAXIAL_GRID: n_cross stop crossings (entrance -> stop
+ * plane, 2x2 each as m00,m01,m10,m11) and the entrance -> sensor matrix. */
+int lfo_paraxial_system(const lfb_lens* lens, int lambda, int i, int j, int physical_backward,
+                        double cross[3][4], double full[4]);
+
+/* Trace the N x N grid of one ghost (i=j=-1: direct path); out has N*N records, row-major b*N+a. */
+int lfo_trace_grid(const lfb_lens* lens, const float* tex, int tw, int th,
+                   const lfb_light* light, const lfb_params* params, int i, int j, int lambda,
+                   lfb_ray_hit* out);
+
+/* Full frame (grid modes or REF_QUADS): out = W*H*3 doubles; accum (optional) = W*H*3 int64
+ * fixed-point sums exactly as the engine keeps them. */
+int lfo_render(const lfb_lens* lens, const float* tex, int tw, int th,
+               const lfb_light* lights, int n_lights, const lfb_params* params,
+               double* out, int64_t* accum);
+
+/* Single-surface reflectance used by EXACT_GRID (Airy single-layer film, or bare
+ * Fresnel when lambda0 = 0).  cos0 = cosine of the incidence angle in medium n0. */
+double lfo_reflectance(double n0, double n2, double cos0, double coating_lambda0_nm,
+                       double lambda_nm);
+
+/* Timed render on nthreads pthreads (jobs split round-robin); returns seconds. */
+double lfo_time_render(const lfb_lens* lens, const float* tex, int tw, int th,
+                       const lfb_light* lights, int n_lights, const lfb_params* params,
+                       int nthreads, double* checksum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
