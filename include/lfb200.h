@@ -150,8 +150,8 @@ const char* lfb_last_error(void);
 /* ---- inputs ----------------------------------------------------------- */
 /* Fills `lens` with the reference's built-in prescription (pathtracer.cpp:539-556)
  * for n_lambda = 3 (the reference's R,G,B index tables) or, for other n_lambda,
- * wavelengths uniform on [400,700] nm with a 3-term Cauchy fit through the R,G,B
- * anchors at 650/550/450 nm.  coating_lambda0_nm > 0 coats every glass surface. */
+ * wavelengths uniform on [400,700] nm with a piecewise two-term Cauchy n(lambda)
+ * (linear in 1/lambda^2) through the R,G,B anchors at 650/550/450 nm.  coating_lambda0_nm > 0 coats every glass surface. */
 int lfb_builtin_lens(lfb_lens* lens, int n_lambda, float coating_lambda0_nm);
 int lfb_set_lens(lfb_engine* e, const lfb_lens* lens);
 /* Replaces Camera::ghost_aperture_texture (camera.h:175, filled by
@@ -202,6 +202,11 @@ int lfb_list_jobs(const lfb_lens* lens, const lfb_params* params, int n_lights,
 /* Kernels launched by this engine since creation, and the device time (ms, CUDA
  * events on the engine stream) of the trace/splat and raster kernels of the last frame. */
 int lfb_stats(lfb_engine* e, uint64_t* kernel_launches, float* last_trace_ms, float* last_frame_ms);
+
+/* Live roofline denominators for the scalar pipes the trace is bound by: FP32 FLOP/s (FMA = 2)
+ * and MUFU op/s of this GPU measured by two register-only micro-kernels, plus the SM clock
+ * (Hz) seen while they ran. */
+int lfb_probe_peaks(lfb_engine* e, double* fp32_flops, double* mufu_ops, double* sm_clock_hz);
 
 /* ---- pinned host memory helpers ---------------------------------------- */
 void* lfb_host_alloc(size_t bytes);  /* cudaHostAlloc; NULL on failure */

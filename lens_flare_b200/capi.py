@@ -1,0 +1,285 @@
+"""ctypes binding of the C ABI declared in include/lfb200.h (liblfb200.so).
+
+This is the only module that talks to the native library; everything above it
+(`pathtracer.py`, `sharding.py`, bench.py, tests) goes through these calls.  The
+library is built in-tree by `lens_flare_b200/csrc/Makefile` (see `build()`); it is
+never looked up in site-packages, and loading fails loudly when it is missing --
+there is no Python or CPU fallback for any compute entry point.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblfb200.so")
+CSRC = os.path.join(HERE, "csrc")
+
+MAX_SURFACES = 16
+MAX_LAMBDA = 64
+ABI_VERSION = 1
+
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
+MODE_REF_QUADS, MODE_PARAXIAL_GRID, MODE_EXACT_GRID = 0, 1, 2
+PAIRS_REF, PAIRS_ALL = 0, 1
+F32x3, F64x3 = 0, 1
+FP32, FP64 = 0, 1
+SPLAT_NEAREST, SPLAT_BILINEAR = 0, 1
+RAY_MISSED, RAY_VIGNETTED, RAY_TIR, RAY_STOPPED, RAY_OFF_SENSOR = 1, 2, 4, 8, 16
+
+# every symbol include/lfb200.h declares (tests check the library exports each one)
+SYMBOLS = (
+    "lfb_abi_version", "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
+    "lfb_set_aperture", "lfb_render_ghosts", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
+    "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
+    "lfb_host_alloc", "lfb_host_free", "lfb_probe_peaks",
+)
+
+
+class Lens(C.Structure):
+    """lfb_lens"""
+    _fields_ = [
+        ("n_surfaces", C.c_int32), ("stop_index", C.c_int32), ("n_lambda", C.c_int32), ("reserved0", C.c_int32),
+        ("curvature", C.c_float * MAX_SURFACES), ("thickness", C.c_float * MAX_SURFACES),
+        ("semi_aperture", C.c_float * MAX_SURFACES), ("coating_lambda0_nm", C.c_float * MAX_SURFACES),
+        ("ior", (C.c_float * MAX_SURFACES) * MAX_LAMBDA), ("lambda_nm", C.c_float * MAX_LAMBDA),
+        ("rgb_weight", (C.c_float * 3) * MAX_LAMBDA),
+        ("entrance_half_height", C.c_double), ("stop_half_height", C.c_double),
+        ("stop_half_height_neg", C.c_double),
+    ]
+
+
+class Light(C.Structure):
+    """lfb_light"""
+    _fields_ = [("ns_x", C.c_double), ("ns_y", C.c_double), ("theta", C.c_float), ("radiance", C.c_float * 3)]
+
+
+class Params(C.Structure):
+    """lfb_params"""
+    _fields_ = [
+        ("mode", C.c_int32), ("pair_set", C.c_int32), ("include_direct", C.c_int32), ("grid_n", C.c_int32),
+        ("width", C.c_int32), ("height", C.c_int32), ("precision", C.c_int32), ("splat", C.c_int32),
+        ("fixed_point_bits", C.c_int32), ("physical_backward", C.c_int32),
+        ("shard_index", C.c_int32), ("shard_count", C.c_int32),
+        ("px_per_unit", C.c_float), ("reserved", C.c_float * 3),
+    ]
+
+
+RAY_HIT_DTYPE = np.dtype([("x_s", "f8"), ("y_s", "f8"), ("x_ap", "f8"), ("y_ap", "f8"), ("px", "f8"),
+                          ("py", "f8"), ("weight", "f8"), ("flags", "u4"), ("pad", "u4")])
+REF_GHOST_DTYPE = np.dtype([("i", "i4"), ("j", "i4"), ("colour", "i4"), ("pad", "i4"), ("r1", "f8"),
+                            ("r2", "f8"), ("verts", "f4", (4, 2)), ("scale", "f4"), ("shift", "f4")])
+
+
+class LfbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"liblfb200 error {code}: {message}")
+        self.code = code
+
+
+def make_light(ns_x, ns_y, theta=None, radiance=(1.0, 1.0, 1.0)):
+    """theta=None -> the reference's angle_to_sun = atan(ns_y/ns_x) (pathtracer.cpp:50)."""
+    lt = Light()
+    lt.ns_x, lt.ns_y = ns_x, ns_y
+    lt.theta = float(np.float32(np.arctan(ns_y / ns_x))) if theta is None else theta
+    lt.radiance[:] = radiance
+    return lt
+
+
+def make_params(mode, width, height, grid_n=0, pair_set=PAIRS_REF, precision=FP32, splat=SPLAT_BILINEAR,
+                include_direct=0, physical_backward=0, bits=0, px_per_unit=0.0, shard=(0, 0)):
+    p = Params()
+    p.mode, p.pair_set, p.include_direct, p.grid_n = mode, pair_set, include_direct, grid_n
+    p.width, p.height, p.precision, p.splat = width, height, precision, splat
+    p.fixed_point_bits, p.physical_backward = bits, physical_backward
+    p.shard_index, p.shard_count = shard
+    p.px_per_unit = px_per_unit
+    return p
+
+
+def copy_params(p, **changes):
+    q = Params.from_buffer_copy(bytes(p))
+    for k, v in changes.items():
+        if k == "shard":
+            q.shard_index, q.shard_count = v
+        else:
+            setattr(q, k, v)
+    return q
+
+
+def lights_array(lights):
+    arr = (Light * max(len(lights), 1))()
+    for k, lt in enumerate(lights):
+        arr[k] = lt
+    return arr
+
+
+def build(verbose=False):
+    """Compile liblfb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j4"] + ([] if verbose else ["-s"])
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load liblfb200.so (once).  Raises if the native library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` or "
+                          f"`make -C {CSRC}`. The engine has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    LP, LiP, PP, vp = C.POINTER(Lens), C.POINTER(Light), C.POINTER(Params), C.c_void_p
+    L.lfb_abi_version.restype = C.c_int
+    L.lfb_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.lfb_destroy.argtypes = [vp]
+    L.lfb_destroy.restype = None
+    L.lfb_last_error.restype = C.c_char_p
+    L.lfb_builtin_lens.argtypes = [LP, C.c_int, C.c_float]
+    L.lfb_set_lens.argtypes = [vp, LP]
+    L.lfb_set_aperture.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.c_int]
+    L.lfb_render_ghosts.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.c_int]
+    L.lfb_dump_rays.argtypes = [vp, LiP, PP, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]
+    L.lfb_ref_ghosts.argtypes = [vp, vp, C.c_int]
+    L.lfb_accum_bytes.argtypes = [C.c_int, C.c_int]
+    L.lfb_accum_bytes.restype = C.c_size_t
+    L.lfb_stream.argtypes = [vp]
+    L.lfb_stream.restype = vp
+    L.lfb_render_ghosts_device.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_int]
+    L.lfb_finalize_device.argtypes = [vp, vp, PP, vp, C.c_size_t, C.c_int]
+    L.lfb_sync.argtypes = [vp]
+    L.lfb_count_work.argtypes = [LP, PP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.lfb_list_jobs.argtypes = [LP, PP, C.c_int, C.POINTER(C.c_int32), C.c_int]
+    L.lfb_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.lfb_host_alloc.argtypes = [C.c_size_t]
+    L.lfb_host_alloc.restype = vp
+    L.lfb_host_free.argtypes = [vp]
+    L.lfb_host_free.restype = None
+    L.lfb_probe_peaks.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    if L.lfb_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {L.lfb_abi_version()} != {ABI_VERSION}; rebuild")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        raise LfbError(rc, lib().lfb_last_error().decode())
+    return rc
+
+
+def builtin_lens(n_lambda=3, coating_lambda0_nm=0.0):
+    """The reference's hard-coded prescription (pathtracer.cpp:539-556) as an lfb_lens."""
+    lens = Lens()
+    check(lib().lfb_builtin_lens(C.byref(lens), n_lambda, coating_lambda0_nm))
+    return lens
+
+
+def count_work(lens, params, n_lights):
+    rays, inter, jobs = C.c_double(), C.c_double(), C.c_int()
+    check(lib().lfb_count_work(C.byref(lens), C.byref(params), n_lights, C.byref(rays), C.byref(inter), C.byref(jobs)))
+    return rays.value, inter.value, jobs.value
+
+
+def list_jobs(lens, params, n_lights):
+    n = check(lib().lfb_list_jobs(C.byref(lens), C.byref(params), n_lights, None, 0))
+    out = np.zeros((max(n, 1), 4), np.int32)
+    check(lib().lfb_list_jobs(C.byref(lens), C.byref(params), n_lights, out.ctypes.data_as(C.POINTER(C.c_int32)), n))
+    return out[:n]
+
+
+class PinnedArray:
+    """A numpy view of cudaHostAlloc'ed memory (lfb_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib().lfb_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise LfbError(ERR_NOMEM, "lfb_host_alloc failed")
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().lfb_host_free(self.ptr)
+            self.ptr = None
+
+
+class Engine:
+    """Owner of one lfb_engine (one CUDA device)."""
+
+    def __init__(self, device_id=-1):
+        self._h = C.c_void_p()
+        check(lib().lfb_create(C.byref(self._h), device_id))
+        self.lens = None
+
+    def close(self):
+        if self._h:
+            lib().lfb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_lens(self, lens):
+        check(lib().lfb_set_lens(self._h, C.byref(lens)))
+        self.lens = lens
+
+    def set_aperture(self, texels):
+        tex = np.ascontiguousarray(texels, np.float32)
+        check(lib().lfb_set_aperture(self._h, tex.ctypes.data_as(C.POINTER(C.c_float)), tex.shape[1], tex.shape[0]))
+
+    def render_ghosts(self, lights, params, out=None, elem=F64x3, stride=None, additive=False):
+        """-> (H, W, 3) array (float64 for F64x3, float32 for F32x3); `out` may be a caller buffer."""
+        dt = np.float64 if elem == F64x3 else np.float32
+        if out is None:
+            out = np.empty((params.height, params.width, 3), dt)
+            stride = out.strides[1]
+        elif stride is None:
+            stride = out.strides[1] if out.ndim == 3 else (24 if elem == F64x3 else 12)
+        check(lib().lfb_render_ghosts(self._h, lights_array(lights), len(lights), C.byref(params),
+                                      out.ctypes.data, stride, elem, int(additive)))
+        return out
+
+    def dump_rays(self, light, params, i, j, lam):
+        out = np.zeros(params.grid_n * params.grid_n, RAY_HIT_DTYPE)
+        check(lib().lfb_dump_rays(self._h, C.byref(light), C.byref(params), i, j, lam, out.ctypes.data, out.size))
+        return out
+
+    def ref_ghosts(self):
+        out = np.zeros(64 * MAX_LAMBDA, REF_GHOST_DTYPE)
+        n = check(lib().lfb_ref_ghosts(self._h, out.ctypes.data, out.size))
+        return out[:n].copy()
+
+    @property
+    def stream(self):
+        return lib().lfb_stream(self._h)
+
+    def render_ghosts_device(self, lights, params, accum_ptr, clear_first=True):
+        check(lib().lfb_render_ghosts_device(self._h, lights_array(lights), len(lights), C.byref(params),
+                                             accum_ptr, int(clear_first)))
+
+    def finalize_device(self, accum_ptr, params, out_ptr, stride, elem):
+        check(lib().lfb_finalize_device(self._h, accum_ptr, C.byref(params), out_ptr, stride, elem))
+
+    def sync(self):
+        check(lib().lfb_sync(self._h))
+
+    def stats(self):
+        n, t, f = C.c_uint64(), C.c_float(), C.c_float()
+        check(lib().lfb_stats(self._h, C.byref(n), C.byref(t), C.byref(f)))
+        return dict(kernel_launches=n.value, last_trace_ms=t.value, last_frame_ms=f.value)
+
+    def probe_peaks(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        check(lib().lfb_probe_peaks(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(fp32_flops=a.value, mufu_ops=b.value, sm_clock_hz=c.value)

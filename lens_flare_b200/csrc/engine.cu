@@ -1,0 +1,694 @@
+// engine.cu -- the C ABI of liblfb200.so (include/lfb200.h): host-side orchestration of the
+// sm_100a ghost kernels.  Nothing here computes pixels or rays on the CPU: the host builds
+// the job list (which ghost, which light, which wavelength, frame constants), uploads it,
+// launches kernels on the engine's stream and copies results out.  There is no CPU fallback;
+// without a CUDA device lfb_create fails with LFB_ERR_NO_DEVICE.
+//
+// Reference seam (paths under the reference tree): the caller is
+// RaytracedRenderer::start_raytracing (src/pathtracer/raytraced_renderer.cpp:303-311), which
+// runs find_sun_pos() and generate_ghost_buffer() once per render on its own thread; the
+// result is PathTracer::ghost_buffer (src/pathtracer/pathtracer.h:54).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "lfb_internal.h"
+
+using namespace lfb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int fail_cuda(cudaError_t err, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(err);
+  return LFB_ERR_CUDA;
+}
+#define CU(call)                                        \
+  do {                                                  \
+    cudaError_t err_ = (call);                          \
+    if (err_ != cudaSuccess) return fail_cuda(err_, #call); \
+  } while (0)
+
+struct JobId {
+  int light, i, j, lambda;
+};
+
+// Ghost pairs in the reference's order: both reflections before the stop, then both after
+// (pathtracer.cpp:735-762); LFB_PAIRS_ALL appends the pairs that straddle the stop.
+int list_pairs(const lfb_lens& L, int pair_set, int pairs[][2]) {
+  int n = 0;
+  const int S = L.stop_index, N = L.n_surfaces;
+  for (int i = 0; i < S; i++)
+    for (int j = i + 1; j < S; j++) { pairs[n][0] = i; pairs[n][1] = j; n++; }
+  for (int i = S + 1; i < N; i++)
+    for (int j = i + 1; j < N; j++) { pairs[n][0] = i; pairs[n][1] = j; n++; }
+  if (pair_set == LFB_PAIRS_ALL)
+    for (int i = 0; i < S; i++)
+      for (int j = S + 1; j < N; j++) { pairs[n][0] = i; pairs[n][1] = j; n++; }
+  return n;
+}
+
+// Ray-surface interactions of one ray along ghost (i,j): forward 0..j, back j-1..i, forward
+// i+1..n-1, sensor plane  =>  2(j-i) + n + 1; the direct path meets n surfaces + the sensor.
+int interactions_of(const lfb_lens& L, int i, int j) { return i < 0 ? L.n_surfaces + 1 : 2 * (j - i) + L.n_surfaces + 1; }
+
+// All (light, pair, lambda) jobs of a frame, then this shard's share: jobs are ordered by
+// decreasing cost (longest-processing-time first, stable) and dealt round-robin to shards.
+void list_jobs(const lfb_lens& L, const lfb_params& P, int n_lights, std::vector<JobId>& out) {
+  int pairs[LFB_MAX_SURFACES * LFB_MAX_SURFACES][2];
+  std::vector<JobId> all;
+  if (P.mode == LFB_MODE_REF_QUADS) {
+    // one job per reference ghost quad (single sun: the last light wins, pathtracer.cpp:50-53)
+    const int np = list_pairs(L, LFB_PAIRS_REF, pairs);
+    if (n_lights > 0)
+      for (int p = 0; p < np; p++)
+        for (int c = 0; c < L.n_lambda; c++) all.push_back({n_lights - 1, pairs[p][0], pairs[p][1], c});
+  } else {
+    const int np = list_pairs(L, P.pair_set, pairs);
+    for (int l = 0; l < n_lights; l++)
+      for (int p = -1; p < np; p++) {
+        if (p < 0 && !P.include_direct) continue;
+        for (int c = 0; c < L.n_lambda; c++) all.push_back({l, p < 0 ? -1 : pairs[p][0], p < 0 ? -1 : pairs[p][1], c});
+      }
+  }
+  out.clear();
+  if (P.shard_count <= 1) { out = all; return; }
+  std::stable_sort(all.begin(), all.end(), [&](const JobId& a, const JobId& b) {
+    return interactions_of(L, a.i, a.j) > interactions_of(L, b.i, b.j);
+  });
+  for (size_t q = 0; q < all.size(); q++)
+    if ((int)(q % (size_t)P.shard_count) == P.shard_index) out.push_back(all[q]);
+}
+
+int check_lens(const lfb_lens* L) {
+  if (!L) return fail(LFB_ERR_INVALID, "lens is NULL");
+  if (L->n_surfaces < 2 || L->n_surfaces > LFB_MAX_SURFACES) return fail(LFB_ERR_INVALID, "n_surfaces out of range");
+  if (L->n_lambda < 1 || L->n_lambda > LFB_MAX_LAMBDA) return fail(LFB_ERR_INVALID, "n_lambda out of range");
+  if (L->stop_index < 0 || L->stop_index >= L->n_surfaces) return fail(LFB_ERR_INVALID, "stop_index out of range");
+  if (!(L->entrance_half_height > 0) || !(L->stop_half_height > 0)) return fail(LFB_ERR_INVALID, "half heights must be > 0");
+  return LFB_OK;
+}
+
+int check_params(const lfb_params* P, bool need_grid) {
+  if (!P) return fail(LFB_ERR_INVALID, "params is NULL");
+  if (P->mode < LFB_MODE_REF_QUADS || P->mode > LFB_MODE_EXACT_GRID) return fail(LFB_ERR_INVALID, "unknown mode");
+  if (P->width < 1 || P->height < 1 || P->width > 32768 || P->height > 32768) return fail(LFB_ERR_INVALID, "sensor size out of range");
+  if (need_grid || P->mode != LFB_MODE_REF_QUADS) {
+    if (P->mode == LFB_MODE_REF_QUADS) return fail(LFB_ERR_INVALID, "this call needs a grid mode");
+    if (P->grid_n < 1 || P->grid_n > 32768) return fail(LFB_ERR_INVALID, "grid_n out of range");
+    if (P->pair_set != LFB_PAIRS_REF && P->pair_set != LFB_PAIRS_ALL) return fail(LFB_ERR_INVALID, "unknown pair_set");
+    if (P->precision != LFB_FP32 && P->precision != LFB_FP64) return fail(LFB_ERR_INVALID, "unknown precision");
+    if (P->splat != LFB_SPLAT_NEAREST && P->splat != LFB_SPLAT_BILINEAR) return fail(LFB_ERR_INVALID, "unknown splat");
+    if (P->fixed_point_bits < 0 || P->fixed_point_bits > 56) return fail(LFB_ERR_INVALID, "fixed_point_bits out of range");
+  }
+  if (P->shard_count < 0 || (P->shard_count > 0 && (P->shard_index < 0 || P->shard_index >= P->shard_count)))
+    return fail(LFB_ERR_INVALID, "bad shard_index/shard_count");
+  return LFB_OK;
+}
+
+size_t elem_bytes(int elem) { return elem == LFB_F32x3 ? 12 : 24; }
+
+}  // namespace
+
+struct lfb_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_frame0 = nullptr, ev_trace0 = nullptr, ev_trace1 = nullptr, ev_frame1 = nullptr;
+  bool has_lens = false, has_tex = false, timed = false;
+  lfb_lens lens;
+  DevLens dev_lens;
+  float* d_tex = nullptr;
+  int tex_w = 0, tex_h = 0;
+  // jobs of the current frame description (re-used while lights/params/lens do not change)
+  Job* d_jobs = nullptr;
+  Job* h_jobs = nullptr;  // pinned staging
+  int jobs_cap = 0, n_jobs = 0;
+  std::vector<unsigned char> job_key;
+  Job* d_dump_job = nullptr;
+  // owned buffers of the host-memory API
+  unsigned long long* d_accum = nullptr;
+  size_t accum_cap = 0;
+  char* d_out = nullptr;
+  size_t out_cap = 0;
+  lfb_ray_hit* d_hits = nullptr;
+  size_t hits_cap = 0;
+  // REF_QUADS state
+  RefTri* d_tris = nullptr;
+  lfb_ref_ghost* d_ghosts = nullptr;
+  int* d_pairs = nullptr;
+  float* d_rgbw = nullptr;
+  int n_ref_pairs = 0, n_ref_ghosts = 0;
+  uint64_t launches = 0;
+  float last_trace_ms = 0, last_frame_ms = 0;
+};
+
+namespace {
+
+// The lens tables live in __constant__ memory, one copy per device: the engine that last
+// uploaded them owns them, others re-upload before launching.
+const lfb_engine* g_const_owner[64] = {nullptr};
+
+int bind(lfb_engine* e) {
+  if (!e) return fail(LFB_ERR_INVALID, "engine is NULL");
+  CU(cudaSetDevice(e->device));
+  return LFB_OK;
+}
+
+int upload_constants(lfb_engine* e) {
+  if (e->device < 64 && g_const_owner[e->device] == e) return LFB_OK;
+  CU(upload_lens_f32(e->dev_lens, e->stream));
+  CU(upload_lens_f64(e->dev_lens, e->stream));
+  CU(upload_lens_ref(e->dev_lens, e->stream));
+  if (e->device < 64) g_const_owner[e->device] = e;
+  return LFB_OK;
+}
+
+template <typename T>
+int grow(T** p, size_t* cap, size_t need) {
+  if (need <= *cap) return LFB_OK;
+  if (*p) CU(cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  cudaError_t err = cudaMalloc((void**)p, need);
+  if (err == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(LFB_ERR_NOMEM, "cudaMalloc: out of device memory"); }
+  if (err != cudaSuccess) return fail_cuda(err, "cudaMalloc");
+  *cap = need;
+  return LFB_OK;
+}
+
+FrameGeom make_geom(const lfb_engine* e, const lfb_params& P) {
+  FrameGeom g;
+  g.W = P.width; g.H = P.height; g.N = P.grid_n; g.splat = P.splat;
+  g.tiles_x = (P.grid_n + 15) / 16;
+  g.tiles_per_job = g.tiles_x * g.tiles_x;
+  g.tex_w = e->tex_w; g.tex_h = e->tex_h;
+  g.fp_scale = ldexp(1.0, P.fixed_point_bits > 0 ? P.fixed_point_bits : 40);
+  return g;
+}
+
+// Frame constants of one job.  The libm calls (atan/cosf/sinf of frame constants,
+// pathtracer.cpp:414, and sin/cos of the light's angle) are made here once per job, not per ray.
+void fill_job(const lfb_engine* e, const lfb_params& P, const lfb_light& lt, const JobId& id, Job* J) {
+  memset(J, 0, sizeof(*J));
+  J->light = id.light; J->i = id.i; J->j = id.j; J->lambda = id.lambda;
+  J->theta = lt.theta;
+  const double dx = lt.ns_x - 0.5, dy = lt.ns_y - 0.5;
+  const float ang = (dx == 0 && dy == 0) ? 0.f : (float)atan(dy / dx);
+  J->cs = cosf(ang); J->sn = sinf(ang);
+  J->sx = ceil(lt.ns_x * (double)P.width);   // draw_ghost, pathtracer.cpp:462-463
+  J->sy = ceil(lt.ns_y * (double)P.height);
+  J->ppu = P.px_per_unit > 0 ? P.px_per_unit : 0.4f;
+  J->sin_t = sin((double)lt.theta); J->cos_t = cos((double)lt.theta);
+  const double cell = 2 * e->lens.entrance_half_height / P.grid_n;
+  const double area = cell * cell * J->ppu * J->ppu;
+  for (int c = 0; c < 3; c++) J->chan[c] = (double)lt.radiance[c] * (double)e->lens.rgb_weight[id.lambda][c] * area;
+}
+
+// Build + upload this shard's jobs unless the frame description is unchanged.
+int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params& P) {
+  std::vector<unsigned char> key(sizeof(lfb_params) + sizeof(lfb_light) * (size_t)n_lights);
+  memcpy(key.data(), &P, sizeof(lfb_params));
+  if (n_lights > 0) memcpy(key.data() + sizeof(lfb_params), lights, sizeof(lfb_light) * (size_t)n_lights);
+  if (key == e->job_key) return LFB_OK;
+  std::vector<JobId> ids;
+  list_jobs(e->lens, P, n_lights, ids);
+  const int n = (int)ids.size();
+  if (n > e->jobs_cap) {
+    if (e->d_jobs) CU(cudaFree(e->d_jobs));
+    if (e->h_jobs) CU(cudaFreeHost(e->h_jobs));
+    e->d_jobs = nullptr; e->h_jobs = nullptr; e->jobs_cap = 0;
+    CU(cudaMalloc((void**)&e->d_jobs, sizeof(Job) * (size_t)n));
+    CU(cudaHostAlloc((void**)&e->h_jobs, sizeof(Job) * (size_t)n, cudaHostAllocDefault));
+    e->jobs_cap = n;
+  }
+  // the previous frame's upload may still be reading h_jobs
+  CU(cudaStreamSynchronize(e->stream));
+  for (int q = 0; q < n; q++) fill_job(e, P, lights[ids[q].light], ids[q], &e->h_jobs[q]);
+  e->n_jobs = n;
+  if (n > 0) {
+    CU(cudaMemcpyAsync(e->d_jobs, e->h_jobs, sizeof(Job) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    if (P.mode == LFB_MODE_PARAXIAL_GRID) {
+      CU(launch_paraxial_setup(e->d_jobs, n, P.physical_backward, e->stream));
+      e->launches++;
+    }
+  }
+  e->job_key.swap(key);
+  return LFB_OK;
+}
+
+int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params& P,
+                       unsigned long long* accum, int clear_first) {
+  int rc = upload_constants(e);
+  if (rc) return rc;
+  rc = prepare_jobs(e, lights, n_lights, P);
+  if (rc) return rc;
+  const FrameGeom g = make_geom(e, P);
+  if (clear_first) CU(cudaMemsetAsync(accum, 0, lfb_accum_bytes(P.width, P.height), e->stream));
+  CU(cudaEventRecord(e->ev_trace0, e->stream));
+  if (e->n_jobs > 0) {
+    if (P.precision == LFB_FP64) CU(launch_trace_splat_f64(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
+    else CU(launch_trace_splat_f32(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
+    e->launches++;
+  }
+  CU(cudaEventRecord(e->ev_trace1, e->stream));
+  e->timed = true;
+  return LFB_OK;
+}
+
+int render_ref_device(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params& P, void* out_dev,
+                      size_t stride, int elem, int additive) {
+  int rc = upload_constants(e);
+  if (rc) return rc;
+  RefFrame f;
+  memset(&f, 0, sizeof(f));
+  f.W = P.width; f.H = P.height; f.tex_w = e->tex_w; f.tex_h = e->tex_h;
+  f.n_pairs = e->n_ref_pairs; f.n_lambda = e->lens.n_lambda;
+  e->n_ref_ghosts = 0;
+  if (n_lights > 0) {
+    const lfb_light& lt = lights[n_lights - 1];  // the last on-screen light wins, pathtracer.cpp:50-53
+    f.has_sun = !(lt.ns_x == 0 && lt.ns_y == 0);  // :724-726
+    f.angle_to_sun = lt.theta;
+    const float ang = (float)atan((lt.ns_y - 0.5) / (lt.ns_x - 0.5));  // shift_vertex :414
+    f.cs = cosf(ang); f.sn = sinf(ang);
+    f.gb_mid_w = ceil(lt.ns_x * (double)P.width);
+    f.gb_mid_h = ceil(lt.ns_y * (double)P.height);
+  }
+  CU(cudaEventRecord(e->ev_trace0, e->stream));
+  const int n_ghosts = f.n_pairs * f.n_lambda;
+  if (f.has_sun && n_ghosts > 0) {
+    CU(launch_ref_setup(f, e->d_pairs, e->d_rgbw, e->d_tris, e->d_ghosts, e->stream));
+    e->launches++;
+    e->n_ref_ghosts = n_ghosts;
+  }
+  CU(launch_ref_raster(f, e->d_tris, f.has_sun ? 2 * n_ghosts : 0, e->d_tex, out_dev, stride, elem, additive, e->stream));
+  e->launches++;
+  CU(cudaEventRecord(e->ev_trace1, e->stream));
+  e->timed = true;
+  return LFB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------
+extern "C" int lfb_abi_version(void) { return LFB_ABI_VERSION; }
+
+extern "C" const char* lfb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int lfb_create(lfb_engine** out, int device_id) {
+  if (!out) return fail(LFB_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    return fail(LFB_ERR_NO_DEVICE, std::string("no CUDA device (") + (err != cudaSuccess ? cudaGetErrorString(err) : "device count 0") +
+                                       "); this engine has no CPU fallback");
+  }
+  if (device_id < 0) CU(cudaGetDevice(&device_id));
+  if (device_id >= n) return fail(LFB_ERR_INVALID, "device_id out of range");
+  CU(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) return fail(LFB_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + "; the kernels are built for sm_100a only");
+  lfb_engine* e = new (std::nothrow) lfb_engine();
+  if (!e) return fail(LFB_ERR_NOMEM, "out of host memory");
+  e->device = device_id;
+  cudaError_t rc = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_frame0);
+  if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_trace0);
+  if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_trace1);
+  if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_frame1);
+  if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_dump_job, sizeof(Job));
+  if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
+  *out = e;
+  return LFB_OK;
+}
+
+extern "C" void lfb_destroy(lfb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
+  cudaFree(e->d_tex); cudaFree(e->d_jobs); cudaFree(e->d_dump_job); cudaFree(e->d_accum); cudaFree(e->d_out);
+  cudaFree(e->d_hits); cudaFree(e->d_tris); cudaFree(e->d_ghosts); cudaFree(e->d_pairs); cudaFree(e->d_rgbw);
+  if (e->h_jobs) cudaFreeHost(e->h_jobs);
+  if (e->ev_frame0) cudaEventDestroy(e->ev_frame0);
+  if (e->ev_trace0) cudaEventDestroy(e->ev_trace0);
+  if (e->ev_trace1) cudaEventDestroy(e->ev_trace1);
+  if (e->ev_frame1) cudaEventDestroy(e->ev_frame1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+// ---------------------------------------------------------------------------
+// inputs
+// ---------------------------------------------------------------------------
+namespace {
+// CIE 1931 colour matching functions (multi-lobe Gaussian fit of Wyman, Sloan & Shirley 2013)
+// -> linear sRGB; used to weight spectral samples into R,G,B when n_lambda != 3.
+double lobe(double lam, double mu, double s1, double s2) {
+  const double t = (lam - mu) / (lam < mu ? s1 : s2);
+  return exp(-0.5 * t * t);
+}
+void lambda_to_rgb(double lam, double rgb[3]) {
+  const double X = 1.056 * lobe(lam, 599.8, 37.9, 31.0) + 0.362 * lobe(lam, 442.0, 16.0, 26.7) - 0.065 * lobe(lam, 501.1, 20.4, 26.2);
+  const double Y = 0.821 * lobe(lam, 568.8, 46.9, 40.5) + 0.286 * lobe(lam, 530.9, 16.3, 31.1);
+  const double Z = 1.217 * lobe(lam, 437.0, 11.8, 36.0) + 0.681 * lobe(lam, 459.0, 26.0, 13.8);
+  rgb[0] = 3.2406 * X - 1.5372 * Y - 0.4986 * Z;
+  rgb[1] = -0.9689 * X + 1.8758 * Y + 0.0415 * Z;
+  rgb[2] = 0.0557 * X - 0.2040 * Y + 1.0570 * Z;
+  for (int c = 0; c < 3; c++) rgb[c] = rgb[c] < 0 ? 0 : rgb[c];
+}
+}  // namespace
+
+extern "C" int lfb_builtin_lens(lfb_lens* L, int n_lambda, float coating_lambda0_nm) {
+  if (!L) return fail(LFB_ERR_INVALID, "lens is NULL");
+  if (n_lambda < 1 || n_lambda > LFB_MAX_LAMBDA) return fail(LFB_ERR_INVALID, "n_lambda out of range");
+  // The reference's hard-coded prescription, pathtracer.cpp:539-556 (thickness after surface k,
+  // radius of curvature, index after surface k for its R, G, B tables).
+  static const double thick[9] = {7.700, 1.850, 3.520, 1.850, 4.180, 3.000, 1.850, 7.270, 83.91};
+  static const double radius[9] = {30.810, -89.350, 580.380, -80.630, 28.340, 0, 0, 32.190, -52.990};
+  static const float n_rgb[3][9] = {{1.652f, 1.5991f, 1, 1.6396f, 1, 1, 1.5776f, 1.68990f, 1},
+                                    {1.652f, 1.6113f, 1, 1.65f, 1, 1, 1.5885f, 1.6999f, 1},
+                                    {1.652f, 1.6164f, 1, 1.6542f, 1, 1, 1.5930f, 1.7040f, 1}};
+  static const double anchor_nm[3] = {650.0, 550.0, 450.0};
+  memset(L, 0, sizeof(*L));
+  L->n_surfaces = 9; L->stop_index = 5; L->n_lambda = n_lambda;
+  L->entrance_half_height = 14.5;  // :737
+  L->stop_half_height = 11.6;      // :621
+  L->stop_half_height_neg = 11.5;  // :624
+  for (int k = 0; k < 9; k++) {
+    L->thickness[k] = (float)thick[k];
+    L->curvature[k] = radius[k] == 0 ? 0.f : (float)(1 / radius[k]);
+    L->semi_aperture[k] = 14.5f;
+  }
+  if (n_lambda == 3) {
+    for (int l = 0; l < 3; l++) {
+      L->lambda_nm[l] = (float)anchor_nm[l];
+      for (int k = 0; k < 9; k++) L->ior[l][k] = n_rgb[l][k];
+      L->rgb_weight[l][l] = 1.f;
+    }
+  } else {
+    double sum[3] = {0, 0, 0}, w[LFB_MAX_LAMBDA][3];
+    for (int l = 0; l < n_lambda; l++) {
+      const double lam = 400.0 + 300.0 * (l + 0.5) / n_lambda;
+      L->lambda_nm[l] = (float)lam;
+      lambda_to_rgb(lam, w[l]);
+      for (int c = 0; c < 3; c++) sum[c] += w[l][c];
+    }
+    for (int l = 0; l < n_lambda; l++)
+      for (int c = 0; c < 3; c++) L->rgb_weight[l][c] = (float)(w[l][c] / sum[c]);
+    // n(lambda): piecewise two-term Cauchy n = A + B/lam^2 through the R,G,B anchors (linear in
+    // u = 1/lam^2 on [650,550] and [550,450] nm, each segment continued beyond its anchor): exact
+    // at the reference's three indices and monotone, which a single 3-term fit of them is not.
+    for (int k = 0; k < 9; k++) {
+      double u[3], n[3];
+      for (int a = 0; a < 3; a++) {
+        const double lm = anchor_nm[a] * 1e-3;
+        u[a] = 1.0 / (lm * lm);
+        n[a] = n_rgb[a][k];
+      }
+      const double f01 = (n[1] - n[0]) / (u[1] - u[0]);
+      const double f12 = (n[2] - n[1]) / (u[2] - u[1]);
+      for (int l = 0; l < n_lambda; l++) {
+        const double lm = (double)L->lambda_nm[l] * 1e-3;
+        const double x = 1.0 / (lm * lm);
+        L->ior[l][k] = (float)(x <= u[1] ? n[1] + (x - u[1]) * f01 : n[1] + (x - u[1]) * f12);
+      }
+    }
+  }
+  for (int k = 0; k < 9; k++) {
+    bool interface = false;
+    for (int l = 0; l < n_lambda; l++) {
+      const float before = k == 0 ? 1.f : L->ior[l][k - 1];
+      if (before != L->ior[l][k]) interface = true;
+    }
+    L->coating_lambda0_nm[k] = interface ? coating_lambda0_nm : 0.f;
+  }
+  return LFB_OK;
+}
+
+extern "C" int lfb_set_lens(lfb_engine* e, const lfb_lens* L) {
+  int rc = bind(e);
+  if (rc) return rc;
+  rc = check_lens(L);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(e->stream));
+  e->lens = *L;
+  DevLens& D = e->dev_lens;
+  memset(&D, 0, sizeof(D));
+  D.n_surfaces = L->n_surfaces; D.stop = L->stop_index; D.n_lambda = L->n_lambda;
+  double z = 0;
+  for (int k = 0; k < L->n_surfaces; k++) {
+    D.c[k] = L->curvature[k]; D.d[k] = L->thickness[k];
+    D.semi[k] = L->semi_aperture[k]; D.coat[k] = L->coating_lambda0_nm[k];
+    D.zv_d[k] = z; D.zv[k] = (float)z;
+    z += (double)L->thickness[k];
+  }
+  D.zv_d[L->n_surfaces] = z; D.zv[L->n_surfaces] = (float)z;
+  memcpy(D.ior, L->ior, sizeof(D.ior));
+  memcpy(D.lambda_nm, L->lambda_nm, sizeof(D.lambda_nm));
+  D.P = L->entrance_half_height; D.h_stop = L->stop_half_height; D.h_stop_neg = L->stop_half_height_neg;
+  if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
+  // REF_QUADS tables: the reference's pair list and per-wavelength colour basis
+  int pairs[LFB_MAX_SURFACES * LFB_MAX_SURFACES][2];
+  const int np = list_pairs(*L, LFB_PAIRS_REF, pairs);
+  const int ng = np * L->n_lambda;
+  cudaFree(e->d_pairs); cudaFree(e->d_rgbw); cudaFree(e->d_tris); cudaFree(e->d_ghosts);
+  e->d_pairs = nullptr; e->d_rgbw = nullptr; e->d_tris = nullptr; e->d_ghosts = nullptr;
+  CU(cudaMalloc((void**)&e->d_pairs, sizeof(int) * 2 * (size_t)std::max(np, 1)));
+  CU(cudaMalloc((void**)&e->d_rgbw, sizeof(float) * 3 * (size_t)L->n_lambda));
+  CU(cudaMalloc((void**)&e->d_tris, sizeof(RefTri) * 2 * (size_t)std::max(ng, 1)));
+  CU(cudaMalloc((void**)&e->d_ghosts, sizeof(lfb_ref_ghost) * (size_t)std::max(ng, 1)));
+  if (np > 0) CU(cudaMemcpy(e->d_pairs, pairs, sizeof(int) * 2 * (size_t)np, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->d_rgbw, L->rgb_weight, sizeof(float) * 3 * (size_t)L->n_lambda, cudaMemcpyHostToDevice));
+  e->n_ref_pairs = np; e->n_ref_ghosts = 0;
+  e->job_key.clear();
+  e->has_lens = true;
+  return LFB_OK;
+}
+
+extern "C" int lfb_set_aperture(lfb_engine* e, const float* texels, int w, int h) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!texels || w < 1 || h < 1 || w > 16384 || h > 16384) return fail(LFB_ERR_INVALID, "bad aperture texture");
+  const size_t bytes = sizeof(float) * (size_t)w * h;
+  if (w != e->tex_w || h != e->tex_h) {
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_tex);
+    e->d_tex = nullptr; e->has_tex = false;
+    CU(cudaMalloc((void**)&e->d_tex, bytes));
+    e->tex_w = w; e->tex_h = h;
+  }
+  CU(cudaMemcpyAsync(e->d_tex, texels, bytes, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));  // the caller may free texels on return
+  e->has_tex = true;
+  return LFB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------
+extern "C" size_t lfb_accum_bytes(int width, int height) { return sizeof(unsigned long long) * 3 * (size_t)width * (size_t)height; }
+
+extern "C" void* lfb_stream(lfb_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+extern "C" int lfb_sync(lfb_engine* e) {
+  int rc = bind(e);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(e->stream));
+  return LFB_OK;
+}
+
+extern "C" int lfb_render_ghosts_device(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P,
+                                        void* accum_dev, int clear_first) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!e->has_lens || !e->has_tex) return fail(LFB_ERR_STATE, "set the lens and the aperture first");
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (n_lights < 0 || (n_lights > 0 && !lights) || !accum_dev) return fail(LFB_ERR_INVALID, "bad lights/accumulator");
+  return render_grid_device(e, lights, n_lights, *P, (unsigned long long*)accum_dev, clear_first);
+}
+
+extern "C" int lfb_finalize_device(lfb_engine* e, const void* accum_dev, const lfb_params* P, void* out_dev,
+                                   size_t out_stride_bytes, int out_elem) {
+  int rc = bind(e);
+  if (rc) return rc;
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (!accum_dev || !out_dev) return fail(LFB_ERR_INVALID, "NULL device pointer");
+  if (out_elem != LFB_F32x3 && out_elem != LFB_F64x3) return fail(LFB_ERR_INVALID, "unknown out_elem");
+  if (out_stride_bytes < elem_bytes(out_elem) || out_stride_bytes % (out_elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
+  const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+  CU(launch_finalize((const unsigned long long*)accum_dev, P->width, P->height, inv, out_dev, out_stride_bytes, out_elem, 0, e->stream));
+  e->launches++;
+  return LFB_OK;
+}
+
+extern "C" int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P, void* out,
+                                 size_t stride, int elem, int additive) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!e->has_lens || !e->has_tex) return fail(LFB_ERR_STATE, "set the lens and the aperture first");
+  rc = check_params(P, false);
+  if (rc) return rc;
+  if (n_lights < 0 || (n_lights > 0 && !lights) || !out) return fail(LFB_ERR_INVALID, "bad lights/out");
+  if (elem != LFB_F32x3 && elem != LFB_F64x3) return fail(LFB_ERR_INVALID, "unknown out_elem");
+  if (stride < elem_bytes(elem) || stride % (elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
+  const size_t npx = (size_t)P->width * P->height;
+  const size_t out_bytes = (npx - 1) * stride + elem_bytes(elem);
+  rc = grow(&e->d_out, &e->out_cap, out_bytes);
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev_frame0, e->stream));
+  if (additive) CU(cudaMemcpyAsync(e->d_out, out, out_bytes, cudaMemcpyHostToDevice, e->stream));
+  else if (stride != elem_bytes(elem)) CU(cudaMemsetAsync(e->d_out, 0, out_bytes, e->stream));  // padding bytes come back as 0
+  if (P->mode == LFB_MODE_REF_QUADS) {
+    rc = render_ref_device(e, lights, n_lights, *P, e->d_out, stride, elem, additive);
+    if (rc) return rc;
+  } else {
+    rc = grow(&e->d_accum, &e->accum_cap, lfb_accum_bytes(P->width, P->height));
+    if (rc) return rc;
+    rc = render_grid_device(e, lights, n_lights, *P, e->d_accum, 1);
+    if (rc) return rc;
+    const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+    CU(launch_finalize(e->d_accum, P->width, P->height, inv, e->d_out, stride, elem, additive, e->stream));
+    e->launches++;
+  }
+  CU(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaEventRecord(e->ev_frame1, e->stream));
+  CU(cudaStreamSynchronize(e->stream));  // the reference's caller reads ghost_buffer right after the call
+  CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
+  CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
+  return LFB_OK;
+}
+
+extern "C" int lfb_dump_rays(lfb_engine* e, const lfb_light* light, const lfb_params* P, int i, int j, int lambda,
+                             lfb_ray_hit* out, size_t cap) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!e->has_lens || !e->has_tex) return fail(LFB_ERR_STATE, "set the lens and the aperture first");
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (!light || !out) return fail(LFB_ERR_INVALID, "NULL light/out");
+  const size_t n = (size_t)P->grid_n * P->grid_n;
+  if (cap < n) return fail(LFB_ERR_INVALID, "out holds fewer than grid_n^2 records");
+  if (lambda < 0 || lambda >= e->lens.n_lambda) return fail(LFB_ERR_INVALID, "lambda out of range");
+  const bool direct = i < 0 && j < 0;
+  if (!direct) {
+    const int S = e->lens.stop_index;
+    if (i < 0 || j <= i || j >= e->lens.n_surfaces || i == S || j == S) return fail(LFB_ERR_INVALID, "bad ghost pair");
+  }
+  rc = upload_constants(e);
+  if (rc) return rc;
+  rc = grow(&e->d_hits, &e->hits_cap, sizeof(lfb_ray_hit) * n);
+  if (rc) return rc;
+  Job J;
+  JobId id = {0, direct ? -1 : i, direct ? -1 : j, lambda};
+  fill_job(e, *P, *light, id, &J);
+  CU(cudaMemcpyAsync(e->d_dump_job, &J, sizeof(Job), cudaMemcpyHostToDevice, e->stream));
+  if (P->mode == LFB_MODE_PARAXIAL_GRID) {
+    CU(launch_paraxial_setup(e->d_dump_job, 1, P->physical_backward, e->stream));
+    e->launches++;
+  }
+  const FrameGeom g = make_geom(e, *P);
+  if (P->precision == LFB_FP64) CU(launch_trace_dump_f64(e->d_dump_job, g, P->mode, e->d_tex, e->d_hits, e->stream));
+  else CU(launch_trace_dump_f32(e->d_dump_job, g, P->mode, e->d_tex, e->d_hits, e->stream));
+  e->launches++;
+  CU(cudaMemcpyAsync(out, e->d_hits, sizeof(lfb_ray_hit) * n, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return LFB_OK;
+}
+
+extern "C" int lfb_ref_ghosts(lfb_engine* e, lfb_ref_ghost* out, int cap) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!out || cap < 0) return fail(LFB_ERR_INVALID, "bad out/cap");
+  const int n = std::min(cap, e->n_ref_ghosts);
+  if (n > 0) {
+    CU(cudaMemcpyAsync(out, e->d_ghosts, sizeof(lfb_ref_ghost) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  return e->n_ref_ghosts;
+}
+
+// ---------------------------------------------------------------------------
+// accounting (host only; usable without a device)
+// ---------------------------------------------------------------------------
+extern "C" int lfb_count_work(const lfb_lens* L, const lfb_params* P, int n_lights, double* rays, double* interactions,
+                              int* jobs) {
+  int rc = check_lens(L);
+  if (rc) return rc;
+  rc = check_params(P, false);
+  if (rc) return rc;
+  if (n_lights < 0) return fail(LFB_ERR_INVALID, "n_lights < 0");
+  std::vector<JobId> ids;
+  list_jobs(*L, *P, n_lights, ids);
+  const double per_job = P->mode == LFB_MODE_REF_QUADS ? 2.0 : (double)P->grid_n * P->grid_n;
+  double r = 0, it = 0;
+  for (const JobId& id : ids) { r += per_job; it += per_job * interactions_of(*L, id.i, id.j); }
+  if (rays) *rays = r;
+  if (interactions) *interactions = it;
+  if (jobs) *jobs = (int)ids.size();
+  return LFB_OK;
+}
+
+extern "C" int lfb_list_jobs(const lfb_lens* L, const lfb_params* P, int n_lights, int32_t* out, int cap) {
+  int rc = check_lens(L);
+  if (rc) return rc;
+  rc = check_params(P, false);
+  if (rc) return rc;
+  if (n_lights < 0 || cap < 0 || (cap > 0 && !out)) return fail(LFB_ERR_INVALID, "bad arguments");
+  std::vector<JobId> ids;
+  list_jobs(*L, *P, n_lights, ids);
+  for (int q = 0; q < (int)ids.size() && q < cap; q++) {
+    out[4 * q] = ids[q].light; out[4 * q + 1] = ids[q].i; out[4 * q + 2] = ids[q].j; out[4 * q + 3] = ids[q].lambda;
+  }
+  return (int)ids.size();
+}
+
+extern "C" int lfb_stats(lfb_engine* e, uint64_t* kernel_launches, float* last_trace_ms, float* last_frame_ms) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (kernel_launches) *kernel_launches = e->launches;
+  if (last_trace_ms) {
+    // the device-resident API does not synchronise: resolve the trace events on demand
+    if (e->timed && cudaEventQuery(e->ev_trace1) == cudaSuccess) cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1);
+    cudaGetLastError();
+    *last_trace_ms = e->last_trace_ms;
+  }
+  if (last_frame_ms) *last_frame_ms = e->last_frame_ms;
+  return LFB_OK;
+}
+
+extern "C" int lfb_probe_peaks(lfb_engine* e, double* fp32_flops, double* mufu_ops, double* sm_clock_hz) {
+  int rc = bind(e);
+  if (rc) return rc;
+  CU(probe_peaks(e->device, e->stream, fp32_flops, mufu_ops, sm_clock_hz));
+  e->launches += 10;
+  return LFB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pinned host memory helpers
+// ---------------------------------------------------------------------------
+extern "C" void* lfb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+extern "C" void lfb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}

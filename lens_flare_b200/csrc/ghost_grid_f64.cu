@@ -1,0 +1,100 @@
+// ghost_grid_f64.cu -- FP64 instantiation of the ray-grid kernels (the parity path), the
+// paraxial set-up kernel and the accumulator finalize kernel.  Compiled with --fmad=false:
+// the CPU oracle (and the x86-64 reference) round every product and sum separately, and the
+// parity tests compare fixed-point sums bit for bit.
+#define LFB_TU f64
+#include "ghost_grid_impl.cuh"
+#include "ref_abcd.cuh"
+
+namespace lfb {
+
+cudaError_t upload_lens_f64(const DevLens& h, cudaStream_t s) {
+  return cudaMemcpyToSymbolAsync(f64::c_lens, &h, sizeof(DevLens), 0, cudaMemcpyHostToDevice, s);
+}
+cudaError_t launch_trace_splat_f64(const Job* jobs, int n_jobs, const FrameGeom& g, int mode, const float* tex,
+                                   unsigned long long* accum, cudaStream_t s) {
+  return f64::launch_trace_splat_t<double>(jobs, n_jobs, g, mode, tex, accum, s);
+}
+cudaError_t launch_trace_dump_f64(const Job* job, const FrameGeom& g, int mode, const float* tex, lfb_ray_hit* out,
+                                  cudaStream_t s) {
+  return f64::launch_trace_dump_t<double>(job, g, mode, tex, out, s);
+}
+
+// ---------------------------------------------------------------------------
+// paraxial set-up (restates lfo_paraxial_system / pathtracer.cpp:588-689)
+// ---------------------------------------------------------------------------
+__global__ void paraxial_setup_kernel(Job* __restrict__ jobs, int n_jobs, int physical_backward) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_jobs) return;
+  const DevLens& L = f64::c_lens;
+  const int n = L.n_surfaces, stop = L.stop;
+  const int i = jobs[q].i, j = jobs[q].j, lam = jobs[q].lambda;
+  int nc = 0;
+  m2 M = make2(1.f, 0.f, 0.f, 1.f);
+  auto record = [&](const m2& X) {
+    jobs[q].cross[nc][0] = X.a; jobs[q].cross[nc][1] = X.b;
+    jobs[q].cross[nc][2] = X.c; jobs[q].cross[nc][3] = X.d;
+    nc++;
+  };
+  if (i < 0) {
+    for (int k = 0; k < n; k++) {
+      if (k == stop) { record(M); M = mmul(mT(L.d[k]), M); continue; }
+      M = step_TR(L, lam, k, M);
+    }
+  } else {
+    for (int k = 0; k < j; k++) {
+      if (k == stop) { record(M); M = mmul(mT(L.d[k]), M); continue; }
+      M = step_TR(L, lam, k, M);
+    }
+    M = mmul(mL(L.c[j]), M);
+    for (int k = j - 1; k > i; k--) {
+      M = step_back(L, lam, k, M, physical_backward);
+      if (k == stop) record(M);
+    }
+    M = step_second_reflection(L, i, M);
+    for (int k = i + 1; k < n; k++) {
+      if (k == stop) { record(M); M = mmul(mT(L.d[k]), M); continue; }
+      M = step_TR(L, lam, k, M);
+    }
+  }
+  jobs[q].n_cross = nc;
+  jobs[q].full[0] = M.a; jobs[q].full[1] = M.b; jobs[q].full[2] = M.c; jobs[q].full[3] = M.d;
+}
+
+cudaError_t launch_paraxial_setup(Job* jobs, int n_jobs, int physical_backward, cudaStream_t s) {
+  if (n_jobs <= 0) return cudaSuccess;
+  paraxial_setup_kernel<<<(n_jobs + 63) / 64, 64, 0, s>>>(jobs, n_jobs, physical_backward);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// finalize: u64 fixed point -> pixels.  One thread per pixel; the accumulators are read
+// once (24 B/px) and the output written once (12 or 24 B/px): purely HBM-bound.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize_kernel(const unsigned long long* __restrict__ accum, size_t npx,
+                                                       double inv_scale, char* __restrict__ out, size_t stride,
+                                                       int elem, int additive) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npx) return;
+  double v[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) v[c] = (double)(long long)accum[3 * p + c] * inv_scale;
+  if (elem == LFB_F32x3) {
+    float* o = reinterpret_cast<float*>(out + p * stride);
+    if (additive) { o[0] += (float)v[0]; o[1] += (float)v[1]; o[2] += (float)v[2]; }
+    else { o[0] = (float)v[0]; o[1] = (float)v[1]; o[2] = (float)v[2]; }
+  } else {
+    double* o = reinterpret_cast<double*>(out + p * stride);
+    if (additive) { o[0] += v[0]; o[1] += v[1]; o[2] += v[2]; }
+    else { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+  }
+}
+
+cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,
+                            size_t stride, int elem, int additive, cudaStream_t s) {
+  size_t npx = (size_t)W * H;
+  finalize_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(accum, npx, inv_scale, (char*)out, stride, elem, additive);
+  return cudaGetLastError();
+}
+
+}  // namespace lfb

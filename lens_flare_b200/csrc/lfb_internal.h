@@ -1,0 +1,91 @@
+// lfb_internal.h -- shared between the host C-ABI layer and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lfb200.h"
+
+namespace lfb {
+
+// Lens tables as the kernels see them (one copy in __constant__ memory per device).
+// Everything the per-ray loops index is warp-uniform, so constant-cache broadcasts apply.
+struct DevLens {
+  int n_surfaces, stop, n_lambda, pad;
+  float c[LFB_MAX_SURFACES];        // curvature
+  float d[LFB_MAX_SURFACES];        // thickness after surface k
+  float zv[LFB_MAX_SURFACES + 1];   // vertex z of surface k; zv[n] = sensor plane
+  float semi[LFB_MAX_SURFACES];     // clear semi-aperture (radius)
+  float coat[LFB_MAX_SURFACES];     // quarter-wave design wavelength (nm), 0 = bare
+  double zv_d[LFB_MAX_SURFACES + 1];
+  float ior[LFB_MAX_LAMBDA][LFB_MAX_SURFACES];
+  float lambda_nm[LFB_MAX_LAMBDA];
+  double P;           // entrance half height
+  double h_stop;      // stop half height
+  double h_stop_neg;  // reference's asymmetric re-aim height
+};
+
+// One (light, ghost pair, wavelength) unit of work.  Filled on the host except the
+// paraxial matrices, which the device set-up kernel writes (paraxial_setup_kernel).
+struct Job {
+  int light, i, j, lambda;  // i = j = -1: direct path
+  int n_cross, pad0, pad1, pad2;
+  float theta;
+  float pad3;
+  double chan[3];           // radiance * rgb_weight * ray area * px_per_unit^2
+  double sx, sy, cs, sn, ppu;  // sensor mapping (sun pixel, rotation, pixels per lens unit)
+  double sin_t, cos_t;         // EXACT_GRID: direction of the light's parallel bundle
+  double cross[3][4];       // entrance -> stop plane, per crossing (m00,m01,m10,m11)
+  double full[4];           // entrance -> sensor
+};
+
+struct FrameGeom {
+  int W, H, N, splat;
+  int tiles_x, tiles_per_job;
+  int tex_w, tex_h;
+  double fp_scale;  // 2^fixed_point_bits
+};
+
+// REF_QUADS: one rasterisable triangle of a ghost quad (pathtracer.cpp:346-410 state
+// after the y-sort and the -0.5 shift), in draw order.
+struct RefTri {
+  float x0, y0, u0, v0, x1, y1, u1, v1, x2, y2, u2, v2;
+  int min_x, max_x, min_y, max_y;  // loop bounds, upper exclusive
+  double col[3];
+};
+
+// Per-frame constants of REF_QUADS computed once on the host with the host libm (the
+// reference calls atan/cosf/sinf per vertex with frame-constant arguments, :414).
+struct RefFrame {
+  int W, H, tex_w, tex_h;
+  int n_pairs, n_lambda;
+  float angle_to_sun;  // ray angle theta
+  float cs, sn;        // cosf/sinf of float(atan((ay-.5)/(ax-.5)))
+  double gb_mid_w, gb_mid_h;
+  int has_sun, pad;
+};
+
+// one __constant__ copy of the lens per translation unit
+cudaError_t upload_lens_f32(const DevLens& h, cudaStream_t s);
+cudaError_t upload_lens_f64(const DevLens& h, cudaStream_t s);
+cudaError_t upload_lens_ref(const DevLens& h, cudaStream_t s);
+
+// kernels' host launchers (definitions in the .cu files)
+cudaError_t launch_paraxial_setup(Job* jobs, int n_jobs, int physical_backward, cudaStream_t s);
+cudaError_t launch_trace_splat_f32(const Job* jobs, int n_jobs, const FrameGeom& g, int mode, const float* tex,
+                                   unsigned long long* accum, cudaStream_t s);
+cudaError_t launch_trace_splat_f64(const Job* jobs, int n_jobs, const FrameGeom& g, int mode, const float* tex,
+                                   unsigned long long* accum, cudaStream_t s);
+cudaError_t launch_trace_dump_f32(const Job* job, const FrameGeom& g, int mode, const float* tex, lfb_ray_hit* out,
+                                  cudaStream_t s);
+cudaError_t launch_trace_dump_f64(const Job* job, const FrameGeom& g, int mode, const float* tex, lfb_ray_hit* out,
+                                  cudaStream_t s);
+cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,
+                            size_t stride, int elem, int additive, cudaStream_t s);
+cudaError_t launch_ref_setup(const RefFrame& f, const int* pairs, const float* rgb_weight, RefTri* tris,
+                             lfb_ref_ghost* ghosts, cudaStream_t s);
+cudaError_t launch_ref_raster(const RefFrame& f, const RefTri* tris, int n_tris, const float* tex, void* out,
+                              size_t stride, int elem, int additive, cudaStream_t s);
+
+cudaError_t probe_peaks(int device, cudaStream_t s, double* fp32_flops, double* mufu_ops, double* sm_clock_hz);
+
+}  // namespace lfb

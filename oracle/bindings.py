@@ -10,81 +10,21 @@ Only tests/, tools/make_golden.py, __graft_entry__.smoke() and bench.py's cpu_ba
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE)) if os.path.dirname(HERE) not in sys.path else None
 REF_SO = os.path.join(HERE, "_ref", "libref_oracle.so")
 PORT_SO = os.path.join(HERE, "_build", "liblf_oracle.so")
 
-MAX_SURFACES = 16
-MAX_LAMBDA = 64
-
-
-class Lens(C.Structure):
-    _fields_ = [
-        ("n_surfaces", C.c_int32), ("stop_index", C.c_int32), ("n_lambda", C.c_int32), ("reserved0", C.c_int32),
-        ("curvature", C.c_float * MAX_SURFACES), ("thickness", C.c_float * MAX_SURFACES),
-        ("semi_aperture", C.c_float * MAX_SURFACES), ("coating_lambda0_nm", C.c_float * MAX_SURFACES),
-        ("ior", (C.c_float * MAX_SURFACES) * MAX_LAMBDA), ("lambda_nm", C.c_float * MAX_LAMBDA),
-        ("rgb_weight", (C.c_float * 3) * MAX_LAMBDA),
-        ("entrance_half_height", C.c_double), ("stop_half_height", C.c_double),
-        ("stop_half_height_neg", C.c_double),
-    ]
-
-
-class Light(C.Structure):
-    _fields_ = [("ns_x", C.c_double), ("ns_y", C.c_double), ("theta", C.c_float), ("radiance", C.c_float * 3)]
-
-
-class Params(C.Structure):
-    _fields_ = [
-        ("mode", C.c_int32), ("pair_set", C.c_int32), ("include_direct", C.c_int32), ("grid_n", C.c_int32),
-        ("width", C.c_int32), ("height", C.c_int32), ("precision", C.c_int32), ("splat", C.c_int32),
-        ("fixed_point_bits", C.c_int32), ("physical_backward", C.c_int32),
-        ("shard_index", C.c_int32), ("shard_count", C.c_int32),
-        ("px_per_unit", C.c_float), ("reserved", C.c_float * 3),
-    ]
-
-
-RAY_HIT_DTYPE = np.dtype([("x_s", "f8"), ("y_s", "f8"), ("x_ap", "f8"), ("y_ap", "f8"), ("px", "f8"),
-                          ("py", "f8"), ("weight", "f8"), ("flags", "u4"), ("pad", "u4")])
-REF_GHOST_DTYPE = np.dtype([("i", "i4"), ("j", "i4"), ("colour", "i4"), ("pad", "i4"), ("r1", "f8"),
-                            ("r2", "f8"), ("verts", "f4", (4, 2)), ("scale", "f4"), ("shift", "f4")])
-
-MODE_REF_QUADS, MODE_PARAXIAL_GRID, MODE_EXACT_GRID = 0, 1, 2
-PAIRS_REF, PAIRS_ALL = 0, 1
-F32x3, F64x3 = 0, 1
-FP32, FP64 = 0, 1
-SPLAT_NEAREST, SPLAT_BILINEAR = 0, 1
-RAY_MISSED, RAY_VIGNETTED, RAY_TIR, RAY_STOPPED, RAY_OFF_SENSOR = 1, 2, 4, 8, 16
-
-
-def make_light(ns_x, ns_y, theta=None, radiance=(1.0, 1.0, 1.0)):
-    """theta=None -> the reference's angle_to_sun = atan(ns_y/ns_x) (pathtracer.cpp:50)."""
-    lt = Light()
-    lt.ns_x, lt.ns_y = ns_x, ns_y
-    lt.theta = float(np.float32(np.arctan(ns_y / ns_x))) if theta is None else theta
-    lt.radiance[:] = radiance
-    return lt
-
-
-def make_params(mode, width, height, grid_n=0, pair_set=PAIRS_REF, precision=FP32, splat=SPLAT_BILINEAR,
-                include_direct=0, physical_backward=0, bits=0, px_per_unit=0.0, shard=(0, 0)):
-    p = Params()
-    p.mode, p.pair_set, p.include_direct, p.grid_n = mode, pair_set, include_direct, grid_n
-    p.width, p.height, p.precision, p.splat = width, height, precision, splat
-    p.fixed_point_bits, p.physical_backward = bits, physical_backward
-    p.shard_index, p.shard_count = shard
-    p.px_per_unit = px_per_unit
-    return p
-
-
-def lights_array(lights):
-    arr = (Light * len(lights))()
-    for k, lt in enumerate(lights):
-        arr[k] = lt
-    return arr
+# struct layouts / enums of include/lfb200.h are shared with the product's binding (the oracle
+# may depend on the product's declarations; the product never imports the oracle)
+from lens_flare_b200.capi import (  # noqa: E402,F401
+    F32x3, F64x3, FP32, FP64, MAX_LAMBDA, MAX_SURFACES, MODE_EXACT_GRID, MODE_PARAXIAL_GRID, MODE_REF_QUADS, PAIRS_ALL,
+    PAIRS_REF, RAY_HIT_DTYPE, RAY_MISSED, RAY_OFF_SENSOR, RAY_STOPPED, RAY_TIR, RAY_VIGNETTED, REF_GHOST_DTYPE,
+    SPLAT_BILINEAR, SPLAT_NEAREST, Lens, Light, Params, copy_params, lights_array, make_light, make_params)
 
 
 def _fp(a):

@@ -73,7 +73,10 @@ int lfo_builtin_lens(lfb_lens* L, int n_lambda, float coating_lambda0_nm) {
     }
     for (int l = 0; l < n_lambda; l++)
       for (int c = 0; c < 3; c++) L->rgb_weight[l][c] = (float)(w[l][c] / sum[c]);
-    /* n = A + B/lam^2 + C/lam^4 through the R,G,B anchors (lam in micrometres) */
+    /* n(lambda): piecewise two-term Cauchy n = A + B/lam^2 through the R,G,B anchors (linear in
+     * u = 1/lam^2 on [650,550] and [550,450] nm, each segment continued beyond its anchor).  The
+     * reference's three indices per glass are not consistent with one smooth 3-term Cauchy curve
+     * (it turns over below 450 nm); this form passes through them exactly and stays monotone. */
     for (int k = 0; k < 9; k++) {
       double u[3], n[3];
       for (int a = 0; a < 3; a++) {
@@ -81,14 +84,12 @@ int lfo_builtin_lens(lfb_lens* L, int n_lambda, float coating_lambda0_nm) {
         u[a] = 1.0 / (lm * lm);
         n[a] = k_n_rgb[a][k];
       }
-      /* Newton divided differences in u */
       double f01 = (n[1] - n[0]) / (u[1] - u[0]);
       double f12 = (n[2] - n[1]) / (u[2] - u[1]);
-      double f012 = (f12 - f01) / (u[2] - u[0]);
       for (int l = 0; l < n_lambda; l++) {
         double lm = (double)L->lambda_nm[l] * 1e-3;
         double x = 1.0 / (lm * lm);
-        L->ior[l][k] = (float)(n[0] + (x - u[0]) * (f01 + (x - u[1]) * f012));
+        L->ior[l][k] = (float)(x <= u[1] ? n[1] + (x - u[1]) * f01 : n[1] + (x - u[1]) * f12);
       }
     }
   }
@@ -651,6 +652,13 @@ static void render_job(const lfb_lens* L, const float* tex, int tw, int th, cons
 
 typedef struct { int light, i, j, lambda; } job_t;
 
+static int job_cost(const lfb_lens* L, const job_t* q) { /* ray-surface interactions per ray */
+  return q->i < 0 ? L->n_surfaces + 1 : 2 * (q->j - q->i) + L->n_surfaces + 1;
+}
+
+/* All jobs in (light, pair, lambda) order; with shard_count > 1 the list is put in
+ * longest-processing-time-first order (stable) and dealt round-robin: this shard keeps the
+ * jobs q with q % shard_count == shard_index. */
 static int list_jobs(const lfb_lens* L, const lfb_params* P, int n_lights, job_t** out) {
   int pairs[LFB_MAX_SURFACES * LFB_MAX_SURFACES][2];
   int np = list_pairs(L, P->pair_set, pairs);
@@ -664,6 +672,18 @@ static int list_jobs(const lfb_lens* L, const lfb_params* P, int n_lights, job_t
         J[n++] = q;
       }
     }
+  if (P->shard_count > 1) {
+    for (int a = 1; a < n; a++) { /* stable insertion sort, decreasing cost */
+      job_t q = J[a];
+      int b = a - 1;
+      while (b >= 0 && job_cost(L, &J[b]) < job_cost(L, &q)) { J[b + 1] = J[b]; b--; }
+      J[b + 1] = q;
+    }
+    int m = 0;
+    for (int q = 0; q < n; q++)
+      if (q % P->shard_count == P->shard_index) J[m++] = J[q];
+    n = m;
+  }
   *out = J;
   return n;
 }
