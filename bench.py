@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the lens-flare ghost path (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our sm_100a engine
+  python bench.py --impl reference [--gpus N] [--steps K] ...     the reference's CPU code (oracle/_ref)
+  N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A STEP is one flare frame of BASELINE config 2 per light: RGB (3 wavelengths), a 256x256 ray grid per
+ghost, every two-reflection ghost of the built-in lens (28 glass-glass pairs) plus the direct path,
+1920x1080 sensor, final_apertures/pentbig500_14.png at the stop, EXACT_GRID physics (sphere/plane
+intersection, vector Snell with n(lambda), Fresnel + quarter-wave coating at 550 nm, aperture lookup,
+bilinear fixed-point splat), FP32.  With N GPUs the frame has N suns (weak scaling: one light's worth of
+ghosts per GPU), the (light x pair x wavelength) jobs are dealt to ranks and the int64 sensor buffers are
+summed with ONE NCCL reduce to rank 0, which converts them to pixels.
+
+  value  ray-surface interactions / s, whole job, frame description resident in HBM, device-timed
+         (CUDA events on the launching stream, per step, L2 flushed between steps, max over ranks)
+  e2e    the same metric through the reference-facing call (lfb_render_ghosts: host buffers; the
+         aperture mask + job table go host->device and the Vector3D[] frame comes back every step)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# declared algorithmic cost of one ray-surface interaction in EXACT_GRID
+FLOP_PER_INTERACTION = 64.0
+MUFU_PER_INTERACTION = 3.0
+GRID_N, WIDTH, HEIGHT = 256, 1920, 1080
+COATING_NM = 550.0
+WORKLOAD = ("cfg2: RGB (3 wavelengths) x 256x256 ray grid per ghost x (28 two-reflection ghost pairs + direct path) per light, "
+            "1920x1080 sensor, pentbig500_14 aperture, EXACT_GRID (sphere/plane hit, Snell, Fresnel + 550 nm quarter-wave coating), "
+            "bilinear fixed-point splat")
+
+
+def sun_positions(n):
+    """Deterministic suns: the first is SURVEY 8d's (0.45, 0.55); more lights sit on a lattice in [0.1,0.9]^2
+    (never the exact screen centre: the reference NaNs there, pathtracer.cpp:414)."""
+    pts = [(0.45, 0.55)]
+    k = 0
+    while len(pts) < n:
+        gx, gy = k % 4, (k // 4) % 4
+        pts.append((0.15 + 0.23 * gx + 0.01 * (k // 16), 0.2 + 0.2 * gy))
+        k += 1
+    return pts[:n]
+
+
+def make_sun(x, y, **kw):
+    """A sun at normalised screen position (x, y) seen through a 50 x 35 degree camera: the physical off-axis angle
+    (capi.physical_theta), not the reference's screen-space atan(y/x) that kills every exactly-traced ray."""
+    from lens_flare_b200 import capi
+    return capi.make_light(x, y, theta=capi.physical_theta(x, y), **kw)
+
+
+def load_aperture():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "apertures.npz"))
+    return z["pentbig500_14"].astype(np.float32) * np.float32(1.0 / 255.0)
+
+
+class ClockSampler:
+    """Polls SM clock and throttle reasons of one GPU through NVML while the timed regions run."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception as exc:  # NVML missing: report that instead of inventing clocks
+            self.nv, self.err = None, str(exc)
+
+    def _run(self):
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        self._active.set()
+        return self
+
+    def __exit__(self, *a):
+        self._active.clear()
+
+    def report(self):
+        self._stop.set()
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable: " + self.err}
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm: the reference's own CPU code for this path, all host threads
+# ------------------------------------------------------------------------------------------------
+def reference_trace_step(ref, theta, threads):
+    """One step of the reference arm: trace_ray_auto_before/after (pathtracer.cpp:588-689) called per ray
+    and per axis over cfg2's grid (256^2 x 28 pairs x RGB), std::threads over ghosts.  -> (s, rays)"""
+    s, rays, _ = ref.time_trace_grid(GRID_N, theta, 3, 28, threads)
+    return s, rays
+
+
+def cpu_baseline_block(sample_steps=1):
+    """The CPU numbers reported beside the GPU line (rank 0, N = 1)."""
+    from lens_flare_b200 import capi
+    from oracle import bindings as ob
+    threads = os.cpu_count() or 1
+    lens = capi.builtin_lens(3, COATING_NM)
+    p = capi.make_params(capi.MODE_EXACT_GRID, WIDTH, HEIGHT, grid_n=GRID_N, pair_set=capi.PAIRS_ALL, include_direct=1)
+    _, inter_frame, _ = capi.count_work(lens, p, 1)
+    inter_pairs = inter_frame - 10 * 3 * GRID_N * GRID_N  # the reference has no direct path
+    theta = make_sun(0.45, 0.55).theta
+    out = {}
+    if os.path.exists(ob.REF_SO):
+        ref = ob.RefOracle()
+        best = min(reference_trace_step(ref, theta, threads)[0] for _ in range(max(1, sample_steps) + 1))
+        out.update(value=inter_pairs / best, unit="interactions/s", cores=threads, kind="reference",
+                   sample=f"trace_ray_auto_before/after per ray and axis over cfg2's grid (256^2 x 28 pairs x RGB = "
+                          f"{inter_pairs:.3g} interactions), {threads} std::threads, best of {max(1, sample_steps) + 1}",
+                   seconds=best)
+        tex = load_aperture()
+        s1, _ = ref.time_ghost_buffer(tex, WIDTH, HEIGHT, 0.45, 0.55, capi.make_light(0.45, 0.55).theta, 5)
+        out["reference_frame_ms_1thread"] = s1 * 1e3  # PathTracer::generate_ghost_buffer, 1080p (13 quads x RGB)
+    if os.path.exists(ob.PORT_SO) or not out:
+        if not os.path.exists(ob.PORT_SO):
+            ob.build(("port",))
+        port = ob.PortOracle()
+        tex = load_aperture()
+        s, _ = port.time_render(lens, tex, [make_sun(0.45, 0.55)], p, threads)
+        exact = dict(value=inter_frame / s, unit="interactions/s", cores=threads, kind="port",
+                     sample=f"oracle/lf_oracle.c EXACT_GRID, one full cfg2 frame ({inter_frame:.3g} interactions), {threads} pthreads",
+                     seconds=s, frame_ms=s * 1e3)
+        if out:
+            out["port_exact"] = exact
+        else:
+            out = exact
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from lens_flare_b200 import capi
+    from oracle import bindings as ob
+    threads = os.cpu_count() or 1
+    lens = capi.builtin_lens(3)
+    p = capi.make_params(capi.MODE_EXACT_GRID, WIDTH, HEIGHT, grid_n=GRID_N, pair_set=capi.PAIRS_ALL)
+    _, inter, _ = capi.count_work(lens, p, 1)
+    theta = make_sun(0.45, 0.55).theta
+    if os.path.exists(ob.REF_SO):
+        ref = ob.RefOracle()
+        kind = "reference"
+        step = lambda: reference_trace_step(ref, theta, threads)[0]  # noqa: E731
+        sample = (f"one step = trace_ray_auto_before/after per ray and axis over 256^2 x 28 pairs x RGB "
+                  f"({inter:.3g} interactions), {threads} std::threads")
+    else:
+        if not os.path.exists(ob.PORT_SO):
+            ob.build(("port",))
+        port = ob.PortOracle()
+        tex = load_aperture()
+        kind = "port"
+        pp = capi.copy_params(p, mode=capi.MODE_PARAXIAL_GRID, precision=capi.FP64)
+        step = lambda: port.time_render(lens, tex, [make_sun(0.45, 0.55)], pp, threads)[0]  # noqa: E731
+        sample = f"one step = oracle port PARAXIAL_GRID frame, 256^2 x 28 pairs x RGB, {threads} pthreads"
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    total = sum(times)
+    value = inter * args.steps / total
+    line = {
+        "impl": "reference", "metric": "ray_surface_interactions_per_s", "value": value, "unit": "interactions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD + " [reference arm: the reference's paraxial ABCD tracer on the same grid; it has no "
+                                          "exact physics and no direct path]"},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from lens_flare_b200 import capi, sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus} (one rank per GPU)")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    tex = load_aperture()
+    lens = capi.builtin_lens(3, COATING_NM)
+    eng = capi.Engine(local)
+    eng.set_lens(lens)
+    eng.set_aperture(tex)
+    n_lights = world
+    params = capi.make_params(capi.MODE_EXACT_GRID, WIDTH, HEIGHT, grid_n=GRID_N, pair_set=capi.PAIRS_ALL, include_direct=1,
+                              precision=capi.FP32, splat=capi.SPLAT_BILINEAR)
+    lights_a = [make_sun(x, y) for x, y in sun_positions(n_lights)]
+    lights_b = [make_sun(1.0 - x, y) for x, y in sun_positions(n_lights)]  # e2e alternates frames
+    rays_frame, inter_frame, jobs_frame = capi.count_work(lens, params, n_lights)
+    sh = sharding.ShardedFlare(eng, params, rank, world, dev)
+    _, inter_rank, jobs_rank = capi.count_work(lens, sh.params, n_lights)
+    out_dev = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(lights):
+        sh.render(lights, reduce_dst=0 if world > 1 else None)
+        if rank == 0:
+            sh.finalize(out_dev, capi.F32x3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    for _ in range(max(args.warmup, 3)):
+        step(lights_a)
+    barrier()
+    launches0 = eng.stats()["kernel_launches"]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    trace_ms = []
+    with clocks:
+        for k in range(args.steps):
+            flush.zero_()  # L2 flush between timed steps (outside the events)
+            if world > 1:
+                dist.barrier()
+            ev[k][0].record()
+            step(lights_a)
+            ev[k][1].record()
+            torch.cuda.synchronize()
+            trace_ms.append(eng.stats()["last_trace_ms"])
+    barrier()
+    launches = eng.stats()["kernel_launches"] - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms, sum(trace_ms) / len(trace_ms) * inter_frame / max(inter_rank, 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t[0])
+    value = inter_frame * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: the reference-facing call with host buffers, every step ------------------------
+    pinned_out = capi.PinnedArray((HEIGHT, WIDTH, 3), np.float64)  # HDRImageBuffer::data layout (Vector3D, 24 B)
+    pinned_tex = capi.PinnedArray(tex.shape, np.float32)
+    pinned_tex.array[...] = tex
+    host_out_t = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float64).pin_memory() if world > 1 else None
+    out64_dev = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def e2e_step(k):
+        lights = lights_a if k % 2 == 0 else lights_b
+        eng.set_aperture(pinned_tex.array)  # this step's input, host -> device
+        if world == 1:
+            eng.render_ghosts(lights, params, out=pinned_out.array, elem=capi.F64x3)  # blocking, frame lands in host memory
+        else:
+            sh.render(lights, reduce_dst=0)
+            if rank == 0:
+                sh.finalize(out64_dev, capi.F64x3)
+                host_out_t.copy_(out64_dev, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for k in range(max(args.warmup, 3)):
+        e2e_step(k)
+    barrier()
+    with clocks:
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            e2e_step(k)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t[0])
+    e2e_value = inter_frame * args.steps / e2e_s
+    job_bytes = 248 + 50 * 48  # sizeof(lfb::Job) + LFB_MAX_STEPS * sizeof(lfb::Step): re-uploaded when the lights change
+    h2d = tex.nbytes * world + jobs_frame * job_bytes
+    d2h = HEIGHT * WIDTH * 24
+
+    peaks = eng.probe_peaks() if rank == 0 else None
+    line = None
+    if rank == 0:
+        # roofline of the dominant kernel (trace_splat_kernel<float, EXACT_GRID>): scalar FP32 FMA / MUFU pipes
+        k_ms = sum(trace_ms) / len(trace_ms)
+        ach = inter_rank * FLOP_PER_INTERACTION / (k_ms * 1e-3)
+        mufu_ach = inter_rank * MUFU_PER_INTERACTION / (k_ms * 1e-3)
+        roofline = {
+            "bound": "fp32", "kernel": "xf32::exact_splat_kernel", "achieved": ach / 1e12, "peak": peaks["fp32_flops"] / 1e12,
+            "unit": "TFLOP/s", "frac": ach / peaks["fp32_flops"], "traffic": None,
+            "kernel_ms": k_ms, "interactions_per_launch": inter_rank, "flop_per_interaction": FLOP_PER_INTERACTION,
+            "peak_source": "measured live on this GPU by lfb_probe_peaks (register-only FFMA chains); MEASURED_PEAKS.json holds no "
+                           "FP32 figure. The trace is scalar FP32/MUFU math: neither 'hbm' nor 'tensor' bounds it",
+            "mufu": {"achieved_gops": mufu_ach / 1e9, "peak_gops": peaks["mufu_ops"] / 1e9, "frac": mufu_ach / peaks["mufu_ops"],
+                     "mufu_per_interaction": MUFU_PER_INTERACTION},
+            "sm_clock_mhz_during_probe": peaks["sm_clock_hz"] / 1e6,
+        }
+        line = {
+            "metric": "ray_surface_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "lights": n_lights, "sun": "ns=(0.45,0.55) through a 50x35 deg camera -> off-axis angle %.4f rad" % lights_a[0].theta, "jobs_per_frame": jobs_frame, "rays_per_frame": rays_frame,
+                       "interactions_per_frame": inter_frame, "l2": "flushed between timed steps (256 MiB memset outside the events)",
+                       "multi_gpu": "jobs (light x pair x wavelength) dealt LPT round-robin to ranks; one NCCL int64 sum-reduce to rank 0"},
+            "frame_ms_1080p": dev_ms / args.steps,
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_s / args.steps * 1e3, "api": "lfb_render_ghosts (F64x3, stride 24 = HDRImageBuffer layout)"
+                    if world == 1 else "ShardedFlare.render + reduce + finalize + D2H"},
+            "gpu_launches": int(launches),
+            "clocks": clocks.report(),
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_block()
+        print(json.dumps(line))
+    pinned_out.free()
+    pinned_tex.free()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,18 @@ def make_light(ns_x, ns_y, theta=None, radiance=(1.0, 1.0, 1.0)):
     return lt
 
 
+def physical_theta(ns_x, ns_y, hfov_deg=50.0, vfov_deg=35.0):
+    """Off-axis angle (radians) of a distant light seen at normalised screen position (ns_x, ns_y) by a camera with
+    the given fields of view: the inverse of Camera::analyze_world_coord (camera.cpp:245-273).  The reference feeds
+    its paraxial tracer atan(ns_y/ns_x) instead (pathtracer.cpp:50) -- a screen-space angle of up to 90 degrees that a
+    linear ABCD model tolerates but real refraction does not (almost every ray is vignetted or totally reflected);
+    the ray-grid modes therefore take the physical angle."""
+    import math
+    tx = (2.0 * ns_x - 1.0) * math.tan(0.5 * math.radians(hfov_deg))
+    ty = (2.0 * ns_y - 1.0) * math.tan(0.5 * math.radians(vfov_deg))
+    return float(np.float32(math.atan(math.hypot(tx, ty))))
+
+
 def make_params(mode, width, height, grid_n=0, pair_set=PAIRS_REF, precision=FP32, splat=SPLAT_BILINEAR,
                 include_direct=0, physical_backward=0, bits=0, px_per_unit=0.0, shard=(0, 0)):
     p = Params()

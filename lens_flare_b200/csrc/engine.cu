@@ -10,6 +10,7 @@
 // result is PathTracer::ghost_buffer (src/pathtracer/pathtracer.h:54).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -134,6 +135,10 @@ struct lfb_engine {
   int jobs_cap = 0, n_jobs = 0;
   std::vector<unsigned char> job_key;
   Job* d_dump_job = nullptr;
+  Step* d_progs = nullptr;   // FP32 EXACT_GRID step programs, LFB_MAX_STEPS per job
+  Step* h_progs = nullptr;   // pinned staging
+  Step* d_dump_prog = nullptr;
+  int patch = 4;             // rays per thread in pass 1 of the FP32 exact kernel (LFB_EXACT_PATCH=1|2|4)
   // owned buffers of the host-memory API
   unsigned long long* d_accum = nullptr;
   size_t accum_cap = 0;
@@ -192,7 +197,53 @@ FrameGeom make_geom(const lfb_engine* e, const lfb_params& P) {
   g.tiles_per_job = g.tiles_x * g.tiles_x;
   g.tex_w = e->tex_w; g.tex_h = e->tex_h;
   g.fp_scale = ldexp(1.0, P.fixed_point_bits > 0 ? P.fixed_point_bits : 40);
+  g.P = (float)e->lens.entrance_half_height; g.h_stop = (float)e->lens.stop_half_height;
+  g.patch = e->patch; g.pad = 0;
   return g;
+}
+
+// Flatten ghost (i, j) at wavelength lam into the FP32 step program (exact_f32.cuh): the surface sequence
+// forward 0..j-1, reflect at j, backward j-1..i+1, reflect at i, forward i+1..n-1, sensor plane (i < 0: the
+// direct path), with every ray-independent quantity of each step computed here, once.
+int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, Step* out) {
+  const int n = L.n_surfaces, stop = L.stop_index;
+  int ns = 0, prev = 0;
+  auto push = [&](int k, int op, bool forward) {
+    Step S;
+    memset(&S, 0, sizeof(S));
+    S.k = k;
+    S.dz = (float)(D.zv_d[prev] - D.zv_d[k]);
+    prev = k;
+    if (k == n) { S.op = STEP_SENSOR; out[ns++] = S; return; }
+    if (k == stop && op != STEP_REFLECT) { S.op = STEP_STOP; out[ns++] = S; return; }
+    S.c = L.curvature[k];
+    S.semi2 = L.semi_aperture[k] * L.semi_aperture[k];
+    const float na = k == 0 ? 1.f : L.ior[lam][k - 1], nb = L.ior[lam][k];
+    const float n0 = forward ? na : nb, n2 = forward ? nb : na;
+    S.n0 = n0; S.n2 = n2;
+    S.eta = n0 / n2; S.eta2 = S.eta * S.eta;
+    S.op = (op == STEP_REFRACT && n0 == n2) ? STEP_PASS : op;
+    const double lam0 = L.coating_lambda0_nm[k];
+    if (lam0 > 0 && n0 != n2) {
+      double n1 = sqrt((double)n0 * (double)n2);
+      if (n1 < 1.38) n1 = 1.38;  // MgF2 floor
+      S.n1 = (float)n1;
+      S.e1sq = (float)(((double)n0 / n1) * ((double)n0 / n1));
+      S.phase = (float)(3.14159265358979323846 * lam0 / (double)L.lambda_nm[lam]);  // 4 pi n1 d1 / lambda, d1 = lambda0 / (4 n1)
+    }
+    out[ns++] = S;
+  };
+  if (i < 0) {
+    for (int k = 0; k < n; k++) push(k, STEP_REFRACT, true);
+  } else {
+    for (int k = 0; k < j; k++) push(k, STEP_REFRACT, true);
+    push(j, STEP_REFLECT, true);
+    for (int k = j - 1; k > i; k--) push(k, STEP_REFRACT, false);
+    push(i, STEP_REFLECT, false);
+    for (int k = i + 1; k < n; k++) push(k, STEP_REFRACT, true);
+  }
+  push(n, STEP_SENSOR, true);
+  return ns;
 }
 
 // Frame constants of one job.  The libm calls (atan/cosf/sinf of frame constants,
@@ -225,17 +276,28 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
   if (n > e->jobs_cap) {
     if (e->d_jobs) CU(cudaFree(e->d_jobs));
     if (e->h_jobs) CU(cudaFreeHost(e->h_jobs));
-    e->d_jobs = nullptr; e->h_jobs = nullptr; e->jobs_cap = 0;
+    if (e->d_progs) CU(cudaFree(e->d_progs));
+    if (e->h_progs) CU(cudaFreeHost(e->h_progs));
+    e->d_jobs = nullptr; e->h_jobs = nullptr; e->d_progs = nullptr; e->h_progs = nullptr; e->jobs_cap = 0;
     CU(cudaMalloc((void**)&e->d_jobs, sizeof(Job) * (size_t)n));
     CU(cudaHostAlloc((void**)&e->h_jobs, sizeof(Job) * (size_t)n, cudaHostAllocDefault));
+    CU(cudaMalloc((void**)&e->d_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)n));
+    CU(cudaHostAlloc((void**)&e->h_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)n, cudaHostAllocDefault));
     e->jobs_cap = n;
   }
   // the previous frame's upload may still be reading h_jobs
   CU(cudaStreamSynchronize(e->stream));
-  for (int q = 0; q < n; q++) fill_job(e, P, lights[ids[q].light], ids[q], &e->h_jobs[q]);
+  const bool want_progs = P.mode == LFB_MODE_EXACT_GRID && P.precision == LFB_FP32;
+  for (int q = 0; q < n; q++) {
+    fill_job(e, P, lights[ids[q].light], ids[q], &e->h_jobs[q]);
+    if (want_progs)
+      e->h_jobs[q].n_steps = build_program(e->lens, e->dev_lens, ids[q].lambda, ids[q].i, ids[q].j, e->h_progs + (size_t)q * LFB_MAX_STEPS);
+  }
   e->n_jobs = n;
   if (n > 0) {
     CU(cudaMemcpyAsync(e->d_jobs, e->h_jobs, sizeof(Job) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    if (want_progs)
+      CU(cudaMemcpyAsync(e->d_progs, e->h_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)n, cudaMemcpyHostToDevice, e->stream));
     if (P.mode == LFB_MODE_PARAXIAL_GRID) {
       CU(launch_paraxial_setup(e->d_jobs, n, P.physical_backward, e->stream));
       e->launches++;
@@ -256,7 +318,7 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
   CU(cudaEventRecord(e->ev_trace0, e->stream));
   if (e->n_jobs > 0) {
     if (P.precision == LFB_FP64) CU(launch_trace_splat_f64(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
-    else CU(launch_trace_splat_f32(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
+    else CU(launch_trace_splat_f32(e->d_jobs, e->d_progs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
     e->launches++;
   }
   CU(cudaEventRecord(e->ev_trace1, e->stream));
@@ -330,6 +392,8 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_trace1);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_frame1);
   if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_dump_job, sizeof(Job));
+  if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_dump_prog, sizeof(Step) * LFB_MAX_STEPS);
+  if (const char* env = getenv("LFB_EXACT_PATCH")) e->patch = atoi(env);
   if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
   *out = e;
   return LFB_OK;
@@ -340,6 +404,8 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
+  cudaFree(e->d_progs); cudaFree(e->d_dump_prog);
+  if (e->h_progs) cudaFreeHost(e->h_progs);
   cudaFree(e->d_tex); cudaFree(e->d_jobs); cudaFree(e->d_dump_job); cudaFree(e->d_accum); cudaFree(e->d_out);
   cudaFree(e->d_hits); cudaFree(e->d_tris); cudaFree(e->d_ghosts); cudaFree(e->d_pairs); cudaFree(e->d_rgbw);
   if (e->h_jobs) cudaFreeHost(e->h_jobs);
@@ -597,14 +663,17 @@ extern "C" int lfb_dump_rays(lfb_engine* e, const lfb_light* light, const lfb_pa
   Job J;
   JobId id = {0, direct ? -1 : i, direct ? -1 : j, lambda};
   fill_job(e, *P, *light, id, &J);
+  Step prog[LFB_MAX_STEPS];
+  J.n_steps = build_program(e->lens, e->dev_lens, lambda, id.i, id.j, prog);
   CU(cudaMemcpyAsync(e->d_dump_job, &J, sizeof(Job), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->d_dump_prog, prog, sizeof(Step) * (size_t)J.n_steps, cudaMemcpyHostToDevice, e->stream));
   if (P->mode == LFB_MODE_PARAXIAL_GRID) {
     CU(launch_paraxial_setup(e->d_dump_job, 1, P->physical_backward, e->stream));
     e->launches++;
   }
   const FrameGeom g = make_geom(e, *P);
   if (P->precision == LFB_FP64) CU(launch_trace_dump_f64(e->d_dump_job, g, P->mode, e->d_tex, e->d_hits, e->stream));
-  else CU(launch_trace_dump_f32(e->d_dump_job, g, P->mode, e->d_tex, e->d_hits, e->stream));
+  else CU(launch_trace_dump_f32(e->d_dump_job, e->d_dump_prog, g, P->mode, e->d_tex, e->d_hits, e->stream));
   e->launches++;
   CU(cudaMemcpyAsync(out, e->d_hits, sizeof(lfb_ray_hit) * n, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));

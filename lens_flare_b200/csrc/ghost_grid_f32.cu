@@ -1,20 +1,35 @@
-// ghost_grid_f32.cu -- FP32 instantiation of the ray-grid kernels (the throughput path).
-// Compiled with FMA contraction on: the trace is FFMA/MUFU-bound scalar math.
+// ghost_grid_f32.cu -- FP32 kernels of the ray-grid path (the throughput path), FMA contraction on.
+//   EXACT_GRID     exact_f32.cuh   step programs, fast scalar math, two passes with survivor compaction,
+//                                  shared-memory sensor tile
+//   PARAXIAL_GRID  ghost_grid_impl.cuh instantiated for float (a 2x2 matrix apply per ray)
 #define LFB_TU f32
 #include "ghost_grid_impl.cuh"
+#include "exact_f32.cuh"
 
 namespace lfb {
 
 cudaError_t upload_lens_f32(const DevLens& h, cudaStream_t s) {
   return cudaMemcpyToSymbolAsync(f32::c_lens, &h, sizeof(DevLens), 0, cudaMemcpyHostToDevice, s);
 }
-cudaError_t launch_trace_splat_f32(const Job* jobs, int n_jobs, const FrameGeom& g, int mode, const float* tex,
-                                   unsigned long long* accum, cudaStream_t s) {
-  return f32::launch_trace_splat_t<float>(jobs, n_jobs, g, mode, tex, accum, s);
+
+cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_jobs, const FrameGeom& g, int mode,
+                                   const float* tex, unsigned long long* accum, cudaStream_t s) {
+  if (n_jobs <= 0) return cudaSuccess;
+  if (mode == LFB_MODE_PARAXIAL_GRID) return f32::launch_trace_splat_t<float>(jobs, n_jobs, g, mode, tex, accum, s);
+  auto blocks = [&](int rx, int ry) {
+    return (unsigned)n_jobs * (unsigned)(((g.N + 16 * rx - 1) / (16 * rx)) * ((g.N + 16 * ry - 1) / (16 * ry)));
+  };
+  if (g.patch >= 4) xf32::exact_splat_kernel<2, 2><<<blocks(2, 2), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
+  else if (g.patch >= 2) xf32::exact_splat_kernel<2, 1><<<blocks(2, 1), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
+  else xf32::exact_splat_kernel<1, 1><<<blocks(1, 1), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
+  return cudaGetLastError();
 }
-cudaError_t launch_trace_dump_f32(const Job* job, const FrameGeom& g, int mode, const float* tex, lfb_ray_hit* out,
-                                  cudaStream_t s) {
-  return f32::launch_trace_dump_t<float>(job, g, mode, tex, out, s);
+
+cudaError_t launch_trace_dump_f32(const Job* job, const Step* prog, const FrameGeom& g, int mode, const float* tex,
+                                  lfb_ray_hit* out, cudaStream_t s) {
+  if (mode == LFB_MODE_PARAXIAL_GRID) return f32::launch_trace_dump_t<float>(job, g, mode, tex, out, s);
+  xf32::exact_dump_kernel<<<(unsigned)g.tiles_per_job, xf32::kThreads, 0, s>>>(job, prog, g, tex, out);
+  return cudaGetLastError();
 }
 
 }  // namespace lfb

@@ -28,7 +28,7 @@ struct DevLens {
 // paraxial matrices, which the device set-up kernel writes (paraxial_setup_kernel).
 struct Job {
   int light, i, j, lambda;  // i = j = -1: direct path
-  int n_cross, pad0, pad1, pad2;
+  int n_cross, n_steps, pad1, pad2;  // n_steps: length of the job's FP32 step program
   float theta;
   float pad3;
   double chan[3];           // radiance * rgb_weight * ray area * px_per_unit^2
@@ -43,6 +43,19 @@ struct FrameGeom {
   int tiles_x, tiles_per_job;
   int tex_w, tex_h;
   double fp_scale;  // 2^fixed_point_bits
+  float P, h_stop;  // entrance half height, stop half height
+  int patch, pad;   // FP32 EXACT_GRID: rays per thread in pass 1 (1, 2 or 4)
+};
+
+// FP32 EXACT_GRID step program (exact_f32.cuh): a ghost flattened into straight-line steps with every
+// ray-independent quantity precomputed on the host.  48 bytes = 3 x float4.
+enum StepOp { STEP_REFRACT = 0, STEP_REFLECT = 1, STEP_PASS = 2, STEP_STOP = 3, STEP_SENSOR = 4 };
+#define LFB_MAX_STEPS (3 * LFB_MAX_SURFACES + 2)
+struct Step {
+  float c, dz, semi2, eta;   // curvature; z of the previous vertex minus z of this one; clear radius^2; n0/n2
+  float eta2, n0, n2, n1;    // (n0/n2)^2; indices before/after along the ray; film index (0 = bare)
+  float e1sq, phase;         // (n0/n1)^2; pi * lambda0 / lambda
+  int op, k;                 // StepOp; surface index (k = n_surfaces for the sensor)
 };
 
 // REF_QUADS: one rasterisable triangle of a ghost quad (pathtracer.cpp:346-410 state
@@ -71,12 +84,12 @@ cudaError_t upload_lens_ref(const DevLens& h, cudaStream_t s);
 
 // kernels' host launchers (definitions in the .cu files)
 cudaError_t launch_paraxial_setup(Job* jobs, int n_jobs, int physical_backward, cudaStream_t s);
-cudaError_t launch_trace_splat_f32(const Job* jobs, int n_jobs, const FrameGeom& g, int mode, const float* tex,
-                                   unsigned long long* accum, cudaStream_t s);
+cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_jobs, const FrameGeom& g, int mode,
+                                   const float* tex, unsigned long long* accum, cudaStream_t s);
 cudaError_t launch_trace_splat_f64(const Job* jobs, int n_jobs, const FrameGeom& g, int mode, const float* tex,
                                    unsigned long long* accum, cudaStream_t s);
-cudaError_t launch_trace_dump_f32(const Job* job, const FrameGeom& g, int mode, const float* tex, lfb_ray_hit* out,
-                                  cudaStream_t s);
+cudaError_t launch_trace_dump_f32(const Job* job, const Step* prog, const FrameGeom& g, int mode, const float* tex,
+                                  lfb_ray_hit* out, cudaStream_t s);
 cudaError_t launch_trace_dump_f64(const Job* job, const FrameGeom& g, int mode, const float* tex, lfb_ray_hit* out,
                                   cudaStream_t s);
 cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,

@@ -16,16 +16,19 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ sink,
   float x[kChains];
 #pragma unroll
   for (int c = 0; c < kChains; c++) x[c] = (float)(threadIdx.x + c);
-  const long long t0 = clock64();
-#pragma unroll 4
+  // the chains depend on t0 and t1 depends on the chains, so the compiler cannot move work across the clock reads
+  long long t0, t1;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0));
+  x[0] += (float)(t0 >> 63);
+#pragma unroll 16
   for (int it = 0; it < kIters; it++) {
 #pragma unroll
     for (int c = 0; c < kChains; c++) x[c] = fmaf(x[c], a, b);
   }
-  const long long t1 = clock64();
   float s = 0;
 #pragma unroll
   for (int c = 0; c < kChains; c++) s += x[c];
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1) : "f"(s) : "memory");
   if (s == 12345.678f) sink[0] = s;  // keeps the chains alive; never true in practice
   if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
 }
@@ -34,16 +37,18 @@ __global__ void __launch_bounds__(256) mufu_peak_kernel(float* __restrict__ sink
   float x[kChains];
 #pragma unroll
   for (int c = 0; c < kChains; c++) x[c] = 1.5f + (float)(threadIdx.x + c);
-  const long long t0 = clock64();
-#pragma unroll 4
+  long long t0, t1;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0));
+  x[0] += (float)(t0 >> 63);
+#pragma unroll 16
   for (int it = 0; it < kIters; it++) {
 #pragma unroll
     for (int c = 0; c < kChains; c++) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
   }
-  const long long t1 = clock64();
   float s = 0;
 #pragma unroll
   for (int c = 0; c < kChains; c++) s += x[c];
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1) : "f"(s) : "memory");
   if (s == 12345.678f) sink[0] = s;
   if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
 }

@@ -153,11 +153,16 @@ class PathTracer:
                 self.axis_ray = (ns_x, ns_y)
 
     def _lfb_lights(self):
-        if self.mode == capi.MODE_REF_QUADS or not self.flare_origins:
+        if self.mode == capi.MODE_REF_QUADS:
             return [capi.make_light(self.axis_ray[0], self.axis_ray[1], theta=self.angle_to_sun)]
+        if not self.flare_origins:  # axis_ray set by hand, as the reference's GUI code paths can
+            self.flare_origins, self.flare_radiance = [self.axis_ray], [np.ones(3)]
         out = []
         for (nx, ny), rad in zip(self.flare_origins, self.flare_radiance):
-            theta = float(np.float32(math.atan(ny / nx))) if nx != 0 else float(np.float32(math.pi / 2))
+            if self.mode == capi.MODE_EXACT_GRID:  # real refraction needs the real off-axis angle
+                theta = capi.physical_theta(nx, ny, self.camera.hFov, self.camera.vFov)
+            else:  # the reference's angle_to_sun (pathtracer.cpp:50)
+                theta = float(np.float32(math.atan(ny / nx))) if nx != 0 else float(np.float32(math.pi / 2))
             out.append(capi.make_light(nx, ny, theta=theta, radiance=tuple(float(v) for v in rad)))
         return out
 
