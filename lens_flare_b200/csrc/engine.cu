@@ -138,7 +138,7 @@ struct lfb_engine {
   Step* d_progs = nullptr;   // FP32 EXACT_GRID step programs, LFB_MAX_STEPS per job
   Step* h_progs = nullptr;   // pinned staging
   Step* d_dump_prog = nullptr;
-  int patch = 4;             // rays per thread in pass 1 of the FP32 exact kernel (LFB_EXACT_PATCH=1|2|4)
+  int patch = 2;             // rays per thread in pass 1 of the FP32 exact kernel (LFB_EXACT_PATCH=1|2|4)
   // owned buffers of the host-memory API
   unsigned long long* d_accum = nullptr;
   size_t accum_cap = 0;
@@ -214,6 +214,8 @@ int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, St
     S.k = k;
     S.dz = (float)(D.zv_d[prev] - D.zv_d[k]);
     prev = k;
+    S.eta = S.eta2 = 1.f;
+    S.semi2 = INFINITY;  // the stop and the sensor are unbounded planes (the mask bounds the stop)
     if (k == n) { S.op = STEP_SENSOR; out[ns++] = S; return; }
     if (k == stop && op != STEP_REFLECT) { S.op = STEP_STOP; out[ns++] = S; return; }
     S.c = L.curvature[k];

@@ -12,6 +12,9 @@
 //  * FAST SCALAR MATH.  rcp.approx / sqrt.approx / cos.approx (one MUFU each) instead of the IEEE
 //    division and square root sequences (MUFU + FCHK + slow-path branch + Newton FFMAs), and Fresnel /
 //    thin-film reflectances restructured to ONE reciprocal per surface.
+//  * MIRROR SYMMETRY.  A distant light's bundle and the lens are symmetric about the meridional plane:
+//    ray (x, -y) is the mirror image of ray (x, y).  One trace serves both; only the (asymmetric)
+//    aperture mask is looked up twice.  Half the grid is traced, every ray is still deposited.
 //  * TWO PASSES WITH SURVIVOR COMPACTION.  Most rays of a bundle die (vignetted, total internal
 //    reflection, blocked by the aperture mask) and carry no energy.  Pass 1 traces geometry only and
 //    queues the survivors of the CTA's ray patch (with their sensor pixel) in shared memory; pass 2
@@ -72,11 +75,6 @@ __device__ __forceinline__ float reflectance(const Step& S, float c0, float c2) 
   return 0.5f * fmaf(Ns, Dp, Np * Ds) * frcp(Ds * Dp);
 }
 
-struct RayOut {
-  float xs, ys, xa, ya, w;
-  unsigned flags;
-};
-
 struct MaskGeom {
   const float* tex;
   int tw, th;
@@ -89,62 +87,74 @@ __device__ __forceinline__ float mask_lookup(const MaskGeom& M, float xa, float 
   return __ldg(M.tex + (int)fv * M.tw + (int)fu);
 }
 
-// Trace one ray through a step program.  WEIGHTS = false: geometry only (w = 1 if the ray survives
-// every step with a non-zero mask, else 0).  KEEP_GOING = true (dump instrument): rays stopped by the
-// mask continue with weight 0 so that their positions stay comparable with the oracle.
-template <bool WEIGHTS, bool KEEP_GOING>
+// What one traced ray yields.  The bundle of a distant light is mirror-symmetric about the meridional
+// (x-z) plane and so is the lens: ray (x, -y) is the mirror image of ray (x, y) -- same path, same
+// incidence angles, same Fresnel weights, sensor point (xs, -ys).  Only the aperture mask is not
+// symmetric, so ONE trace serves both rays and carries two mask weights: wa for (x, y), wb for (x, -y).
+struct RayOut {
+  float xs, ys, xa, ya;  // sensor point and last stop crossing of the traced ray (x, y)
+  float wa, wb;          // weights of the ray and of its mirror image (Fresnel product x mask products)
+  unsigned flags;        // FLAGS variant only
+};
+
+// Trace one ray through a step program.
+//   WEIGHTS    accumulate the Fresnel / coating weight (else geometry + mask only)
+//   MIRROR     also look the mask up at (xa, -ya) for the mirror-image ray
+//   FLAGS      parity-instrument variant: classify the death (missed / vignetted / TIR), and let rays the
+//              mask stopped continue with weight 0 so that their positions stay comparable with the oracle
+// Every step runs the same straight-line code (planes are c = 0 surfaces with an infinite clear radius); a
+// missed surface or a total internal reflection turns the state into NaNs, which the next clear-radius
+// test catches, so the throughput variants carry ONE death test per step.
+template <bool WEIGHTS, bool MIRROR, bool FLAGS>
 __device__ __forceinline__ bool trace(const Step* __restrict__ prog, int n_steps, const MaskGeom& M, float x, float y,
                                       float sin_t, float cos_t, RayOut& o) {
-  float ox = x, oy = y, oz = 0.f, dx = sin_t, dy = 0.f, dz = cos_t, w = 1.f;
-  o.flags = 0;
-  o.xa = o.ya = CUDART_NAN_F;
+  float ox = x, oy = y, oz = 0.f, dx = sin_t, dy = 0.f, dz = cos_t, w = 1.f, ma = 1.f, mb = 1.f;
+  if (FLAGS) { o.flags = 0; o.xa = o.ya = CUDART_NAN_F; }
+#pragma unroll 1
   for (int s = 0; s < n_steps; s++) {
-    const Step S = prog[s];
-    const float px = ox, py = oy, pz = oz + S.dz;
-    if (S.op >= STEP_STOP) {  // planes perpendicular to the axis: the stop and the sensor
-      const float t = -pz * frcp(dz);
-      ox = fmaf(t, dx, px); oy = fmaf(t, dy, py); oz = 0.f;
-      if (S.op == STEP_STOP) {
-        o.xa = ox; o.ya = oy;
-        const float m = mask_lookup(M, ox, oy);
-        w *= m;
-        if (m == 0.f) {
-          o.flags |= LFB_RAY_STOPPED;
-          if (!KEEP_GOING) { o.w = 0.f; return false; }
-        }
-      }
-      continue;
-    }
-    const float c = S.c;
-    const float pd = fmaf(px, dx, fmaf(py, dy, pz * dz));
-    const float pp = fmaf(px, px, fmaf(py, py, pz * pz));
+    const Step& S = prog[s];
+    const float c = S.c, eta = S.eta;
+    const int op = S.op;
+    const float pz = oz + S.dz;
+    const float pd = fmaf(ox, dx, fmaf(oy, dy, pz * dz));
+    const float pp = fmaf(ox, ox, fmaf(oy, oy, pz * pz));
     const float B = fmaf(c, pd, -dz);
     const float Cq = fmaf(c, pp, -2.f * pz);
     const float disc = fmaf(B, B, -c * Cq);
-    if (disc < 0.f) { o.flags |= LFB_RAY_MISSED; o.w = 0.f; return false; }
+    if (FLAGS && disc < 0.f) { o.flags |= LFB_RAY_MISSED; return false; }
     const float t = -Cq * frcp(B + copysignf(fsqrt(disc), B));
-    const float hx = fmaf(t, dx, px), hy = fmaf(t, dy, py), hz = fmaf(t, dz, pz);
-    ox = hx; oy = hy; oz = hz;
-    if (fmaf(hx, hx, hy * hy) > S.semi2) { o.flags |= LFB_RAY_VIGNETTED; o.w = 0.f; return false; }
-    if (S.op == STEP_PASS) continue;
-    const float nx = -c * hx, ny = -c * hy, nz = fmaf(-c, hz, 1.f);
+    ox = fmaf(t, dx, ox); oy = fmaf(t, dy, oy); oz = fmaf(t, dz, pz);
+    if (!(fmaf(ox, ox, oy * oy) <= S.semi2)) {  // outside the clear aperture, or NaN from a miss / TIR upstream
+      if (FLAGS) o.flags |= LFB_RAY_VIGNETTED;
+      return false;
+    }
+    if (op >= STEP_PASS) {  // no change of direction: identical media, the stop, the sensor
+      if (op == STEP_STOP) {
+        const float m = mask_lookup(M, ox, oy);
+        ma *= m;
+        if (MIRROR) mb *= mask_lookup(M, ox, -oy);
+        if (FLAGS) { o.xa = ox; o.ya = oy; if (m == 0.f) o.flags |= LFB_RAY_STOPPED; }
+        else if (MIRROR ? (ma == 0.f && mb == 0.f) : (ma == 0.f)) return false;
+      }
+      continue;
+    }
+    const float nx = -c * ox, ny = -c * oy, nz = fmaf(-c, oz, 1.f);
     const float nd = fmaf(nx, dx, fmaf(ny, dy, nz * dz));
     const float c0 = fabsf(nd);
     const float k2 = fmaf(-S.eta2, fmaf(-c0, c0, 1.f), 1.f);
-    if (S.op == STEP_REFLECT) {
-      const float m2 = -2.f * nd;
-      dx = fmaf(m2, nx, dx); dy = fmaf(m2, ny, dy); dz = fmaf(m2, nz, dz);
-      if (WEIGHTS) w *= (k2 < 0.f) ? 1.f : reflectance(S, c0, fsqrt(k2));
-    } else {
-      if (k2 < 0.f) { o.flags |= LFB_RAY_TIR; o.w = 0.f; return false; }
-      const float c2 = fsqrt(k2);
-      // d' = eta d + (eta c0 - c2) N with N = -sign(nd) n the normal facing the ray: flip the factor's sign when nd > 0
-      const float g = __int_as_float(__float_as_int(fmaf(S.eta, c0, -c2)) ^ (~__float_as_int(nd) & 0x80000000));
-      dx = fmaf(S.eta, dx, g * nx); dy = fmaf(S.eta, dy, g * ny); dz = fmaf(S.eta, dz, g * nz);
-      if (WEIGHTS) w *= 1.f - reflectance(S, c0, c2);
+    const float c2 = fsqrt(k2);  // NaN beyond the critical angle
+    const bool refl = op == STEP_REFLECT;
+    if (FLAGS && !refl && k2 < 0.f) { o.flags |= LFB_RAY_TIR; return false; }
+    // refract: d' = eta d + (eta c0 - c2) N with N = -sign(nd) n the normal facing the ray;  reflect: d' = d - 2 nd n
+    const float g = __int_as_float(__float_as_int(fmaf(eta, c0, -c2)) ^ (~__float_as_int(nd) & 0x80000000));
+    const float alpha = refl ? 1.f : eta, beta = refl ? -2.f * nd : g;
+    dx = fmaf(alpha, dx, beta * nx); dy = fmaf(alpha, dy, beta * ny); dz = fmaf(alpha, dz, beta * nz);
+    if (WEIGHTS) {
+      const float R = (k2 < 0.f) ? 1.f : reflectance(S, c0, c2);
+      w *= refl ? R : 1.f - R;
     }
   }
-  o.xs = ox; o.ys = oy; o.w = w;
+  o.xs = ox; o.ys = oy; o.wa = w * ma; o.wb = w * mb;
   return true;
 }
 
@@ -160,23 +170,75 @@ __device__ __forceinline__ void to_pixel(const PixMap& P, float xs, float ys, fl
 constexpr int kThreads = 256;
 constexpr int kTilePx = 256;  // shared-memory sensor tile capacity (pixels)
 
-// One CTA = a (16*RX) x (16*RY) patch of one ghost's ray grid; RPT = RX*RY rays per thread in pass 1.
+// Footprint of one splat (bilinear: 2x2 taps around (px, py) - 0.5; nearest: the pixel holding (px, py)),
+// clipped to the sensor.  False when nothing lands (or px/py is NaN).
+__device__ __forceinline__ bool footprint(bool bilinear, float px, float py, int W, int H, int& x0, int& y0, int& x1, int& y1) {
+  if (bilinear) {
+    const float fx = floorf(px - 0.5f), fy = floorf(py - 0.5f);
+    if (!(fx >= -1.f && fx < (float)W && fy >= -1.f && fy < (float)H)) return false;
+    x0 = max((int)fx, 0); y0 = max((int)fy, 0); x1 = min((int)fx + 1, W - 1); y1 = min((int)fy + 1, H - 1);
+  } else {
+    const float fx = floorf(px), fy = floorf(py);
+    if (!(fx >= 0.f && fx < (float)W && fy >= 0.f && fy < (float)H)) return false;
+    x0 = x1 = (int)fx; y0 = y1 = (int)fy;
+  }
+  return true;
+}
+
+struct SplatCtx {
+  unsigned long long* tile;   // shared-memory tile (or nullptr: straight to global)
+  unsigned long long* accum;  // global sensor accumulators
+  int tx0, ty0, tw, W, H;
+  float ch0, ch1, ch2;        // radiance * rgb_weight * ray area * 2^bits
+  bool bilinear;
+};
+
+__device__ __forceinline__ void splat(const SplatCtx& C, float px, float py, float w) {
+  int ix, iy, ntap;
+  float wt[4];
+  if (C.bilinear) {
+    const float qx = px - 0.5f, qy = py - 0.5f;
+    const float fx0 = floorf(qx), fy0 = floorf(qy);
+    const float fx = qx - fx0, fy = qy - fy0;
+    ix = (int)fx0; iy = (int)fy0; ntap = 4;
+    wt[0] = w * ((1.f - fx) * (1.f - fy)); wt[1] = w * (fx * (1.f - fy));
+    wt[2] = w * ((1.f - fx) * fy); wt[3] = w * (fx * fy);
+  } else {
+    ix = (int)floorf(px); iy = (int)floorf(py); ntap = 1;
+    wt[0] = w;
+  }
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    if (t >= ntap) break;
+    const int jx = ix + (t & 1), jy = iy + (t >> 1);
+    if (jx < 0 || jx >= C.W || jy < 0 || jy >= C.H) continue;
+    const long long q0 = __float2ll_rn(wt[t] * C.ch0), q1 = __float2ll_rn(wt[t] * C.ch1), q2 = __float2ll_rn(wt[t] * C.ch2);
+    unsigned long long* dst = C.tile ? C.tile + 3 * ((jy - C.ty0) * C.tw + (jx - C.tx0)) : C.accum + 3 * ((size_t)jx + (size_t)jy * C.W);
+    if (q0) atomicAdd(dst + 0, (unsigned long long)q0);
+    if (q1) atomicAdd(dst + 1, (unsigned long long)q1);
+    if (q2) atomicAdd(dst + 2, (unsigned long long)q2);
+  }
+}
+
+// One CTA = a (16*RX) x (16*RY) patch of the UPPER HALF of one ghost's ray grid (rows with y >= 0; each
+// traced ray also stands for its mirror image in the lower half); RPT = RX*RY rays per thread in pass 1.
 template <int RX, int RY>
 __global__ void __launch_bounds__(kThreads) exact_splat_kernel(const Job* __restrict__ jobs, const Step* __restrict__ progs,
                                                                FrameGeom g, const float* __restrict__ tex,
                                                                unsigned long long* __restrict__ accum) {
-  constexpr int RPT = RX * RY, PATCH = RPT * kThreads;
+  constexpr int RPT = RX * RY, PATCH = RPT * kThreads, PW = 16 * RX, PH = 16 * RY;
   __shared__ Step s_prog[LFB_MAX_STEPS];
   __shared__ unsigned long long s_tile[kTilePx * 3];
-  __shared__ float s_qx[PATCH], s_qy[PATCH];
-  __shared__ unsigned short s_qid[PATCH];
+  __shared__ float4 s_qp[PATCH];         // survivor queue: (pxA, pyA, pxB, pyB)
+  __shared__ unsigned short s_qid[PATCH];  // ray id within the patch | mirror-alive bits
   __shared__ int s_count, s_bbox[4];
 
-  const int patches_x = (g.N + 16 * RX - 1) / (16 * RX);
-  const int patches_per_job = patches_x * ((g.N + 16 * RY - 1) / (16 * RY));
+  const int half_rows = (g.N + 1) / 2;  // rows b' = 0 .. half_rows-1 stand for b = N-1-b' (y > 0) and b' itself (y < 0)
+  const int patches_x = (g.N + PW - 1) / PW;
+  const int patches_per_job = patches_x * ((half_rows + PH - 1) / PH);
   const int job_id = blockIdx.x / patches_per_job;
   const int patch = blockIdx.x - job_id * patches_per_job;
-  const int a0 = (patch % patches_x) * (16 * RX), b0 = (patch / patches_x) * (16 * RY);
+  const int a0 = (patch % patches_x) * PW, b0 = (patch / patches_x) * PH;
   const Job& J = jobs[job_id];
   const int n_steps = J.n_steps;
   const int tid = threadIdx.x;
@@ -203,43 +265,43 @@ __global__ void __launch_bounds__(kThreads) exact_splat_kernel(const Job* __rest
   PM.sx = (float)J.sx; PM.sy = (float)J.sy; PM.cs = (float)J.cs; PM.sn = (float)J.sn; PM.ppu = (float)J.ppu;
   const bool bilinear = g.splat == LFB_SPLAT_BILINEAR;
 
-  // ---- pass 1: geometry only; queue the survivors with their sensor pixel ---------------------
+  // ---- pass 1: geometry + mask only; queue the survivors with their sensor pixels -----------------
   int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
 #pragma unroll 1
   for (int r = 0; r < RPT; r++) {
     const int la = (tid & 15) + 16 * (r % RX), lb = (tid >> 4) + 16 * (r / RX);
-    const int a = a0 + la, b = b0 + lb;
-    bool live = a < g.N && b < g.N;
-    float px = 0.f, py = 0.f;
-    int ix0 = 0, iy0 = 0, ix1 = 0, iy1 = 0;
-    if (live) {
+    const int a = a0 + la, bp = b0 + lb;  // bp: row of the half grid
+    const int b = g.N - 1 - bp;
+    unsigned bits = 0;  // 1: the traced ray lands, 2: its mirror image lands
+    float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a < g.N && bp < half_rows) {
       RayOut o;
-      live = trace<false, false>(s_prog, n_steps, M, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o);
-      if (live) {
-        to_pixel(PM, o.xs, o.ys, px, py);
-        if (bilinear) {
-          const float fx = floorf(px - 0.5f), fy = floorf(py - 0.5f);
-          live = fx >= -1.f && fx < (float)g.W && fy >= -1.f && fy < (float)g.H;  // false for NaN
-          ix0 = max((int)fx, 0); iy0 = max((int)fy, 0);
-          ix1 = min((int)fx + 1, g.W - 1); iy1 = min((int)fy + 1, g.H - 1);
-        } else {
-          const float fx = floorf(px), fy = floorf(py);
-          live = fx >= 0.f && fx < (float)g.W && fy >= 0.f && fy < (float)g.H;
-          ix0 = ix1 = (int)fx; iy0 = iy1 = (int)fy;
+      if (trace<false, true, false>(s_prog, n_steps, M, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o)) {
+        int x0, y0, x1, y1;
+        if (o.wa > 0.f) {
+          to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
+          if (footprint(bilinear, pp.x, pp.y, g.W, g.H, x0, y0, x1, y1)) {
+            bits |= 1; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+          }
+        }
+        if (o.wb > 0.f && b != bp) {  // b == bp: the middle row of an odd grid is its own mirror image
+          to_pixel(PM, o.xs, -o.ys, pp.z, pp.w);
+          if (footprint(bilinear, pp.z, pp.w, g.W, g.H, x0, y0, x1, y1)) {
+            bits |= 2; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+          }
         }
       }
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, live);
+    const unsigned ballot = __ballot_sync(0xffffffffu, bits != 0);
     if (ballot) {
       const int lane = tid & 31;
       int base = 0;
       if (lane == 0) base = atomicAdd(&s_count, __popc(ballot));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (live) {
+      if (bits) {
         const int slot = base + __popc(ballot & ((1u << lane) - 1u));
-        s_qid[slot] = (unsigned short)(lb * (16 * RX) + la);
-        s_qx[slot] = px; s_qy[slot] = py;
-        bx0 = min(bx0, ix0); by0 = min(by0, iy0); bx1 = max(bx1, ix1); by1 = max(by1, iy1);
+        s_qid[slot] = (unsigned short)((lb * PW + la) | (bits << 14));
+        s_qp[slot] = pp;
       }
     }
   }
@@ -252,57 +314,39 @@ __global__ void __launch_bounds__(kThreads) exact_splat_kernel(const Job* __rest
   __syncthreads();
   const int count = s_count;
   if (count == 0) return;
-  const int tx0 = s_bbox[0], ty0 = s_bbox[1];
-  const int tw = s_bbox[2] - tx0 + 1, th = s_bbox[3] - ty0 + 1;
-  const bool use_tile = tw * th <= kTilePx;
+  SplatCtx C;
+  C.tx0 = s_bbox[0]; C.ty0 = s_bbox[1];
+  C.tw = s_bbox[2] - C.tx0 + 1;
+  const int th = s_bbox[3] - C.ty0 + 1;
+  const bool use_tile = C.tw * th <= kTilePx;
+  C.tile = use_tile ? s_tile : nullptr;
+  C.accum = accum; C.W = g.W; C.H = g.H; C.bilinear = bilinear;
   if (use_tile) {
-    for (int q = tid; q < tw * th * 3; q += kThreads) s_tile[q] = 0ull;
+    for (int q = tid; q < C.tw * th * 3; q += kThreads) s_tile[q] = 0ull;
     __syncthreads();
   }
 
-  // ---- pass 2: survivors only, dense warps: full trace with Fresnel / coating weights -----------
+  // ---- pass 2: survivors only, dense warps: full trace with Fresnel / coating weights ---------------
   const float scale = (float)g.fp_scale;
-  const float ch0 = (float)J.chan[0] * scale, ch1 = (float)J.chan[1] * scale, ch2 = (float)J.chan[2] * scale;
+  C.ch0 = (float)J.chan[0] * scale; C.ch1 = (float)J.chan[1] * scale; C.ch2 = (float)J.chan[2] * scale;
   for (int q = tid; q < count; q += kThreads) {
-    const int id = s_qid[q];
-    const int la = id % (16 * RX), lb = id / (16 * RX);
+    const unsigned id = s_qid[q];
+    const int la = (id & 0x3fff) % PW, lb = (id & 0x3fff) / PW;
+    const int a = a0 + la, b = g.N - 1 - (b0 + lb);
     RayOut o;
-    if (!trace<true, false>(s_prog, n_steps, M, fmaf((float)(a0 + la) + 0.5f, cell, -P), fmaf((float)(b0 + lb) + 0.5f, cell, -P), sin_t, cos_t, o)) continue;
-    if (!(o.w > 0.f)) continue;
-    const float px = s_qx[q], py = s_qy[q];
-    int ix, iy, ntap;
-    float wt[4];
-    if (bilinear) {
-      const float qx = px - 0.5f, qy = py - 0.5f;
-      const float fx0 = floorf(qx), fy0 = floorf(qy);
-      const float fx = qx - fx0, fy = qy - fy0;
-      ix = (int)fx0; iy = (int)fy0; ntap = 4;
-      wt[0] = o.w * ((1.f - fx) * (1.f - fy)); wt[1] = o.w * (fx * (1.f - fy));
-      wt[2] = o.w * ((1.f - fx) * fy); wt[3] = o.w * (fx * fy);
-    } else {
-      ix = (int)floorf(px); iy = (int)floorf(py); ntap = 1;
-      wt[0] = o.w;
-    }
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      if (t >= ntap) break;
-      const int jx = ix + (t & 1), jy = iy + (t >> 1);
-      if (jx < 0 || jx >= g.W || jy < 0 || jy >= g.H) continue;
-      const long long q0 = __float2ll_rn(wt[t] * ch0), q1 = __float2ll_rn(wt[t] * ch1), q2 = __float2ll_rn(wt[t] * ch2);
-      unsigned long long* dst = use_tile ? s_tile + 3 * ((jy - ty0) * tw + (jx - tx0)) : accum + 3 * ((size_t)jx + (size_t)jy * g.W);
-      if (q0) atomicAdd(dst + 0, (unsigned long long)q0);
-      if (q1) atomicAdd(dst + 1, (unsigned long long)q1);
-      if (q2) atomicAdd(dst + 2, (unsigned long long)q2);
-    }
+    if (!trace<true, true, false>(s_prog, n_steps, M, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o)) continue;
+    const float4 pp = s_qp[q];
+    if ((id & (1u << 14)) && o.wa > 0.f) splat(C, pp.x, pp.y, o.wa);
+    if ((id & (2u << 14)) && o.wb > 0.f) splat(C, pp.z, pp.w, o.wb);
   }
   if (!use_tile) return;
   __syncthreads();
-  // ---- flush the tile: one global atomic per touched (pixel, channel) --------------------------
-  for (int q = tid; q < tw * th * 3; q += kThreads) {
+  // ---- flush the tile: one global atomic per touched (pixel, channel) ------------------------------
+  for (int q = tid; q < C.tw * th * 3; q += kThreads) {
     const unsigned long long v = s_tile[q];
     if (v) {
       const int p = q / 3, c = q - 3 * p;
-      const int jy = ty0 + p / tw, jx = tx0 + (p - (p / tw) * tw);
+      const int jy = C.ty0 + p / C.tw, jx = C.tx0 + (p - (p / C.tw) * C.tw);
       atomicAdd(accum + 3 * ((size_t)jx + (size_t)jy * g.W) + c, v);
     }
   }
@@ -334,14 +378,14 @@ __global__ void __launch_bounds__(kThreads) exact_dump_kernel(const Job* __restr
   PixMap PM;
   PM.sx = (float)J.sx; PM.sy = (float)J.sy; PM.cs = (float)J.cs; PM.sn = (float)J.sn; PM.ppu = (float)J.ppu;
   RayOut o;
-  const bool alive = trace<true, true>(s_prog, n_steps, M, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P),
-                                       (float)J.sin_t, (float)J.cos_t, o);
+  const bool alive = trace<true, false, true>(s_prog, n_steps, M, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P),
+                                              (float)J.sin_t, (float)J.cos_t, o);
   lfb_ray_hit rec;
   rec.x_ap = o.xa; rec.y_ap = o.ya; rec.flags = o.flags; rec.pad = 0;
   if (alive) {
     float px, py;
     to_pixel(PM, o.xs, o.ys, px, py);
-    rec.x_s = o.xs; rec.y_s = o.ys; rec.weight = o.w; rec.px = px; rec.py = py;
+    rec.x_s = o.xs; rec.y_s = o.ys; rec.weight = o.wa; rec.px = px; rec.py = py;
     const float fx = floorf(px), fy = floorf(py);
     if (!(fx >= 0.f && fx < (float)g.W && fy >= 0.f && fy < (float)g.H)) rec.flags |= LFB_RAY_OFF_SENSOR;
   } else {

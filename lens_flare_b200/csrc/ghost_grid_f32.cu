@@ -16,8 +16,8 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
                                    const float* tex, unsigned long long* accum, cudaStream_t s) {
   if (n_jobs <= 0) return cudaSuccess;
   if (mode == LFB_MODE_PARAXIAL_GRID) return f32::launch_trace_splat_t<float>(jobs, n_jobs, g, mode, tex, accum, s);
-  auto blocks = [&](int rx, int ry) {
-    return (unsigned)n_jobs * (unsigned)(((g.N + 16 * rx - 1) / (16 * rx)) * ((g.N + 16 * ry - 1) / (16 * ry)));
+  auto blocks = [&](int rx, int ry) {  // patches tile the upper half of the grid (mirror symmetry, exact_f32.cuh)
+    return (unsigned)n_jobs * (unsigned)(((g.N + 16 * rx - 1) / (16 * rx)) * (((g.N + 1) / 2 + 16 * ry - 1) / (16 * ry)));
   };
   if (g.patch >= 4) xf32::exact_splat_kernel<2, 2><<<blocks(2, 2), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
   else if (g.patch >= 2) xf32::exact_splat_kernel<2, 1><<<blocks(2, 1), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);

@@ -52,10 +52,10 @@ struct FrameGeom {
 enum StepOp { STEP_REFRACT = 0, STEP_REFLECT = 1, STEP_PASS = 2, STEP_STOP = 3, STEP_SENSOR = 4 };
 #define LFB_MAX_STEPS (3 * LFB_MAX_SURFACES + 2)
 struct Step {
-  float c, dz, semi2, eta;   // curvature; z of the previous vertex minus z of this one; clear radius^2; n0/n2
-  float eta2, n0, n2, n1;    // (n0/n2)^2; indices before/after along the ray; film index (0 = bare)
-  float e1sq, phase;         // (n0/n1)^2; pi * lambda0 / lambda
+  float c, dz, semi2, eta;   // curvature (0: plane); z of the previous vertex minus z of this one; clear radius^2; n0/n2
+  float eta2, phase;         // (n0/n2)^2; coating phase factor pi * lambda0 / lambda
   int op, k;                 // StepOp; surface index (k = n_surfaces for the sensor)
+  float n0, n2, n1, e1sq;    // indices before/after along the ray; film index (0 = bare); (n0/n1)^2
 };
 
 // REF_QUADS: one rasterisable triangle of a ghost quad (pathtracer.cpp:346-410 state
