@@ -138,6 +138,7 @@ struct lfb_engine {
   Step* d_progs = nullptr;   // FP32 EXACT_GRID step programs, LFB_MAX_STEPS per job
   Step* h_progs = nullptr;   // pinned staging
   Step* d_dump_prog = nullptr;
+  int min_blocks = 0;        // register-allocation target of the FP32 exact kernel, CTAs/SM (LFB_EXACT_MINB=4|5|6)
   int patch = 2;             // rays per thread in pass 1 of the FP32 exact kernel (LFB_EXACT_PATCH=1|2|4)
   // owned buffers of the host-memory API
   unsigned long long* d_accum = nullptr;
@@ -198,7 +199,7 @@ FrameGeom make_geom(const lfb_engine* e, const lfb_params& P) {
   g.tex_w = e->tex_w; g.tex_h = e->tex_h;
   g.fp_scale = ldexp(1.0, P.fixed_point_bits > 0 ? P.fixed_point_bits : 40);
   g.P = (float)e->lens.entrance_half_height; g.h_stop = (float)e->lens.stop_half_height;
-  g.patch = e->patch; g.pad = 0;
+  g.patch = e->patch; g.pad = e->min_blocks;
   return g;
 }
 
@@ -396,6 +397,7 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_dump_job, sizeof(Job));
   if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_dump_prog, sizeof(Step) * LFB_MAX_STEPS);
   if (const char* env = getenv("LFB_EXACT_PATCH")) e->patch = atoi(env);
+  if (const char* env = getenv("LFB_EXACT_MINB")) e->min_blocks = atoi(env);
   if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
   *out = e;
   return LFB_OK;

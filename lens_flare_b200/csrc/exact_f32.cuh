@@ -222,8 +222,8 @@ __device__ __forceinline__ void splat(const SplatCtx& C, float px, float py, flo
 
 // One CTA = a (16*RX) x (16*RY) patch of the UPPER HALF of one ghost's ray grid (rows with y >= 0; each
 // traced ray also stands for its mirror image in the lower half); RPT = RX*RY rays per thread in pass 1.
-template <int RX, int RY>
-__global__ void __launch_bounds__(kThreads) exact_splat_kernel(const Job* __restrict__ jobs, const Step* __restrict__ progs,
+template <int RX, int RY, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) exact_splat_kernel(const Job* __restrict__ jobs, const Step* __restrict__ progs,
                                                                FrameGeom g, const float* __restrict__ tex,
                                                                unsigned long long* __restrict__ accum) {
   constexpr int RPT = RX * RY, PATCH = RPT * kThreads, PW = 16 * RX, PH = 16 * RY;

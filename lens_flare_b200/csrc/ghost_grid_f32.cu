@@ -19,9 +19,20 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
   auto blocks = [&](int rx, int ry) {  // patches tile the upper half of the grid (mirror symmetry, exact_f32.cuh)
     return (unsigned)n_jobs * (unsigned)(((g.N + 16 * rx - 1) / (16 * rx)) * (((g.N + 1) / 2 + 16 * ry - 1) / (16 * ry)));
   };
-  if (g.patch >= 4) xf32::exact_splat_kernel<2, 2><<<blocks(2, 2), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
-  else if (g.patch >= 2) xf32::exact_splat_kernel<2, 1><<<blocks(2, 1), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
-  else xf32::exact_splat_kernel<1, 1><<<blocks(1, 1), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
+  // patch shape (rays per thread in pass 1) x resident CTAs per SM the register allocation targets
+  const int minb = g.pad;  // 0 (default) -> 4
+#define LFB_LAUNCH(RX, RY, MB) xf32::exact_splat_kernel<RX, RY, MB><<<blocks(RX, RY), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum)
+#define LFB_PATCH(MB)                       \
+  do {                                      \
+    if (g.patch >= 4) LFB_LAUNCH(2, 2, MB); \
+    else if (g.patch >= 2) LFB_LAUNCH(2, 1, MB); \
+    else LFB_LAUNCH(1, 1, MB);              \
+  } while (0)
+  if (minb >= 6) LFB_PATCH(6);
+  else if (minb == 5) LFB_PATCH(5);
+  else LFB_PATCH(4);
+#undef LFB_PATCH
+#undef LFB_LAUNCH
   return cudaGetLastError();
 }
 

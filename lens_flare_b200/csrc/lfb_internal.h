@@ -44,7 +44,7 @@ struct FrameGeom {
   int tex_w, tex_h;
   double fp_scale;  // 2^fixed_point_bits
   float P, h_stop;  // entrance half height, stop half height
-  int patch, pad;   // FP32 EXACT_GRID: rays per thread in pass 1 (1, 2 or 4)
+  int patch, pad;   // FP32 EXACT_GRID tuning: rays per thread in pass 1 (1, 2 or 4); resident CTAs/SM target (0 -> 4)
 };
 
 // FP32 EXACT_GRID step program (exact_f32.cuh): a ghost flattened into straight-line steps with every

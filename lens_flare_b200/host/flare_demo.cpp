@@ -1,0 +1,94 @@
+// flare_demo.cpp -- the reference application's flare flags on top of the C++ facade:
+//   flare_demo -r W H -y ghost_aperture.png [-x starburst_aperture.png] [-s ns_x ns_y] [-m ref|paraxial|exact] [-g N] [-f out.pfm]
+// (-r, -x, -y, -f as in src/application/main.cpp:87, 135-152).  Prints frame statistics as one JSON line.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "flare_pathtracer.hpp"
+
+int main(int argc, char** argv) {
+  size_t W = 512, H = 512;
+  std::string ghost_png, star_png, out;
+  double sx = 0.45, sy = 0.55;
+  int mode = LFB_MODE_REF_QUADS, grid = 256;
+  if (argc == 3 && std::string(argv[1]) == "--png-info") {  // host-only: what CameraApertureTexture::init decodes
+    try {
+      lfb::CameraApertureTexture t;
+      t.init(argv[2]);
+      unsigned long long bytes = 0;
+      for (float v : t.aperture) bytes += (unsigned long long)(v * 255.0f + 0.5f);
+      std::printf("{\"w\": %zu, \"h\": %zu, \"total\": %.17g, \"bbox\": [%d, %d, %d, %d], \"byte_sum\": %llu}\n", t.width, t.height,
+                  t.total_value, t.min_x, t.min_y, t.max_x, t.max_y, bytes);
+      return 0;
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "flare_demo: %s\n", e.what());
+      return 1;
+    }
+  }
+  for (int a = 1; a < argc; a++) {
+    const std::string k = argv[a];
+    if (k == "-r" && a + 2 < argc) { W = std::strtoul(argv[a + 1], nullptr, 10); H = std::strtoul(argv[a + 2], nullptr, 10); a += 2; }
+    else if (k == "-y" && a + 1 < argc) ghost_png = argv[++a];
+    else if (k == "-x" && a + 1 < argc) star_png = argv[++a];
+    else if (k == "-f" && a + 1 < argc) out = argv[++a];
+    else if (k == "-s" && a + 2 < argc) { sx = std::atof(argv[a + 1]); sy = std::atof(argv[a + 2]); a += 2; }
+    else if (k == "-g" && a + 1 < argc) grid = std::atoi(argv[++a]);
+    else if (k == "-m" && a + 1 < argc) {
+      const std::string m = argv[++a];
+      mode = m == "exact" ? LFB_MODE_EXACT_GRID : (m == "paraxial" ? LFB_MODE_PARAXIAL_GRID : LFB_MODE_REF_QUADS);
+    } else { std::fprintf(stderr, "unknown argument %s\n", argv[a]); return 2; }
+  }
+  if (ghost_png.empty()) { std::fprintf(stderr, "usage: flare_demo -r W H -y ghost_aperture.png [-s ns_x ns_y] [-m ref|paraxial|exact] [-g N] [-f out.pfm]\n"); return 2; }
+  try {
+    lfb::CameraApertureTexture ghost_tex;
+    ghost_tex.init(ghost_png);
+    lfb::Camera camera;
+    camera.ghost_aperture_texture = &ghost_tex;
+    camera.aperture_texture = &ghost_tex;
+    // a directional light whose image lands at (sx, sy): invert analyze_world_coord for the identity camera
+    const double kPi = 3.14159265358979323846;
+    const double ex = std::tan(0.5 * camera.hFov * kPi / 180.0), ey = std::tan(0.5 * camera.vFov * kPi / 180.0);
+    lfb::DirectionalLight sun(lfb::Vector3D(1, 1, 1), lfb::Vector3D(-(2 * sx - 1) * ex, -(2 * sy - 1) * ey, 1.0), lfb::Vector3D(0, 0, -1));
+    lfb::Scene scene;
+    scene.lights.push_back(&sun);
+    lfb::PathTracer pt(0);
+    pt.scene = &scene;
+    pt.camera = &camera;
+    pt.params.mode = mode;
+    pt.params.grid_n = grid;
+    if (mode != LFB_MODE_REF_QUADS) { pt.params.pair_set = LFB_PAIRS_ALL; pt.params.include_direct = 1; }
+    pt.set_frame_size(W, H);
+    pt.find_sun_pos();
+    pt.generate_ghost_buffer();
+    double sum[3] = {0, 0, 0}, l2 = 0;
+    size_t nz = 0;
+    for (const lfb::Vector3D& v : pt.ghost_buffer.data) {
+      sum[0] += v.x; sum[1] += v.y; sum[2] += v.z;
+      l2 += v.x * v.x + v.y * v.y + v.z * v.z;
+      nz += (v.x != 0 || v.y != 0 || v.z != 0);
+    }
+    std::printf("{\"w\": %zu, \"h\": %zu, \"axis_ray\": [%.17g, %.17g], \"angle_to_sun\": %.9g, \"sum\": [%.17g, %.17g, %.17g], "
+                "\"l2\": %.17g, \"nonzero\": %zu, \"trace_ms\": %.4f, \"frame_ms\": %.4f, \"tex_total\": %.17g}\n",
+                W, H, pt.axis_ray.x, pt.axis_ray.y, pt.angle_to_sun, sum[0], sum[1], sum[2], std::sqrt(l2), nz, pt.last_trace_ms(),
+                pt.last_frame_ms(), ghost_tex.total_value);
+    if (!out.empty()) {  // PFM, bottom row first -- the same vertical flip the reference applies on save (raytraced_renderer.cpp:739-742)
+      FILE* f = std::fopen(out.c_str(), "wb");
+      if (!f) { std::fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
+      std::fprintf(f, "PF\n%zu %zu\n-1.0\n", W, H);
+      for (size_t y = 0; y < H; y++)
+        for (size_t x = 0; x < W; x++) {
+          const lfb::Vector3D& v = pt.ghost_buffer.get_pixel_value(x, y);
+          const float rgb[3] = {(float)v.x, (float)v.y, (float)v.z};
+          std::fwrite(rgb, sizeof(float), 3, f);
+        }
+      std::fclose(f);
+    }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "flare_demo: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,161 @@
+#include "flare_pathtracer.hpp"
+
+#include <cmath>
+#include <cstring>
+
+#include "png_reader.hpp"
+
+namespace lfb {
+namespace {
+void check(int rc, const char* what) {
+  if (rc < 0) throw Error(rc, std::string(what) + ": " + lfb_last_error());
+}
+const double kPi = 3.14159265358979323846;
+}  // namespace
+
+// ---- CameraApertureTexture (camera.h:26-83) -------------------------------------------------
+void CameraApertureTexture::init(const std::string& aperture_filename) {
+  std::vector<unsigned char> red;
+  unsigned w = 0, h = 0;
+  read_png_red(aperture_filename, red, w, h);  // throws: the reference prints "UNABLE TO LOAD" and then indexes an empty vector
+  init_from_bytes(red.data(), w, h);
+}
+
+void CameraApertureTexture::init_from_bytes(const unsigned char* red, size_t w, size_t h) {
+  width = w; height = h;
+  aperture.resize(w * h);
+  const float inv = 1.0 / 255.0;  // Color(const uchar*), CGL/src/color.cpp:16-21
+  min_x = min_y = (int)w; max_x = max_y = -1;
+  total_value = 0.0;
+  for (size_t y = 0; y < h; y++)
+    for (size_t x = 0; x < w; x++) {
+      const float v = red[y * w + x] * inv;
+      aperture[y * w + x] = v;
+      total_value += v;
+      if (v > 0) {
+        if ((int)x < min_x) min_x = (int)x;
+        if ((int)y < min_y) min_y = (int)y;
+        if ((int)x > max_x) max_x = (int)x;
+        if ((int)y > max_y) max_y = (int)y;
+      }
+    }
+}
+
+// ---- DirectionalLight (light.cpp:11-16) ------------------------------------------------------
+DirectionalLight::DirectionalLight(const Vector3D& rad, const Vector3D& posLight_, const Vector3D& lightDir) : radiance(rad) {
+  posLight = Vector3D(-posLight_.x, -posLight_.y, -posLight_.z);
+  const double n = std::sqrt(lightDir.x * lightDir.x + lightDir.y * lightDir.y + lightDir.z * lightDir.z);
+  dirToLight = Vector3D(-lightDir.x / n, -lightDir.y / n, -lightDir.z / n);
+}
+
+// ---- Camera::analyze_world_coord (camera.cpp:245-273) ------------------------------------------
+void Camera::analyze_world_coord(const Vector3D& p, double& ns_x, double& ns_y) const {
+  const double edge_x = std::tan(0.5 * (hFov * (kPi / 180.0)));
+  const double edge_y = std::tan(0.5 * (vFov * (kPi / 180.0)));
+  const double dx = p.x - pos.x, dy = p.y - pos.y, dz = p.z - pos.z;
+  // c2w.T() * (p - pos)
+  const double cx = c2w(0, 0) * dx + c2w(1, 0) * dy + c2w(2, 0) * dz;
+  const double cy = c2w(0, 1) * dx + c2w(1, 1) * dy + c2w(2, 1) * dz;
+  const double cz = c2w(0, 2) * dx + c2w(1, 2) * dy + c2w(2, 2) * dz;
+  const double a = std::fabs(cz);
+  ns_x = ((cx / a / edge_x) + 1) / 2.0;
+  ns_y = ((cy / a / edge_y) + 1) / 2.0;
+}
+
+// ---- PathTracer ----------------------------------------------------------------------------
+PathTracer::PathTracer(int device_id) : device_id_(device_id) {
+  std::memset(&params, 0, sizeof(params));
+  params.mode = LFB_MODE_REF_QUADS;
+  params.pair_set = LFB_PAIRS_REF;
+  params.grid_n = 256;
+  params.precision = LFB_FP32;
+  params.splat = LFB_SPLAT_BILINEAR;
+  check(lfb_builtin_lens(&lens_, 3, 0.f), "lfb_builtin_lens");
+}
+
+PathTracer::~PathTracer() { lfb_destroy(engine_); }
+
+void PathTracer::set_lens(const lfb_lens& lens) {
+  lens_ = lens;
+  lens_dirty_ = true;
+}
+
+void PathTracer::ensure_engine() {
+  if (!engine_) check(lfb_create(&engine_, device_id_), "lfb_create");
+  if (lens_dirty_) {
+    check(lfb_set_lens(engine_, &lens_), "lfb_set_lens");
+    lens_dirty_ = false;
+  }
+}
+
+// pathtracer.cpp:32-64: every on-screen directional light is recorded; axis_ray / angle_to_sun describe the last one
+void PathTracer::find_sun_pos() {
+  if (!scene || !camera) return;
+  for (DirectionalLight* light : scene->lights) {
+    double ns_x, ns_y;
+    camera->analyze_world_coord(light->posLight, ns_x, ns_y);
+    if ((ns_x >= 0 && ns_x <= 1) && (ns_y >= 0 && ns_y <= 1)) {
+      flare_origins.emplace_back(ns_x, ns_y);
+      flare_radiance.push_back(light->radiance);
+      angle_to_sun = (float)std::atan(ns_y / ns_x);
+      axis_ray = Vector2D(ns_x, ns_y);
+    }
+  }
+}
+
+// pathtracer.cpp:714-762
+void PathTracer::generate_ghost_buffer() {
+  ghost_buffer.clear();
+  ghost_buffer.resize(frame_w_, frame_h_);
+  if (axis_ray.x == 0 && axis_ray.y == 0) return;  // :724-726
+  if (!camera || !camera->ghost_aperture_texture || camera->ghost_aperture_texture->aperture.empty())
+    throw Error(LFB_ERR_STATE, "camera->ghost_aperture_texture is not loaded");
+  ensure_engine();
+  const CameraApertureTexture* t = camera->ghost_aperture_texture;
+  if (uploaded_ != t) {
+    check(lfb_set_aperture(engine_, t->aperture.data(), (int)t->width, (int)t->height), "lfb_set_aperture");
+    uploaded_ = t;
+  }
+  params.width = (int)frame_w_;
+  params.height = (int)frame_h_;
+  std::vector<lfb_light> lights;
+  if (params.mode == LFB_MODE_REF_QUADS || flare_origins.empty()) {
+    lfb_light lt;
+    std::memset(&lt, 0, sizeof(lt));
+    lt.ns_x = axis_ray.x; lt.ns_y = axis_ray.y; lt.theta = angle_to_sun;
+    lt.radiance[0] = lt.radiance[1] = lt.radiance[2] = 1.f;
+    lights.push_back(lt);
+  } else {
+    for (size_t l = 0; l < flare_origins.size(); l++) {
+      lfb_light lt;
+      std::memset(&lt, 0, sizeof(lt));
+      lt.ns_x = flare_origins[l].x; lt.ns_y = flare_origins[l].y;
+      if (params.mode == LFB_MODE_EXACT_GRID) {
+        // real refraction needs the real off-axis angle of the light (the inverse of analyze_world_coord), not the
+        // reference's screen-space atan(ns_y/ns_x)
+        const double tx = (2 * lt.ns_x - 1) * std::tan(0.5 * camera->hFov * kPi / 180.0);
+        const double ty = (2 * lt.ns_y - 1) * std::tan(0.5 * camera->vFov * kPi / 180.0);
+        lt.theta = (float)std::atan(std::sqrt(tx * tx + ty * ty));
+      } else {
+        lt.theta = (float)std::atan(lt.ns_y / lt.ns_x);
+      }
+      lt.radiance[0] = (float)flare_radiance[l].x; lt.radiance[1] = (float)flare_radiance[l].y; lt.radiance[2] = (float)flare_radiance[l].z;
+      lights.push_back(lt);
+    }
+  }
+  check(lfb_render_ghosts(engine_, lights.data(), (int)lights.size(), &params, ghost_buffer.data.data(), sizeof(Vector3D), LFB_F64x3, 0),
+        "lfb_render_ghosts");
+}
+
+float PathTracer::last_trace_ms() const {
+  float t = 0;
+  if (engine_) lfb_stats(engine_, nullptr, &t, nullptr);
+  return t;
+}
+float PathTracer::last_frame_ms() const {
+  float t = 0;
+  if (engine_) lfb_stats(engine_, nullptr, nullptr, &t);
+  return t;
+}
+
+}  // namespace lfb

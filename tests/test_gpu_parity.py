@@ -387,3 +387,38 @@ def test_host_mirror_generate_ghost_buffer(golden, apertures):
         assert not pt.ghost_buffer.data.any()
     finally:
         pt.close()
+
+
+def test_cpp_facade_end_to_end(golden, apertures, port, tmp_path):
+    """The C++ host path (lens_flare_b200/host): PNG -> CameraApertureTexture -> DirectionalLight -> find_sun_pos ->
+    generate_ghost_buffer -> ghost_buffer (Vector3D[]), through liblfb200.so, vs the oracle on the sun it found."""
+    import json
+    import os
+    import subprocess
+    from PIL import Image
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "lens_flare_b200", "host")
+    subprocess.run(["make", "-s", "-C", host], check=True)
+    png = tmp_path / "pent_11.png"
+    Image.fromarray(apertures["pent_11_u8"], "L").save(png)
+    pfm = tmp_path / "out.pfm"
+    out = subprocess.run([os.path.join(host, "flare_demo"), "-r", "512", "512", "-y", str(png), "-s", "0.7", "0.6", "-f", str(pfm)],
+                         check=True, capture_output=True, text=True).stdout
+    info = json.loads(out)
+    ax, ay = info["axis_ray"]
+    assert abs(ax - 0.7) < 1e-12 and abs(ay - 0.6) < 1e-12
+    want = port.generate_ghost_buffer(port.builtin_lens(3), apertures["pent_11"], 512, 512, ax, ay, float(np.float32(info["angle_to_sun"])))
+    assert info["nonzero"] == np.count_nonzero((want != 0).any(-1)) == 781
+    assert np.allclose(info["sum"], want.reshape(-1, 3).sum(0), rtol=1e-12)
+    assert np.isclose(info["l2"], np.sqrt((want ** 2).sum()), rtol=1e-12)
+    raw = np.fromfile(pfm, np.float32, offset=len(b"PF\n512 512\n-1.0\n")).reshape(512, 512, 3)
+    assert np.array_equal(raw, want.astype(np.float32))
+    # exact ray-grid mode through the same facade
+    out = subprocess.run([os.path.join(host, "flare_demo"), "-r", "640", "360", "-y", str(png), "-s", "0.45", "0.55", "-m", "exact", "-g", "64"],
+                         check=True, capture_output=True, text=True).stdout
+    info = json.loads(out)
+    lens = port.builtin_lens(3)
+    lt = [capi.make_light(info["axis_ray"][0], info["axis_ray"][1], theta=capi.physical_theta(0.45, 0.55))]
+    p = capi.make_params(capi.MODE_EXACT_GRID, 640, 360, grid_n=64, pair_set=capi.PAIRS_ALL, include_direct=1)
+    want = port.render(lens, apertures["pent_11"], lt, p)
+    assert want.any() and np.allclose(info["sum"], want.reshape(-1, 3).sum(0), rtol=2e-3)

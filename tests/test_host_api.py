@@ -166,3 +166,35 @@ def test_aperture_texture_loader(apertures, tmp_path):
         assert np.array_equal(t.aperture, apertures["pent_11"])
     with pytest.raises(IOError):
         pathtracer.CameraApertureTexture().init(str(tmp_path / "missing.png"))
+
+
+# ---- the C++ facade (lens_flare_b200/host): host-only parts -------------------------------------
+def _flare_demo():
+    import subprocess
+    host = os.path.join(ROOT, "lens_flare_b200", "host")
+    subprocess.run(["make", "-s", "-C", host], check=True)
+    return os.path.join(host, "flare_demo")
+
+
+def test_cpp_png_reader_matches_reference_loader(native_lib, apertures, tmp_path):
+    """lfb::CameraApertureTexture::init (own PNG decoder on zlib) yields the same mask statistics as the reference's
+    loader (golden fixture), for gray, RGB, RGBA and palette PNGs with every scanline filter PIL chooses."""
+    import json
+    import subprocess
+    from PIL import Image
+    exe = _flare_demo()
+    u8 = apertures["pentbig500_14_u8"]
+    files = {}
+    Image.fromarray(u8, "L").save(tmp_path / "gray.png")
+    Image.fromarray(np.stack([u8, u8 // 2, 255 - u8], -1), "RGB").save(tmp_path / "rgb.png")
+    Image.fromarray(np.stack([u8, u8 // 2, u8 // 3, np.full_like(u8, 200)], -1), "RGBA").save(tmp_path / "rgba.png", compress_level=9)
+    Image.fromarray(u8, "L").convert("P").save(tmp_path / "pal.png")
+    for name in ("gray.png", "rgb.png", "rgba.png", "pal.png"):
+        out = subprocess.run([exe, "--png-info", str(tmp_path / name)], check=True, capture_output=True, text=True).stdout
+        info = json.loads(out)
+        assert (info["w"], info["h"]) == (500, 500), name
+        assert info["byte_sum"] == int(u8.astype(np.int64).sum()), name
+        assert tuple(info["bbox"]) == apertures["pentbig500_14_bbox"], name
+        assert np.isclose(info["total"], apertures["pentbig500_14_total"], rtol=1e-12), name
+    bad = subprocess.run([exe, "--png-info", str(tmp_path / "missing.png")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "cannot open" in bad.stderr
