@@ -138,8 +138,8 @@ struct lfb_engine {
   Step* d_progs = nullptr;   // FP32 EXACT_GRID step programs, LFB_MAX_STEPS per job
   Step* h_progs = nullptr;   // pinned staging
   Step* d_dump_prog = nullptr;
-  int min_blocks = 0;        // register-allocation target of the FP32 exact kernel, CTAs/SM (LFB_EXACT_MINB=4|5|6)
-  int patch = 2;             // rays per thread in pass 1 of the FP32 exact kernel (LFB_EXACT_PATCH=1|2|4)
+  int min_blocks = 6;        // register-allocation target of the FP32 exact kernel, CTAs/SM (LFB_EXACT_MINB=4|5|6)
+  int patch = 1;             // rays per thread in pass 1 of the FP32 exact kernel (LFB_EXACT_PATCH=1|2|4)
   // owned buffers of the host-memory API
   unsigned long long* d_accum = nullptr;
   size_t accum_cap = 0;
