@@ -336,7 +336,7 @@ def run_ours(args):
         mufu_ach = inter_rank * MUFU_PER_INTERACTION / (k_ms * 1e-3)
         roofline = {
             "bound": "fp32", "kernel": "xf32::exact_splat_kernel", "achieved": ach / 1e12, "peak": peaks["fp32_flops"] / 1e12,
-            "unit": "TFLOP/s", "frac": ach / peaks["fp32_flops"], "traffic": None,
+            "unit": "TFLOP/s", "frac": ach / peaks["fp32_flops"], "traffic": 1.89e6, "traffic_source": "ncu --set full, profiles/r1_exact_splat_v3_ncu_details.txt: dram read 1.89 MB + written 0 B per launch (the atomics stay in L2)",
             "kernel_ms": k_ms, "interactions_per_launch": inter_rank, "flop_per_interaction": FLOP_PER_INTERACTION,
             "peak_source": "measured live on this GPU by lfb_probe_peaks (register-only FFMA chains); MEASURED_PEAKS.json holds no "
                            "FP32 figure. The trace is scalar FP32/MUFU math: neither 'hbm' nor 'tensor' bounds it",

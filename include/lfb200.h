@@ -167,6 +167,15 @@ int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_lights,
                       const lfb_params* params, void* out, size_t out_stride_bytes,
                       int out_elem, int additive);
 
+/* Dirty-rectangle form of lfb_render_ghosts.  A flare covers a small part of the sensor and the caller's buffer is
+ * normally already clear (the reference clears ghost_buffer right before drawing, pathtracer.cpp:719-720; util/image.h:126-131),
+ * so only the bounding rectangle of the pixels this frame deposits into is converted and copied back: pixels outside
+ * rect_out are NOT touched, pixels inside are overwritten (zero where nothing landed).  rect_out = {x0, y0, x1, y1},
+ * inclusive; {0, 0, -1, -1} when nothing landed. */
+int lfb_render_ghosts_rect(lfb_engine* e, const lfb_light* lights, int n_lights,
+                           const lfb_params* params, void* out, size_t out_stride_bytes,
+                           int out_elem, int* rect_out);
+
 /* Parity instrument: trace the N x N grid of one ghost (i, j, lambda) of one light
  * and return every ray's record (grid modes only).  i = j = -1 selects the direct path. */
 int lfb_dump_rays(lfb_engine* e, const lfb_light* light, const lfb_params* params,

@@ -153,6 +153,12 @@ struct lfb_engine {
   int* d_pairs = nullptr;
   float* d_rgbw = nullptr;
   int n_ref_pairs = 0, n_ref_ghosts = 0;
+  // dirty-rectangle path (lfb_render_ghosts_rect)
+  int* d_bbox = nullptr;      // device {min_x, min_y, max_x, max_y} of the pixels the frame deposits into
+  int* h_bbox = nullptr;      // pinned: [0..3] reset pattern, [4..7] read-back
+  bool track_bbox = false;
+  int accum_dirty[4] = {0, 0, -1, -1};  // what the last rect frame left non-zero in d_accum
+  int accum_dirty_w = 0, accum_dirty_h = 0;
   uint64_t launches = 0;
   float last_trace_ms = 0, last_frame_ms = 0;
 };
@@ -199,6 +205,7 @@ FrameGeom make_geom(const lfb_engine* e, const lfb_params& P) {
   g.tex_w = e->tex_w; g.tex_h = e->tex_h;
   g.fp_scale = ldexp(1.0, P.fixed_point_bits > 0 ? P.fixed_point_bits : 40);
   g.P = (float)e->lens.entrance_half_height; g.h_stop = (float)e->lens.stop_half_height;
+  g.bbox = e->track_bbox ? e->d_bbox : nullptr;
   g.patch = e->patch; g.pad = e->min_blocks;
   return g;
 }
@@ -350,11 +357,19 @@ int render_ref_device(lfb_engine* e, const lfb_light* lights, int n_lights, cons
   CU(cudaEventRecord(e->ev_trace0, e->stream));
   const int n_ghosts = f.n_pairs * f.n_lambda;
   if (f.has_sun && n_ghosts > 0) {
-    CU(launch_ref_setup(f, e->d_pairs, e->d_rgbw, e->d_tris, e->d_ghosts, e->stream));
+    CU(launch_ref_setup(f, e->d_pairs, e->d_rgbw, e->d_tris, e->d_ghosts, e->track_bbox ? e->d_bbox : nullptr, e->stream));
     e->launches++;
     e->n_ref_ghosts = n_ghosts;
   }
-  CU(launch_ref_raster(f, e->d_tris, f.has_sun ? 2 * n_ghosts : 0, e->d_tex, out_dev, stride, elem, additive, e->stream));
+  int rect[4];
+  if (e->track_bbox) {  // rect path: raster only the ghosts' bounding rectangle, into a packed buffer
+    CU(cudaMemcpyAsync(e->h_bbox + 4, e->d_bbox, 4 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    memcpy(rect, e->h_bbox + 4, sizeof(rect));
+    if (rect[2] < rect[0] || rect[3] < rect[1]) { CU(cudaEventRecord(e->ev_trace1, e->stream)); e->timed = true; return LFB_OK; }
+  }
+  CU(launch_ref_raster(f, e->d_tris, f.has_sun ? 2 * n_ghosts : 0, e->d_tex, out_dev, stride, elem, additive,
+                       e->track_bbox ? rect : nullptr, e->stream));
   e->launches++;
   CU(cudaEventRecord(e->ev_trace1, e->stream));
   e->timed = true;
@@ -396,6 +411,9 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_frame1);
   if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_dump_job, sizeof(Job));
   if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_dump_prog, sizeof(Step) * LFB_MAX_STEPS);
+  if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_bbox, 4 * sizeof(int));
+  if (rc == cudaSuccess) rc = cudaHostAlloc((void**)&e->h_bbox, 8 * sizeof(int), cudaHostAllocDefault);
+  if (rc == cudaSuccess) { e->h_bbox[0] = e->h_bbox[1] = 0x7fffffff; e->h_bbox[2] = e->h_bbox[3] = -0x7fffffff; }
   if (const char* env = getenv("LFB_EXACT_PATCH")) e->patch = atoi(env);
   if (const char* env = getenv("LFB_EXACT_MINB")) e->min_blocks = atoi(env);
   if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
@@ -408,7 +426,8 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
-  cudaFree(e->d_progs); cudaFree(e->d_dump_prog);
+  cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox);
+  if (e->h_bbox) cudaFreeHost(e->h_bbox);
   if (e->h_progs) cudaFreeHost(e->h_progs);
   cudaFree(e->d_tex); cudaFree(e->d_jobs); cudaFree(e->d_dump_job); cudaFree(e->d_accum); cudaFree(e->d_out);
   cudaFree(e->d_hits); cudaFree(e->d_tris); cudaFree(e->d_ghosts); cudaFree(e->d_pairs); cudaFree(e->d_rgbw);
@@ -630,6 +649,7 @@ extern "C" int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_l
   } else {
     rc = grow(&e->d_accum, &e->accum_cap, lfb_accum_bytes(P->width, P->height));
     if (rc) return rc;
+    e->accum_dirty_w = e->accum_dirty_h = 0;  // the whole buffer is about to be used: the rect path must start fresh
     rc = render_grid_device(e, lights, n_lights, *P, e->d_accum, 1);
     if (rc) return rc;
     const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
@@ -639,6 +659,78 @@ extern "C" int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_l
   CU(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaEventRecord(e->ev_frame1, e->stream));
   CU(cudaStreamSynchronize(e->stream));  // the reference's caller reads ghost_buffer right after the call
+  CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
+  CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
+  return LFB_OK;
+}
+
+// The dirty-rectangle form of lfb_render_ghosts: a flare covers a small part of the sensor, and the caller's
+// buffer is normally already clear (the reference clears ghost_buffer right before, pathtracer.cpp:719-720), so only
+// the bounding rectangle of the pixels the frame deposits into is converted and copied.  Pixels outside rect_out are
+// NOT touched; inside it every pixel is overwritten (zeros where nothing landed).  rect_out = {x0, y0, x1, y1}
+// inclusive, or {0, 0, -1, -1} for an empty frame.
+extern "C" int lfb_render_ghosts_rect(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P, void* out,
+                                      size_t stride, int elem, int* rect_out) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!e->has_lens || !e->has_tex) return fail(LFB_ERR_STATE, "set the lens and the aperture first");
+  rc = check_params(P, false);
+  if (rc) return rc;
+  if (n_lights < 0 || (n_lights > 0 && !lights) || !out || !rect_out) return fail(LFB_ERR_INVALID, "bad lights/out/rect_out");
+  if (elem != LFB_F32x3 && elem != LFB_F64x3) return fail(LFB_ERR_INVALID, "unknown out_elem");
+  if (stride < elem_bytes(elem) || stride % (elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
+  rect_out[0] = rect_out[1] = 0; rect_out[2] = rect_out[3] = -1;
+  const size_t npx = (size_t)P->width * P->height;
+  rc = grow(&e->d_out, &e->out_cap, npx * stride);
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev_frame0, e->stream));
+  CU(cudaMemcpyAsync(e->d_bbox, e->h_bbox, 4 * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  struct Track { lfb_engine* e; Track(lfb_engine* x) : e(x) { e->track_bbox = true; } ~Track() { e->track_bbox = false; } } track(e);
+  int rect[4] = {0, 0, -1, -1};
+  if (P->mode == LFB_MODE_REF_QUADS) {
+    if (stride != elem_bytes(elem)) CU(cudaMemsetAsync(e->d_out, 0, npx * stride, e->stream));
+    rc = render_ref_device(e, lights, n_lights, *P, e->d_out, stride, elem, 0);  // reads the box back itself
+    if (rc) return rc;
+    memcpy(rect, e->h_bbox + 4, sizeof(rect));
+    if (n_lights == 0 || e->n_ref_ghosts == 0) { rect[0] = rect[1] = 0; rect[2] = rect[3] = -1; }
+  } else {
+    const size_t need = lfb_accum_bytes(P->width, P->height);
+    const bool fresh = need > e->accum_cap || e->accum_dirty_w != P->width || e->accum_dirty_h != P->height;
+    rc = grow(&e->d_accum, &e->accum_cap, need);
+    if (rc) return rc;
+    // the accumulators are zero except for the rectangle the previous rect frame left: clear only that
+    if (fresh) {
+      CU(cudaMemsetAsync(e->d_accum, 0, need, e->stream));
+    } else if (e->accum_dirty[2] >= e->accum_dirty[0]) {
+      const int* d = e->accum_dirty;
+      CU(cudaMemset2DAsync(e->d_accum + 3 * ((size_t)d[0] + (size_t)d[1] * P->width), (size_t)P->width * 24, 0, (size_t)(d[2] - d[0] + 1) * 24,
+                           (size_t)(d[3] - d[1] + 1), e->stream));
+    }
+    e->accum_dirty_w = P->width; e->accum_dirty_h = P->height;
+    e->accum_dirty[0] = e->accum_dirty[1] = 0; e->accum_dirty[2] = P->width - 1; e->accum_dirty[3] = P->height - 1;  // until the box is known
+    rc = render_grid_device(e, lights, n_lights, *P, e->d_accum, 0);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(e->h_bbox + 4, e->d_bbox, 4 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    memcpy(rect, e->h_bbox + 4, sizeof(rect));
+    memcpy(e->accum_dirty, rect, sizeof(rect));
+    if (rect[2] >= rect[0] && rect[3] >= rect[1]) {
+      if (stride != elem_bytes(elem)) CU(cudaMemsetAsync(e->d_out, 0, (size_t)(rect[2] - rect[0] + 1) * (rect[3] - rect[1] + 1) * stride, e->stream));
+      const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+      CU(launch_finalize_rect(e->d_accum, P->width, rect, inv, e->d_out, stride, elem, e->stream));
+      e->launches++;
+    }
+  }
+  if (rect[2] >= rect[0] && rect[3] >= rect[1]) {
+    const size_t rw = (size_t)(rect[2] - rect[0] + 1), rh = (size_t)(rect[3] - rect[1] + 1);
+    char* dst = (char*)out + ((size_t)rect[0] + (size_t)rect[1] * P->width) * stride;
+    // each row: rw pixels; the last pixel's padding lane (stride > element) is left alone in the last row only
+    CU(cudaMemcpy2DAsync(dst, (size_t)P->width * stride, e->d_out, rw * stride, (rw - 1) * stride + elem_bytes(elem), rh,
+                         cudaMemcpyDeviceToHost, e->stream));
+    memcpy(rect_out, rect, sizeof(rect));
+  }
+  CU(cudaEventRecord(e->ev_frame1, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
   CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
   CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
   return LFB_OK;

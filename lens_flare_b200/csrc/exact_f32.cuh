@@ -314,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat_kernel(const Job* 
   __syncthreads();
   const int count = s_count;
   if (count == 0) return;
+  if (tid == 0) grow_bbox(g.bbox, s_bbox[0], s_bbox[1], s_bbox[2], s_bbox[3]);
   SplatCtx C;
   C.tx0 = s_bbox[0]; C.ty0 = s_bbox[1];
   C.tw = s_bbox[2] - C.tx0 + 1;

@@ -90,6 +90,34 @@ __global__ void __launch_bounds__(256) finalize_kernel(const unsigned long long*
   }
 }
 
+__global__ void __launch_bounds__(256) finalize_rect_kernel(const unsigned long long* __restrict__ accum, int W, int x0, int y0,
+                                                            int rw, int rh, double inv_scale, char* __restrict__ out,
+                                                            size_t stride, int elem) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)rw * rh) return;
+  const int ry = (int)(q / rw), rx = (int)(q - (size_t)ry * rw);
+  const size_t p = (size_t)(x0 + rx) + (size_t)(y0 + ry) * W;
+  double v[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) v[c] = (double)(long long)accum[3 * p + c] * inv_scale;
+  if (elem == LFB_F32x3) {
+    float* o = reinterpret_cast<float*>(out + q * stride);
+    o[0] = (float)v[0]; o[1] = (float)v[1]; o[2] = (float)v[2];
+  } else {
+    double* o = reinterpret_cast<double*>(out + q * stride);
+    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+  }
+}
+
+cudaError_t launch_finalize_rect(const unsigned long long* accum, int W, const int rect[4], double inv_scale, void* out,
+                                 size_t stride, int elem, cudaStream_t s) {
+  const int rw = rect[2] - rect[0] + 1, rh = rect[3] - rect[1] + 1;
+  if (rw <= 0 || rh <= 0) return cudaSuccess;
+  const size_t n = (size_t)rw * rh;
+  finalize_rect_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(accum, W, rect[0], rect[1], rw, rh, inv_scale, (char*)out, stride, elem);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,
                             size_t stride, int elem, int additive, cudaStream_t s) {
   size_t npx = (size_t)W * H;

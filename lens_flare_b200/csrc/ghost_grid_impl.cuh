@@ -247,6 +247,7 @@ template <typename R>
 __device__ __forceinline__ void deposit(unsigned long long* __restrict__ accum, const FrameGeom& g, int ix, int iy,
                                         R wgt, const R* chan) {
   if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) return;
+  grow_bbox(g.bbox, ix, iy, ix, iy);
   unsigned long long* p = accum + 3 * ((size_t)ix + (size_t)iy * g.W);
 #pragma unroll
   for (int c = 0; c < 3; c++) {

@@ -44,6 +44,7 @@ struct FrameGeom {
   int tex_w, tex_h;
   double fp_scale;  // 2^fixed_point_bits
   float P, h_stop;  // entrance half height, stop half height
+  int* bbox;        // device int[4] = {min_x, min_y, max_x, max_y} of every pixel the frame deposits into (or nullptr)
   int patch, pad;   // FP32 EXACT_GRID tuning: rays per thread in pass 1 (1, 2 or 4); resident CTAs/SM target (0 -> 4)
 };
 
@@ -94,10 +95,24 @@ cudaError_t launch_trace_dump_f64(const Job* job, const FrameGeom& g, int mode, 
                                   cudaStream_t s);
 cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,
                             size_t stride, int elem, int additive, cudaStream_t s);
+// rect = {x0, y0, x1, y1} inclusive; out is PACKED: pixel (x, y) at ((y - y0) * (x1 - x0 + 1) + (x - x0)) * stride
+cudaError_t launch_finalize_rect(const unsigned long long* accum, int W, const int rect[4], double inv_scale, void* out,
+                                 size_t stride, int elem, cudaStream_t s);
+
+// Grow the frame's bounding box (device int[4]) to cover [x0,x1] x [y0,y1].  Read first: after the first few CTAs
+// almost no caller extends the box, so the atomics are rare.
+__device__ __forceinline__ void grow_bbox(int* bb, int x0, int y0, int x1, int y1) {
+  if (!bb) return;
+  volatile int* v = bb;
+  if (x0 < v[0]) atomicMin(bb + 0, x0);
+  if (y0 < v[1]) atomicMin(bb + 1, y0);
+  if (x1 > v[2]) atomicMax(bb + 2, x1);
+  if (y1 > v[3]) atomicMax(bb + 3, y1);
+}
 cudaError_t launch_ref_setup(const RefFrame& f, const int* pairs, const float* rgb_weight, RefTri* tris,
-                             lfb_ref_ghost* ghosts, cudaStream_t s);
+                             lfb_ref_ghost* ghosts, int* bbox, cudaStream_t s);
 cudaError_t launch_ref_raster(const RefFrame& f, const RefTri* tris, int n_tris, const float* tex, void* out,
-                              size_t stride, int elem, int additive, cudaStream_t s);
+                              size_t stride, int elem, int additive, const int* rect, cudaStream_t s);
 
 cudaError_t probe_peaks(int device, cudaStream_t s, double* fp32_flops, double* mufu_ops, double* sm_clock_hz);
 

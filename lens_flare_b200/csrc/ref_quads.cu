@@ -115,7 +115,7 @@ __device__ void make_tri(RefTri& T, int W, int H, float x0, float y0, float u0, 
 }
 
 __global__ void ref_setup_kernel(RefFrame f, const int* __restrict__ pairs, const float* __restrict__ rgb_weight,
-                                 RefTri* __restrict__ tris, lfb_ref_ghost* __restrict__ ghosts) {
+                                 RefTri* __restrict__ tris, lfb_ref_ghost* __restrict__ ghosts, int* bbox) {
   const DevLens& L = c_lens_ref;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= f.n_pairs * f.n_lambda) return;
@@ -146,6 +146,10 @@ __global__ void ref_setup_kernel(RefFrame f, const int* __restrict__ pairs, cons
   const float lrx = (float)(f.gb_mid_w + lr[0]), lry = (float)(f.gb_mid_h + lr[1]);
   make_tri(tris[2 * g], f.W, f.H, ulx, uly, 0.f, 0.f, llx, lly, 0.f, th, urx, ury, tw, 0.f, col);
   make_tri(tris[2 * g + 1], f.W, f.H, lrx, lry, 0.f, 0.f, llx, lly, 0.f, th, urx, ury, tw, 0.f, col);  // sic :498
+  for (int t = 0; t < 2; t++) {  // the pixels the reference's bbox loops visit (upper bounds exclusive)
+    const RefTri& T = tris[2 * g + t];
+    if (T.max_x > T.min_x && T.max_y > T.min_y) grow_bbox(bbox, T.min_x, T.min_y, T.max_x - 1, T.max_y - 1);
+  }
   lfb_ref_ghost& G = ghosts[g];
   G.i = i; G.j = j; G.colour = c; G.pad = 0; G.r1 = s1; G.r2 = s2;
   G.verts[0][0] = ulx; G.verts[0][1] = uly; G.verts[1][0] = llx; G.verts[1][1] = lly;
@@ -178,11 +182,12 @@ __device__ __forceinline__ bool fill_sample(const RefTri& T, int x, int y, const
 __global__ void __launch_bounds__(kTileW * kTileH) ref_raster_kernel(RefFrame f, const RefTri* __restrict__ tris,
                                                                      int n_tris, const float* __restrict__ tex,
                                                                      char* __restrict__ out, size_t stride, int elem,
-                                                                     int additive) {
+                                                                     int additive, int rx0, int ry0, int rw, int rh) {
   __shared__ unsigned short s_list[kMaxTris];
   __shared__ int s_count;
   const int tid = threadIdx.y * kTileW + threadIdx.x;
-  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  // rw > 0: only the rectangle [rx0, rx0+rw) x [ry0, ry0+rh) is rastered, into a PACKED rw x rh output
+  const int x0 = rx0 + blockIdx.x * kTileW, y0 = ry0 + blockIdx.y * kTileH;
   // triangles whose loop bounds touch this tile, kept in draw order
   if (tid == 0) {
     int n = 0;
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(kTileW * kTileH) ref_raster_kernel(RefFrame f,
   __syncthreads();
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
   if (x >= f.W || y >= f.H) return;
+  if (rw > 0 && (x >= rx0 + rw || y >= ry0 + rh)) return;
   double acc[3] = {0.0, 0.0, 0.0};
   const int n = f.has_sun ? s_count : 0;
   for (int q = 0; q < n; q++) {
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kTileW * kTileH) ref_raster_kernel(RefFrame f,
     acc[1] += (double)sample * T.col[1];
     acc[2] += (double)sample * T.col[2];
   }
-  char* o = out + ((size_t)x + (size_t)y * f.W) * stride;
+  char* o = out + (rw > 0 ? ((size_t)(x - rx0) + (size_t)(y - ry0) * rw) : ((size_t)x + (size_t)y * f.W)) * stride;
   if (elem == LFB_F32x3) {
     float* p = reinterpret_cast<float*>(o);
     if (additive) { p[0] += (float)acc[0]; p[1] += (float)acc[1]; p[2] += (float)acc[2]; }
@@ -221,18 +227,22 @@ __global__ void __launch_bounds__(kTileW * kTileH) ref_raster_kernel(RefFrame f,
 }  // namespace
 
 cudaError_t launch_ref_setup(const RefFrame& f, const int* pairs, const float* rgb_weight, RefTri* tris,
-                             lfb_ref_ghost* ghosts, cudaStream_t s) {
+                             lfb_ref_ghost* ghosts, int* bbox, cudaStream_t s) {
   const int n = f.n_pairs * f.n_lambda;
   if (n <= 0) return cudaSuccess;
-  ref_setup_kernel<<<(n + 31) / 32, 32, 0, s>>>(f, pairs, rgb_weight, tris, ghosts);
+  ref_setup_kernel<<<(n + 31) / 32, 32, 0, s>>>(f, pairs, rgb_weight, tris, ghosts, bbox);
   return cudaGetLastError();
 }
 
 cudaError_t launch_ref_raster(const RefFrame& f, const RefTri* tris, int n_tris, const float* tex, void* out,
-                              size_t stride, int elem, int additive, cudaStream_t s) {
+                              size_t stride, int elem, int additive, const int* rect, cudaStream_t s) {
   if (n_tris > kMaxTris) return cudaErrorInvalidValue;
-  dim3 block(kTileW, kTileH), grid((f.W + kTileW - 1) / kTileW, (f.H + kTileH - 1) / kTileH);
-  ref_raster_kernel<<<grid, block, 0, s>>>(f, tris, n_tris, tex, (char*)out, stride, elem, additive);
+  const int rx0 = rect ? rect[0] : 0, ry0 = rect ? rect[1] : 0;
+  const int rw = rect ? rect[2] - rect[0] + 1 : 0, rh = rect ? rect[3] - rect[1] + 1 : 0;
+  if (rect && (rw <= 0 || rh <= 0)) return cudaSuccess;
+  const int gw = rect ? rw : f.W, gh = rect ? rh : f.H;
+  dim3 block(kTileW, kTileH), grid((gw + kTileW - 1) / kTileW, (gh + kTileH - 1) / kTileH);
+  ref_raster_kernel<<<grid, block, 0, s>>>(f, tris, n_tris, tex, (char*)out, stride, elem, additive, rx0, ry0, rw, rh);
   return cudaGetLastError();
 }
 

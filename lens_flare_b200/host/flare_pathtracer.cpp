@@ -105,8 +105,17 @@ void PathTracer::find_sun_pos() {
 
 // pathtracer.cpp:714-762
 void PathTracer::generate_ghost_buffer() {
-  ghost_buffer.clear();
-  ghost_buffer.resize(frame_w_, frame_h_);
+  const bool rect_mode = dirty_rect_mode && params.mode != LFB_MODE_EXACT_GRID;
+  const bool reuse = rect_mode && ghost_buffer.w == frame_w_ && ghost_buffer.h == frame_h_ &&
+                     ghost_buffer.data.size() == frame_w_ * frame_h_ && frame_w_ > 0;
+  if (reuse) {  // same result as clear() + resize() (:719-720): only the previous frame's rectangle is non-zero
+    for (int y = dirty_[1]; y <= dirty_[3]; y++)
+      std::memset(static_cast<void*>(&ghost_buffer.data[(size_t)dirty_[0] + (size_t)y * frame_w_]), 0, sizeof(Vector3D) * (size_t)(dirty_[2] - dirty_[0] + 1));
+  } else {
+    ghost_buffer.clear();
+    ghost_buffer.resize(frame_w_, frame_h_);
+  }
+  dirty_[0] = dirty_[1] = 0; dirty_[2] = dirty_[3] = -1;
   if (axis_ray.x == 0 && axis_ray.y == 0) return;  // :724-726
   if (!camera || !camera->ghost_aperture_texture || camera->ghost_aperture_texture->aperture.empty())
     throw Error(LFB_ERR_STATE, "camera->ghost_aperture_texture is not loaded");
@@ -143,8 +152,12 @@ void PathTracer::generate_ghost_buffer() {
       lights.push_back(lt);
     }
   }
-  check(lfb_render_ghosts(engine_, lights.data(), (int)lights.size(), &params, ghost_buffer.data.data(), sizeof(Vector3D), LFB_F64x3, 0),
-        "lfb_render_ghosts");
+  if (rect_mode)
+    check(lfb_render_ghosts_rect(engine_, lights.data(), (int)lights.size(), &params, ghost_buffer.data.data(), sizeof(Vector3D), LFB_F64x3, dirty_),
+          "lfb_render_ghosts_rect");
+  else
+    check(lfb_render_ghosts(engine_, lights.data(), (int)lights.size(), &params, ghost_buffer.data.data(), sizeof(Vector3D), LFB_F64x3, 0),
+          "lfb_render_ghosts");
 }
 
 float PathTracer::last_trace_ms() const {

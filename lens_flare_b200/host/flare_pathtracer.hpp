@@ -118,6 +118,13 @@ class PathTracer {
   lfb_params params;
   void set_lens(const lfb_lens& lens);  // default: the built-in prescription, RGB
   const lfb_lens& lens() const { return lens_; }
+  // Dirty-rectangle mode (used for REF_QUADS and PARAXIAL_GRID, whose ghosts are compact): ghost_buffer stays allocated
+  // between renders of the same size, only the rectangle the previous frame wrote is cleared on the host and only the
+  // rectangle the new frame deposits into comes back over PCIe (lfb_render_ghosts_rect) -- instead of zero-filling and
+  // copying W x H x 24 bytes every render.  ghost_buffer must then only be written by generate_ghost_buffer(); call
+  // ghost_buffer.clear() to force a full reset.  EXACT_GRID ghosts throw stray rays across the frame, so that mode
+  // always takes the full-frame path.
+  bool dirty_rect_mode = true;
   // stats of the last generate_ghost_buffer(): device ms of the trace kernels and of the whole call
   float last_trace_ms() const;
   float last_frame_ms() const;
@@ -130,6 +137,7 @@ class PathTracer {
   bool lens_dirty_ = true;
   const CameraApertureTexture* uploaded_ = nullptr;
   size_t frame_w_ = 0, frame_h_ = 0;
+  int dirty_[4] = {0, 0, -1, -1};  // what the last frame wrote into ghost_buffer
 };
 
 }  // namespace lfb

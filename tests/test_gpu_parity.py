@@ -422,3 +422,35 @@ def test_cpp_facade_end_to_end(golden, apertures, port, tmp_path):
     p = capi.make_params(capi.MODE_EXACT_GRID, 640, 360, grid_n=64, pair_set=capi.PAIRS_ALL, include_direct=1)
     want = port.render(lens, apertures["pent_11"], lt, p)
     assert want.any() and np.allclose(info["sum"], want.reshape(-1, 3).sum(0), rtol=2e-3)
+
+
+@pytest.mark.parametrize("mode", [capi.MODE_REF_QUADS, capi.MODE_PARAXIAL_GRID, capi.MODE_EXACT_GRID])
+def test_dirty_rectangle_render_equals_full_frame(engine, apertures, mode):
+    """lfb_render_ghosts_rect writes exactly the full frame's pixels inside the rectangle it reports, the full frame is
+    zero outside it, and pixels outside the rectangle are left untouched -- across consecutive frames that move the sun
+    (the engine clears only the rectangle its previous frame dirtied)."""
+    engine.set_lens(capi.builtin_lens(3, 550.0))
+    engine.set_aperture(apertures["pentbig500_14"])
+    W, H = 960, 540
+    p = capi.make_params(mode, W, H, grid_n=96, pair_set=capi.PAIRS_ALL if mode != capi.MODE_REF_QUADS else capi.PAIRS_REF,
+                         include_direct=int(mode != capi.MODE_REF_QUADS))
+    suns = [(0.45, 0.55), (0.8, 0.25), (0.45, 0.55), (0.02, 0.97)]
+    for stride_lanes in (3, 4):
+        for (sx, sy) in suns:
+            theta = capi.physical_theta(sx, sy) if mode == capi.MODE_EXACT_GRID else None
+            lt = [capi.make_light(sx, sy, theta=theta)]
+            full = engine.render_ghosts(lt, p)
+            buf = np.full((H, W, stride_lanes), -5.0)
+            rect = engine.render_ghosts_rect(lt, p, buf, stride=8 * stride_lanes)
+            assert rect is not None
+            x0, y0, x1, y1 = rect
+            assert 0 <= x0 <= x1 < W and 0 <= y0 <= y1 < H
+            assert np.array_equal(buf[y0:y1 + 1, x0:x1 + 1, :3], full[y0:y1 + 1, x0:x1 + 1])
+            outside = np.ones((H, W), bool)
+            outside[y0:y1 + 1, x0:x1 + 1] = False
+            assert not full[outside].any()
+            assert (buf[outside] == -5.0).all()
+            if mode != capi.MODE_EXACT_GRID:  # exact ghosts throw a few stray rays far out: their box can approach the frame
+                assert (x1 - x0 + 1) * (y1 - y0 + 1) < 0.25 * W * H
+    # empty frame
+    assert engine.render_ghosts_rect([], p, np.zeros((H, W, 3))) is None
