@@ -138,6 +138,8 @@ struct lfb_engine {
   Step* d_progs = nullptr;   // FP32 EXACT_GRID step programs, LFB_MAX_STEPS per job
   Step* h_progs = nullptr;   // pinned staging
   Step* d_dump_prog = nullptr;
+  float2* d_lut = nullptr;   // reflectance tables, kLutSize entries per (lambda, surface, direction)
+  bool use_lut = true;       // LFB_EXACT_WEIGHTS=closed selects the closed-form two-pass kernel instead
   int min_blocks = 6;        // register-allocation target of the FP32 exact kernel, CTAs/SM (LFB_EXACT_MINB=4|5|6)
   int patch = 1;             // rays per thread in pass 1 of the FP32 exact kernel (LFB_EXACT_PATCH=1|2|4)
   // owned buffers of the host-memory API
@@ -205,9 +207,68 @@ FrameGeom make_geom(const lfb_engine* e, const lfb_params& P) {
   g.tex_w = e->tex_w; g.tex_h = e->tex_h;
   g.fp_scale = ldexp(1.0, P.fixed_point_bits > 0 ? P.fixed_point_bits : 40);
   g.P = (float)e->lens.entrance_half_height; g.h_stop = (float)e->lens.stop_half_height;
+  g.cell = 2.f * g.P / (float)P.grid_n;
+  g.mask_su = 0.5f * (float)e->tex_w / g.h_stop; g.mask_ou = 0.5f * (float)e->tex_w;
+  g.mask_sv = -0.5f * (float)e->tex_h / g.h_stop; g.mask_ov = 0.5f * (float)e->tex_h;
+  g.lut = (e->use_lut && P.mode == LFB_MODE_EXACT_GRID && P.precision == LFB_FP32) ? e->d_lut : nullptr;
   g.bbox = e->track_bbox ? e->d_bbox : nullptr;
   g.patch = e->patch; g.pad = e->min_blocks;
   return g;
+}
+
+// Polarisation-averaged reflectance of one interface as a function of s2 = sin^2(theta0): bare Fresnel, or the exact
+// single-layer (Airy) film of index max(sqrt(n0 n2), 1.38) and quarter-wave thickness at lambda0.  Host-side, double:
+// it fills the tables the FP32 kernel interpolates; it is evaluated per table node, never per ray.
+double interface_reflectance(double n0, double n2, double s2, double lambda0, double lambda) {
+  if (n0 == n2) return 0.0;
+  const double cos0 = sqrt(1.0 - s2);
+  const double e2 = n0 / n2, k2 = 1.0 - e2 * e2 * s2;
+  if (k2 < 0) return 1.0;  // total internal reflection
+  const double cos2 = sqrt(k2);
+  if (lambda0 <= 0) {
+    const double a = n0 * cos0 + n2 * cos2, b = n2 * cos0 + n0 * cos2;
+    if (a == 0 || b == 0) return 1.0;
+    const double rs = (n0 * cos0 - n2 * cos2) / a, rp = (n2 * cos0 - n0 * cos2) / b;
+    return 0.5 * (rs * rs + rp * rp);
+  }
+  double n1 = sqrt(n0 * n2);
+  if (n1 < 1.38) n1 = 1.38;
+  const double e1 = n0 / n1, k1 = 1.0 - e1 * e1 * s2;
+  if (k1 < 0) return 1.0;
+  const double cos1 = sqrt(k1);
+  const double cd = cos(3.14159265358979323846 * lambda0 * cos1 / lambda);  // 4 pi n1 d1 cos1 / lambda, d1 = lambda0 / (4 n1)
+  auto ratio = [](double a, double b) { return (a + b) == 0 ? 1.0 : (a - b) / (a + b); };
+  const double r01s = ratio(n0 * cos0, n1 * cos1), r12s = ratio(n1 * cos1, n2 * cos2);
+  const double r01p = ratio(n1 * cos0, n0 * cos1), r12p = ratio(n2 * cos1, n1 * cos2);
+  const double ps = r01s * r12s, pp = r01p * r12p;
+  const double Rs = (r01s * r01s + r12s * r12s + 2 * ps * cd) / (1 + ps * ps + 2 * ps * cd);
+  const double Rp = (r01p * r01p + r12p * r12p + 2 * pp * cd) / (1 + pp * pp + 2 * pp * cd);
+  return 0.5 * (Rs + Rp);
+}
+
+// Tables for every (wavelength, surface, direction): index (lam * n_surfaces + k) * 2 + (backward ? 1 : 0).
+void build_reflectance_tables(const lfb_lens& L, std::vector<float2>& out) {
+  out.assign((size_t)L.n_lambda * L.n_surfaces * 2 * kLutSize, make_float2(0.f, 0.f));
+  for (int lam = 0; lam < L.n_lambda; lam++)
+    for (int k = 0; k < L.n_surfaces; k++)
+      for (int dir = 0; dir < 2; dir++) {
+        const double na = k == 0 ? 1.0 : (double)L.ior[lam][k - 1], nb = (double)L.ior[lam][k];
+        const double n0 = dir ? nb : na, n2 = dir ? na : nb;
+        float2* T = &out[((size_t)(lam * L.n_surfaces + k) * 2 + dir) * kLutSize];
+        // table variable v = cosine of the ray's angle in the RARER medium (c0 when entering the denser medium, c2
+        // otherwise): R is analytic in v on [0, 1] -- R -> 1 linearly as v -> 0, at grazing incidence or at the critical
+        // angle -- whereas in sin^2(theta0) it has a square-root singularity at the critical angle
+        auto R_of = [&](double v) {
+          const double s2 = n0 <= n2 ? 1.0 - v * v : (1.0 - v * v) * (n2 / n0) * (n2 / n0);
+          return interface_reflectance(n0, n2, s2 < 0 ? 0 : s2, L.coating_lambda0_nm[k], L.lambda_nm[lam]);
+        };
+        double prev = R_of(0.0);
+        for (int i = 0; i < kLutSize; i++) {
+          const double next = R_of((double)(i + 1) / kLutSize);
+          T[i] = make_float2((float)prev, (float)(next - prev));
+          prev = next;
+        }
+      }
 }
 
 // Flatten ghost (i, j) at wavelength lam into the FP32 step program (exact_f32.cuh): the surface sequence
@@ -219,7 +280,7 @@ int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, St
   auto push = [&](int k, int op, bool forward) {
     Step S;
     memset(&S, 0, sizeof(S));
-    S.k = k;
+    S.lut = (lam * L.n_surfaces + (k < n ? k : 0)) * 2 + (forward ? 0 : 1);
     S.dz = (float)(D.zv_d[prev] - D.zv_d[k]);
     prev = k;
     S.eta = S.eta2 = 1.f;
@@ -272,6 +333,10 @@ void fill_job(const lfb_engine* e, const lfb_params& P, const lfb_light& lt, con
   const double cell = 2 * e->lens.entrance_half_height / P.grid_n;
   const double area = cell * cell * J->ppu * J->ppu;
   for (int c = 0; c < 3; c++) J->chan[c] = (double)lt.radiance[c] * (double)e->lens.rgb_weight[id.lambda][c] * area;
+  const double scale = ldexp(1.0, P.fixed_point_bits > 0 ? P.fixed_point_bits : 40);
+  J->f_sin_t = (float)J->sin_t; J->f_cos_t = (float)J->cos_t;
+  J->f_sx = (float)J->sx; J->f_sy = (float)J->sy; J->f_cs = (float)J->cs; J->f_sn = (float)J->sn; J->f_ppu = (float)J->ppu;
+  for (int c = 0; c < 3; c++) J->f_chan[c] = (float)J->chan[c] * (float)scale;
 }
 
 // Build + upload this shard's jobs unless the frame description is unchanged.
@@ -416,6 +481,7 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   if (rc == cudaSuccess) { e->h_bbox[0] = e->h_bbox[1] = 0x7fffffff; e->h_bbox[2] = e->h_bbox[3] = -0x7fffffff; }
   if (const char* env = getenv("LFB_EXACT_PATCH")) e->patch = atoi(env);
   if (const char* env = getenv("LFB_EXACT_MINB")) e->min_blocks = atoi(env);
+  if (const char* env = getenv("LFB_EXACT_WEIGHTS")) e->use_lut = strcmp(env, "closed") != 0;
   if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
   *out = e;
   return LFB_OK;
@@ -426,7 +492,7 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
-  cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox);
+  cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox); cudaFree(e->d_lut);
   if (e->h_bbox) cudaFreeHost(e->h_bbox);
   if (e->h_progs) cudaFreeHost(e->h_progs);
   cudaFree(e->d_tex); cudaFree(e->d_jobs); cudaFree(e->d_dump_job); cudaFree(e->d_accum); cudaFree(e->d_out);
@@ -563,6 +629,14 @@ extern "C" int lfb_set_lens(lfb_engine* e, const lfb_lens* L) {
   if (np > 0) CU(cudaMemcpy(e->d_pairs, pairs, sizeof(int) * 2 * (size_t)np, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(e->d_rgbw, L->rgb_weight, sizeof(float) * 3 * (size_t)L->n_lambda, cudaMemcpyHostToDevice));
   e->n_ref_pairs = np; e->n_ref_ghosts = 0;
+  {
+    std::vector<float2> lut;
+    build_reflectance_tables(*L, lut);
+    cudaFree(e->d_lut);
+    e->d_lut = nullptr;
+    CU(cudaMalloc((void**)&e->d_lut, sizeof(float2) * lut.size()));
+    CU(cudaMemcpy(e->d_lut, lut.data(), sizeof(float2) * lut.size(), cudaMemcpyHostToDevice));
+  }
   e->job_key.clear();
   e->has_lens = true;
   return LFB_OK;

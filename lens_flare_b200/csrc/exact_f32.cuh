@@ -97,17 +97,28 @@ struct RayOut {
   unsigned flags;        // FLAGS variant only
 };
 
+// Reflectance from the interface's table: R as a function of v = the cosine of the ray's angle in the RARER of the two
+// media (in which R is analytic: R -> 1 linearly as v -> 0, i.e. at grazing incidence or at the critical angle), 1024
+// intervals, linear interpolation of (R_i, R_{i+1} - R_i) pairs built on the host in double from the exact formulas
+// (one 8-byte load, ~10 instructions, instead of ~60 for the closed-form coated interface).
+__device__ __forceinline__ float reflectance_lut(const float2* __restrict__ lut, int table, float v) {
+  const float t = fminf(fmaxf(v, 0.f), 1.f) * (float)kLutSize;  // fmaxf(NaN, 0) = 0: beyond the critical angle R = 1
+  const int i = min((int)t, kLutSize - 1);
+  const float2 e = __ldg(lut + table * kLutSize + i);
+  return fmaf(t - (float)i, e.y, e.x);
+}
+
 // Trace one ray through a step program.
-//   WEIGHTS    accumulate the Fresnel / coating weight (else geometry + mask only)
+//   WEIGHTS    0: geometry + mask only; 1: closed-form Fresnel / coating weights; 2: tabulated weights
 //   MIRROR     also look the mask up at (xa, -ya) for the mirror-image ray
 //   FLAGS      parity-instrument variant: classify the death (missed / vignetted / TIR), and let rays the
 //              mask stopped continue with weight 0 so that their positions stay comparable with the oracle
 // Every step runs the same straight-line code (planes are c = 0 surfaces with an infinite clear radius); a
 // missed surface or a total internal reflection turns the state into NaNs, which the next clear-radius
 // test catches, so the throughput variants carry ONE death test per step.
-template <bool WEIGHTS, bool MIRROR, bool FLAGS>
-__device__ __forceinline__ bool trace(const Step* __restrict__ prog, int n_steps, const MaskGeom& M, float x, float y,
-                                      float sin_t, float cos_t, RayOut& o) {
+template <int WEIGHTS, bool MIRROR, bool FLAGS>
+__device__ __forceinline__ bool trace(const Step* __restrict__ prog, int n_steps, const MaskGeom& M, const float2* __restrict__ lut,
+                                      float x, float y, float sin_t, float cos_t, RayOut& o) {
   float ox = x, oy = y, oz = 0.f, dx = sin_t, dy = 0.f, dz = cos_t, w = 1.f, ma = 1.f, mb = 1.f;
   if (FLAGS) { o.flags = 0; o.xa = o.ya = CUDART_NAN_F; }
 #pragma unroll 1
@@ -141,7 +152,8 @@ __device__ __forceinline__ bool trace(const Step* __restrict__ prog, int n_steps
     const float nx = -c * ox, ny = -c * oy, nz = fmaf(-c, oz, 1.f);
     const float nd = fmaf(nx, dx, fmaf(ny, dy, nz * dz));
     const float c0 = fabsf(nd);
-    const float k2 = fmaf(-S.eta2, fmaf(-c0, c0, 1.f), 1.f);
+    const float s2 = fmaf(-c0, c0, 1.f);
+    const float k2 = fmaf(-S.eta2, s2, 1.f);
     const float c2 = fsqrt(k2);  // NaN beyond the critical angle
     const bool refl = op == STEP_REFLECT;
     if (FLAGS && !refl && k2 < 0.f) { o.flags |= LFB_RAY_TIR; return false; }
@@ -149,8 +161,11 @@ __device__ __forceinline__ bool trace(const Step* __restrict__ prog, int n_steps
     const float g = __int_as_float(__float_as_int(fmaf(eta, c0, -c2)) ^ (~__float_as_int(nd) & 0x80000000));
     const float alpha = refl ? 1.f : eta, beta = refl ? -2.f * nd : g;
     dx = fmaf(alpha, dx, beta * nx); dy = fmaf(alpha, dy, beta * ny); dz = fmaf(alpha, dz, beta * nz);
-    if (WEIGHTS) {
+    if (WEIGHTS == 1) {
       const float R = (k2 < 0.f) ? 1.f : reflectance(S, c0, c2);
+      w *= refl ? R : 1.f - R;
+    } else if (WEIGHTS == 2) {
+      const float R = reflectance_lut(lut, S.lut, eta > 1.f ? c2 : c0);
       w *= refl ? R : 1.f - R;
     }
   }
@@ -163,8 +178,8 @@ struct PixMap {
 };
 __device__ __forceinline__ void to_pixel(const PixMap& P, float xs, float ys, float& px, float& py) {
   const float X = -P.ppu * xs, Y = P.ppu * ys;
-  px = P.sx + (X * P.cs - Y * P.sn);
-  py = P.sy + (X * P.sn + Y * P.cs);
+  px = P.sx + fmaf(X, P.cs, -__fmul_rn(Y, P.sn));
+  py = P.sy + fmaf(X, P.sn, __fmul_rn(Y, P.cs));
 }
 
 constexpr int kThreads = 256;
@@ -197,12 +212,14 @@ __device__ __forceinline__ void splat(const SplatCtx& C, float px, float py, flo
   int ix, iy, ntap;
   float wt[4];
   if (C.bilinear) {
-    const float qx = px - 0.5f, qy = py - 0.5f;
+    const float qx = __fsub_rn(px, 0.5f), qy = __fsub_rn(py, 0.5f);
     const float fx0 = floorf(qx), fy0 = floorf(qy);
-    const float fx = qx - fx0, fy = qy - fy0;
+    const float fx = __fsub_rn(qx, fx0), fy = __fsub_rn(qy, fy0);
     ix = (int)fx0; iy = (int)fy0; ntap = 4;
-    wt[0] = w * ((1.f - fx) * (1.f - fy)); wt[1] = w * (fx * (1.f - fy));
-    wt[2] = w * ((1.f - fx) * fy); wt[3] = w * (fx * fy);
+    // explicit roundings: no FMA contraction, so every instantiation of the kernel produces the same bits
+    const float gx = __fsub_rn(1.f, fx), gy = __fsub_rn(1.f, fy);
+    wt[0] = __fmul_rn(w, __fmul_rn(gx, gy)); wt[1] = __fmul_rn(w, __fmul_rn(fx, gy));
+    wt[2] = __fmul_rn(w, __fmul_rn(gx, fy)); wt[3] = __fmul_rn(w, __fmul_rn(fx, fy));
   } else {
     ix = (int)floorf(px); iy = (int)floorf(py); ntap = 1;
     wt[0] = w;
@@ -276,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat_kernel(const Job* 
     float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a < g.N && bp < half_rows) {
       RayOut o;
-      if (trace<false, true, false>(s_prog, n_steps, M, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o)) {
+      if (trace<0, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o)) {
         int x0, y0, x1, y1;
         if (o.wa > 0.f) {
           to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
@@ -335,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat_kernel(const Job* 
     const int la = (id & 0x3fff) % PW, lb = (id & 0x3fff) / PW;
     const int a = a0 + la, b = g.N - 1 - (b0 + lb);
     RayOut o;
-    if (!trace<true, true, false>(s_prog, n_steps, M, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o)) continue;
+    if (!trace<1, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o)) continue;
     const float4 pp = s_qp[q];
     if ((id & (1u << 14)) && o.wa > 0.f) splat(C, pp.x, pp.y, o.wa);
     if ((id & (2u << 14)) && o.wb > 0.f) splat(C, pp.z, pp.w, o.wb);
@@ -349,6 +366,162 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat_kernel(const Job* 
       const int p = q / 3, c = q - 3 * p;
       const int jy = C.ty0 + p / C.tw, jx = C.tx0 + (p - (p / C.tw) * C.tw);
       atomicAdd(accum + 3 * ((size_t)jx + (size_t)jy * g.W) + c, v);
+    }
+  }
+}
+
+// v4: ONE pass.  With tabulated reflectances the weight costs ~10 instructions per surface, so it is carried along in
+// the single trace instead of re-tracing the survivors: the queue holds each surviving ray pair's sensor pixels AND
+// weights, and the second phase only splats (dense warps) into the shared-memory tile.  Everything ray-independent
+// (float copies of the job constants, cell size, mask mapping) is precomputed on the host: the per-CTA prologue is a few
+// loads, which matters because a CTA lives for only ~10 surface steps per ray.
+__device__ __forceinline__ void splat1(const SplatCtx& C, float px, float py, float w) {
+  int ix, iy;
+  float wt[4];
+  if (C.bilinear) {
+    const float qx = __fsub_rn(px, 0.5f), qy = __fsub_rn(py, 0.5f);
+    const float fx0 = floorf(qx), fy0 = floorf(qy);
+    const float fx = __fsub_rn(qx, fx0), fy = __fsub_rn(qy, fy0);
+    ix = (int)fx0; iy = (int)fy0;
+    // explicit roundings: no FMA contraction, so every instantiation of the kernel produces the same bits
+    const float gx = __fsub_rn(1.f, fx), gy = __fsub_rn(1.f, fy);
+    wt[0] = __fmul_rn(w, __fmul_rn(gx, gy)); wt[1] = __fmul_rn(w, __fmul_rn(fx, gy));
+    wt[2] = __fmul_rn(w, __fmul_rn(gx, fy)); wt[3] = __fmul_rn(w, __fmul_rn(fx, fy));
+  } else {
+    ix = (int)floorf(px); iy = (int)floorf(py);
+    wt[0] = w; wt[1] = wt[2] = wt[3] = 0.f;
+  }
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int jx = ix + (t & 1), jy = iy + (t >> 1);
+    if (wt[t] == 0.f || jx < 0 || jx >= C.W || jy < 0 || jy >= C.H) continue;
+    unsigned long long* dst = C.tile ? C.tile + 3 * ((jy - C.ty0) * C.tw + (jx - C.tx0)) : C.accum + 3 * ((size_t)jx + (size_t)jy * C.W);
+    // channels a wavelength does not feed (RGB lenses: two of three) are skipped without converting anything
+    if (C.ch0 != 0.f) { const long long q = __float2ll_rn(__fmul_rn(wt[t], C.ch0)); if (q) atomicAdd(dst + 0, (unsigned long long)q); }
+    if (C.ch1 != 0.f) { const long long q = __float2ll_rn(__fmul_rn(wt[t], C.ch1)); if (q) atomicAdd(dst + 1, (unsigned long long)q); }
+    if (C.ch2 != 0.f) { const long long q = __float2ll_rn(__fmul_rn(wt[t], C.ch2)); if (q) atomicAdd(dst + 2, (unsigned long long)q); }
+  }
+}
+
+template <int RX, int RY, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) exact_splat1_kernel(const Job* __restrict__ jobs, const Step* __restrict__ progs,
+                                                                      FrameGeom g, const float* __restrict__ tex,
+                                                                      unsigned long long* __restrict__ accum) {
+  constexpr int RPT = RX * RY, PATCH = RPT * kThreads, PW = 16 * RX, PH = 16 * RY;
+  static_assert(kTilePx <= kThreads, "one thread per tile pixel in the zero / flush loops");
+  __shared__ Step s_prog[LFB_MAX_STEPS];
+  __shared__ unsigned long long s_tile[kTilePx * 3];
+  __shared__ float4 s_qp[PATCH];  // survivor queue: (pxA, pyA, pxB, pyB)
+  __shared__ float2 s_qw[PATCH];  //                 (wA, wB); 0 = that image of the pair does not land
+  __shared__ int s_count, s_bbox[4];
+
+  const int half_rows = (g.N + 1) / 2;
+  const int patches_x = (g.N + PW - 1) / PW;
+  const int patches_per_job = patches_x * ((half_rows + PH - 1) / PH);
+  const int job_id = blockIdx.x / patches_per_job;
+  const int patch = blockIdx.x - job_id * patches_per_job;
+  const int a0 = (patch % patches_x) * PW, b0 = (patch / patches_x) * PH;
+  const Job& J = jobs[job_id];
+  const int n_steps = J.n_steps;
+  const int tid = threadIdx.x;
+  {
+    const float4* src = reinterpret_cast<const float4*>(progs + (size_t)job_id * LFB_MAX_STEPS);
+    float4* dst = reinterpret_cast<float4*>(s_prog);
+    for (int q = tid; q < n_steps * 3; q += kThreads) dst[q] = __ldg(src + q);
+    if (tid == 0) { s_count = 0; s_bbox[0] = s_bbox[1] = 0x7fffffff; s_bbox[2] = s_bbox[3] = -0x7fffffff; }
+  }
+  __syncthreads();
+
+  const float P = g.P, cell = g.cell;
+  const float sin_t = J.f_sin_t, cos_t = J.f_cos_t;
+  MaskGeom M;
+  M.tex = tex; M.tw = g.tex_w; M.th = g.tex_h;
+  M.su = g.mask_su; M.ou = g.mask_ou; M.sv = g.mask_sv; M.ov = g.mask_ov;
+  PixMap PM;
+  PM.sx = J.f_sx; PM.sy = J.f_sy; PM.cs = J.f_cs; PM.sn = J.f_sn; PM.ppu = J.f_ppu;
+  const bool bilinear = g.splat == LFB_SPLAT_BILINEAR;
+
+  // ---- phase 1: trace (geometry, mask, tabulated weights); queue what lands ------------------------
+  int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
+#pragma unroll 1
+  for (int r = 0; r < RPT; r++) {
+    const int la = (tid & 15) + 16 * (r % RX), lb = (tid >> 4) + 16 * (r / RX);
+    const int a = a0 + la, bp = b0 + lb;
+    const int b = g.N - 1 - bp;
+    float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 ww = make_float2(0.f, 0.f);
+    if (a < g.N && bp < half_rows) {
+      RayOut o;
+      if (trace<2, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o)) {
+        int x0, y0, x1, y1;
+        if (o.wa > 0.f) {
+          to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
+          if (footprint(bilinear, pp.x, pp.y, g.W, g.H, x0, y0, x1, y1)) {
+            ww.x = o.wa; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+          }
+        }
+        if (o.wb > 0.f && b != bp) {
+          to_pixel(PM, o.xs, -o.ys, pp.z, pp.w);
+          if (footprint(bilinear, pp.z, pp.w, g.W, g.H, x0, y0, x1, y1)) {
+            ww.y = o.wb; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+          }
+        }
+      }
+    }
+    const bool lands = ww.x > 0.f || ww.y > 0.f;
+    const unsigned ballot = __ballot_sync(0xffffffffu, lands);
+    if (ballot) {
+      const int lane = tid & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_count, __popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (lands) {
+        const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+        s_qp[slot] = pp; s_qw[slot] = ww;
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, bx1 >= bx0)) {
+    bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+    bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+    if ((tid & 31) == 0) {
+      atomicMin(&s_bbox[0], bx0); atomicMin(&s_bbox[1], by0);
+      atomicMax(&s_bbox[2], bx1); atomicMax(&s_bbox[3], by1);
+    }
+  }
+  __syncthreads();
+  const int count = s_count;
+  if (count == 0) return;
+  if (tid == 0) grow_bbox(g.bbox, s_bbox[0], s_bbox[1], s_bbox[2], s_bbox[3]);
+  SplatCtx C;
+  C.tx0 = s_bbox[0]; C.ty0 = s_bbox[1];
+  C.tw = s_bbox[2] - C.tx0 + 1;
+  const int area = C.tw * (s_bbox[3] - C.ty0 + 1);
+  const bool use_tile = area <= kTilePx;
+  C.tile = use_tile ? s_tile : nullptr;
+  C.accum = accum; C.W = g.W; C.H = g.H; C.bilinear = bilinear;
+  if (use_tile) {  // one thread per tile pixel
+    if (tid < area) { s_tile[3 * tid] = 0ull; s_tile[3 * tid + 1] = 0ull; s_tile[3 * tid + 2] = 0ull; }
+    __syncthreads();
+  }
+  // ---- phase 2: splat the queue (dense warps) -----------------------------------------------------------
+  C.ch0 = J.f_chan[0]; C.ch1 = J.f_chan[1]; C.ch2 = J.f_chan[2];
+  for (int q = tid; q < count; q += kThreads) {
+    const float4 pp = s_qp[q];
+    const float2 ww = s_qw[q];
+    if (ww.x > 0.f) splat1(C, pp.x, pp.y, ww.x);
+    if (ww.y > 0.f) splat1(C, pp.z, pp.w, ww.y);
+  }
+  if (!use_tile) return;
+  __syncthreads();
+  if (tid < area) {  // flush: one global atomic per touched (pixel, channel)
+    const int jy = (int)(((float)tid + 0.5f) * frcp((float)C.tw));  // tid / tw, exact for these small integers
+    const int jx = tid - jy * C.tw;
+    unsigned long long* dst = accum + 3 * ((size_t)(C.tx0 + jx) + (size_t)(C.ty0 + jy) * g.W);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const unsigned long long v = s_tile[3 * tid + c];
+      if (v) atomicAdd(dst + c, v);
     }
   }
 }
@@ -379,8 +552,10 @@ __global__ void __launch_bounds__(kThreads) exact_dump_kernel(const Job* __restr
   PixMap PM;
   PM.sx = (float)J.sx; PM.sy = (float)J.sy; PM.cs = (float)J.cs; PM.sn = (float)J.sn; PM.ppu = (float)J.ppu;
   RayOut o;
-  const bool alive = trace<true, false, true>(s_prog, n_steps, M, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P),
-                                              (float)J.sin_t, (float)J.cos_t, o);
+  const bool alive = g.lut ? trace<2, false, true>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P),
+                                                   (float)J.sin_t, (float)J.cos_t, o)
+                           : trace<1, false, true>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P),
+                                                   (float)J.sin_t, (float)J.cos_t, o);
   lfb_ray_hit rec;
   rec.x_ap = o.xa; rec.y_ap = o.ya; rec.flags = o.flags; rec.pad = 0;
   if (alive) {

@@ -21,7 +21,12 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
   };
   // patch shape (rays per thread in pass 1) x resident CTAs per SM the register allocation targets
   const int minb = g.pad;  // 0 (default) -> 4
-#define LFB_LAUNCH(RX, RY, MB) xf32::exact_splat_kernel<RX, RY, MB><<<blocks(RX, RY), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum)
+  // g.lut set: the one-pass kernel with tabulated reflectances (v4); else the two-pass closed-form kernel (v3)
+#define LFB_LAUNCH(RX, RY, MB)                                                                                              \
+  do {                                                                                                                      \
+    if (g.lut) xf32::exact_splat1_kernel<RX, RY, MB><<<blocks(RX, RY), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum); \
+    else xf32::exact_splat_kernel<RX, RY, MB><<<blocks(RX, RY), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);        \
+  } while (0)
 #define LFB_PATCH(MB)                       \
   do {                                      \
     if (g.patch >= 4) LFB_LAUNCH(2, 2, MB); \

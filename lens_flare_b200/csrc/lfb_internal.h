@@ -36,6 +36,9 @@ struct Job {
   double sin_t, cos_t;         // EXACT_GRID: direction of the light's parallel bundle
   double cross[3][4];       // entrance -> stop plane, per crossing (m00,m01,m10,m11)
   double full[4];           // entrance -> sensor
+  // the same constants as floats, for the FP32 throughput kernel (no per-CTA double -> float conversions)
+  float f_sin_t, f_cos_t, f_sx, f_sy, f_cs, f_sn, f_ppu, f_pad;
+  float f_chan[4];          // chan * 2^fixed_point_bits
 };
 
 struct FrameGeom {
@@ -44,6 +47,9 @@ struct FrameGeom {
   int tex_w, tex_h;
   double fp_scale;  // 2^fixed_point_bits
   float P, h_stop;  // entrance half height, stop half height
+  float cell;       // 2P / N
+  float mask_su, mask_sv, mask_ou, mask_ov;  // aperture texel of a stop-plane point: u = x*su + ou, v = y*sv + ov
+  const float2* lut;  // reflectance tables R(sin^2 theta0), one per (wavelength, surface, direction): (R_i, R_{i+1} - R_i)
   int* bbox;        // device int[4] = {min_x, min_y, max_x, max_y} of every pixel the frame deposits into (or nullptr)
   int patch, pad;   // FP32 EXACT_GRID tuning: rays per thread in pass 1 (1, 2 or 4); resident CTAs/SM target (0 -> 4)
 };
@@ -52,10 +58,11 @@ struct FrameGeom {
 // ray-independent quantity precomputed on the host.  48 bytes = 3 x float4.
 enum StepOp { STEP_REFRACT = 0, STEP_REFLECT = 1, STEP_PASS = 2, STEP_STOP = 3, STEP_SENSOR = 4 };
 #define LFB_MAX_STEPS (3 * LFB_MAX_SURFACES + 2)
+constexpr int kLutSize = 1024;  // intervals of the table variable (cosine in the rarer medium) on [0, 1]
 struct Step {
   float c, dz, semi2, eta;   // curvature (0: plane); z of the previous vertex minus z of this one; clear radius^2; n0/n2
   float eta2, phase;         // (n0/n2)^2; coating phase factor pi * lambda0 / lambda
-  int op, k;                 // StepOp; surface index (k = n_surfaces for the sensor)
+  int op, lut;               // StepOp; index of the interface's reflectance table (kLutSize float2 entries each)
   float n0, n2, n1, e1sq;    // indices before/after along the ray; film index (0 = bare); (n0/n1)^2
 };
 

@@ -208,7 +208,9 @@ def test_exact_rays_vs_oracle(engine, port, apertures, precision, coat):
             if ratio.size:
                 assert ratio.max() <= 1e-3 and np.median(ratio) <= 1e-5 and np.quantile(ratio, 0.99) <= 2e-4, (i, j, ratio.max())
             live = ok & (want["weight"] > 0) & (got["weight"] > 0)
-            assert np.allclose(got["weight"][live], want["weight"][live], rtol=2e-3)
+            # tabulated reflectances (1024-interval linear interpolation): 2e-3 relative, or 1e-9 absolute where a
+            # coating drives R to ~0 (a -90 dB contribution)
+            assert np.allclose(got["weight"][live], want["weight"][live], rtol=2e-3, atol=1e-9)
         n_live += int((want["weight"] > 0).sum())
     assert n_live > 1000
 
