@@ -185,6 +185,20 @@ int lfb_dump_rays(lfb_engine* e, const lfb_light* light, const lfb_params* param
  * (trace_ray_auto_* results and draw_ghost vertices). Returns the count or <0. */
 int lfb_ref_ghosts(lfb_engine* e, lfb_ref_ghost* out, int cap);
 
+/* ---- starburst (the diffraction pattern of the aperture) ----------------- */
+/* Replaces Camera::aperture_texture (camera.h:173, the -x PNG) for the starburst: texels as CameraApertureTexture::init
+ * produces them; total_value and the bbox of texels > 0 (camera.h:61-73) are derived here. */
+int lfb_set_starburst_aperture(lfb_engine* e, const float* texels, int w, int h);
+/* Replaces PathTracer::raytrace_starburst (pathtracer.cpp:947-1004, called per pixel from raytrace_pixel :881) and
+ * calculate_irradiance_falloff (:1030-1052) for the WHOLE frame: the per-pixel brute-force DFT of the mask becomes two
+ * complex FP64 matrix products on the device.  lights[0] is flare_origins[0] (it alone drives the pattern, :919); every
+ * light's radiance and falloff are summed like the reference does.  flare_radius / flare_intensity are the -n / -i
+ * options (main.cpp:135-152).  The falloff's 16 random samples per pixel become the pixel's 4x4 stratified midpoints.
+ * out: as lfb_render_ghosts (additive = 1 adds to the caller's sampleBuffer-like buffer, as raytrace_pixel :891 does). */
+int lfb_render_starburst(lfb_engine* e, const lfb_light* lights, int n_lights, int width, int height,
+                         double flare_radius, double flare_intensity, void* out, size_t out_stride_bytes,
+                         int out_elem, int additive);
+
 /* ---- device-resident API (multi-GPU sharding, benchmarking) ------------- */
 /* Sensor accumulators: width*height*3 u64 fixed-point sums, owned by the caller. */
 size_t lfb_accum_bytes(int width, int height);

@@ -33,7 +33,7 @@ SYMBOLS = (
     "lfb_abi_version", "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
     "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
     "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
-    "lfb_host_alloc", "lfb_host_free", "lfb_probe_peaks",
+    "lfb_host_alloc", "lfb_host_free", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst",
 )
 
 
@@ -173,6 +173,8 @@ def lib():
     L.lfb_host_alloc.restype = vp
     L.lfb_host_free.argtypes = [vp]
     L.lfb_host_free.restype = None
+    L.lfb_set_starburst_aperture.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.c_int]
+    L.lfb_render_starburst.argtypes = [vp, LiP, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, C.c_size_t, C.c_int, C.c_int]
     L.lfb_probe_peaks.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     if L.lfb_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {L.lfb_abi_version()} != {ABI_VERSION}; rebuild")
@@ -272,6 +274,18 @@ class Engine:
         check(lib().lfb_render_ghosts_rect(self._h, lights_array(lights), len(lights), C.byref(params),
                                            out.ctypes.data, stride, elem, rect))
         return None if rect[2] < rect[0] else tuple(rect)
+
+    def set_starburst_aperture(self, texels):
+        tex = np.ascontiguousarray(texels, np.float32)
+        check(lib().lfb_set_starburst_aperture(self._h, tex.ctypes.data_as(C.POINTER(C.c_float)), tex.shape[1], tex.shape[0]))
+
+    def render_starburst(self, lights, width, height, flare_radius, flare_intensity, out=None, elem=F64x3, additive=False):
+        """The whole frame of PathTracer::raytrace_starburst: (H, W, 3)."""
+        if out is None:
+            out = np.empty((height, width, 3), np.float64 if elem == F64x3 else np.float32)
+        check(lib().lfb_render_starburst(self._h, lights_array(lights), len(lights), width, height, flare_radius, flare_intensity,
+                                         out.ctypes.data, out.strides[1], elem, int(additive)))
+        return out
 
     def dump_rays(self, light, params, i, j, lam):
         out = np.zeros(params.grid_n * params.grid_n, RAY_HIT_DTYPE)

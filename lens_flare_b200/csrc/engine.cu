@@ -155,6 +155,14 @@ struct lfb_engine {
   int* d_pairs = nullptr;
   float* d_rgbw = nullptr;
   int n_ref_pairs = 0, n_ref_ghosts = 0;
+  // starburst (lfb_set_starburst_aperture / lfb_render_starburst)
+  float* d_star_tex = nullptr;
+  int star_w = 0, star_h = 0, star_bbox[4] = {0, 0, -1, -1};
+  double star_total = 0;
+  char* d_star_scratch = nullptr;
+  size_t star_scratch_cap = 0;
+  double* d_star_lights = nullptr;
+  size_t star_lights_cap = 0;
   // dirty-rectangle path (lfb_render_ghosts_rect)
   int* d_bbox = nullptr;      // device {min_x, min_y, max_x, max_y} of the pixels the frame deposits into
   int* h_bbox = nullptr;      // pinned: [0..3] reset pattern, [4..7] read-back
@@ -493,6 +501,7 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
   cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox); cudaFree(e->d_lut);
+  cudaFree(e->d_star_tex); cudaFree(e->d_star_scratch); cudaFree(e->d_star_lights);
   if (e->h_bbox) cudaFreeHost(e->h_bbox);
   if (e->h_progs) cudaFreeHost(e->h_progs);
   cudaFree(e->d_tex); cudaFree(e->d_jobs); cudaFree(e->d_dump_job); cudaFree(e->d_accum); cudaFree(e->d_out);
@@ -860,6 +869,94 @@ extern "C" int lfb_ref_ghosts(lfb_engine* e, lfb_ref_ghost* out, int cap) {
     CU(cudaStreamSynchronize(e->stream));
   }
   return e->n_ref_ghosts;
+}
+
+// ---------------------------------------------------------------------------
+// starburst
+// ---------------------------------------------------------------------------
+extern "C" int lfb_set_starburst_aperture(lfb_engine* e, const float* texels, int w, int h) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!texels || w < 1 || h < 1 || w > 16384 || h > 16384) return fail(LFB_ERR_INVALID, "bad aperture texture");
+  // what CameraApertureTexture::init keeps beside the texels (camera.h:61-73): total_value and the bbox of texels > 0
+  double total = 0;
+  int bb[4] = {w, w, -1, -1};  // sic: min_y also starts at the width (camera.h:55)
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const float v = texels[(size_t)y * w + x];
+      total += v;
+      if (v > 0) {
+        if (x < bb[0]) bb[0] = x;
+        if (y < bb[1]) bb[1] = y;
+        if (x > bb[2]) bb[2] = x;
+        if (y > bb[3]) bb[3] = y;
+      }
+    }
+  CU(cudaStreamSynchronize(e->stream));
+  cudaFree(e->d_star_tex);
+  e->d_star_tex = nullptr;
+  CU(cudaMalloc((void**)&e->d_star_tex, sizeof(float) * (size_t)w * h));
+  CU(cudaMemcpy(e->d_star_tex, texels, sizeof(float) * (size_t)w * h, cudaMemcpyHostToDevice));
+  e->star_w = w; e->star_h = h; e->star_total = total;
+  memcpy(e->star_bbox, bb, sizeof(bb));
+  return LFB_OK;
+}
+
+extern "C" int lfb_render_starburst(lfb_engine* e, const lfb_light* lights, int n_lights, int width, int height,
+                                    double flare_radius, double flare_intensity, void* out, size_t stride, int elem, int additive) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!e->d_star_tex) return fail(LFB_ERR_STATE, "set the starburst aperture first");
+  if (n_lights < 1 || !lights) return fail(LFB_ERR_INVALID, "the starburst needs at least one light (flare_origins[0], pathtracer.cpp:919)");
+  if (width < 1 || height < 1 || width > 32768 || height > 32768 || !out) return fail(LFB_ERR_INVALID, "bad frame/out");
+  if (elem != LFB_F32x3 && elem != LFB_F64x3) return fail(LFB_ERR_INVALID, "unknown out_elem");
+  if (stride < elem_bytes(elem) || stride % (elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
+  if (e->star_bbox[2] < e->star_bbox[0] || !(e->star_total > 0)) return fail(LFB_ERR_INVALID, "the starburst aperture is empty");
+  StarFrame f;
+  memset(&f, 0, sizeof(f));
+  f.W = width; f.H = height; f.tw = e->star_w; f.th = e->star_h;
+  f.bx0 = e->star_bbox[0]; f.by0 = e->star_bbox[1];
+  f.bw = e->star_bbox[2] - e->star_bbox[0] + 1; f.bh = e->star_bbox[3] - e->star_bbox[1] + 1;
+  // compute_phase(0, ...) pathtracer.cpp:918-934: only the FIRST light's origin drives the diffraction pattern
+  f.org_x = ceil(lights[0].ns_x * (double)width);
+  f.org_y = ceil(lights[0].ns_y * (double)height);
+  f.lr = f.org_x - (double)width / 2.0;
+  f.ud = -f.org_y + (double)height / 2.0;
+  f.total = e->star_total;
+  f.flare_radius = flare_radius;
+  f.exponent = -flare_intensity + 3.0;  // :998-1001
+  if (f.exponent <= 0) f.exponent = 2.0;
+  std::vector<double> L(5 * (size_t)n_lights);
+  double rad_sum[3] = {0, 0, 0};
+  for (int l = 0; l < n_lights; l++) {
+    L[5 * l] = lights[l].ns_x * (double)width;   // fo_s, :1041 (no ceil here)
+    L[5 * l + 1] = lights[l].ns_y * (double)height;
+    for (int c = 0; c < 3; c++) { L[5 * l + 2 + c] = lights[l].radiance[c]; rad_sum[c] += lights[l].radiance[c]; }
+  }
+  const size_t npx = (size_t)width * height;
+  const size_t out_bytes = (npx - 1) * stride + elem_bytes(elem);
+  rc = grow(&e->d_out, &e->out_cap, out_bytes);
+  if (rc) return rc;
+  rc = grow(&e->d_star_scratch, &e->star_scratch_cap, starburst_scratch_bytes(f));
+  if (rc) return rc;
+  rc = grow(&e->d_star_lights, &e->star_lights_cap, sizeof(double) * L.size());
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev_frame0, e->stream));
+  CU(cudaMemcpyAsync(e->d_star_lights, L.data(), sizeof(double) * L.size(), cudaMemcpyHostToDevice, e->stream));
+  if (additive) CU(cudaMemcpyAsync(e->d_out, out, out_bytes, cudaMemcpyHostToDevice, e->stream));
+  else if (stride != elem_bytes(elem)) CU(cudaMemsetAsync(e->d_out, 0, out_bytes, e->stream));
+  CU(cudaEventRecord(e->ev_trace0, e->stream));
+  int n = 0;
+  CU(launch_starburst(f, e->d_star_tex, e->d_star_scratch, e->d_star_lights, n_lights, rad_sum, e->d_out, stride, elem, additive, e->stream, &n));
+  e->launches += (uint64_t)n;
+  CU(cudaEventRecord(e->ev_trace1, e->stream));
+  CU(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaEventRecord(e->ev_frame1, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
+  CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
+  e->timed = true;
+  return LFB_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -121,6 +121,19 @@ cudaError_t launch_ref_setup(const RefFrame& f, const int* pairs, const float* r
 cudaError_t launch_ref_raster(const RefFrame& f, const RefTri* tris, int n_tris, const float* tex, void* out,
                               size_t stride, int elem, int additive, const int* rect, cudaStream_t s);
 
+// Starburst (starburst.cu): frame constants of PathTracer::raytrace_starburst (pathtracer.cpp:947-1004)
+struct StarFrame {
+  int W, H, tw, th;
+  int bx0, by0, bw, bh;     // bounding box of mask texels > 0 (CameraApertureTexture min/max_x/y, camera.h:64-70)
+  double lr, ud;            // compute_phase :918-934
+  double org_x, org_y;      // flare origin in pixels (ceil(fo * size))
+  double total;             // CameraApertureTexture::total_value
+  double flare_radius, exponent;  // exponent = 3 - flare_intensity (2 when that is <= 0), :998-1001
+};
+size_t starburst_scratch_bytes(const StarFrame& f);
+cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch, const double* lights_dev, int n_lights,
+                             const double rad_sum[3], void* out, size_t stride, int elem, int additive, cudaStream_t s, int* launches);
+
 cudaError_t probe_peaks(int device, cudaStream_t s, double* fp32_flops, double* mufu_ops, double* sm_clock_hz);
 
 }  // namespace lfb

@@ -66,6 +66,22 @@ class RefOracle:
                                     C.POINTER(C.c_double), C.c_double, C.c_double, C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double)]
 
+    def starburst_multi(self, tex, W, H, origins, radiances, flare_radius, flare_intensity, xs, ys):
+        """-> (n, 6): raytrace_starburst rgb, then a separate calculate_irradiance_falloff draw rgb."""
+        tex = np.ascontiguousarray(tex, np.float32)
+        xs = np.ascontiguousarray(xs, np.int32)
+        ys = np.ascontiguousarray(ys, np.int32)
+        fo = np.ascontiguousarray(origins, np.float64).reshape(-1, 2)
+        rad = np.ascontiguousarray(radiances, np.float64).reshape(-1, 3)
+        out = np.zeros((xs.size, 6))
+        f = self.lib.ref_starburst_multi
+        f.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                      C.POINTER(C.c_double), C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                      C.POINTER(C.c_double)]
+        f(_fp(tex), tex.shape[1], tex.shape[0], W, H, fo.shape[0], _dp(fo), _dp(rad), flare_radius, flare_intensity,
+          xs.ctypes.data_as(C.POINTER(C.c_int)), ys.ctypes.data_as(C.POINTER(C.c_int)), xs.size, _dp(out))
+        return out
+
     def sizeof_vector3d(self):
         return self.lib.ref_sizeof_vector3d()
 
@@ -191,6 +207,23 @@ class PortOracle:
                                  C.byref(params), _dp(out), acc.ctypes.data if want_accum else None)
         assert rc == 0
         return (out, acc) if want_accum else out
+
+    def starburst_pixels(self, tex, W, H, origins, radiances, flare_radius, flare_intensity, xs, ys):
+        """-> (dft scalar (n,), deterministic falloff (n, 3))"""
+        tex = np.ascontiguousarray(tex, np.float32)
+        xs = np.ascontiguousarray(xs, np.int32)
+        ys = np.ascontiguousarray(ys, np.int32)
+        fo = np.ascontiguousarray(origins, np.float64).reshape(-1, 2)
+        rad = np.ascontiguousarray(radiances, np.float64).reshape(-1, 3)
+        dft, fall = np.zeros(xs.size), np.zeros((xs.size, 3))
+        f = self.lib.lfo_starburst_pixels
+        f.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                      C.POINTER(C.c_double), C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        rc = f(_fp(tex), tex.shape[1], tex.shape[0], W, H, fo.shape[0], _dp(fo), _dp(rad), flare_radius, flare_intensity,
+               xs.ctypes.data_as(C.POINTER(C.c_int)), ys.ctypes.data_as(C.POINTER(C.c_int)), xs.size, _dp(dft), _dp(fall))
+        assert rc == 0
+        return dft, fall
 
     def reflectance(self, n0, n2, cos0, lambda0, lam):
         return self.lib.lfo_reflectance(n0, n2, cos0, lambda0, lam)

@@ -716,6 +716,86 @@ int lfo_render(const lfb_lens* L, const float* tex, int tw, int th, const lfb_li
 }
 
 /* ------------------------------------------------------------------------- */
+/* starburst: pathtracer.cpp:901-1052                           */
+/* ------------------------------------------------------------------------- */
+static double convert_coordinate(int pixel_coord, int length, int is_y) { /* :936-945, float arithmetic as written */
+  double cc;
+  if (is_y) cc = -((float)pixel_coord) + ((float)length / 2.0);
+  else cc = ((float)pixel_coord) - ((float)length / 2.0);
+  return cc >= 0 ? cc : length + cc;
+}
+
+int lfo_starburst_pixels(const float* tex, int tw, int th, int W, int H, int n_lights, const double* fo,
+                         const double* rad, double flare_radius, double flare_intensity, const int* xs,
+                         const int* ys, int n, double* out_dft, double* out_falloff) {
+  if (n_lights < 1) return LFB_ERR_INVALID;
+  /* CameraApertureTexture::init (camera.h:61-73): total and bbox of texels > 0 */
+  double total = 0;
+  int min_x = tw, min_y = tw, max_x = -1, max_y = -1;
+  for (int y = 0; y < th; y++)
+    for (int x = 0; x < tw; x++) {
+      float v = tex[(size_t)y * tw + x];
+      total += v;
+      if (v > 0) {
+        if (x < min_x) min_x = x;
+        if (y < min_y) min_y = y;
+        if (x > max_x) max_x = x;
+        if (y > max_y) max_y = y;
+      }
+    }
+  /* compute_phase(0, ...) :918-934 */
+  double lr = ceil(fo[0] * (double)W), ud = ceil(fo[1] * (double)H);
+  const double org_x = lr, org_y = ud;
+  lr -= (double)W / 2.0;
+  ud = -ud + (double)H / 2.0;
+  for (int k = 0; k < n; k++) {
+    const int x = xs[k], y = ys[k];
+    const double xprime = convert_coordinate(x, W, 0), yprime = convert_coordinate(y, H, 1);
+    double re = 0, im = 0;
+    for (int yc = min_y; yc <= max_y; yc++)
+      for (int xc = min_x; xc <= max_x; xc++) {
+        const double a = (double)tex[(size_t)yc * tw + xc];
+        const double u = ((double)xc / (double)tw) - 0.5;
+        const double v = ((double)yc / (double)tw) - 0.5; /* sic: divided by the WIDTH, :964 */
+        const double e1 = u * xprime + v * yprime, e2 = u * lr + v * ud;
+        /* a * additional_phase * complex_exponential, complex products as std::complex does */
+        const double c1 = cos(2.0 * M_PI * e1), s1 = -sin(2.0 * M_PI * e1);
+        const double c2 = cos(2.0 * M_PI * e2), s2 = sin(2.0 * M_PI * e2);
+        const double pr = a * c2, pi = a * s2;
+        re += pr * c1 - pi * s1;
+        im += pr * s1 + pi * c1;
+      }
+    double I = sqrt(re * re + im * im) / total;
+    const double dx = org_x - x, dy = org_y - y, dist = sqrt(dx * dx + dy * dy);
+    if (dist > (double)tw / 2.0) { /* suppression :983-989 */
+      const double factor = ((double)tw / 2.0) / dist;
+      I = pow(factor, 8.0) * I;
+    } else if (dist <= flare_radius) { /* amplification :990-996 */
+      I = pow(I, dist / flare_radius);
+    }
+    double intensity = -flare_intensity + 3.0;
+    if (intensity <= 0) intensity = 2.0;
+    out_dft[k] = pow(I, intensity);
+    if (out_falloff) { /* :1030-1052 with 4x4 stratified midpoints instead of 16 random samples */
+      double f[3] = {0, 0, 0};
+      for (int sy = 0; sy < 4; sy++)
+        for (int sx = 0; sx < 4; sx++) {
+          const double px = x + (sx + 0.5) / 4, py = y + (sy + 0.5) / 4;
+          for (int l = 0; l < n_lights; l++) {
+            const double ox = fo[2 * l] * (double)W - px, oy = fo[2 * l + 1] * (double)H - py;
+            double r = sqrt(ox * ox + oy * oy) - 5.0;
+            r = 1 + (r > 0 ? r : 0);
+            const double r2 = pow(r, 1.5);
+            for (int c = 0; c < 3; c++) f[c] += rad[3 * l + c] / r2;
+          }
+        }
+      for (int c = 0; c < 3; c++) out_falloff[3 * k + c] = f[c] / 16.0;
+    }
+  }
+  return LFB_OK;
+}
+
+/* ------------------------------------------------------------------------- */
 /* timed multi-threaded render (cpu_baseline "port")                          */
 /* ------------------------------------------------------------------------- */
 typedef struct {

@@ -62,6 +62,17 @@ int lfo_render(const lfb_lens* lens, const float* tex, int tw, int th,
 double lfo_reflectance(double n0, double n2, double cos0, double coating_lambda0_nm,
                        double lambda_nm);
 
+/* pathtracer.cpp:947-1004 (raytrace_starburst) restated per pixel, brute force like the reference, for the pixels
+ * (xs[k], ys[k]).  fo = normalised flare origins (origin 0 drives the DFT phase, :918-934), rad = radiance per light.
+ *   out_dft[k]      = pow(|sum A e^{j..}| / total_value, with suppression / amplification applied, 3 - flare_intensity)
+ *                     -- the scalar the reference multiplies with the sum of the lights' radiance
+ *   out_falloff[3k] = calculate_irradiance_falloff (:1030-1052) with the 16 random samples replaced by the 4x4 stratified
+ *                     midpoints of the pixel (the reference draws from a process-global RNG: only its expectation is defined)
+ * PINNED against the compiled reference: the DFT scalar exactly (ref_starburst_multi), the falloff statistically. */
+int lfo_starburst_pixels(const float* tex, int tw, int th, int W, int H, int n_lights, const double* fo_xy,
+                         const double* radiance3, double flare_radius, double flare_intensity, const int* xs,
+                         const int* ys, int n, double* out_dft, double* out_falloff);
+
 /* Timed render on nthreads pthreads (jobs split round-robin); returns seconds. */
 double lfo_time_render(const lfb_lens* lens, const float* tex, int tw, int th,
                        const lfb_light* lights, int n_lights, const lfb_params* params,

@@ -218,6 +218,35 @@ int ref_starburst(const float* tex, int tw, int th, int W, int H, double fo_x, d
   return 0;
 }
 
+// The same call with several lights (origins may lie off screen: find_sun_pos is bypassed).  This is how the DFT term
+// is pinned EXACTLY despite the random falloff draw: the reference uses origin 0 for the DFT phase and sums radiance over
+// ALL lights, while the falloff of light l decays with the distance to origin l.  With light 0 = (A, radiance (1,0,0))
+// and light 1 = (B far off screen, radiance (0,1,0)), channel G = pow(I, e) + O(|B|^-1.5) with negligible noise.
+int ref_starburst_multi(const float* tex, int tw, int th, int W, int H, int n_lights, const double* fo_xy,
+                        const double* radiance3, double flare_radius, double flare_intensity,
+                        const int* xs, const int* ys, int n, double* out6) {
+  Quiet q;
+  PathTracer pt;
+  Camera cam;
+  CameraApertureTexture t;
+  fill_texture(t, tex, tw, th);
+  cam.aperture_texture = &t; cam.ghost_aperture_texture = &t;
+  pt.camera = &cam;
+  pt.set_frame_size(W, H);
+  for (int l = 0; l < n_lights; l++) {
+    pt.flare_origins.emplace_back(fo_xy[2 * l], fo_xy[2 * l + 1]);
+    pt.flare_radiance.push_back(Vector3D(radiance3[3 * l], radiance3[3 * l + 1], radiance3[3 * l + 2]));
+  }
+  pt.flare_radius = flare_radius; pt.flare_intensity = flare_intensity;
+  for (int k = 0; k < n; k++) {
+    Vector3D s = pt.raytrace_starburst(xs[k], ys[k]);
+    Vector3D f = pt.calculate_irradiance_falloff(xs[k], ys[k], 5.0);
+    out6[6 * k + 0] = s.x; out6[6 * k + 1] = s.y; out6[6 * k + 2] = s.z;
+    out6[6 * k + 3] = f.x; out6[6 * k + 4] = f.y; out6[6 * k + 5] = f.z;
+  }
+  return 0;
+}
+
 // pathtracer.cpp:918-934 (compute_phase -> complex_exp :901-916).
 void ref_starburst_phase(int W, int H, double fo_x, double fo_y, double u, double v,
                          double* re_im, double* screen_pos) {

@@ -1,0 +1,93 @@
+"""Starburst: PathTracer::raytrace_starburst (pathtracer.cpp:947-1004) + calculate_irradiance_falloff
+(:1030-1052).  Golden vectors come from the compiled reference at sample pixels (tools/make_golden.py): light 0 drives
+the DFT with radiance (1,0,0); light 1 sits far off screen with radiance (0,1,0), so channel G is the DFT scalar plus a
+~1e-8 falloff with negligible noise -- an exact pin despite the reference's random falloff draw.
+
+Tolerances: DFT scalar 2e-9 relative + 1e-11 absolute (double, different summation order; the absolute term is the
+residual noise of the far light's falloff in the pin itself); falloff: the reference averages 16 RANDOM samples
+of the pixel, ours (and the oracle's) its 4x4 stratified midpoints -> statistical agreement (5 %) only."""
+import os
+
+import numpy as np
+import pytest
+
+from lens_flare_b200 import capi
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "starburst.npz")
+
+
+def cases():
+    z = np.load(GOLDEN)
+    for name, apn in zip(z["names"], z["apertures"]):
+        W, H, fx, fy, radius, intensity = z[str(name) + "_meta"]
+        yield str(name), str(apn), int(W), int(H), (float(fx), float(fy)), float(radius), float(intensity), z[str(name) + "_xy"], z[str(name) + "_out"]
+
+
+FAR = (60.0, -45.0)
+RAD = [(1, 0, 0), (0, 1, 0)]
+
+
+@pytest.mark.parametrize("case", list(cases()), ids=lambda c: c[0])
+def test_oracle_starburst_vs_reference_golden(port, apertures, case):
+    name, apn, W, H, fo, radius, intensity, xy, ref = case
+    dft, fall = port.starburst_pixels(apertures[apn], W, H, [fo, FAR], RAD, radius, intensity, xy[0], xy[1])
+    assert np.allclose(ref[:, 1], dft + fall[:, 1], rtol=2e-9, atol=1e-11)      # the DFT scalar, exactly pinned
+    assert dft.max() == pytest.approx(1.0, abs=1e-12)                            # at the flare origin I^0 = 1
+    for rnd in (ref[:, 0] - dft, ref[:, 3]):  # the falloff inside raytrace_starburst, and a second, separate draw
+        err = np.abs(rnd - fall[:, 0]) / fall[:, 0]
+        assert err.max() < 0.25 and np.median(err) < 0.01   # 16 random samples vs 4x4 stratified midpoints
+    assert (ref[:, 2] == 0).all()
+
+
+def test_oracle_starburst_vs_compiled_reference(port, ref, apertures):
+    rng = np.random.default_rng(1)
+    xs, ys = rng.integers(0, 200, 24), rng.integers(0, 120, 24)
+    for intensity in (0.5, 3.5):
+        a = ref.starburst_multi(apertures["pent_11"], 200, 120, [(0.3, 0.8), FAR], RAD, 12.0, intensity, xs, ys)
+        dft, fall = port.starburst_pixels(apertures["pent_11"], 200, 120, [(0.3, 0.8), FAR], RAD, 12.0, intensity, xs, ys)
+        # a 200-px frame puts the "far" light only 1.3e4 px away: its falloff noise is ~1e-11 here
+        assert np.allclose(a[:, 1], dft + fall[:, 1], rtol=2e-9, atol=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(cases()), ids=lambda c: c[0])
+def test_gpu_starburst_frame_vs_reference_golden(engine, port, apertures, case):
+    name, apn, W, H, fo, radius, intensity, xy, ref = case
+    engine.set_starburst_aperture(apertures[apn])
+    lights = [capi.make_light(fo[0], fo[1], theta=0.0, radiance=RAD[0]), capi.make_light(FAR[0], FAR[1], theta=0.0, radiance=RAD[1])]
+    img = engine.render_starburst(lights, W, H, radius, intensity)
+    got = img[xy[1], xy[0]]
+    assert np.allclose(got[:, 1], ref[:, 1], rtol=2e-9, atol=1e-11)              # DFT scalar (+ the tiny far falloff) vs the reference
+    dft, fall = port.starburst_pixels(apertures[apn], W, H, [fo, FAR], RAD, radius, intensity, xy[0], xy[1])
+    assert np.allclose(got[:, 0], dft + fall[:, 0], rtol=1e-9, atol=1e-12)       # deterministic falloff vs the oracle
+    assert (img[:, :, 2] == 0).all() and np.isfinite(img).all()
+    # more pixels than the reference could afford: 400 random ones vs the oracle
+    rng = np.random.default_rng(9)
+    xs, ys = rng.integers(0, W, 400), rng.integers(0, H, 400)
+    dft, fall = port.starburst_pixels(apertures[apn], W, H, [fo, FAR], RAD, radius, intensity, xs, ys)
+    assert np.allclose(img[ys, xs, 1], dft + fall[:, 1], rtol=2e-9, atol=1e-11)
+    st = engine.stats()
+    assert st["last_trace_ms"] > 0
+
+
+@pytest.mark.gpu
+def test_gpu_starburst_layouts_and_composition(engine, apertures):
+    """additive = 1 composes like raytrace_pixel (pathtracer.cpp:881-891): sampleBuffer += ghost + starburst."""
+    engine.set_lens(capi.builtin_lens(3))
+    engine.set_aperture(apertures["pent_11"])
+    engine.set_starburst_aperture(apertures["pent_11"])
+    W, H = 320, 200
+    lt = [capi.make_light(0.6, 0.45, radiance=(1.0, 0.8, 0.6))]
+    star = engine.render_starburst(lt, W, H, 20.0, 1.0)
+    ghosts = engine.render_ghosts(lt, capi.make_params(capi.MODE_REF_QUADS, W, H))
+    both = ghosts.copy()
+    engine.render_starburst(lt, W, H, 20.0, 1.0, out=both, additive=True)
+    assert np.array_equal(both, ghosts + star)
+    f32 = engine.render_starburst(lt, W, H, 20.0, 1.0, elem=capi.F32x3)
+    assert np.array_equal(f32, star.astype(np.float32))
+    assert np.allclose(star[:, :, 1], 0.8 * star[:, :, 0], rtol=1e-6) and star.min() > 0  # radiance is float32 in lfb_light
+    # the pattern peaks at the flare origin: I^(dist/radius) -> 1 there, + falloff 1 (r = 1 inside 5 px)
+    oy, ox = int(np.ceil(0.45 * H)), int(np.ceil(0.6 * W))
+    assert star[oy, ox, 0] == pytest.approx(2.0, rel=1e-12)
+    with pytest.raises(capi.LfbError):
+        engine.render_starburst([], W, H, 20.0, 1.0)

@@ -103,6 +103,31 @@ def main():
         sun.append(list(np.asarray(c2w, float).ravel()) + list(pos) + [hf, vf] + list(lp) + [n, nx, ny, ang])
     g["sun_table"] = np.array(sun, np.float64)
     np.savez_compressed(os.path.join(OUT, "ref_vectors.npz"), **g)
+
+    # --- starburst: raytrace_starburst at sample pixels.  Light 0 = (origin, radiance (1,0,0)) drives the
+    # DFT; light 1 sits far off screen with radiance (0,1,0), so channel G = the DFT scalar + a ~1e-8 falloff with
+    # negligible noise (the falloff draws from the process-global RNG); columns 3..5 are a separate falloff draw.
+    sb = {}
+    cfgs = [  # name, aperture, W, H, origin, flare_radius, flare_intensity, n pixels
+        ("sb512", "pent_11", 512, 512, (0.7, 0.6), 30.0, 1.0, 160),
+        ("sb_odd", "pent_11", 333, 217, (0.4, 0.3), 10.0, 2.5, 120),
+        ("sb1080", "pentbig500_14", 1920, 1080, (0.45, 0.55), 50.0, 4.0, 80),
+    ]
+    for name, apn, W, H, fo, radius, intensity, npx in cfgs:
+        rng = np.random.default_rng(len(name))
+        ox, oy = int(np.ceil(fo[0] * W)), int(np.ceil(fo[1] * H))
+        xs = list(rng.integers(0, W, npx - 40)) + [min(max(ox + d, 0), W - 1) for d in rng.integers(-int(radius), int(radius) + 1, 40)]
+        ys = list(rng.integers(0, H, npx - 40)) + [min(max(oy + d, 0), H - 1) for d in rng.integers(-int(radius), int(radius) + 1, 40)]
+        xs[0], ys[0] = ox, oy
+        out = ref.starburst_multi(tex_f[apn], W, H, [fo, (60.0, -45.0)], [(1, 0, 0), (0, 1, 0)], radius, intensity, xs, ys)
+        sb[name + "_meta"] = np.array([W, H, fo[0], fo[1], radius, intensity], np.float64)
+        sb[name + "_xy"] = np.array([xs, ys], np.int32)
+        sb[name + "_out"] = out
+        print(name, "pixels", len(xs), "G range", out[:, 1].min(), out[:, 1].max())
+    sb["names"] = np.array([c[0] for c in cfgs])
+    sb["apertures"] = np.array([c[1] for c in cfgs])
+    sb["far_origin"] = np.array([60.0, -45.0])
+    np.savez_compressed(os.path.join(OUT, "starburst.npz"), **sb)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
