@@ -199,6 +199,15 @@ int lfb_render_starburst(lfb_engine* e, const lfb_light* lights, int n_lights, i
                          double flare_radius, double flare_intensity, void* out, size_t out_stride_bytes,
                          int out_elem, int additive);
 
+/* The displayable flare frame in one call: [base] + ghosts + [starburst] composited on the device as
+ * raytrace_pixel does (pathtracer.cpp:881-891), tone-mapped by HDRImageBuffer::toColor (util/image.h:208-223) and packed
+ * like ImageBuffer::update_pixel (util/image.h:53-62, 0xFFBBGGRR).  base_hdr: optional host W*H packed F64x3 (the path-traced
+ * radiance); flare_radius < 0 skips the starburst; flip_vertical = 1 applies save_image's row flip
+ * (raytraced_renderer.cpp:739-742).  Only 4 bytes per pixel come back over PCIe. */
+int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* params,
+                           double flare_radius, double flare_intensity, const double* base_hdr,
+                           uint32_t* out_rgba8, int flip_vertical);
+
 /* ---- device-resident API (multi-GPU sharding, benchmarking) ------------- */
 /* Sensor accumulators: width*height*3 u64 fixed-point sums, owned by the caller. */
 size_t lfb_accum_bytes(int width, int height);

@@ -33,7 +33,7 @@ SYMBOLS = (
     "lfb_abi_version", "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
     "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
     "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
-    "lfb_host_alloc", "lfb_host_free", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst",
+    "lfb_host_alloc", "lfb_host_free", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
 )
 
 
@@ -175,6 +175,7 @@ def lib():
     L.lfb_host_free.restype = None
     L.lfb_set_starburst_aperture.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.c_int]
     L.lfb_render_starburst.argtypes = [vp, LiP, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, C.c_size_t, C.c_int, C.c_int]
+    L.lfb_render_frame_rgba8.argtypes = [vp, LiP, C.c_int, PP, C.c_double, C.c_double, vp, vp, C.c_int]
     L.lfb_probe_peaks.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     if L.lfb_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {L.lfb_abi_version()} != {ABI_VERSION}; rebuild")
@@ -285,6 +286,15 @@ class Engine:
             out = np.empty((height, width, 3), np.float64 if elem == F64x3 else np.float32)
         check(lib().lfb_render_starburst(self._h, lights_array(lights), len(lights), width, height, flare_radius, flare_intensity,
                                          out.ctypes.data, out.strides[1], elem, int(additive)))
+        return out
+
+    def render_frame_rgba8(self, lights, params, flare_radius=-1.0, flare_intensity=1.0, base_hdr=None, out=None, flip=False):
+        """[base] + ghosts + [starburst] -> toColor -> (H, W) uint32 0xFFBBGGRR."""
+        if out is None:
+            out = np.empty((params.height, params.width), np.uint32)
+        base = None if base_hdr is None else np.ascontiguousarray(base_hdr, np.float64)
+        check(lib().lfb_render_frame_rgba8(self._h, lights_array(lights), len(lights), C.byref(params), flare_radius, flare_intensity,
+                                           None if base is None else base.ctypes.data, out.ctypes.data, int(flip)))
         return out
 
     def dump_rays(self, light, params, i, j, lam):

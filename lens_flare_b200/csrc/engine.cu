@@ -163,6 +163,11 @@ struct lfb_engine {
   size_t star_scratch_cap = 0;
   double* d_star_lights = nullptr;
   size_t star_lights_cap = 0;
+  // display-frame path (lfb_render_frame_rgba8)
+  double* d_hdr = nullptr;
+  size_t hdr_cap = 0;
+  uint32_t* d_rgba = nullptr;
+  size_t rgba_cap = 0;
   // dirty-rectangle path (lfb_render_ghosts_rect)
   int* d_bbox = nullptr;      // device {min_x, min_y, max_x, max_y} of the pixels the frame deposits into
   int* h_bbox = nullptr;      // pinned: [0..3] reset pattern, [4..7] read-back
@@ -501,7 +506,7 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
   cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox); cudaFree(e->d_lut);
-  cudaFree(e->d_star_tex); cudaFree(e->d_star_scratch); cudaFree(e->d_star_lights);
+  cudaFree(e->d_star_tex); cudaFree(e->d_star_scratch); cudaFree(e->d_star_lights); cudaFree(e->d_hdr); cudaFree(e->d_rgba);
   if (e->h_bbox) cudaFreeHost(e->h_bbox);
   if (e->h_progs) cudaFreeHost(e->h_progs);
   cudaFree(e->d_tex); cudaFree(e->d_jobs); cudaFree(e->d_dump_job); cudaFree(e->d_accum); cudaFree(e->d_out);
@@ -902,15 +907,12 @@ extern "C" int lfb_set_starburst_aperture(lfb_engine* e, const float* texels, in
   return LFB_OK;
 }
 
-extern "C" int lfb_render_starburst(lfb_engine* e, const lfb_light* lights, int n_lights, int width, int height,
-                                    double flare_radius, double flare_intensity, void* out, size_t stride, int elem, int additive) {
-  int rc = bind(e);
-  if (rc) return rc;
+namespace {
+// Enqueue the starburst of a frame into a device buffer (out_dev: width*height pixels, stride/elem as given).
+int starburst_device(lfb_engine* e, const lfb_light* lights, int n_lights, int width, int height, double flare_radius,
+                     double flare_intensity, void* out_dev, size_t stride, int elem, int additive) {
   if (!e->d_star_tex) return fail(LFB_ERR_STATE, "set the starburst aperture first");
   if (n_lights < 1 || !lights) return fail(LFB_ERR_INVALID, "the starburst needs at least one light (flare_origins[0], pathtracer.cpp:919)");
-  if (width < 1 || height < 1 || width > 32768 || height > 32768 || !out) return fail(LFB_ERR_INVALID, "bad frame/out");
-  if (elem != LFB_F32x3 && elem != LFB_F64x3) return fail(LFB_ERR_INVALID, "unknown out_elem");
-  if (stride < elem_bytes(elem) || stride % (elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
   if (e->star_bbox[2] < e->star_bbox[0] || !(e->star_total > 0)) return fail(LFB_ERR_INVALID, "the starburst aperture is empty");
   StarFrame f;
   memset(&f, 0, sizeof(f));
@@ -933,22 +935,35 @@ extern "C" int lfb_render_starburst(lfb_engine* e, const lfb_light* lights, int 
     L[5 * l + 1] = lights[l].ns_y * (double)height;
     for (int c = 0; c < 3; c++) { L[5 * l + 2 + c] = lights[l].radiance[c]; rad_sum[c] += lights[l].radiance[c]; }
   }
+  int rc = grow(&e->d_star_scratch, &e->star_scratch_cap, starburst_scratch_bytes(f));
+  if (rc) return rc;
+  rc = grow(&e->d_star_lights, &e->star_lights_cap, sizeof(double) * L.size());
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(e->d_star_lights, L.data(), sizeof(double) * L.size(), cudaMemcpyHostToDevice, e->stream));
+  int n = 0;
+  CU(launch_starburst(f, e->d_star_tex, e->d_star_scratch, e->d_star_lights, n_lights, rad_sum, out_dev, stride, elem, additive, e->stream, &n));
+  e->launches += (uint64_t)n;
+  return LFB_OK;
+}
+}  // namespace
+
+extern "C" int lfb_render_starburst(lfb_engine* e, const lfb_light* lights, int n_lights, int width, int height,
+                                    double flare_radius, double flare_intensity, void* out, size_t stride, int elem, int additive) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (width < 1 || height < 1 || width > 32768 || height > 32768 || !out) return fail(LFB_ERR_INVALID, "bad frame/out");
+  if (elem != LFB_F32x3 && elem != LFB_F64x3) return fail(LFB_ERR_INVALID, "unknown out_elem");
+  if (stride < elem_bytes(elem) || stride % (elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
   const size_t npx = (size_t)width * height;
   const size_t out_bytes = (npx - 1) * stride + elem_bytes(elem);
   rc = grow(&e->d_out, &e->out_cap, out_bytes);
   if (rc) return rc;
-  rc = grow(&e->d_star_scratch, &e->star_scratch_cap, starburst_scratch_bytes(f));
-  if (rc) return rc;
-  rc = grow(&e->d_star_lights, &e->star_lights_cap, sizeof(double) * L.size());
-  if (rc) return rc;
   CU(cudaEventRecord(e->ev_frame0, e->stream));
-  CU(cudaMemcpyAsync(e->d_star_lights, L.data(), sizeof(double) * L.size(), cudaMemcpyHostToDevice, e->stream));
   if (additive) CU(cudaMemcpyAsync(e->d_out, out, out_bytes, cudaMemcpyHostToDevice, e->stream));
   else if (stride != elem_bytes(elem)) CU(cudaMemsetAsync(e->d_out, 0, out_bytes, e->stream));
   CU(cudaEventRecord(e->ev_trace0, e->stream));
-  int n = 0;
-  CU(launch_starburst(f, e->d_star_tex, e->d_star_scratch, e->d_star_lights, n_lights, rad_sum, e->d_out, stride, elem, additive, e->stream, &n));
-  e->launches += (uint64_t)n;
+  rc = starburst_device(e, lights, n_lights, width, height, flare_radius, flare_intensity, e->d_out, stride, elem, additive);
+  if (rc) return rc;
   CU(cudaEventRecord(e->ev_trace1, e->stream));
   CU(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaEventRecord(e->ev_frame1, e->stream));
@@ -956,6 +971,54 @@ extern "C" int lfb_render_starburst(lfb_engine* e, const lfb_light* lights, int 
   CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
   CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
   e->timed = true;
+  return LFB_OK;
+}
+
+// The displayable flare frame in one call, everything device-resident until the 8-bit frame comes back:
+//   hdr = [base] + ghosts (any mode) + [starburst]   ->   toColor (util/image.h:208-223)   ->   RGBA8 (ImageBuffer, :53-62)
+// i.e. what raytrace_pixel (:881-891) + raytrace_tile's toColor + frameBuffer do for the flare terms.  base_hdr (optional,
+// host, W*H F64x3 packed) is the path-traced radiance to composite over; flare_radius < 0 skips the starburst;
+// flip_vertical = 1 applies save_image's row flip (raytraced_renderer.cpp:739-742).  4 bytes per pixel cross PCIe, not 24.
+extern "C" int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P,
+                                      double flare_radius, double flare_intensity, const double* base_hdr, uint32_t* out_rgba8,
+                                      int flip_vertical) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!e->has_lens || !e->has_tex) return fail(LFB_ERR_STATE, "set the lens and the aperture first");
+  rc = check_params(P, false);
+  if (rc) return rc;
+  if (n_lights < 0 || (n_lights > 0 && !lights) || !out_rgba8) return fail(LFB_ERR_INVALID, "bad lights/out");
+  const size_t npx = (size_t)P->width * P->height;
+  rc = grow(&e->d_hdr, &e->hdr_cap, npx * 24);
+  if (rc) return rc;
+  rc = grow(&e->d_rgba, &e->rgba_cap, npx * 4);
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev_frame0, e->stream));
+  if (base_hdr) CU(cudaMemcpyAsync(e->d_hdr, base_hdr, npx * 24, cudaMemcpyHostToDevice, e->stream));
+  if (P->mode == LFB_MODE_REF_QUADS) {
+    rc = render_ref_device(e, lights, n_lights, *P, e->d_hdr, 24, LFB_F64x3, base_hdr ? 1 : 0);
+    if (rc) return rc;
+  } else {
+    rc = grow(&e->d_accum, &e->accum_cap, lfb_accum_bytes(P->width, P->height));
+    if (rc) return rc;
+    e->accum_dirty_w = e->accum_dirty_h = 0;
+    rc = render_grid_device(e, lights, n_lights, *P, e->d_accum, 1);
+    if (rc) return rc;
+    const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+    CU(launch_finalize(e->d_accum, P->width, P->height, inv, e->d_hdr, 24, LFB_F64x3, base_hdr ? 1 : 0, e->stream));
+    e->launches++;
+  }
+  if (flare_radius >= 0 && n_lights > 0) {
+    rc = starburst_device(e, lights, n_lights, P->width, P->height, flare_radius, flare_intensity, e->d_hdr, 24, LFB_F64x3, 1);
+    if (rc) return rc;
+  }
+  CU(launch_to_color(e->d_hdr, P->width, P->height, e->d_rgba, flip_vertical, e->stream));
+  e->launches++;
+  CU(cudaMemcpyAsync(out_rgba8, e->d_rgba, npx * 4, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaEventRecord(e->ev_frame1, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
+  CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
   return LFB_OK;
 }
 

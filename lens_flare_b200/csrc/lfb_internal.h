@@ -134,6 +134,8 @@ size_t starburst_scratch_bytes(const StarFrame& f);
 cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch, const double* lights_dev, int n_lights,
                              const double rad_sum[3], void* out, size_t stride, int elem, int additive, cudaStream_t s, int* launches);
 
+cudaError_t launch_to_color(const double* hdr, int W, int H, uint32_t* out, int flip, cudaStream_t s);
+
 cudaError_t probe_peaks(int device, cudaStream_t s, double* fp32_flops, double* mufu_ops, double* sm_clock_hz);
 
 }  // namespace lfb

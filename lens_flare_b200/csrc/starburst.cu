@@ -151,6 +151,32 @@ __global__ void __launch_bounds__(256) zgemm_kernel(const double2* __restrict__ 
 
 }  // namespace
 
+// HDRImageBuffer::toColor (util/image.h:208-223: gamma 2.2, exposure sqrt(2), clamp) + ImageBuffer::update_pixel
+// (:53-62: truncating 8-bit pack 0xFFBBGGRR); flip = 1 also applies save_image's vertical flip (raytraced_renderer.cpp:739-742).
+__global__ void __launch_bounds__(256) to_color_kernel(const double* __restrict__ hdr, int W, int H, uint32_t* __restrict__ out, int flip) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (size_t)W * H) return;
+  const float one_over_gamma = 1.0f / 2.2f;
+  const float exposure = (float)sqrt(pow(2.0, (double)1.0f));
+  uint32_t px = 0xFF000000u;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double v = pow(hdr[3 * p + k] * (double)exposure, (double)one_over_gamma);
+    v = (1.0 < v) ? 1.0 : v;  // std::min(pow, 1.0): NaN passes
+    v = (0.0 < v) ? v : 0.0;  // std::max(0.0, .): NaN -> 0
+    const float c = (float)v;
+    px |= ((uint32_t)(fminf(fmaxf(c, 0.f), 1.f) * 255.f)) << (8 * k);
+  }
+  const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+  out[(size_t)x + (size_t)(flip ? H - 1 - y : y) * W] = px;
+}
+
+cudaError_t launch_to_color(const double* hdr, int W, int H, uint32_t* out, int flip, cudaStream_t s) {
+  const size_t n = (size_t)W * H;
+  to_color_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(hdr, W, H, out, flip);
+  return cudaGetLastError();
+}
+
 // scratch: E1 (bw*W) | E2 (H*bh) | Ac (bh*bw) | G (bh*W) complex doubles
 size_t starburst_scratch_bytes(const StarFrame& f) {
   return sizeof(double2) * ((size_t)f.bw * f.W + (size_t)f.H * f.bh + (size_t)f.bh * f.bw + (size_t)f.bh * f.W);

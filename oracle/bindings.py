@@ -82,6 +82,13 @@ class RefOracle:
           xs.ctypes.data_as(C.POINTER(C.c_int)), ys.ctypes.data_as(C.POINTER(C.c_int)), xs.size, _dp(out))
         return out
 
+    def to_color(self, hdr):
+        hdr = np.ascontiguousarray(hdr, np.float64)
+        out = np.zeros(hdr.shape[:2], np.uint32)
+        self.lib.ref_to_color.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_void_p]
+        self.lib.ref_to_color(_dp(hdr), hdr.shape[1], hdr.shape[0], out.ctypes.data)
+        return out
+
     def sizeof_vector3d(self):
         return self.lib.ref_sizeof_vector3d()
 
@@ -224,6 +231,13 @@ class PortOracle:
                xs.ctypes.data_as(C.POINTER(C.c_int)), ys.ctypes.data_as(C.POINTER(C.c_int)), xs.size, _dp(dft), _dp(fall))
         assert rc == 0
         return dft, fall
+
+    def to_color(self, hdr):
+        hdr = np.ascontiguousarray(hdr, np.float64)
+        out = np.zeros(hdr.shape[:2], np.uint32)
+        self.lib.lfo_to_color.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_void_p]
+        self.lib.lfo_to_color(_dp(hdr), hdr.shape[1], hdr.shape[0], out.ctypes.data)
+        return out
 
     def reflectance(self, n0, n2, cos0, lambda0, lam):
         return self.lib.lfo_reflectance(n0, n2, cos0, lambda0, lam)

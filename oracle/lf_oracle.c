@@ -795,6 +795,29 @@ int lfo_starburst_pixels(const float* tex, int tw, int th, int W, int H, int n_l
   return LFB_OK;
 }
 
+/* util/image.h:208-223 + :53-62 */
+void lfo_to_color(const double* hdr, int W, int H, uint32_t* out) {
+  const float gamma = 2.2f, level = 1.0f;
+  const float one_over_gamma = 1.0f / gamma;
+  const float exposure = (float)sqrt(pow(2, level));
+  for (size_t p = 0; p < (size_t)W * H; p++) {
+    float c[3];
+    for (int k = 0; k < 3; k++) {
+      double v = pow(hdr[3 * p + k] * exposure, one_over_gamma);
+      v = (1.0 < v) ? 1.0 : v; /* std::min(pow, 1.0): a NaN pow (negative radiance) passes through */
+      v = (0.0 < v) ? v : 0.0; /* std::max(0.0, .): ... and becomes 0 here */
+      c[k] = (float)v;
+    }
+    uint32_t px = 0;
+    for (int k = 0; k < 3; k++) {
+      float v = c[k] < 0.f ? 0.f : (c[k] > 1.f ? 1.f : c[k]);
+      if (!(c[k] == c[k])) v = 0.f;
+      px |= ((uint32_t)(v * 255)) << (8 * k); /* r | g << 8 | b << 16 */
+    }
+    out[p] = px | 0xFF000000u;
+  }
+}
+
 /* ------------------------------------------------------------------------- */
 /* timed multi-threaded render (cpu_baseline "port")                          */
 /* ------------------------------------------------------------------------- */

@@ -73,6 +73,9 @@ int lfo_starburst_pixels(const float* tex, int tw, int th, int W, int H, int n_l
                          const double* radiance3, double flare_radius, double flare_intensity, const int* xs,
                          const int* ys, int n, double* out_dft, double* out_falloff);
 
+/* util/image.h:208-223 (toColor) + :53-62 (ImageBuffer::update_pixel): HDR doubles -> 0xAABBGGRR, alpha 0xFF. */
+void lfo_to_color(const double* hdr, int W, int H, uint32_t* out);
+
 /* Timed render on nthreads pthreads (jobs split round-robin); returns seconds. */
 double lfo_time_render(const lfb_lens* lens, const float* tex, int tw, int th,
                        const lfb_light* lights, int n_lights, const lfb_params* params,

@@ -14,6 +14,7 @@
 #undef private
 #include "pathtracer/pathtracer.h"
 #include "scene/light.h"
+#include "util/image.h"
 
 #include <chrono>
 #include <cstring>
@@ -245,6 +246,16 @@ int ref_starburst_multi(const float* tex, int tw, int th, int W, int H, int n_li
     out6[6 * k + 3] = f.x; out6[6 * k + 4] = f.y; out6[6 * k + 5] = f.z;
   }
   return 0;
+}
+
+// util/image.h:208-223 (HDRImageBuffer::toColor: gamma 2.2, exposure sqrt(2), clamp) into an ImageBuffer
+// (update_pixel :53-62: truncating 8-bit pack, alpha 0xFF).  hdr = W*H*3 doubles; out = W*H uint32.
+void ref_to_color(const double* hdr, int W, int H, uint32_t* out) {
+  HDRImageBuffer src(W, H);
+  ImageBuffer dst(W, H);
+  for (size_t p = 0; p < (size_t)W * H; p++) src.data[p] = Vector3D(hdr[3 * p], hdr[3 * p + 1], hdr[3 * p + 2]);
+  src.toColor(dst, 0, 0, W, H);
+  std::memcpy(out, dst.data.data(), sizeof(uint32_t) * (size_t)W * H);
 }
 
 // pathtracer.cpp:918-934 (compute_phase -> complex_exp :901-916).

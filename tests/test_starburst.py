@@ -91,3 +91,47 @@ def test_gpu_starburst_layouts_and_composition(engine, apertures):
     assert star[oy, ox, 0] == pytest.approx(2.0, rel=1e-12)
     with pytest.raises(capi.LfbError):
         engine.render_starburst([], W, H, 20.0, 1.0)
+
+
+# ---- composite + tonemap -------------------------------------------------------------------------
+def test_oracle_to_color_vs_reference_golden(port):
+    """HDRImageBuffer::toColor + ImageBuffer::update_pixel: bit-exact 8-bit packing, NaN/negative/over-range included."""
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "tocolor.npz"))
+    assert np.array_equal(port.to_color(z["hdr"]), z["rgba"])
+
+
+def test_oracle_to_color_vs_compiled_reference(port, ref):
+    rng = np.random.default_rng(4)
+    hdr = 10 ** rng.uniform(-6, 0.5, (40, 50, 3))
+    assert np.array_equal(port.to_color(hdr), ref.to_color(hdr))
+
+
+@pytest.mark.gpu
+def test_gpu_frame_rgba8(engine, port, apertures):
+    """lfb_render_frame_rgba8 = toColor(base + ghosts + starburst), composited on the device.  The 8-bit values equal the
+    oracle's toColor of the engine's own HDR frames except where pow() lands within an ulp of a quantisation step."""
+    engine.set_lens(capi.builtin_lens(3, 550.0))
+    engine.set_aperture(apertures["pentbig500_14"])
+    engine.set_starburst_aperture(apertures["pent_11"])
+    W, H = 640, 360
+    lt = [capi.make_light(0.45, 0.55, theta=capi.physical_theta(0.45, 0.55), radiance=(1.0, 0.9, 0.7))]
+    rng = np.random.default_rng(2)
+    base = rng.uniform(0, 0.2, (H, W, 3))
+    for mode in (capi.MODE_REF_QUADS, capi.MODE_EXACT_GRID):
+        p = capi.make_params(mode, W, H, grid_n=128, pair_set=capi.PAIRS_ALL if mode else capi.PAIRS_REF, include_direct=int(mode != 0))
+        if mode == capi.MODE_REF_QUADS:
+            lt_m = [capi.make_light(0.45, 0.55, radiance=(1.0, 0.9, 0.7))]
+        else:
+            lt_m = lt
+        ghosts = engine.render_ghosts(lt_m, p)
+        star = engine.render_starburst(lt_m, W, H, 25.0, 1.0)
+        for b, use_star, flip in ((None, False, False), (base, True, False), (base, True, True)):
+            hdr = ghosts + (star if use_star else 0) + (b if b is not None else 0)
+            want = port.to_color(hdr)
+            if flip:
+                want = want[::-1]
+            got = engine.render_frame_rgba8(lt_m, p, flare_radius=25.0 if use_star else -1.0, flare_intensity=1.0, base_hdr=b, flip=flip)
+            assert (got >> 24 == 0xFF).all()
+            diff = np.abs(got.view(np.uint8).astype(int) - np.ascontiguousarray(want).view(np.uint8).astype(int))
+            assert diff.max() <= 1 and (diff > 0).mean() < 1e-4, (mode, use_star, flip, diff.max(), (diff > 0).mean())
+            assert (got & 0xFFFFFF).any()
