@@ -327,6 +327,28 @@ def run_ours(args):
     h2d = tex.nbytes * world + jobs_frame * job_bytes
     d2h = HEIGHT * WIDTH * 24
 
+    # ---- the displayable frame (N = 1): ghosts -> toColor -> RGBA8 on the device, 4 B/pixel back over PCIe -----------
+    e2e_rgba8 = None
+    if world == 1:
+        pinned_rgba = capi.PinnedArray((HEIGHT, WIDTH), np.uint32)
+
+        def rgba_step(k):
+            eng.set_aperture(pinned_tex.array)
+            eng.render_frame_rgba8(lights_a if k % 2 == 0 else lights_b, params, flare_radius=-1.0, out=pinned_rgba.array)
+
+        for k in range(max(args.warmup, 3)):
+            rgba_step(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            rgba_step(k)
+        torch.cuda.synchronize()
+        rgba_s = time.perf_counter() - t0
+        e2e_rgba8 = {"value": inter_frame * args.steps / rgba_s, "unit": "interactions/s", "ms_per_step": rgba_s / args.steps * 1e3,
+                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": HEIGHT * WIDTH * 4,
+                     "api": "lfb_render_frame_rgba8: ghosts -> HDRImageBuffer::toColor -> ImageBuffer RGBA8 on the device (the displayable frame)"}
+        pinned_rgba.free()
+
     peaks = eng.probe_peaks() if rank == 0 else None
     line = None
     if rank == 0:
@@ -357,6 +379,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s / args.steps * 1e3, "api": "lfb_render_ghosts (F64x3, stride 24 = HDRImageBuffer layout)"
                     if world == 1 else "ShardedFlare.render + reduce + finalize + D2H"},
+            "e2e_rgba8": e2e_rgba8,
             "gpu_launches": int(launches),
             "clocks": clocks.report(),
         }

@@ -14,6 +14,7 @@ int main(int argc, char** argv) {
   std::string ghost_png, star_png, out;
   double sx = 0.45, sy = 0.55;
   int mode = LFB_MODE_REF_QUADS, grid = 256;
+  double flare_intensity = 1.0, flare_radius = 30.0;  // -i / -n, main.cpp:135-152
   if (argc == 3 && std::string(argv[1]) == "--png-info") {  // host-only: what CameraApertureTexture::init decodes
     try {
       lfb::CameraApertureTexture t;
@@ -36,6 +37,8 @@ int main(int argc, char** argv) {
     else if (k == "-f" && a + 1 < argc) out = argv[++a];
     else if (k == "-s" && a + 2 < argc) { sx = std::atof(argv[a + 1]); sy = std::atof(argv[a + 2]); a += 2; }
     else if (k == "-g" && a + 1 < argc) grid = std::atoi(argv[++a]);
+    else if (k == "-i" && a + 1 < argc) flare_intensity = std::atof(argv[++a]);
+    else if (k == "-n" && a + 1 < argc) flare_radius = std::atof(argv[++a]);
     else if (k == "-m" && a + 1 < argc) {
       const std::string m = argv[++a];
       mode = m == "exact" ? LFB_MODE_EXACT_GRID : (m == "paraxial" ? LFB_MODE_PARAXIAL_GRID : LFB_MODE_REF_QUADS);
@@ -45,9 +48,11 @@ int main(int argc, char** argv) {
   try {
     lfb::CameraApertureTexture ghost_tex;
     ghost_tex.init(ghost_png);
+    lfb::CameraApertureTexture star_tex;
+    if (!star_png.empty()) star_tex.init(star_png);
     lfb::Camera camera;
     camera.ghost_aperture_texture = &ghost_tex;
-    camera.aperture_texture = &ghost_tex;
+    camera.aperture_texture = star_png.empty() ? &ghost_tex : &star_tex;
     // a directional light whose image lands at (sx, sy): invert analyze_world_coord for the identity camera
     const double kPi = 3.14159265358979323846;
     const double ex = std::tan(0.5 * camera.hFov * kPi / 180.0), ey = std::tan(0.5 * camera.vFov * kPi / 180.0);
@@ -74,6 +79,20 @@ int main(int argc, char** argv) {
                 "\"l2\": %.17g, \"nonzero\": %zu, \"trace_ms\": %.4f, \"frame_ms\": %.4f, \"tex_total\": %.17g}\n",
                 W, H, pt.axis_ray.x, pt.axis_ray.y, pt.angle_to_sun, sum[0], sum[1], sum[2], std::sqrt(l2), nz, pt.last_trace_ms(),
                 pt.last_frame_ms(), ghost_tex.total_value);
+    if (!star_png.empty()) {  // the rest of raytrace_pixel's flare terms (:881-891) and the displayable frame
+      pt.flare_radius = flare_radius;
+      pt.flare_intensity = flare_intensity;
+      lfb::HDRImageBuffer sample = pt.ghost_buffer;
+      pt.render_starburst(sample, true);
+      double ssum[3] = {0, 0, 0};
+      for (const lfb::Vector3D& v : sample.data) { ssum[0] += v.x; ssum[1] += v.y; ssum[2] += v.z; }
+      std::vector<uint32_t> rgba;
+      pt.render_frame(rgba, nullptr, true, true);
+      unsigned long long bytes = 0;
+      for (uint32_t px : rgba) bytes += (px & 0xFF) + ((px >> 8) & 0xFF) + ((px >> 16) & 0xFF);
+      std::printf("{\"ghost_plus_starburst_sum\": [%.17g, %.17g, %.17g], \"starburst_ms\": %.4f, \"rgba8_byte_sum\": %llu, \"frame_ms\": %.4f}\n",
+                  ssum[0], ssum[1], ssum[2], pt.last_trace_ms(), bytes, pt.last_frame_ms());
+    }
     if (!out.empty()) {  // PFM, bottom row first -- the same vertical flip the reference applies on save (raytraced_renderer.cpp:739-742)
       FILE* f = std::fopen(out.c_str(), "wb");
       if (!f) { std::fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }

@@ -119,45 +119,93 @@ void PathTracer::generate_ghost_buffer() {
   if (axis_ray.x == 0 && axis_ray.y == 0) return;  // :724-726
   if (!camera || !camera->ghost_aperture_texture || camera->ghost_aperture_texture->aperture.empty())
     throw Error(LFB_ERR_STATE, "camera->ghost_aperture_texture is not loaded");
-  ensure_engine();
-  const CameraApertureTexture* t = camera->ghost_aperture_texture;
-  if (uploaded_ != t) {
-    check(lfb_set_aperture(engine_, t->aperture.data(), (int)t->width, (int)t->height), "lfb_set_aperture");
-    uploaded_ = t;
-  }
+  upload_textures(true, false);
   params.width = (int)frame_w_;
   params.height = (int)frame_h_;
-  std::vector<lfb_light> lights;
-  if (params.mode == LFB_MODE_REF_QUADS || flare_origins.empty()) {
-    lfb_light lt;
-    std::memset(&lt, 0, sizeof(lt));
-    lt.ns_x = axis_ray.x; lt.ns_y = axis_ray.y; lt.theta = angle_to_sun;
-    lt.radiance[0] = lt.radiance[1] = lt.radiance[2] = 1.f;
-    lights.push_back(lt);
-  } else {
-    for (size_t l = 0; l < flare_origins.size(); l++) {
-      lfb_light lt;
-      std::memset(&lt, 0, sizeof(lt));
-      lt.ns_x = flare_origins[l].x; lt.ns_y = flare_origins[l].y;
-      if (params.mode == LFB_MODE_EXACT_GRID) {
-        // real refraction needs the real off-axis angle of the light (the inverse of analyze_world_coord), not the
-        // reference's screen-space atan(ns_y/ns_x)
-        const double tx = (2 * lt.ns_x - 1) * std::tan(0.5 * camera->hFov * kPi / 180.0);
-        const double ty = (2 * lt.ns_y - 1) * std::tan(0.5 * camera->vFov * kPi / 180.0);
-        lt.theta = (float)std::atan(std::sqrt(tx * tx + ty * ty));
-      } else {
-        lt.theta = (float)std::atan(lt.ns_y / lt.ns_x);
-      }
-      lt.radiance[0] = (float)flare_radiance[l].x; lt.radiance[1] = (float)flare_radiance[l].y; lt.radiance[2] = (float)flare_radiance[l].z;
-      lights.push_back(lt);
-    }
-  }
+  std::vector<lfb_light> lights = make_lights(true);
   if (rect_mode)
     check(lfb_render_ghosts_rect(engine_, lights.data(), (int)lights.size(), &params, ghost_buffer.data.data(), sizeof(Vector3D), LFB_F64x3, dirty_),
           "lfb_render_ghosts_rect");
   else
     check(lfb_render_ghosts(engine_, lights.data(), (int)lights.size(), &params, ghost_buffer.data.data(), sizeof(Vector3D), LFB_F64x3, 0),
           "lfb_render_ghosts");
+}
+
+void PathTracer::upload_textures(bool ghost, bool star) {
+  ensure_engine();
+  if (ghost) {
+    const CameraApertureTexture* t = camera ? camera->ghost_aperture_texture : nullptr;
+    if (!t || t->aperture.empty()) throw Error(LFB_ERR_STATE, "camera->ghost_aperture_texture is not loaded");
+    if (uploaded_ != t) {
+      check(lfb_set_aperture(engine_, t->aperture.data(), (int)t->width, (int)t->height), "lfb_set_aperture");
+      uploaded_ = t;
+    }
+  }
+  if (star) {
+    const CameraApertureTexture* t = camera ? camera->aperture_texture : nullptr;
+    if (!t || t->aperture.empty()) throw Error(LFB_ERR_STATE, "camera->aperture_texture is not loaded");
+    if (uploaded_star_ != t) {
+      check(lfb_set_starburst_aperture(engine_, t->aperture.data(), (int)t->width, (int)t->height), "lfb_set_starburst_aperture");
+      uploaded_star_ = t;
+    }
+  }
+}
+
+std::vector<lfb_light> PathTracer::make_lights(bool for_ghosts) const {
+  std::vector<lfb_light> lights;
+  if ((for_ghosts && params.mode == LFB_MODE_REF_QUADS) || flare_origins.empty()) {
+    lfb_light lt;
+    std::memset(&lt, 0, sizeof(lt));
+    lt.ns_x = axis_ray.x; lt.ns_y = axis_ray.y; lt.theta = angle_to_sun;
+    lt.radiance[0] = lt.radiance[1] = lt.radiance[2] = 1.f;
+    if (!for_ghosts && !flare_radiance.empty()) {
+      lt.radiance[0] = (float)flare_radiance[0].x; lt.radiance[1] = (float)flare_radiance[0].y; lt.radiance[2] = (float)flare_radiance[0].z;
+    }
+    lights.push_back(lt);
+    return lights;
+  }
+  for (size_t l = 0; l < flare_origins.size(); l++) {
+    lfb_light lt;
+    std::memset(&lt, 0, sizeof(lt));
+    lt.ns_x = flare_origins[l].x; lt.ns_y = flare_origins[l].y;
+    if (params.mode == LFB_MODE_EXACT_GRID && camera) {
+      // real refraction needs the real off-axis angle of the light (the inverse of analyze_world_coord), not the
+      // reference's screen-space atan(ns_y/ns_x)
+      const double tx = (2 * lt.ns_x - 1) * std::tan(0.5 * camera->hFov * kPi / 180.0);
+      const double ty = (2 * lt.ns_y - 1) * std::tan(0.5 * camera->vFov * kPi / 180.0);
+      lt.theta = (float)std::atan(std::sqrt(tx * tx + ty * ty));
+    } else {
+      lt.theta = (float)std::atan(lt.ns_y / lt.ns_x);
+    }
+    lt.radiance[0] = (float)flare_radiance[l].x; lt.radiance[1] = (float)flare_radiance[l].y; lt.radiance[2] = (float)flare_radiance[l].z;
+    lights.push_back(lt);
+  }
+  return lights;
+}
+
+void PathTracer::render_starburst(HDRImageBuffer& target, bool additive) {
+  if (flare_origins.empty()) return;  // the reference dereferences flare_origins[0] unconditionally (pathtracer.cpp:919): UB there
+  if (target.w != frame_w_ || target.h != frame_h_ || target.data.size() != frame_w_ * frame_h_) {
+    target.resize(frame_w_, frame_h_);
+  }
+  upload_textures(false, true);
+  std::vector<lfb_light> lights = make_lights(false);
+  check(lfb_render_starburst(engine_, lights.data(), (int)lights.size(), (int)frame_w_, (int)frame_h_, flare_radius, flare_intensity,
+                             target.data.data(), sizeof(Vector3D), LFB_F64x3, additive ? 1 : 0),
+        "lfb_render_starburst");
+}
+
+void PathTracer::render_frame(std::vector<uint32_t>& rgba8, const HDRImageBuffer* base, bool with_starburst, bool flip_vertical) {
+  rgba8.assign(frame_w_ * frame_h_, 0xFF000000u);
+  if (base && (base->w != frame_w_ || base->h != frame_h_)) throw Error(LFB_ERR_INVALID, "base frame size mismatch");
+  upload_textures(true, with_starburst);
+  params.width = (int)frame_w_;
+  params.height = (int)frame_h_;
+  const bool sun = !(axis_ray.x == 0 && axis_ray.y == 0);
+  std::vector<lfb_light> lights = sun ? make_lights(true) : std::vector<lfb_light>();
+  check(lfb_render_frame_rgba8(engine_, lights.data(), (int)lights.size(), &params, with_starburst && sun ? flare_radius : -1.0, flare_intensity,
+                               base ? &base->data[0].x : nullptr, rgba8.data(), flip_vertical ? 1 : 0),
+        "lfb_render_frame_rgba8");
 }
 
 float PathTracer::last_trace_ms() const {

@@ -16,6 +16,7 @@
 // carry on with).  Header + flare_pathtracer.cpp + png_reader.cpp; link with -llfb200 -lz.
 #pragma once
 #include <cstddef>
+#include <cstdint>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -109,8 +110,17 @@ class PathTracer {
   Vector2D axis_ray;
   float angle_to_sun = 0;
   void set_frame_size(size_t width, size_t height) { frame_w_ = width; frame_h_ = height; }
+  double flare_radius = 30.0;     // pathtracer.h:93 (-n)
+  double flare_intensity = 1.0;   // pathtracer.h:94 (-i)
   void find_sun_pos();
   void generate_ghost_buffer();
+  // PathTracer::raytrace_starburst (pathtracer.cpp:947-1004) for the whole frame at once (the reference evaluates it per
+  // pixel from raytrace_pixel :881).  additive = true adds into `target` like sampleBuffer.update_pixel(total + ghost +
+  // starburst) (:891); camera->aperture_texture is the mask (-x).  Uses flare_origins / flare_radiance from find_sun_pos().
+  void render_starburst(HDRImageBuffer& target, bool additive);
+  // The displayable frame: [base] + ghosts + [starburst] -> HDRImageBuffer::toColor (util/image.h:208-223) -> 0xFFBBGGRR
+  // pixels (ImageBuffer, util/image.h:53-62), composited and tone-mapped on the device.  base may be null.
+  void render_frame(std::vector<uint32_t>& rgba8, const HDRImageBuffer* base, bool with_starburst, bool flip_vertical);
 
   // --- what the reference hard-codes, exposed ------------------------------------------------
   // Rendering mode of generate_ghost_buffer: LFB_MODE_REF_QUADS (default) reproduces the reference bit for
@@ -136,6 +146,9 @@ class PathTracer {
   lfb_lens lens_;
   bool lens_dirty_ = true;
   const CameraApertureTexture* uploaded_ = nullptr;
+  const CameraApertureTexture* uploaded_star_ = nullptr;
+  std::vector<lfb_light> make_lights(bool for_ghosts) const;
+  void upload_textures(bool ghost, bool star);
   size_t frame_w_ = 0, frame_h_ = 0;
   int dirty_[4] = {0, 0, -1, -1};  // what the last frame wrote into ghost_buffer
 };

@@ -166,6 +166,22 @@ class PathTracer:
             out.append(capi.make_light(nx, ny, theta=theta, radiance=tuple(float(v) for v in rad)))
         return out
 
+    def raytrace_starburst_frame(self, flare_radius=30.0, flare_intensity=1.0, out=None, additive=False):
+        """PathTracer::raytrace_starburst (pathtracer.cpp:947-1004) + calculate_irradiance_falloff (:1030-1052) for every
+        pixel of the frame at once; camera.aperture_texture is the mask.  -> (H, W, 3) float64."""
+        tex = self.camera.aperture_texture
+        if tex is None or tex.aperture is None:
+            raise RuntimeError("camera.aperture_texture is not loaded")
+        if not self.flare_origins:
+            raise RuntimeError("no flare origin: run find_sun_pos() first (the reference dereferences flare_origins[0])")
+        if getattr(self, "_uploaded_star", None) is not tex:
+            self.engine.set_starburst_aperture(tex.aperture)
+            self._uploaded_star = tex
+        w, h = self._frame
+        lights = [capi.make_light(nx, ny, theta=0.0, radiance=tuple(float(v) for v in rad))
+                  for (nx, ny), rad in zip(self.flare_origins, self.flare_radiance)]
+        return self.engine.render_starburst(lights, w, h, flare_radius, flare_intensity, out=out, additive=additive)
+
     def generate_ghost_buffer(self):
         """pathtracer.cpp:714-762: clear + resize ghost_buffer to the frame size, draw every ghost."""
         w, h = self._frame

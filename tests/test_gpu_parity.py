@@ -415,6 +415,23 @@ def test_cpp_facade_end_to_end(golden, apertures, port, tmp_path):
     assert np.isclose(info["l2"], np.sqrt((want ** 2).sum()), rtol=1e-12)
     raw = np.fromfile(pfm, np.float32, offset=len(b"PF\n512 512\n-1.0\n")).reshape(512, 512, 3)
     assert np.array_equal(raw, want.astype(np.float32))
+    # starburst + displayable frame through the facade (-x / -i / -n as in the reference's CLI)
+    lines = subprocess.run([os.path.join(host, "flare_demo"), "-r", "320", "200", "-y", str(png), "-x", str(png), "-s", "0.6", "0.45",
+                            "-i", "1.0", "-n", "20"], check=True, capture_output=True, text=True).stdout.splitlines()
+    first, second = json.loads(lines[0]), json.loads(lines[1])
+    eng = capi.Engine(0)
+    try:
+        eng.set_lens(capi.builtin_lens(3))
+        eng.set_aperture(apertures["pent_11"])
+        eng.set_starburst_aperture(apertures["pent_11"])
+        lt = [capi.make_light(first["axis_ray"][0], first["axis_ray"][1], theta=float(np.float32(first["angle_to_sun"])))]
+        pr = capi.make_params(capi.MODE_REF_QUADS, 320, 200)
+        hdr = eng.render_ghosts(lt, pr) + eng.render_starburst(lt, 320, 200, 20.0, 1.0)
+        assert np.allclose(second["ghost_plus_starburst_sum"], hdr.reshape(-1, 3).sum(0), rtol=1e-10)
+        rgba = eng.render_frame_rgba8(lt, pr, flare_radius=20.0, flare_intensity=1.0, flip=True)
+        assert second["rgba8_byte_sum"] == int((rgba & 0xFF).sum() + ((rgba >> 8) & 0xFF).sum() + ((rgba >> 16) & 0xFF).sum())
+    finally:
+        eng.close()
     # exact ray-grid mode through the same facade
     out = subprocess.run([os.path.join(host, "flare_demo"), "-r", "640", "360", "-y", str(png), "-s", "0.45", "0.55", "-m", "exact", "-g", "64"],
                          check=True, capture_output=True, text=True).stdout
