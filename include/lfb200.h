@@ -26,6 +26,7 @@ extern "C" {
 #define LFB_ABI_VERSION 1
 #define LFB_MAX_SURFACES 16
 #define LFB_MAX_LAMBDA 64
+#define LFB_MAX_PEERS 16
 
 typedef struct lfb_engine lfb_engine;
 
@@ -221,6 +222,15 @@ int lfb_render_ghosts_device(lfb_engine* e, const lfb_light* lights, int n_light
 int lfb_finalize_device(lfb_engine* e, const void* accum_dev, const lfb_params* params,
                         void* out_dev, size_t out_stride_bytes, int out_elem);
 int lfb_sync(lfb_engine* e);
+/* Multi-GPU: fused reduce + finalize over NVLink peer memory (replaces an NCCL reduce followed by lfb_finalize_device).
+ * accum_ptrs[r] is rank r's accumulator buffer AS MAPPED IN THIS PROCESS (CUDA IPC / symmetric memory); multicast_accum,
+ * when not NULL, is the same buffer's NVSwitch multicast address (the switch performs the additions).  This rank converts
+ * the pixels [rank*npx/n, (rank+1)*npx/n) and stores them into out_dev, the OWNER rank's output buffer as mapped here.
+ * The caller orders this call after every rank's lfb_render_ghosts_device (a device-side barrier on lfb_stream) and reads
+ * the owner's buffer after another one.  Integer sums: the frame has the same bits for any rank count. */
+int lfb_reduce_finalize_peers(lfb_engine* e, const void* const* accum_ptrs, int n_ranks, int rank,
+                              const void* multicast_accum, const lfb_params* params, void* out_dev,
+                              size_t out_stride_bytes, int out_elem);
 
 /* ---- accounting --------------------------------------------------------- */
 /* Ray-surface interactions (I(i,j) = 2(j-i) + n_surfaces + 1 per ray,

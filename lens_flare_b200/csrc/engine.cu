@@ -714,6 +714,29 @@ extern "C" int lfb_finalize_device(lfb_engine* e, const void* accum_dev, const l
   return LFB_OK;
 }
 
+extern "C" int lfb_reduce_finalize_peers(lfb_engine* e, const void* const* accum_ptrs, int n_ranks, int rank, const void* multicast_accum,
+                                         const lfb_params* P, void* out_dev, size_t out_stride_bytes, int out_elem) {
+  int rc = bind(e);
+  if (rc) return rc;
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (!accum_ptrs || n_ranks < 1 || n_ranks > LFB_MAX_PEERS || rank < 0 || rank >= n_ranks || !out_dev) return fail(LFB_ERR_INVALID, "bad peer set");
+  if (out_elem != LFB_F32x3 && out_elem != LFB_F64x3) return fail(LFB_ERR_INVALID, "unknown out_elem");
+  if (out_stride_bytes < elem_bytes(out_elem) || out_stride_bytes % (out_elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
+  PeerAccums A;
+  A.n = n_ranks;
+  for (int r = 0; r < n_ranks; r++) {
+    if (!accum_ptrs[r]) return fail(LFB_ERR_INVALID, "NULL peer accumulator");
+    A.ptr[r] = (const unsigned long long*)accum_ptrs[r];
+  }
+  const size_t npx = (size_t)P->width * P->height;
+  const size_t p0 = npx * (size_t)rank / (size_t)n_ranks, p1 = npx * (size_t)(rank + 1) / (size_t)n_ranks;
+  const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+  CU(launch_reduce_finalize(A, (const unsigned long long*)multicast_accum, p0, p1, inv, out_dev, out_stride_bytes, out_elem, e->stream));
+  e->launches++;
+  return LFB_OK;
+}
+
 extern "C" int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P, void* out,
                                  size_t stride, int elem, int additive) {
   int rc = bind(e);

@@ -118,6 +118,50 @@ cudaError_t launch_finalize_rect(const unsigned long long* accum, int W, const i
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// fused cross-GPU reduce + finalize over NVLink peer memory.  Every rank runs this kernel on ITS slice of the frame's
+// pixels [p0, p1): it sums the ranks' u64 accumulators -- plain loads from the peers' mapped buffers, or ONE
+// multimem.ld_reduce per value when the buffers are bound to an NVSwitch multicast object (the switch adds) -- converts
+// to pixels and stores them straight into the owner rank's output buffer (a peer store for every other rank).
+// Integer sums: the result is bit-identical to a single-GPU frame for any rank count.  Replaces NCCL reduce + finalize.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long multimem_add_u64(const unsigned long long* mc) {
+  unsigned long long v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v) : "l"(mc) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) reduce_finalize_kernel(PeerAccums P, const unsigned long long* __restrict__ mc, size_t p0, size_t p1,
+                                                              double inv_scale, char* __restrict__ out, size_t stride, int elem) {
+  const size_t p = p0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= p1) return;
+  double v[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    unsigned long long sum = 0;
+    if (mc) {
+      sum = multimem_add_u64(mc + 3 * p + c);
+    } else {
+      for (int r = 0; r < P.n; r++) sum += P.ptr[r][3 * p + c];
+    }
+    v[c] = (double)(long long)sum * inv_scale;
+  }
+  if (elem == LFB_F32x3) {
+    float* o = reinterpret_cast<float*>(out + p * stride);
+    o[0] = (float)v[0]; o[1] = (float)v[1]; o[2] = (float)v[2];
+  } else {
+    double* o = reinterpret_cast<double*>(out + p * stride);
+    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+  }
+}
+
+cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long* mc, size_t p0, size_t p1, double inv_scale,
+                                   void* out, size_t stride, int elem, cudaStream_t s) {
+  if (p1 <= p0) return cudaSuccess;
+  reduce_finalize_kernel<<<(unsigned)((p1 - p0 + 255) / 256), 256, 0, s>>>(P, mc, p0, p1, inv_scale, (char*)out, stride, elem);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,
                             size_t stride, int elem, int additive, cudaStream_t s) {
   size_t npx = (size_t)W * H;

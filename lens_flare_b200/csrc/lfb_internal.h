@@ -102,6 +102,12 @@ cudaError_t launch_trace_dump_f64(const Job* job, const FrameGeom& g, int mode, 
                                   cudaStream_t s);
 cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,
                             size_t stride, int elem, int additive, cudaStream_t s);
+struct PeerAccums {  // the ranks' sensor accumulators as mapped in THIS process (NVLink peer memory)
+  const unsigned long long* ptr[LFB_MAX_PEERS];
+  int n;
+};
+cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long* mc, size_t p0, size_t p1, double inv_scale,
+                                   void* out, size_t stride, int elem, cudaStream_t s);
 // rect = {x0, y0, x1, y1} inclusive; out is PACKED: pixel (x, y) at ((y - y0) * (x1 - x0 + 1) + (x - x0)) * stride
 cudaError_t launch_finalize_rect(const unsigned long long* accum, int W, const int rect[4], double inv_scale, void* out,
                                  size_t stride, int elem, cudaStream_t s);

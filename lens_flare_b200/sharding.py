@@ -115,3 +115,65 @@ class ShardedFlare:
         self.fin_engine.finalize_device(self.accum.data_ptr(), self.full_params, out.data_ptr(), out.stride(1) * out.element_size(), elem)
         cur.wait_stream(self.B)
         return out
+
+
+class PeerFlare:
+    """The B200-native form of the multi-GPU frame: NO collective call.  Every rank's accumulators live in symmetric
+    memory (mapped into all ranks over NVLink); after the trace, each rank runs ONE fused kernel
+    (lfb_reduce_finalize_peers) that sums all ranks' accumulators for its 1/N slice of the pixels -- peer loads, or
+    in-switch multimem.ld_reduce when the buffers are bound to an NVSwitch multicast object -- converts to pixels and
+    stores them directly into the owner rank's output buffer.  A device-side barrier (symmetric-memory signal pads) on
+    the engine stream separates trace and reduce; with >= 2 rotating accumulator sets one barrier per frame suffices,
+    because a rank can only arrive at barrier k+1 after its own reduce k has finished reading the peers.
+
+    torch supplies the plumbing (symmetric allocation, rendezvous, barrier); the data path is liblfb200.so."""
+
+    def __init__(self, engine, params, rank, world_size, device, group, n_buffers=2, out_dtype=torch.float32,
+                 use_multicast=False):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.engine, self.rank, self.world, self.device = engine, rank, world_size, device
+        self.full_params = params
+        self.params = shard_params(params, rank, world_size)
+        self.n_buffers = n_buffers
+        H, W = params.height, params.width
+        self.accum_all = symm_mem.empty((n_buffers, H, W, 3), dtype=torch.int64, device=device)
+        self.out_all = symm_mem.empty((n_buffers, H, W, 3), dtype=out_dtype, device=device)
+        self.h_acc = symm_mem.rendezvous(self.accum_all, group.group_name)
+        self.h_out = symm_mem.rendezvous(self.out_all, group.group_name)
+        self.accum_all.zero_()
+        self.acc_bytes = H * W * 3 * 8
+        self.out_bytes = H * W * 3 * self.out_all.element_size()
+        self.elem = capi.F32x3 if out_dtype == torch.float32 else capi.F64x3
+        self.mc = int(self.h_acc.multicast_ptr) if (use_multicast and self.h_acc.has_multicast_support) else 0
+        self.A = torch.cuda.ExternalStream(engine.stream, device=device)
+        self.k = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    def begin(self, stream=None):
+        self.A.wait_stream(stream or torch.cuda.current_stream(self.device))
+
+    def join(self, stream=None):
+        (stream or torch.cuda.current_stream(self.device)).wait_stream(self.A)
+
+    def barrier(self):
+        """Device-side barrier across the ranks, enqueued on the engine stream."""
+        with torch.cuda.stream(self.A):
+            self.h_acc.barrier(channel=0)
+
+    def frame(self, lights, owner=0):
+        """Enqueue one frame.  Returns the buffer index; the owner's pixels are complete after the NEXT barrier()."""
+        b = self.k % self.n_buffers
+        self.k += 1
+        my_acc = int(self.h_acc.buffer_ptrs[self.rank]) + b * self.acc_bytes
+        self.engine.render_ghosts_device(lights, self.params, my_acc, clear_first=True)
+        self.barrier()  # every rank has finished splatting into buffer b (and reading buffer b of the previous round)
+        ptrs = [int(p) + b * self.acc_bytes for p in self.h_acc.buffer_ptrs]
+        out_ptr = int(self.h_out.buffer_ptrs[owner]) + b * self.out_bytes
+        self.engine.reduce_finalize_peers(ptrs, self.rank, self.full_params, out_ptr, 3 * self.out_all.element_size(), self.elem,
+                                          multicast_ptr=(self.mc + b * self.acc_bytes) if self.mc else None)
+        return b
+
+    def result(self, b):
+        """The owner's pixels of buffer b (valid after a barrier() + join() following frame())."""
+        return self.out_all[b]

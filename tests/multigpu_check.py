@@ -1,0 +1,69 @@
+"""Multi-GPU parity check, launched with torchrun on a box with >= 2 GPUs (tests/test_multigpu.py does that when it can):
+the sharded frame -- NCCL reduce path (ShardedFlare) and fused peer-memory path (PeerFlare, with and without NVSwitch
+multicast) -- must equal the unsharded single-GPU frame bit for bit."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lens_flare_b200 import capi, sharding  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "apertures.npz"))
+    tex = z["pentbig500_14"].astype(np.float32) * np.float32(1.0 / 255.0)
+    lens = capi.builtin_lens(3, 550.0)
+    eng = capi.Engine(local)
+    eng.set_lens(lens)
+    eng.set_aperture(tex)
+    W, H = 960, 540
+    params = capi.make_params(capi.MODE_EXACT_GRID, W, H, grid_n=128, pair_set=capi.PAIRS_ALL, include_direct=1)
+    lights = [capi.make_light(0.45, 0.55, theta=capi.physical_theta(0.45, 0.55)), capi.make_light(0.7, 0.3, theta=0.1, radiance=(0.5, 1.0, 2.0))]
+    whole = torch.from_numpy(eng.render_ghosts(lights, params, elem=capi.F32x3)).to(dev)  # unsharded, on every rank
+    ok = True
+    # --- NCCL path
+    sh = sharding.ShardedFlare(eng, params, rank, world, dev, n_buffers=2)
+    out = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    sh.begin()
+    for _ in range(3):
+        sh.frame(lights, out=out, elem=capi.F32x3, reduce_dst=0)
+    sh.join()
+    torch.cuda.synchronize()
+    if rank == 0:
+        same = torch.equal(out, whole)
+        print("nccl reduce path == single GPU:", same)
+        ok &= same
+    # --- fused peer-memory path, plain peer loads then NVSwitch multicast
+    for mc in (False, True):
+        pf = sharding.PeerFlare(eng, params, rank, world, dev, dist.group.WORLD, n_buffers=2, use_multicast=mc)
+        if mc and not pf.mc:
+            if rank == 0:
+                print("multicast not supported on this box: skipped")
+            continue
+        pf.begin()
+        for _ in range(3):
+            b = pf.frame(lights, owner=0)
+        pf.barrier()
+        pf.join()
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = torch.equal(pf.result(b), whole)
+            print(f"peer path (multicast={mc}) == single GPU:", same)
+            ok &= same
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    eng.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
