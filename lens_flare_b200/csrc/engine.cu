@@ -482,7 +482,13 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   lfb_engine* e = new (std::nothrow) lfb_engine();
   if (!e) return fail(LFB_ERR_NOMEM, "out of host memory");
   e->device = device_id;
-  cudaError_t rc = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  // LFB_STREAM_PRIORITY=high: for a second engine whose short kernels (finalize, peer reduce) must slip in between the
+  // CTAs of another engine's long trace kernel on the same device
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  const char* prio_env = getenv("LFB_STREAM_PRIORITY");
+  const int prio = (prio_env && !strcmp(prio_env, "high")) ? prio_hi : prio_lo;
+  cudaError_t rc = cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_frame0);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_trace0);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_trace1);

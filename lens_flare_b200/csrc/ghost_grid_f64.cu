@@ -5,6 +5,7 @@
 #define LFB_TU f64
 #include "ghost_grid_impl.cuh"
 #include "ref_abcd.cuh"
+#include <stdlib.h>
 
 namespace lfb {
 
@@ -131,34 +132,98 @@ __device__ __forceinline__ unsigned long long multimem_add_u64(const unsigned lo
   return v;
 }
 
-__global__ void __launch_bounds__(256) reduce_finalize_kernel(PeerAccums P, const unsigned long long* __restrict__ mc, size_t p0, size_t p1,
-                                                              double inv_scale, char* __restrict__ out, size_t stride, int elem) {
-  const size_t p = p0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= p1) return;
-  double v[3];
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-    unsigned long long sum = 0;
-    if (mc) {
-      sum = multimem_add_u64(mc + 3 * p + c);
-    } else {
-      for (int r = 0; r < P.n; r++) sum += P.ptr[r][3 * p + c];
-    }
-    v[c] = (double)(long long)sum * inv_scale;
-  }
-  if (elem == LFB_F32x3) {
-    float* o = reinterpret_cast<float*>(out + p * stride);
-    o[0] = (float)v[0]; o[1] = (float)v[1]; o[2] = (float)v[2];
+// The accumulators are treated as a flat u64 array: each thread owns 4 consecutive values (two 16-byte loads per rank,
+// all issued before any is used, so a warp keeps 32 x 32 B x n_ranks in flight across NVLink).
+__device__ __forceinline__ void store_value(char* out, size_t e, double v, size_t stride, int elem, bool packed) {
+  if (packed) {
+    if (elem == LFB_F32x3) reinterpret_cast<float*>(out)[e] = (float)v;
+    else reinterpret_cast<double*>(out)[e] = v;
   } else {
-    double* o = reinterpret_cast<double*>(out + p * stride);
-    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+    const size_t p = e / 3;
+    const int c = (int)(e - 3 * p);
+    if (elem == LFB_F32x3) reinterpret_cast<float*>(out + p * stride)[c] = (float)v;
+    else reinterpret_cast<double*>(out + p * stride)[c] = v;
+  }
+}
+
+// Persistent form: a fixed grid (2 CTAs per SM) strides over the slice, so the kernel co-runs with the next frame's trace
+// kernel instead of queueing thousands of CTAs behind it; each thread keeps UNROLL x 32 B per rank in flight.
+template <int UNROLL>
+__global__ void __launch_bounds__(256) reduce_finalize_kernel(PeerAccums P, const unsigned long long* __restrict__ mc, size_t e0, size_t e1,
+                                                              double inv_scale, char* __restrict__ out, size_t stride, int elem) {
+  const bool packed = stride == (elem == LFB_F32x3 ? 12u : 24u);
+  const size_t chunk = 4;  // values per thread per load group
+  const size_t n_groups = (e1 - e0) / chunk;  // full groups; the tail is handled by thread 0 of block 0
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t g0 = tid; g0 < n_groups; g0 += nthreads * UNROLL) {
+    unsigned long long sum[UNROLL][4];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) { sum[u][0] = sum[u][1] = sum[u][2] = sum[u][3] = 0; }
+    if (mc) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        const size_t g = g0 + (size_t)u * nthreads;
+        if (g < n_groups) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) sum[u][k] = multimem_add_u64(mc + e0 + g * chunk + k);
+        }
+      }
+    } else {
+      for (int r = 0; r < P.n; r++) {
+        ulonglong2 v[UNROLL][2];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+          const size_t g = g0 + (size_t)u * nthreads;
+          if (g < n_groups) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.ptr[r] + e0 + g * chunk);
+            v[u][0] = src[0]; v[u][1] = src[1];
+          } else {
+            v[u][0] = v[u][1] = make_ulonglong2(0, 0);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) { sum[u][0] += v[u][0].x; sum[u][1] += v[u][0].y; sum[u][2] += v[u][1].x; sum[u][3] += v[u][1].y; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const size_t g = g0 + (size_t)u * nthreads;
+      if (g < n_groups) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) store_value(out, e0 + g * chunk + k, (double)(long long)sum[u][k] * inv_scale, stride, elem, packed);
+      }
+    }
+  }
+  if (tid == 0) {
+    for (size_t q = e0 + n_groups * chunk; q < e1; q++) {
+      unsigned long long t = 0;
+      if (mc) t = multimem_add_u64(mc + q);
+      else for (int r = 0; r < P.n; r++) t += P.ptr[r][q];
+      store_value(out, q, (double)(long long)t * inv_scale, stride, elem, packed);
+    }
   }
 }
 
 cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long* mc, size_t p0, size_t p1, double inv_scale,
                                    void* out, size_t stride, int elem, cudaStream_t s) {
   if (p1 <= p0) return cudaSuccess;
-  reduce_finalize_kernel<<<(unsigned)((p1 - p0 + 255) / 256), 256, 0, s>>>(P, mc, p0, p1, inv_scale, (char*)out, stride, elem);
+  size_t e0 = 3 * p0, e1 = 3 * p1;
+  if (e0 & 1) {  // keep the 16-byte loads aligned: the first (odd) value goes through the scalar tail of a 1-thread launch
+    reduce_finalize_kernel<1><<<1, 1, 0, s>>>(P, mc, e0, e0 + 1, inv_scale, (char*)out, stride, elem);
+    e0 += 1;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // few, fat CTAs: the kernel is bound by NVLink latency, not by SM resources, and must leave the SMs to the trace
+  // kernel it overlaps with (LFB_REDUCE_CTAS overrides the CTA count for tuning)
+  static int ctas = 0;
+  if (!ctas) {
+    const char* env = getenv("LFB_REDUCE_CTAS");
+    ctas = env ? atoi(env) : sms;
+    if (ctas < 1) ctas = sms;
+  }
+  if (e1 > e0) reduce_finalize_kernel<8><<<ctas, 256, 0, s>>>(P, mc, e0, e1, inv_scale, (char*)out, stride, elem);
   return cudaGetLastError();
 }
 

@@ -122,22 +122,29 @@ class PeerFlare:
     memory (mapped into all ranks over NVLink); after the trace, each rank runs ONE fused kernel
     (lfb_reduce_finalize_peers) that sums all ranks' accumulators for its 1/N slice of the pixels -- peer loads, or
     in-switch multimem.ld_reduce when the buffers are bound to an NVSwitch multicast object -- converts to pixels and
-    stores them directly into the owner rank's output buffer.  A device-side barrier (symmetric-memory signal pads) on
-    the engine stream separates trace and reduce; with >= 2 rotating accumulator sets one barrier per frame suffices,
-    because a rank can only arrive at barrier k+1 after its own reduce k has finished reading the peers.
+    stores them directly into the owner rank's output buffer.
+
+    Two streams, R >= 3 rotating accumulator / output sets:
+        stream A (engine)           trace frame k into accum[k % R]; device-side barrier (symmetric-memory signal pads)
+        stream B (finalize engine)  fused reduce + finalize of frame k (reads every rank's accum[k % R])
+    so the reduce of frame k overlaps the trace of frame k+1.  Buffer safety: trace(k) first waits for this rank's own
+    reduce(k-R+1); a peer can only pass barrier(k+R-1) -- and then overwrite accum[k % R] in trace(k+R) -- after this
+    rank arrived there, i.e. after this rank's reduce(k) finished reading it.  The owner's pixels of frame k are complete
+    after finish() (or once R-1 further frames have passed their barrier).
 
     torch supplies the plumbing (symmetric allocation, rendezvous, barrier); the data path is liblfb200.so."""
 
-    def __init__(self, engine, params, rank, world_size, device, group, n_buffers=2, out_dtype=torch.float32,
-                 use_multicast=False):
+    def __init__(self, engine, params, rank, world_size, device, group, n_buffers=3, out_dtype=torch.float32,
+                 use_multicast=False, finalize_engine=None):
         import torch.distributed._symmetric_memory as symm_mem
         self.engine, self.rank, self.world, self.device = engine, rank, world_size, device
+        self.fin_engine = finalize_engine if finalize_engine is not None else engine
         self.full_params = params
         self.params = shard_params(params, rank, world_size)
-        self.n_buffers = n_buffers
+        self.n_buffers = max(int(n_buffers), 3 if finalize_engine is not None else 2)
         H, W = params.height, params.width
-        self.accum_all = symm_mem.empty((n_buffers, H, W, 3), dtype=torch.int64, device=device)
-        self.out_all = symm_mem.empty((n_buffers, H, W, 3), dtype=out_dtype, device=device)
+        self.accum_all = symm_mem.empty((self.n_buffers, H, W, 3), dtype=torch.int64, device=device)
+        self.out_all = symm_mem.empty((self.n_buffers, H, W, 3), dtype=out_dtype, device=device)
         self.h_acc = symm_mem.rendezvous(self.accum_all, group.group_name)
         self.h_out = symm_mem.rendezvous(self.out_all, group.group_name)
         self.accum_all.zero_()
@@ -146,34 +153,51 @@ class PeerFlare:
         self.elem = capi.F32x3 if out_dtype == torch.float32 else capi.F64x3
         self.mc = int(self.h_acc.multicast_ptr) if (use_multicast and self.h_acc.has_multicast_support) else 0
         self.A = torch.cuda.ExternalStream(engine.stream, device=device)
+        self.B = torch.cuda.ExternalStream(self.fin_engine.stream, device=device)
+        self.two_streams = self.fin_engine is not engine
+        self.reduce_done = {}
         self.k = 0
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
 
     def begin(self, stream=None):
-        self.A.wait_stream(stream or torch.cuda.current_stream(self.device))
-
-    def join(self, stream=None):
-        (stream or torch.cuda.current_stream(self.device)).wait_stream(self.A)
+        cur = stream or torch.cuda.current_stream(self.device)
+        self.A.wait_stream(cur)
+        self.B.wait_stream(cur)
 
     def barrier(self):
         """Device-side barrier across the ranks, enqueued on the engine stream."""
         with torch.cuda.stream(self.A):
             self.h_acc.barrier(channel=0)
 
+    def finish(self, stream=None):
+        """All frames enqueued so far are complete in the owner's buffers once `stream` passes this point."""
+        self.A.wait_stream(self.B)
+        self.barrier()
+        (stream or torch.cuda.current_stream(self.device)).wait_stream(self.A)
+
     def frame(self, lights, owner=0):
-        """Enqueue one frame.  Returns the buffer index; the owner's pixels are complete after the NEXT barrier()."""
-        b = self.k % self.n_buffers
+        """Enqueue one frame; returns its buffer index."""
+        k, R = self.k, self.n_buffers
+        b = k % R
         self.k += 1
+        if self.two_streams and (k - R + 1) in self.reduce_done:
+            self.A.wait_event(self.reduce_done.pop(k - R + 1))
         my_acc = int(self.h_acc.buffer_ptrs[self.rank]) + b * self.acc_bytes
         self.engine.render_ghosts_device(lights, self.params, my_acc, clear_first=True)
-        self.barrier()  # every rank has finished splatting into buffer b (and reading buffer b of the previous round)
+        self.barrier()  # every rank has finished splatting into buffer b
+        if self.two_streams:
+            self.B.wait_stream(self.A)
         ptrs = [int(p) + b * self.acc_bytes for p in self.h_acc.buffer_ptrs]
         out_ptr = int(self.h_out.buffer_ptrs[owner]) + b * self.out_bytes
-        self.engine.reduce_finalize_peers(ptrs, self.rank, self.full_params, out_ptr, 3 * self.out_all.element_size(), self.elem,
-                                          multicast_ptr=(self.mc + b * self.acc_bytes) if self.mc else None)
+        self.fin_engine.reduce_finalize_peers(ptrs, self.rank, self.full_params, out_ptr, 3 * self.out_all.element_size(), self.elem,
+                                              multicast_ptr=(self.mc + b * self.acc_bytes) if self.mc else None)
+        if self.two_streams:
+            ev = torch.cuda.Event()
+            ev.record(self.B)
+            self.reduce_done[k] = ev
         return b
 
     def result(self, b):
-        """The owner's pixels of buffer b (valid after a barrier() + join() following frame())."""
+        """The owner's pixels of buffer b (valid after finish())."""
         return self.out_all[b]

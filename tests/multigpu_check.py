@@ -42,24 +42,26 @@ def main():
         print("nccl reduce path == single GPU:", same)
         ok &= same
     # --- fused peer-memory path, plain peer loads then NVSwitch multicast
-    for mc in (False, True):
-        pf = sharding.PeerFlare(eng, params, rank, world, dev, dist.group.WORLD, n_buffers=2, use_multicast=mc)
+    fin = capi.Engine(local)
+    for mc, two in ((False, False), (False, True), (True, True)):
+        pf = sharding.PeerFlare(eng, params, rank, world, dev, dist.group.WORLD, n_buffers=3, use_multicast=mc,
+                                finalize_engine=fin if two else None)
         if mc and not pf.mc:
             if rank == 0:
                 print("multicast not supported on this box: skipped")
             continue
         pf.begin()
-        for _ in range(3):
+        for _ in range(7):
             b = pf.frame(lights, owner=0)
-        pf.barrier()
-        pf.join()
+        pf.finish()
         torch.cuda.synchronize()
         if rank == 0:
-            same = torch.equal(pf.result(b), whole)
-            print(f"peer path (multicast={mc}) == single GPU:", same)
+            same = all(torch.equal(pf.result(q), whole) for q in range(3))
+            print(f"peer path (multicast={mc}, two streams={two}) == single GPU:", same)
             ok &= same
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    fin.close()
     eng.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag) == 1 else 1)
