@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Runs BASELINE.json's configs 1-4 on one GPU (device-resident frames, CUDA-event timed) and prints one JSON line per
+config: ms per frame, nominal ray-surface interactions / s, image checksum.  Config 1 is also checked against the CPU oracle.
+Config 5 (path-traced dae/dragon.dae composite) is blocked: the asset is missing from the reference checkout."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lens_flare_b200 import capi, sharding  # noqa: E402
+
+
+def suns(n):
+    pts = []
+    side = int(np.ceil(np.sqrt(n)))
+    for k in range(n):
+        gx, gy = k % side, k // side
+        x, y = 0.1 + 0.8 * (gx + 0.5) / side, 0.1 + 0.8 * (gy + 0.5) / side
+        pts.append((x + 0.013, y - 0.007))  # never the exact screen centre
+    return pts
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "apertures.npz"))
+    ap = {k: z[k].astype(np.float32) * np.float32(1.0 / 255.0) for k in ("pent_11", "pentbig500_14")}
+    cfgs = [
+        ("cfg1", dict(n_lambda=1, coat=0.0, grid=64, W=512, H=512, tex="pent_11", lights=1, pairs=capi.PAIRS_REF, direct=0, reps=50)),
+        ("cfg2", dict(n_lambda=3, coat=550.0, grid=256, W=1920, H=1080, tex="pentbig500_14", lights=1, pairs=capi.PAIRS_ALL, direct=1, reps=50)),
+        ("cfg3", dict(n_lambda=32, coat=550.0, grid=512, W=1920, H=1080, tex="pentbig500_14", lights=1, pairs=capi.PAIRS_ALL, direct=1, reps=10)),
+        ("cfg4", dict(n_lambda=3, coat=550.0, grid=1024, W=3840, H=2160, tex="pentbig500_14", lights=64, pairs=capi.PAIRS_ALL, direct=1, reps=3)),
+    ]
+    only = sys.argv[1:]
+    for name, c in cfgs:
+        if only and name not in only:
+            continue
+        eng, fin = capi.Engine(0), capi.Engine(0)
+        lens = capi.builtin_lens(3 if c["n_lambda"] == 1 else c["n_lambda"], c["coat"])
+        if c["n_lambda"] == 1:  # config 1: one wavelength (G)
+            g = capi.builtin_lens(3, c["coat"])
+            lens.n_lambda = 1
+            for k in range(9):
+                lens.ior[0][k] = g.ior[1][k]
+            lens.lambda_nm[0] = g.lambda_nm[1]
+            for ch in range(3):
+                lens.rgb_weight[0][ch] = 1.0
+        eng.set_lens(lens)
+        eng.set_aperture(ap[c["tex"]])
+        p = capi.make_params(capi.MODE_EXACT_GRID, c["W"], c["H"], grid_n=c["grid"], pair_set=c["pairs"], include_direct=c["direct"])
+        lights = [capi.make_light(x, y, theta=capi.physical_theta(x, y)) for x, y in ([(0.45, 0.55)] if c["lights"] == 1 else suns(c["lights"]))]
+        rays, inter, jobs = capi.count_work(lens, p, len(lights))
+        sh = sharding.ShardedFlare(eng, p, 0, 1, dev, n_buffers=2, finalize_engine=fin)
+        out = torch.empty((c["H"], c["W"], 3), dtype=torch.float32, device=dev)
+        sh.begin()
+        for _ in range(2):
+            sh.frame(lights, out=out)
+        sh.join()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sh.begin()
+        for _ in range(c["reps"]):
+            sh.frame(lights, out=out)
+        sh.join()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / c["reps"]
+        img = out.cpu().numpy().astype(np.float64)
+        line = {"config": name, "lights": len(lights), "n_lambda": lens.n_lambda, "grid": c["grid"], "sensor": [c["W"], c["H"]], "jobs": jobs,
+                "rays": rays, "interactions": inter, "ms_per_frame": ms, "interactions_per_s": inter / (ms * 1e-3),
+                "kernel_ms": eng.stats()["last_trace_ms"], "image_sum": [float(v) for v in img.reshape(-1, 3).sum(0)],
+                "nonzero_px": int((img != 0).any(-1).sum())}
+        if name == "cfg1":
+            from oracle import bindings as ob
+            if not os.path.exists(ob.PORT_SO):
+                ob.build(("port",))
+            t0 = time.perf_counter()
+            want = ob.PortOracle().render(lens, ap[c["tex"]], lights, p)
+            line["cpu_oracle_ms_1thread"] = (time.perf_counter() - t0) * 1e3
+            line["rel_l2_vs_oracle"] = float(np.sqrt(((img - want) ** 2).sum() / (want ** 2).sum()))
+        print(json.dumps(line), flush=True)
+        fin.close()
+        eng.close()
+
+
+if __name__ == "__main__":
+    main()
