@@ -138,6 +138,15 @@ struct lfb_engine {
   Step* d_progs = nullptr;   // FP32 EXACT_GRID step programs, LFB_MAX_STEPS per job
   Step* h_progs = nullptr;   // pinned staging
   Step* d_dump_prog = nullptr;
+  // prefix cache (FP32 EXACT_GRID v5): one slot per (light, lambda) of the frame
+  Job* d_slots = nullptr;  Job* h_slots = nullptr;
+  Step* d_slot_progs = nullptr;  Step* h_slot_progs = nullptr;
+  int slots_cap = 0, n_slots = 0;
+  float4* d_prefix = nullptr;
+  size_t prefix_cap = 0;
+  bool use_prefix = true;            // LFB_EXACT_PREFIX=0 disables
+  size_t prefix_budget = (size_t)40 << 30;  // bytes of HBM the cache may take (LFB_PREFIX_BUDGET_MB)
+  bool frame_has_prefix = false;
   float2* d_lut = nullptr;   // reflectance tables, kLutSize entries per (lambda, surface, direction)
   bool use_lut = true;       // LFB_EXACT_WEIGHTS=closed selects the closed-form two-pass kernel instead
   int min_blocks = 6;        // register-allocation target of the FP32 exact kernel, CTAs/SM (LFB_EXACT_MINB=4|5|6)
@@ -224,6 +233,9 @@ FrameGeom make_geom(const lfb_engine* e, const lfb_params& P) {
   g.mask_su = 0.5f * (float)e->tex_w / g.h_stop; g.mask_ou = 0.5f * (float)e->tex_w;
   g.mask_sv = -0.5f * (float)e->tex_h / g.h_stop; g.mask_ov = 0.5f * (float)e->tex_h;
   g.lut = (e->use_lut && P.mode == LFB_MODE_EXACT_GRID && P.precision == LFB_FP32) ? e->d_lut : nullptr;
+  g.prefix = nullptr;  // set by render_grid_device when the frame's jobs were built against the prefix cache
+  g.half_rays = P.grid_n * ((P.grid_n + 1) / 2);
+  g.n_surf = e->lens.n_surfaces;
   g.bbox = e->track_bbox ? e->d_bbox : nullptr;
   g.patch = e->patch; g.pad = e->min_blocks;
   return g;
@@ -287,9 +299,12 @@ void build_reflectance_tables(const lfb_lens& L, std::vector<float2>& out) {
 // Flatten ghost (i, j) at wavelength lam into the FP32 step program (exact_f32.cuh): the surface sequence
 // forward 0..j-1, reflect at j, backward j-1..i+1, reflect at i, forward i+1..n-1, sensor plane (i < 0: the
 // direct path), with every ray-independent quantity of each step computed here, once.
-int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, Step* out) {
+// from_reflection: the program starts ON surface j with the first reflection (the forward sweep 0 .. j-1 comes from the
+// prefix cache).  prefix_only: just the forward sweep 0 .. n-1 (no reflections, no sensor) -- what prefix_kernel traces.
+int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, Step* out, bool from_reflection = false,
+                  bool prefix_only = false) {
   const int n = L.n_surfaces, stop = L.stop_index;
-  int ns = 0, prev = 0;
+  int ns = 0, prev = from_reflection ? j : 0;
   auto push = [&](int k, int op, bool forward) {
     Step S;
     memset(&S, 0, sizeof(S));
@@ -317,10 +332,15 @@ int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, St
     }
     out[ns++] = S;
   };
+  if (prefix_only) {
+    for (int k = 0; k < n; k++) push(k, STEP_REFRACT, true);
+    return ns;
+  }
   if (i < 0) {
     for (int k = 0; k < n; k++) push(k, STEP_REFRACT, true);
   } else {
-    for (int k = 0; k < j; k++) push(k, STEP_REFRACT, true);
+    if (!from_reflection)
+      for (int k = 0; k < j; k++) push(k, STEP_REFRACT, true);
     push(j, STEP_REFLECT, true);
     for (int k = j - 1; k > i; k--) push(k, STEP_REFRACT, false);
     push(i, STEP_REFLECT, false);
@@ -376,10 +396,58 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
   // the previous frame's upload may still be reading h_jobs
   CU(cudaStreamSynchronize(e->stream));
   const bool want_progs = P.mode == LFB_MODE_EXACT_GRID && P.precision == LFB_FP32;
+  // prefix cache: one slot per (light, lambda) that has ghost jobs in this shard
+  std::vector<int> slot_of;   // [light * n_lambda + lambda] -> slot or -1
+  std::vector<JobId> slot_ids;
+  e->frame_has_prefix = false;
+  if (want_progs && e->use_lut && e->use_prefix) {
+    slot_of.assign((size_t)std::max(n_lights, 1) * e->lens.n_lambda, -1);
+    for (int q = 0; q < n; q++)
+      if (ids[q].i >= 0) {
+        int& sl = slot_of[(size_t)ids[q].light * e->lens.n_lambda + ids[q].lambda];
+        if (sl < 0) { sl = (int)slot_ids.size(); slot_ids.push_back({ids[q].light, -1, -1, ids[q].lambda}); }
+      }
+    const size_t half_rays = (size_t)P.grid_n * ((P.grid_n + 1) / 2);
+    const size_t need = slot_ids.size() * (size_t)e->lens.n_surfaces * 2 * half_rays * sizeof(float4);
+    if (!slot_ids.empty() && need <= e->prefix_budget) {
+      int rc = grow(&e->d_prefix, &e->prefix_cap, need);
+      if (rc == LFB_OK) e->frame_has_prefix = true;
+      else if (rc != LFB_ERR_NOMEM) return rc;
+    }
+  }
+  if (e->frame_has_prefix) {
+    const int ns = (int)slot_ids.size();
+    if (ns > e->slots_cap) {
+      if (e->d_slots) CU(cudaFree(e->d_slots));
+      if (e->h_slots) CU(cudaFreeHost(e->h_slots));
+      if (e->d_slot_progs) CU(cudaFree(e->d_slot_progs));
+      if (e->h_slot_progs) CU(cudaFreeHost(e->h_slot_progs));
+      e->d_slots = nullptr; e->h_slots = nullptr; e->d_slot_progs = nullptr; e->h_slot_progs = nullptr; e->slots_cap = 0;
+      CU(cudaMalloc((void**)&e->d_slots, sizeof(Job) * (size_t)ns));
+      CU(cudaHostAlloc((void**)&e->h_slots, sizeof(Job) * (size_t)ns, cudaHostAllocDefault));
+      CU(cudaMalloc((void**)&e->d_slot_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)ns));
+      CU(cudaHostAlloc((void**)&e->h_slot_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)ns, cudaHostAllocDefault));
+      e->slots_cap = ns;
+    }
+    for (int sl = 0; sl < ns; sl++) {
+      fill_job(e, P, lights[slot_ids[sl].light], slot_ids[sl], &e->h_slots[sl]);
+      e->h_slots[sl].n_steps = build_program(e->lens, e->dev_lens, slot_ids[sl].lambda, -1, -1, e->h_slot_progs + (size_t)sl * LFB_MAX_STEPS, false, true);
+    }
+    e->n_slots = ns;
+    CU(cudaMemcpyAsync(e->d_slots, e->h_slots, sizeof(Job) * (size_t)ns, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->d_slot_progs, e->h_slot_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)ns, cudaMemcpyHostToDevice, e->stream));
+  }
   for (int q = 0; q < n; q++) {
     fill_job(e, P, lights[ids[q].light], ids[q], &e->h_jobs[q]);
-    if (want_progs)
-      e->h_jobs[q].n_steps = build_program(e->lens, e->dev_lens, ids[q].lambda, ids[q].i, ids[q].j, e->h_progs + (size_t)q * LFB_MAX_STEPS);
+    e->h_jobs[q].slot = -1;
+    if (want_progs) {
+      const bool cached = e->frame_has_prefix && ids[q].i >= 0;
+      if (cached) {
+        e->h_jobs[q].slot = slot_of[(size_t)ids[q].light * e->lens.n_lambda + ids[q].lambda];
+        e->h_jobs[q].j_first = ids[q].j;
+      }
+      e->h_jobs[q].n_steps = build_program(e->lens, e->dev_lens, ids[q].lambda, ids[q].i, ids[q].j, e->h_progs + (size_t)q * LFB_MAX_STEPS, cached);
+    }
   }
   e->n_jobs = n;
   if (n > 0) {
@@ -401,9 +469,14 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
   if (rc) return rc;
   rc = prepare_jobs(e, lights, n_lights, P);
   if (rc) return rc;
-  const FrameGeom g = make_geom(e, P);
+  FrameGeom g = make_geom(e, P);
   if (clear_first) CU(cudaMemsetAsync(accum, 0, lfb_accum_bytes(P.width, P.height), e->stream));
   CU(cudaEventRecord(e->ev_trace0, e->stream));
+  if (e->n_jobs > 0 && e->frame_has_prefix && g.lut) {
+    CU(launch_prefix_f32(e->d_slots, e->d_slot_progs, e->n_slots, g, e->d_tex, e->d_prefix, e->stream));
+    e->launches++;
+    g.prefix = e->d_prefix;
+  }
   if (e->n_jobs > 0) {
     if (P.precision == LFB_FP64) CU(launch_trace_splat_f64(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
     else CU(launch_trace_splat_f32(e->d_jobs, e->d_progs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
@@ -501,6 +574,8 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   if (const char* env = getenv("LFB_EXACT_PATCH")) e->patch = atoi(env);
   if (const char* env = getenv("LFB_EXACT_MINB")) e->min_blocks = atoi(env);
   if (const char* env = getenv("LFB_EXACT_WEIGHTS")) e->use_lut = strcmp(env, "closed") != 0;
+  if (const char* env = getenv("LFB_EXACT_PREFIX")) e->use_prefix = atoi(env) != 0;
+  if (const char* env = getenv("LFB_PREFIX_BUDGET_MB")) e->prefix_budget = (size_t)atoll(env) << 20;
   if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
   *out = e;
   return LFB_OK;
@@ -512,6 +587,9 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
   cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox); cudaFree(e->d_lut);
+  cudaFree(e->d_slots); cudaFree(e->d_slot_progs); cudaFree(e->d_prefix);
+  if (e->h_slots) cudaFreeHost(e->h_slots);
+  if (e->h_slot_progs) cudaFreeHost(e->h_slot_progs);
   cudaFree(e->d_star_tex); cudaFree(e->d_star_scratch); cudaFree(e->d_star_lights); cudaFree(e->d_hdr); cudaFree(e->d_rgba);
   if (e->h_bbox) cudaFreeHost(e->h_bbox);
   if (e->h_progs) cudaFreeHost(e->h_progs);

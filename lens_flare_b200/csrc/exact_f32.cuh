@@ -116,61 +116,96 @@ __device__ __forceinline__ float reflectance_lut(const float2* __restrict__ lut,
 // Every step runs the same straight-line code (planes are c = 0 surfaces with an infinite clear radius); a
 // missed surface or a total internal reflection turns the state into NaNs, which the next clear-radius
 // test catches, so the throughput variants carry ONE death test per step.
+struct RayState {
+  float ox, oy, oz, dx, dy, dz;  // position relative to the current surface's vertex; unit direction
+  float w, ma, mb;               // Fresnel product; mask products of the ray and of its mirror image
+};
+
+// First half of a step: move the ray onto the step's surface (sphere or plane through its vertex) and test the clear
+// aperture.  False = the ray is dead (missed, vignetted, or NaN from a total internal reflection upstream).
+template <bool FLAGS>
+__device__ __forceinline__ bool propagate(const Step& S, RayState& r, RayOut& o) {
+  const float c = S.c;
+  const float pz = r.oz + S.dz;
+  const float pd = fmaf(r.ox, r.dx, fmaf(r.oy, r.dy, pz * r.dz));
+  const float pp = fmaf(r.ox, r.ox, fmaf(r.oy, r.oy, pz * pz));
+  const float B = fmaf(c, pd, -r.dz);
+  const float Cq = fmaf(c, pp, -2.f * pz);
+  const float disc = fmaf(B, B, -c * Cq);
+  if (FLAGS && disc < 0.f) { o.flags |= LFB_RAY_MISSED; return false; }
+  const float t = -Cq * frcp(B + copysignf(fsqrt(disc), B));
+  r.ox = fmaf(t, r.dx, r.ox); r.oy = fmaf(t, r.dy, r.oy); r.oz = fmaf(t, r.dz, pz);
+  if (!(fmaf(r.ox, r.ox, r.oy * r.oy) <= S.semi2)) {  // outside the clear aperture, or NaN from a miss / TIR upstream
+    if (FLAGS) o.flags |= LFB_RAY_VIGNETTED;
+    return false;
+  }
+  return true;
+}
+
+// Second half: what the surface does to the ray (mask lookup at the stop; refraction or reflection + weight elsewhere).
+template <int WEIGHTS, bool MIRROR, bool FLAGS>
+__device__ __forceinline__ bool interact(const Step& S, const MaskGeom& M, const float2* __restrict__ lut, RayState& r, RayOut& o) {
+  const int op = S.op;
+  if (op >= STEP_PASS) {  // no change of direction: identical media, the stop, the sensor
+    if (op == STEP_STOP) {
+      const float m = mask_lookup(M, r.ox, r.oy);
+      r.ma *= m;
+      if (MIRROR) r.mb *= mask_lookup(M, r.ox, -r.oy);
+      if (FLAGS) { o.xa = r.ox; o.ya = r.oy; if (m == 0.f) o.flags |= LFB_RAY_STOPPED; }
+      else if (MIRROR ? (r.ma == 0.f && r.mb == 0.f) : (r.ma == 0.f)) return false;
+    }
+    return true;
+  }
+  const float c = S.c, eta = S.eta;
+  const float nx = -c * r.ox, ny = -c * r.oy, nz = fmaf(-c, r.oz, 1.f);
+  const float nd = fmaf(nx, r.dx, fmaf(ny, r.dy, nz * r.dz));
+  const float c0 = fabsf(nd);
+  const float s2 = fmaf(-c0, c0, 1.f);
+  const float k2 = fmaf(-S.eta2, s2, 1.f);
+  const float c2 = fsqrt(k2);  // NaN beyond the critical angle
+  const bool refl = op == STEP_REFLECT;
+  if (FLAGS && !refl && k2 < 0.f) { o.flags |= LFB_RAY_TIR; return false; }
+  // refract: d' = eta d + (eta c0 - c2) N with N = -sign(nd) n the normal facing the ray;  reflect: d' = d - 2 nd n
+  const float g = __int_as_float(__float_as_int(fmaf(eta, c0, -c2)) ^ (~__float_as_int(nd) & 0x80000000));
+  const float alpha = refl ? 1.f : eta, beta = refl ? -2.f * nd : g;
+  r.dx = fmaf(alpha, r.dx, beta * nx); r.dy = fmaf(alpha, r.dy, beta * ny); r.dz = fmaf(alpha, r.dz, beta * nz);
+  if (WEIGHTS == 1) {
+    const float R = (k2 < 0.f) ? 1.f : reflectance(S, c0, c2);
+    r.w *= refl ? R : 1.f - R;
+  } else if (WEIGHTS == 2) {
+    const float R = reflectance_lut(lut, S.lut, eta > 1.f ? c2 : c0);
+    r.w *= refl ? R : 1.f - R;
+  }
+  return true;
+}
+
+// Run a step program on a ray state.  ON_SURFACE: the state already sits on the first step's surface (it was loaded
+// from the prefix buffer), so step 0 only interacts.
+template <int WEIGHTS, bool MIRROR, bool FLAGS, bool ON_SURFACE>
+__device__ __forceinline__ bool run_program(const Step* __restrict__ prog, int n_steps, const MaskGeom& M, const float2* __restrict__ lut,
+                                            RayState& r, RayOut& o) {
+  int s = 0;
+  if (ON_SURFACE) {
+    if (!interact<WEIGHTS, MIRROR, FLAGS>(prog[0], M, lut, r, o)) return false;
+    s = 1;
+  }
+#pragma unroll 1
+  for (; s < n_steps; s++) {
+    const Step& S = prog[s];
+    if (!propagate<FLAGS>(S, r, o)) return false;
+    if (!interact<WEIGHTS, MIRROR, FLAGS>(S, M, lut, r, o)) return false;
+  }
+  o.xs = r.ox; o.ys = r.oy; o.wa = r.w * r.ma; o.wb = r.w * r.mb;
+  return true;
+}
+
 template <int WEIGHTS, bool MIRROR, bool FLAGS>
 __device__ __forceinline__ bool trace(const Step* __restrict__ prog, int n_steps, const MaskGeom& M, const float2* __restrict__ lut,
                                       float x, float y, float sin_t, float cos_t, RayOut& o) {
-  float ox = x, oy = y, oz = 0.f, dx = sin_t, dy = 0.f, dz = cos_t, w = 1.f, ma = 1.f, mb = 1.f;
+  RayState r;
+  r.ox = x; r.oy = y; r.oz = 0.f; r.dx = sin_t; r.dy = 0.f; r.dz = cos_t; r.w = 1.f; r.ma = 1.f; r.mb = 1.f;
   if (FLAGS) { o.flags = 0; o.xa = o.ya = CUDART_NAN_F; }
-#pragma unroll 1
-  for (int s = 0; s < n_steps; s++) {
-    const Step& S = prog[s];
-    const float c = S.c, eta = S.eta;
-    const int op = S.op;
-    const float pz = oz + S.dz;
-    const float pd = fmaf(ox, dx, fmaf(oy, dy, pz * dz));
-    const float pp = fmaf(ox, ox, fmaf(oy, oy, pz * pz));
-    const float B = fmaf(c, pd, -dz);
-    const float Cq = fmaf(c, pp, -2.f * pz);
-    const float disc = fmaf(B, B, -c * Cq);
-    if (FLAGS && disc < 0.f) { o.flags |= LFB_RAY_MISSED; return false; }
-    const float t = -Cq * frcp(B + copysignf(fsqrt(disc), B));
-    ox = fmaf(t, dx, ox); oy = fmaf(t, dy, oy); oz = fmaf(t, dz, pz);
-    if (!(fmaf(ox, ox, oy * oy) <= S.semi2)) {  // outside the clear aperture, or NaN from a miss / TIR upstream
-      if (FLAGS) o.flags |= LFB_RAY_VIGNETTED;
-      return false;
-    }
-    if (op >= STEP_PASS) {  // no change of direction: identical media, the stop, the sensor
-      if (op == STEP_STOP) {
-        const float m = mask_lookup(M, ox, oy);
-        ma *= m;
-        if (MIRROR) mb *= mask_lookup(M, ox, -oy);
-        if (FLAGS) { o.xa = ox; o.ya = oy; if (m == 0.f) o.flags |= LFB_RAY_STOPPED; }
-        else if (MIRROR ? (ma == 0.f && mb == 0.f) : (ma == 0.f)) return false;
-      }
-      continue;
-    }
-    const float nx = -c * ox, ny = -c * oy, nz = fmaf(-c, oz, 1.f);
-    const float nd = fmaf(nx, dx, fmaf(ny, dy, nz * dz));
-    const float c0 = fabsf(nd);
-    const float s2 = fmaf(-c0, c0, 1.f);
-    const float k2 = fmaf(-S.eta2, s2, 1.f);
-    const float c2 = fsqrt(k2);  // NaN beyond the critical angle
-    const bool refl = op == STEP_REFLECT;
-    if (FLAGS && !refl && k2 < 0.f) { o.flags |= LFB_RAY_TIR; return false; }
-    // refract: d' = eta d + (eta c0 - c2) N with N = -sign(nd) n the normal facing the ray;  reflect: d' = d - 2 nd n
-    const float g = __int_as_float(__float_as_int(fmaf(eta, c0, -c2)) ^ (~__float_as_int(nd) & 0x80000000));
-    const float alpha = refl ? 1.f : eta, beta = refl ? -2.f * nd : g;
-    dx = fmaf(alpha, dx, beta * nx); dy = fmaf(alpha, dy, beta * ny); dz = fmaf(alpha, dz, beta * nz);
-    if (WEIGHTS == 1) {
-      const float R = (k2 < 0.f) ? 1.f : reflectance(S, c0, c2);
-      w *= refl ? R : 1.f - R;
-    } else if (WEIGHTS == 2) {
-      const float R = reflectance_lut(lut, S.lut, eta > 1.f ? c2 : c0);
-      w *= refl ? R : 1.f - R;
-    }
-  }
-  o.xs = ox; o.ys = oy; o.wa = w * ma; o.wb = w * mb;
-  return true;
+  return run_program<WEIGHTS, MIRROR, FLAGS, false>(prog, n_steps, M, lut, r, o);
 }
 
 struct PixMap {
@@ -516,6 +551,191 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat1_kernel(const Job*
   __syncthreads();
   if (tid < area) {  // flush: one global atomic per touched (pixel, channel)
     const int jy = (int)(((float)tid + 0.5f) * frcp((float)C.tw));  // tid / tw, exact for these small integers
+    const int jx = tid - jy * C.tw;
+    unsigned long long* dst = accum + 3 * ((size_t)(C.tx0 + jx) + (size_t)(C.ty0 + jy) * g.W);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const unsigned long long v = s_tile[3 * tid + c];
+      if (v) atomicAdd(dst + c, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// v5: PREFIX SHARING.  Every ghost (i, j) of a light and wavelength begins with the same forward sweep through surfaces
+// 0 .. j-1 -- 28 ghosts re-trace it 28 times, and more than half of all executed steps are in it (most rays die late in
+// the sweep or right after the first reflection).  prefix_kernel traces that sweep ONCE per (light, wavelength) "slot"
+// and caches each ray's state as it arrives ON every surface (32 bytes: position, direction x/y, Fresnel product, the
+// two mask products; NaN = dead).  A ghost job then loads the state at its first-reflection surface j and starts with
+// the reflection.  The cache is written once and read ~3 times per ray per slot out of L2.
+// Layout: prefix[((slot * n_surf + k) * 2 + part) * half_rays + ray], part 0 = (ox, oy, oz, w), part 1 = (dx, dy, ma, mb);
+// dz = +sqrt(1 - dx^2 - dy^2) (the sweep only travels forward).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) prefix_kernel(const Job* __restrict__ slots, const Step* __restrict__ progs, FrameGeom g,
+                                                          const float* __restrict__ tex, float4* __restrict__ prefix) {
+  __shared__ Step s_prog[LFB_MAX_STEPS];
+  const int half_rows = (g.N + 1) / 2;
+  const int patches_x = (g.N + 15) / 16;
+  const int patches_per_slot = patches_x * ((half_rows + 15) / 16);
+  const int slot = blockIdx.x / patches_per_slot;
+  const int patch = blockIdx.x - slot * patches_per_slot;
+  const Job& J = slots[slot];
+  const int n_steps = J.n_steps;  // forward refractions 0 .. n_surf-1 (the stop included), no sensor step
+  const int tid = threadIdx.x;
+  {
+    const float4* src = reinterpret_cast<const float4*>(progs + (size_t)slot * LFB_MAX_STEPS);
+    float4* dst = reinterpret_cast<float4*>(s_prog);
+    for (int q = tid; q < n_steps * 3; q += kThreads) dst[q] = __ldg(src + q);
+  }
+  __syncthreads();
+  const int a = (patch % patches_x) * 16 + (tid & 15), bp = (patch / patches_x) * 16 + (tid >> 4);
+  if (a >= g.N || bp >= half_rows) return;
+  const int b = g.N - 1 - bp;
+  const size_t ray = (size_t)bp * g.N + a;
+  MaskGeom M;
+  M.tex = tex; M.tw = g.tex_w; M.th = g.tex_h;
+  M.su = g.mask_su; M.ou = g.mask_ou; M.sv = g.mask_sv; M.ov = g.mask_ov;
+  RayState r;
+  r.ox = fmaf((float)a + 0.5f, g.cell, -g.P); r.oy = fmaf((float)b + 0.5f, g.cell, -g.P); r.oz = 0.f;
+  r.dx = J.f_sin_t; r.dy = 0.f; r.dz = J.f_cos_t; r.w = 1.f; r.ma = 1.f; r.mb = 1.f;
+  RayOut o;
+  bool alive = true;
+  float4* base = prefix + (size_t)slot * g.n_surf * 2 * g.half_rays + ray;
+#pragma unroll 1
+  for (int s = 0; s < n_steps; s++) {
+    const Step& S = s_prog[s];
+    if (alive) alive = propagate<false>(S, r, o);
+    float4* dst = base + (size_t)s * 2 * g.half_rays;
+    if (alive) {
+      dst[0] = make_float4(r.ox, r.oy, r.oz, r.w);
+      dst[g.half_rays] = make_float4(r.dx, r.dy, r.ma, r.mb);
+      alive = interact<2, true, false>(S, M, g.lut, r, o);
+    } else {
+      dst[0] = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// The ghost kernel of v5: exact_splat1_kernel with the ray states loaded from the prefix cache (jobs whose slot is >= 0);
+// jobs without a slot (the direct path) trace from the entrance as before.
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) exact_splat2_kernel(const Job* __restrict__ jobs, const Step* __restrict__ progs,
+                                                                      FrameGeom g, const float* __restrict__ tex,
+                                                                      unsigned long long* __restrict__ accum) {
+  static_assert(kTilePx <= kThreads, "one thread per tile pixel in the zero / flush loops");
+  __shared__ Step s_prog[LFB_MAX_STEPS];
+  __shared__ unsigned long long s_tile[kTilePx * 3];
+  __shared__ float4 s_qp[kThreads];
+  __shared__ float2 s_qw[kThreads];
+  __shared__ int s_count, s_bbox[4];
+
+  const int half_rows = (g.N + 1) / 2;
+  const int patches_x = (g.N + 15) / 16;
+  const int patches_per_job = patches_x * ((half_rows + 15) / 16);
+  const int job_id = blockIdx.x / patches_per_job;
+  const int patch = blockIdx.x - job_id * patches_per_job;
+  const Job& J = jobs[job_id];
+  const int n_steps = J.n_steps;
+  const int tid = threadIdx.x;
+  {
+    const float4* src = reinterpret_cast<const float4*>(progs + (size_t)job_id * LFB_MAX_STEPS);
+    float4* dst = reinterpret_cast<float4*>(s_prog);
+    for (int q = tid; q < n_steps * 3; q += kThreads) dst[q] = __ldg(src + q);
+    if (tid == 0) { s_count = 0; s_bbox[0] = s_bbox[1] = 0x7fffffff; s_bbox[2] = s_bbox[3] = -0x7fffffff; }
+  }
+  __syncthreads();
+
+  MaskGeom M;
+  M.tex = tex; M.tw = g.tex_w; M.th = g.tex_h;
+  M.su = g.mask_su; M.ou = g.mask_ou; M.sv = g.mask_sv; M.ov = g.mask_ov;
+  PixMap PM;
+  PM.sx = J.f_sx; PM.sy = J.f_sy; PM.cs = J.f_cs; PM.sn = J.f_sn; PM.ppu = J.f_ppu;
+  const bool bilinear = g.splat == LFB_SPLAT_BILINEAR;
+
+  int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
+  const int a = (patch % patches_x) * 16 + (tid & 15), bp = (patch / patches_x) * 16 + (tid >> 4);
+  const int b = g.N - 1 - bp;
+  float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 ww = make_float2(0.f, 0.f);
+  if (a < g.N && bp < half_rows) {
+    RayState r;
+    RayOut o;
+    bool alive;
+    if (J.slot >= 0) {
+      const float4* src = g.prefix + ((size_t)(J.slot * g.n_surf + J.j_first) * 2) * g.half_rays + ((size_t)bp * g.N + a);
+      const float4 s0 = __ldg(src);
+      alive = s0.x == s0.x;  // NaN: the ray died in the forward sweep before reaching surface j
+      if (alive) {
+        const float4 s1 = __ldg(src + g.half_rays);
+        r.ox = s0.x; r.oy = s0.y; r.oz = s0.z; r.w = s0.w;
+        r.dx = s1.x; r.dy = s1.y; r.ma = s1.z; r.mb = s1.w;
+        r.dz = fsqrt(fmaxf(fmaf(-r.dx, r.dx, fmaf(-r.dy, r.dy, 1.f)), 0.f));
+        alive = run_program<2, true, false, true>(s_prog, n_steps, M, g.lut, r, o);
+      }
+    } else {
+      alive = trace<2, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, g.cell, -g.P), fmaf((float)b + 0.5f, g.cell, -g.P),
+                                    J.f_sin_t, J.f_cos_t, o);
+    }
+    if (alive) {
+      int x0, y0, x1, y1;
+      if (o.wa > 0.f) {
+        to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
+        if (footprint(bilinear, pp.x, pp.y, g.W, g.H, x0, y0, x1, y1)) {
+          ww.x = o.wa; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+        }
+      }
+      if (o.wb > 0.f && b != bp) {
+        to_pixel(PM, o.xs, -o.ys, pp.z, pp.w);
+        if (footprint(bilinear, pp.z, pp.w, g.W, g.H, x0, y0, x1, y1)) {
+          ww.y = o.wb; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+        }
+      }
+    }
+  }
+  const bool lands = ww.x > 0.f || ww.y > 0.f;
+  const unsigned ballot = __ballot_sync(0xffffffffu, lands);
+  if (ballot) {
+    const int lane = tid & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&s_count, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lands) {
+      const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+      s_qp[slot] = pp; s_qw[slot] = ww;
+    }
+    bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+    bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+    if (lane == 0) {
+      atomicMin(&s_bbox[0], bx0); atomicMin(&s_bbox[1], by0);
+      atomicMax(&s_bbox[2], bx1); atomicMax(&s_bbox[3], by1);
+    }
+  }
+  __syncthreads();
+  const int count = s_count;
+  if (count == 0) return;
+  if (tid == 0) grow_bbox(g.bbox, s_bbox[0], s_bbox[1], s_bbox[2], s_bbox[3]);
+  SplatCtx C;
+  C.tx0 = s_bbox[0]; C.ty0 = s_bbox[1];
+  C.tw = s_bbox[2] - C.tx0 + 1;
+  const int area = C.tw * (s_bbox[3] - C.ty0 + 1);
+  const bool use_tile = area <= kTilePx;
+  C.tile = use_tile ? s_tile : nullptr;
+  C.accum = accum; C.W = g.W; C.H = g.H; C.bilinear = bilinear;
+  if (use_tile) {
+    if (tid < area) { s_tile[3 * tid] = 0ull; s_tile[3 * tid + 1] = 0ull; s_tile[3 * tid + 2] = 0ull; }
+    __syncthreads();
+  }
+  C.ch0 = J.f_chan[0]; C.ch1 = J.f_chan[1]; C.ch2 = J.f_chan[2];
+  if (tid < count) {
+    const float4 qp = s_qp[tid];
+    const float2 qw = s_qw[tid];
+    if (qw.x > 0.f) splat1(C, qp.x, qp.y, qw.x);
+    if (qw.y > 0.f) splat1(C, qp.z, qp.w, qw.y);
+  }
+  if (!use_tile) return;
+  __syncthreads();
+  if (tid < area) {
+    const int jy = (int)(((float)tid + 0.5f) * frcp((float)C.tw));
     const int jx = tid - jy * C.tw;
     unsigned long long* dst = accum + 3 * ((size_t)(C.tx0 + jx) + (size_t)(C.ty0 + jy) * g.W);
 #pragma unroll

@@ -19,6 +19,13 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
   auto blocks = [&](int rx, int ry) {  // patches tile the upper half of the grid (mirror symmetry, exact_f32.cuh)
     return (unsigned)n_jobs * (unsigned)(((g.N + 16 * rx - 1) / (16 * rx)) * (((g.N + 1) / 2 + 16 * ry - 1) / (16 * ry)));
   };
+  if (g.prefix) {  // v5: ray states come from the prefix cache (launch_prefix_f32 ran first); 16x16 ray pairs per CTA
+    const unsigned nb = blocks(1, 1);
+    if (g.pad >= 6) xf32::exact_splat2_kernel<6><<<nb, xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
+    else if (g.pad == 5) xf32::exact_splat2_kernel<5><<<nb, xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
+    else xf32::exact_splat2_kernel<4><<<nb, xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
+    return cudaGetLastError();
+  }
   // patch shape (rays per thread in pass 1) x resident CTAs per SM the register allocation targets
   const int minb = g.pad;  // 0 (default) -> 4
   // g.lut set: the one-pass kernel with tabulated reflectances (v4); else the two-pass closed-form kernel (v3)
@@ -38,6 +45,14 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
   else LFB_PATCH(4);
 #undef LFB_PATCH
 #undef LFB_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prefix_f32(const Job* slots, const Step* progs, int n_slots, const FrameGeom& g, const float* tex, float4* prefix,
+                              cudaStream_t s) {
+  if (n_slots <= 0) return cudaSuccess;
+  const unsigned nb = (unsigned)n_slots * (unsigned)(((g.N + 15) / 16) * (((g.N + 1) / 2 + 15) / 16));
+  xf32::prefix_kernel<<<nb, xf32::kThreads, 0, s>>>(slots, progs, g, tex, prefix);
   return cudaGetLastError();
 }
 

@@ -28,7 +28,9 @@ struct DevLens {
 // paraxial matrices, which the device set-up kernel writes (paraxial_setup_kernel).
 struct Job {
   int light, i, j, lambda;  // i = j = -1: direct path
-  int n_cross, n_steps, pad1, pad2;  // n_steps: length of the job's FP32 step program
+  int n_cross, n_steps;     // n_steps: length of the job's FP32 step program
+  int slot, j_first;        // FP32 prefix path: (light, lambda) slot of the cached forward sweep and the surface of the first
+                            // reflection the job's program starts ON (slot < 0: the program starts at the entrance)
   float theta;
   float pad3;
   double chan[3];           // radiance * rgb_weight * ray area * px_per_unit^2
@@ -49,6 +51,8 @@ struct FrameGeom {
   float P, h_stop;  // entrance half height, stop half height
   float cell;       // 2P / N
   float mask_su, mask_sv, mask_ou, mask_ov;  // aperture texel of a stop-plane point: u = x*su + ou, v = y*sv + ov
+  const float4* prefix;  // cached forward sweeps: [slot][surface][part 0|1][ray of the half grid], see exact_f32.cuh
+  int half_rays, n_surf;
   const float2* lut;  // reflectance tables R(sin^2 theta0), one per (wavelength, surface, direction): (R_i, R_{i+1} - R_i)
   int* bbox;        // device int[4] = {min_x, min_y, max_x, max_y} of every pixel the frame deposits into (or nullptr)
   int patch, pad;   // FP32 EXACT_GRID tuning: rays per thread in pass 1 (1, 2 or 4); resident CTAs/SM target (0 -> 4)
@@ -96,6 +100,9 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
                                    const float* tex, unsigned long long* accum, cudaStream_t s);
 cudaError_t launch_trace_splat_f64(const Job* jobs, int n_jobs, const FrameGeom& g, int mode, const float* tex,
                                    unsigned long long* accum, cudaStream_t s);
+// FP32 EXACT_GRID prefix pass: trace the forward sweep of every (light, lambda) slot once and cache the ray states
+cudaError_t launch_prefix_f32(const Job* slots, const Step* progs, int n_slots, const FrameGeom& g, const float* tex, float4* prefix,
+                              cudaStream_t s);
 cudaError_t launch_trace_dump_f32(const Job* job, const Step* prog, const FrameGeom& g, int mode, const float* tex,
                                   lfb_ray_hit* out, cudaStream_t s);
 cudaError_t launch_trace_dump_f64(const Job* job, const FrameGeom& g, int mode, const float* tex, lfb_ray_hit* out,

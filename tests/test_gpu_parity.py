@@ -321,6 +321,35 @@ def test_exact_fp32_patch_variants_agree(engine, apertures, monkeypatch):
         assert np.array_equal(frames[("1", splat)], frames[("4", splat)])
 
 
+def test_exact_fp32_kernel_generations_agree(engine, port, apertures, monkeypatch):
+    """The throughput kernel's variants -- v5 (prefix cache + tabulated reflectances, the default), v4 (no prefix cache,
+    LFB_EXACT_PREFIX=0) and v3 (closed-form Fresnel, two passes, LFB_EXACT_WEIGHTS=closed) -- render the same frame: each
+    within 1e-3 of the double oracle, v5 vs v4 within 1e-6 (same arithmetic, different kernels), multi-light and ragged N."""
+    lens = capi.builtin_lens(3, 550.0)
+    lt = [capi.make_light(0.45, 0.55, theta=capi.physical_theta(0.45, 0.55)), capi.make_light(0.75, 0.3, theta=0.09, radiance=(2.0, 1.0, 0.5))]
+    p = capi.make_params(capi.MODE_EXACT_GRID, 800, 450, grid_n=90, pair_set=capi.PAIRS_ALL, include_direct=1)
+    want = port.render(lens, apertures["pentbig500_14"], lt, p)
+    frames = {}
+    for name, env in (("v5", {}), ("v4", {"LFB_EXACT_PREFIX": "0"}), ("v3", {"LFB_EXACT_WEIGHTS": "closed"})):
+        for k in ("LFB_EXACT_PREFIX", "LFB_EXACT_WEIGHTS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = capi.Engine(0)
+        try:
+            e.set_lens(lens)
+            e.set_aperture(apertures["pentbig500_14"])
+            frames[name] = e.render_ghosts(lt, p)
+            # sharded frames through the same variant sum to the whole frame exactly
+            parts = sum(e.render_ghosts(lt, capi.copy_params(p, shard=(r, 3))) for r in range(3))
+            assert np.array_equal(parts, frames[name]), name
+        finally:
+            e.close()
+        assert rel_l2(frames[name], want) <= 1e-3, name
+    assert rel_l2(frames["v5"], frames["v4"]) <= 1e-6
+    assert rel_l2(frames["v4"], frames["v3"]) <= 1e-3
+
+
 def test_large_footprint_falls_back_to_global_atomics(engine, port, apertures):
     """px_per_unit large enough that a CTA's ray patch covers more pixels than the shared-memory tile holds."""
     lens = capi.builtin_lens(3)
