@@ -380,6 +380,8 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
   if (key == e->job_key) return LFB_OK;
   std::vector<JobId> ids;
   list_jobs(e->lens, P, n_lights, ids);
+  // launch order = list order.  (Measured on cfg2: sorting the ghosts longest-first, or interleaving long and short
+  // ones, is 20 % SLOWER than the reference order; the sensor sums are integers, so the order never changes the result.)
   const int n = (int)ids.size();
   if (n > e->jobs_cap) {
     if (e->d_jobs) CU(cudaFree(e->d_jobs));

@@ -618,22 +618,24 @@ __global__ void __launch_bounds__(kThreads) prefix_kernel(const Job* __restrict_
 
 // The ghost kernel of v5: exact_splat1_kernel with the ray states loaded from the prefix cache (jobs whose slot is >= 0);
 // jobs without a slot (the direct path) trace from the entrance as before.
-template <int MINB>
+template <int RX, int RY, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) exact_splat2_kernel(const Job* __restrict__ jobs, const Step* __restrict__ progs,
                                                                       FrameGeom g, const float* __restrict__ tex,
                                                                       unsigned long long* __restrict__ accum) {
+  constexpr int RPT = RX * RY, PATCH = RPT * kThreads, PW = 16 * RX, PH = 16 * RY;
   static_assert(kTilePx <= kThreads, "one thread per tile pixel in the zero / flush loops");
   __shared__ Step s_prog[LFB_MAX_STEPS];
   __shared__ unsigned long long s_tile[kTilePx * 3];
-  __shared__ float4 s_qp[kThreads];
-  __shared__ float2 s_qw[kThreads];
+  __shared__ float4 s_qp[PATCH];
+  __shared__ float2 s_qw[PATCH];
   __shared__ int s_count, s_bbox[4];
 
   const int half_rows = (g.N + 1) / 2;
-  const int patches_x = (g.N + 15) / 16;
-  const int patches_per_job = patches_x * ((half_rows + 15) / 16);
+  const int patches_x = (g.N + PW - 1) / PW;
+  const int patches_per_job = patches_x * ((half_rows + PH - 1) / PH);
   const int job_id = blockIdx.x / patches_per_job;
   const int patch = blockIdx.x - job_id * patches_per_job;
+  const int a0 = (patch % patches_x) * PW, b0 = (patch / patches_x) * PH;
   const Job& J = jobs[job_id];
   const int n_steps = J.n_steps;
   const int tid = threadIdx.x;
@@ -651,61 +653,68 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat2_kernel(const Job*
   PixMap PM;
   PM.sx = J.f_sx; PM.sy = J.f_sy; PM.cs = J.f_cs; PM.sn = J.f_sn; PM.ppu = J.f_ppu;
   const bool bilinear = g.splat == LFB_SPLAT_BILINEAR;
+  const int slot = J.slot;
+  const float4* pre = slot >= 0 ? g.prefix + ((size_t)(slot * g.n_surf + J.j_first) * 2) * g.half_rays : nullptr;
 
   int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
-  const int a = (patch % patches_x) * 16 + (tid & 15), bp = (patch / patches_x) * 16 + (tid >> 4);
-  const int b = g.N - 1 - bp;
-  float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
-  float2 ww = make_float2(0.f, 0.f);
-  if (a < g.N && bp < half_rows) {
-    RayState r;
-    RayOut o;
-    bool alive;
-    if (J.slot >= 0) {
-      const float4* src = g.prefix + ((size_t)(J.slot * g.n_surf + J.j_first) * 2) * g.half_rays + ((size_t)bp * g.N + a);
-      const float4 s0 = __ldg(src);
-      alive = s0.x == s0.x;  // NaN: the ray died in the forward sweep before reaching surface j
+#pragma unroll 1
+  for (int rr = 0; rr < RPT; rr++) {
+    const int a = a0 + (tid & 15) + 16 * (rr % RX), bp = b0 + (tid >> 4) + 16 * (rr / RX);
+    const int b = g.N - 1 - bp;
+    float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 ww = make_float2(0.f, 0.f);
+    if (a < g.N && bp < half_rows) {
+      RayState r;
+      RayOut o;
+      bool alive;
+      if (pre) {
+        const float4* src = pre + ((size_t)bp * g.N + a);
+        const float4 s0 = __ldg(src);
+        alive = s0.x == s0.x;  // NaN: the ray died in the forward sweep before reaching surface j
+        if (alive) {
+          const float4 s1 = __ldg(src + g.half_rays);
+          r.ox = s0.x; r.oy = s0.y; r.oz = s0.z; r.w = s0.w;
+          r.dx = s1.x; r.dy = s1.y; r.ma = s1.z; r.mb = s1.w;
+          r.dz = fsqrt(fmaxf(fmaf(-r.dx, r.dx, fmaf(-r.dy, r.dy, 1.f)), 0.f));
+          alive = run_program<2, true, false, true>(s_prog, n_steps, M, g.lut, r, o);
+        }
+      } else {
+        alive = trace<2, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, g.cell, -g.P), fmaf((float)b + 0.5f, g.cell, -g.P),
+                                      J.f_sin_t, J.f_cos_t, o);
+      }
       if (alive) {
-        const float4 s1 = __ldg(src + g.half_rays);
-        r.ox = s0.x; r.oy = s0.y; r.oz = s0.z; r.w = s0.w;
-        r.dx = s1.x; r.dy = s1.y; r.ma = s1.z; r.mb = s1.w;
-        r.dz = fsqrt(fmaxf(fmaf(-r.dx, r.dx, fmaf(-r.dy, r.dy, 1.f)), 0.f));
-        alive = run_program<2, true, false, true>(s_prog, n_steps, M, g.lut, r, o);
+        int x0, y0, x1, y1;
+        if (o.wa > 0.f) {
+          to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
+          if (footprint(bilinear, pp.x, pp.y, g.W, g.H, x0, y0, x1, y1)) {
+            ww.x = o.wa; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+          }
+        }
+        if (o.wb > 0.f && b != bp) {
+          to_pixel(PM, o.xs, -o.ys, pp.z, pp.w);
+          if (footprint(bilinear, pp.z, pp.w, g.W, g.H, x0, y0, x1, y1)) {
+            ww.y = o.wb; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+          }
+        }
       }
-    } else {
-      alive = trace<2, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, g.cell, -g.P), fmaf((float)b + 0.5f, g.cell, -g.P),
-                                    J.f_sin_t, J.f_cos_t, o);
     }
-    if (alive) {
-      int x0, y0, x1, y1;
-      if (o.wa > 0.f) {
-        to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
-        if (footprint(bilinear, pp.x, pp.y, g.W, g.H, x0, y0, x1, y1)) {
-          ww.x = o.wa; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
-        }
-      }
-      if (o.wb > 0.f && b != bp) {
-        to_pixel(PM, o.xs, -o.ys, pp.z, pp.w);
-        if (footprint(bilinear, pp.z, pp.w, g.W, g.H, x0, y0, x1, y1)) {
-          ww.y = o.wb; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
-        }
+    const bool lands = ww.x > 0.f || ww.y > 0.f;
+    const unsigned ballot = __ballot_sync(0xffffffffu, lands);
+    if (ballot) {
+      const int lane = tid & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_count, __popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (lands) {
+        const int q = base + __popc(ballot & ((1u << lane) - 1u));
+        s_qp[q] = pp; s_qw[q] = ww;
       }
     }
   }
-  const bool lands = ww.x > 0.f || ww.y > 0.f;
-  const unsigned ballot = __ballot_sync(0xffffffffu, lands);
-  if (ballot) {
-    const int lane = tid & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&s_count, __popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (lands) {
-      const int slot = base + __popc(ballot & ((1u << lane) - 1u));
-      s_qp[slot] = pp; s_qw[slot] = ww;
-    }
+  if (__any_sync(0xffffffffu, bx1 >= bx0)) {
     bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
     bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
-    if (lane == 0) {
+    if ((tid & 31) == 0) {
       atomicMin(&s_bbox[0], bx0); atomicMin(&s_bbox[1], by0);
       atomicMax(&s_bbox[2], bx1); atomicMax(&s_bbox[3], by1);
     }
@@ -726,9 +735,9 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat2_kernel(const Job*
     __syncthreads();
   }
   C.ch0 = J.f_chan[0]; C.ch1 = J.f_chan[1]; C.ch2 = J.f_chan[2];
-  if (tid < count) {
-    const float4 qp = s_qp[tid];
-    const float2 qw = s_qw[tid];
+  for (int q = tid; q < count; q += kThreads) {
+    const float4 qp = s_qp[q];
+    const float2 qw = s_qw[q];
     if (qw.x > 0.f) splat1(C, qp.x, qp.y, qw.x);
     if (qw.y > 0.f) splat1(C, qp.z, qp.w, qw.y);
   }

@@ -19,11 +19,19 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
   auto blocks = [&](int rx, int ry) {  // patches tile the upper half of the grid (mirror symmetry, exact_f32.cuh)
     return (unsigned)n_jobs * (unsigned)(((g.N + 16 * rx - 1) / (16 * rx)) * (((g.N + 1) / 2 + 16 * ry - 1) / (16 * ry)));
   };
-  if (g.prefix) {  // v5: ray states come from the prefix cache (launch_prefix_f32 ran first); 16x16 ray pairs per CTA
-    const unsigned nb = blocks(1, 1);
-    if (g.pad >= 6) xf32::exact_splat2_kernel<6><<<nb, xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
-    else if (g.pad == 5) xf32::exact_splat2_kernel<5><<<nb, xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
-    else xf32::exact_splat2_kernel<4><<<nb, xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum);
+  if (g.prefix) {  // v5: ray states come from the prefix cache (launch_prefix_f32 ran first)
+#define LFB_LAUNCH2(RX, RY, MB) xf32::exact_splat2_kernel<RX, RY, MB><<<blocks(RX, RY), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum)
+#define LFB_PATCH2(MB)                        \
+  do {                                        \
+    if (g.patch >= 4) LFB_LAUNCH2(2, 2, MB);  \
+    else if (g.patch >= 2) LFB_LAUNCH2(2, 1, MB); \
+    else LFB_LAUNCH2(1, 1, MB);               \
+  } while (0)
+    if (g.pad >= 6) LFB_PATCH2(6);
+    else if (g.pad == 5) LFB_PATCH2(5);
+    else LFB_PATCH2(4);
+#undef LFB_PATCH2
+#undef LFB_LAUNCH2
     return cudaGetLastError();
   }
   // patch shape (rays per thread in pass 1) x resident CTAs per SM the register allocation targets
