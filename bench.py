@@ -124,6 +124,16 @@ def reference_trace_step(ref, theta, threads):
     return s, rays
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline_block(sample_steps=1):
     """The CPU numbers reported beside the GPU line (rank 0, N = 1)."""
     from lens_flare_b200 import capi
@@ -145,7 +155,8 @@ def cpu_baseline_block(sample_steps=1):
         tex = load_aperture()
         s1, _ = ref.time_ghost_buffer(tex, WIDTH, HEIGHT, 0.45, 0.55, capi.make_light(0.45, 0.55).theta, 5)
         out["reference_frame_ms_1thread"] = s1 * 1e3  # PathTracer::generate_ghost_buffer, 1080p (13 quads x RGB)
-    if os.path.exists(ob.PORT_SO) or not out:
+    out["cpu_model"] = cpu_model()
+    if os.path.exists(ob.PORT_SO) or not out.get("kind"):
         if not os.path.exists(ob.PORT_SO):
             ob.build(("port",))
         port = ob.PortOracle()
@@ -154,10 +165,10 @@ def cpu_baseline_block(sample_steps=1):
         exact = dict(value=inter_frame / s, unit="interactions/s", cores=threads, kind="port",
                      sample=f"oracle/lf_oracle.c EXACT_GRID, one full cfg2 frame ({inter_frame:.3g} interactions), {threads} pthreads",
                      seconds=s, frame_ms=s * 1e3)
-        if out:
+        if out.get("kind"):
             out["port_exact"] = exact
         else:
-            out = exact
+            out.update(exact)
     return out
 
 
@@ -198,7 +209,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD + " [reference arm: the reference's paraxial ABCD tracer on the same grid; it has no "
                                           "exact physics and no direct path]"},
-        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": threads, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": threads, "kind": kind, "sample": sample, "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -375,8 +386,8 @@ def run_ours(args):
         ach = inter_rank * FLOP_PER_INTERACTION / (k_ms * 1e-3)
         mufu_ach = inter_rank * MUFU_PER_INTERACTION / (k_ms * 1e-3)
         roofline = {
-            "bound": "fp32", "kernel": "xf32::exact_splat_kernel", "achieved": ach / 1e12, "peak": peaks["fp32_flops"] / 1e12,
-            "unit": "TFLOP/s", "frac": ach / peaks["fp32_flops"], "traffic": 1.89e6, "traffic_source": "ncu --set full, profiles/r1_exact_splat_v3_ncu_details.txt: dram read 1.89 MB + written 0 B per launch (the atomics stay in L2)",
+            "bound": "fp32", "kernel": "xf32::exact_splat2_kernel (+ xf32::prefix_kernel)", "achieved": ach / 1e12, "peak": peaks["fp32_flops"] / 1e12,
+            "unit": "TFLOP/s", "frac": ach / peaks["fp32_flops"], "traffic": 1.97e7, "traffic_source": "ncu --set full, profiles/r1_exact_splat_v5_ncu_details.txt: DRAM read 19.7 MB (prefix-cache lines that fell out of L2) + written 0 B per launch; the kernel has no algorithmic HBM stream",
             "kernel_ms": k_ms, "interactions_per_launch": inter_rank, "flop_per_interaction": FLOP_PER_INTERACTION,
             "peak_source": "measured live on this GPU by lfb_probe_peaks (register-only FFMA chains); MEASURED_PEAKS.json holds no "
                            "FP32 figure. The trace is scalar FP32/MUFU math: neither 'hbm' nor 'tensor' bounds it",
