@@ -352,8 +352,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
     e2e_value = inter_frame * args.steps / e2e_s
-    job_bytes = 248 + 50 * 48  # sizeof(lfb::Job) + LFB_MAX_STEPS * sizeof(lfb::Step): re-uploaded when the lights change
-    h2d = tex.nbytes * world + jobs_frame * job_bytes
+    job_bytes = 296 + 50 * 48  # sizeof(lfb::Job) + LFB_MAX_STEPS * sizeof(lfb::Step): re-uploaded when the lights change
+    h2d = tex.nbytes * world + (jobs_frame + 3 * n_lights) * job_bytes  # ghost jobs + one prefix slot per (light, lambda)
     d2h = HEIGHT * WIDTH * 24
 
     # ---- the displayable frame (N = 1): ghosts -> toColor -> RGBA8 on the device, 4 B/pixel back over PCIe -----------
