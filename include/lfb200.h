@@ -228,6 +228,10 @@ int lfb_sync(lfb_engine* e);
  * the pixels [rank*npx/n, (rank+1)*npx/n) and stores them into out_dev, the OWNER rank's output buffer as mapped here.
  * The caller orders this call after every rank's lfb_render_ghosts_device (a device-side barrier on lfb_stream) and reads
  * the owner's buffer after another one.  Integer sums: the frame has the same bits for any rank count. */
+/* Device-side barrier across the ranks of one node, enqueued on lfb_stream: flag_ptrs[r] is rank r's flag array
+ * (LFB_MAX_PEERS zero-initialised u64, symmetric / IPC memory) as mapped in this process; epoch must increase by one per
+ * barrier.  Work enqueued before it on every rank is complete and visible to work enqueued after it on any rank. */
+int lfb_peer_barrier(lfb_engine* e, void* const* flag_ptrs, int n_ranks, int rank, uint64_t epoch);
 int lfb_reduce_finalize_peers(lfb_engine* e, const void* const* accum_ptrs, int n_ranks, int rank,
                               const void* multicast_accum, const lfb_params* params, void* out_dev,
                               size_t out_stride_bytes, int out_elem);

@@ -32,7 +32,7 @@ RAY_MISSED, RAY_VIGNETTED, RAY_TIR, RAY_STOPPED, RAY_OFF_SENSOR = 1, 2, 4, 8, 16
 SYMBOLS = (
     "lfb_abi_version", "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
     "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
-    "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_reduce_finalize_peers", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
+    "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_reduce_finalize_peers", "lfb_peer_barrier", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
     "lfb_host_alloc", "lfb_host_free", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
 )
 
@@ -166,6 +166,7 @@ def lib():
     L.lfb_render_ghosts_device.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_int]
     L.lfb_finalize_device.argtypes = [vp, vp, PP, vp, C.c_size_t, C.c_int]
     L.lfb_sync.argtypes = [vp]
+    L.lfb_peer_barrier.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_uint64]
     L.lfb_reduce_finalize_peers.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, vp, PP, vp, C.c_size_t, C.c_int]
     L.lfb_count_work.argtypes = [LP, PP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.lfb_list_jobs.argtypes = [LP, PP, C.c_int, C.POINTER(C.c_int32), C.c_int]
@@ -318,6 +319,10 @@ class Engine:
 
     def finalize_device(self, accum_ptr, params, out_ptr, stride, elem):
         check(lib().lfb_finalize_device(self._h, accum_ptr, C.byref(params), out_ptr, stride, elem))
+
+    def peer_barrier(self, flag_ptrs, rank, epoch):
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        check(lib().lfb_peer_barrier(self._h, arr, len(flag_ptrs), rank, epoch))
 
     def reduce_finalize_peers(self, accum_ptrs, rank, params, out_ptr, stride, elem, multicast_ptr=None):
         arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)

@@ -472,8 +472,13 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
   rc = prepare_jobs(e, lights, n_lights, P);
   if (rc) return rc;
   FrameGeom g = make_geom(e, P);
+  // inside a CUDA-graph capture (a host may capture whole frames and replay them) the timing events are not recorded:
+  // they could not be read back anyway
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CU(cudaStreamIsCapturing(e->stream, &cap));
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
   if (clear_first) CU(cudaMemsetAsync(accum, 0, lfb_accum_bytes(P.width, P.height), e->stream));
-  CU(cudaEventRecord(e->ev_trace0, e->stream));
+  if (!capturing) CU(cudaEventRecord(e->ev_trace0, e->stream));
   if (e->n_jobs > 0 && e->frame_has_prefix && g.lut) {
     CU(launch_prefix_f32(e->d_slots, e->d_slot_progs, e->n_slots, g, e->d_tex, e->d_prefix, e->stream));
     e->launches++;
@@ -484,8 +489,10 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
     else CU(launch_trace_splat_f32(e->d_jobs, e->d_progs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
     e->launches++;
   }
-  CU(cudaEventRecord(e->ev_trace1, e->stream));
-  e->timed = true;
+  if (!capturing) {
+    CU(cudaEventRecord(e->ev_trace1, e->stream));
+    e->timed = true;
+  }
   return LFB_OK;
 }
 
@@ -796,6 +803,21 @@ extern "C" int lfb_finalize_device(lfb_engine* e, const void* accum_dev, const l
   if (out_stride_bytes < elem_bytes(out_elem) || out_stride_bytes % (out_elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
   const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
   CU(launch_finalize((const unsigned long long*)accum_dev, P->width, P->height, inv, out_dev, out_stride_bytes, out_elem, 0, e->stream));
+  e->launches++;
+  return LFB_OK;
+}
+
+extern "C" int lfb_peer_barrier(lfb_engine* e, void* const* flag_ptrs, int n_ranks, int rank, uint64_t epoch) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!flag_ptrs || n_ranks < 1 || n_ranks > LFB_MAX_PEERS || rank < 0 || rank >= n_ranks) return fail(LFB_ERR_INVALID, "bad peer set");
+  PeerFlags F;
+  F.n = n_ranks; F.rank_self = rank;
+  for (int r = 0; r < n_ranks; r++) {
+    if (!flag_ptrs[r]) return fail(LFB_ERR_INVALID, "NULL flag array");
+    F.ptr[r] = (unsigned long long*)flag_ptrs[r];
+  }
+  CU(launch_peer_barrier(F, rank, (unsigned long long)epoch, e->stream));
   e->launches++;
   return LFB_OK;
 }

@@ -618,12 +618,11 @@ __global__ void __launch_bounds__(kThreads) prefix_kernel(const Job* __restrict_
 
 // The ghost kernel of v5: exact_splat1_kernel with the ray states loaded from the prefix cache (jobs whose slot is >= 0);
 // jobs without a slot (the direct path) trace from the entrance as before.
-template <int RX, int RY, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) exact_splat2_kernel(const Job* __restrict__ jobs, const Step* __restrict__ progs,
+template <int RX, int RY, int MINB, int BT>
+__global__ void __launch_bounds__(BT, MINB) exact_splat2_kernel(const Job* __restrict__ jobs, const Step* __restrict__ progs,
                                                                       FrameGeom g, const float* __restrict__ tex,
                                                                       unsigned long long* __restrict__ accum) {
-  constexpr int RPT = RX * RY, PATCH = RPT * kThreads, PW = 16 * RX, PH = 16 * RY;
-  static_assert(kTilePx <= kThreads, "one thread per tile pixel in the zero / flush loops");
+  constexpr int RPT = RX * RY, PATCH = RPT * BT, PW = 16 * RX, PH = (BT / 16) * RY;  // BT threads = 16 x BT/16 rays per round
   __shared__ Step s_prog[LFB_MAX_STEPS];
   __shared__ unsigned long long s_tile[kTilePx * 3];
   __shared__ float4 s_qp[PATCH];
@@ -642,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat2_kernel(const Job*
   {
     const float4* src = reinterpret_cast<const float4*>(progs + (size_t)job_id * LFB_MAX_STEPS);
     float4* dst = reinterpret_cast<float4*>(s_prog);
-    for (int q = tid; q < n_steps * 3; q += kThreads) dst[q] = __ldg(src + q);
+    for (int q = tid; q < n_steps * 3; q += BT) dst[q] = __ldg(src + q);
     if (tid == 0) { s_count = 0; s_bbox[0] = s_bbox[1] = 0x7fffffff; s_bbox[2] = s_bbox[3] = -0x7fffffff; }
   }
   __syncthreads();
@@ -659,7 +658,7 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat2_kernel(const Job*
   int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
 #pragma unroll 1
   for (int rr = 0; rr < RPT; rr++) {
-    const int a = a0 + (tid & 15) + 16 * (rr % RX), bp = b0 + (tid >> 4) + 16 * (rr / RX);
+    const int a = a0 + (tid & 15) + 16 * (rr % RX), bp = b0 + (tid >> 4) + (BT / 16) * (rr / RX);
     const int b = g.N - 1 - bp;
     float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
     float2 ww = make_float2(0.f, 0.f);
@@ -731,11 +730,11 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat2_kernel(const Job*
   C.tile = use_tile ? s_tile : nullptr;
   C.accum = accum; C.W = g.W; C.H = g.H; C.bilinear = bilinear;
   if (use_tile) {
-    if (tid < area) { s_tile[3 * tid] = 0ull; s_tile[3 * tid + 1] = 0ull; s_tile[3 * tid + 2] = 0ull; }
+    for (int q = tid; q < 3 * area; q += BT) s_tile[q] = 0ull;
     __syncthreads();
   }
   C.ch0 = J.f_chan[0]; C.ch1 = J.f_chan[1]; C.ch2 = J.f_chan[2];
-  for (int q = tid; q < count; q += kThreads) {
+  for (int q = tid; q < count; q += BT) {
     const float4 qp = s_qp[q];
     const float2 qw = s_qw[q];
     if (qw.x > 0.f) splat1(C, qp.x, qp.y, qw.x);
@@ -743,13 +742,14 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat2_kernel(const Job*
   }
   if (!use_tile) return;
   __syncthreads();
-  if (tid < area) {
-    const int jy = (int)(((float)tid + 0.5f) * frcp((float)C.tw));
-    const int jx = tid - jy * C.tw;
+  const float inv_tw = frcp((float)C.tw);
+  for (int t = tid; t < area; t += BT) {
+    const int jy = (int)(((float)t + 0.5f) * inv_tw);  // t / tw, exact for these small integers
+    const int jx = t - jy * C.tw;
     unsigned long long* dst = accum + 3 * ((size_t)(C.tx0 + jx) + (size_t)(C.ty0 + jy) * g.W);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      const unsigned long long v = s_tile[3 * tid + c];
+      const unsigned long long v = s_tile[3 * t + c];
       if (v) atomicAdd(dst + c, v);
     }
   }

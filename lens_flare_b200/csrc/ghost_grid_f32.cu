@@ -5,6 +5,7 @@
 #define LFB_TU f32
 #include "ghost_grid_impl.cuh"
 #include "exact_f32.cuh"
+#include <stdlib.h>
 
 namespace lfb {
 
@@ -20,16 +21,29 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
     return (unsigned)n_jobs * (unsigned)(((g.N + 16 * rx - 1) / (16 * rx)) * (((g.N + 1) / 2 + 16 * ry - 1) / (16 * ry)));
   };
   if (g.prefix) {  // v5: ray states come from the prefix cache (launch_prefix_f32 ran first)
-#define LFB_LAUNCH2(RX, RY, MB) xf32::exact_splat2_kernel<RX, RY, MB><<<blocks(RX, RY), xf32::kThreads, 0, s>>>(jobs, progs, g, tex, accum)
-#define LFB_PATCH2(MB)                        \
-  do {                                        \
-    if (g.patch >= 4) LFB_LAUNCH2(2, 2, MB);  \
-    else if (g.patch >= 2) LFB_LAUNCH2(2, 1, MB); \
-    else LFB_LAUNCH2(1, 1, MB);               \
+    // block size 64 / 128 / 256 (16 x 4 / 8 / 16 ray pairs per round); LFB_EXACT_BLOCK selects, default 128 (measured best)
+    static int bt = 0;
+    if (!bt) { const char* env = getenv("LFB_EXACT_BLOCK"); bt = env ? atoi(env) : 128; if (bt != 64 && bt != 256) bt = 128; }
+    auto blocks2 = [&](int rx, int ry, int rows) {
+      return (unsigned)n_jobs * (unsigned)(((g.N + 16 * rx - 1) / (16 * rx)) * (((g.N + 1) / 2 + rows * ry - 1) / (rows * ry)));
+    };
+#define LFB_LAUNCH2(RX, RY, MB, BT) xf32::exact_splat2_kernel<RX, RY, MB, BT><<<blocks2(RX, RY, BT / 16), BT, 0, s>>>(jobs, progs, g, tex, accum)
+#define LFB_PATCH2(MB, BT)                        \
+  do {                                            \
+    if (g.patch >= 4) LFB_LAUNCH2(2, 2, MB, BT);  \
+    else if (g.patch >= 2) LFB_LAUNCH2(2, 1, MB, BT); \
+    else LFB_LAUNCH2(1, 1, MB, BT);               \
   } while (0)
-    if (g.pad >= 6) LFB_PATCH2(6);
-    else if (g.pad == 5) LFB_PATCH2(5);
-    else LFB_PATCH2(4);
+    if (bt == 64) {
+      LFB_PATCH2(24, 64);
+    } else if (bt == 128) {
+      if (g.pad >= 6) LFB_PATCH2(12, 128);
+      else LFB_PATCH2(8, 128);
+    } else {
+      if (g.pad >= 6) LFB_PATCH2(6, 256);
+      else if (g.pad == 5) LFB_PATCH2(5, 256);
+      else LFB_PATCH2(4, 256);
+    }
 #undef LFB_PATCH2
 #undef LFB_LAUNCH2
     return cudaGetLastError();

@@ -132,6 +132,28 @@ __device__ __forceinline__ unsigned long long multimem_add_u64(const unsigned lo
   return v;
 }
 
+// Device-side barrier across the ranks of one node, for stream-ordered use: rank r publishes `epoch` into slot r of every
+// peer's flag array (system-scope release stores over NVLink) and then waits until all slots of ITS OWN array reached the
+// epoch.  Everything a rank enqueued before the barrier (its trace kernel's sums) is complete and visible to the peers'
+// kernels enqueued after it.  One warp; ranks run on different GPUs, so the spin cannot starve the peers it waits for.
+__global__ void peer_barrier_kernel(PeerFlags F, int rank, unsigned long long epoch) {
+  const int r = threadIdx.x;
+  if (r < F.n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(F.ptr[r] + rank), "l"(epoch) : "memory");
+    unsigned long long seen = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(F.ptr[F.rank_self] + r) : "memory");
+    } while (seen < epoch);
+  }
+  __syncwarp();
+}
+
+cudaError_t launch_peer_barrier(const PeerFlags& F, int rank, unsigned long long epoch, cudaStream_t s) {
+  peer_barrier_kernel<<<1, 32, 0, s>>>(F, rank, epoch);
+  return cudaGetLastError();
+}
+
 // The accumulators are treated as a flat u64 array: each thread owns 4 consecutive values (two 16-byte loads per rank,
 // all issued before any is used, so a warp keeps 32 x 32 B x n_ranks in flight across NVLink).
 __device__ __forceinline__ void store_value(char* out, size_t e, double v, size_t stride, int elem, bool packed) {

@@ -113,6 +113,11 @@ struct PeerAccums {  // the ranks' sensor accumulators as mapped in THIS process
   const unsigned long long* ptr[LFB_MAX_PEERS];
   int n;
 };
+struct PeerFlags {  // every rank's barrier flag array (LFB_MAX_PEERS u64 each) as mapped in THIS process
+  unsigned long long* ptr[LFB_MAX_PEERS];
+  int n, rank_self;
+};
+cudaError_t launch_peer_barrier(const PeerFlags& F, int rank, unsigned long long epoch, cudaStream_t s);
 cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long* mc, size_t p0, size_t p1, double inv_scale,
                                    void* out, size_t stride, int elem, cudaStream_t s);
 // rect = {x0, y0, x1, y1} inclusive; out is PACKED: pixel (x, y) at ((y - y0) * (x1 - x0 + 1) + (x - x0)) * stride

@@ -59,6 +59,13 @@ class ShardedFlare:
         self.traced = [torch.cuda.Event() for _ in range(n_buffers)]
         self.reduced = [torch.cuda.Event() for _ in range(n_buffers)]
         self.finalized = [None] * n_buffers
+        self.dirty = [False] * n_buffers  # buffers whose sums were kept: cleared by the next trace into them
+        self.k = 0
+
+    def reset(self):
+        """Forget the cross-frame dependencies (call with all streams idle, e.g. before capturing frames into a CUDA graph:
+        a capture may not wait on events recorded outside it)."""
+        self.finalized = [None] * len(self.accums)
         self.k = 0
 
     def begin(self, stream=None):
@@ -76,16 +83,20 @@ class ShardedFlare:
         if self.C is not None:
             cur.wait_stream(self.C)
 
-    def frame(self, lights, out=None, elem=capi.F32x3, reduce_dst=0):
+    def frame(self, lights, out=None, elem=capi.F32x3, reduce_dst=0, keep=False):
         """Enqueue one frame: trace this shard, reduce (to `reduce_dst`, or all-reduce when None), and -- on the rank(s)
-        holding the sum, when `out` (an (H, W, 3) device tensor) is given -- convert to pixels.  Returns the buffer index."""
+        holding the sum, when `out` (an (H, W, 3) device tensor) is given -- convert to pixels.  Returns the buffer index.
+        keep=True leaves the summed accumulators in the buffer (it is then cleared at its next use instead of right away)."""
         b = self.k % len(self.accums)
         self.k += 1
         acc = self.accums[b]
         self.accum = acc
         if self.finalized[b] is not None:
-            self.A.wait_event(self.finalized[b])  # the buffer's previous frame has been read out
-        self.engine.render_ghosts_device(lights, self.params, acc.data_ptr(), clear_first=True)
+            self.A.wait_event(self.finalized[b])  # the buffer's previous frame has been read out (and the buffer re-zeroed)
+        # the accumulators are zero here: freshly allocated, or cleared on stream B right after they were read out, which
+        # takes the 49.8 MB memset off the trace stream's critical path
+        self.engine.render_ghosts_device(lights, self.params, acc.data_ptr(), clear_first=bool(self.dirty[b]))
+        self.dirty[b] = keep
         self.traced[b].record(self.A)
         last = self.traced[b]
         if self.C is not None:
@@ -97,6 +108,9 @@ class ShardedFlare:
         self.B.wait_event(last)
         if out is not None and (reduce_dst is None or self.world_size == 1 or self.rank == reduce_dst):
             self.fin_engine.finalize_device(acc.data_ptr(), self.full_params, out.data_ptr(), out.stride(1) * out.element_size(), elem)
+        if not keep:
+            with torch.cuda.stream(self.B):
+                acc.zero_()
         ev = torch.cuda.Event()
         ev.record(self.B)
         self.finalized[b] = ev
@@ -105,7 +119,7 @@ class ShardedFlare:
     # --- the serial one-frame form (kept for callers that want a frame at a time) -----------------------
     def render(self, lights, reduce_dst=None):
         self.begin()
-        b = self.frame(lights, out=None, reduce_dst=reduce_dst)
+        b = self.frame(lights, out=None, reduce_dst=reduce_dst, keep=True)
         self.join()
         return self.accums[b]
 
@@ -147,6 +161,10 @@ class PeerFlare:
         self.out_all = symm_mem.empty((self.n_buffers, H, W, 3), dtype=out_dtype, device=device)
         self.h_acc = symm_mem.rendezvous(self.accum_all, group.group_name)
         self.h_out = symm_mem.rendezvous(self.out_all, group.group_name)
+        self.flags = symm_mem.empty((16,), dtype=torch.int64, device=device)
+        self.flags.zero_()
+        self.h_flags = symm_mem.rendezvous(self.flags, group.group_name)
+        self.epoch = 0
         self.accum_all.zero_()
         self.acc_bytes = H * W * 3 * 8
         self.out_bytes = H * W * 3 * self.out_all.element_size()
@@ -166,9 +184,10 @@ class PeerFlare:
         self.B.wait_stream(cur)
 
     def barrier(self):
-        """Device-side barrier across the ranks, enqueued on the engine stream."""
-        with torch.cuda.stream(self.A):
-            self.h_acc.barrier(channel=0)
+        """Device-side barrier across the ranks, enqueued on the engine stream (lfb_peer_barrier: one warp, system-scope
+        flags in symmetric memory; nothing blocks on the host)."""
+        self.epoch += 1
+        self.engine.peer_barrier([int(p) for p in self.h_flags.buffer_ptrs], self.rank, self.epoch)
 
     def finish(self, stream=None):
         """All frames enqueued so far are complete in the owner's buffers once `stream` passes this point."""
