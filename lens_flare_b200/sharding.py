@@ -58,6 +58,7 @@ class ShardedFlare:
         self.C = torch.cuda.Stream(device=device) if world_size > 1 else None
         self.traced = [torch.cuda.Event() for _ in range(n_buffers)]
         self.reduced = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.fin_events = [torch.cuda.Event() for _ in range(n_buffers)]  # reused: no per-frame allocations
         self.finalized = [None] * n_buffers
         self.dirty = [False] * n_buffers  # buffers whose sums were kept: cleared by the next trace into them
         self.k = 0
@@ -101,17 +102,24 @@ class ShardedFlare:
         last = self.traced[b]
         if self.C is not None:
             self.C.wait_event(last)
-            with torch.cuda.stream(self.C):
-                reduce_accum(acc, dst=reduce_dst)
-                self.reduced[b].record(self.C)
+            prev = torch.cuda.current_stream(self.device)
+            torch.cuda.set_stream(self.C)  # cheaper than the context manager: this runs once per frame
+            if reduce_dst is None:
+                dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            else:
+                dist.reduce(acc, dst=reduce_dst, op=dist.ReduceOp.SUM)
+            self.reduced[b].record(self.C)
+            torch.cuda.set_stream(prev)
             last = self.reduced[b]
         self.B.wait_event(last)
         if out is not None and (reduce_dst is None or self.world_size == 1 or self.rank == reduce_dst):
             self.fin_engine.finalize_device(acc.data_ptr(), self.full_params, out.data_ptr(), out.stride(1) * out.element_size(), elem)
         if not keep:
-            with torch.cuda.stream(self.B):
-                acc.zero_()
-        ev = torch.cuda.Event()
+            prev = torch.cuda.current_stream(self.device)
+            torch.cuda.set_stream(self.B)
+            acc.zero_()
+            torch.cuda.set_stream(prev)
+        ev = self.fin_events[b]
         ev.record(self.B)
         self.finalized[b] = ev
         return b
