@@ -1059,6 +1059,15 @@ int starburst_device(lfb_engine* e, const lfb_light* lights, int n_lights, int w
   f.flare_radius = flare_radius;
   f.exponent = -flare_intensity + 3.0;  // :998-1001
   if (f.exponent <= 0) f.exponent = 2.0;
+  // the pattern is periodic in the (integer) pixel offsets with period W_t (2 W_t for an odd W_t): evaluate one period
+  // when the frame is larger (LFB_STARBURST_LATTICE=0 forces one column / row per pixel)
+  f.period = (e->star_w % 2 == 0) ? e->star_w : 2 * e->star_w;
+  const char* lat = getenv("LFB_STARBURST_LATTICE");
+  const bool lattice_ok = !(lat && atoi(lat) == 0);
+  f.lattice_x = lattice_ok && width > f.period;
+  f.lattice_y = lattice_ok && height > f.period;
+  f.n_col = f.lattice_x ? f.period : width;
+  f.n_row = f.lattice_y ? f.period : height;
   std::vector<double> L(5 * (size_t)n_lights);
   double rad_sum[3] = {0, 0, 0};
   for (int l = 0; l < n_lights; l++) {

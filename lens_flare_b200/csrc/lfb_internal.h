@@ -147,6 +147,9 @@ struct StarFrame {
   double org_x, org_y;      // flare origin in pixels (ceil(fo * size))
   double total;             // CameraApertureTexture::total_value
   double flare_radius, exponent;  // exponent = 3 - flare_intensity (2 when that is <= 0), :998-1001
+  // the lattice the two matrix products are evaluated on: n_col columns / n_row rows; lattice_x / lattice_y: that axis is
+  // the P-periodic class lattice (period P = W_t or 2 W_t), else one column / row per pixel
+  int n_col, n_row, lattice_x, lattice_y, period, pad;
 };
 size_t starburst_scratch_bytes(const StarFrame& f);
 cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch, const double* lights_dev, int n_lights,

@@ -12,6 +12,12 @@
 // -- 6.6 GFLOP for a 1080p frame instead of 2.6e11 sincos pairs -- followed by a per-pixel epilogue fused into the second
 // product.  FP64 throughout (the reference is double; the parity tolerance is 1e-9 relative on the DFT scalar).
 //
+// PERIODICITY.  alpha(x) = lr - x'(x) and beta(y) = ud - y'(y) are always INTEGERS (the W/2 and H/2 cancel), and
+// u_xc alpha = (xc - W_t/2) alpha / W_t, so E1 only depends on alpha mod P with P = W_t (W_t even) or 2 W_t; likewise E2 on
+// beta mod P.  When the frame is wider / taller than P (1080p vs the 500-texel masks: P = 500) the products are evaluated
+// on the P-periodic lattice only -- 7x fewer FLOPs at 1080p -- and every pixel looks its |F| up at
+// (beta(y) mod P, alpha(x) mod P); with the reduced arguments the twiddles are also more accurate than the reference's.
+//
 //   twiddle_kernel            E1 / E2 / complex copy of the mask's bounding box
 //   zgemm_kernel<EPILOGUE>    tiled complex FP64 GEMM, 64x64 tile per CTA, 4x4 outputs per thread, K step 16
 //   the EPILOGUE variant      |F| / total -> suppression (dist > W_t/2: factor^8) / amplification (dist <= radius:
@@ -28,10 +34,29 @@ __device__ __forceinline__ double convert_coordinate(int pixel, int length, bool
   return cc >= 0 ? cc : (double)length + cc;
 }
 
-// which = 0: E1[xc_i][x]  (rows = bw, cols = W);  which = 1: E2[y][yc_i]  (rows = H, cols = bh);
+// alpha of lattice column c / beta of lattice row r: the class index itself on the periodic lattice, else the pixel's value
+__device__ __forceinline__ double star_alpha(const StarFrame& f, int c) {
+  return f.lattice_x ? (double)c : f.lr - convert_coordinate(c, f.W, false);
+}
+__device__ __forceinline__ double star_beta(const StarFrame& f, int r) {
+  return f.lattice_y ? (double)r : f.ud - convert_coordinate(r, f.H, true);
+}
+// lattice column of pixel x / row of pixel y
+__device__ __forceinline__ int star_col(const StarFrame& f, int x) {
+  if (!f.lattice_x) return x;
+  const long long a = (long long)llrint(f.lr - convert_coordinate(x, f.W, false));
+  return (int)(((a % f.period) + f.period) % f.period);
+}
+__device__ __forceinline__ int star_row(const StarFrame& f, int y) {
+  if (!f.lattice_y) return y;
+  const long long b = (long long)llrint(f.ud - convert_coordinate(y, f.H, true));
+  return (int)(((b % f.period) + f.period) % f.period);
+}
+
+// which = 0: E1[xc_i][col]  (rows = bw, cols = n_col);  which = 1: E2[row][yc_i]  (rows = n_row, cols = bh);
 // which = 2: complex copy of the mask's bounding box A[yc_i][xc_i] (rows = bh, cols = bw)
 __global__ void __launch_bounds__(256) twiddle_kernel(StarFrame f, const float* __restrict__ tex, double2* __restrict__ out, int which) {
-  const int rows = which == 0 ? f.bw : (which == 1 ? f.H : f.bh), cols = which == 0 ? f.W : (which == 1 ? f.bh : f.bw);
+  const int rows = which == 0 ? f.bw : (which == 1 ? f.n_row : f.bh), cols = which == 0 ? f.n_col : (which == 1 ? f.bh : f.bw);
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (size_t)rows * cols) return;
   const int r = (int)(q / cols), c = (int)(q - (size_t)r * cols);
@@ -41,8 +66,8 @@ __global__ void __launch_bounds__(256) twiddle_kernel(StarFrame f, const float* 
     v.y = 0.0;
   } else {
     double e;
-    if (which == 0) e = (((double)(f.bx0 + r) / (double)f.tw) - 0.5) * (f.lr - convert_coordinate(c, f.W, false));
-    else e = (((double)(f.by0 + c) / (double)f.tw) - 0.5) * (f.ud - convert_coordinate(r, f.H, true));
+    if (which == 0) e = (((double)(f.bx0 + r) / (double)f.tw) - 0.5) * star_alpha(f, c);
+    else e = (((double)(f.by0 + c) / (double)f.tw) - 0.5) * star_beta(f, r);
     sincospi(2.0 * e, &v.y, &v.x);
   }
   out[q] = v;
@@ -56,8 +81,8 @@ struct StarEpilogue {
   double rad_sum[3];
 };
 
-__device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogue& E, int x, int y, double re, double im) {
-  double I = sqrt(re * re + im * im) / f.total;
+__device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogue& E, int x, int y, double mag) {
+  double I = mag / f.total;
   const double dx = f.org_x - (double)x, dy = f.org_y - (double)y, dist = sqrt(dx * dx + dy * dy);
   if (dist > (double)f.tw / 2.0) {  // suppression :983-989
     const double factor = ((double)f.tw / 2.0) / dist;
@@ -95,7 +120,7 @@ __device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogu
   }
 }
 
-// C[M x N] = A[M x K] . B[K x N], complex FP64, row-major.  EPILOGUE: C is not stored; (row, col) = pixel (y, x).
+// C[M x N] = A[M x K] . B[K x N], complex FP64, row-major.  EPILOGUE: only |C| is stored (as a double array in C).
 template <bool EPILOGUE>
 __global__ void __launch_bounds__(256) zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__ B, double2* __restrict__ C,
                                                     int M, int N, int K, StarFrame f, StarEpilogue E) {
@@ -144,12 +169,20 @@ __global__ void __launch_bounds__(256) zgemm_kernel(const double2* __restrict__ 
     for (int j = 0; j < 4; j++) {
       const int gm = m0 + ty + 16 * i, gn = n0 + tx + 16 * j;
       if (gm >= M || gn >= N) continue;
-      if (EPILOGUE) star_pixel(f, E, gn, gm, acc[i][j].x, acc[i][j].y);
+      if (EPILOGUE) reinterpret_cast<double*>(C)[(size_t)gm * N + gn] = sqrt(acc[i][j].x * acc[i][j].x + acc[i][j].y * acc[i][j].y);
       else C[(size_t)gm * N + gn] = acc[i][j];
     }
 }
 
 }  // namespace
+
+// one thread per pixel: |F| from the lattice, then suppression / amplification / power law / falloff / output
+__global__ void __launch_bounds__(256) star_pixels_kernel(StarFrame f, StarEpilogue E, const double* __restrict__ mag) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (size_t)f.W * f.H) return;
+  const int y = (int)(p / f.W), x = (int)(p - (size_t)y * f.W);
+  star_pixel(f, E, x, y, mag[(size_t)star_row(f, y) * f.n_col + star_col(f, x)]);
+}
 
 // HDRImageBuffer::toColor (util/image.h:208-223: gamma 2.2, exposure sqrt(2), clamp) + ImageBuffer::update_pixel
 // (:53-62: truncating 8-bit pack 0xFFBBGGRR); flip = 1 also applies save_image's vertical flip (raytraced_renderer.cpp:739-742).
@@ -177,33 +210,36 @@ cudaError_t launch_to_color(const double* hdr, int W, int H, uint32_t* out, int 
   return cudaGetLastError();
 }
 
-// scratch: E1 (bw*W) | E2 (H*bh) | Ac (bh*bw) | G (bh*W) complex doubles
+// scratch: E1 (bw*n_col) | E2 (n_row*bh) | Ac (bh*bw) | G (bh*n_col) complex doubles | |F| (n_row*n_col) doubles
 size_t starburst_scratch_bytes(const StarFrame& f) {
-  return sizeof(double2) * ((size_t)f.bw * f.W + (size_t)f.H * f.bh + (size_t)f.bh * f.bw + (size_t)f.bh * f.W);
+  return sizeof(double2) * ((size_t)f.bw * f.n_col + (size_t)f.n_row * f.bh + (size_t)f.bh * f.bw + (size_t)f.bh * f.n_col) +
+         sizeof(double) * (size_t)f.n_row * f.n_col;
 }
 
 cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch, const double* lights_dev, int n_lights,
                              const double rad_sum[3], void* out, size_t stride, int elem, int additive, cudaStream_t s, int* launches) {
   double2* E1 = (double2*)scratch;
-  double2* E2 = E1 + (size_t)f.bw * f.W;
-  double2* Ac = E2 + (size_t)f.H * f.bh;
+  double2* E2 = E1 + (size_t)f.bw * f.n_col;
+  double2* Ac = E2 + (size_t)f.n_row * f.bh;
   double2* G = Ac + (size_t)f.bh * f.bw;
+  double* mag = (double*)(G + (size_t)f.bh * f.n_col);
   auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
-  twiddle_kernel<<<blocks((size_t)f.bw * f.W), 256, 0, s>>>(f, tex, E1, 0);
-  twiddle_kernel<<<blocks((size_t)f.H * f.bh), 256, 0, s>>>(f, tex, E2, 1);
+  twiddle_kernel<<<blocks((size_t)f.bw * f.n_col), 256, 0, s>>>(f, tex, E1, 0);
+  twiddle_kernel<<<blocks((size_t)f.n_row * f.bh), 256, 0, s>>>(f, tex, E2, 1);
   twiddle_kernel<<<blocks((size_t)f.bh * f.bw), 256, 0, s>>>(f, tex, Ac, 2);
   StarEpilogue E;
   E.out = (char*)out; E.stride = stride; E.elem = elem; E.additive = additive; E.n_lights = n_lights; E.lights = lights_dev;
   E.rad_sum[0] = rad_sum[0]; E.rad_sum[1] = rad_sum[1]; E.rad_sum[2] = rad_sum[2];
-  {  // G = Ac . E1   (bh x bw) . (bw x W)
-    dim3 grid((f.W + TN - 1) / TN, (f.bh + TM - 1) / TM);
-    zgemm_kernel<false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, f.W, f.bw, f, E);
+  {  // G = Ac . E1   (bh x bw) . (bw x n_col)
+    dim3 grid((f.n_col + TN - 1) / TN, (f.bh + TM - 1) / TM);
+    zgemm_kernel<false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, f.n_col, f.bw, f, E);
   }
-  {  // F = E2 . G    (H x bh) . (bh x W), fused epilogue
-    dim3 grid((f.W + TN - 1) / TN, (f.H + TM - 1) / TM);
-    zgemm_kernel<true><<<grid, 256, 0, s>>>(E2, G, nullptr, f.H, f.W, f.bh, f, E);
+  {  // |F| = |E2 . G|   (n_row x bh) . (bh x n_col)
+    dim3 grid((f.n_col + TN - 1) / TN, (f.n_row + TM - 1) / TM);
+    zgemm_kernel<true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh, f, E);
   }
-  if (launches) *launches += 5;
+  star_pixels_kernel<<<blocks((size_t)f.W * f.H), 256, 0, s>>>(f, E, mag);
+  if (launches) *launches += 6;
   return cudaGetLastError();
 }
 

@@ -71,6 +71,23 @@ def test_gpu_starburst_frame_vs_reference_golden(engine, port, apertures, case):
 
 
 @pytest.mark.gpu
+def test_gpu_starburst_lattice_equals_per_pixel_evaluation(apertures, monkeypatch):
+    """The P-periodic lattice evaluation (frames larger than the mask's period) equals one column / row per pixel."""
+    lt = [capi.make_light(0.31, 0.64, radiance=(1.0, 0.5, 0.25))]
+    frames = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LFB_STARBURST_LATTICE", mode)
+        e = capi.Engine(0)
+        try:
+            e.set_starburst_aperture(apertures["pent_11"])
+            frames[mode] = [e.render_starburst(lt, W, H, 40.0, 1.5) for (W, H) in ((1280, 720), (700, 300), (333, 641))]
+        finally:
+            e.close()
+    for a, b in zip(frames["1"], frames["0"]):
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-14)
+
+
+@pytest.mark.gpu
 def test_gpu_starburst_layouts_and_composition(engine, apertures):
     """additive = 1 composes like raytrace_pixel (pathtracer.cpp:881-891): sampleBuffer += ghost + starburst."""
     engine.set_lens(capi.builtin_lens(3))
