@@ -116,8 +116,9 @@ typedef struct lfb_params {
   int32_t fixed_point_bits; /* sensor accumulators are u64 fixed point with this many fractional bits; 0 -> 40 */
   int32_t physical_backward; /* PARAXIAL_GRID only: 0 = the reference's R^-1 on backward legs
                                 (pathtracer.cpp:607-608), 1 = physically consistent backward refraction */
-  int32_t shard_index, shard_count; /* this engine renders jobs q with q % shard_count == shard_index
-                                       of the LPT-ordered (light x pair x lambda) job list; 0,0 -> all */
+  int32_t shard_index, shard_count; /* this engine renders its share of the (light x pair x lambda) job list: whole
+                                       (light, lambda) groups round-robin when there are at least shard_count groups,
+                                       else single jobs, longest first, round-robin; 0,0 -> all */
   float px_per_unit;       /* sensor pixels per lens unit; 0 -> 0.4 (pathtracer.cpp:457-463) */
   float reserved[3];
 } lfb_params;

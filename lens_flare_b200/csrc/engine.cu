@@ -62,8 +62,7 @@ int list_pairs(const lfb_lens& L, int pair_set, int pairs[][2]) {
 // i+1..n-1, sensor plane  =>  2(j-i) + n + 1; the direct path meets n surfaces + the sensor.
 int interactions_of(const lfb_lens& L, int i, int j) { return i < 0 ? L.n_surfaces + 1 : 2 * (j - i) + L.n_surfaces + 1; }
 
-// All (light, pair, lambda) jobs of a frame, then this shard's share: jobs are ordered by
-// decreasing cost (longest-processing-time first, stable) and dealt round-robin to shards.
+// All (light, pair, lambda) jobs of a frame, then this shard's share (see the rule at the end).
 void list_jobs(const lfb_lens& L, const lfb_params& P, int n_lights, std::vector<JobId>& out) {
   int pairs[LFB_MAX_SURFACES * LFB_MAX_SURFACES][2];
   std::vector<JobId> all;
@@ -83,6 +82,15 @@ void list_jobs(const lfb_lens& L, const lfb_params& P, int n_lights, std::vector
   }
   out.clear();
   if (P.shard_count <= 1) { out = all; return; }
+  // Sharding.  When the frame has at least as many (light, lambda) groups as shards, whole groups are dealt round-robin:
+  // all ghosts of a group share one forward sweep (the prefix cache of the FP32 kernel), and equal groups balance
+  // exactly.  Otherwise single jobs are dealt, longest-processing-time first (stable), round-robin.
+  const int n_groups = P.mode == LFB_MODE_REF_QUADS ? 0 : n_lights * L.n_lambda;
+  if (n_groups >= P.shard_count) {
+    for (const JobId& id : all)
+      if ((id.light * L.n_lambda + id.lambda) % P.shard_count == P.shard_index) out.push_back(id);
+    return;
+  }
   std::stable_sort(all.begin(), all.end(), [&](const JobId& a, const JobId& b) {
     return interactions_of(L, a.i, a.j) > interactions_of(L, b.i, b.j);
   });

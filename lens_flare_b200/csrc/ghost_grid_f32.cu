@@ -37,7 +37,7 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
     if (bt == 64) {
       LFB_PATCH2(24, 64);
     } else if (bt == 128) {
-      if (g.pad >= 6) LFB_PATCH2(12, 128);
+      if (g.pad >= 7) LFB_PATCH2(16, 128); else if (g.pad >= 6) LFB_PATCH2(12, 128);
       else LFB_PATCH2(8, 128);
     } else {
       if (g.pad >= 6) LFB_PATCH2(6, 256);

@@ -656,9 +656,9 @@ static int job_cost(const lfb_lens* L, const job_t* q) { /* ray-surface interact
   return q->i < 0 ? L->n_surfaces + 1 : 2 * (q->j - q->i) + L->n_surfaces + 1;
 }
 
-/* All jobs in (light, pair, lambda) order; with shard_count > 1 the list is put in
- * longest-processing-time-first order (stable) and dealt round-robin: this shard keeps the
- * jobs q with q % shard_count == shard_index. */
+/* All jobs in (light, pair, lambda) order.  Sharding: whole (light, lambda) groups round-robin when there are at
+ * least as many groups as shards; otherwise the list is put in longest-processing-time-first order (stable) and
+ * single jobs are dealt round-robin (q % shard_count == shard_index). */
 static int list_jobs(const lfb_lens* L, const lfb_params* P, int n_lights, job_t** out) {
   int pairs[LFB_MAX_SURFACES * LFB_MAX_SURFACES][2];
   int np = list_pairs(L, P->pair_set, pairs);
@@ -672,7 +672,13 @@ static int list_jobs(const lfb_lens* L, const lfb_params* P, int n_lights, job_t
         J[n++] = q;
       }
     }
-  if (P->shard_count > 1) {
+  if (P->shard_count > 1 && n_lights * L->n_lambda >= P->shard_count) {
+    /* at least as many (light, lambda) groups as shards: whole groups are dealt round-robin */
+    int m = 0;
+    for (int q = 0; q < n; q++)
+      if ((J[q].light * L->n_lambda + J[q].lambda) % P->shard_count == P->shard_index) J[m++] = J[q];
+    n = m;
+  } else if (P->shard_count > 1) {
     for (int a = 1; a < n; a++) { /* stable insertion sort, decreasing cost */
       job_t q = J[a];
       int b = a - 1;
