@@ -34,6 +34,15 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
     else if (g.patch >= 2) LFB_LAUNCH2(2, 1, MB, BT); \
     else LFB_LAUNCH2(1, 1, MB, BT);               \
   } while (0)
+    static int warp_mode = -1;
+    if (warp_mode < 0) { const char* env = getenv("LFB_EXACT_WARP"); warp_mode = env ? atoi(env) : 1; }
+    if (warp_mode && g.patch <= 1) {  // v6: warp-autonomous splat (default)
+      const unsigned nb = blocks2(1, 1, bt / 16);
+      if (bt == 64) xf32::exact_splat3_kernel<24, 64><<<nb, 64, 0, s>>>(jobs, progs, g, tex, accum);
+      else if (bt == 256) xf32::exact_splat3_kernel<6, 256><<<nb, 256, 0, s>>>(jobs, progs, g, tex, accum);
+      else xf32::exact_splat3_kernel<12, 128><<<nb, 128, 0, s>>>(jobs, progs, g, tex, accum);
+      return cudaGetLastError();
+    }
     if (bt == 64) {
       LFB_PATCH2(24, 64);
     } else if (bt == 128) {
