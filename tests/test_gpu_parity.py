@@ -503,3 +503,60 @@ def test_dirty_rectangle_render_equals_full_frame(engine, apertures, mode):
                 assert (x1 - x0 + 1) * (y1 - y0 + 1) < 0.25 * W * H
     # empty frame
     assert engine.render_ghosts_rect([], p, np.zeros((H, W, 3))) is None
+
+
+def test_custom_prescription(engine, port, apertures):
+    """Nothing is hard-wired to the built-in lens: a 6-surface triplet-like prescription with the stop at index 3, its own
+    glass table and coatings on some surfaces, all modes, vs the oracle."""
+    lens = capi.Lens()
+    lens.n_surfaces, lens.stop_index, lens.n_lambda = 6, 3, 2
+    radii = [40.0, -120.0, -55.0, 0.0, 60.0, -45.0]
+    thick = [5.0, 3.0, 2.0, 4.0, 6.0, 70.0]
+    n_after = [[1.62, 1.0, 1.70, 1.0, 1.55, 1.0], [1.63, 1.0, 1.72, 1.0, 1.56, 1.0]]
+    for k in range(6):
+        lens.curvature[k] = 0.0 if radii[k] == 0 else 1.0 / radii[k]
+        lens.thickness[k] = thick[k]
+        lens.semi_aperture[k] = 12.0
+        lens.coating_lambda0_nm[k] = 520.0 if k in (0, 4) else 0.0
+        for l in range(2):
+            lens.ior[l][k] = n_after[l][k]
+    lens.lambda_nm[0], lens.lambda_nm[1] = 620.0, 480.0
+    lens.rgb_weight[0][0], lens.rgb_weight[0][1], lens.rgb_weight[1][1], lens.rgb_weight[1][2] = 1.0, 0.4, 0.6, 1.0
+    lens.entrance_half_height, lens.stop_half_height, lens.stop_half_height_neg = 10.0, 8.0, 8.0
+    engine.set_lens(lens)
+    engine.set_aperture(apertures["pentbig500_14"])
+    lt = [capi.make_light(0.4, 0.6, theta=0.05, radiance=(1.0, 2.0, 0.5))]
+    assert capi.count_work(lens, capi.make_params(capi.MODE_EXACT_GRID, 8, 8, grid_n=1, pair_set=capi.PAIRS_ALL), 1)[2] == 2 * 10
+    for mode in (capi.MODE_REF_QUADS, capi.MODE_PARAXIAL_GRID, capi.MODE_EXACT_GRID):
+        p = capi.make_params(mode, 400, 300, grid_n=48, pair_set=capi.PAIRS_ALL if mode else capi.PAIRS_REF, include_direct=int(mode != 0),
+                             precision=capi.FP64, px_per_unit=0.5)
+        got = engine.render_ghosts(lt, p)
+        want = port.render(lens, apertures["pentbig500_14"], lt, p)
+        assert want.any(), mode
+        if mode == capi.MODE_EXACT_GRID:  # coated surfaces: cos() last-ulp, see test_exact_frame_fixed_point_sums
+            assert np.abs(np.rint(got * 2.0 ** 40) - np.rint(want * 2.0 ** 40)).max() <= 4 * 64
+            got32 = engine.render_ghosts(lt, capi.copy_params(p, precision=capi.FP32))
+            assert rel_l2(got32, want) <= 1e-3
+        else:
+            assert np.array_equal(got, want), mode
+    engine.set_lens(capi.builtin_lens(3))
+
+
+def test_prefix_cache_budget_fallback(apertures, monkeypatch):
+    """When the prefix cache would not fit its HBM budget the engine traces every ghost from the entrance instead:
+    same frame (to FP32 rounding of the two code paths)."""
+    lens = capi.builtin_lens(3, 550.0)
+    lt = [capi.make_light(0.45, 0.55, theta=capi.physical_theta(0.45, 0.55))]
+    p = capi.make_params(capi.MODE_EXACT_GRID, 640, 360, grid_n=96, pair_set=capi.PAIRS_ALL, include_direct=1)
+    frames = []
+    for budget in (None, "1"):
+        if budget:
+            monkeypatch.setenv("LFB_PREFIX_BUDGET_MB", budget)
+        e = capi.Engine(0)
+        try:
+            e.set_lens(lens)
+            e.set_aperture(apertures["pentbig500_14"])
+            frames.append(e.render_ghosts(lt, p))
+        finally:
+            e.close()
+    assert frames[0].any() and rel_l2(frames[1], frames[0]) <= 1e-6
