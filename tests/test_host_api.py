@@ -201,3 +201,16 @@ def test_cpp_png_reader_matches_reference_loader(native_lib, apertures, tmp_path
         assert np.isclose(info["total"], apertures["pentbig500_14_total"], rtol=1e-12), name
     bad = subprocess.run([exe, "--png-info", str(tmp_path / "missing.png")], capture_output=True, text=True)
     assert bad.returncode == 1 and "cannot open" in bad.stderr
+
+
+def test_header_is_plain_c(native_lib, tmp_path):
+    """include/lfb200.h compiles as strict C99 and the library links and runs from a plain C program."""
+    import subprocess
+    exe = tmp_path / "abi_from_c"
+    lib_dir = os.path.join(ROOT, "lens_flare_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_from_c.c"), "-o", str(exe), "-L" + lib_dir, "-llfb200", "-Wl,-rpath," + lib_dir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "abi 1 jobs 87 rays 5701632 interactions 95944704" in out
+    assert "sizeof(lens)=5416 light=32 params=64 hit=64" in out
+    assert "lfb_create -> 0" in out or "lfb_create -> -2" in out
