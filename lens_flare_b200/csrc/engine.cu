@@ -715,6 +715,7 @@ extern "C" int lfb_set_lens(lfb_engine* e, const lfb_lens* L) {
   rc = check_lens(L);
   if (rc) return rc;
   CU(cudaStreamSynchronize(e->stream));
+  e->has_lens = false;  // until every table below is rebuilt
   e->lens = *L;
   DevLens& D = e->dev_lens;
   memset(&D, 0, sizeof(D));
