@@ -1,31 +1,35 @@
-// exact_f32.cuh -- the throughput kernel of the ghost path: EXACT_GRID in FP32.
+// exact_f32.cuh -- the throughput kernels of the ghost path: EXACT_GRID in FP32.
 //
-// The kernel is bound by instruction issue on the scalar FP32 pipes (ncu, profiles/): there is no
-// memory stream to speak of (rays are generated from their grid index, a ghost's whole description is
-// ~1 KB, the 1 MB aperture mask is L2/L1 resident), so the design minimises instructions per ray:
+// There is no memory stream to speak of (rays are generated from their grid index, a ghost's whole description is ~1 KB,
+// the 1 MB aperture mask is L2/L1 resident), so the design minimises instructions and stalls per ray (ncu, profiles/):
 //
-//  * STEP PROGRAM.  The host flattens each ghost (i, j, lambda) into a straight list of steps
-//    (refract / reflect / stop plane / sensor plane) with every ray-independent quantity already
-//    computed: curvature, vertex shift, clear radius^2, n0/n2 and its square, the coating's film index,
-//    (n0/n1)^2 and phase factor.  A CTA stages its ghost's program in shared memory once; the per-ray
-//    loop has no "which surface / which direction / which glass" logic and no divisions by constants.
-//  * FAST SCALAR MATH.  rcp.approx / sqrt.approx / cos.approx (one MUFU each) instead of the IEEE
-//    division and square root sequences (MUFU + FCHK + slow-path branch + Newton FFMAs), and Fresnel /
-//    thin-film reflectances restructured to ONE reciprocal per surface.
-//  * MIRROR SYMMETRY.  A distant light's bundle and the lens are symmetric about the meridional plane:
-//    ray (x, -y) is the mirror image of ray (x, y).  One trace serves both; only the (asymmetric)
-//    aperture mask is looked up twice.  Half the grid is traced, every ray is still deposited.
-//  * TWO PASSES WITH SURVIVOR COMPACTION.  Most rays of a bundle die (vignetted, total internal
-//    reflection, blocked by the aperture mask) and carry no energy.  Pass 1 traces geometry only and
-//    queues the survivors of the CTA's ray patch (with their sensor pixel) in shared memory; pass 2
-//    re-traces only the survivors, in dense warps, with the Fresnel / coating weights.
-//  * SHARED-MEMORY SENSOR TILE.  Neighbouring rays land on neighbouring (often the same) pixels: the
-//    CTA accumulates its deposits in a small u64 fixed-point tile in shared memory and flushes each
-//    touched pixel with one global atomic (falls back to direct global atomics when the patch's footprint
-//    exceeds the tile).  Integer accumulation keeps the frame bit-stable for any schedule or GPU count.
+//  * STEP PROGRAM.  The host flattens each ghost (i, j, lambda) into a straight list of steps (refract / reflect / stop
+//    plane / sensor plane) with every ray-independent quantity already computed: curvature, vertex shift, clear radius^2,
+//    n0/n2 and its square, the reflectance table of the interface.  A CTA stages its ghost's program in shared memory
+//    once; the per-ray loop has no "which surface / which direction / which glass" logic and no divisions by constants.
+//  * UNIFIED STEP.  Planes are c = 0 surfaces with an infinite clear radius; a missed surface or a total internal
+//    reflection turns the state into NaNs that the next clear-radius test catches: ONE death test per step.
+//  * FAST SCALAR MATH.  rcp.approx / sqrt.approx (one MUFU each) instead of the IEEE division and square root sequences
+//    (MUFU + FCHK + slow-path branch + Newton FFMAs).
+//  * TABULATED REFLECTANCES (v4).  Fresnel / quarter-wave-film reflectance of every (wavelength, surface, direction) is
+//    tabulated on the host in double over the cosine in the rarer medium (where it is analytic): ~10 instructions and one
+//    8-byte load per surface instead of ~60, cheap enough to carry the weight along in a single trace.
+//  * MIRROR SYMMETRY (v3).  A distant light's bundle and the lens are symmetric about the meridional plane: ray (x, -y) is
+//    the mirror image of ray (x, y).  One trace serves both; only the (asymmetric) aperture mask is looked up twice.
+//  * PREFIX CACHE (v5).  The forward sweep 0 .. j-1 shared by all ghosts of a (light, wavelength) is traced once
+//    (prefix_kernel) and the ray states on every surface cached in L2; ghost jobs start ON their first-reflection surface.
+//  * WARP-AUTONOMOUS SPLAT (v6).  A warp owns its 32 ray pairs from trace to flush: survivors stay in registers, deposits
+//    go to a 64-pixel u64 fixed-point tile per warp in shared memory and each touched pixel is flushed with one global
+//    atomic (direct global atomics when the footprint exceeds the tile).  The only CTA barrier is the one after staging the
+//    program.  Integer accumulation keeps the frame bit-stable for any schedule, kernel generation or GPU count.
 //
-// Parity: per-ray and image tolerances against the double-precision oracle are in
-// tests/test_gpu_parity.py; the FP64 kernels in ghost_grid_impl.cuh remain the bit-exact instruments.
+// Kernel generations, all selectable and tested against each other and the oracle (tests/test_gpu_parity.py):
+//   exact_splat_kernel   v3  two passes (geometry, then survivors with closed-form Fresnel)     LFB_EXACT_WEIGHTS=closed
+//   exact_splat1_kernel  v4  one pass with tabulated reflectances, CTA-level queue and tile      LFB_EXACT_PREFIX=0
+//   exact_splat2_kernel  v5  + prefix cache                                                      LFB_EXACT_WARP=0
+//   exact_splat3_kernel  v6  + warp-autonomous splat (default)
+// Parity: per-ray and image tolerances against the double-precision oracle are in tests/test_gpu_parity.py; the FP64
+// kernels in ghost_grid_impl.cuh remain the bit-exact instruments.
 #pragma once
 #include <math_constants.h>
 
