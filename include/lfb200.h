@@ -169,6 +169,12 @@ int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_lights,
                       const lfb_params* params, void* out, size_t out_stride_bytes,
                       int out_elem, int additive);
 
+/* lfb_render_ghosts without the wait (grid modes, overwrite semantics): the frame's device->host copy runs on a second
+ * stream out of one of two device buffers and overlaps the next frame's trace.  `out` (pinned memory for a truly
+ * asynchronous copy) is complete after lfb_sync(); alternate between two host buffers to keep two frames in flight. */
+int lfb_render_ghosts_async(lfb_engine* e, const lfb_light* lights, int n_lights,
+                            const lfb_params* params, void* out, size_t out_stride_bytes, int out_elem);
+
 /* Dirty-rectangle form of lfb_render_ghosts.  A flare covers a small part of the sensor and the caller's buffer is
  * normally already clear (the reference clears ghost_buffer right before drawing, pathtracer.cpp:719-720; util/image.h:126-131),
  * so only the bounding rectangle of the pixels this frame deposits into is converted and copied back: pixels outside

@@ -31,7 +31,7 @@ RAY_MISSED, RAY_VIGNETTED, RAY_TIR, RAY_STOPPED, RAY_OFF_SENSOR = 1, 2, 4, 8, 16
 # every symbol include/lfb200.h declares (tests check the library exports each one)
 SYMBOLS = (
     "lfb_abi_version", "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
-    "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
+    "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_render_ghosts_async", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
     "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_reduce_finalize_peers", "lfb_peer_barrier", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
     "lfb_host_alloc", "lfb_host_free", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
 )
@@ -156,6 +156,7 @@ def lib():
     L.lfb_set_lens.argtypes = [vp, LP]
     L.lfb_set_aperture.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.c_int]
     L.lfb_render_ghosts.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.c_int]
+    L.lfb_render_ghosts_async.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int]
     L.lfb_render_ghosts_rect.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
     L.lfb_dump_rays.argtypes = [vp, LiP, PP, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]
     L.lfb_ref_ghosts.argtypes = [vp, vp, C.c_int]
@@ -267,6 +268,12 @@ class Engine:
         check(lib().lfb_render_ghosts(self._h, lights_array(lights), len(lights), C.byref(params),
                                       out.ctypes.data, stride, elem, int(additive)))
         return out
+
+    def render_ghosts_async(self, lights, params, out, elem=F64x3, stride=None):
+        """Enqueue a frame into `out` (pinned host array) without waiting; complete after sync()."""
+        if stride is None:
+            stride = out.strides[1]
+        check(lib().lfb_render_ghosts_async(self._h, lights_array(lights), len(lights), C.byref(params), out.ctypes.data, stride, elem))
 
     def render_ghosts_rect(self, lights, params, out, elem=F64x3, stride=None):
         """Dirty-rectangle form: writes only the bounding rectangle of the frame's deposits into `out` (which the

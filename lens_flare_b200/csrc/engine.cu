@@ -180,6 +180,14 @@ struct lfb_engine {
   size_t star_scratch_cap = 0;
   double* d_star_lights = nullptr;
   size_t star_lights_cap = 0;
+  // asynchronous host path (lfb_render_ghosts_async): the frame's device->host copy runs on its own stream out of one of
+  // two device buffers, so it overlaps the next frame's trace
+  cudaStream_t copy_stream = nullptr;
+  char* d_out_ab[2] = {nullptr, nullptr};
+  size_t out_ab_cap[2] = {0, 0};
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  bool copied_valid[2] = {false, false};
+  int ab = 0;
   // display-frame path (lfb_render_frame_rgba8)
   double* d_hdr = nullptr;
   size_t hdr_cap = 0;
@@ -607,6 +615,12 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   cudaFree(e->d_slots); cudaFree(e->d_slot_progs); cudaFree(e->d_prefix);
   if (e->h_slots) cudaFreeHost(e->h_slots);
   if (e->h_slot_progs) cudaFreeHost(e->h_slot_progs);
+  if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+  for (int k = 0; k < 2; k++) {
+    cudaFree(e->d_out_ab[k]);
+    if (e->ev_ready[k]) cudaEventDestroy(e->ev_ready[k]);
+    if (e->ev_copied[k]) cudaEventDestroy(e->ev_copied[k]);
+  }
   cudaFree(e->d_star_tex); cudaFree(e->d_star_scratch); cudaFree(e->d_star_lights); cudaFree(e->d_hdr); cudaFree(e->d_rgba);
   if (e->h_bbox) cudaFreeHost(e->h_bbox);
   if (e->h_progs) cudaFreeHost(e->h_progs);
@@ -787,6 +801,7 @@ extern "C" int lfb_sync(lfb_engine* e) {
   int rc = bind(e);
   if (rc) return rc;
   CU(cudaStreamSynchronize(e->stream));
+  if (e->copy_stream) CU(cudaStreamSynchronize(e->copy_stream));
   return LFB_OK;
 }
 
@@ -889,6 +904,56 @@ extern "C" int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_l
   CU(cudaStreamSynchronize(e->stream));  // the reference's caller reads ghost_buffer right after the call
   CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
   CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
+  return LFB_OK;
+}
+
+// lfb_render_ghosts without the wait: the frame is traced and converted on the engine stream, then copied to `out` on a
+// second stream out of one of two device buffers, so the 49.8 MB copy of frame k overlaps the trace of frame k+1 (the PCIe
+// copy is ~8x longer than the trace).  `out` is complete after lfb_sync(); alternate between two host buffers to keep two
+// frames in flight.  Grid modes only, overwrite semantics.
+extern "C" int lfb_render_ghosts_async(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P, void* out,
+                                       size_t stride, int elem) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!e->has_lens || !e->has_tex) return fail(LFB_ERR_STATE, "set the lens and the aperture first");
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (n_lights < 0 || (n_lights > 0 && !lights) || !out) return fail(LFB_ERR_INVALID, "bad lights/out");
+  if (elem != LFB_F32x3 && elem != LFB_F64x3) return fail(LFB_ERR_INVALID, "unknown out_elem");
+  if (stride < elem_bytes(elem) || stride % (elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
+  if (!e->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      CU(cudaEventCreateWithFlags(&e->ev_ready[k], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e->ev_copied[k], cudaEventDisableTiming));
+    }
+  }
+  const int b = e->ab;
+  e->ab ^= 1;
+  const size_t npx = (size_t)P->width * P->height;
+  const size_t out_bytes = (npx - 1) * stride + elem_bytes(elem);
+  if (out_bytes > e->out_ab_cap[b]) {
+    CU(cudaStreamSynchronize(e->copy_stream));
+    rc = grow(&e->d_out_ab[b], &e->out_ab_cap[b], out_bytes);
+    if (rc) return rc;
+    e->copied_valid[b] = false;
+  }
+  rc = grow(&e->d_accum, &e->accum_cap, lfb_accum_bytes(P->width, P->height));
+  if (rc) return rc;
+  // buffer b's previous copy must have left the device buffer before it is overwritten
+  if (e->copied_valid[b]) CU(cudaStreamWaitEvent(e->stream, e->ev_copied[b], 0));
+  if (stride != elem_bytes(elem)) CU(cudaMemsetAsync(e->d_out_ab[b], 0, out_bytes, e->stream));
+  e->accum_dirty_w = e->accum_dirty_h = 0;
+  rc = render_grid_device(e, lights, n_lights, *P, e->d_accum, 1);
+  if (rc) return rc;
+  const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+  CU(launch_finalize(e->d_accum, P->width, P->height, inv, e->d_out_ab[b], stride, elem, 0, e->stream));
+  e->launches++;
+  CU(cudaEventRecord(e->ev_ready[b], e->stream));
+  CU(cudaStreamWaitEvent(e->copy_stream, e->ev_ready[b], 0));
+  CU(cudaMemcpyAsync(out, e->d_out_ab[b], out_bytes, cudaMemcpyDeviceToHost, e->copy_stream));
+  CU(cudaEventRecord(e->ev_copied[b], e->copy_stream));
+  e->copied_valid[b] = true;
   return LFB_OK;
 }
 

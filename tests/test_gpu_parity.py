@@ -560,3 +560,29 @@ def test_prefix_cache_budget_fallback(apertures, monkeypatch):
         finally:
             e.close()
     assert frames[0].any() and rel_l2(frames[1], frames[0]) <= 1e-6
+
+
+def test_async_render_equals_blocking_render(engine, apertures):
+    """lfb_render_ghosts_async: two frames in flight through two pinned host buffers give the blocking call's frames."""
+    engine.set_lens(capi.builtin_lens(3, 550.0))
+    engine.set_aperture(apertures["pentbig500_14"])
+    p = capi.make_params(capi.MODE_EXACT_GRID, 800, 450, grid_n=96, pair_set=capi.PAIRS_ALL, include_direct=1)
+    suns = [capi.make_light(x, y, theta=capi.physical_theta(x, y)) for x, y in ((0.45, 0.55), (0.6, 0.4), (0.52, 0.47), (0.4, 0.6), (0.45, 0.55))]
+    want = [engine.render_ghosts([s], p) for s in suns]
+    bufs = [capi.PinnedArray((450, 800, 3), np.float64) for _ in range(2)]
+    try:
+        got = []
+        for k, s in enumerate(suns):
+            if k >= 2:           # the buffer about to be reused holds frame k-2: read it out first
+                engine.sync()
+                got.append(bufs[k % 2].array.copy())
+            engine.render_ghosts_async([s], p, bufs[k % 2].array)
+        engine.sync()
+        got.append(bufs[(len(suns) - 2) % 2].array.copy())
+        got.append(bufs[(len(suns) - 1) % 2].array.copy())
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert b.any() and np.array_equal(a, b)
+    finally:
+        for b in bufs:
+            b.free()
