@@ -188,13 +188,18 @@ __global__ void __launch_bounds__(kTileW * kTileH) ref_raster_kernel(RefFrame f,
   const int tid = threadIdx.y * kTileW + threadIdx.x;
   // rw > 0: only the rectangle [rx0, rx0+rw) x [ry0, ry0+rh) is rastered, into a PACKED rw x rh output
   const int x0 = rx0 + blockIdx.x * kTileW, y0 = ry0 + blockIdx.y * kTileH;
-  // triangles whose loop bounds touch this tile, kept in draw order
+  // triangles whose loop bounds touch this tile, kept in draw order: every thread tests its share of the triangles in
+  // parallel (flags in shared memory), then one thread compacts the flags in index order
+  __shared__ unsigned char s_hit[kMaxTris];
+  for (int t = tid; t < n_tris; t += kTileW * kTileH) {
+    const RefTri& T = tris[t];
+    s_hit[t] = T.min_x < x0 + kTileW && T.max_x > x0 && T.min_y < y0 + kTileH && T.max_y > y0;
+  }
+  __syncthreads();
   if (tid == 0) {
     int n = 0;
-    for (int t = 0; t < n_tris; t++) {
-      const RefTri& T = tris[t];
-      if (T.min_x < x0 + kTileW && T.max_x > x0 && T.min_y < y0 + kTileH && T.max_y > y0) s_list[n++] = (unsigned short)t;
-    }
+    for (int t = 0; t < n_tris; t++)
+      if (s_hit[t]) s_list[n++] = (unsigned short)t;
     s_count = n;
   }
   __syncthreads();
