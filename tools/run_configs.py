@@ -26,7 +26,13 @@ def suns(n):
 
 
 def main():
-    dev = torch.device("cuda", 0)
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     z = np.load(os.path.join(ROOT, "tests", "golden", "apertures.npz"))
     ap = {k: z[k].astype(np.float32) * np.float32(1.0 / 255.0) for k in ("pent_11", "pentbig500_14")}
     cfgs = [
@@ -35,11 +41,11 @@ def main():
         ("cfg3", dict(n_lambda=32, coat=550.0, grid=512, W=1920, H=1080, tex="pentbig500_14", lights=1, pairs=capi.PAIRS_ALL, direct=1, reps=10)),
         ("cfg4", dict(n_lambda=3, coat=550.0, grid=1024, W=3840, H=2160, tex="pentbig500_14", lights=64, pairs=capi.PAIRS_ALL, direct=1, reps=3)),
     ]
-    only = sys.argv[1:]
+    only = [a for a in sys.argv[1:] if a.startswith("cfg")]
     for name, c in cfgs:
         if only and name not in only:
             continue
-        eng, fin = capi.Engine(0), capi.Engine(0)
+        eng, fin = capi.Engine(local), capi.Engine(local)
         lens = capi.builtin_lens(3 if c["n_lambda"] == 1 else c["n_lambda"], c["coat"])
         if c["n_lambda"] == 1:  # config 1: one wavelength (G)
             g = capi.builtin_lens(3, c["coat"])
@@ -54,13 +60,15 @@ def main():
         p = capi.make_params(capi.MODE_EXACT_GRID, c["W"], c["H"], grid_n=c["grid"], pair_set=c["pairs"], include_direct=c["direct"])
         lights = [capi.make_light(x, y, theta=capi.physical_theta(x, y)) for x, y in ([(0.45, 0.55)] if c["lights"] == 1 else suns(c["lights"]))]
         rays, inter, jobs = capi.count_work(lens, p, len(lights))
-        sh = sharding.ShardedFlare(eng, p, 0, 1, dev, n_buffers=2, finalize_engine=fin)
+        sh = sharding.ShardedFlare(eng, p, rank, world, dev, n_buffers=2, finalize_engine=fin)
         out = torch.empty((c["H"], c["W"], 3), dtype=torch.float32, device=dev)
         sh.begin()
         for _ in range(2):
             sh.frame(lights, out=out)
         sh.join()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         sh.begin()
@@ -69,9 +77,16 @@ def main():
         sh.join()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / c["reps"]
+        t = torch.tensor([e0.elapsed_time(e1) / c["reps"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        if rank != 0:
+            fin.close()
+            eng.close()
+            continue
         img = out.cpu().numpy().astype(np.float64)
-        line = {"config": name, "lights": len(lights), "n_lambda": lens.n_lambda, "grid": c["grid"], "sensor": [c["W"], c["H"]], "jobs": jobs,
+        line = {"config": name, "n_gpus": world, "lights": len(lights), "n_lambda": lens.n_lambda, "grid": c["grid"], "sensor": [c["W"], c["H"]], "jobs": jobs,
                 "rays": rays, "interactions": inter, "ms_per_frame": ms, "interactions_per_s": inter / (ms * 1e-3),
                 "kernel_ms": eng.stats()["last_trace_ms"], "image_sum": [float(v) for v in img.reshape(-1, 3).sum(0)],
                 "nonzero_px": int((img != 0).any(-1).sum())}
@@ -83,9 +98,14 @@ def main():
             want = ob.PortOracle().render(lens, ap[c["tex"]], lights, p)
             line["cpu_oracle_ms_1thread"] = (time.perf_counter() - t0) * 1e3
             line["rel_l2_vs_oracle"] = float(np.sqrt(((img - want) ** 2).sum() / (want ** 2).sum()))
+        if world > 1:  # the sharded, reduced frame must equal this GPU's own unsharded frame bit for bit
+            whole = eng.render_ghosts(lights, p, elem=capi.F32x3)
+            line["equals_single_gpu_frame"] = bool(np.array_equal(whole, out.cpu().numpy()))
         print(json.dumps(line), flush=True)
         fin.close()
         eng.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
