@@ -411,6 +411,31 @@ def run_ours(args):
                      "api": "lfb_render_frame_rgba8: ghosts -> HDRImageBuffer::toColor -> ImageBuffer RGBA8 on the device (the displayable frame)"}
         pinned_rgba.free()
 
+    # ---- SURVEY 8f-1 for the record (N = 1): the starburst of the same frame, device time vs the reference per pixel ----
+    starburst = None
+    if world == 1:
+        eng.set_starburst_aperture(tex)
+        for _ in range(3):
+            eng.render_starburst(lights_a, WIDTH, HEIGHT, 50.0, 1.0, out=pinned_out.array)
+        ts = []
+        for _ in range(10):
+            eng.render_starburst(lights_a, WIDTH, HEIGHT, 50.0, 1.0, out=pinned_out.array)
+            ts.append(eng.stats()["last_trace_ms"])
+        starburst = {"gpu_frame_ms_device": sum(ts) / len(ts), "api": "lfb_render_starburst, 1920x1080, pentbig500_14 (bbox 340x350 texels)"}
+        if not args.no_cpu:
+            try:
+                from oracle import bindings as ob
+                if os.path.exists(ob.REF_SO):
+                    rng = np.random.default_rng(0)
+                    xs, ys = rng.integers(0, WIDTH, 64), rng.integers(0, HEIGHT, 64)
+                    t0 = time.perf_counter()
+                    ob.RefOracle().starburst_multi(tex, WIDTH, HEIGHT, [(0.45, 0.55)], [(1, 1, 1)], 50.0, 1.0, xs, ys)
+                    per_px = (time.perf_counter() - t0) / 64
+                    starburst.update(reference_ms_per_pixel_1thread=per_px * 1e3, reference_frame_s_1thread_extrapolated=per_px * WIDTH * HEIGHT,
+                                     reference_sample="PathTracer::raytrace_starburst at 64 random pixels, one host thread")
+            except Exception as exc:
+                starburst["reference_error"] = repr(exc)[:200]
+
     peaks = eng.probe_peaks() if rank == 0 else None
     line = None
     if rank == 0:
@@ -444,6 +469,7 @@ def run_ours(args):
                     "ms_per_step": e2e_s / args.steps * 1e3, "api": "lfb_render_ghosts (F64x3, stride 24 = HDRImageBuffer layout)"
                     if world == 1 else "ShardedFlare.render + reduce + finalize + D2H"},
             "e2e_async": e2e_async,
+            "starburst": starburst,
             "e2e_rgba8": e2e_rgba8,
             "gpu_launches": int(launches),
             "clocks": clocks.report(),
