@@ -102,6 +102,13 @@ def test_output_layouts(engine, apertures):
     assert d2.any() and np.array_equal(padded[:, :, :3], d2)
     f32 = engine.render_ghosts(lt, g, elem=capi.F32x3)
     assert np.array_equal(f32, d2.astype(np.float32))
+    # additive in the grid modes too (FP32 exact kernel), into a float32 buffer
+    x = capi.make_params(capi.MODE_EXACT_GRID, 200, 120, grid_n=48, pair_set=capi.PAIRS_ALL, include_direct=1, px_per_unit=0.5)
+    lx = [capi.make_light(0.45, 0.55, theta=0.06)]
+    once = engine.render_ghosts(lx, x, elem=capi.F32x3)
+    twice = once.copy()
+    engine.render_ghosts(lx, x, out=twice, elem=capi.F32x3, additive=True)
+    assert once.any() and np.array_equal(twice, once + once)
 
 
 # ---------------------------------------------------------------------------------------------
