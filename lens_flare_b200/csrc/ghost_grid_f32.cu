@@ -40,7 +40,6 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
       const unsigned nb = blocks2(1, 1, bt / 16);
       if (bt == 64) xf32::exact_splat3_kernel<24, 64><<<nb, 64, 0, s>>>(jobs, progs, g, tex, accum);
       else if (bt == 256) xf32::exact_splat3_kernel<6, 256><<<nb, 256, 0, s>>>(jobs, progs, g, tex, accum);
-      else if (g.pad == 7) xf32::exact_splat3_kernel<14, 128><<<nb, 128, 0, s>>>(jobs, progs, g, tex, accum);
       else xf32::exact_splat3_kernel<12, 128><<<nb, 128, 0, s>>>(jobs, progs, g, tex, accum);
       return cudaGetLastError();
     }
