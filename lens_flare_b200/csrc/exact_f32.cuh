@@ -579,10 +579,7 @@ __global__ void __launch_bounds__(kThreads) prefix_kernel(const Job* __restrict_
                                                           const float* __restrict__ tex, float4* __restrict__ prefix) {
   __shared__ Step s_prog[LFB_MAX_STEPS];
   const int half_rows = (g.N + 1) / 2;
-  const int patches_x = (g.N + 15) / 16;
-  const int patches_per_slot = patches_x * ((half_rows + 15) / 16);
-  const int slot = blockIdx.x / patches_per_slot;
-  const int patch = blockIdx.x - slot * patches_per_slot;
+  const int slot = blockIdx.z;  // 3-D grid (patch column, patch row, slot)
   const Job& J = slots[slot];
   const int n_steps = J.n_steps;  // forward refractions 0 .. n_surf-1 (the stop included), no sensor step
   const int tid = threadIdx.x;
@@ -592,7 +589,7 @@ __global__ void __launch_bounds__(kThreads) prefix_kernel(const Job* __restrict_
     for (int q = tid; q < n_steps * 3; q += kThreads) dst[q] = __ldg(src + q);
   }
   __syncthreads();
-  const int a = (patch % patches_x) * 16 + (tid & 15), bp = (patch / patches_x) * 16 + (tid >> 4);
+  const int a = blockIdx.x * 16 + (tid & 15), bp = blockIdx.y * 16 + (tid >> 4);
   if (a >= g.N || bp >= half_rows) return;
   const int b = g.N - 1 - bp;
   const size_t ray = (size_t)bp * g.N + a;
@@ -773,11 +770,9 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat3_kernel(const Job* __res
   __shared__ Step s_prog[LFB_MAX_STEPS];
   __shared__ unsigned long long s_tile[(BT / 32) * kWarpTilePx * 3];
 
+  // 3-D grid (patch column, patch row, job): no integer divisions in the prologue every warp pays
   const int half_rows = (g.N + 1) / 2;
-  const int patches_x = (g.N + 15) / 16;
-  const int patches_per_job = patches_x * ((half_rows + PH - 1) / PH);
-  const int job_id = blockIdx.x / patches_per_job;
-  const int patch = blockIdx.x - job_id * patches_per_job;
+  const int job_id = blockIdx.z;
   const Job& J = jobs[job_id];
   const int n_steps = J.n_steps;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -795,7 +790,7 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat3_kernel(const Job* __res
   PM.sx = J.f_sx; PM.sy = J.f_sy; PM.cs = J.f_cs; PM.sn = J.f_sn; PM.ppu = J.f_ppu;
   const bool bilinear = g.splat == LFB_SPLAT_BILINEAR;
 
-  const int a = (patch % patches_x) * 16 + (tid & 15), bp = (patch / patches_x) * PH + (tid >> 4);
+  const int a = blockIdx.x * 16 + (tid & 15), bp = blockIdx.y * PH + (tid >> 4);
   const int b = g.N - 1 - bp;
   int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
   float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -37,7 +37,9 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
     static int warp_mode = -1;
     if (warp_mode < 0) { const char* env = getenv("LFB_EXACT_WARP"); warp_mode = env ? atoi(env) : 1; }
     if (warp_mode && g.patch <= 1) {  // v6: warp-autonomous splat (default)
-      const unsigned nb = blocks2(1, 1, bt / 16);
+      const int rows = bt / 16;
+      const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + rows - 1) / rows, n_jobs);  // (patch column, patch row, job)
+      if (nb.y > 65535u || nb.z > 65535u) return cudaErrorInvalidConfiguration;
       if (bt == 64) xf32::exact_splat3_kernel<24, 64><<<nb, 64, 0, s>>>(jobs, progs, g, tex, accum);
       else if (bt == 256) xf32::exact_splat3_kernel<6, 256><<<nb, 256, 0, s>>>(jobs, progs, g, tex, accum);
       else xf32::exact_splat3_kernel<12, 128><<<nb, 128, 0, s>>>(jobs, progs, g, tex, accum);
@@ -82,7 +84,8 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
 cudaError_t launch_prefix_f32(const Job* slots, const Step* progs, int n_slots, const FrameGeom& g, const float* tex, float4* prefix,
                               cudaStream_t s) {
   if (n_slots <= 0) return cudaSuccess;
-  const unsigned nb = (unsigned)n_slots * (unsigned)(((g.N + 15) / 16) * (((g.N + 1) / 2 + 15) / 16));
+  const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + 15) / 16, n_slots);  // (patch column, patch row, slot)
+  if (nb.z > 65535u) return cudaErrorInvalidConfiguration;
   xf32::prefix_kernel<<<nb, xf32::kThreads, 0, s>>>(slots, progs, g, tex, prefix);
   return cudaGetLastError();
 }
