@@ -155,6 +155,13 @@ struct lfb_engine {
   bool use_prefix = true;            // LFB_EXACT_PREFIX=0 disables
   size_t prefix_budget = (size_t)40 << 30;  // bytes of HBM the cache may take (LFB_PREFIX_BUDGET_MB)
   bool frame_has_prefix = false;
+  // ghost families (v7): one job per (light, lambda, first reflection j) of the frame
+  Job* d_fams = nullptr;  Job* h_fams = nullptr;
+  Step* d_fam_progs = nullptr;  Step* h_fam_progs = nullptr;
+  int fams_cap = 0, n_fams = 0;
+  bool use_family = true;            // LFB_EXACT_FAMILY=0: always one job per ghost pair (v6)
+  bool force_family = false;         // LFB_EXACT_FAMILY=1: always families; unset: by frame size (see render_grid_device)
+  bool frame_has_family = false;
   float2* d_lut = nullptr;   // reflectance tables, kLutSize entries per (lambda, surface, direction)
   bool use_lut = true;       // LFB_EXACT_WEIGHTS=closed selects the closed-form two-pass kernel instead
   int min_blocks = 6;        // register-allocation target of the FP32 exact kernel, CTAs/SM (LFB_EXACT_MINB=4|5|6)
@@ -317,40 +324,50 @@ void build_reflectance_tables(const lfb_lens& L, std::vector<float2>& out) {
 // direct path), with every ray-independent quantity of each step computed here, once.
 // from_reflection: the program starts ON surface j with the first reflection (the forward sweep 0 .. j-1 comes from the
 // prefix cache).  prefix_only: just the forward sweep 0 .. n-1 (no reflections, no sensor) -- what prefix_kernel traces.
+// One step of a program: the ray arrives on surface k coming from surface prev_k (k = n_surfaces: the sensor plane).
+Step make_step(const lfb_lens& L, const DevLens& D, int lam, int k, int op, bool forward, int prev_k) {
+  const int n = L.n_surfaces, stop = L.stop_index;
+  Step S;
+  memset(&S, 0, sizeof(S));
+  S.lut = (lam * L.n_surfaces + (k < n ? k : 0)) * 2 + (forward ? 0 : 1);
+  S.dz = (float)(D.zv_d[prev_k] - D.zv_d[k]);
+  S.eta = S.eta2 = 1.f;
+  S.semi2 = INFINITY;  // the stop and the sensor are unbounded planes (the mask bounds the stop)
+  if (k == n) { S.op = STEP_SENSOR; return S; }
+  if (k == stop && op != STEP_REFLECT) { S.op = STEP_STOP; return S; }
+  S.c = L.curvature[k];
+  S.semi2 = L.semi_aperture[k] * L.semi_aperture[k];
+  const float na = k == 0 ? 1.f : L.ior[lam][k - 1], nb = L.ior[lam][k];
+  const float n0 = forward ? na : nb, n2 = forward ? nb : na;
+  S.n0 = n0; S.n2 = n2;
+  S.eta = n0 / n2; S.eta2 = S.eta * S.eta;
+  S.op = (op == STEP_REFRACT && n0 == n2) ? STEP_PASS : op;
+  const double lam0 = L.coating_lambda0_nm[k];
+  if (lam0 > 0 && n0 != n2) {
+    double n1 = sqrt((double)n0 * (double)n2);
+    if (n1 < 1.38) n1 = 1.38;  // MgF2 floor
+    S.n1 = (float)n1;
+    S.e1sq = (float)(((double)n0 / n1) * ((double)n0 / n1));
+    S.phase = (float)(3.14159265358979323846 * lam0 / (double)L.lambda_nm[lam]);  // 4 pi n1 d1 / lambda, d1 = lambda0 / (4 n1)
+  }
+  return S;
+}
+
+// from_reflection: the program starts ON surface j with the first reflection (the forward sweep 0 .. j-1 comes from the
+// prefix cache).  prefix_only: the forward sweep 0 .. n-1 followed by the sensor step (prefix_kernel traces the first n
+// steps; the sensor step serves the direct path and the forks of the family kernel); returns n.
 int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, Step* out, bool from_reflection = false,
                   bool prefix_only = false) {
-  const int n = L.n_surfaces, stop = L.stop_index;
+  const int n = L.n_surfaces;
   int ns = 0, prev = from_reflection ? j : 0;
   auto push = [&](int k, int op, bool forward) {
-    Step S;
-    memset(&S, 0, sizeof(S));
-    S.lut = (lam * L.n_surfaces + (k < n ? k : 0)) * 2 + (forward ? 0 : 1);
-    S.dz = (float)(D.zv_d[prev] - D.zv_d[k]);
+    out[ns++] = make_step(L, D, lam, k, op, forward, prev);
     prev = k;
-    S.eta = S.eta2 = 1.f;
-    S.semi2 = INFINITY;  // the stop and the sensor are unbounded planes (the mask bounds the stop)
-    if (k == n) { S.op = STEP_SENSOR; out[ns++] = S; return; }
-    if (k == stop && op != STEP_REFLECT) { S.op = STEP_STOP; out[ns++] = S; return; }
-    S.c = L.curvature[k];
-    S.semi2 = L.semi_aperture[k] * L.semi_aperture[k];
-    const float na = k == 0 ? 1.f : L.ior[lam][k - 1], nb = L.ior[lam][k];
-    const float n0 = forward ? na : nb, n2 = forward ? nb : na;
-    S.n0 = n0; S.n2 = n2;
-    S.eta = n0 / n2; S.eta2 = S.eta * S.eta;
-    S.op = (op == STEP_REFRACT && n0 == n2) ? STEP_PASS : op;
-    const double lam0 = L.coating_lambda0_nm[k];
-    if (lam0 > 0 && n0 != n2) {
-      double n1 = sqrt((double)n0 * (double)n2);
-      if (n1 < 1.38) n1 = 1.38;  // MgF2 floor
-      S.n1 = (float)n1;
-      S.e1sq = (float)(((double)n0 / n1) * ((double)n0 / n1));
-      S.phase = (float)(3.14159265358979323846 * lam0 / (double)L.lambda_nm[lam]);  // 4 pi n1 d1 / lambda, d1 = lambda0 / (4 n1)
-    }
-    out[ns++] = S;
   };
   if (prefix_only) {
     for (int k = 0; k < n; k++) push(k, STEP_REFRACT, true);
-    return ns;
+    push(n, STEP_SENSOR, true);
+    return n;
   }
   if (i < 0) {
     for (int k = 0; k < n; k++) push(k, STEP_REFRACT, true);
@@ -363,6 +380,21 @@ int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, St
     for (int k = i + 1; k < n; k++) push(k, STEP_REFRACT, true);
   }
   push(n, STEP_SENSOR, true);
+  return ns;
+}
+
+// The program of a ghost family (exact_f32.cuh, v7): first reflection at j, then for k = j-1 .. 0 the backward step at k
+// followed by the fork step (reflection at k seen from behind; op = -1 when ghost (k, j) is not in `mask`).
+int build_family_program(const lfb_lens& L, const DevLens& D, int lam, int j, unsigned mask, Step* out) {
+  int ns = 0, prev = j;
+  out[ns++] = make_step(L, D, lam, j, STEP_REFLECT, true, j);
+  for (int k = j - 1; k >= 0; k--) {
+    out[ns++] = make_step(L, D, lam, k, STEP_REFRACT, false, prev);
+    prev = k;
+    Step fork = make_step(L, D, lam, k, STEP_REFLECT, false, k);
+    if (!((mask >> k) & 1u) || k == L.stop_index) fork.op = -1;
+    out[ns++] = fork;
+  }
   return ns;
 }
 
@@ -418,10 +450,11 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
   std::vector<int> slot_of;   // [light * n_lambda + lambda] -> slot or -1
   std::vector<JobId> slot_ids;
   e->frame_has_prefix = false;
+  e->frame_has_family = false;
   if (want_progs && e->use_lut && e->use_prefix) {
     slot_of.assign((size_t)std::max(n_lights, 1) * e->lens.n_lambda, -1);
     for (int q = 0; q < n; q++)
-      if (ids[q].i >= 0) {
+      if (ids[q].i >= 0 || e->use_family) {  // with families the direct path is splatted by the prefix kernel itself
         int& sl = slot_of[(size_t)ids[q].light * e->lens.n_lambda + ids[q].lambda];
         if (sl < 0) { sl = (int)slot_ids.size(); slot_ids.push_back({ids[q].light, -1, -1, ids[q].lambda}); }
       }
@@ -450,6 +483,50 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
     for (int sl = 0; sl < ns; sl++) {
       fill_job(e, P, lights[slot_ids[sl].light], slot_ids[sl], &e->h_slots[sl]);
       e->h_slots[sl].n_steps = build_program(e->lens, e->dev_lens, slot_ids[sl].lambda, -1, -1, e->h_slot_progs + (size_t)sl * LFB_MAX_STEPS, false, true);
+      e->h_slots[sl].i = 0;  // set to 1 below when this shard owns the slot's direct path
+    }
+    // ghost families: the pairs (i, j) of a slot grouped by their first reflection j
+    e->frame_has_family = false;
+    if (e->use_family) {
+      struct Fam { int slot, j; unsigned mask; };
+      std::vector<Fam> fams;
+      std::vector<int> fam_of((size_t)ns * LFB_MAX_SURFACES, -1);
+      for (int q = 0; q < n; q++) {
+        const int sl = slot_of[(size_t)ids[q].light * e->lens.n_lambda + ids[q].lambda];
+        if (ids[q].i < 0) { e->h_slots[sl].i = 1; continue; }
+        int& f = fam_of[(size_t)sl * LFB_MAX_SURFACES + ids[q].j];
+        if (f < 0) { f = (int)fams.size(); fams.push_back({sl, ids[q].j, 0u}); }
+        fams[f].mask |= 1u << ids[q].i;
+      }
+      const int nf = (int)fams.size();
+      if (nf > e->fams_cap) {
+        if (e->d_fams) CU(cudaFree(e->d_fams));
+        if (e->h_fams) CU(cudaFreeHost(e->h_fams));
+        if (e->d_fam_progs) CU(cudaFree(e->d_fam_progs));
+        if (e->h_fam_progs) CU(cudaFreeHost(e->h_fam_progs));
+        e->d_fams = nullptr; e->h_fams = nullptr; e->d_fam_progs = nullptr; e->h_fam_progs = nullptr; e->fams_cap = 0;
+        CU(cudaMalloc((void**)&e->d_fams, sizeof(Job) * (size_t)nf));
+        CU(cudaHostAlloc((void**)&e->h_fams, sizeof(Job) * (size_t)nf, cudaHostAllocDefault));
+        CU(cudaMalloc((void**)&e->d_fam_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)nf));
+        CU(cudaHostAlloc((void**)&e->h_fam_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)nf, cudaHostAllocDefault));
+        e->fams_cap = nf;
+      }
+      for (int f = 0; f < nf; f++) {
+        const JobId& sid = slot_ids[fams[f].slot];
+        Job* FJ = &e->h_fams[f];
+        fill_job(e, P, lights[sid.light], sid, FJ);
+        FJ->slot = fams[f].slot;
+        FJ->j_first = fams[f].j;
+        FJ->i = (int)fams[f].mask;
+        FJ->j = fams[f].j;
+        FJ->n_steps = build_family_program(e->lens, e->dev_lens, sid.lambda, fams[f].j, fams[f].mask, e->h_fam_progs + (size_t)f * LFB_MAX_STEPS);
+      }
+      e->n_fams = nf;
+      if (nf > 0) {
+        CU(cudaMemcpyAsync(e->d_fams, e->h_fams, sizeof(Job) * (size_t)nf, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->d_fam_progs, e->h_fam_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)nf, cudaMemcpyHostToDevice, e->stream));
+      }
+      e->frame_has_family = true;
     }
     e->n_slots = ns;
     CU(cudaMemcpyAsync(e->d_slots, e->h_slots, sizeof(Job) * (size_t)ns, cudaMemcpyHostToDevice, e->stream));
@@ -495,12 +572,21 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
   const bool capturing = cap != cudaStreamCaptureStatusNone;
   if (clear_first) CU(cudaMemsetAsync(accum, 0, lfb_accum_bytes(P.width, P.height), e->stream));
   if (!capturing) CU(cudaEventRecord(e->ev_trace0, e->stream));
+  // Families do ~25 % less work but in 4x fewer, longer-lived CTAs: they win once the grid is many waves deep (cfg3 / cfg4:
+  // x1.3), and lose ~8 % on a frame as small as cfg2 (5 376 CTAs = 3.6 waves), where the per-pair kernel keeps the SMs fuller.
+  const long long fam_ctas = (long long)e->n_fams * ((P.grid_n + 15) / 16) * (((P.grid_n + 1) / 2 + 7) / 8);
+  const bool families = e->frame_has_prefix && e->frame_has_family && g.lut && (e->force_family || fam_ctas >= 16384);
   if (e->n_jobs > 0 && e->frame_has_prefix && g.lut) {
-    CU(launch_prefix_f32(e->d_slots, e->d_slot_progs, e->n_slots, g, e->d_tex, e->d_prefix, e->stream));
+    CU(launch_prefix_f32(e->d_slots, e->d_slot_progs, e->n_slots, g, e->d_tex, e->d_prefix, families ? accum : nullptr, e->stream));
     e->launches++;
     g.prefix = e->d_prefix;
   }
-  if (e->n_jobs > 0) {
+  if (families) {  // v7: one job per (light, lambda, first reflection); the direct path was splatted by the prefix kernel
+    if (e->n_fams > 0) {
+      CU(launch_family_f32(e->d_fams, e->d_fam_progs, e->n_fams, e->d_slots, e->d_slot_progs, g, e->d_tex, accum, e->stream));
+      e->launches++;
+    }
+  } else if (e->n_jobs > 0) {
     if (P.precision == LFB_FP64) CU(launch_trace_splat_f64(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
     else CU(launch_trace_splat_f32(e->d_jobs, e->d_progs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
     e->launches++;
@@ -600,6 +686,7 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   if (const char* env = getenv("LFB_EXACT_MINB")) e->min_blocks = atoi(env);
   if (const char* env = getenv("LFB_EXACT_WEIGHTS")) e->use_lut = strcmp(env, "closed") != 0;
   if (const char* env = getenv("LFB_EXACT_PREFIX")) e->use_prefix = atoi(env) != 0;
+  if (const char* env = getenv("LFB_EXACT_FAMILY")) { e->use_family = atoi(env) != 0; e->force_family = e->use_family; }
   if (const char* env = getenv("LFB_PREFIX_BUDGET_MB")) e->prefix_budget = (size_t)atoll(env) << 20;
   if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
   *out = e;
@@ -613,6 +700,9 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
   cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox); cudaFree(e->d_lut);
   cudaFree(e->d_slots); cudaFree(e->d_slot_progs); cudaFree(e->d_prefix);
+  cudaFree(e->d_fams); cudaFree(e->d_fam_progs);
+  if (e->h_fams) cudaFreeHost(e->h_fams);
+  if (e->h_fam_progs) cudaFreeHost(e->h_fam_progs);
   if (e->h_slots) cudaFreeHost(e->h_slots);
   if (e->h_slot_progs) cudaFreeHost(e->h_slot_progs);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }

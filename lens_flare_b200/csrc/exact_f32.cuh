@@ -565,6 +565,72 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat1_kernel(const Job*
   }
 }
 
+constexpr int kWarpTilePx = 64;  // per-warp shared-memory sensor tile (pixels)
+
+struct WarpSplat {  // what a warp needs to deposit its lanes' results
+  unsigned long long* tile;   // this warp's shared-memory tile
+  unsigned long long* accum;
+  int* bbox;
+  int W, H;
+  float ch0, ch1, ch2;
+  bool bilinear;
+};
+
+// Deposit one (ray, mirror image) result per lane; warp-collective (all 32 lanes call it).
+__device__ __forceinline__ void warp_splat(const WarpSplat& S, const PixMap& PM, bool alive, const RayOut& o, bool has_mirror, int lane) {
+  int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
+  float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 ww = make_float2(0.f, 0.f);
+  if (alive) {
+    int x0, y0, x1, y1;
+    if (o.wa > 0.f) {
+      to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
+      if (footprint(S.bilinear, pp.x, pp.y, S.W, S.H, x0, y0, x1, y1)) {
+        ww.x = o.wa; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+      }
+    }
+    if (o.wb > 0.f && has_mirror) {
+      to_pixel(PM, o.xs, -o.ys, pp.z, pp.w);
+      if (footprint(S.bilinear, pp.z, pp.w, S.W, S.H, x0, y0, x1, y1)) {
+        ww.y = o.wb; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+      }
+    }
+  }
+  const bool lands = ww.x > 0.f || ww.y > 0.f;
+  if (!__any_sync(0xffffffffu, lands)) return;
+  bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+  bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+  if (lane == 0) grow_bbox(S.bbox, bx0, by0, bx1, by1);
+  SplatCtx C;
+  C.tx0 = bx0; C.ty0 = by0;
+  C.tw = bx1 - bx0 + 1;
+  const int area = C.tw * (by1 - by0 + 1);
+  const bool use_tile = area <= kWarpTilePx;
+  C.tile = use_tile ? S.tile : nullptr;
+  C.accum = S.accum; C.W = S.W; C.H = S.H; C.bilinear = S.bilinear;
+  C.ch0 = S.ch0; C.ch1 = S.ch1; C.ch2 = S.ch2;
+  if (use_tile) {
+    for (int q = lane; q < 3 * area; q += 32) S.tile[q] = 0ull;
+    __syncwarp();
+  }
+  if (ww.x > 0.f) splat1(C, pp.x, pp.y, ww.x);
+  if (ww.y > 0.f) splat1(C, pp.z, pp.w, ww.y);
+  if (!use_tile) return;
+  __syncwarp();
+  const float inv_tw = frcp((float)C.tw);
+  for (int t = lane; t < area; t += 32) {
+    const int jy = (int)(((float)t + 0.5f) * inv_tw);  // t / tw, exact for these small integers
+    const int jx = t - jy * C.tw;
+    unsigned long long* dst = S.accum + 3 * ((size_t)(bx0 + jx) + (size_t)(by0 + jy) * S.W);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const unsigned long long v = S.tile[3 * t + c];
+      if (v) atomicAdd(dst + c, v);
+    }
+  }
+  __syncwarp();  // the tile is reused by the warp's next fork
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // v5: PREFIX SHARING.  Every ghost (i, j) of a light and wavelength begins with the same forward sweep through surfaces
 // 0 .. j-1 -- 28 ghosts re-trace it 28 times, and more than half of all executed steps are in it (most rays die late in
@@ -576,21 +642,24 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat1_kernel(const Job*
 // dz = +sqrt(1 - dx^2 - dy^2) (the sweep only travels forward).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) prefix_kernel(const Job* __restrict__ slots, const Step* __restrict__ progs, FrameGeom g,
-                                                          const float* __restrict__ tex, float4* __restrict__ prefix) {
+                                                          const float* __restrict__ tex, float4* __restrict__ prefix,
+                                                          unsigned long long* __restrict__ accum) {
   __shared__ Step s_prog[LFB_MAX_STEPS];
+  __shared__ unsigned long long s_tile[(kThreads / 32) * kWarpTilePx * 3];
   const int half_rows = (g.N + 1) / 2;
   const int slot = blockIdx.z;  // 3-D grid (patch column, patch row, slot)
   const Job& J = slots[slot];
-  const int n_steps = J.n_steps;  // forward refractions 0 .. n_surf-1 (the stop included), no sensor step
+  const int n_steps = J.n_steps;  // forward refractions 0 .. n_surf-1 (the stop included); step n_surf is the sensor
+  const bool do_direct = accum != nullptr && J.i != 0;  // this shard owns the slot's direct (unreflected) path: splat it too
   const int tid = threadIdx.x;
   {
     const float4* src = reinterpret_cast<const float4*>(progs + (size_t)slot * LFB_MAX_STEPS);
     float4* dst = reinterpret_cast<float4*>(s_prog);
-    for (int q = tid; q < n_steps * 3; q += kThreads) dst[q] = __ldg(src + q);
+    for (int q = tid; q < (n_steps + 1) * 3; q += kThreads) dst[q] = __ldg(src + q);
   }
   __syncthreads();
   const int a = blockIdx.x * 16 + (tid & 15), bp = blockIdx.y * 16 + (tid >> 4);
-  if (a >= g.N || bp >= half_rows) return;
+  const bool in_grid = a < g.N && bp < half_rows;
   const int b = g.N - 1 - bp;
   const size_t ray = (size_t)bp * g.N + a;
   MaskGeom M;
@@ -600,21 +669,35 @@ __global__ void __launch_bounds__(kThreads) prefix_kernel(const Job* __restrict_
   r.ox = fmaf((float)a + 0.5f, g.cell, -g.P); r.oy = fmaf((float)b + 0.5f, g.cell, -g.P); r.oz = 0.f;
   r.dx = J.f_sin_t; r.dy = 0.f; r.dz = J.f_cos_t; r.w = 1.f; r.ma = 1.f; r.mb = 1.f;
   RayOut o;
-  bool alive = true;
+  bool alive = in_grid;
   float4* base = prefix + (size_t)slot * g.n_surf * 2 * g.half_rays + ray;
 #pragma unroll 1
   for (int s = 0; s < n_steps; s++) {
     const Step& S = s_prog[s];
     if (alive) alive = propagate<false>(S, r, o);
-    float4* dst = base + (size_t)s * 2 * g.half_rays;
-    if (alive) {
-      dst[0] = make_float4(r.ox, r.oy, r.oz, r.w);
-      dst[g.half_rays] = make_float4(r.dx, r.dy, r.ma, r.mb);
-      alive = interact<2, true, false>(S, M, g.lut, r, o);
-    } else {
-      dst[0] = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+    if (in_grid) {
+      float4* dst = base + (size_t)s * 2 * g.half_rays;
+      if (alive) {
+        dst[0] = make_float4(r.ox, r.oy, r.oz, r.w);
+        dst[g.half_rays] = make_float4(r.dx, r.dy, r.ma, r.mb);
+      } else {
+        dst[0] = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+      }
     }
+    if (alive) alive = interact<2, true, false>(S, M, g.lut, r, o);
   }
+  if (!do_direct) return;
+  // the direct path: on to the sensor plane and splat, one warp at a time
+  if (alive) alive = propagate<false>(s_prog[n_steps], r, o);
+  if (alive) { o.xs = r.ox; o.ys = r.oy; o.wa = r.w * r.ma; o.wb = r.w * r.mb; }
+  PixMap PM;
+  PM.sx = J.f_sx; PM.sy = J.f_sy; PM.cs = J.f_cs; PM.sn = J.f_sn; PM.ppu = J.f_ppu;
+  WarpSplat WS;
+  WS.tile = s_tile + (tid >> 5) * (kWarpTilePx * 3);
+  WS.accum = accum; WS.bbox = g.bbox; WS.W = g.W; WS.H = g.H;
+  WS.ch0 = J.f_chan[0]; WS.ch1 = J.f_chan[1]; WS.ch2 = J.f_chan[2];
+  WS.bilinear = g.splat == LFB_SPLAT_BILINEAR;
+  warp_splat(WS, PM, alive, o, b != bp, tid & 31);
 }
 
 // The ghost kernel of v5: exact_splat1_kernel with the ray states loaded from the prefix cache (jobs whose slot is >= 0);
@@ -760,7 +843,6 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat2_kernel(const Job* __res
 // the one warp still tracing.  Here a warp owns its 32 ray pairs from trace to flush: survivors stay in registers (no
 // queue), the sensor tile is per warp (64 pixels), and the only CTA-wide barrier is the one after staging the program.
 // Flushing per warp instead of per CTA costs more global atomics (a few per warp), which the L2 absorbs.
-constexpr int kWarpTilePx = 64;
 
 template <int MINB, int BT>
 __global__ void __launch_bounds__(BT, MINB) exact_splat3_kernel(const Job* __restrict__ jobs, const Step* __restrict__ progs,
@@ -862,6 +944,98 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat3_kernel(const Job* __res
       const unsigned long long v = tile[3 * t + c];
       if (v) atomicAdd(dst + c, v);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// v7: GHOST FAMILIES.  After the forward sweep, the ghosts (i, j) of one (light, wavelength) with the same first
+// reflection j also share the BACKWARD sweep j-1, j-2, ... : ghost (i, j) leaves it at surface i.  One thread now follows
+// the whole family: it starts ON surface j (prefix cache), reflects, and walks backward; at every candidate surface k
+// it forks -- a copy of the ray reflects at k and runs the forward program k+1 .. n-1 to the sensor, where the warp
+// splats it -- and then continues backward through k.  28 ghost jobs per (light, wavelength) become 7 family jobs: the
+// per-warp fixed costs (launch prologue, state load, program staging), which dominated v6, are paid once per family, and
+// the backward sweeps are not repeated.  The arithmetic along every ghost path is unchanged, so the frame is bit-identical.
+//
+// Family program (shared memory): [0] reflect at j; then for k = j-1 .. 0 two steps: (backward step at k: refraction or
+// the stop plane, fork step: reflection at k seen from behind, op < 0 when ghost (k, j) is not wanted).  The forward
+// program of the slot (refractions 0 .. n-1 + sensor) supplies the suffix k+1 .. n of every fork.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MINB, int BT>
+__global__ void __launch_bounds__(BT, MINB) exact_family_kernel(const Job* __restrict__ fams, const Step* __restrict__ fam_progs,
+                                                                const Job* __restrict__ slots, const Step* __restrict__ slot_progs,
+                                                                FrameGeom g, const float* __restrict__ tex,
+                                                                unsigned long long* __restrict__ accum) {
+  constexpr int PH = BT / 16;
+  __shared__ Step s_fam[2 * LFB_MAX_SURFACES + 2];
+  __shared__ Step s_fwd[LFB_MAX_SURFACES + 2];
+  __shared__ unsigned long long s_tile[(BT / 32) * kWarpTilePx * 3];
+
+  const int half_rows = (g.N + 1) / 2;
+  const Job& J = fams[blockIdx.z];
+  const int slot = J.slot, j = J.j_first, n_fam = J.n_steps;
+  const int n_fwd = g.n_surf + 1;  // forward refractions 0 .. n-1 and the sensor
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int a = blockIdx.x * 16 + (tid & 15), bp = blockIdx.y * PH + (tid >> 4);
+  const int b = g.N - 1 - bp;
+  const bool in_grid = a < g.N && bp < half_rows;
+  {
+    const float4* src = reinterpret_cast<const float4*>(fam_progs + (size_t)blockIdx.z * LFB_MAX_STEPS);
+    float4* dst = reinterpret_cast<float4*>(s_fam);
+    for (int q = tid; q < n_fam * 3; q += BT) dst[q] = __ldg(src + q);
+    const float4* src2 = reinterpret_cast<const float4*>(slot_progs + (size_t)slot * LFB_MAX_STEPS);
+    float4* dst2 = reinterpret_cast<float4*>(s_fwd);
+    for (int q = tid; q < n_fwd * 3; q += BT) dst2[q] = __ldg(src2 + q);
+  }
+  __syncthreads();  // the only CTA-wide barrier
+
+  MaskGeom M;
+  M.tex = tex; M.tw = g.tex_w; M.th = g.tex_h;
+  M.su = g.mask_su; M.ou = g.mask_ou; M.sv = g.mask_sv; M.ov = g.mask_ov;
+  PixMap PM;
+  PM.sx = J.f_sx; PM.sy = J.f_sy; PM.cs = J.f_cs; PM.sn = J.f_sn; PM.ppu = J.f_ppu;
+  WarpSplat WS;
+  WS.tile = s_tile + (tid >> 5) * (kWarpTilePx * 3);
+  WS.accum = accum; WS.bbox = g.bbox; WS.W = g.W; WS.H = g.H;
+  WS.ch0 = J.f_chan[0]; WS.ch1 = J.f_chan[1]; WS.ch2 = J.f_chan[2];
+  WS.bilinear = g.splat == LFB_SPLAT_BILINEAR;
+
+  RayState r;
+  RayOut o;
+  bool alive = false;
+  if (in_grid) {
+    const float4* src = g.prefix + ((size_t)(slot * g.n_surf + j) * 2) * g.half_rays + ((size_t)bp * g.N + a);
+    const float4 s0 = __ldg(src);
+    alive = s0.x == s0.x;  // NaN: the ray died in the forward sweep before reaching surface j
+    if (alive) {
+      const float4 s1 = __ldg(src + g.half_rays);
+      r.ox = s0.x; r.oy = s0.y; r.oz = s0.z; r.w = s0.w;
+      r.dx = s1.x; r.dy = s1.y; r.ma = s1.z; r.mb = s1.w;
+      r.dz = fsqrt(fmaxf(fmaf(-r.dx, r.dx, fmaf(-r.dy, r.dy, 1.f)), 0.f));
+      alive = interact<2, true, false>(s_fam[0], M, g.lut, r, o);  // the first reflection, at j
+    }
+  }
+  if (!__any_sync(0xffffffffu, alive)) return;  // nothing below involves other warps
+#pragma unroll 1
+  for (int e = 0; e < j; e++) {
+    const int k = j - 1 - e;
+    const Step& Sb = s_fam[1 + 2 * e];
+    const Step& Sf = s_fam[2 + 2 * e];
+    if (alive) alive = propagate<false>(Sb, r, o);  // onto surface k, travelling backward
+    if (Sf.op >= 0) {  // ghost (k, j): fork a copy that reflects here and runs forward to the sensor
+      RayState q = r;
+      RayOut oq;
+      bool a2 = alive;
+      if (a2) a2 = interact<2, true, false>(Sf, M, g.lut, q, oq);
+#pragma unroll 1
+      for (int s = k + 1; s < n_fwd; s++) {
+        if (a2) a2 = propagate<false>(s_fwd[s], q, oq);
+        if (a2) a2 = interact<2, true, false>(s_fwd[s], M, g.lut, q, oq);
+      }
+      if (a2) { oq.xs = q.ox; oq.ys = q.oy; oq.wa = q.w * q.ma; oq.wb = q.w * q.mb; }
+      warp_splat(WS, PM, a2, oq, b != bp, lane);
+    }
+    if (alive) alive = interact<2, true, false>(Sb, M, g.lut, r, o);  // on through surface k (or the stop's mask)
+    if (!__any_sync(0xffffffffu, alive)) return;
   }
 }
 

@@ -82,11 +82,28 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
 }
 
 cudaError_t launch_prefix_f32(const Job* slots, const Step* progs, int n_slots, const FrameGeom& g, const float* tex, float4* prefix,
-                              cudaStream_t s) {
+                              unsigned long long* accum_for_direct, cudaStream_t s) {
   if (n_slots <= 0) return cudaSuccess;
   const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + 15) / 16, n_slots);  // (patch column, patch row, slot)
   if (nb.z > 65535u) return cudaErrorInvalidConfiguration;
-  xf32::prefix_kernel<<<nb, xf32::kThreads, 0, s>>>(slots, progs, g, tex, prefix);
+  xf32::prefix_kernel<<<nb, xf32::kThreads, 0, s>>>(slots, progs, g, tex, prefix, accum_for_direct);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_family_f32(const Job* fams, const Step* fam_progs, int n_fams, const Job* slots, const Step* slot_progs,
+                              const FrameGeom& g, const float* tex, unsigned long long* accum, cudaStream_t s) {
+  if (n_fams <= 0) return cudaSuccess;
+  static int cfg = -1;  // LFB_FAMILY_CFG: 0 = 128 threads / 10 CTAs per SM (default), 1 = 128 / 12, 2 = 64 / 20, 3 = 64 / 24, 4 = 256 / 5
+  if (cfg < 0) { const char* env = getenv("LFB_FAMILY_CFG"); cfg = env ? atoi(env) : 0; }
+  const int bt = (cfg == 2 || cfg == 3) ? 64 : (cfg == 4 ? 256 : 128);
+  const int rows = bt / 16;
+  const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + rows - 1) / rows, n_fams);  // (patch column, patch row, family)
+  if (nb.y > 65535u || nb.z > 65535u) return cudaErrorInvalidConfiguration;
+  if (cfg == 1) xf32::exact_family_kernel<12, 128><<<nb, 128, 0, s>>>(fams, fam_progs, slots, slot_progs, g, tex, accum);
+  else if (cfg == 2) xf32::exact_family_kernel<20, 64><<<nb, 64, 0, s>>>(fams, fam_progs, slots, slot_progs, g, tex, accum);
+  else if (cfg == 3) xf32::exact_family_kernel<24, 64><<<nb, 64, 0, s>>>(fams, fam_progs, slots, slot_progs, g, tex, accum);
+  else if (cfg == 4) xf32::exact_family_kernel<5, 256><<<nb, 256, 0, s>>>(fams, fam_progs, slots, slot_progs, g, tex, accum);
+  else xf32::exact_family_kernel<10, 128><<<nb, 128, 0, s>>>(fams, fam_progs, slots, slot_progs, g, tex, accum);
   return cudaGetLastError();
 }
 

@@ -102,7 +102,10 @@ cudaError_t launch_trace_splat_f64(const Job* jobs, int n_jobs, const FrameGeom&
                                    unsigned long long* accum, cudaStream_t s);
 // FP32 EXACT_GRID prefix pass: trace the forward sweep of every (light, lambda) slot once and cache the ray states
 cudaError_t launch_prefix_f32(const Job* slots, const Step* progs, int n_slots, const FrameGeom& g, const float* tex, float4* prefix,
-                              cudaStream_t s);
+                              unsigned long long* accum_for_direct, cudaStream_t s);
+// FP32 EXACT_GRID ghost families (v7): one job per (light, lambda, first reflection j)
+cudaError_t launch_family_f32(const Job* fams, const Step* fam_progs, int n_fams, const Job* slots, const Step* slot_progs,
+                              const FrameGeom& g, const float* tex, unsigned long long* accum, cudaStream_t s);
 cudaError_t launch_trace_dump_f32(const Job* job, const Step* prog, const FrameGeom& g, int mode, const float* tex,
                                   lfb_ray_hit* out, cudaStream_t s);
 cudaError_t launch_trace_dump_f64(const Job* job, const FrameGeom& g, int mode, const float* tex, lfb_ray_hit* out,
