@@ -27,7 +27,9 @@
 //   exact_splat_kernel   v3  two passes (geometry, then survivors with closed-form Fresnel)     LFB_EXACT_WEIGHTS=closed
 //   exact_splat1_kernel  v4  one pass with tabulated reflectances, CTA-level queue and tile      LFB_EXACT_PREFIX=0
 //   exact_splat2_kernel  v5  + prefix cache                                                      LFB_EXACT_WARP=0
-//   exact_splat3_kernel  v6  + warp-autonomous splat (default)
+//   exact_splat3_kernel  v6  + warp-autonomous splat (default for small frames)                  LFB_EXACT_FAMILY=0
+//   exact_family_kernel  v7  ghost families: one thread per (ray, first reflection), forks at every second reflection
+//                            (default from 16 384 family CTAs up; LFB_EXACT_FAMILY=1 forces it)
 // Parity: per-ray and image tolerances against the double-precision oracle are in tests/test_gpu_parity.py; the FP64
 // kernels in ghost_grid_impl.cuh remain the bit-exact instruments.
 #pragma once
