@@ -386,9 +386,10 @@ int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, St
 // The program of a ghost family (exact_f32.cuh, v7): first reflection at j, then for k = j-1 .. 0 the backward step at k
 // followed by the fork step (reflection at k seen from behind; op = -1 when ghost (k, j) is not in `mask`).
 int build_family_program(const lfb_lens& L, const DevLens& D, int lam, int j, unsigned mask, Step* out) {
-  int ns = 0, prev = j;
+  int ns = 0, prev = j, kmin = 0;
+  while (kmin < j && !((mask >> kmin) & 1u)) kmin++;  // the backward sweep ends at the lowest wanted second reflection
   out[ns++] = make_step(L, D, lam, j, STEP_REFLECT, true, j);
-  for (int k = j - 1; k >= 0; k--) {
+  for (int k = j - 1; k >= kmin; k--) {
     out[ns++] = make_step(L, D, lam, k, STEP_REFRACT, false, prev);
     prev = k;
     Step fork = make_step(L, D, lam, k, STEP_REFLECT, false, k);
@@ -497,6 +498,25 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
         int& f = fam_of[(size_t)sl * LFB_MAX_SURFACES + ids[q].j];
         if (f < 0) { f = (int)fams.size(); fams.push_back({sl, ids[q].j, 0u}); }
         fams[f].mask |= 1u << ids[q].i;
+      }
+      // LFB_FAMILY_SPLIT = m: at most m forks per family job (more, shorter CTAs for small frames; the part of the backward
+      // sweep above a chunk's forks is then repeated per chunk)
+      if (const char* env = getenv("LFB_FAMILY_SPLIT")) {
+        const int m = atoi(env);
+        if (m > 0) {
+          std::vector<Fam> split;
+          for (const Fam& f : fams) {
+            unsigned cur = 0;
+            int cnt = 0;
+            for (int k = f.j - 1; k >= 0; k--) {
+              if (!((f.mask >> k) & 1u)) continue;
+              cur |= 1u << k;
+              if (++cnt == m) { split.push_back({f.slot, f.j, cur}); cur = 0; cnt = 0; }
+            }
+            if (cnt) split.push_back({f.slot, f.j, cur});
+          }
+          fams.swap(split);
+        }
       }
       const int nf = (int)fams.size();
       if (nf > e->fams_cap) {

@@ -1017,8 +1017,9 @@ __global__ void __launch_bounds__(BT, MINB) exact_family_kernel(const Job* __res
     }
   }
   if (!__any_sync(0xffffffffu, alive)) return;  // nothing below involves other warps
+  const int n_back = (n_fam - 1) >> 1;  // backward surfaces in this job's program: j-1 .. down to its lowest fork
 #pragma unroll 1
-  for (int e = 0; e < j; e++) {
+  for (int e = 0; e < n_back; e++) {
     const int k = j - 1 - e;
     const Step& Sb = s_fam[1 + 2 * e];
     const Step& Sf = s_fam[2 + 2 * e];
