@@ -86,11 +86,12 @@ __device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogu
   const double dx = f.org_x - (double)x, dy = f.org_y - (double)y, dist = sqrt(dx * dx + dy * dy);
   if (dist > (double)f.tw / 2.0) {  // suppression :983-989
     const double factor = ((double)f.tw / 2.0) / dist;
-    I = pow(factor, 8.0) * I;
+    const double f2 = factor * factor, f4 = f2 * f2;
+    I = (f4 * f4) * I;  // pow(factor, 8.0)
   } else if (dist <= f.flare_radius) {  // amplification :990-996
     I = pow(I, dist / f.flare_radius);
   }
-  const double s = pow(I, f.exponent);
+  const double s = f.exponent == 2.0 ? I * I : (f.exponent == 1.0 ? I : pow(I, f.exponent));  // the usual -i values, exactly
   // calculate_irradiance_falloff :1030-1052; the reference's 16 random samples of the pixel -> its 4x4 stratified midpoints
   double fall[3] = {0.0, 0.0, 0.0};
   for (int l = 0; l < E.n_lights; l++) {
