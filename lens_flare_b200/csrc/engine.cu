@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -215,6 +216,7 @@ namespace {
 // The lens tables live in __constant__ memory, one copy per device: the engine that last
 // uploaded them owns them, others re-upload before launching.
 const lfb_engine* g_const_owner[64] = {nullptr};
+std::mutex g_const_mutex;  // engines are single-threaded, but two engines of one device may live on two threads
 
 int bind(lfb_engine* e) {
   if (!e) return fail(LFB_ERR_INVALID, "engine is NULL");
@@ -223,6 +225,7 @@ int bind(lfb_engine* e) {
 }
 
 int upload_constants(lfb_engine* e) {
+  std::lock_guard<std::mutex> lock(g_const_mutex);
   if (e->device < 64 && g_const_owner[e->device] == e) return LFB_OK;
   CU(upload_lens_f32(e->dev_lens, e->stream));
   CU(upload_lens_f64(e->dev_lens, e->stream));
