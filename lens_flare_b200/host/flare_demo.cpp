@@ -1,5 +1,5 @@
 // flare_demo.cpp -- the reference application's flare flags on top of the C++ facade:
-//   flare_demo -r W H -y ghost_aperture.png [-x starburst_aperture.png] [-s ns_x ns_y] [-m ref|paraxial|exact] [-g N] [-f out.pfm]
+//   flare_demo -r W H -y ghost_aperture.png [-x starburst_aperture.png] [-s ns_x ns_y] [-m ref|paraxial|exact] [-g N] [-f out.pfm|out.png]
 // (-r, -x, -y, -f as in src/application/main.cpp:87, 135-152).  Prints frame statistics as one JSON line.
 #include <cmath>
 #include <cstdio>
@@ -8,6 +8,8 @@
 #include <string>
 
 #include "flare_pathtracer.hpp"
+#include "png_reader.hpp"
+#include "png_writer.hpp"
 
 int main(int argc, char** argv) {
   size_t W = 512, H = 512;
@@ -23,6 +25,20 @@ int main(int argc, char** argv) {
       for (float v : t.aperture) bytes += (unsigned long long)(v * 255.0f + 0.5f);
       std::printf("{\"w\": %zu, \"h\": %zu, \"total\": %.17g, \"bbox\": [%d, %d, %d, %d], \"byte_sum\": %llu}\n", t.width, t.height,
                   t.total_value, t.min_x, t.min_y, t.max_x, t.max_y, bytes);
+      return 0;
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "flare_demo: %s\n", e.what());
+      return 1;
+    }
+  }
+  if (argc == 4 && std::string(argv[1]) == "--png-copy") {  // host-only: decode -> save_image (bottom-up rows, alpha 255)
+    try {
+      std::vector<unsigned char> red;
+      unsigned w = 0, h = 0;
+      lfb::read_png_red(argv[2], red, w, h);
+      std::vector<uint32_t> frame((size_t)w * h);
+      for (size_t i = 0; i < frame.size(); i++) frame[i] = red[i] | ((uint32_t)(red[i] / 2) << 8) | ((uint32_t)(255 - red[i]) << 16);
+      lfb::save_image(argv[3], frame.data(), w, h, true);
       return 0;
     } catch (const std::exception& e) {
       std::fprintf(stderr, "flare_demo: %s\n", e.what());
@@ -93,7 +109,12 @@ int main(int argc, char** argv) {
       std::printf("{\"ghost_plus_starburst_sum\": [%.17g, %.17g, %.17g], \"starburst_ms\": %.4f, \"rgba8_byte_sum\": %llu, \"frame_ms\": %.4f}\n",
                   ssum[0], ssum[1], ssum[2], pt.last_trace_ms(), bytes, pt.last_frame_ms());
     }
-    if (!out.empty()) {  // PFM, bottom row first -- the same vertical flip the reference applies on save (raytraced_renderer.cpp:739-742)
+    const bool out_png = out.size() > 4 && out.compare(out.size() - 4, 4, ".png") == 0;
+    if (out_png) {  // the tone-mapped flare frame, as save_image writes it (raytraced_renderer.cpp:717-755)
+      std::vector<uint32_t> rgba;
+      pt.render_frame(rgba, nullptr, !star_png.empty(), true);  // rows already bottom-up
+      lfb::save_image(out, rgba.data(), W, H, false);
+    } else if (!out.empty()) {  // PFM, bottom row first -- the same vertical flip the reference applies on save (raytraced_renderer.cpp:739-742)
       FILE* f = std::fopen(out.c_str(), "wb");
       if (!f) { std::fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
       std::fprintf(f, "PF\n%zu %zu\n-1.0\n", W, H);

@@ -203,6 +203,28 @@ def test_cpp_png_reader_matches_reference_loader(native_lib, apertures, tmp_path
     assert bad.returncode == 1 and "cannot open" in bad.stderr
 
 
+def test_cpp_png_writer_save_image(native_lib, apertures, tmp_path):
+    """lfb::save_image (RaytracedRenderer::save_image, raytraced_renderer.cpp:717-755): rows bottom-up, alpha forced
+    to 255, RGBA8 PNG that a conforming decoder (PIL) and our own reader return byte for byte."""
+    import json
+    import subprocess
+    from PIL import Image
+    exe = _flare_demo()
+    u8 = apertures["pent_11_u8"][:123, :77].copy()  # ragged, non-square
+    Image.fromarray(u8, "L").save(tmp_path / "in.png")
+    subprocess.run([exe, "--png-copy", str(tmp_path / "in.png"), str(tmp_path / "out.png")], check=True)
+    img = Image.open(tmp_path / "out.png")
+    assert img.mode == "RGBA" and img.size == (u8.shape[1], u8.shape[0])
+    got = np.asarray(img)
+    flipped = u8[::-1]
+    want = np.stack([flipped, flipped // 2, 255 - flipped, np.full_like(u8, 255)], -1)
+    np.testing.assert_array_equal(got, want)
+    info = json.loads(subprocess.run([exe, "--png-info", str(tmp_path / "out.png")], check=True, capture_output=True, text=True).stdout)
+    assert (info["w"], info["h"]) == (u8.shape[1], u8.shape[0]) and info["byte_sum"] == int(u8.astype(np.int64).sum())
+    bad = subprocess.run([exe, "--png-copy", str(tmp_path / "in.png"), str(tmp_path / "no_such_dir" / "o.png")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "cannot write" in bad.stderr
+
+
 def test_header_is_plain_c(native_lib, tmp_path):
     """include/lfb200.h compiles as strict C99 and the library links and runs from a plain C program."""
     import subprocess
