@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LFB_ABI_VERSION 1
+#define LFB_ABI_VERSION 2
 #define LFB_MAX_SURFACES 16
 #define LFB_MAX_LAMBDA 64
 #define LFB_MAX_PEERS 16
@@ -98,11 +98,21 @@ typedef struct lfb_lens {
 
 /* One light.  Replaces PathTracer::axis_ray / angle_to_sun / flare_radiance
  * (pathtracer.h:131-135), which find_sun_pos (pathtracer.cpp:32-64) fills for the
- * single sun of the reference. */
+ * single sun of the reference.
+ *
+ * distance: 0 (a zero-initialised struct), negative or infinite = a directional light, the
+ * only kind the reference's flares fire for (pathtracer.cpp:35): every ray of the bundle
+ * enters along theta.  > 0 = a point light (the reference's PointLight, scene/light.h,
+ * which its flare code ignores) that many lens units in front of the first surface
+ * vertex, in the direction theta: the grid modes aim every entrance ray away from that
+ * point, and EXACT_GRID weighs it by the inverse-square/cosine falloff relative to the
+ * vertex, so distance -> infinity converges to the directional frame.  REF_QUADS and the
+ * starburst do not use it (the reference has no counterpart there). */
 typedef struct lfb_light {
   double ns_x, ns_y;  /* normalised screen position in [0,1]^2 (axis_ray) */
   float theta;        /* ray angle in the meridional plane, radians (angle_to_sun) */
   float radiance[3];
+  double distance;    /* 0: directional; > 0: point light at this distance (lens units) */
 } lfb_light;
 
 typedef struct lfb_params {

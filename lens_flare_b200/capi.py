@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 
 MAX_SURFACES = 16
 MAX_LAMBDA = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 MODE_REF_QUADS, MODE_PARAXIAL_GRID, MODE_EXACT_GRID = 0, 1, 2
@@ -52,7 +52,8 @@ class Lens(C.Structure):
 
 class Light(C.Structure):
     """lfb_light"""
-    _fields_ = [("ns_x", C.c_double), ("ns_y", C.c_double), ("theta", C.c_float), ("radiance", C.c_float * 3)]
+    _fields_ = [("ns_x", C.c_double), ("ns_y", C.c_double), ("theta", C.c_float), ("radiance", C.c_float * 3),
+                ("distance", C.c_double)]
 
 
 class Params(C.Structure):
@@ -78,9 +79,11 @@ class LfbError(RuntimeError):
         self.code = code
 
 
-def make_light(ns_x, ns_y, theta=None, radiance=(1.0, 1.0, 1.0)):
-    """theta=None -> the reference's angle_to_sun = atan(ns_y/ns_x) (pathtracer.cpp:50)."""
+def make_light(ns_x, ns_y, theta=None, radiance=(1.0, 1.0, 1.0), distance=0.0):
+    """theta=None -> the reference's angle_to_sun = atan(ns_y/ns_x) (pathtracer.cpp:50).  distance > 0: a point light
+    that many lens units in front of the first surface (0: directional, the reference's only flare source)."""
     lt = Light()
+    lt.distance = distance
     lt.ns_x, lt.ns_y = ns_x, ns_y
     lt.theta = float(np.float32(np.arctan(ns_y / ns_x))) if theta is None else theta
     lt.radiance[:] = radiance

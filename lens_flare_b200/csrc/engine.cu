@@ -415,11 +415,12 @@ void fill_job(const lfb_engine* e, const lfb_params& P, const lfb_light& lt, con
   J->sy = ceil(lt.ns_y * (double)P.height);
   J->ppu = P.px_per_unit > 0 ? P.px_per_unit : 0.4f;
   J->sin_t = sin((double)lt.theta); J->cos_t = cos((double)lt.theta);
+  J->inv_dist = (lt.distance > 0 && std::isfinite(lt.distance)) ? 1.0 / lt.distance : 0.0;  // 0: directional
   const double cell = 2 * e->lens.entrance_half_height / P.grid_n;
   const double area = cell * cell * J->ppu * J->ppu;
   for (int c = 0; c < 3; c++) J->chan[c] = (double)lt.radiance[c] * (double)e->lens.rgb_weight[id.lambda][c] * area;
   const double scale = ldexp(1.0, P.fixed_point_bits > 0 ? P.fixed_point_bits : 40);
-  J->f_sin_t = (float)J->sin_t; J->f_cos_t = (float)J->cos_t;
+  J->f_sin_t = (float)J->sin_t; J->f_cos_t = (float)J->cos_t; J->f_inv_dist = (float)J->inv_dist;
   J->f_sx = (float)J->sx; J->f_sy = (float)J->sy; J->f_cs = (float)J->cs; J->f_sn = (float)J->sn; J->f_ppu = (float)J->ppu;
   for (int c = 0; c < 3; c++) J->f_chan[c] = (float)J->chan[c] * (float)scale;
 }

@@ -205,11 +205,25 @@ __device__ __forceinline__ bool run_program(const Step* __restrict__ prog, int n
   return true;
 }
 
+// Entrance ray of grid point (x, y).  Directional light (inv_d = 0): the bundle's common direction.  Point light at
+// -D (sin t, 0, cos t): along v = (x/D + sin t, y/D, cos t), carrying the irradiance at the entrance point relative to the
+// vertex, |v|^-3 (lfb_light.distance).  The light lies in the plane y = 0, so the mirror pair (x, -y) stays a mirror pair.
+__device__ __forceinline__ void start_ray(RayState& r, float x, float y, float sin_t, float cos_t, float inv_d) {
+  r.ox = x; r.oy = y; r.oz = 0.f; r.dx = sin_t; r.dy = 0.f; r.dz = cos_t; r.w = 1.f; r.ma = 1.f; r.mb = 1.f;
+  if (inv_d != 0.f) {  // uniform per job
+    const float vx = fmaf(x, inv_d, sin_t), vy = __fmul_rn(y, inv_d);
+    const float q = fmaf(vx, vx, fmaf(vy, vy, __fmul_rn(cos_t, cos_t)));
+    const float rl = rsqrtf(q);
+    r.dx = __fmul_rn(vx, rl); r.dy = __fmul_rn(vy, rl); r.dz = __fmul_rn(cos_t, rl);
+    r.w = __fmul_rn(__fmul_rn(rl, rl), rl);
+  }
+}
+
 template <int WEIGHTS, bool MIRROR, bool FLAGS>
 __device__ __forceinline__ bool trace(const Step* __restrict__ prog, int n_steps, const MaskGeom& M, const float2* __restrict__ lut,
-                                      float x, float y, float sin_t, float cos_t, RayOut& o) {
+                                      float x, float y, float sin_t, float cos_t, float inv_d, RayOut& o) {
   RayState r;
-  r.ox = x; r.oy = y; r.oz = 0.f; r.dx = sin_t; r.dy = 0.f; r.dz = cos_t; r.w = 1.f; r.ma = 1.f; r.mb = 1.f;
+  start_ray(r, x, y, sin_t, cos_t, inv_d);
   if (FLAGS) { o.flags = 0; o.xa = o.ya = CUDART_NAN_F; }
   return run_program<WEIGHTS, MIRROR, FLAGS, false>(prog, n_steps, M, lut, r, o);
 }
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat_kernel(const Job* 
 
   const float P = g.P;
   const float cell = 2.f * P / (float)g.N;
-  const float sin_t = (float)J.sin_t, cos_t = (float)J.cos_t;
+  const float sin_t = (float)J.sin_t, cos_t = (float)J.cos_t, inv_d = (float)J.inv_dist;
   MaskGeom M;
   M.tex = tex; M.tw = g.tex_w; M.th = g.tex_h;
   {
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat_kernel(const Job* 
     float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a < g.N && bp < half_rows) {
       RayOut o;
-      if (trace<0, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o)) {
+      if (trace<0, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, inv_d, o)) {
         int x0, y0, x1, y1;
         if (o.wa > 0.f) {
           to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
@@ -393,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat_kernel(const Job* 
     const int la = (id & 0x3fff) % PW, lb = (id & 0x3fff) / PW;
     const int a = a0 + la, b = g.N - 1 - (b0 + lb);
     RayOut o;
-    if (!trace<1, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o)) continue;
+    if (!trace<1, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, inv_d, o)) continue;
     const float4 pp = s_qp[q];
     if ((id & (1u << 14)) && o.wa > 0.f) splat(C, pp.x, pp.y, o.wa);
     if ((id & (2u << 14)) && o.wb > 0.f) splat(C, pp.z, pp.w, o.wb);
@@ -474,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat1_kernel(const Job*
   __syncthreads();
 
   const float P = g.P, cell = g.cell;
-  const float sin_t = J.f_sin_t, cos_t = J.f_cos_t;
+  const float sin_t = J.f_sin_t, cos_t = J.f_cos_t, inv_d = J.f_inv_dist;
   MaskGeom M;
   M.tex = tex; M.tw = g.tex_w; M.th = g.tex_h;
   M.su = g.mask_su; M.ou = g.mask_ou; M.sv = g.mask_sv; M.ov = g.mask_ov;
@@ -493,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, MINB) exact_splat1_kernel(const Job*
     float2 ww = make_float2(0.f, 0.f);
     if (a < g.N && bp < half_rows) {
       RayOut o;
-      if (trace<2, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, o)) {
+      if (trace<2, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P), sin_t, cos_t, inv_d, o)) {
         int x0, y0, x1, y1;
         if (o.wa > 0.f) {
           to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
@@ -668,8 +682,7 @@ __global__ void __launch_bounds__(kThreads) prefix_kernel(const Job* __restrict_
   M.tex = tex; M.tw = g.tex_w; M.th = g.tex_h;
   M.su = g.mask_su; M.ou = g.mask_ou; M.sv = g.mask_sv; M.ov = g.mask_ov;
   RayState r;
-  r.ox = fmaf((float)a + 0.5f, g.cell, -g.P); r.oy = fmaf((float)b + 0.5f, g.cell, -g.P); r.oz = 0.f;
-  r.dx = J.f_sin_t; r.dy = 0.f; r.dz = J.f_cos_t; r.w = 1.f; r.ma = 1.f; r.mb = 1.f;
+  start_ray(r, fmaf((float)a + 0.5f, g.cell, -g.P), fmaf((float)b + 0.5f, g.cell, -g.P), J.f_sin_t, J.f_cos_t, J.f_inv_dist);
   RayOut o;
   bool alive = in_grid;
   float4* base = prefix + (size_t)slot * g.n_surf * 2 * g.half_rays + ray;
@@ -765,7 +778,7 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat2_kernel(const Job* __res
         }
       } else {
         alive = trace<2, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, g.cell, -g.P), fmaf((float)b + 0.5f, g.cell, -g.P),
-                                      J.f_sin_t, J.f_cos_t, o);
+                                      J.f_sin_t, J.f_cos_t, J.f_inv_dist, o);
       }
       if (alive) {
         int x0, y0, x1, y1;
@@ -896,7 +909,7 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat3_kernel(const Job* __res
       }
     } else {
       alive = trace<2, true, false>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, g.cell, -g.P), fmaf((float)b + 0.5f, g.cell, -g.P),
-                                    J.f_sin_t, J.f_cos_t, o);
+                                    J.f_sin_t, J.f_cos_t, J.f_inv_dist, o);
     }
     if (alive) {
       int x0, y0, x1, y1;
@@ -1069,9 +1082,9 @@ __global__ void __launch_bounds__(kThreads) exact_dump_kernel(const Job* __restr
   PM.sx = (float)J.sx; PM.sy = (float)J.sy; PM.cs = (float)J.cs; PM.sn = (float)J.sn; PM.ppu = (float)J.ppu;
   RayOut o;
   const bool alive = g.lut ? trace<2, false, true>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P),
-                                                   (float)J.sin_t, (float)J.cos_t, o)
+                                                   (float)J.sin_t, (float)J.cos_t, (float)J.inv_dist, o)
                            : trace<1, false, true>(s_prog, n_steps, M, g.lut, fmaf((float)a + 0.5f, cell, -P), fmaf((float)b + 0.5f, cell, -P),
-                                                   (float)J.sin_t, (float)J.cos_t, o);
+                                                   (float)J.sin_t, (float)J.cos_t, (float)J.inv_dist, o);
   lfb_ray_hit rec;
   rec.x_ap = o.xa; rec.y_ap = o.ya; rec.flags = o.flags; rec.pad = 0;
   if (alive) {

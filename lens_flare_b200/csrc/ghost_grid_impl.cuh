@@ -176,6 +176,16 @@ __device__ __forceinline__ bool trace_exact(const Job& J, const float* __restric
   r.ox = x; r.oy = y; r.oz = (R)0;
   r.dx = (R)J.sin_t; r.dy = (R)0; r.dz = (R)J.cos_t;
   r.w = (R)1; r.flags = 0; r.xa = r.ya = Num<R>::nan();
+  if (J.inv_dist != 0.0) {
+    // point light at -D (sin t, 0, cos t): the ray through (x, y, 0) runs along v = (x/D + sin t, y/D, cos t); its weight is
+    // the irradiance at the entrance point relative to the vertex, (D/|E-P|)^2 * (cos of incidence / cos t) = |v|^-3
+    const R inv_d = (R)J.inv_dist;
+    const R vx = x * inv_d + r.dx, vy = y * inv_d, vz = r.dz;
+    const R q = vx * vx + vy * vy + vz * vz;
+    const R len = sqrt(q);
+    r.dx = vx / len; r.dy = vy / len; r.dz = vz / len;
+    r.w = (R)1 / (q * len);
+  }
 #define LFB_STEP(expr) do { if (!(expr)) return false; if (EARLY_OUT && r.w == (R)0) return false; } while (0)
 #define LFB_FWD(k) do { if ((k) == stop) { cross_stop<R>(tex, tw, th, r); if (EARLY_OUT && r.w == (R)0) return false; } \
                         else LFB_STEP(refract_at<R>(lam, (k), true, r)); } while (0)
@@ -212,12 +222,15 @@ __device__ __forceinline__ Hit<R> trace_ray(const Job& J, const FrameGeom& g, co
   const R y = -P + ((R)b + (R)0.5) * cell;
   Hit<R> h;
   if (MODE == LFB_MODE_PARAXIAL_GRID) {
-    const R th = (R)J.theta;
+    R th = (R)J.theta, th_y = (R)0;
+    const bool point = J.inv_dist != 0.0;  // paraxial point light: the entrance angle grows linearly across the pupil
+    if (point) { th = x * (R)J.inv_dist + th; th_y = y * (R)J.inv_dist; }
     R w = (R)1;
     h.flags = 0; h.xa = h.ya = Num<R>::nan();
     for (int c = 0; c < J.n_cross; c++) {
       R xa = x * (R)J.cross[c][0] + th * (R)J.cross[c][1];
       R ya = y * (R)J.cross[c][0];
+      if (point) ya = ya + th_y * (R)J.cross[c][1];
       R m = mask_lookup<R>(tex, g.tex_w, g.tex_h, xa, ya);
       if (m == (R)0) h.flags |= LFB_RAY_STOPPED;
       w *= m;
@@ -225,6 +238,7 @@ __device__ __forceinline__ Hit<R> trace_ray(const Job& J, const FrameGeom& g, co
     }
     h.xs = x * (R)J.full[0] + th * (R)J.full[1];
     h.ys = y * (R)J.full[0];
+    if (point) h.ys = h.ys + th_y * (R)J.full[1];
     h.w = w; h.alive = true;
   } else {
     Ray<R> r;

@@ -36,10 +36,11 @@ struct Job {
   double chan[3];           // radiance * rgb_weight * ray area * px_per_unit^2
   double sx, sy, cs, sn, ppu;  // sensor mapping (sun pixel, rotation, pixels per lens unit)
   double sin_t, cos_t;         // EXACT_GRID: direction of the light's parallel bundle
+  double inv_dist;             // point light: 1 / distance to the first vertex (0: directional)
   double cross[3][4];       // entrance -> stop plane, per crossing (m00,m01,m10,m11)
   double full[4];           // entrance -> sensor
   // the same constants as floats, for the FP32 throughput kernel (no per-CTA double -> float conversions)
-  float f_sin_t, f_cos_t, f_sx, f_sy, f_cs, f_sn, f_ppu, f_pad;
+  float f_sin_t, f_cos_t, f_sx, f_sy, f_cs, f_sn, f_ppu, f_inv_dist;
   float f_chan[4];          // chan * 2^fixed_point_bits
 };
 

@@ -97,6 +97,19 @@ void PathTracer::find_sun_pos() {
     if ((ns_x >= 0 && ns_x <= 1) && (ns_y >= 0 && ns_y <= 1)) {
       flare_origins.emplace_back(ns_x, ns_y);
       flare_radiance.push_back(light->radiance);
+      flare_distance.push_back(0.0);
+      angle_to_sun = (float)std::atan(ns_y / ns_x);
+      axis_ray = Vector2D(ns_x, ns_y);
+    }
+  }
+  for (PointLight* light : scene->point_lights) {  // ours: same projection, finite distance
+    double ns_x, ns_y;
+    camera->analyze_world_coord(light->position, ns_x, ns_y);
+    if ((ns_x >= 0 && ns_x <= 1) && (ns_y >= 0 && ns_y <= 1)) {
+      const double dx = light->position.x - camera->pos.x, dy = light->position.y - camera->pos.y, dz = light->position.z - camera->pos.z;
+      flare_origins.emplace_back(ns_x, ns_y);
+      flare_radiance.push_back(light->radiance);
+      flare_distance.push_back(std::sqrt(dx * dx + dy * dy + dz * dz) * scene_unit);
       angle_to_sun = (float)std::atan(ns_y / ns_x);
       axis_ray = Vector2D(ns_x, ns_y);
     }
@@ -178,6 +191,7 @@ std::vector<lfb_light> PathTracer::make_lights(bool for_ghosts) const {
       lt.theta = (float)std::atan(lt.ns_y / lt.ns_x);
     }
     lt.radiance[0] = (float)flare_radiance[l].x; lt.radiance[1] = (float)flare_radiance[l].y; lt.radiance[2] = (float)flare_radiance[l].z;
+    lt.distance = l < flare_distance.size() ? flare_distance[l] : 0.0;
     lights.push_back(lt);
   }
   return lights;

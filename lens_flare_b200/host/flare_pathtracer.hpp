@@ -79,6 +79,13 @@ struct DirectionalLight {
   DirectionalLight(const Vector3D& rad, const Vector3D& posLight, const Vector3D& lightDir);
 };
 
+// scene/light.h:49-59, light.cpp:47-48.  The reference's flare code skips point lights (pathtracer.cpp:35 only takes
+// DirectionalLight); here one becomes an lfb_light with a finite distance.
+struct PointLight {
+  Vector3D radiance, position;
+  PointLight(const Vector3D& rad, const Vector3D& pos) : radiance(rad), position(pos) {}
+};
+
 // the members of CGL::Camera the ghost path reads (camera.h:93-200)
 class Camera {
  public:
@@ -92,6 +99,7 @@ class Camera {
 
 struct Scene {
   std::vector<DirectionalLight*> lights;
+  std::vector<PointLight*> point_lights;
 };
 
 class PathTracer {
@@ -107,6 +115,8 @@ class PathTracer {
   HDRImageBuffer ghost_buffer;
   std::vector<Vector2D> flare_origins;
   std::vector<Vector3D> flare_radiance;
+  std::vector<double> flare_distance;  // ours: lens units per flare origin, 0 = directional
+  double scene_unit = 1000.0;          // ours: lens units (mm) per scene unit, for PointLight distances
   Vector2D axis_ray;
   float angle_to_sun = 0;
   void set_frame_size(size_t width, size_t height) { frame_w_ = width; frame_h_ = height; }

@@ -100,6 +100,15 @@ class HDRImageBuffer:
         return self.data[y, x]
 
 
+class PointLight:
+    """scene/light.h:49-59, light.cpp:47-48.  The reference's flare code skips it (pathtracer.cpp:35 only takes
+    DirectionalLight); here it becomes an lfb_light with a finite distance."""
+
+    def __init__(self, rad, pos):
+        self.radiance = np.asarray(rad, np.float64)
+        self.position = np.asarray(pos, np.float64)
+
+
 class PathTracer:
     """The ghost-path members of CGL::PathTracer, backed by the CUDA engine.
 
@@ -116,6 +125,8 @@ class PathTracer:
         self.lights = []              # scene->lights
         self.flare_origins = []
         self.flare_radiance = []
+        self.flare_distance = []      # lens units per flare origin; 0 = directional (ours: the reference has no point flares)
+        self.scene_unit = 1000.0      # lens units (mm) per scene unit, for PointLight distances
         self.axis_ray = (0.0, 0.0)
         self.angle_to_sun = 0.0
         self.ghost_buffer = HDRImageBuffer()
@@ -143,12 +154,18 @@ class PathTracer:
         """pathtracer.cpp:32-64.  Every on-screen directional light is recorded; like the reference,
         axis_ray / angle_to_sun end up describing the LAST one."""
         for light in self.lights:
-            if not isinstance(light, DirectionalLight):
+            if isinstance(light, DirectionalLight):
+                where, distance = light.posLight, 0.0
+            elif isinstance(light, PointLight):
+                where = light.position
+                distance = float(np.linalg.norm(where - np.asarray(self.camera.pos, np.float64))) * self.scene_unit
+            else:
                 continue
-            ns_x, ns_y = self.camera.analyze_world_coord(light.posLight)
+            ns_x, ns_y = self.camera.analyze_world_coord(where)
             if 0 <= ns_x <= 1 and 0 <= ns_y <= 1:
                 self.flare_origins.append((ns_x, ns_y))
                 self.flare_radiance.append(light.radiance)
+                self.flare_distance.append(distance)
                 self.angle_to_sun = float(np.float32(math.atan(ns_y / ns_x))) if ns_x != 0 else float(np.float32(math.pi / 2))
                 self.axis_ray = (ns_x, ns_y)
 
@@ -157,13 +174,14 @@ class PathTracer:
             return [capi.make_light(self.axis_ray[0], self.axis_ray[1], theta=self.angle_to_sun)]
         if not self.flare_origins:  # axis_ray set by hand, as the reference's GUI code paths can
             self.flare_origins, self.flare_radiance = [self.axis_ray], [np.ones(3)]
+        dist = list(self.flare_distance) + [0.0] * (len(self.flare_origins) - len(self.flare_distance))
         out = []
-        for (nx, ny), rad in zip(self.flare_origins, self.flare_radiance):
+        for (nx, ny), rad, d in zip(self.flare_origins, self.flare_radiance, dist):
             if self.mode == capi.MODE_EXACT_GRID:  # real refraction needs the real off-axis angle
                 theta = capi.physical_theta(nx, ny, self.camera.hFov, self.camera.vFov)
             else:  # the reference's angle_to_sun (pathtracer.cpp:50)
                 theta = float(np.float32(math.atan(ny / nx))) if nx != 0 else float(np.float32(math.pi / 2))
-            out.append(capi.make_light(nx, ny, theta=theta, radiance=tuple(float(v) for v in rad)))
+            out.append(capi.make_light(nx, ny, theta=theta, radiance=tuple(float(v) for v in rad), distance=d))
         return out
 
     def raytrace_starburst_frame(self, flare_radius=30.0, flare_intensity=1.0, out=None, additive=False):

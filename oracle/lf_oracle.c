@@ -522,7 +522,7 @@ static void cross_stop(const lfb_lens* L, const double* zv, const float* tex, in
 }
 
 static void trace_exact(const lfb_lens* L, const float* tex, int tw, int th, int lambda, int i, int j,
-                        double x, double y, double theta, ray_t* r) {
+                        double x, double y, double theta, double inv_dist, ray_t* r) {
   const int n = L->n_surfaces, stop = L->stop_index;
   double zv[LFB_MAX_SURFACES + 1];
   zv[0] = 0;
@@ -530,6 +530,15 @@ static void trace_exact(const lfb_lens* L, const float* tex, int tw, int th, int
   r->o[0] = x; r->o[1] = y; r->o[2] = 0;
   r->d[0] = sin(theta); r->d[1] = 0; r->d[2] = cos(theta);
   r->w = 1; r->flags = 0; r->xa = r->ya = NAN;
+  if (inv_dist != 0) {
+    /* point light at -D (sin t, 0, cos t) (lfb_light.distance, include/lfb200.h): direction (E - P)/D normalised; weight =
+     * irradiance at the entrance point relative to the vertex = (D/|E-P|)^2 * cos(incidence)/cos t = |v|^-3 */
+    double vx = x * inv_dist + r->d[0], vy = y * inv_dist, vz = r->d[2];
+    double q = vx * vx + vy * vy + vz * vz;
+    double len = sqrt(q);
+    r->d[0] = vx / len; r->d[1] = vy / len; r->d[2] = vz / len;
+    r->w = 1 / (q * len);
+  }
 #define STEP(expr) do { if (!(expr)) { r->w = 0; r->o[0] = r->o[1] = NAN; return; } } while (0)
   if (i < 0) {
     for (int k = 0; k < n; k++) {
@@ -555,6 +564,10 @@ static void trace_exact(const lfb_lens* L, const float* tex, int tw, int th, int
 /* ------------------------------------------------------------------------- */
 /* grid tracing                                                               */
 /* ------------------------------------------------------------------------- */
+static double light_inv_dist(const lfb_light* lt) {
+  return (lt->distance > 0 && isfinite(lt->distance)) ? 1.0 / lt->distance : 0.0;
+}
+
 static void trace_one(const lfb_lens* L, const float* tex, int tw, int th, const lfb_light* lt,
                       const lfb_params* P, const pixmap* pm, int i, int j, int lambda, int nc,
                       double cross[3][4], const double full[4], int a, int b, lfb_ray_hit* h) {
@@ -564,11 +577,14 @@ static void trace_one(const lfb_lens* L, const float* tex, int tw, int th, const
   double y = -Pe + (b + 0.5) * (2 * Pe / N);
   memset(h, 0, sizeof(*h));
   if (P->mode == LFB_MODE_PARAXIAL_GRID) {
-    double th_ = lt->theta, w = 1;
+    double th_ = lt->theta, thy = 0, w = 1;
+    const double inv_dist = light_inv_dist(lt);
+    if (inv_dist != 0) { th_ = x * inv_dist + th_; thy = y * inv_dist; }  /* paraxial point light */
     h->x_ap = h->y_ap = NAN;
     for (int c = 0; c < nc; c++) {
       double xa = x * cross[c][0] + th_ * cross[c][1];
       double ya = y * cross[c][0];
+      if (inv_dist != 0) ya = ya + thy * cross[c][1];
       double m = mask_lookup(L, tex, tw, th, xa, ya);
       if (m == 0) h->flags |= LFB_RAY_STOPPED;
       w *= m;
@@ -576,10 +592,11 @@ static void trace_one(const lfb_lens* L, const float* tex, int tw, int th, const
     }
     h->x_s = x * full[0] + th_ * full[1];
     h->y_s = y * full[0];
+    if (inv_dist != 0) h->y_s = h->y_s + thy * full[1];
     h->weight = w;
   } else {
     ray_t r;
-    trace_exact(L, tex, tw, th, lambda, i, j, x, y, lt->theta, &r);
+    trace_exact(L, tex, tw, th, lambda, i, j, x, y, lt->theta, light_inv_dist(lt), &r);
     h->x_s = r.o[0]; h->y_s = r.o[1]; h->x_ap = r.xa; h->y_ap = r.ya;
     h->weight = r.w; h->flags = r.flags;
   }

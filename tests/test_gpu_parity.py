@@ -254,6 +254,87 @@ def test_spectral_coated_frame_vs_oracle(engine, port, apertures):
 
 
 # ---------------------------------------------------------------------------------------------
+# point lights (lfb_light.distance): oracle restatement pinned by tests/test_oracle_physics.py
+# ---------------------------------------------------------------------------------------------
+def test_point_light_rays_vs_oracle(engine, port, apertures):
+    """Per-ray hits of a near point light, EXACT_GRID and PARAXIAL_GRID: FP64 to 1e-9 (paraxial: bit for bit), FP32
+    within the directional bundle's tolerances."""
+    lens = capi.builtin_lens(3, 550.0)
+    engine.set_lens(lens)
+    tex = apertures["pentbig500_14"]
+    engine.set_aperture(tex)
+    lt = capi.make_light(0.45, 0.55, theta=0.08, distance=140.0)
+    n_live = 0
+    for (i, j) in [(0, 1), (0, 4), (1, 2), (2, 7), (6, 8), (7, 8), (-1, -1)]:
+        p = capi.make_params(capi.MODE_EXACT_GRID, 1920, 1080, grid_n=48, precision=capi.FP64)
+        want = port.trace_grid(lens, tex, lt, p, i, j, 1)
+        got = engine.dump_rays(lt, p, i, j, 1)
+        assert np.array_equal(got["flags"], want["flags"])
+        ok = ~np.isnan(want["x_s"])
+        assert np.array_equal(np.isnan(got["x_s"]), ~ok)
+        for f in ("x_s", "y_s", "px", "py"):
+            assert (np.abs(got[f][ok] - want[f][ok]) <= 1e-9).all(), (i, j, f)
+        assert np.allclose(got["weight"], want["weight"], rtol=1e-12, atol=0)
+        n_live += int((want["weight"] > 0).sum())
+        got32 = engine.dump_rays(lt, capi.copy_params(p, precision=capi.FP32), i, j, 1)
+        geo = ob.RAY_MISSED | ob.RAY_VIGNETTED | ob.RAY_TIR
+        same = (got32["flags"] & geo) == (want["flags"] & geo)
+        assert same.mean() > 0.99
+        ok32 = same & ok & ~np.isnan(got32["x_s"])
+        if ok32.any():
+            ratio = np.abs(got32["x_s"][ok32] - want["x_s"][ok32]) / np.maximum(1.0, np.abs(want["x_s"][ok32]))
+            assert ratio.max() <= 1e-3 and np.median(ratio) <= 1e-5, (i, j, ratio.max())
+        live = ok32 & (want["weight"] > 0) & (got32["weight"] > 0)
+        assert np.allclose(got32["weight"][live], want["weight"][live], rtol=2e-3, atol=1e-9)
+        pp = capi.make_params(capi.MODE_PARAXIAL_GRID, 1920, 1080, grid_n=48, precision=capi.FP64)
+        assert engine.dump_rays(lt, pp, i, j, 1).tobytes() == port.trace_grid(lens, tex, lt, pp, i, j, 1).tobytes()
+    assert n_live > 500
+
+
+def test_point_light_frames_vs_oracle(port, apertures, monkeypatch):
+    """Frames lit by a point light, a directional light and a second point light together: the FP64 sensor sums equal the
+    oracle's integer sums (bare Fresnel: exactly), every FP32 kernel generation is within 1e-3 of the oracle and the prefix
+    generations agree bit for bit; a far point light renders the directional frame; shards sum to the whole."""
+    lens = capi.builtin_lens(3)
+    tex = apertures["pentbig500_14"]
+    lt = [capi.make_light(0.45, 0.55, theta=capi.physical_theta(0.45, 0.55), distance=160.0),
+          capi.make_light(0.75, 0.3, theta=0.09, radiance=(2.0, 1.0, 0.5)),
+          capi.make_light(0.3, 0.6, theta=0.05, radiance=(0.5, 1.0, 2.0), distance=900.0)]
+    p = capi.make_params(capi.MODE_EXACT_GRID, 800, 450, grid_n=90, pair_set=capi.PAIRS_ALL, include_direct=1)
+    want, acc = port.render(lens, tex, lt, capi.copy_params(p, precision=capi.FP64), want_accum=True)
+    assert np.count_nonzero(acc) > 1000
+    frames = {}
+    for name, env in (("v7", {"LFB_EXACT_FAMILY": "1"}), ("v6", {"LFB_EXACT_FAMILY": "0"}), ("v5", {"LFB_EXACT_FAMILY": "0", "LFB_EXACT_WARP": "0"}),
+                      ("v4", {"LFB_EXACT_PREFIX": "0"}), ("v3", {"LFB_EXACT_WEIGHTS": "closed"})):
+        for k in ("LFB_EXACT_PREFIX", "LFB_EXACT_WEIGHTS", "LFB_EXACT_WARP", "LFB_EXACT_FAMILY"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = capi.Engine(0)
+        try:
+            e.set_lens(lens)
+            e.set_aperture(tex)
+            frames[name] = e.render_ghosts(lt, p)
+            if name == "v7":
+                parts = sum(e.render_ghosts(lt, capi.copy_params(p, shard=(r, 3))) for r in range(3))
+                assert np.array_equal(parts, frames[name])
+                got64 = e.render_ghosts(lt, capi.copy_params(p, precision=capi.FP64))
+                assert np.array_equal(np.rint(got64 * 2.0 ** 40), acc)
+                pq = capi.copy_params(p, mode=capi.MODE_PARAXIAL_GRID, precision=capi.FP64)
+                assert np.array_equal(e.render_ghosts(lt, pq), port.render(lens, tex, lt, pq))
+                far = [capi.make_light(0.45, 0.55, theta=0.07, distance=1e9)]
+                sun = [capi.make_light(0.45, 0.55, theta=0.07)]
+                a, b = e.render_ghosts(far, p), e.render_ghosts(sun, p)
+                assert b.any() and rel_l2(a, b) <= 1e-4
+        finally:
+            e.close()
+        assert rel_l2(frames[name], want) <= 1e-3, name
+    assert np.array_equal(frames["v7"], frames["v6"])
+    assert np.array_equal(frames["v6"], frames["v5"])
+    assert rel_l2(frames["v5"], frames["v4"]) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
 # size-independent properties at full BASELINE sizes, sharding, determinism, edge cases
 # ---------------------------------------------------------------------------------------------
 def test_full_size_properties_cfg2(engine, apertures):

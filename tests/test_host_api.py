@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(native_lib):
 def test_struct_layouts_match_header(native_lib):
     # sizes the C compiler sees (oracle/lf_oracle.c shares the header) vs ctypes
     assert C.sizeof(capi.Lens) == 16 + 4 * 4 * 16 + 4 * 64 * 16 + 4 * 64 + 4 * 64 * 3 + 3 * 8
-    assert C.sizeof(capi.Light) == 32
+    assert C.sizeof(capi.Light) == 40
     assert C.sizeof(capi.Params) == 64
     assert capi.RAY_HIT_DTYPE.itemsize == 64
     assert capi.REF_GHOST_DTYPE.itemsize == 72
@@ -151,6 +151,24 @@ def test_find_sun_pos_matches_reference(golden):
             assert pt.axis_ray == (0.0, 0.0)
 
 
+def test_find_sun_pos_point_lights():
+    """Ours: a PointLight is projected like a DirectionalLight's posLight and carries its distance to the
+    camera in lens units into lfb_light.distance; directional lights keep distance 0."""
+    pt = pathtracer.PathTracer(mode=capi.MODE_EXACT_GRID)
+    pt.camera = pathtracer.Camera(pos=(0.0, 0.0, 1.0))
+    pt.lights = [pathtracer.DirectionalLight((1, 1, 1), (0.05, 0.02, 2.0), (0, 0, -1)),
+                 pathtracer.PointLight((3, 2, 1), (0.1, -0.05, -0.5)),
+                 pathtracer.PointLight((1, 1, 1), (50.0, 0.0, -0.5))]  # off screen
+    pt.find_sun_pos()
+    assert len(pt.flare_origins) == 2 and pt.flare_distance[0] == 0.0
+    assert np.isclose(pt.flare_distance[1], 1000.0 * np.linalg.norm([0.1, -0.05, -1.5]))
+    want = pt.camera.analyze_world_coord(np.array([0.1, -0.05, -0.5]))
+    assert pt.flare_origins[1] == want and pt.axis_ray == want
+    lights = pt._lfb_lights()
+    assert [lt.distance for lt in lights] == pt.flare_distance
+    assert lights[1].theta == capi.physical_theta(want[0], want[1]) and tuple(lights[1].radiance) == (3.0, 2.0, 1.0)
+
+
 def test_aperture_texture_loader(apertures, tmp_path):
     """CameraApertureTexture::init (camera.h:26-83) semantics: red byte * float(1/255), total, bbox."""
     from PIL import Image
@@ -233,6 +251,6 @@ def test_header_is_plain_c(native_lib, tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "tests", "c", "abi_from_c.c"), "-o", str(exe), "-L" + lib_dir, "-llfb200", "-Wl,-rpath," + lib_dir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
-    assert "abi 1 jobs 87 rays 5701632 interactions 95944704" in out
-    assert "sizeof(lens)=5416 light=32 params=64 hit=64" in out
+    assert "abi 2 jobs 87 rays 5701632 interactions 95944704" in out
+    assert "sizeof(lens)=5416 light=40 params=64 hit=64" in out
     assert "lfb_create -> 0" in out or "lfb_create -> -2" in out

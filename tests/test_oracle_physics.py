@@ -149,3 +149,89 @@ def test_sharded_oracle_sums_to_whole(port, apertures):
             _, a = port.render(lens, apertures["pent_11"], lights, ob.copy_params(p, shard=(r, n)), want_accum=True)
             tot += a
         assert np.array_equal(tot, whole)
+
+
+# ---------------------------------------------------------------------------------------------
+# point lights (lfb_light.distance; SURVEY 8f-3 -- the reference's flares only fire for DirectionalLight,
+# pathtracer.cpp:35, so this too is pinned by invariants)
+# ---------------------------------------------------------------------------------------------
+def _open_lens(port, P=14.5):
+    lens = port.builtin_lens(3)
+    lens.entrance_half_height = P
+    lens.stop_half_height = 100.0
+    for k in range(9):
+        lens.semi_aperture[k] = 60.0
+    return lens
+
+
+def test_point_light_through_empty_lens_is_a_straight_line(port):
+    """All indices 1: no refraction, transmittance 1.  The ray from the point source through entrance point (x, y) hits
+    the sensor plane at (x, y) + Z * (vx, vy) / vz with v = (x/D + sin t, y/D, cos t), carrying |v|^-3."""
+    lens = _open_lens(port)
+    for lam in range(3):
+        for k in range(9):
+            lens.ior[lam][k] = 1.0
+    Z = sum(float(lens.thickness[k]) for k in range(9))  # the vertices are sums of the float thicknesses, in double
+    theta, D, N = 0.07, 180.0, 12
+    lt = ob.make_light(0.6, 0.55, theta=theta, distance=D)
+    p = ob.make_params(ob.MODE_EXACT_GRID, 64, 64, grid_n=N)
+    h = port.trace_grid(lens, tiny_tex(), lt, p, -1, -1, 1)
+    idx = np.arange(N * N)
+    x = -14.5 + ((idx % N) + 0.5) * (29.0 / N)
+    y = -14.5 + ((idx // N) + 0.5) * (29.0 / N)
+    th = float(np.float32(theta))
+    vx, vy, vz = x / D + np.sin(th), y / D, np.cos(th)
+    order = np.lexsort((np.round(h["x_s"], 6), np.round(h["y_s"], 6)))  # hits come in grid order whatever it is: compare as sets
+    want_x, want_y = x + Z * vx / vz, y + Z * vy / vz
+    worder = np.lexsort((np.round(want_x, 6), np.round(want_y, 6)))
+    assert np.allclose(h["x_s"][order], want_x[worder], rtol=0, atol=1e-9)
+    assert np.allclose(h["y_s"][order], want_y[worder], rtol=0, atol=1e-9)
+    q = vx * vx + vy * vy + vz * vz
+    assert np.allclose(h["weight"][order], (q ** -1.5)[worder], rtol=1e-12)
+
+
+def test_point_light_limits(port, apertures):
+    """distance 0, negative or infinite = directional (bit for bit); a very distant point light converges to it; a near
+    one does not."""
+    tex = apertures["pent_11"]
+    lens = port.builtin_lens(3, 550.0)
+    p = ob.make_params(ob.MODE_EXACT_GRID, 512, 512, grid_n=24)
+    base = port.trace_grid(lens, tex, ob.make_light(0.6, 0.55, theta=0.06), p, 6, 8, 1)
+    for d in (0.0, -5.0, float("inf")):
+        same = port.trace_grid(lens, tex, ob.make_light(0.6, 0.55, theta=0.06, distance=d), p, 6, 8, 1)
+        assert same.tobytes() == base.tobytes()
+    far = port.trace_grid(lens, tex, ob.make_light(0.6, 0.55, theta=0.06, distance=1e12), p, 6, 8, 1)
+    ok = ~np.isnan(base["x_s"])
+    assert ok.sum() > 100 and np.array_equal(np.isnan(far["x_s"]), ~ok)
+    assert np.abs(far["x_s"][ok] - base["x_s"][ok]).max() < 1e-7 and np.allclose(far["weight"], base["weight"], rtol=1e-9)
+    near = port.trace_grid(lens, tex, ob.make_light(0.6, 0.55, theta=0.06, distance=150.0), p, 6, 8, 1)
+    both = ok & ~np.isnan(near["x_s"])
+    assert np.abs(near["x_s"][both] - base["x_s"][both]).max() > 1.0
+    # whole frames: the near light's ghosts are a different picture, the distant one's the same picture
+    pr = ob.make_params(ob.MODE_EXACT_GRID, 256, 256, grid_n=32, pair_set=ob.PAIRS_ALL, include_direct=1)
+    f0 = port.render(lens, tex, [ob.make_light(0.6, 0.55, theta=0.06)], pr)
+    f1 = port.render(lens, tex, [ob.make_light(0.6, 0.55, theta=0.06, distance=1e9)], pr)
+    f2 = port.render(lens, tex, [ob.make_light(0.6, 0.55, theta=0.06, distance=150.0)], pr)
+    nrm = np.linalg.norm(f0)
+    assert nrm > 0 and np.linalg.norm(f1 - f0) / nrm < 1e-5 and np.linalg.norm(f2 - f0) / nrm > 1e-2
+
+
+def test_point_light_exact_converges_to_paraxial(port):
+    """Same O(h^2) relative residual as the directional bundle: the paraxial point light enters with angle
+    (theta + x/D, y/D)."""
+    tex = tiny_tex()
+    errs = []
+    for P in (1.0, 0.5, 0.25):
+        lens = _open_lens(port, P)
+        lt = ob.make_light(0.6, 0.55, theta=0.02 * P, distance=120.0)
+        worst = 0.0
+        for (i, j) in [(0, 1), (2, 4), (6, 8), (1, 7), (-1, -1)]:
+            pe = ob.make_params(ob.MODE_EXACT_GRID, 64, 64, grid_n=4)
+            pp = ob.make_params(ob.MODE_PARAXIAL_GRID, 64, 64, grid_n=4, physical_backward=1)
+            he = port.trace_grid(lens, tex, lt, pe, i, j, 1)
+            hp = port.trace_grid(lens, tex, lt, pp, i, j, 1)
+            scale = max(np.abs(hp["x_s"]).max(), np.abs(hp["y_s"]).max())
+            worst = max(worst, np.abs(he["x_s"] - hp["x_s"]).max() / scale, np.abs(he["y_s"] - hp["y_s"]).max() / scale)
+        errs.append(worst)
+    assert errs[0] < 0.15 and errs[2] < 0.01
+    assert errs[1] < errs[0] / 3.0 and errs[2] < errs[1] / 3.0
