@@ -439,13 +439,13 @@ def run_ours(args):
     peaks = eng.probe_peaks() if rank == 0 else None
     line = None
     if rank == 0:
-        # roofline of the dominant kernel (trace_splat_kernel<float, EXACT_GRID>): scalar FP32 FMA / MUFU pipes
+        # roofline of the dominant kernel (the FP32 EXACT_GRID ghost kernel): scalar FP32 FMA / MUFU pipes
         k_ms = sum(trace_ms) / len(trace_ms)
         ach = inter_rank * FLOP_PER_INTERACTION / (k_ms * 1e-3)
         mufu_ach = inter_rank * MUFU_PER_INTERACTION / (k_ms * 1e-3)
         roofline = {
-            "bound": "fp32", "kernel": "xf32::exact_splat2_kernel (+ xf32::prefix_kernel)", "achieved": ach / 1e12, "peak": peaks["fp32_flops"] / 1e12,
-            "unit": "TFLOP/s", "frac": ach / peaks["fp32_flops"], "traffic": 1.97e7, "traffic_source": "ncu --set full, profiles/r1_exact_splat_v5_ncu_details.txt: DRAM read 19.7 MB (prefix-cache lines that fell out of L2) + written 0 B per launch; the kernel has no algorithmic HBM stream",
+            "bound": "fp32", "kernel": "xf32::exact_splat3_kernel<12,128> (+ xf32::prefix_kernel)", "achieved": ach / 1e12, "peak": peaks["fp32_flops"] / 1e12,
+            "unit": "TFLOP/s", "frac": ach / peaks["fp32_flops"], "traffic": 1.97e7, "traffic_source": "ncu --set full, profiles/r1_exact_splat_v6_ncu_details.txt: 221.7 GB/s of DRAM traffic x 88.9 us = 19.7 MB per launch (prefix-cache lines that fell out of L2; sensor atomics stay in L2); the kernel has no algorithmic HBM stream",
             "kernel_ms": k_ms, "interactions_per_launch": inter_rank, "flop_per_interaction": FLOP_PER_INTERACTION,
             "peak_source": "measured live on this GPU by lfb_probe_peaks (register-only FFMA chains); MEASURED_PEAKS.json holds no "
                            "FP32 figure. The trace is scalar FP32/MUFU math: neither 'hbm' nor 'tensor' bounds it",
