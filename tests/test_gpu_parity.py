@@ -363,6 +363,35 @@ def test_full_size_properties_cfg2(engine, apertures):
     assert jobs == 87 and rays == 87 * 65536.0
 
 
+def test_maximum_sizes_8k_sensor_4096_grid(apertures):
+    """Beyond BASELINE's largest shape per light: 4096^2 rays per ghost (1.46e9 rays, 7 GB of cached forward sweeps) onto a
+    7680x4320 sensor.  No 32-bit index may wrap anywhere: the frame is bit-stable, equals the sum of its shards, and carries
+    the energy of the 1024^2-ray frame of the same scene (the ray area scales the deposits, so sums converge with N)."""
+    e = capi.Engine(0)
+    try:
+        lens = capi.builtin_lens(3, 550.0)
+        e.set_lens(lens)
+        e.set_aperture(apertures["pentbig500_14"])
+        lt = [capi.make_light(0.45, 0.55, theta=capi.physical_theta(0.45, 0.55), radiance=(1.0, 0.8, 0.6))]
+        big = capi.make_params(capi.MODE_EXACT_GRID, 7680, 4320, grid_n=4096, pair_set=capi.PAIRS_ALL, include_direct=1, px_per_unit=1.6)
+        rays, inter, jobs = capi.count_work(lens, big, 1)
+        assert jobs == 87 and rays == 87 * 4096.0 ** 2
+        a = e.render_ghosts(lt, big)
+        assert a.shape == (4320, 7680, 3) and np.isfinite(a).all() and (a >= 0).all()
+        parts = e.render_ghosts(lt, capi.copy_params(big, shard=(0, 2)))
+        parts += e.render_ghosts(lt, capi.copy_params(big, shard=(1, 2)))
+        assert np.array_equal(parts, a)
+        del parts
+        small = e.render_ghosts(lt, capi.copy_params(big, grid_n=1024))
+        sa, ss = a.sum(axis=(0, 1)), small.sum(axis=(0, 1))
+        assert (ss > 0).all() and np.allclose(sa, ss, rtol=2e-3)
+        # the same picture, not just the same energy: 16x16 block sums agree
+        blk = lambda f: f.reshape(270, 16, 480, 16, 3).sum(axis=(1, 3))
+        assert rel_l2(blk(a), blk(small)) < 2e-2
+    finally:
+        e.close()
+
+
 def test_ragged_grids_and_tiny_sensors(engine, port, apertures):
     lens = capi.builtin_lens(3)
     engine.set_lens(lens)
