@@ -195,9 +195,15 @@ __global__ void __launch_bounds__(256) to_color_kernel(const double* __restrict_
   uint32_t px = 0xFF000000u;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    double v = pow(hdr[3 * p + k] * (double)exposure, (double)one_over_gamma);
-    v = (1.0 < v) ? 1.0 : v;  // std::min(pow, 1.0): NaN passes
-    v = (0.0 < v) ? v : 0.0;  // std::max(0.0, .): NaN -> 0
+    const double s = hdr[3 * p + k] * (double)exposure;
+    double v;
+    if (s == 0.0) v = 0.0;       // pow(+-0, y > 0) = +0: the empty part of a flare frame skips the FP64 pow
+    else if (s >= 1.0) v = 1.0;  // pow(s >= 1, y > 0) >= 1, clamped below anyway
+    else {
+      v = pow(s, (double)one_over_gamma);
+      v = (1.0 < v) ? 1.0 : v;  // std::min(pow, 1.0): NaN passes
+      v = (0.0 < v) ? v : 0.0;  // std::max(0.0, .): NaN -> 0
+    }
     const float c = (float)v;
     px |= ((uint32_t)(fminf(fmaxf(c, 0.f), 1.f) * 255.f)) << (8 * k);
   }
