@@ -27,7 +27,7 @@
 namespace lfb {
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TK = 16;
 
 __device__ __forceinline__ double convert_coordinate(int pixel, int length, bool is_y) {  // :936-945
   const double cc = is_y ? -((double)(float)pixel) + ((double)(float)length / 2.0) : ((double)(float)pixel) - ((double)(float)length / 2.0);
@@ -81,6 +81,16 @@ struct StarEpilogue {
   double rad_sum[3];
 };
 
+// 1/sqrt(x) for a normal positive x that fits a float's range: FP32 MUFU seed + two Newton steps (the seed's 2^-22 relative
+// error squares twice: full double precision up to rounding), no special-case branches.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double h = 0.5 * x;
+  y = y * fma(-h, y * y, 1.5);
+  y = y * fma(-h, y * y, 1.5);
+  return y;
+}
+
 __device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogue& E, int x, int y, double mag) {
   double I = mag / f.total;
   const double dx = f.org_x - (double)x, dy = f.org_y - (double)y, dist = sqrt(dx * dx + dy * dy);
@@ -102,8 +112,12 @@ __device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogu
 #pragma unroll
       for (int sx = 0; sx < 4; sx++) {
         const double ox = L[0] - ((double)x + (sx + 0.5) / 4), oy = L[1] - ((double)y + (sy + 0.5) / 4);
-        const double r = 1.0 + fmax(0.0, sqrt(ox * ox + oy * oy) - 5.0);
-        acc += 1.0 / (r * sqrt(r));
+        // r^-1.5 through two branch-free reciprocal square roots instead of sqrt, sqrt and a division: this loop is the
+        // kernel's instruction budget (16 samples x lights per pixel)
+        const double d2 = fmax(ox * ox + oy * oy, 1e-30);
+        const double r = 1.0 + fmax(0.0, d2 * rsqrt_pos(d2) - 5.0);
+        const double q = rsqrt_pos(r);
+        acc += q * q * q;
       }
     acc *= (1.0 / 16.0);
     fall[0] += L[2] * acc; fall[1] += L[3] * acc; fall[2] += L[4] * acc;
@@ -122,44 +136,61 @@ __device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogu
 }
 
 // C[M x N] = A[M x K] . B[K x N], complex FP64, row-major.  EPILOGUE: only |C| is stored (as a double array in C).
-template <bool EPILOGUE>
-__global__ void __launch_bounds__(256) zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__ B, double2* __restrict__ C,
-                                                    int M, int N, int K, StarFrame f, StarEpilogue E) {
-  __shared__ double2 sA[TK][TM + 1];  // transposed: sA[k][m]
-  __shared__ double2 sB[TK][TN];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+// BM x BN tile per CTA, 4 x 4 outputs per thread ((BM/4) x (BN/4) threads), K step 16.  The lattice products are small
+// (350..1000 per side): 32 x 32 tiles give 176..256+ CTAs for the 148 SMs where 64 x 64 gave 48..64.  REAL_A: the mask is
+// real, so the first product needs two FMAs per term instead of four (and half the shared-memory traffic for A).
+template <int BM, int BN, bool REAL_A, bool EPILOGUE>
+__global__ void __launch_bounds__((BM / 4) * (BN / 4)) zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__ B,
+                                                                   double2* __restrict__ C, int M, int N, int K) {
+  constexpr int NT = (BM / 4) * (BN / 4), SM_ROWS = BM / 4, SN_COLS = BN / 4;
+  __shared__ double sAr[TK][BM + 1];                       // transposed: sA[k][m]; real parts
+  __shared__ double sAi[REAL_A ? 1 : TK][REAL_A ? 1 : BM + 1];  // imaginary parts (unused for a real A)
+  __shared__ double2 sB[TK][BN];
+  const int tx = threadIdx.x % SN_COLS, ty = threadIdx.x / SN_COLS;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   double2 acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = make_double2(0.0, 0.0);
   for (int k0 = 0; k0 < K; k0 += TK) {
-    // A tile: 64 x 16, B tile: 16 x 64 -> 1024 elements each, 4 per thread
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const int e = threadIdx.x + 256 * r;
-      const int am = e >> 4, ak = e & 15;
+    for (int e = threadIdx.x; e < BM * TK; e += NT) {  // A tile: BM x 16, 16 consecutive k per row
+      const int am = e / TK, ak = e % TK;
       const int gm = m0 + am, gk = k0 + ak;
-      sA[ak][am] = (gm < M && gk < K) ? A[(size_t)gm * K + gk] : make_double2(0.0, 0.0);
-      const int bk = e >> 6, bn = e & 63;
-      const int gk2 = k0 + bk, gn = n0 + bn;
-      sB[bk][bn] = (gk2 < K && gn < N) ? B[(size_t)gk2 * N + gn] : make_double2(0.0, 0.0);
+      const double2 v = (gm < M && gk < K) ? A[(size_t)gm * K + gk] : make_double2(0.0, 0.0);
+      sAr[ak][am] = v.x;
+      if (!REAL_A) sAi[ak][am] = v.y;
+    }
+#pragma unroll
+    for (int e = threadIdx.x; e < TK * BN; e += NT) {  // B tile: 16 x BN
+      const int bk = e / BN, bn = e % BN;
+      const int gk = k0 + bk, gn = n0 + bn;
+      sB[bk][bn] = (gk < K && gn < N) ? B[(size_t)gk * N + gn] : make_double2(0.0, 0.0);
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TK; k++) {
-      double2 a[4], b[4];
+      double ar[4], ai[4];
+      double2 b[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = sA[k][ty + 16 * i];
+      for (int i = 0; i < 4; i++) {
+        ar[i] = sAr[k][ty + SM_ROWS * i];
+        ai[i] = REAL_A ? 0.0 : sAi[k][ty + SM_ROWS * i];
+      }
 #pragma unroll
-      for (int j = 0; j < 4; j++) b[j] = sB[k][tx + 16 * j];
+      for (int j = 0; j < 4; j++) b[j] = sB[k][tx + SN_COLS * j];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          acc[i][j].x = fma(a[i].x, b[j].x, fma(-a[i].y, b[j].y, acc[i][j].x));
-          acc[i][j].y = fma(a[i].x, b[j].y, fma(a[i].y, b[j].x, acc[i][j].y));
+          if (REAL_A) {
+            acc[i][j].x = fma(ar[i], b[j].x, acc[i][j].x);
+            acc[i][j].y = fma(ar[i], b[j].y, acc[i][j].y);
+          } else {
+            acc[i][j].x = fma(ar[i], b[j].x, fma(-ai[i], b[j].y, acc[i][j].x));
+            acc[i][j].y = fma(ar[i], b[j].y, fma(ai[i], b[j].x, acc[i][j].y));
+          }
         }
     }
     __syncthreads();
@@ -168,7 +199,7 @@ __global__ void __launch_bounds__(256) zgemm_kernel(const double2* __restrict__ 
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const int gm = m0 + ty + 16 * i, gn = n0 + tx + 16 * j;
+      const int gm = m0 + ty + SM_ROWS * i, gn = n0 + tx + SN_COLS * j;
       if (gm >= M || gn >= N) continue;
       if (EPILOGUE) reinterpret_cast<double*>(C)[(size_t)gm * N + gn] = sqrt(acc[i][j].x * acc[i][j].x + acc[i][j].y * acc[i][j].y);
       else C[(size_t)gm * N + gn] = acc[i][j];
@@ -237,13 +268,25 @@ cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch
   StarEpilogue E;
   E.out = (char*)out; E.stride = stride; E.elem = elem; E.additive = additive; E.n_lights = n_lights; E.lights = lights_dev;
   E.rad_sum[0] = rad_sum[0]; E.rad_sum[1] = rad_sum[1]; E.rad_sum[2] = rad_sum[2];
-  {  // G = Ac . E1   (bh x bw) . (bw x n_col)
-    dim3 grid((f.n_col + TN - 1) / TN, (f.bh + TM - 1) / TM);
-    zgemm_kernel<false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, f.n_col, f.bw, f, E);
+  // tile size by problem size: 64 x 64 tiles once they fill the GPU twice over, 32 x 32 below that
+  auto big = [](int m, int n) { return (size_t)((m + 63) / 64) * ((n + 63) / 64) >= 2 * 148; };
+  {  // G = Ac . E1   (bh x bw) . (bw x n_col); Ac is real
+    if (big(f.bh, f.n_col)) {
+      dim3 grid((f.n_col + 63) / 64, (f.bh + 63) / 64);
+      zgemm_kernel<64, 64, true, false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, f.n_col, f.bw);
+    } else {
+      dim3 grid((f.n_col + 31) / 32, (f.bh + 31) / 32);
+      zgemm_kernel<32, 32, true, false><<<grid, 64, 0, s>>>(Ac, E1, G, f.bh, f.n_col, f.bw);
+    }
   }
   {  // |F| = |E2 . G|   (n_row x bh) . (bh x n_col)
-    dim3 grid((f.n_col + TN - 1) / TN, (f.n_row + TM - 1) / TM);
-    zgemm_kernel<true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh, f, E);
+    if (big(f.n_row, f.n_col)) {
+      dim3 grid((f.n_col + 63) / 64, (f.n_row + 63) / 64);
+      zgemm_kernel<64, 64, false, true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh);
+    } else {
+      dim3 grid((f.n_col + 31) / 32, (f.n_row + 31) / 32);
+      zgemm_kernel<32, 32, false, true><<<grid, 64, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh);
+    }
   }
   star_pixels_kernel<<<blocks((size_t)f.W * f.H), 256, 0, s>>>(f, E, mag);
   if (launches) *launches += 6;
