@@ -1256,6 +1256,9 @@ int starburst_device(lfb_engine* e, const lfb_light* lights, int n_lights, int w
   f.lattice_y = lattice_ok && height > f.period;
   f.n_col = f.lattice_x ? f.period : width;
   f.n_row = f.lattice_y ? f.period : height;
+  // a real mask makes the lattice spectrum Hermitian: F(P-r, P-c) = conj F(r, c), so |F| needs half the rows
+  f.herm = (f.lattice_x && f.lattice_y) ? 1 : 0;
+  if (f.herm) f.n_row = f.period / 2 + 1;
   std::vector<double> L(5 * (size_t)n_lights);
   double rad_sum[3] = {0, 0, 0};
   for (int l = 0; l < n_lights; l++) {

@@ -153,7 +153,8 @@ struct StarFrame {
   double flare_radius, exponent;  // exponent = 3 - flare_intensity (2 when that is <= 0), :998-1001
   // the lattice the two matrix products are evaluated on: n_col columns / n_row rows; lattice_x / lattice_y: that axis is
   // the P-periodic class lattice (period P = W_t or 2 W_t), else one column / row per pixel
-  int n_col, n_row, lattice_x, lattice_y, period, pad;
+  // herm: both axes on the lattice -> |F(-r,-c)| = |F(r,c)| (real mask), only rows 0..period/2 are computed (n_row = P/2+1)
+  int n_col, n_row, lattice_x, lattice_y, period, herm;
 };
 size_t starburst_scratch_bytes(const StarFrame& f);
 cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch, const double* lights_dev, int n_lights,

@@ -41,16 +41,16 @@ __device__ __forceinline__ double star_alpha(const StarFrame& f, int c) {
 __device__ __forceinline__ double star_beta(const StarFrame& f, int r) {
   return f.lattice_y ? (double)r : f.ud - convert_coordinate(r, f.H, true);
 }
-// lattice column of pixel x / row of pixel y
+// lattice column of pixel x / row of pixel y (the class index in [0, P); the offsets are integers well inside int range)
 __device__ __forceinline__ int star_col(const StarFrame& f, int x) {
   if (!f.lattice_x) return x;
-  const long long a = (long long)llrint(f.lr - convert_coordinate(x, f.W, false));
-  return (int)(((a % f.period) + f.period) % f.period);
+  const int m = __double2int_rn(f.lr - convert_coordinate(x, f.W, false)) % f.period;
+  return m < 0 ? m + f.period : m;
 }
 __device__ __forceinline__ int star_row(const StarFrame& f, int y) {
   if (!f.lattice_y) return y;
-  const long long b = (long long)llrint(f.ud - convert_coordinate(y, f.H, true));
-  return (int)(((b % f.period) + f.period) % f.period);
+  const int m = __double2int_rn(f.ud - convert_coordinate(y, f.H, true)) % f.period;
+  return m < 0 ? m + f.period : m;
 }
 
 // which = 0: E1[xc_i][col]  (rows = bw, cols = n_col);  which = 1: E2[row][yc_i]  (rows = n_row, cols = bh);
@@ -81,10 +81,11 @@ struct StarEpilogue {
   double rad_sum[3];
 };
 
-// 1/sqrt(x) for a normal positive x that fits a float's range: FP32 MUFU seed + two Newton steps (the seed's 2^-22 relative
-// error squares twice: full double precision up to rounding), no special-case branches.
+// 1/sqrt(x) for a normal positive x: the hardware's FP64 seed (MUFU.RSQ64H, ~2^-22 relative) + two Newton steps -- the
+// error squares twice, i.e. full double precision up to rounding -- with none of rsqrt()'s special-case branches.
 __device__ __forceinline__ double rsqrt_pos(double x) {
-  double y = (double)rsqrtf((float)x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double h = 0.5 * x;
   y = y * fma(-h, y * y, 1.5);
   y = y * fma(-h, y * y, 1.5);
@@ -106,18 +107,23 @@ __device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogu
   double fall[3] = {0.0, 0.0, 0.0};
   for (int l = 0; l < E.n_lights; l++) {
     const double* L = E.lights + 5 * l;
+    double ox2[4], oy2[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double ox = L[0] - ((double)x + (k + 0.5) / 4), oy = L[1] - ((double)y + (k + 0.5) / 4);
+      ox2[k] = ox * ox; oy2[k] = oy * oy;
+    }
     double acc = 0.0;
 #pragma unroll
     for (int sy = 0; sy < 4; sy++)
 #pragma unroll
       for (int sx = 0; sx < 4; sx++) {
-        const double ox = L[0] - ((double)x + (sx + 0.5) / 4), oy = L[1] - ((double)y + (sy + 0.5) / 4);
-        // r^-1.5 through two branch-free reciprocal square roots instead of sqrt, sqrt and a division: this loop is the
-        // kernel's instruction budget (16 samples x lights per pixel)
-        const double d2 = fmax(ox * ox + oy * oy, 1e-30);
+        // r^-1.5 with r = 1 + max(0, |o| - 5), through two branch-free reciprocal square roots instead of sqrt, sqrt and
+        // a division: this loop is the kernel's FP64 budget (16 samples x lights per pixel)
+        const double d2 = (ox2[sx] + oy2[sy]) + 1e-30;
         const double r = 1.0 + fmax(0.0, d2 * rsqrt_pos(d2) - 5.0);
         const double q = rsqrt_pos(r);
-        acc += q * q * q;
+        acc = fma(q * q, q, acc);
       }
     acc *= (1.0 / 16.0);
     fall[0] += L[2] * acc; fall[1] += L[3] * acc; fall[2] += L[4] * acc;
@@ -210,10 +216,14 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) zgemm_kernel(const double
 
 // one thread per pixel: |F| from the lattice, then suppression / amplification / power law / falloff / output
 __global__ void __launch_bounds__(256) star_pixels_kernel(StarFrame f, StarEpilogue E, const double* __restrict__ mag) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= (size_t)f.W * f.H) return;
-  const int y = (int)(p / f.W), x = (int)(p - (size_t)y * f.W);
-  star_pixel(f, E, x, y, mag[(size_t)star_row(f, y) * f.n_col + star_col(f, x)]);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;  // one row per blockIdx.y: no 64-bit divisions
+  if (x >= f.W) return;
+  int row = star_row(f, y), col = star_col(f, x);
+  if (f.herm && row > f.period / 2) {  // |F(r, c)| = |F(P - r, P - c)|
+    row = f.period - row;
+    col = col ? f.period - col : 0;
+  }
+  star_pixel(f, E, x, y, mag[(size_t)row * f.n_col + col]);
 }
 
 // HDRImageBuffer::toColor (util/image.h:208-223: gamma 2.2, exposure sqrt(2), clamp) + ImageBuffer::update_pixel
@@ -288,7 +298,7 @@ cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch
       zgemm_kernel<32, 32, false, true><<<grid, 64, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh);
     }
   }
-  star_pixels_kernel<<<blocks((size_t)f.W * f.H), 256, 0, s>>>(f, E, mag);
+  star_pixels_kernel<<<dim3((unsigned)((f.W + 255) / 256), (unsigned)f.H), 256, 0, s>>>(f, E, mag);
   if (launches) *launches += 6;
   return cudaGetLastError();
 }
