@@ -19,7 +19,8 @@
 // (beta(y) mod P, alpha(x) mod P); with the reduced arguments the twiddles are also more accurate than the reference's.
 //
 //   twiddle_kernel            E1 / E2 / complex copy of the mask's bounding box
-//   zgemm_kernel<EPILOGUE>    tiled complex FP64 GEMM, 64x64 tile per CTA, 4x4 outputs per thread, K step 16
+//   zgemm_kernel<...>         tiled complex FP64 GEMM (32x32 or 64x64 tile per CTA, 4x4 outputs per thread, K step 16,
+//                             K-split thread groups for the small lattice products)
 //   the EPILOGUE variant      |F| / total -> suppression (dist > W_t/2: factor^8) / amplification (dist <= radius:
 //                             I^(dist/radius)) -> I^(3 - flare_intensity) -> x sum of radiance + falloff -> caller layout
 #include "lfb_internal.h"
@@ -142,17 +143,24 @@ __device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogu
 }
 
 // C[M x N] = A[M x K] . B[K x N], complex FP64, row-major.  EPILOGUE: only |C| is stored (as a double array in C).
-// BM x BN tile per CTA, 4 x 4 outputs per thread ((BM/4) x (BN/4) threads), K step 16.  The lattice products are small
-// (350..1000 per side): 32 x 32 tiles give 176..256+ CTAs for the 148 SMs where 64 x 64 gave 48..64.  REAL_A: the mask is
-// real, so the first product needs two FMAs per term instead of four (and half the shared-memory traffic for A).
-template <int BM, int BN, bool REAL_A, bool EPILOGUE>
-__global__ void __launch_bounds__((BM / 4) * (BN / 4)) zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__ B,
-                                                                   double2* __restrict__ C, int M, int N, int K) {
-  constexpr int NT = (BM / 4) * (BN / 4), SM_ROWS = BM / 4, SN_COLS = BN / 4;
-  __shared__ double sAr[TK][BM + 1];                       // transposed: sA[k][m]; real parts
-  __shared__ double sAi[REAL_A ? 1 : TK][REAL_A ? 1 : BM + 1];  // imaginary parts (unused for a real A)
-  __shared__ double2 sB[TK][BN];
-  const int tx = threadIdx.x % SN_COLS, ty = threadIdx.x / SN_COLS;
+// BM x BN tile per CTA, 4 x 4 outputs per thread, K step 16.  The lattice products are small (250..1000 per side, K ~ 350):
+//   * 32 x 32 tiles give 130..260 CTAs for the 148 SMs where 64 x 64 gave 48..64;
+//   * KG thread groups share each staged K tile and take every KG-th k of it, so a CTA runs KG x 2 warps instead of 2 and its
+//     serial FMA chain is KG times shorter (one warp per scheduler cannot hide the LDS -> DFMA latency); the groups' partial
+//     tiles are summed through shared memory in a fixed order at the end (deterministic);
+//   * REAL_A: the mask is real, so the first product needs two FMAs per term instead of four.
+template <int BM, int BN, int KG, bool REAL_A, bool EPILOGUE>
+__global__ void __launch_bounds__((BM / 4) * (BN / 4) * KG) zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__ B,
+                                                                        double2* __restrict__ C, int M, int N, int K) {
+  constexpr int NT0 = (BM / 4) * (BN / 4), NT = NT0 * KG, SM_ROWS = BM / 4, SN_COLS = BN / 4;
+  constexpr int A_DOUBLES = TK * (BM + 1) * (REAL_A ? 1 : 2), B_DOUBLES = TK * BN * 2, RED_DOUBLES = KG > 1 ? NT0 * 32 : 0;
+  constexpr int SMEM_DOUBLES = (A_DOUBLES + B_DOUBLES) > RED_DOUBLES ? (A_DOUBLES + B_DOUBLES) : RED_DOUBLES;
+  __shared__ __align__(16) double smem[SMEM_DOUBLES];
+  double2 (*sB)[BN] = reinterpret_cast<double2 (*)[BN]>(smem);                    // [TK][BN]
+  double (*sAr)[BM + 1] = reinterpret_cast<double (*)[BM + 1]>(smem + B_DOUBLES);  // transposed: [TK][BM + 1], real parts
+  double (*sAi)[BM + 1] = sAr + TK;                                                // imaginary parts (absent for a real A)
+  const int grp = threadIdx.x / NT0, lt = threadIdx.x % NT0;
+  const int tx = lt % SN_COLS, ty = lt / SN_COLS;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   double2 acc[4][4];
 #pragma unroll
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) zgemm_kernel(const double
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < TK; k++) {
+    for (int k = grp; k < TK; k += KG) {
       double ar[4], ai[4];
       double2 b[4];
 #pragma unroll
@@ -200,6 +208,29 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) zgemm_kernel(const double
         }
     }
     __syncthreads();
+  }
+  if (KG > 1) {  // group 0 += group 1, 2, ... (fixed order), through the (now idle) tile storage
+    double2* red = reinterpret_cast<double2*>(smem);
+    for (int g = 1; g < KG; g++) {
+      if (grp == g) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) red[(i * 4 + j) * NT0 + lt] = acc[i][j];
+      }
+      __syncthreads();
+      if (grp == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const double2 v = red[(i * 4 + j) * NT0 + lt];
+            acc[i][j].x += v.x; acc[i][j].y += v.y;
+          }
+      }
+      __syncthreads();
+    }
+    if (grp != 0) return;
   }
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -283,19 +314,19 @@ cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch
   {  // G = Ac . E1   (bh x bw) . (bw x n_col); Ac is real
     if (big(f.bh, f.n_col)) {
       dim3 grid((f.n_col + 63) / 64, (f.bh + 63) / 64);
-      zgemm_kernel<64, 64, true, false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, f.n_col, f.bw);
+      zgemm_kernel<64, 64, 1, true, false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, f.n_col, f.bw);
     } else {
       dim3 grid((f.n_col + 31) / 32, (f.bh + 31) / 32);
-      zgemm_kernel<32, 32, true, false><<<grid, 64, 0, s>>>(Ac, E1, G, f.bh, f.n_col, f.bw);
+      zgemm_kernel<32, 32, 4, true, false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, f.n_col, f.bw);
     }
   }
   {  // |F| = |E2 . G|   (n_row x bh) . (bh x n_col)
     if (big(f.n_row, f.n_col)) {
       dim3 grid((f.n_col + 63) / 64, (f.n_row + 63) / 64);
-      zgemm_kernel<64, 64, false, true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh);
+      zgemm_kernel<64, 64, 1, false, true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh);
     } else {
       dim3 grid((f.n_col + 31) / 32, (f.n_row + 31) / 32);
-      zgemm_kernel<32, 32, false, true><<<grid, 64, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh);
+      zgemm_kernel<32, 32, 4, false, true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh);
     }
   }
   star_pixels_kernel<<<dim3((unsigned)((f.W + 255) / 256), (unsigned)f.H), 256, 0, s>>>(f, E, mag);
