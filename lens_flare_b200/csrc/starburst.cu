@@ -54,13 +54,19 @@ __device__ __forceinline__ int star_row(const StarFrame& f, int y) {
   return m < 0 ? m + f.period : m;
 }
 
-// which = 0: E1[xc_i][col]  (rows = bw, cols = n_col);  which = 1: E2[row][yc_i]  (rows = n_row, cols = bh);
-// which = 2: complex copy of the mask's bounding box A[yc_i][xc_i] (rows = bh, cols = bw)
-__global__ void __launch_bounds__(256) twiddle_kernel(StarFrame f, const float* __restrict__ tex, double2* __restrict__ out, int which) {
-  const int rows = which == 0 ? f.bw : (which == 1 ? f.n_row : f.bh), cols = which == 0 ? f.n_col : (which == 1 ? f.bh : f.bw);
-  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= (size_t)rows * cols) return;
-  const int r = (int)(q / cols), c = (int)(q - (size_t)r * cols);
+// E1[xc_i][col]  (rows = bw, cols = n_col);  E2[row][yc_i]  (rows = n_row, cols = bh);
+// Ac = complex copy of the mask's bounding box A[yc_i][xc_i] (rows = bh, cols = bw)
+__global__ void __launch_bounds__(256) twiddle_kernel(StarFrame f, const float* __restrict__ tex, double2* __restrict__ E1,
+                                                      double2* __restrict__ E2, double2* __restrict__ Ac) {
+  // one launch for the three tables: [0, n0) -> E1, [n0, n0 + n1) -> E2, the rest -> Ac
+  const size_t n0 = (size_t)f.bw * f.n_col, n1 = (size_t)f.n_row * f.bh, n2 = (size_t)f.bh * f.bw;
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n0 + n1 + n2) return;
+  const int which = q < n0 ? 0 : (q < n0 + n1 ? 1 : 2);
+  if (which == 1) q -= n0;
+  if (which == 2) q -= n0 + n1;
+  const unsigned cols = which == 0 ? f.n_col : (which == 1 ? f.bh : f.bw);
+  const int r = (int)((unsigned)q / cols), c = (int)((unsigned)q - (unsigned)r * cols);  // every table is far below 2^32 entries
   double2 v;
   if (which == 2) {
     v.x = (double)tex[(size_t)(f.by0 + r) * f.tw + (f.bx0 + c)];
@@ -71,7 +77,7 @@ __global__ void __launch_bounds__(256) twiddle_kernel(StarFrame f, const float* 
     else e = (((double)(f.by0 + c) / (double)f.tw) - 0.5) * star_beta(f, r);
     sincospi(2.0 * e, &v.y, &v.x);
   }
-  out[q] = v;
+  (which == 0 ? E1 : (which == 1 ? E2 : Ac))[q] = v;
 }
 
 struct StarEpilogue {
@@ -82,15 +88,13 @@ struct StarEpilogue {
   double rad_sum[3];
 };
 
-// 1/sqrt(x) for a normal positive x: the hardware's FP64 seed (MUFU.RSQ64H, ~2^-22 relative) + two Newton steps -- the
-// error squares twice, i.e. full double precision up to rounding -- with none of rsqrt()'s special-case branches.
+// 1/sqrt(x) for a normal positive x: the hardware's FP64 seed (MUFU.RSQ64H, ~2^-22 relative) + one Newton step (1.5 e^2:
+// < 1e-13 relative) with none of rsqrt()'s special-case branches.  Used by the falloff term only, whose 4x4 stratified
+// quadrature already differs from the reference's 16 random samples by ~1e-2; the oracle pin on it is 1e-11 absolute.
 __device__ __forceinline__ double rsqrt_pos(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double h = 0.5 * x;
-  y = y * fma(-h, y * y, 1.5);
-  y = y * fma(-h, y * y, 1.5);
-  return y;
+  return y * fma(-0.5 * x, y * y, 1.5);
 }
 
 __device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogue& E, int x, int y, double mag) {
@@ -167,21 +171,39 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4) * KG) zgemm_kernel(const d
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = make_double2(0.0, 0.0);
+  // the next K tile travels global -> registers while the current one is multiplied (register double buffering)
+  constexpr int A_PER = (BM * TK + NT - 1) / NT, B_PER = (TK * BN + NT - 1) / NT;
+  double2 pa[A_PER], pb[B_PER];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < A_PER; q++) {  // A tile: BM x 16, 16 consecutive k per row
+      const int e = threadIdx.x + q * NT, am = e / TK, ak = e % TK;
+      const int gm = m0 + am, gk = k0 + ak;
+      pa[q] = (e < BM * TK && gm < M && gk < K) ? A[(size_t)gm * K + gk] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < B_PER; q++) {  // B tile: 16 x BN
+      const int e = threadIdx.x + q * NT, bk = e / BN, bn = e % BN;
+      const int gk = k0 + bk, gn = n0 + bn;
+      pb[q] = (e < TK * BN && gk < K && gn < N) ? B[(size_t)gk * N + gn] : make_double2(0.0, 0.0);
+    }
+  };
+  fetch(0);
   for (int k0 = 0; k0 < K; k0 += TK) {
 #pragma unroll
-    for (int e = threadIdx.x; e < BM * TK; e += NT) {  // A tile: BM x 16, 16 consecutive k per row
-      const int am = e / TK, ak = e % TK;
-      const int gm = m0 + am, gk = k0 + ak;
-      const double2 v = (gm < M && gk < K) ? A[(size_t)gm * K + gk] : make_double2(0.0, 0.0);
-      sAr[ak][am] = v.x;
-      if (!REAL_A) sAi[ak][am] = v.y;
+    for (int q = 0; q < A_PER; q++) {
+      const int e = threadIdx.x + q * NT;
+      if (e < BM * TK) {
+        sAr[e % TK][e / TK] = pa[q].x;
+        if (!REAL_A) sAi[e % TK][e / TK] = pa[q].y;
+      }
     }
 #pragma unroll
-    for (int e = threadIdx.x; e < TK * BN; e += NT) {  // B tile: 16 x BN
-      const int bk = e / BN, bn = e % BN;
-      const int gk = k0 + bk, gn = n0 + bn;
-      sB[bk][bn] = (gk < K && gn < N) ? B[(size_t)gk * N + gn] : make_double2(0.0, 0.0);
+    for (int q = 0; q < B_PER; q++) {
+      const int e = threadIdx.x + q * NT;
+      if (e < TK * BN) sB[e / BN][e % BN] = pb[q];
     }
+    if (k0 + TK < K) fetch(k0 + TK);
     __syncthreads();
 #pragma unroll
     for (int k = grp; k < TK; k += KG) {
@@ -303,9 +325,7 @@ cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch
   double2* G = Ac + (size_t)f.bh * f.bw;
   double* mag = (double*)(G + (size_t)f.bh * f.n_col);
   auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
-  twiddle_kernel<<<blocks((size_t)f.bw * f.n_col), 256, 0, s>>>(f, tex, E1, 0);
-  twiddle_kernel<<<blocks((size_t)f.n_row * f.bh), 256, 0, s>>>(f, tex, E2, 1);
-  twiddle_kernel<<<blocks((size_t)f.bh * f.bw), 256, 0, s>>>(f, tex, Ac, 2);
+  twiddle_kernel<<<blocks((size_t)f.bw * f.n_col + (size_t)f.n_row * f.bh + (size_t)f.bh * f.bw), 256, 0, s>>>(f, tex, E1, E2, Ac);
   StarEpilogue E;
   E.out = (char*)out; E.stride = stride; E.elem = elem; E.additive = additive; E.n_lights = n_lights; E.lights = lights_dev;
   E.rad_sum[0] = rad_sum[0]; E.rad_sum[1] = rad_sum[1]; E.rad_sum[2] = rad_sum[2];
@@ -330,7 +350,7 @@ cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch
     }
   }
   star_pixels_kernel<<<dim3((unsigned)((f.W + 255) / 256), (unsigned)f.H), 256, 0, s>>>(f, E, mag);
-  if (launches) *launches += 6;
+  if (launches) *launches += 4;
   return cudaGetLastError();
 }
 
