@@ -154,8 +154,9 @@ __device__ __forceinline__ void star_pixel(const StarFrame& f, const StarEpilogu
 //     tiles are summed through shared memory in a fixed order at the end (deterministic);
 //   * REAL_A: the mask is real, so the first product needs two FMAs per term instead of four.
 template <int BM, int BN, int KG, bool REAL_A, bool EPILOGUE>
-__global__ void __launch_bounds__((BM / 4) * (BN / 4) * KG) zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__ B,
-                                                                        double2* __restrict__ C, int M, int N, int K) {
+__global__ void __launch_bounds__((BM / 4) * (BN / 4) * KG, KG > 1 ? 2 : 1)
+zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__ B, double2* __restrict__ C, int M, int N, int K, int ldb, int ldc,
+             int mirror_p) {
   constexpr int NT0 = (BM / 4) * (BN / 4), NT = NT0 * KG, SM_ROWS = BM / 4, SN_COLS = BN / 4;
   constexpr int A_DOUBLES = TK * (BM + 1) * (REAL_A ? 1 : 2), B_DOUBLES = TK * BN * 2, RED_DOUBLES = KG > 1 ? NT0 * 32 : 0;
   constexpr int SMEM_DOUBLES = (A_DOUBLES + B_DOUBLES) > RED_DOUBLES ? (A_DOUBLES + B_DOUBLES) : RED_DOUBLES;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4) * KG) zgemm_kernel(const d
     for (int q = 0; q < B_PER; q++) {  // B tile: 16 x BN
       const int e = threadIdx.x + q * NT, bk = e / BN, bn = e % BN;
       const int gk = k0 + bk, gn = n0 + bn;
-      pb[q] = (e < TK * BN && gk < K && gn < N) ? B[(size_t)gk * N + gn] : make_double2(0.0, 0.0);
+      pb[q] = (e < TK * BN && gk < K && gn < N) ? B[(size_t)gk * ldb + gn] : make_double2(0.0, 0.0);
     }
   };
   fetch(0);
@@ -260,8 +261,13 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4) * KG) zgemm_kernel(const d
     for (int j = 0; j < 4; j++) {
       const int gm = m0 + ty + SM_ROWS * i, gn = n0 + tx + SN_COLS * j;
       if (gm >= M || gn >= N) continue;
-      if (EPILOGUE) reinterpret_cast<double*>(C)[(size_t)gm * N + gn] = sqrt(acc[i][j].x * acc[i][j].x + acc[i][j].y * acc[i][j].y);
-      else C[(size_t)gm * N + gn] = acc[i][j];
+      if (EPILOGUE) {
+        reinterpret_cast<double*>(C)[(size_t)gm * ldc + gn] = sqrt(acc[i][j].x * acc[i][j].x + acc[i][j].y * acc[i][j].y);
+      } else {
+        C[(size_t)gm * ldc + gn] = acc[i][j];
+        // real A, lattice columns: C[., P - c] = conj C[., c]; only columns 0..P/2 were computed
+        if (mirror_p && gn > 0 && 2 * gn < mirror_p) C[(size_t)gm * ldc + (mirror_p - gn)] = make_double2(acc[i][j].x, -acc[i][j].y);
+      }
     }
 }
 
@@ -331,22 +337,23 @@ cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch
   E.rad_sum[0] = rad_sum[0]; E.rad_sum[1] = rad_sum[1]; E.rad_sum[2] = rad_sum[2];
   // tile size by problem size: 64 x 64 tiles once they fill the GPU twice over, 32 x 32 below that
   auto big = [](int m, int n) { return (size_t)((m + 63) / 64) * ((n + 63) / 64) >= 2 * 148; };
-  {  // G = Ac . E1   (bh x bw) . (bw x n_col); Ac is real
-    if (big(f.bh, f.n_col)) {
-      dim3 grid((f.n_col + 63) / 64, (f.bh + 63) / 64);
-      zgemm_kernel<64, 64, 1, true, false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, f.n_col, f.bw);
+  {  // G = Ac . E1   (bh x bw) . (bw x n_col); Ac is real.  On the column lattice G[., P - c] = conj G[., c]: half the columns
+    const int n_half = f.lattice_x ? f.period / 2 + 1 : f.n_col, mirror = f.lattice_x ? f.period : 0;
+    if (big(f.bh, n_half)) {
+      dim3 grid((n_half + 63) / 64, (f.bh + 63) / 64);
+      zgemm_kernel<64, 64, 1, true, false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, n_half, f.bw, f.n_col, f.n_col, mirror);
     } else {
-      dim3 grid((f.n_col + 31) / 32, (f.bh + 31) / 32);
-      zgemm_kernel<32, 32, 4, true, false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, f.n_col, f.bw);
+      dim3 grid((n_half + 31) / 32, (f.bh + 31) / 32);
+      zgemm_kernel<32, 32, 4, true, false><<<grid, 256, 0, s>>>(Ac, E1, G, f.bh, n_half, f.bw, f.n_col, f.n_col, mirror);
     }
   }
   {  // |F| = |E2 . G|   (n_row x bh) . (bh x n_col)
     if (big(f.n_row, f.n_col)) {
       dim3 grid((f.n_col + 63) / 64, (f.n_row + 63) / 64);
-      zgemm_kernel<64, 64, 1, false, true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh);
+      zgemm_kernel<64, 64, 1, false, true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh, f.n_col, f.n_col, 0);
     } else {
       dim3 grid((f.n_col + 31) / 32, (f.n_row + 31) / 32);
-      zgemm_kernel<32, 32, 4, false, true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh);
+      zgemm_kernel<32, 32, 4, false, true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh, f.n_col, f.n_col, 0);
     }
   }
   star_pixels_kernel<<<dim3((unsigned)((f.W + 255) / 256), (unsigned)f.H), 256, 0, s>>>(f, E, mag);
