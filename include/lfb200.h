@@ -274,6 +274,13 @@ int lfb_probe_peaks(lfb_engine* e, double* fp32_flops, double* mufu_ops, double*
 /* ---- pinned host memory helpers ---------------------------------------- */
 void* lfb_host_alloc(size_t bytes);  /* cudaHostAlloc; NULL on failure */
 void lfb_host_free(void* p);
+/* Page-lock memory the caller already owns -- e.g. the storage of the reference's
+ * HDRImageBuffer::data (std::vector<Vector3D>, util/image.h:239) -- so that lfb_render_ghosts
+ * copies the frame back at PCIe rate instead of through the driver's pageable staging.
+ * One-time cost of the order of the copy itself; undo before the memory is freed or
+ * reallocated.  Returns LFB_OK or LFB_ERR_CUDA (the memory then simply stays pageable). */
+int lfb_host_register(void* p, size_t bytes);
+int lfb_host_unregister(void* p);
 
 #ifdef __cplusplus
 }

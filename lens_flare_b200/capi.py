@@ -33,7 +33,7 @@ SYMBOLS = (
     "lfb_abi_version", "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
     "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_render_ghosts_async", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
     "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_reduce_finalize_peers", "lfb_peer_barrier", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
-    "lfb_host_alloc", "lfb_host_free", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
+    "lfb_host_alloc", "lfb_host_free", "lfb_host_register", "lfb_host_unregister", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
 )
 
 
@@ -179,6 +179,10 @@ def lib():
     L.lfb_host_alloc.restype = vp
     L.lfb_host_free.argtypes = [vp]
     L.lfb_host_free.restype = None
+    L.lfb_host_register.argtypes = [vp, C.c_size_t]
+    L.lfb_host_register.restype = C.c_int
+    L.lfb_host_unregister.argtypes = [vp]
+    L.lfb_host_unregister.restype = C.c_int
     L.lfb_set_starburst_aperture.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.c_int]
     L.lfb_render_starburst.argtypes = [vp, LiP, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, C.c_size_t, C.c_int, C.c_int]
     L.lfb_render_frame_rgba8.argtypes = [vp, LiP, C.c_int, PP, C.c_double, C.c_double, vp, vp, C.c_int]

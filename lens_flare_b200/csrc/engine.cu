@@ -1422,3 +1422,17 @@ extern "C" void* lfb_host_alloc(size_t bytes) {
 extern "C" void lfb_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
+
+extern "C" int lfb_host_register(void* p, size_t bytes) {
+  if (!p || bytes == 0) return fail(LFB_ERR_INVALID, "lfb_host_register: empty range");
+  const cudaError_t rc = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (rc != cudaSuccess) { cudaGetLastError(); return fail(LFB_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(rc)); }
+  return LFB_OK;
+}
+
+extern "C" int lfb_host_unregister(void* p) {
+  if (!p) return LFB_OK;
+  const cudaError_t rc = cudaHostUnregister(p);
+  if (rc != cudaSuccess) { cudaGetLastError(); return fail(LFB_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(rc)); }
+  return LFB_OK;
+}

@@ -1,6 +1,7 @@
 // flare_demo.cpp -- the reference application's flare flags on top of the C++ facade:
 //   flare_demo -r W H -y ghost_aperture.png [-x starburst_aperture.png] [-s ns_x ns_y] [-m ref|paraxial|exact] [-g N] [-f out.pfm|out.png]
 // (-r, -x, -y, -f as in src/application/main.cpp:87, 135-152).  Prints frame statistics as one JSON line.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +18,7 @@ int main(int argc, char** argv) {
   double sx = 0.45, sy = 0.55;
   int mode = LFB_MODE_REF_QUADS, grid = 256;
   double flare_intensity = 1.0, flare_radius = 30.0;  // -i / -n, main.cpp:135-152
+  int repeat = 0, pin = 1;                            // --repeat K: time K more generate_ghost_buffer() calls on the host clock
   if (argc == 3 && std::string(argv[1]) == "--png-info") {  // host-only: what CameraApertureTexture::init decodes
     try {
       lfb::CameraApertureTexture t;
@@ -55,6 +57,8 @@ int main(int argc, char** argv) {
     else if (k == "-g" && a + 1 < argc) grid = std::atoi(argv[++a]);
     else if (k == "-i" && a + 1 < argc) flare_intensity = std::atof(argv[++a]);
     else if (k == "-n" && a + 1 < argc) flare_radius = std::atof(argv[++a]);
+    else if (k == "--repeat" && a + 1 < argc) repeat = std::atoi(argv[++a]);
+    else if (k == "--no-pin") pin = 0;
     else if (k == "-m" && a + 1 < argc) {
       const std::string m = argv[++a];
       mode = m == "exact" ? LFB_MODE_EXACT_GRID : (m == "paraxial" ? LFB_MODE_PARAXIAL_GRID : LFB_MODE_REF_QUADS);
@@ -81,9 +85,16 @@ int main(int argc, char** argv) {
     pt.params.mode = mode;
     pt.params.grid_n = grid;
     if (mode != LFB_MODE_REF_QUADS) { pt.params.pair_set = LFB_PAIRS_ALL; pt.params.include_direct = 1; }
+    pt.pin_ghost_buffer = pin != 0;
     pt.set_frame_size(W, H);
     pt.find_sun_pos();
     pt.generate_ghost_buffer();
+    double host_ms = 0;
+    if (repeat > 0) {  // steady state of the drop-in call: what the application's render loop pays per frame
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int r = 0; r < repeat; r++) pt.generate_ghost_buffer();
+      host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / repeat;
+    }
     double sum[3] = {0, 0, 0}, l2 = 0;
     size_t nz = 0;
     for (const lfb::Vector3D& v : pt.ghost_buffer.data) {
@@ -92,9 +103,9 @@ int main(int argc, char** argv) {
       nz += (v.x != 0 || v.y != 0 || v.z != 0);
     }
     std::printf("{\"w\": %zu, \"h\": %zu, \"axis_ray\": [%.17g, %.17g], \"angle_to_sun\": %.9g, \"sum\": [%.17g, %.17g, %.17g], "
-                "\"l2\": %.17g, \"nonzero\": %zu, \"trace_ms\": %.4f, \"frame_ms\": %.4f, \"tex_total\": %.17g}\n",
+                "\"l2\": %.17g, \"nonzero\": %zu, \"trace_ms\": %.4f, \"frame_ms\": %.4f, \"host_ms_per_render\": %.4f, \"tex_total\": %.17g}\n",
                 W, H, pt.axis_ray.x, pt.axis_ray.y, pt.angle_to_sun, sum[0], sum[1], sum[2], std::sqrt(l2), nz, pt.last_trace_ms(),
-                pt.last_frame_ms(), ghost_tex.total_value);
+                pt.last_frame_ms(), host_ms, ghost_tex.total_value);
     if (!star_png.empty()) {  // the rest of raytrace_pixel's flare terms (:881-891) and the displayable frame
       pt.flare_radius = flare_radius;
       pt.flare_intensity = flare_intensity;

@@ -73,7 +73,24 @@ PathTracer::PathTracer(int device_id) : device_id_(device_id) {
   check(lfb_builtin_lens(&lens_, 3, 0.f), "lfb_builtin_lens");
 }
 
-PathTracer::~PathTracer() { lfb_destroy(engine_); }
+PathTracer::~PathTracer() {
+  unpin_storage();
+  lfb_destroy(engine_);
+}
+
+void PathTracer::unpin_storage() {
+  if (pinned_) lfb_host_unregister(pinned_);  // best effort: a failure leaves nothing to undo
+  pinned_ = nullptr;
+  pinned_bytes_ = 0;
+}
+
+void PathTracer::pin_storage() {
+  void* p = ghost_buffer.data.empty() ? nullptr : static_cast<void*>(ghost_buffer.data.data());
+  const size_t bytes = ghost_buffer.data.size() * sizeof(Vector3D);
+  if (p == pinned_ && bytes == pinned_bytes_) return;
+  unpin_storage();
+  if (p && lfb_host_register(p, bytes) == LFB_OK) { pinned_ = p; pinned_bytes_ = bytes; }  // else: stays pageable, still correct
+}
 
 void PathTracer::set_lens(const lfb_lens& lens) {
   lens_ = lens;
@@ -125,8 +142,14 @@ void PathTracer::generate_ghost_buffer() {
     for (int y = dirty_[1]; y <= dirty_[3]; y++)
       std::memset(static_cast<void*>(&ghost_buffer.data[(size_t)dirty_[0] + (size_t)y * frame_w_]), 0, sizeof(Vector3D) * (size_t)(dirty_[2] - dirty_[0] + 1));
   } else {
-    ghost_buffer.clear();
-    ghost_buffer.resize(frame_w_, frame_h_);
+    const bool sun = !(axis_ray.x == 0 && axis_ray.y == 0);
+    const bool same = ghost_buffer.w == frame_w_ && ghost_buffer.h == frame_h_ && ghost_buffer.data.size() == frame_w_ * frame_h_ && frame_w_ > 0;
+    const bool overwritten = !rect_mode && sun && pin_ghost_buffer;  // the full-frame render below writes every pixel
+    if (!(same && overwritten)) {
+      if (!same) unpin_storage();  // the vector may reallocate
+      ghost_buffer.clear();
+      ghost_buffer.resize(frame_w_, frame_h_);
+    }
   }
   dirty_[0] = dirty_[1] = 0; dirty_[2] = dirty_[3] = -1;
   if (axis_ray.x == 0 && axis_ray.y == 0) return;  // :724-726
@@ -139,9 +162,11 @@ void PathTracer::generate_ghost_buffer() {
   if (rect_mode)
     check(lfb_render_ghosts_rect(engine_, lights.data(), (int)lights.size(), &params, ghost_buffer.data.data(), sizeof(Vector3D), LFB_F64x3, dirty_),
           "lfb_render_ghosts_rect");
-  else
+  else {
+    if (pin_ghost_buffer) pin_storage(); else unpin_storage();
     check(lfb_render_ghosts(engine_, lights.data(), (int)lights.size(), &params, ghost_buffer.data.data(), sizeof(Vector3D), LFB_F64x3, 0),
           "lfb_render_ghosts");
+  }
 }
 
 void PathTracer::upload_textures(bool ghost, bool star) {

@@ -145,6 +145,11 @@ class PathTracer {
   // ghost_buffer.clear() to force a full reset.  EXACT_GRID ghosts throw stray rays across the frame, so that mode
   // always takes the full-frame path.
   bool dirty_rect_mode = true;
+  // Full-frame renders (EXACT_GRID): page-lock ghost_buffer's storage once (lfb_host_register) so the 24 B/pixel frame comes
+  // back at PCIe rate, and skip the host-side zero fill of clear() + resize() when the size is unchanged -- the render
+  // overwrites every pixel.  The storage is unregistered when it moves, changes size, or the PathTracer dies; do not
+  // reallocate ghost_buffer.data behind the PathTracer's back while this is on.
+  bool pin_ghost_buffer = true;
   // stats of the last generate_ghost_buffer(): device ms of the trace kernels and of the whole call
   float last_trace_ms() const;
   float last_frame_ms() const;
@@ -161,6 +166,10 @@ class PathTracer {
   void upload_textures(bool ghost, bool star);
   size_t frame_w_ = 0, frame_h_ = 0;
   int dirty_[4] = {0, 0, -1, -1};  // what the last frame wrote into ghost_buffer
+  void* pinned_ = nullptr;         // ghost_buffer storage currently page-locked
+  size_t pinned_bytes_ = 0;
+  void pin_storage();
+  void unpin_storage();
 };
 
 }  // namespace lfb

@@ -541,6 +541,46 @@ def test_host_mirror_generate_ghost_buffer(golden, apertures):
         pt.close()
 
 
+def test_registered_caller_memory_and_facade_pinning(engine, apertures, tmp_path):
+    """lfb_host_register page-locks memory the caller owns (the reference's std::vector<Vector3D> storage): the frame
+    rendered into it is the same frame.  The C++ facade pins ghost_buffer that way for full-frame renders and skips the
+    zero fill of clear() + resize() on repeats: same statistics with and without, first render and steady state."""
+    import json
+    import os
+    import subprocess
+    from PIL import Image
+    lens = capi.builtin_lens(3, 550.0)
+    engine.set_lens(lens)
+    engine.set_aperture(apertures["pentbig500_14"])
+    lt = [capi.make_light(0.45, 0.55, theta=capi.physical_theta(0.45, 0.55))]
+    p = capi.make_params(capi.MODE_EXACT_GRID, 640, 360, grid_n=64, pair_set=capi.PAIRS_ALL, include_direct=1)
+    want = engine.render_ghosts(lt, p)
+    mine = np.full((360, 640, 3), -1.0)  # pageable numpy memory
+    L = capi.lib()
+    assert L.lfb_host_register(mine.ctypes.data, mine.nbytes) == capi.OK
+    try:
+        got = engine.render_ghosts(lt, p, out=mine)
+        assert got is mine and np.array_equal(mine, want)
+    finally:
+        assert L.lfb_host_unregister(mine.ctypes.data) == capi.OK
+    assert L.lfb_host_register(None, 16) == capi.ERR_INVALID
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "lens_flare_b200", "host")
+    subprocess.run(["make", "-s", "-C", host], check=True)
+    png = tmp_path / "pentbig.png"
+    Image.fromarray(apertures["pentbig500_14_u8"], "L").save(png)
+    runs = {}
+    for name, extra in (("once", []), ("pinned", ["--repeat", "3"]), ("pageable", ["--repeat", "3", "--no-pin"])):
+        out = subprocess.run([os.path.join(host, "flare_demo"), "-r", "1920", "1080", "-y", str(png), "-s", "0.45", "0.55", "-m", "exact",
+                              "-g", "128"] + extra, check=True, capture_output=True, text=True).stdout
+        runs[name] = json.loads(out.splitlines()[0])
+    for name in ("pinned", "pageable"):
+        for k in ("sum", "l2", "nonzero"):
+            assert runs[name][k] == runs["once"][k], (name, k)
+        assert runs[name]["host_ms_per_render"] > 0
+    print("facade EXACT 1080p host ms per render: pinned %.3f, pageable %.3f" % (runs["pinned"]["host_ms_per_render"], runs["pageable"]["host_ms_per_render"]))
+
+
 def test_cpp_facade_end_to_end(golden, apertures, port, tmp_path):
     """The C++ host path (lens_flare_b200/host): PNG -> CameraApertureTexture -> DirectionalLight -> find_sun_pos ->
     generate_ghost_buffer -> ghost_buffer (Vector3D[]), through liblfb200.so, vs the oracle on the sun it found."""
