@@ -238,6 +238,11 @@ int lfb_render_ghosts_device(lfb_engine* e, const lfb_light* lights, int n_light
 /* accum (u64 fixed point) -> packed F32x3 / F64x3 pixels in device memory. */
 int lfb_finalize_device(lfb_engine* e, const void* accum_dev, const lfb_params* params,
                         void* out_dev, size_t out_stride_bytes, int out_elem);
+/* The same, and the accumulators are left zeroed (cleared as they are read): one launch instead of finalize +
+ * 24 B/pixel memset before the buffer's next frame (lfb_render_ghosts_device, clear_first = 0).  For serial hosts;
+ * a host that overlaps this with the next frame's trace is better off with the separate memset (measured). */
+int lfb_finalize_clear_device(lfb_engine* e, void* accum_dev, const lfb_params* params,
+                              void* out_dev, size_t out_stride_bytes, int out_elem);
 int lfb_sync(lfb_engine* e);
 /* Multi-GPU: fused reduce + finalize over NVLink peer memory (replaces an NCCL reduce followed by lfb_finalize_device).
  * accum_ptrs[r] is rank r's accumulator buffer AS MAPPED IN THIS PROCESS (CUDA IPC / symmetric memory); multicast_accum,

@@ -33,7 +33,7 @@ SYMBOLS = (
     "lfb_abi_version", "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
     "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_render_ghosts_async", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
     "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_reduce_finalize_peers", "lfb_peer_barrier", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
-    "lfb_host_alloc", "lfb_host_free", "lfb_host_register", "lfb_host_unregister", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
+    "lfb_host_alloc", "lfb_host_free", "lfb_host_register", "lfb_host_unregister", "lfb_finalize_clear_device", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
 )
 
 
@@ -169,6 +169,7 @@ def lib():
     L.lfb_stream.restype = vp
     L.lfb_render_ghosts_device.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_int]
     L.lfb_finalize_device.argtypes = [vp, vp, PP, vp, C.c_size_t, C.c_int]
+    L.lfb_finalize_clear_device.argtypes = [vp, vp, PP, vp, C.c_size_t, C.c_int]
     L.lfb_sync.argtypes = [vp]
     L.lfb_peer_barrier.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_uint64]
     L.lfb_reduce_finalize_peers.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, vp, PP, vp, C.c_size_t, C.c_int]
@@ -331,8 +332,10 @@ class Engine:
         check(lib().lfb_render_ghosts_device(self._h, lights_array(lights), len(lights), C.byref(params),
                                              accum_ptr, int(clear_first)))
 
-    def finalize_device(self, accum_ptr, params, out_ptr, stride, elem):
-        check(lib().lfb_finalize_device(self._h, accum_ptr, C.byref(params), out_ptr, stride, elem))
+    def finalize_device(self, accum_ptr, params, out_ptr, stride, elem, clear=False):
+        """accum -> pixels on the engine stream; clear=True also leaves the accumulators zeroed (one kernel)."""
+        fn = lib().lfb_finalize_clear_device if clear else lib().lfb_finalize_device
+        check(fn(self._h, accum_ptr, C.byref(params), out_ptr, stride, elem))
 
     def peer_barrier(self, flag_ptrs, rank, epoch):
         arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)

@@ -945,6 +945,21 @@ extern "C" int lfb_finalize_device(lfb_engine* e, const void* accum_dev, const l
   return LFB_OK;
 }
 
+extern "C" int lfb_finalize_clear_device(lfb_engine* e, void* accum_dev, const lfb_params* P, void* out_dev,
+                                         size_t out_stride_bytes, int out_elem) {
+  int rc = bind(e);
+  if (rc) return rc;
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (!accum_dev || !out_dev) return fail(LFB_ERR_INVALID, "NULL device pointer");
+  if (out_elem != LFB_F32x3 && out_elem != LFB_F64x3) return fail(LFB_ERR_INVALID, "unknown out_elem");
+  if (out_stride_bytes < elem_bytes(out_elem) || out_stride_bytes % (out_elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
+  const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+  CU(launch_finalize_clear((unsigned long long*)accum_dev, P->width, P->height, inv, out_dev, out_stride_bytes, out_elem, e->stream));
+  e->launches++;
+  return LFB_OK;
+}
+
 extern "C" int lfb_peer_barrier(lfb_engine* e, void* const* flag_ptrs, int n_ranks, int rank, uint64_t epoch) {
   int rc = bind(e);
   if (rc) return rc;

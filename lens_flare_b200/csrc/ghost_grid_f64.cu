@@ -72,14 +72,32 @@ cudaError_t launch_paraxial_setup(Job* jobs, int n_jobs, int physical_backward, 
 // finalize: u64 fixed point -> pixels.  One thread per pixel; the accumulators are read
 // once (24 B/px) and the output written once (12 or 24 B/px): purely HBM-bound.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) finalize_kernel(const unsigned long long* __restrict__ accum, size_t npx,
+// CLEAR: the accumulators are zeroed as they are read, so a pipelined host needs no separate 24 B/px memset per frame.
+template <bool CLEAR>
+__global__ void __launch_bounds__(256) finalize_kernel(unsigned long long* __restrict__ accum, size_t npx,
                                                        double inv_scale, char* __restrict__ out, size_t stride,
                                                        int elem, int additive) {
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long a[3] = {0ull, 0ull, 0ull};
+  if (p < npx) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) a[c] = CLEAR ? accum[3 * p + c] : __ldg(accum + 3 * p + c);  // read-only path only when nothing is written
+  }
+  if (CLEAR) {
+    // the CTA's 256 pixels are one contiguous, 16-byte aligned 6 KB range (256 * 24 B): once every thread has read its
+    // pixel, zero the range with coalesced 16-byte stores instead of three 8-byte stores at a 24-byte stride per thread
+    __syncthreads();
+    const size_t first = (size_t)blockIdx.x * blockDim.x * 3;                 // first u64 of this CTA's range (even)
+    const size_t last = (first + (size_t)blockDim.x * 3 < npx * 3) ? first + (size_t)blockDim.x * 3 : npx * 3;
+    ulonglong2* z = reinterpret_cast<ulonglong2*>(accum + first);
+    const size_t pairs = (last - first) / 2;
+    for (size_t q = threadIdx.x; q < pairs; q += blockDim.x) z[q] = make_ulonglong2(0ull, 0ull);
+    if (threadIdx.x == 0 && ((last - first) & 1)) accum[last - 1] = 0ull;
+  }
   if (p >= npx) return;
   double v[3];
 #pragma unroll
-  for (int c = 0; c < 3; c++) v[c] = (double)(long long)accum[3 * p + c] * inv_scale;
+  for (int c = 0; c < 3; c++) v[c] = (double)(long long)a[c] * inv_scale;
   if (elem == LFB_F32x3) {
     float* o = reinterpret_cast<float*>(out + p * stride);
     if (additive) { o[0] += (float)v[0]; o[1] += (float)v[1]; o[2] += (float)v[2]; }
@@ -252,7 +270,15 @@ cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long
 cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,
                             size_t stride, int elem, int additive, cudaStream_t s) {
   size_t npx = (size_t)W * H;
-  finalize_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(accum, npx, inv_scale, (char*)out, stride, elem, additive);
+  finalize_kernel<false><<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(const_cast<unsigned long long*>(accum), npx, inv_scale, (char*)out,
+                                                                       stride, elem, additive);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_clear(unsigned long long* accum, int W, int H, double inv_scale, void* out, size_t stride, int elem,
+                                  cudaStream_t s) {
+  size_t npx = (size_t)W * H;
+  finalize_kernel<true><<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(accum, npx, inv_scale, (char*)out, stride, elem, 0);
   return cudaGetLastError();
 }
 

@@ -113,6 +113,8 @@ cudaError_t launch_trace_dump_f64(const Job* job, const FrameGeom& g, int mode, 
                                   cudaStream_t s);
 cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,
                             size_t stride, int elem, int additive, cudaStream_t s);
+cudaError_t launch_finalize_clear(unsigned long long* accum, int W, int H, double inv_scale, void* out, size_t stride, int elem,
+                                  cudaStream_t s);
 struct PeerAccums {  // the ranks' sensor accumulators as mapped in THIS process (NVLink peer memory)
   const unsigned long long* ptr[LFB_MAX_PEERS];
   int n;

@@ -46,9 +46,14 @@ class ShardedFlare:
     steady-state frame time is max(trace, reduce, finalize) rather than their sum.  Everything is asynchronous;
     join() makes a torch stream wait for all three."""
 
-    def __init__(self, engine, params, rank, world_size, device, n_buffers=3, finalize_engine=None):
+    def __init__(self, engine, params, rank, world_size, device, n_buffers=3, finalize_engine=None, fused_clear=False):
         self.engine, self.rank, self.world_size, self.device = engine, rank, world_size, device
         self.fin_engine = finalize_engine if finalize_engine is not None else engine
+        # fused_clear: lfb_finalize_clear_device (one kernel converts and zeroes) instead of finalize + memset.  Measured on
+        # cfg2 (B200): 19.0 us vs 12.9 + 8.7 us as kernels, but the pipelined step got SLOWER (0.1167 vs 0.1114 ms) -- the
+        # read-modify-write kernel disturbs the co-running trace more than a pure streaming memset -- so it is off by default
+        # and meant for serial hosts, where it saves a launch.
+        self.fused_clear = fused_clear
         self.full_params = params
         self.params = shard_params(params, rank, world_size)
         self.accums = [accum_tensor(params, device) for _ in range(n_buffers)]
@@ -112,9 +117,12 @@ class ShardedFlare:
             torch.cuda.set_stream(prev)
             last = self.reduced[b]
         self.B.wait_event(last)
+        cleared = False
         if out is not None and (reduce_dst is None or self.world_size == 1 or self.rank == reduce_dst):
-            self.fin_engine.finalize_device(acc.data_ptr(), self.full_params, out.data_ptr(), out.stride(1) * out.element_size(), elem)
-        if not keep:
+            self.fin_engine.finalize_device(acc.data_ptr(), self.full_params, out.data_ptr(), out.stride(1) * out.element_size(), elem,
+                                            clear=self.fused_clear and not keep)
+            cleared = self.fused_clear and not keep
+        if not keep and not cleared:
             prev = torch.cuda.current_stream(self.device)
             torch.cuda.set_stream(self.B)
             acc.zero_()

@@ -541,6 +541,48 @@ def test_host_mirror_generate_ghost_buffer(golden, apertures):
         pt.close()
 
 
+@pytest.mark.parametrize("fused_clear", [False, True])
+def test_pipelined_frames_single_gpu(apertures, fused_clear):
+    """ShardedFlare on one GPU (trace | finalize + clear on a second engine's stream, rotating accumulators): a sequence of
+    DIFFERENT frames through the pipeline equals the blocking renders bit for bit -- every buffer is zeroed for its next
+    frame, by a memset or by the fused lfb_finalize_clear_device -- and keep=True leaves the sums readable."""
+    import torch
+    from lens_flare_b200 import sharding
+    dev = torch.device("cuda", 0)
+    eng, fin = capi.Engine(0), capi.Engine(0)
+    try:
+        lens = capi.builtin_lens(3, 550.0)
+        for e in (eng, fin):
+            e.set_lens(lens)
+            e.set_aperture(apertures["pentbig500_14"])
+        p = capi.make_params(capi.MODE_EXACT_GRID, 640, 360, grid_n=64, pair_set=capi.PAIRS_ALL, include_direct=1)
+        suns = [[capi.make_light(0.3 + 0.1 * k, 0.4 + 0.03 * k, theta=0.04 + 0.01 * k, radiance=(1.0, 0.5 + 0.1 * k, 2.0 - 0.2 * k))]
+                for k in range(5)]
+        want = [torch.from_numpy(eng.render_ghosts(lt, p, elem=capi.F32x3)) for lt in suns]
+        sh = sharding.ShardedFlare(eng, p, 0, 1, dev, n_buffers=2, finalize_engine=fin, fused_clear=fused_clear)
+        outs = [torch.zeros((360, 640, 3), dtype=torch.float32, device=dev) for _ in suns]
+        sh.begin()
+        for lt, out in zip(suns, outs):
+            sh.frame(lt, out=out, elem=capi.F32x3)
+        sh.join()
+        torch.cuda.synchronize()
+        for k, (out, w) in enumerate(zip(outs, want)):
+            assert torch.equal(out.cpu(), w), k
+        assert all(int(a.abs().max()) == 0 for a in sh.accums)
+        b = sh.frame(suns[0], out=outs[0], elem=capi.F32x3, keep=True)
+        sh.join()
+        torch.cuda.synchronize()
+        assert int(sh.accums[b].abs().max()) > 0 and torch.equal(outs[0].cpu(), want[0])
+        sh.frame(suns[1], out=outs[1], elem=capi.F32x3)  # the kept buffer's turn comes again after one more frame
+        sh.frame(suns[2], out=outs[2], elem=capi.F32x3)
+        sh.join()
+        torch.cuda.synchronize()
+        assert torch.equal(outs[1].cpu(), want[1]) and torch.equal(outs[2].cpu(), want[2])
+    finally:
+        fin.close()
+        eng.close()
+
+
 def test_registered_caller_memory_and_facade_pinning(engine, apertures, tmp_path):
     """lfb_host_register page-locks memory the caller owns (the reference's std::vector<Vector3D> storage): the frame
     rendered into it is the same frame.  The C++ facade pins ghost_buffer that way for full-frame renders and skips the
