@@ -153,6 +153,16 @@ struct lfb_engine {
   int slots_cap = 0, n_slots = 0;
   float4* d_prefix = nullptr;
   size_t prefix_cap = 0;
+  // prefix overlap: the forward sweeps of frame k+1 run on their own (high-priority) stream into the other of two caches while
+  // the ghost kernel of frame k still reads its own, when a host enqueues frames back to back (LFB_PREFIX_OVERLAP=0 disables)
+  float4* d_prefix2 = nullptr;
+  size_t prefix2_cap = 0;
+  bool prefix_overlap = true, frame_has_prefix2 = false;
+  cudaStream_t prefix_stream = nullptr;
+  cudaEvent_t ev_prefix_done[2] = {nullptr, nullptr}, ev_prefix_free[2] = {nullptr, nullptr}, ev_upload = nullptr;
+  bool prefix_free_valid[2] = {false, false};
+  bool upload_pending = true;  // tables / constants were (re)uploaded on `stream` since the last sweep on prefix_stream
+  int prefix_flip = 0;
   bool use_prefix = true;            // LFB_EXACT_PREFIX=0 disables
   size_t prefix_budget = (size_t)40 << 30;  // bytes of HBM the cache may take (LFB_PREFIX_BUDGET_MB)
   bool frame_has_prefix = false;
@@ -231,6 +241,7 @@ int upload_constants(lfb_engine* e) {
   CU(upload_lens_f64(e->dev_lens, e->stream));
   CU(upload_lens_ref(e->dev_lens, e->stream));
   if (e->device < 64) g_const_owner[e->device] = e;
+  e->upload_pending = true;
   return LFB_OK;
 }
 
@@ -469,6 +480,12 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
       int rc = grow(&e->d_prefix, &e->prefix_cap, need);
       if (rc == LFB_OK) e->frame_has_prefix = true;
       else if (rc != LFB_ERR_NOMEM) return rc;
+      e->frame_has_prefix2 = false;
+      if (e->frame_has_prefix && e->prefix_overlap && e->prefix_stream && 2 * need <= e->prefix_budget) {
+        rc = grow(&e->d_prefix2, &e->prefix2_cap, need);
+        if (rc == LFB_OK) e->frame_has_prefix2 = true;
+        else if (rc != LFB_ERR_NOMEM) return rc;
+      }
     }
   }
   if (e->frame_has_prefix) {
@@ -579,6 +596,7 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
     }
   }
   e->job_key.swap(key);
+  e->upload_pending = true;
   return LFB_OK;
 }
 
@@ -600,10 +618,30 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
   // x1.3), and lose ~8 % on a frame as small as cfg2 (5 376 CTAs = 3.6 waves), where the per-pair kernel keeps the SMs fuller.
   const long long fam_ctas = (long long)e->n_fams * ((P.grid_n + 15) / 16) * (((P.grid_n + 1) / 2 + 7) / 8);
   const bool families = e->frame_has_prefix && e->frame_has_family && g.lut && (e->force_family || fam_ctas >= 16384);
+  int overlap_buf = -1;
   if (e->n_jobs > 0 && e->frame_has_prefix && g.lut) {
-    CU(launch_prefix_f32(e->d_slots, e->d_slot_progs, e->n_slots, g, e->d_tex, e->d_prefix, families ? accum : nullptr, e->stream));
+    if (!families && !capturing && e->frame_has_prefix2) {
+      // forward sweeps on their own stream, alternating caches: they do not touch the sensor, so the sweeps of this frame may
+      // run while the previous frame's ghost kernel (reading the other cache) is still draining
+      const int b = e->prefix_flip;
+      e->prefix_flip ^= 1;
+      float4* cache = b ? e->d_prefix2 : e->d_prefix;
+      if (e->upload_pending) {  // the tables this sweep reads were just written on `stream`
+        CU(cudaEventRecord(e->ev_upload, e->stream));
+        CU(cudaStreamWaitEvent(e->prefix_stream, e->ev_upload, 0));
+        e->upload_pending = false;
+      }
+      if (e->prefix_free_valid[b]) CU(cudaStreamWaitEvent(e->prefix_stream, e->ev_prefix_free[b], 0));
+      CU(launch_prefix_f32(e->d_slots, e->d_slot_progs, e->n_slots, g, e->d_tex, cache, nullptr, e->prefix_stream));
+      CU(cudaEventRecord(e->ev_prefix_done[b], e->prefix_stream));
+      CU(cudaStreamWaitEvent(e->stream, e->ev_prefix_done[b], 0));
+      g.prefix = cache;
+      overlap_buf = b;
+    } else {
+      CU(launch_prefix_f32(e->d_slots, e->d_slot_progs, e->n_slots, g, e->d_tex, e->d_prefix, families ? accum : nullptr, e->stream));
+      g.prefix = e->d_prefix;
+    }
     e->launches++;
-    g.prefix = e->d_prefix;
   }
   if (families) {  // v7: one job per (light, lambda, first reflection); the direct path was splatted by the prefix kernel
     if (e->n_fams > 0) {
@@ -614,6 +652,10 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
     if (P.precision == LFB_FP64) CU(launch_trace_splat_f64(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
     else CU(launch_trace_splat_f32(e->d_jobs, e->d_progs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
     e->launches++;
+  }
+  if (overlap_buf >= 0) {  // the cache may be rewritten once this frame's ghost kernel is done with it
+    CU(cudaEventRecord(e->ev_prefix_free[overlap_buf], e->stream));
+    e->prefix_free_valid[overlap_buf] = true;
   }
   if (!capturing) {
     CU(cudaEventRecord(e->ev_trace1, e->stream));
@@ -697,6 +739,12 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   const char* prio_env = getenv("LFB_STREAM_PRIORITY");
   const int prio = (prio_env && !strcmp(prio_env, "high")) ? prio_hi : prio_lo;
   cudaError_t rc = cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio);
+  if (rc == cudaSuccess) rc = cudaStreamCreateWithPriority(&e->prefix_stream, cudaStreamNonBlocking, prio_hi);
+  for (int k = 0; k < 2 && rc == cudaSuccess; k++) {
+    rc = cudaEventCreateWithFlags(&e->ev_prefix_done[k], cudaEventDisableTiming);
+    if (rc == cudaSuccess) rc = cudaEventCreateWithFlags(&e->ev_prefix_free[k], cudaEventDisableTiming);
+  }
+  if (rc == cudaSuccess) rc = cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_frame0);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_trace0);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_trace1);
@@ -710,6 +758,7 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   if (const char* env = getenv("LFB_EXACT_MINB")) e->min_blocks = atoi(env);
   if (const char* env = getenv("LFB_EXACT_WEIGHTS")) e->use_lut = strcmp(env, "closed") != 0;
   if (const char* env = getenv("LFB_EXACT_PREFIX")) e->use_prefix = atoi(env) != 0;
+  if (const char* env = getenv("LFB_PREFIX_OVERLAP")) e->prefix_overlap = atoi(env) != 0;
   if (const char* env = getenv("LFB_EXACT_FAMILY")) { e->use_family = atoi(env) != 0; e->force_family = e->use_family; }
   if (const char* env = getenv("LFB_PREFIX_BUDGET_MB")) e->prefix_budget = (size_t)atoll(env) << 20;
   if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
@@ -723,7 +772,13 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
   cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox); cudaFree(e->d_lut);
-  cudaFree(e->d_slots); cudaFree(e->d_slot_progs); cudaFree(e->d_prefix);
+  cudaFree(e->d_slots); cudaFree(e->d_slot_progs); cudaFree(e->d_prefix); cudaFree(e->d_prefix2);
+  if (e->prefix_stream) { cudaStreamSynchronize(e->prefix_stream); cudaStreamDestroy(e->prefix_stream); }
+  for (int k = 0; k < 2; k++) {
+    if (e->ev_prefix_done[k]) cudaEventDestroy(e->ev_prefix_done[k]);
+    if (e->ev_prefix_free[k]) cudaEventDestroy(e->ev_prefix_free[k]);
+  }
+  if (e->ev_upload) cudaEventDestroy(e->ev_upload);
   cudaFree(e->d_fams); cudaFree(e->d_fam_progs);
   if (e->h_fams) cudaFreeHost(e->h_fams);
   if (e->h_fam_progs) cudaFreeHost(e->h_fam_progs);
@@ -901,6 +956,7 @@ extern "C" int lfb_set_aperture(lfb_engine* e, const float* texels, int w, int h
   CU(cudaMemcpyAsync(e->d_tex, texels, bytes, cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));  // the caller may free texels on return
   e->has_tex = true;
+  e->upload_pending = true;
   return LFB_OK;
 }
 
