@@ -889,9 +889,12 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat3_kernel(const Job* __res
 
   const int a = blockIdx.x * 16 + (tid & 15), bp = blockIdx.y * PH + (tid >> 4);
   const int b = g.N - 1 - bp;
-  int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
-  float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
-  float2 ww = make_float2(0.f, 0.f);
+  // Only lanes whose ray (or its mirror image) lands carry a sensor point, weights and a footprint: nothing below reads
+  // them on the other lanes, so the trace loop's many death exits need no sentinel values kept in registers.
+  int bx0, by0, bx1, by1;
+  float4 pp;
+  float2 ww;
+  bool lands = false;
   if (a < g.N && bp < half_rows) {
     RayState r;
     RayOut o;
@@ -913,6 +916,9 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat3_kernel(const Job* __res
     }
     if (alive) {
       int x0, y0, x1, y1;
+      bx0 = by0 = 0x7fffffff; bx1 = by1 = -0x7fffffff;
+      pp = make_float4(0.f, 0.f, 0.f, 0.f);
+      ww = make_float2(0.f, 0.f);
       if (o.wa > 0.f) {
         to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
         if (footprint(bilinear, pp.x, pp.y, g.W, g.H, x0, y0, x1, y1)) {
@@ -925,12 +931,18 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat3_kernel(const Job* __res
           ww.y = o.wb; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
         }
       }
+      lands = ww.x > 0.f || ww.y > 0.f;
     }
   }
-  const bool lands = ww.x > 0.f || ww.y > 0.f;
-  if (!__any_sync(0xffffffffu, lands)) return;  // the whole warp is done: nothing below involves other warps
-  bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
-  bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+  const unsigned landing = __ballot_sync(0xffffffffu, lands);
+  if (!landing) return;  // the whole warp is done: nothing below involves other warps
+  if (lands) {  // the footprint of the warp's landing rays, reduced among those lanes only
+    bx0 = __reduce_min_sync(landing, bx0); by0 = __reduce_min_sync(landing, by0);
+    bx1 = __reduce_max_sync(landing, bx1); by1 = __reduce_max_sync(landing, by1);
+  }
+  const int leader = __ffs(landing) - 1;
+  bx0 = __shfl_sync(0xffffffffu, bx0, leader); by0 = __shfl_sync(0xffffffffu, by0, leader);
+  bx1 = __shfl_sync(0xffffffffu, bx1, leader); by1 = __shfl_sync(0xffffffffu, by1, leader);
   if (lane == 0) grow_bbox(g.bbox, bx0, by0, bx1, by1);
   SplatCtx C;
   C.tx0 = bx0; C.ty0 = by0;
@@ -945,8 +957,10 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat3_kernel(const Job* __res
     for (int q = lane; q < 3 * area; q += 32) tile[q] = 0ull;
     __syncwarp();
   }
-  if (ww.x > 0.f) splat1(C, pp.x, pp.y, ww.x);
-  if (ww.y > 0.f) splat1(C, pp.z, pp.w, ww.y);
+  if (lands) {
+    if (ww.x > 0.f) splat1(C, pp.x, pp.y, ww.x);
+    if (ww.y > 0.f) splat1(C, pp.z, pp.w, ww.y);
+  }
   if (!use_tile) return;
   __syncwarp();
   const float inv_tw = frcp((float)C.tw);
