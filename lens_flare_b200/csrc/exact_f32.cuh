@@ -90,7 +90,7 @@ struct MaskGeom {
 __device__ __forceinline__ float mask_lookup(const MaskGeom& M, float xa, float ya) {
   const float fu = floorf(fmaf(xa, M.su, M.ou)), fv = floorf(fmaf(ya, M.sv, M.ov));
   if (!(fu >= 0.f && fu < (float)M.tw && fv >= 0.f && fv < (float)M.th)) return 0.f;
-  return __ldg(M.tex + (int)fv * M.tw + (int)fu);
+  return __ldg(M.tex + ((unsigned)(int)fv * (unsigned)M.tw + (unsigned)(int)fu));  // in range, checked above
 }
 
 // What one traced ray yields.  The bundle of a distant light is mirror-symmetric about the meridional
@@ -110,7 +110,7 @@ struct RayOut {
 __device__ __forceinline__ float reflectance_lut(const float2* __restrict__ lut, int table, float v) {
   const float t = fminf(fmaxf(v, 0.f), 1.f) * (float)kLutSize;  // fmaxf(NaN, 0) = 0: beyond the critical angle R = 1
   const int i = min((int)t, kLutSize - 1);
-  const float2 e = __ldg(lut + table * kLutSize + i);
+  const float2 e = __ldg(lut + ((unsigned)table * (unsigned)kLutSize + (unsigned)i));  // unsigned: one IMAD.WIDE.U32, no sign extension
   return fmaf(t - (float)i, e.y, e.x);
 }
 
