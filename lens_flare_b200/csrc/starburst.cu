@@ -9,8 +9,8 @@
 // it SEPARATES, so the whole frame is two complex matrix products
 //     G[yc, x] = sum_xc A[yc, xc] E1[xc, x]          E1 = exp(j 2 pi u_xc (lr - x'(x)))          (bh x bw) . (bw x W)
 //     F[y,  x] = sum_yc E2[y, yc] G[yc, x]           E2 = exp(j 2 pi v_yc (ud - y'(y)))          (H x bh) . (bh x W)
-// -- 6.6 GFLOP for a 1080p frame instead of 2.6e11 sincos pairs -- followed by a per-pixel epilogue fused into the second
-// product.  FP64 throughout (the reference is double; the parity tolerance is 1e-9 relative on the DFT scalar).
+// -- 6.6 GFLOP for a 1080p frame instead of 2.6e11 sincos pairs -- followed by a per-pixel epilogue kernel.  FP64
+// throughout (the reference is double; the parity tolerance is 1e-9 relative on the DFT scalar).
 //
 // PERIODICITY.  alpha(x) = lr - x'(x) and beta(y) = ud - y'(y) are always INTEGERS (the W/2 and H/2 cancel), and
 // u_xc alpha = (xc - W_t/2) alpha / W_t, so E1 only depends on alpha mod P with P = W_t (W_t even) or 2 W_t; likewise E2 on
@@ -18,10 +18,15 @@
 // on the P-periodic lattice only -- 7x fewer FLOPs at 1080p -- and every pixel looks its |F| up at
 // (beta(y) mod P, alpha(x) mod P); with the reduced arguments the twiddles are also more accurate than the reference's.
 //
+// HERMITIAN SYMMETRY.  The mask is real and u_xc P, v_yc P are integers, so on the lattice E1[xc, P - c] = conj E1[xc, c],
+// G[yc, P - c] = conj G[yc, c] and F[P - r, P - c] = conj F[r, c]: the first product computes columns 0..P/2 (two FMAs per
+// term, mirrored on store), the second rows 0..P/2, and a pixel in the other half reads |F| at (P - r, P - c).
+//
 //   twiddle_kernel            E1 / E2 / complex copy of the mask's bounding box
 //   zgemm_kernel<...>         tiled complex FP64 GEMM (32x32 or 64x64 tile per CTA, 4x4 outputs per thread, K step 16,
 //                             K-split thread groups for the small lattice products)
-//   the EPILOGUE variant      |F| / total -> suppression (dist > W_t/2: factor^8) / amplification (dist <= radius:
+//                             EPILOGUE: stores |F| only
+//   star_pixels_kernel        |F| / total -> suppression (dist > W_t/2: factor^8) / amplification (dist <= radius:
 //                             I^(dist/radius)) -> I^(3 - flare_intensity) -> x sum of radiance + falloff -> caller layout
 #include "lfb_internal.h"
 
