@@ -28,6 +28,7 @@
 //   exact_splat1_kernel  v4  one pass with tabulated reflectances, CTA-level queue and tile      LFB_EXACT_PREFIX=0
 //   exact_splat2_kernel  v5  + prefix cache                                                      LFB_EXACT_WARP=0
 //   exact_splat3_kernel  v6  + warp-autonomous splat (default for small frames)                  LFB_EXACT_FAMILY=0
+//   exact_splat4_kernel  v6i v6 with two ray pairs per thread in lockstep (opt-in: +1 % only)     LFB_EXACT_ILP=2
 //   exact_family_kernel  v7  ghost families: one thread per (ray, first reflection), forks at every second reflection
 //                            (default from 16 384 family CTAs up; LFB_EXACT_FAMILY=1 forces it)
 // Parity: per-ray and image tolerances against the double-precision oracle are in tests/test_gpu_parity.py; the FP64
@@ -974,6 +975,190 @@ __global__ void __launch_bounds__(BT, MINB) exact_splat3_kernel(const Job* __res
       if (v) atomicAdd(dst + c, v);
     }
   }
+}
+
+// v6i: TWO RAY PAIRS PER THREAD IN LOCKSTEP (opt-in, LFB_EXACT_ILP=2).  The final v6 capture is latency bound (1.3 eligible
+// of 9.9 active warps per scheduler): here a thread carries the ray pairs of rows bp and bp + PH through the SAME step
+// program with straight-line code -- two independent dependency chains per warp instruction stream, the step constants
+// read from shared memory once for both.  Death needs no branch: a dead ray is a NaN state that stays NaN (the table and
+// mask lookups clamp NaN indices), and the loop only exits when both are dead.  Same arithmetic per ray => same bits.
+__device__ __forceinline__ void propagate2(const Step& S, RayState& r, bool& alive) {  // propagate<> without the branch
+  const float c = S.c;
+  const float pz = r.oz + S.dz;
+  const float pd = fmaf(r.ox, r.dx, fmaf(r.oy, r.dy, pz * r.dz));
+  const float pp = fmaf(r.ox, r.ox, fmaf(r.oy, r.oy, pz * pz));
+  const float B = fmaf(c, pd, -r.dz);
+  const float Cq = fmaf(c, pp, -2.f * pz);
+  const float disc = fmaf(B, B, -c * Cq);
+  const float t = -Cq * frcp(B + copysignf(fsqrt(disc), B));
+  r.ox = fmaf(t, r.dx, r.ox); r.oy = fmaf(t, r.dy, r.oy); r.oz = fmaf(t, r.dz, pz);
+  alive = alive && (fmaf(r.ox, r.ox, r.oy * r.oy) <= S.semi2);
+}
+__device__ __forceinline__ void bend2(const Step& S, bool refl, const float2* __restrict__ lut, RayState& r) {  // interact<2,...>
+  const float c = S.c, eta = S.eta;
+  const float nx = -c * r.ox, ny = -c * r.oy, nz = fmaf(-c, r.oz, 1.f);
+  const float nd = fmaf(nx, r.dx, fmaf(ny, r.dy, nz * r.dz));
+  const float c0 = fabsf(nd);
+  const float s2 = fmaf(-c0, c0, 1.f);
+  const float k2 = fmaf(-S.eta2, s2, 1.f);
+  const float c2 = fsqrt(k2);
+  const float g = __int_as_float(__float_as_int(fmaf(eta, c0, -c2)) ^ (~__float_as_int(nd) & 0x80000000));
+  const float alpha = refl ? 1.f : eta, beta = refl ? -2.f * nd : g;
+  r.dx = fmaf(alpha, r.dx, beta * nx); r.dy = fmaf(alpha, r.dy, beta * ny); r.dz = fmaf(alpha, r.dz, beta * nz);
+  const float R = reflectance_lut(lut, S.lut, eta > 1.f ? c2 : c0);
+  r.w *= refl ? R : 1.f - R;
+}
+// one step for the lane's two rays: every (uniform) branch is taken once for both, so the two chains share basic blocks
+__device__ __forceinline__ void step_pair(const Step& S, const MaskGeom& M, const float2* __restrict__ lut, RayState& r0, RayState& r1,
+                                          bool& al0, bool& al1) {
+  propagate2(S, r0, al0);
+  propagate2(S, r1, al1);
+  const int op = S.op;
+  if (op >= STEP_PASS) {
+    if (op == STEP_STOP) {
+      r0.ma *= mask_lookup(M, r0.ox, r0.oy);
+      r1.ma *= mask_lookup(M, r1.ox, r1.oy);
+      r0.mb *= mask_lookup(M, r0.ox, -r0.oy);
+      r1.mb *= mask_lookup(M, r1.ox, -r1.oy);
+      al0 = al0 && !(r0.ma == 0.f && r0.mb == 0.f);
+      al1 = al1 && !(r1.ma == 0.f && r1.mb == 0.f);
+    }
+    return;
+  }
+  const bool refl = op == STEP_REFLECT;
+  bend2(S, refl, lut, r0);
+  bend2(S, refl, lut, r1);
+}
+
+// the landing / tile / flush phase of one ray pair per lane (what exact_splat3_kernel does after its trace)
+__device__ __forceinline__ void warp_land(const FrameGeom& g, const Job& J, const PixMap& PM, bool bilinear, bool alive, const RayOut& o,
+                                          bool has_mirror, unsigned long long* tile, unsigned long long* __restrict__ accum, int lane) {
+  int bx0, by0, bx1, by1;
+  float4 pp;
+  float2 ww;
+  bool lands = false;
+  if (alive) {
+    int x0, y0, x1, y1;
+    bx0 = by0 = 0x7fffffff; bx1 = by1 = -0x7fffffff;
+    pp = make_float4(0.f, 0.f, 0.f, 0.f);
+    ww = make_float2(0.f, 0.f);
+    if (o.wa > 0.f) {
+      to_pixel(PM, o.xs, o.ys, pp.x, pp.y);
+      if (footprint(bilinear, pp.x, pp.y, g.W, g.H, x0, y0, x1, y1)) {
+        ww.x = o.wa; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+      }
+    }
+    if (o.wb > 0.f && has_mirror) {
+      to_pixel(PM, o.xs, -o.ys, pp.z, pp.w);
+      if (footprint(bilinear, pp.z, pp.w, g.W, g.H, x0, y0, x1, y1)) {
+        ww.y = o.wb; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+      }
+    }
+    lands = ww.x > 0.f || ww.y > 0.f;
+  }
+  const unsigned landing = __ballot_sync(0xffffffffu, lands);
+  if (!landing) return;
+  if (lands) {
+    bx0 = __reduce_min_sync(landing, bx0); by0 = __reduce_min_sync(landing, by0);
+    bx1 = __reduce_max_sync(landing, bx1); by1 = __reduce_max_sync(landing, by1);
+  }
+  const int leader = __ffs(landing) - 1;
+  bx0 = __shfl_sync(0xffffffffu, bx0, leader); by0 = __shfl_sync(0xffffffffu, by0, leader);
+  bx1 = __shfl_sync(0xffffffffu, bx1, leader); by1 = __shfl_sync(0xffffffffu, by1, leader);
+  if (lane == 0) grow_bbox(g.bbox, bx0, by0, bx1, by1);
+  SplatCtx C;
+  C.tx0 = bx0; C.ty0 = by0;
+  C.tw = bx1 - bx0 + 1;
+  const int area = C.tw * (by1 - by0 + 1);
+  const bool use_tile = area <= kWarpTilePx;
+  C.tile = use_tile ? tile : nullptr;
+  C.accum = accum; C.W = g.W; C.H = g.H; C.bilinear = bilinear;
+  C.ch0 = J.f_chan[0]; C.ch1 = J.f_chan[1]; C.ch2 = J.f_chan[2];
+  if (use_tile) {
+    for (int q = lane; q < 3 * area; q += 32) tile[q] = 0ull;
+    __syncwarp();
+  }
+  if (lands) {
+    if (ww.x > 0.f) splat1(C, pp.x, pp.y, ww.x);
+    if (ww.y > 0.f) splat1(C, pp.z, pp.w, ww.y);
+  }
+  if (!use_tile) return;
+  __syncwarp();
+  const float inv_tw = frcp((float)C.tw);
+  for (int t = lane; t < area; t += 32) {
+    const int jy = (int)(((float)t + 0.5f) * inv_tw);
+    const int jx = t - jy * C.tw;
+    unsigned long long* dst = accum + 3 * ((size_t)(bx0 + jx) + (size_t)(by0 + jy) * g.W);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const unsigned long long v = tile[3 * t + c];
+      if (v) atomicAdd(dst + c, v);
+    }
+  }
+  __syncwarp();  // the tile is reused by the lane's second ray pair
+}
+
+template <int MINB, int BT>
+__global__ void __launch_bounds__(BT, MINB) exact_splat4_kernel(const Job* __restrict__ jobs, const Step* __restrict__ progs,
+                                                                FrameGeom g, const float* __restrict__ tex,
+                                                                unsigned long long* __restrict__ accum) {
+  constexpr int PH = BT / 16;  // BT threads = 16 x PH lanes, each with the ray pairs of rows bp and bp + PH
+  __shared__ Step s_prog[LFB_MAX_STEPS];
+  __shared__ unsigned long long s_tile[(BT / 32) * kWarpTilePx * 3];
+  const int half_rows = (g.N + 1) / 2;
+  const int job_id = blockIdx.z;
+  const Job& J = jobs[job_id];
+  const int n_steps = J.n_steps;
+  const int tid = threadIdx.x, lane = tid & 31;
+  {
+    const float4* src = reinterpret_cast<const float4*>(progs + (size_t)job_id * LFB_MAX_STEPS);
+    float4* dst = reinterpret_cast<float4*>(s_prog);
+    for (int q = tid; q < n_steps * 3; q += BT) dst[q] = __ldg(src + q);
+  }
+  __syncthreads();  // the only CTA-wide barrier
+  MaskGeom M;
+  M.tex = tex; M.tw = g.tex_w; M.th = g.tex_h;
+  M.su = g.mask_su; M.ou = g.mask_ou; M.sv = g.mask_sv; M.ov = g.mask_ov;
+  PixMap PM;
+  PM.sx = J.f_sx; PM.sy = J.f_sy; PM.cs = J.f_cs; PM.sn = J.f_sn; PM.ppu = J.f_ppu;
+  const bool bilinear = g.splat == LFB_SPLAT_BILINEAR;
+  const int a = blockIdx.x * 16 + (tid & 15);
+  const int bp0 = blockIdx.y * (2 * PH) + (tid >> 4), bp1 = bp0 + PH;
+  RayState r0, r1;
+  bool al0 = a < g.N && bp0 < half_rows, al1 = a < g.N && bp1 < half_rows;
+  int s_begin = 0;
+  if (J.slot >= 0) {  // (uniform) both states start ON the first-reflection surface, from the prefix cache
+    const float4* base = g.prefix + ((size_t)(J.slot * g.n_surf + J.j_first) * 2) * g.half_rays;
+    const float4 nanv = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, 0.f);
+    const float4 p0 = al0 ? __ldg(base + ((size_t)bp0 * g.N + a)) : nanv;
+    const float4 p1 = al1 ? __ldg(base + ((size_t)bp1 * g.N + a)) : nanv;
+    al0 = al0 && p0.x == p0.x;
+    al1 = al1 && p1.x == p1.x;
+    const float4 q0 = al0 ? __ldg(base + g.half_rays + ((size_t)bp0 * g.N + a)) : nanv;
+    const float4 q1 = al1 ? __ldg(base + g.half_rays + ((size_t)bp1 * g.N + a)) : nanv;
+    r0.ox = p0.x; r0.oy = p0.y; r0.oz = p0.z; r0.w = p0.w; r0.dx = q0.x; r0.dy = q0.y; r0.ma = q0.z; r0.mb = q0.w;
+    r1.ox = p1.x; r1.oy = p1.y; r1.oz = p1.z; r1.w = p1.w; r1.dx = q1.x; r1.dy = q1.y; r1.ma = q1.z; r1.mb = q1.w;
+    r0.dz = fsqrt(fmaxf(fmaf(-r0.dx, r0.dx, fmaf(-r0.dy, r0.dy, 1.f)), 0.f));
+    r1.dz = fsqrt(fmaxf(fmaf(-r1.dx, r1.dx, fmaf(-r1.dy, r1.dy, 1.f)), 0.f));
+    RayOut o;  // interact<> wants one; unused in the throughput variant
+    if (al0) al0 = interact<2, true, false>(s_prog[0], M, g.lut, r0, o);  // step 0: interaction only
+    if (al1) al1 = interact<2, true, false>(s_prog[0], M, g.lut, r1, o);
+    s_begin = 1;
+  } else {  // the direct path (or a job without a cached sweep): from the entrance grid
+    start_ray(r0, fmaf((float)a + 0.5f, g.cell, -g.P), fmaf((float)(g.N - 1 - bp0) + 0.5f, g.cell, -g.P), J.f_sin_t, J.f_cos_t, J.f_inv_dist);
+    start_ray(r1, fmaf((float)a + 0.5f, g.cell, -g.P), fmaf((float)(g.N - 1 - bp1) + 0.5f, g.cell, -g.P), J.f_sin_t, J.f_cos_t, J.f_inv_dist);
+  }
+#pragma unroll 1
+  for (int s = s_begin; s < n_steps && (al0 || al1); s++) {
+    const Step& S = s_prog[s];
+    step_pair(S, M, g.lut, r0, r1, al0, al1);
+  }
+  unsigned long long* tile = s_tile + (tid >> 5) * (kWarpTilePx * 3);
+  RayOut o0, o1;
+  o0.xs = r0.ox; o0.ys = r0.oy; o0.wa = r0.w * r0.ma; o0.wb = r0.w * r0.mb;
+  o1.xs = r1.ox; o1.ys = r1.oy; o1.wa = r1.w * r1.ma; o1.wb = r1.w * r1.mb;
+  warp_land(g, J, PM, bilinear, al0, o0, (g.N - 1 - bp0) != bp0, tile, accum, lane);
+  warp_land(g, J, PM, bilinear, al1, o1, (g.N - 1 - bp1) != bp1, tile, accum, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -36,6 +36,16 @@ cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_job
   } while (0)
     static int warp_mode = -1;
     if (warp_mode < 0) { const char* env = getenv("LFB_EXACT_WARP"); warp_mode = env ? atoi(env) : 1; }
+    // read per launch (not cached) so that one process can compare the generations
+    const char* ilp_env = getenv("LFB_EXACT_ILP");
+    const int ilp_mode = ilp_env ? atoi(ilp_env) : 1;
+    if (warp_mode && g.patch <= 1 && ilp_mode == 2) {  // v6i: two ray pairs per thread in lockstep (opt-in)
+      const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + 15) / 16, n_jobs);  // 128 threads = 16 x 8 lanes x 2 rows each
+      if (nb.y > 65535u || nb.z > 65535u) return cudaErrorInvalidConfiguration;
+      if (g.pad >= 10) xf32::exact_splat4_kernel<10, 128><<<nb, 128, 0, s>>>(jobs, progs, g, tex, accum);
+      else xf32::exact_splat4_kernel<8, 128><<<nb, 128, 0, s>>>(jobs, progs, g, tex, accum);
+      return cudaGetLastError();
+    }
     if (warp_mode && g.patch <= 1) {  // v6: warp-autonomous splat (default)
       const int rows = bt / 16;
       const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + rows - 1) / rows, n_jobs);  // (patch column, patch row, job)

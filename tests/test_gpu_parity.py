@@ -439,7 +439,7 @@ def test_exact_fp32_patch_variants_agree(engine, apertures, monkeypatch):
 
 
 def test_exact_fp32_kernel_generations_agree(engine, port, apertures, monkeypatch):
-    """The throughput kernel's variants -- v7 (ghost families, the default), v6 (one job per ghost, warp-autonomous splat), v5 (CTA-level queue and tile), v4 (no prefix cache,
+    """The throughput kernel's variants -- v7 (ghost families, the default), v6 (one job per ghost, warp-autonomous splat), v6i (v6 with two ray pairs per thread, LFB_EXACT_ILP=2), v5 (CTA-level queue and tile), v4 (no prefix cache,
     LFB_EXACT_PREFIX=0) and v3 (closed-form Fresnel, two passes, LFB_EXACT_WEIGHTS=closed) -- render the same frame: each
     within 1e-3 of the double oracle, v5 vs v4 within 1e-6 (same arithmetic, different kernels), multi-light and ragged N."""
     lens = capi.builtin_lens(3, 550.0)
@@ -447,9 +447,10 @@ def test_exact_fp32_kernel_generations_agree(engine, port, apertures, monkeypatc
     p = capi.make_params(capi.MODE_EXACT_GRID, 800, 450, grid_n=90, pair_set=capi.PAIRS_ALL, include_direct=1)
     want = port.render(lens, apertures["pentbig500_14"], lt, p)
     frames = {}
-    for name, env in (("v7", {"LFB_EXACT_FAMILY": "1"}), ("v6", {"LFB_EXACT_FAMILY": "0"}), ("v5", {"LFB_EXACT_FAMILY": "0", "LFB_EXACT_WARP": "0"}),
+    for name, env in (("v7", {"LFB_EXACT_FAMILY": "1"}), ("v6", {"LFB_EXACT_FAMILY": "0"}), ("v6i", {"LFB_EXACT_FAMILY": "0", "LFB_EXACT_ILP": "2"}),
+                      ("v5", {"LFB_EXACT_FAMILY": "0", "LFB_EXACT_WARP": "0"}),
                       ("v4", {"LFB_EXACT_PREFIX": "0"}), ("v3", {"LFB_EXACT_WEIGHTS": "closed"})):
-        for k in ("LFB_EXACT_PREFIX", "LFB_EXACT_WEIGHTS", "LFB_EXACT_WARP", "LFB_EXACT_FAMILY"):
+        for k in ("LFB_EXACT_PREFIX", "LFB_EXACT_WEIGHTS", "LFB_EXACT_WARP", "LFB_EXACT_FAMILY", "LFB_EXACT_ILP"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -465,6 +466,7 @@ def test_exact_fp32_kernel_generations_agree(engine, port, apertures, monkeypatc
             e.close()
         assert rel_l2(frames[name], want) <= 1e-3, name
     assert np.array_equal(frames["v7"], frames["v6"])   # ghost families: the same arithmetic along every ghost path
+    assert np.array_equal(frames["v6i"], frames["v6"])  # two ray pairs per thread in lockstep (opt-in): the same rays, the same bits
     # (without LFB_EXACT_FAMILY the engine picks by frame size: families from 16 384 family CTAs up)
     assert np.array_equal(frames["v6"], frames["v5"])   # same rays, same arithmetic, integer sums: only the splat grouping differs
     assert rel_l2(frames["v5"], frames["v4"]) <= 1e-6
