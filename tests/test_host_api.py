@@ -122,6 +122,13 @@ def test_no_cpu_fallback(native_lib):
         pt.generate_ghost_buffer()
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps every exported function of include/lfb200.h to the reference interface it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [name for name in capi.SYMBOLS if name not in doc]
+    assert not missing, missing
+
+
 def test_product_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under lens_flare_b200/ may reference it."""
     pkg = os.path.join(ROOT, "lens_flare_b200")
