@@ -152,11 +152,16 @@ typedef struct lfb_ref_ghost {
 } lfb_ref_ghost;
 
 /* ---- lifecycle -------------------------------------------------------- */
+/* LFB_ABI_VERSION of the library that was loaded (no reference counterpart: the reference is one binary). */
 int lfb_abi_version(void);
-/* One engine per CUDA device (one process per GPU under torchrun; a C++ host may
- * create several).  device_id < 0 -> current device. */
+/* Replaces `new PathTracer` (raytraced_renderer.cpp:58) for the ghost path.  One engine per CUDA device (one
+ * process per GPU under torchrun; a C++ host may create several).  device_id < 0 -> current device.  Fails with
+ * LFB_ERR_NO_DEVICE without an sm_100 GPU: there is no CPU fallback. */
 int lfb_create(lfb_engine** out, int device_id);
+/* Replaces `delete pt` (raytraced_renderer.cpp:104). */
 void lfb_destroy(lfb_engine* e);
+/* The message of this thread's last failing call.  The reference has no error channel (it prints and goes on,
+ * camera.h:40-44, or exit()s in its parsers); every int-returning entry point here returns 0 or a negative lfb_status. */
 const char* lfb_last_error(void);
 
 /* ---- inputs ----------------------------------------------------------- */
@@ -165,6 +170,8 @@ const char* lfb_last_error(void);
  * wavelengths uniform on [400,700] nm with a piecewise two-term Cauchy n(lambda)
  * (linear in 1/lambda^2) through the R,G,B anchors at 650/550/450 nm.  coating_lambda0_nm > 0 coats every glass surface. */
 int lfb_builtin_lens(lfb_lens* lens, int n_lambda, float coating_lambda0_nm);
+/* Replaces the file-scope prescription and its derived matrices: Ts, red/green/blue_refr, curvatures, Ls, R_red/green/blue
+ * (pathtracer.cpp:539-586) and the constants 14.5 / 11.6 / -11.5 (:737, :621-625).  The engine copies the struct. */
 int lfb_set_lens(lfb_engine* e, const lfb_lens* lens);
 /* Replaces Camera::ghost_aperture_texture (camera.h:175, filled by
  * CameraApertureTexture::init, camera.h:26-83): row-major y*w+x, values in [0,1]. */
@@ -179,7 +186,8 @@ int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_lights,
                       const lfb_params* params, void* out, size_t out_stride_bytes,
                       int out_elem, int additive);
 
-/* lfb_render_ghosts without the wait (grid modes, overwrite semantics): the frame's device->host copy runs on a second
+/* No reference counterpart (the reference renders one frame per call, raytraced_renderer.cpp:303-311).
+ * lfb_render_ghosts without the wait (grid modes, overwrite semantics): the frame's device->host copy runs on a second
  * stream out of one of two device buffers and overlaps the next frame's trace.  `out` (pinned memory for a truly
  * asynchronous copy) is complete after lfb_sync(); alternate between two host buffers to keep two frames in flight. */
 int lfb_render_ghosts_async(lfb_engine* e, const lfb_light* lights, int n_lights,
@@ -194,13 +202,14 @@ int lfb_render_ghosts_rect(lfb_engine* e, const lfb_light* lights, int n_lights,
                            const lfb_params* params, void* out, size_t out_stride_bytes,
                            int out_elem, int* rect_out);
 
-/* Parity instrument: trace the N x N grid of one ghost (i, j, lambda) of one light
+/* Parity instrument (no reference counterpart; PARAXIAL_GRID records are what trace_ray_auto_before / _after,
+ * pathtracer.cpp:588-689, return per axis): trace the N x N grid of one ghost (i, j, lambda) of one light
  * and return every ray's record (grid modes only).  i = j = -1 selects the direct path. */
 int lfb_dump_rays(lfb_engine* e, const lfb_light* light, const lfb_params* params,
                   int i, int j, int lambda, lfb_ray_hit* out, size_t cap);
 
-/* REF_QUADS introspection: the ghosts the device set up for the last REF_QUADS frame
- * (trace_ray_auto_* results and draw_ghost vertices). Returns the count or <0. */
+/* REF_QUADS introspection (no reference counterpart): the ghosts the device set up for the last REF_QUADS frame --
+ * the trace_ray_auto_* results (pathtracer.cpp:738-757) and the draw_ghost vertices (:433-508).  Returns the count or <0. */
 int lfb_ref_ghosts(lfb_engine* e, lfb_ref_ghost* out, int cap);
 
 /* ---- starburst (the diffraction pattern of the aperture) ----------------- */
@@ -227,6 +236,9 @@ int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, int n_lights,
                            uint32_t* out_rgba8, int flip_vertical);
 
 /* ---- device-resident API (multi-GPU sharding, benchmarking) ------------- */
+/* No reference counterparts in this section: the reference is a single-process CPU program.  Together these calls are
+ * generate_ghost_buffer (pathtracer.cpp:714-762) split into its device stages so that one process per GPU can shard a
+ * frame by (light, ghost pair, wavelength) and sum the shards. */
 /* Sensor accumulators: width*height*3 u64 fixed-point sums, owned by the caller. */
 size_t lfb_accum_bytes(int width, int height);
 /* The engine's CUDA stream (cudaStream_t) so callers can order work / record events. */
@@ -243,22 +255,23 @@ int lfb_finalize_device(lfb_engine* e, const void* accum_dev, const lfb_params* 
  * a host that overlaps this with the next frame's trace is better off with the separate memset (measured). */
 int lfb_finalize_clear_device(lfb_engine* e, void* accum_dev, const lfb_params* params,
                               void* out_dev, size_t out_stride_bytes, int out_elem);
+/* Wait for everything enqueued on the engine's streams (what the blocking calls do before they return). */
 int lfb_sync(lfb_engine* e);
-/* Multi-GPU: fused reduce + finalize over NVLink peer memory (replaces an NCCL reduce followed by lfb_finalize_device).
- * accum_ptrs[r] is rank r's accumulator buffer AS MAPPED IN THIS PROCESS (CUDA IPC / symmetric memory); multicast_accum,
- * when not NULL, is the same buffer's NVSwitch multicast address (the switch performs the additions).  This rank converts
- * the pixels [rank*npx/n, (rank+1)*npx/n) and stores them into out_dev, the OWNER rank's output buffer as mapped here.
- * The caller orders this call after every rank's lfb_render_ghosts_device (a device-side barrier on lfb_stream) and reads
- * the owner's buffer after another one.  Integer sums: the frame has the same bits for any rank count. */
 /* Device-side barrier across the ranks of one node, enqueued on lfb_stream: flag_ptrs[r] is rank r's flag array
  * (LFB_MAX_PEERS zero-initialised u64, symmetric / IPC memory) as mapped in this process; epoch must increase by one per
  * barrier.  Work enqueued before it on every rank is complete and visible to work enqueued after it on any rank. */
 int lfb_peer_barrier(lfb_engine* e, void* const* flag_ptrs, int n_ranks, int rank, uint64_t epoch);
+/* Multi-GPU: fused reduce + finalize over NVLink peer memory (replaces an NCCL reduce followed by lfb_finalize_device).
+ * accum_ptrs[r] is rank r's accumulator buffer AS MAPPED IN THIS PROCESS (CUDA IPC / symmetric memory); multicast_accum,
+ * when not NULL, is the same buffer's NVSwitch multicast address (the switch performs the additions).  This rank converts
+ * the pixels [rank*npx/n, (rank+1)*npx/n) and stores them into out_dev, the OWNER rank's output buffer as mapped here.
+ * The caller orders this call after every rank's lfb_render_ghosts_device (lfb_peer_barrier) and reads
+ * the owner's buffer after another one.  Integer sums: the frame has the same bits for any rank count. */
 int lfb_reduce_finalize_peers(lfb_engine* e, const void* const* accum_ptrs, int n_ranks, int rank,
                               const void* multicast_accum, const lfb_params* params, void* out_dev,
                               size_t out_stride_bytes, int out_elem);
 
-/* ---- accounting --------------------------------------------------------- */
+/* ---- accounting (no reference counterparts) ------------------------------ */
 /* Ray-surface interactions (I(i,j) = 2(j-i) + n_surfaces + 1 per ray,
  * n_surfaces + 1 for the direct path) and rays this shard traces for one frame. */
 int lfb_count_work(const lfb_lens* lens, const lfb_params* params, int n_lights,
@@ -276,8 +289,9 @@ int lfb_stats(lfb_engine* e, uint64_t* kernel_launches, float* last_trace_ms, fl
  * (Hz) seen while they ran. */
 int lfb_probe_peaks(lfb_engine* e, double* fp32_flops, double* mufu_ops, double* sm_clock_hz);
 
-/* ---- pinned host memory helpers ---------------------------------------- */
-void* lfb_host_alloc(size_t bytes);  /* cudaHostAlloc; NULL on failure */
+/* ---- pinned host memory helpers (no reference counterparts) -------------- */
+/* cudaHostAlloc / cudaFreeHost for callers that stage frames themselves; NULL on failure. */
+void* lfb_host_alloc(size_t bytes);
 void lfb_host_free(void* p);
 /* Page-lock memory the caller already owns -- e.g. the storage of the reference's
  * HDRImageBuffer::data (std::vector<Vector3D>, util/image.h:239) -- so that lfb_render_ghosts
