@@ -42,6 +42,8 @@ static void lambda_to_rgb(double lam, double rgb[3]) {
     if (rgb[c] < 0) rgb[c] = 0;
 }
 
+/* The file-scope prescription of pathtracer.cpp:539-556 as an lfb_lens (+ ours: wavelengths other than the reference's
+ * three tables, and the coating flag -- neither exists in the reference). */
 int lfo_builtin_lens(lfb_lens* L, int n_lambda, float coating_lambda0_nm) {
   if (!L || n_lambda < 1 || n_lambda > LFB_MAX_LAMBDA) return LFB_ERR_INVALID;
   memset(L, 0, sizeof(*L));
@@ -143,6 +145,7 @@ static m2 surf_R(const lfb_lens* L, int lambda, int k) { /* create_Rs_for_color 
   return mR(L->curvature[k], n_before(L, lambda, k), L->ior[lambda][k]);
 }
 
+/* The reference's globals Ts / Ls / R_<colour> (pathtracer.cpp:559-586) as 2x2 blocks, for the golden comparison. */
 void lfo_prescription(const lfb_lens* L, int lambda, double* t, double* l, double* r) {
   for (int k = 0; k < L->n_surfaces; k++) {
     m2 T = mT(L->thickness[k]), Lm = mL(L->curvature[k]), R = surf_R(L, lambda, k);
@@ -165,6 +168,8 @@ static void reaim(const lfb_lens* L, m2 M, float r, float theta, double ray[2]) 
   }
 }
 
+/* trace_ray_auto_before (pathtracer.cpp:588-641, which = 0) and trace_ray_auto_after (:643-689, which = 1), including the
+ * by-value matrix products in the reference's order and the stop re-aim; pinned bit for bit by tests/golden/ref_vectors.npz. */
 void lfo_trace_ray_auto(const lfb_lens* L, int lambda, int which, float r, float theta, int i,
                         int j, double out[2]) {
   const int n = L->n_surfaces, stop = L->stop_index;
@@ -329,6 +334,8 @@ static int list_pairs(const lfb_lens* L, int pair_set, int pairs[][2]) {
   return n;
 }
 
+/* PathTracer::generate_ghost_buffer (pathtracer.cpp:714-762): 13 pairs x 3 colours of marginal rays -> draw_ghost ->
+ * two textured triangles each, accumulated in double; pinned bit for bit to the compiled reference (tests/golden/ref_vectors.npz). */
 int lfo_generate_ghost_buffer(const lfb_lens* L, const float* tex, int tw, int th, int W, int H,
                               double ax, double ay, float angle, double* out,
                               lfb_ref_ghost* ghosts, int cap) {
@@ -357,6 +364,8 @@ int lfo_generate_ghost_buffer(const lfb_lens* L, const float* tex, int tw, int t
 /* ------------------------------------------------------------------------- */
 /* PARAXIAL_GRID: per-ghost system matrices                                   */
 /* ------------------------------------------------------------------------- */
+/* The matrix chain of trace_ray_auto_* (pathtracer.cpp:588-689) WITHOUT the stop re-aim, split at every stop crossing;
+ * physical_backward = 1 replaces the reference's R_k^-1 on the backward legs (:607-608) by the physical refraction (ours). */
 int lfo_paraxial_system(const lfb_lens* L, int lambda, int i, int j, int physical_backward,
                         double cross[3][4], double full[4]) {
   const int n = L->n_surfaces, stop = L->stop_index;
@@ -426,6 +435,9 @@ static void to_pixel(const pixmap* m, double xs, double ys, double* px, double* 
 /* ------------------------------------------------------------------------- */
 /* EXACT_GRID physics (absent from the reference; see lf_oracle.h)            */
 /* ------------------------------------------------------------------------- */
+/* Fresnel reflectance of a bare interface, or of one carrying a quarter-wave film designed for lambda0 (Hullin et al. 2011,
+ * the formulas quoted in SURVEY.md 8c).  PARITY UNPINNED by the reference (its Fresnel code is an empty stub,
+ * advanced_bsdf.cpp:52-60); pinned by the analytic invariants of tests/test_oracle_physics.py. */
 double lfo_reflectance(double n0, double n2, double cos0, double lambda0, double lambda) {
   if (n0 == n2) return 0.0;
   double sin2 = 1.0 - cos0 * cos0;
@@ -609,6 +621,8 @@ static void trace_one(const lfb_lens* L, const float* tex, int tw, int th, const
   }
 }
 
+/* Per-ray records of one ghost's N x N grid (the checker for lfb_dump_rays): PARAXIAL_GRID applies the reference's system
+ * matrices per axis (pinned through lfo_trace_ray_auto); EXACT_GRID is ours (unpinned by the reference, see above). */
 int lfo_trace_grid(const lfb_lens* L, const float* tex, int tw, int th, const lfb_light* lt,
                    const lfb_params* P, int i, int j, int lambda, lfb_ray_hit* out) {
   if (P->mode != LFB_MODE_PARAXIAL_GRID && P->mode != LFB_MODE_EXACT_GRID) return LFB_ERR_INVALID;
@@ -711,6 +725,8 @@ static int list_jobs(const lfb_lens* L, const lfb_params* P, int n_lights, job_t
   return n;
 }
 
+/* A whole frame in any mode, with the engine's job list, sharding and u64 fixed-point deposits restated (ours: the
+ * reference has none of these; REF_QUADS delegates to lfo_generate_ghost_buffer). */
 int lfo_render(const lfb_lens* L, const float* tex, int tw, int th, const lfb_light* lights,
                int n_lights, const lfb_params* P, double* out, int64_t* accum) {
   const size_t npx = (size_t)P->width * P->height;
@@ -748,6 +764,9 @@ static double convert_coordinate(int pixel_coord, int length, int is_y) { /* :93
   return cc >= 0 ? cc : length + cc;
 }
 
+/* PathTracer::raytrace_starburst (pathtracer.cpp:947-1004) + compute_phase (:918-934) + convertCoordinate (:936-945) +
+ * calculate_irradiance_falloff (:1030-1052, its 16 random samples replaced by the 4x4 stratified midpoints), brute force per
+ * pixel like the reference; the DFT scalar is pinned to the compiled reference by tests/golden/starburst.npz. */
 int lfo_starburst_pixels(const float* tex, int tw, int th, int W, int H, int n_lights, const double* fo,
                          const double* rad, double flare_radius, double flare_intensity, const int* xs,
                          const int* ys, int n, double* out_dft, double* out_falloff) {
@@ -818,7 +837,7 @@ int lfo_starburst_pixels(const float* tex, int tw, int th, int W, int H, int n_l
   return LFB_OK;
 }
 
-/* util/image.h:208-223 + :53-62 */
+/* HDRImageBuffer::toColor (util/image.h:208-223) + ImageBuffer::update_pixel (:53-62); pinned bit for bit by tests/golden/tocolor.npz. */
 void lfo_to_color(const double* hdr, int W, int H, uint32_t* out) {
   const float gamma = 2.2f, level = 1.0f;
   const float one_over_gamma = 1.0f / gamma;
@@ -857,6 +876,7 @@ static void* worker(void* arg) {
   return NULL;
 }
 
+/* Wall-clock of lfo_render's ghost jobs on nthreads pthreads: bench.py's cpu_baseline "port" leg (no reference counterpart). */
 double lfo_time_render(const lfb_lens* L, const float* tex, int tw, int th, const lfb_light* lights,
                        int n_lights, const lfb_params* P, int nthreads, double* checksum) {
   if (nthreads < 1) nthreads = 1;
