@@ -255,9 +255,9 @@ def run_ours(args):
     lights_a = [make_sun(x, y) for x, y in sun_positions(n_lights)]
     lights_b = [make_sun(1.0 - x, 1.0 - y) for x, y in sun_positions(n_lights)]  # e2e alternates frames (same off-axis angle)
     rays_frame, inter_frame, jobs_frame = capi.count_work(lens, params, n_lights)
-    os.environ["LFB_STREAM_PRIORITY"] = "high"  # the finalize / reduce engine's short kernels slip in between trace CTAs
-    fin = capi.Engine(local)  # a second engine = a second stream: converts frame k to pixels while frame k+1 traces
-    os.environ.pop("LFB_STREAM_PRIORITY", None)
+    # a second engine = a second stream: converts frame k to pixels while frame k+1 traces; high priority so that its short
+    # kernels slip in between the trace CTAs
+    fin = capi.Engine(local, stream_priority=1)
     N_BUF = 3                 # rotating accumulator / output sets: 3 x (49.8 + 24.9 MB) > the 126 MB L2
     sh = sharding.ShardedFlare(eng, params, rank, world, dev, n_buffers=N_BUF, finalize_engine=fin)
     _, inter_rank, jobs_rank = capi.count_work(lens, sh.params, n_lights)

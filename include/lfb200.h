@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LFB_ABI_VERSION 2
+#define LFB_ABI_VERSION 3
 #define LFB_MAX_SURFACES 16
 #define LFB_MAX_LAMBDA 64
 #define LFB_MAX_PEERS 16
@@ -62,7 +62,14 @@ enum lfb_pairset { LFB_PAIRS_REF = 0, LFB_PAIRS_ALL = 1 };
  * is 24, or 32 when the reference is built with -mavx, CGL/include/CGL/vector3D.h:30-43). */
 enum lfb_elem { LFB_F32x3 = 0, LFB_F64x3 = 1 };
 
-enum lfb_precision { LFB_FP32 = 0, LFB_FP64 = 1 };
+/* Arithmetic of the grid modes.
+ * LFB_FP32    the throughput kernels north_star asks for: FP32 geometry and weights (images <= 1e-3 relative L2 of the
+ *             double oracle; per-ray sensor positions ~1e-5 RELATIVE, i.e. up to ~1e-2 lens units on the most defocused ghosts).
+ * LFB_FP64    the oracle-order parity kernels: every operation in double, in the order of oracle/lf_oracle.c, so that the
+ *             fixed-point sensor sums agree bit for bit.  Instruments, not throughput kernels.
+ * LFB_STRICT  EXACT_GRID only: the throughput kernels with FP64 positions and directions (FP32 weights): per-ray sensor
+ *             positions within 1e-5 lens units ABSOLUTE of the oracle (north_star's per-ray bar; measured ~1e-9). */
+enum lfb_precision { LFB_FP32 = 0, LFB_FP64 = 1, LFB_STRICT = 2 };
 enum lfb_splat { LFB_SPLAT_NEAREST = 0, LFB_SPLAT_BILINEAR = 1 };
 
 /* Per-ray flags reported by lfb_dump_rays. */
@@ -130,7 +137,13 @@ typedef struct lfb_params {
                                        (light, lambda) groups round-robin when there are at least shard_count groups,
                                        else single jobs, longest first, round-robin; 0,0 -> all */
   float px_per_unit;       /* sensor pixels per lens unit; 0 -> 0.4 (pathtracer.cpp:457-463) */
-  float reserved[3];
+  int32_t physical_mapping; /* grid modes.  0 = the reference's screen mapping (draw_ghost / shift_vertex, pathtracer.cpp:412-430,
+                               457-463): origin at the sun pixel, ghosts laid out along atan((ay-.5)/(ax-.5)) -- an angle mod pi, so
+                               the ghosts of a sun left of centre are mirrored through the sun.  1 = the physical mapping: origin at
+                               the image centre, the meridional axis along the light's azimuth atan2, a sensor point (xs, ys)
+                               drawn at centre + ppu (xs u + ys v): with px_per_unit = W / (2 f tan(hFov/2)) the direct image of
+                               the light lands on its own pixel (Camera::analyze_world_coord, camera.cpp:245-273). */
+  float reserved[2];
 } lfb_params;
 
 /* Per-ray record of lfb_dump_rays (parity instrument). */
@@ -151,6 +164,26 @@ typedef struct lfb_ref_ghost {
   float scale, shift;
 } lfb_ref_ghost;
 
+/* Engine options (lfb_create_ex).  Zero-initialise, set struct_size = sizeof(lfb_options), change what you need: 0 always
+ * means "the default".  No reference counterpart (the reference has no tunables on this path); the library reads NO
+ * environment variables. */
+typedef struct lfb_options {
+  int32_t struct_size;        /* sizeof(lfb_options) of the caller (fields beyond it are taken as 0) */
+  int32_t stream_priority;    /* 0: default priority; 1: highest -- for a second engine whose short kernels (finalize, reduce)
+                                 must slip in between the CTAs of another engine's long trace kernel on the same device */
+  int32_t kernel_select;      /* EXACT_GRID throughput kernels: 0 = by frame size (one job per ghost pair for small frames,
+                                 ghost families from 16 384 family CTAs up), 1 = always per pair, 2 = always families */
+  int32_t family_split;       /* > 0: at most this many forks per family job */
+  int32_t ctas_per_sm;        /* register-allocation target of the ghost / family kernels: 0 = default, 1 = the alternative build */
+  int32_t prefix_overlap;     /* forward sweeps of frame k+1 overlap the ghost kernel of frame k: 0 = on, -1 = off */
+  int32_t starburst_lattice;  /* starburst on the aperture's periodic lattice: 0 = when the frame is larger than the period, -1 = never */
+  int32_t starburst_cache;    /* keep the lattice spectrum |F| between frames (it depends on the mask alone): 0 = on, -1 = off */
+  int32_t reduce_ctas;        /* CTAs of the cross-GPU reduce kernels: 0 = one per SM */
+  int32_t collect_stats;      /* 1: run the counting instantiation of the EXACT_GRID kernels (lfb_exec_stats); slower */
+  int64_t prefix_budget_bytes; /* device memory the cached forward sweeps may take: 0 = 40 GiB; < 0 = no cache */
+  int32_t reserved[8];
+} lfb_options;
+
 /* ---- lifecycle -------------------------------------------------------- */
 /* LFB_ABI_VERSION of the library that was loaded (no reference counterpart: the reference is one binary). */
 int lfb_abi_version(void);
@@ -158,6 +191,8 @@ int lfb_abi_version(void);
  * process per GPU under torchrun; a C++ host may create several).  device_id < 0 -> current device.  Fails with
  * LFB_ERR_NO_DEVICE without an sm_100 GPU: there is no CPU fallback. */
 int lfb_create(lfb_engine** out, int device_id);
+/* lfb_create with options (NULL = defaults).  No reference counterpart. */
+int lfb_create_ex(lfb_engine** out, int device_id, const lfb_options* options);
 /* Replaces `delete pt` (raytraced_renderer.cpp:104). */
 void lfb_destroy(lfb_engine* e);
 /* The message of this thread's last failing call.  The reference has no error channel (it prints and goes on,
@@ -283,6 +318,12 @@ int lfb_list_jobs(const lfb_lens* lens, const lfb_params* params, int n_lights,
 /* Kernels launched by this engine since creation, and the device time (ms, CUDA
  * events on the engine stream) of the trace/splat and raster kernels of the last frame. */
 int lfb_stats(lfb_engine* e, uint64_t* kernel_launches, float* last_trace_ms, float* last_frame_ms);
+/* What the EXACT_GRID throughput kernels actually executed for the last frame rendered by an engine created with
+ * options.collect_stats = 1 (the counting instantiation; waits for the engine's stream): out[0] = surface steps executed
+ * (one ray reaching one surface or the sensor; mirror pairs, the shared forward sweep and early deaths make this ~10x
+ * fewer than the NOMINAL interactions lfb_count_work reports), out[1] = ray pairs started, out[2] = ray pairs landed.
+ * out[3] = 1 when the frame ran the family kernel, 0 for the per-pair kernel. */
+int lfb_exec_stats(lfb_engine* e, uint64_t out[4]);
 
 /* Live roofline denominators for the scalar pipes the trace is bound by: FP32 FLOP/s (FMA = 2)
  * and MUFU op/s of this GPU measured by two register-only micro-kernels, plus the SM clock

@@ -18,19 +18,19 @@ CSRC = os.path.join(HERE, "csrc")
 
 MAX_SURFACES = 16
 MAX_LAMBDA = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 MODE_REF_QUADS, MODE_PARAXIAL_GRID, MODE_EXACT_GRID = 0, 1, 2
 PAIRS_REF, PAIRS_ALL = 0, 1
 F32x3, F64x3 = 0, 1
-FP32, FP64 = 0, 1
+FP32, FP64, STRICT = 0, 1, 2
 SPLAT_NEAREST, SPLAT_BILINEAR = 0, 1
 RAY_MISSED, RAY_VIGNETTED, RAY_TIR, RAY_STOPPED, RAY_OFF_SENSOR = 1, 2, 4, 8, 16
 
 # every symbol include/lfb200.h declares (tests check the library exports each one)
 SYMBOLS = (
-    "lfb_abi_version", "lfb_create", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
+    "lfb_abi_version", "lfb_create", "lfb_create_ex", "lfb_exec_stats", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
     "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_render_ghosts_async", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
     "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_reduce_finalize_peers", "lfb_peer_barrier", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
     "lfb_host_alloc", "lfb_host_free", "lfb_host_register", "lfb_host_unregister", "lfb_finalize_clear_device", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
@@ -63,8 +63,25 @@ class Params(C.Structure):
         ("width", C.c_int32), ("height", C.c_int32), ("precision", C.c_int32), ("splat", C.c_int32),
         ("fixed_point_bits", C.c_int32), ("physical_backward", C.c_int32),
         ("shard_index", C.c_int32), ("shard_count", C.c_int32),
-        ("px_per_unit", C.c_float), ("reserved", C.c_float * 3),
+        ("px_per_unit", C.c_float), ("physical_mapping", C.c_int32), ("reserved", C.c_float * 2),
     ]
+
+
+class Options(C.Structure):
+    """lfb_options (lfb_create_ex): zeros = defaults."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("stream_priority", C.c_int32), ("kernel_select", C.c_int32), ("family_split", C.c_int32),
+        ("ctas_per_sm", C.c_int32), ("prefix_overlap", C.c_int32), ("starburst_lattice", C.c_int32), ("starburst_cache", C.c_int32),
+        ("reduce_ctas", C.c_int32), ("collect_stats", C.c_int32), ("prefix_budget_bytes", C.c_int64), ("reserved", C.c_int32 * 8),
+    ]
+
+
+def make_options(**fields):
+    o = Options()
+    o.struct_size = C.sizeof(Options)
+    for k, v in fields.items():
+        setattr(o, k, v)
+    return o
 
 
 RAY_HIT_DTYPE = np.dtype([("x_s", "f8"), ("y_s", "f8"), ("x_ap", "f8"), ("y_ap", "f8"), ("px", "f8"),
@@ -152,6 +169,8 @@ def lib():
     LP, LiP, PP, vp = C.POINTER(Lens), C.POINTER(Light), C.POINTER(Params), C.c_void_p
     L.lfb_abi_version.restype = C.c_int
     L.lfb_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.lfb_create_ex.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Options)]
+    L.lfb_exec_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.lfb_destroy.argtypes = [vp]
     L.lfb_destroy.restype = None
     L.lfb_last_error.restype = C.c_char_p
@@ -241,9 +260,13 @@ class PinnedArray:
 class Engine:
     """Owner of one lfb_engine (one CUDA device)."""
 
-    def __init__(self, device_id=-1):
+    def __init__(self, device_id=-1, **options):
+        """options: fields of lfb_options (stream_priority=1, kernel_select=2, collect_stats=1, ...)."""
         self._h = C.c_void_p()
-        check(lib().lfb_create(C.byref(self._h), device_id))
+        if options:
+            check(lib().lfb_create_ex(C.byref(self._h), device_id, C.byref(make_options(**options))))
+        else:
+            check(lib().lfb_create(C.byref(self._h), device_id))
         self.lens = None
 
     def close(self):
@@ -352,6 +375,12 @@ class Engine:
         n, t, f = C.c_uint64(), C.c_float(), C.c_float()
         check(lib().lfb_stats(self._h, C.byref(n), C.byref(t), C.byref(f)))
         return dict(kernel_launches=n.value, last_trace_ms=t.value, last_frame_ms=f.value)
+
+    def exec_stats(self):
+        """Executed work of the last EXACT_GRID frame (engine created with collect_stats=1)."""
+        out = (C.c_uint64 * 4)()
+        check(lib().lfb_exec_stats(self._h, out))
+        return dict(steps=out[0], ray_pairs_started=out[1], ray_pairs_landed=out[2], families=bool(out[3]))
 
     def probe_peaks(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

@@ -116,7 +116,8 @@ int check_params(const lfb_params* P, bool need_grid) {
     if (P->mode == LFB_MODE_REF_QUADS) return fail(LFB_ERR_INVALID, "this call needs a grid mode");
     if (P->grid_n < 1 || P->grid_n > 32768) return fail(LFB_ERR_INVALID, "grid_n out of range");
     if (P->pair_set != LFB_PAIRS_REF && P->pair_set != LFB_PAIRS_ALL) return fail(LFB_ERR_INVALID, "unknown pair_set");
-    if (P->precision != LFB_FP32 && P->precision != LFB_FP64) return fail(LFB_ERR_INVALID, "unknown precision");
+    if (P->precision != LFB_FP32 && P->precision != LFB_FP64 && P->precision != LFB_STRICT) return fail(LFB_ERR_INVALID, "unknown precision");
+    if (P->precision == LFB_STRICT && P->mode != LFB_MODE_EXACT_GRID) return fail(LFB_ERR_INVALID, "LFB_STRICT applies to LFB_MODE_EXACT_GRID only");
     if (P->splat != LFB_SPLAT_NEAREST && P->splat != LFB_SPLAT_BILINEAR) return fail(LFB_ERR_INVALID, "unknown splat");
     if (P->fixed_point_bits < 0 || P->fixed_point_bits > 56) return fail(LFB_ERR_INVALID, "fixed_point_bits out of range");
   }
@@ -131,6 +132,7 @@ size_t elem_bytes(int elem) { return elem == LFB_F32x3 ? 12 : 24; }
 
 struct lfb_engine {
   int device = 0;
+  lfb_options opt;  // as given to lfb_create_ex (0 = default everywhere)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_frame0 = nullptr, ev_trace0 = nullptr, ev_trace1 = nullptr, ev_frame1 = nullptr;
   bool has_lens = false, has_tex = false, timed = false;
@@ -144,39 +146,37 @@ struct lfb_engine {
   int jobs_cap = 0, n_jobs = 0;
   std::vector<unsigned char> job_key;
   Job* d_dump_job = nullptr;
-  Step* d_progs = nullptr;   // FP32 EXACT_GRID step programs, LFB_MAX_STEPS per job
-  Step* h_progs = nullptr;   // pinned staging
-  Step* d_dump_prog = nullptr;
-  // prefix cache (FP32 EXACT_GRID v5): one slot per (light, lambda) of the frame
+  // EXACT_GRID step programs, LFB_MAX_STEPS per job: StepF (LFB_FP32) or StepD (LFB_STRICT) records, buffers sized for StepD
+  char* d_progs = nullptr;
+  char* h_progs = nullptr;   // pinned staging
+  char* d_dump_prog = nullptr;
+  bool frame_strict = false;  // the current job table holds StepD programs
+  // prefix cache: one slot per (light, lambda) of the frame
   Job* d_slots = nullptr;  Job* h_slots = nullptr;
-  Step* d_slot_progs = nullptr;  Step* h_slot_progs = nullptr;
+  char* d_slot_progs = nullptr;  char* h_slot_progs = nullptr;
   int slots_cap = 0, n_slots = 0;
   float4* d_prefix = nullptr;
   size_t prefix_cap = 0;
   // prefix overlap: the forward sweeps of frame k+1 run on their own (high-priority) stream into the other of two caches while
-  // the ghost kernel of frame k still reads its own, when a host enqueues frames back to back (LFB_PREFIX_OVERLAP=0 disables)
+  // the ghost kernel of frame k still reads its own, when a host enqueues frames back to back (options.prefix_overlap)
   float4* d_prefix2 = nullptr;
   size_t prefix2_cap = 0;
-  bool prefix_overlap = true, frame_has_prefix2 = false;
+  bool frame_has_prefix2 = false;
   cudaStream_t prefix_stream = nullptr;
   cudaEvent_t ev_prefix_done[2] = {nullptr, nullptr}, ev_prefix_free[2] = {nullptr, nullptr}, ev_upload = nullptr;
   bool prefix_free_valid[2] = {false, false};
   bool upload_pending = true;  // tables / constants were (re)uploaded on `stream` since the last sweep on prefix_stream
   int prefix_flip = 0;
-  bool use_prefix = true;            // LFB_EXACT_PREFIX=0 disables
-  size_t prefix_budget = (size_t)40 << 30;  // bytes of HBM the cache may take (LFB_PREFIX_BUDGET_MB)
+  size_t prefix_budget = (size_t)40 << 30;  // bytes of HBM the cache may take (options.prefix_budget_bytes)
   bool frame_has_prefix = false;
-  // ghost families (v7): one job per (light, lambda, first reflection j) of the frame
+  // ghost families: one job per (light, lambda, first reflection j) of the frame
   Job* d_fams = nullptr;  Job* h_fams = nullptr;
-  Step* d_fam_progs = nullptr;  Step* h_fam_progs = nullptr;
+  char* d_fam_progs = nullptr;  char* h_fam_progs = nullptr;
   int fams_cap = 0, n_fams = 0;
-  bool use_family = true;            // LFB_EXACT_FAMILY=0: always one job per ghost pair (v6)
-  bool force_family = false;         // LFB_EXACT_FAMILY=1: always families; unset: by frame size (see render_grid_device)
-  bool frame_has_family = false;
+  bool frame_has_family = false, last_families = false;
   float2* d_lut = nullptr;   // reflectance tables, kLutSize entries per (lambda, surface, direction)
-  bool use_lut = true;       // LFB_EXACT_WEIGHTS=closed selects the closed-form two-pass kernel instead
-  int min_blocks = 6;        // register-allocation target of the FP32 exact kernel, CTAs/SM (LFB_EXACT_MINB=4|5|6)
-  int patch = 1;             // rays per thread in pass 1 of the FP32 exact kernel (LFB_EXACT_PATCH=1|2|4)
+  std::vector<float> poly;   // reflectance polynomials, kPolyN coefficients per (lambda, surface, direction)
+  unsigned long long* d_stats = nullptr;  // options.collect_stats: executed steps / ray pairs started / landed of the last frame
   // owned buffers of the host-memory API
   unsigned long long* d_accum = nullptr;
   size_t accum_cap = 0;
@@ -258,8 +258,9 @@ int grow(T** p, size_t* cap, size_t need) {
   return LFB_OK;
 }
 
-FrameGeom make_geom(const lfb_engine* e, const lfb_params& P) {
+FrameGeom make_geom(const lfb_engine* e, const lfb_params& P, unsigned* tile_bits) {
   FrameGeom g;
+  memset(&g, 0, sizeof(g));
   g.W = P.width; g.H = P.height; g.N = P.grid_n; g.splat = P.splat;
   g.tiles_x = (P.grid_n + 15) / 16;
   g.tiles_per_job = g.tiles_x * g.tiles_x;
@@ -267,20 +268,25 @@ FrameGeom make_geom(const lfb_engine* e, const lfb_params& P) {
   g.fp_scale = ldexp(1.0, P.fixed_point_bits > 0 ? P.fixed_point_bits : 40);
   g.P = (float)e->lens.entrance_half_height; g.h_stop = (float)e->lens.stop_half_height;
   g.cell = 2.f * g.P / (float)P.grid_n;
+  g.P_d = e->lens.entrance_half_height; g.cell_d = 2.0 * g.P_d / (double)P.grid_n;
   g.mask_su = 0.5f * (float)e->tex_w / g.h_stop; g.mask_ou = 0.5f * (float)e->tex_w;
   g.mask_sv = -0.5f * (float)e->tex_h / g.h_stop; g.mask_ov = 0.5f * (float)e->tex_h;
-  g.lut = (e->use_lut && P.mode == LFB_MODE_EXACT_GRID && P.precision == LFB_FP32) ? e->d_lut : nullptr;
+  g.lut = e->d_lut;
   g.prefix = nullptr;  // set by render_grid_device when the frame's jobs were built against the prefix cache
   g.half_rays = P.grid_n * ((P.grid_n + 1) / 2);
   g.n_surf = e->lens.n_surfaces;
   g.bbox = e->track_bbox ? e->d_bbox : nullptr;
-  g.patch = e->patch; g.pad = e->min_blocks;
+  g.tile_bits = tile_bits;
+  g.tiles_w = tiles_across(P.width);
+  g.stats = e->opt.collect_stats ? e->d_stats : nullptr;
   return g;
 }
 
+bool is_exact_fast(const lfb_params& P) { return P.mode == LFB_MODE_EXACT_GRID && (P.precision == LFB_FP32 || P.precision == LFB_STRICT); }
+
 // Polarisation-averaged reflectance of one interface as a function of s2 = sin^2(theta0): bare Fresnel, or the exact
 // single-layer (Airy) film of index max(sqrt(n0 n2), 1.38) and quarter-wave thickness at lambda0.  Host-side, double:
-// it fills the tables the FP32 kernel interpolates; it is evaluated per table node, never per ray.
+// it feeds the polynomial fits and the tables of the throughput kernels; it is evaluated per node, never per ray.
 double interface_reflectance(double n0, double n2, double s2, double lambda0, double lambda) {
   if (n0 == n2) return 0.0;
   const double cos0 = sqrt(1.0 - s2);
@@ -308,74 +314,120 @@ double interface_reflectance(double n0, double n2, double s2, double lambda0, do
   return 0.5 * (Rs + Rp);
 }
 
-// Tables for every (wavelength, surface, direction): index (lam * n_surfaces + k) * 2 + (backward ? 1 : 0).
-void build_reflectance_tables(const lfb_lens& L, std::vector<float2>& out) {
-  out.assign((size_t)L.n_lambda * L.n_surfaces * 2 * kLutSize, make_float2(0.f, 0.f));
+// R of interface (lam, k, dir) over v = the cosine of the ray's angle in the RARER medium (c0 when entering the denser
+// medium, c2 otherwise): R is analytic in v on [0, 1] -- R -> 1 linearly as v -> 0, at grazing incidence or at the critical
+// angle -- whereas in sin^2(theta0) it has a square-root singularity at the critical angle.
+struct Interface {
+  double n0, n2, lambda0, lambda;
+  double R(double v) const {
+    const double s2 = n0 <= n2 ? 1.0 - v * v : (1.0 - v * v) * (n2 / n0) * (n2 / n0);
+    return interface_reflectance(n0, n2, s2 < 0 ? 0 : s2, lambda0, lambda);
+  }
+};
+Interface interface_of(const lfb_lens& L, int lam, int k, int dir) {
+  const double na = k == 0 ? 1.0 : (double)L.ior[lam][k - 1], nb = (double)L.ior[lam][k];
+  return {dir ? nb : na, dir ? na : nb, (double)L.coating_lambda0_nm[k], (double)L.lambda_nm[lam]};
+}
+
+// Tables and polynomials for every (wavelength, surface, direction): index (lam * n_surfaces + k) * 2 + (backward ? 1 : 0).
+//   lut   kLutSize linear-interpolation intervals on v in [0, 1]: (R_i, R_{i+1} - R_i)
+//   poly  degree kPolyN-1 interpolant of R at the Chebyshev nodes of v in [kPolyV0, 1], as monomial coefficients in
+//         x = (1 - v) / (1 - kPolyV0) in [0, 1], lowest order first (|error| ~ 3e-8 for the air / glass interfaces)
+void build_reflectance_tables(const lfb_lens& L, std::vector<float2>& lut, std::vector<float>& poly) {
+  const size_t n_if = (size_t)L.n_lambda * L.n_surfaces * 2;
+  lut.assign(n_if * kLutSize, make_float2(0.f, 0.f));
+  poly.assign(n_if * kPolyN, 0.f);
+  const double kPi = 3.14159265358979323846;
   for (int lam = 0; lam < L.n_lambda; lam++)
     for (int k = 0; k < L.n_surfaces; k++)
       for (int dir = 0; dir < 2; dir++) {
-        const double na = k == 0 ? 1.0 : (double)L.ior[lam][k - 1], nb = (double)L.ior[lam][k];
-        const double n0 = dir ? nb : na, n2 = dir ? na : nb;
-        float2* T = &out[((size_t)(lam * L.n_surfaces + k) * 2 + dir) * kLutSize];
-        // table variable v = cosine of the ray's angle in the RARER medium (c0 when entering the denser medium, c2
-        // otherwise): R is analytic in v on [0, 1] -- R -> 1 linearly as v -> 0, at grazing incidence or at the critical
-        // angle -- whereas in sin^2(theta0) it has a square-root singularity at the critical angle
-        auto R_of = [&](double v) {
-          const double s2 = n0 <= n2 ? 1.0 - v * v : (1.0 - v * v) * (n2 / n0) * (n2 / n0);
-          return interface_reflectance(n0, n2, s2 < 0 ? 0 : s2, L.coating_lambda0_nm[k], L.lambda_nm[lam]);
-        };
-        double prev = R_of(0.0);
+        const Interface I = interface_of(L, lam, k, dir);
+        const size_t idx = (size_t)(lam * L.n_surfaces + k) * 2 + dir;
+        float2* T = &lut[idx * kLutSize];
+        double prev = I.R(0.0);
         for (int i = 0; i < kLutSize; i++) {
-          const double next = R_of((double)(i + 1) / kLutSize);
+          const double next = I.R((double)(i + 1) / kLutSize);
           T[i] = make_float2((float)prev, (float)(next - prev));
           prev = next;
         }
+        // Chebyshev interpolation on t in [-1, 1], x = (t + 1) / 2, v = 1 - x (1 - v0)
+        double f[kPolyN], cheb[kPolyN];
+        for (int m = 0; m < kPolyN; m++) {
+          const double t = cos(kPi * (m + 0.5) / kPolyN);
+          f[m] = I.R(1.0 - 0.5 * (t + 1.0) * (1.0 - (double)kPolyV0));
+        }
+        for (int q = 0; q < kPolyN; q++) {
+          double sum = 0;
+          for (int m = 0; m < kPolyN; m++) sum += f[m] * cos(kPi * q * (m + 0.5) / kPolyN);
+          cheb[q] = sum * (q == 0 ? 1.0 : 2.0) / kPolyN;
+        }
+        // sum_q cheb[q] T_q(2x - 1) as monomials in x: T_0 = 1, T_1 = 2x - 1, T_{q+1} = 2 (2x - 1) T_q - T_{q-1}
+        double mono[kPolyN] = {0}, t0[kPolyN] = {1.0}, t1[kPolyN] = {-1.0, 2.0}, t2[kPolyN];
+        for (int q = 0; q < kPolyN; q++) {
+          const double* tq = q == 0 ? t0 : t1;
+          for (int d = 0; d < kPolyN; d++) mono[d] += cheb[q] * tq[d];
+          if (q >= 1) {
+            for (int d = 0; d < kPolyN; d++) t2[d] = 2.0 * ((d > 0 ? 2.0 * t1[d - 1] : 0.0) - t1[d]) - t0[d];
+            memcpy(t0, t1, sizeof(t0));
+            memcpy(t1, t2, sizeof(t1));
+          }
+        }
+        for (int d = 0; d < kPolyN; d++) poly[idx * kPolyN + d] = (float)mono[d];
       }
 }
 
-// Flatten ghost (i, j) at wavelength lam into the FP32 step program (exact_f32.cuh): the surface sequence
-// forward 0..j-1, reflect at j, backward j-1..i+1, reflect at i, forward i+1..n-1, sensor plane (i < 0: the
-// direct path), with every ray-independent quantity of each step computed here, once.
-// from_reflection: the program starts ON surface j with the first reflection (the forward sweep 0 .. j-1 comes from the
-// prefix cache).  prefix_only: just the forward sweep 0 .. n-1 (no reflections, no sensor) -- what prefix_kernel traces.
 // One step of a program: the ray arrives on surface k coming from surface prev_k (k = n_surfaces: the sensor plane).
-Step make_step(const lfb_lens& L, const DevLens& D, int lam, int k, int op, bool forward, int prev_k) {
+// Everything ray-independent is computed here, once, in double; put_step narrows it to the kernel's geometry type.
+StepD make_step(const lfb_engine* e, int lam, int k, int op, bool forward, int prev_k) {
+  const lfb_lens& L = e->lens;
+  const DevLens& D = e->dev_lens;
   const int n = L.n_surfaces, stop = L.stop_index;
-  Step S;
+  StepD S;
   memset(&S, 0, sizeof(S));
   S.lut = (lam * L.n_surfaces + (k < n ? k : 0)) * 2 + (forward ? 0 : 1);
-  S.dz = (float)(D.zv_d[prev_k] - D.zv_d[k]);
-  S.eta = S.eta2 = 1.f;
+  S.dz = D.zv_d[prev_k] - D.zv_d[k];
+  S.eta = S.eta2 = 1.0;
   S.semi2 = INFINITY;  // the stop and the sensor are unbounded planes (the mask bounds the stop)
   if (k == n) { S.op = STEP_SENSOR; return S; }
   if (k == stop && op != STEP_REFLECT) { S.op = STEP_STOP; return S; }
-  S.c = L.curvature[k];
+  S.c = (double)L.curvature[k];
   S.semi2 = L.semi_aperture[k] * L.semi_aperture[k];
   const float na = k == 0 ? 1.f : L.ior[lam][k - 1], nb = L.ior[lam][k];
   const float n0 = forward ? na : nb, n2 = forward ? nb : na;
-  S.n0 = n0; S.n2 = n2;
-  S.eta = n0 / n2; S.eta2 = S.eta * S.eta;
+  S.eta = (double)n0 / (double)n2;
   S.op = (op == STEP_REFRACT && n0 == n2) ? STEP_PASS : op;
-  const double lam0 = L.coating_lambda0_nm[k];
-  if (lam0 > 0 && n0 != n2) {
-    double n1 = sqrt((double)n0 * (double)n2);
-    if (n1 < 1.38) n1 = 1.38;  // MgF2 floor
-    S.n1 = (float)n1;
-    S.e1sq = (float)(((double)n0 / n1) * ((double)n0 / n1));
-    S.phase = (float)(3.14159265358979323846 * lam0 / (double)L.lambda_nm[lam]);  // 4 pi n1 d1 / lambda, d1 = lambda0 / (4 n1)
-  }
+  // the weight factor: R at a reflection, 1 - R at a refraction
+  const float* R = &e->poly[(size_t)S.lut * kPolyN];
+  for (int d = 0; d < kPolyN; d++) S.p[d] = op == STEP_REFLECT ? R[d] : (d == 0 ? 1.f - R[d] : -R[d]);
   return S;
 }
 
+template <typename T>
+void put_step(char* base, size_t index, const StepD& S) {
+  StepT<T> o;
+  memset(&o, 0, sizeof(o));
+  o.c = (T)S.c; o.dz = (T)S.dz; o.eta = (T)S.eta; o.eta2 = o.eta * o.eta;
+  o.semi2 = S.semi2; o.op = S.op; o.lut = S.lut;
+  memcpy(o.p, S.p, sizeof(o.p));
+  memcpy(base + index * sizeof(StepT<T>), &o, sizeof(o));
+}
+void put_steps(bool strict, char* base, size_t first, const StepD* steps, int n) {
+  for (int s = 0; s < n; s++) {
+    if (strict) put_step<double>(base, first + (size_t)s, steps[s]);
+    else put_step<float>(base, first + (size_t)s, steps[s]);
+  }
+}
+
+// Flatten ghost (i, j) at wavelength lam into a step program (exact_trace.cuh): the surface sequence forward 0..j-1,
+// reflect at j, backward j-1..i+1, reflect at i, forward i+1..n-1, sensor plane (i < 0: the direct path).
 // from_reflection: the program starts ON surface j with the first reflection (the forward sweep 0 .. j-1 comes from the
 // prefix cache).  prefix_only: the forward sweep 0 .. n-1 followed by the sensor step (prefix_kernel traces the first n
 // steps; the sensor step serves the direct path and the forks of the family kernel); returns n.
-int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, Step* out, bool from_reflection = false,
-                  bool prefix_only = false) {
-  const int n = L.n_surfaces;
+int build_program(const lfb_engine* e, int lam, int i, int j, StepD* out, bool from_reflection = false, bool prefix_only = false) {
+  const int n = e->lens.n_surfaces;
   int ns = 0, prev = from_reflection ? j : 0;
   auto push = [&](int k, int op, bool forward) {
-    out[ns++] = make_step(L, D, lam, k, op, forward, prev);
+    out[ns++] = make_step(e, lam, k, op, forward, prev);
     prev = k;
   };
   if (prefix_only) {
@@ -397,17 +449,17 @@ int build_program(const lfb_lens& L, const DevLens& D, int lam, int i, int j, St
   return ns;
 }
 
-// The program of a ghost family (exact_f32.cuh, v7): first reflection at j, then for k = j-1 .. 0 the backward step at k
-// followed by the fork step (reflection at k seen from behind; op = -1 when ghost (k, j) is not in `mask`).
-int build_family_program(const lfb_lens& L, const DevLens& D, int lam, int j, unsigned mask, Step* out) {
+// The program of a ghost family: first reflection at j, then for k = j-1 .. 0 the backward step at k followed by the
+// fork step (reflection at k seen from behind; op = -1 when ghost (k, j) is not in `mask`).
+int build_family_program(const lfb_engine* e, int lam, int j, unsigned mask, StepD* out) {
   int ns = 0, prev = j, kmin = 0;
   while (kmin < j && !((mask >> kmin) & 1u)) kmin++;  // the backward sweep ends at the lowest wanted second reflection
-  out[ns++] = make_step(L, D, lam, j, STEP_REFLECT, true, j);
+  out[ns++] = make_step(e, lam, j, STEP_REFLECT, true, j);
   for (int k = j - 1; k >= kmin; k--) {
-    out[ns++] = make_step(L, D, lam, k, STEP_REFRACT, false, prev);
+    out[ns++] = make_step(e, lam, k, STEP_REFRACT, false, prev);
     prev = k;
-    Step fork = make_step(L, D, lam, k, STEP_REFLECT, false, k);
-    if (!((mask >> k) & 1u) || k == L.stop_index) fork.op = -1;
+    StepD fork = make_step(e, lam, k, STEP_REFLECT, false, k);
+    if (!((mask >> k) & 1u) || k == e->lens.stop_index) fork.op = -1;
     out[ns++] = fork;
   }
   return ns;
@@ -420,10 +472,20 @@ void fill_job(const lfb_engine* e, const lfb_params& P, const lfb_light& lt, con
   J->light = id.light; J->i = id.i; J->j = id.j; J->lambda = id.lambda;
   J->theta = lt.theta;
   const double dx = lt.ns_x - 0.5, dy = lt.ns_y - 0.5;
-  const float ang = (dx == 0 && dy == 0) ? 0.f : (float)atan(dy / dx);
-  J->cs = cosf(ang); J->sn = sinf(ang);
-  J->sx = ceil(lt.ns_x * (double)P.width);   // draw_ghost, pathtracer.cpp:462-463
-  J->sy = ceil(lt.ns_y * (double)P.height);
+  if (P.physical_mapping) {
+    // the flare axis runs from the image centre through the light: the rotation is the light's azimuth (atan2, not the
+    // reference's atan, which folds left-of-centre suns onto the right) and the origin is the image centre, so that a ray
+    // landing at local (xs, ys) is drawn at centre + ppu * R(phi) (xs, ys).  See lfb_params.physical_mapping.
+    const double phi = (dx == 0 && dy == 0) ? 0.0 : atan2(dy * (double)P.height, dx * (double)P.width);
+    J->cs = -cos(phi); J->sn = -sin(phi);  // to_pixel maps X = -ppu xs: fold the sign into the rotation
+    J->sx = 0.5 * (double)P.width;
+    J->sy = 0.5 * (double)P.height;
+  } else {
+    const float ang = (dx == 0 && dy == 0) ? 0.f : (float)atan(dy / dx);
+    J->cs = cosf(ang); J->sn = sinf(ang);
+    J->sx = ceil(lt.ns_x * (double)P.width);   // draw_ghost, pathtracer.cpp:462-463
+    J->sy = ceil(lt.ns_y * (double)P.height);
+  }
   J->ppu = P.px_per_unit > 0 ? P.px_per_unit : 0.4f;
   J->sin_t = sin((double)lt.theta); J->cos_t = cos((double)lt.theta);
   J->inv_dist = (lt.distance > 0 && std::isfinite(lt.distance)) ? 1.0 / lt.distance : 0.0;  // 0: directional
@@ -434,6 +496,16 @@ void fill_job(const lfb_engine* e, const lfb_params& P, const lfb_light& lt, con
   J->f_sin_t = (float)J->sin_t; J->f_cos_t = (float)J->cos_t; J->f_inv_dist = (float)J->inv_dist;
   J->f_sx = (float)J->sx; J->f_sy = (float)J->sy; J->f_cs = (float)J->cs; J->f_sn = (float)J->sn; J->f_ppu = (float)J->ppu;
   for (int c = 0; c < 3; c++) J->f_chan[c] = (float)J->chan[c] * (float)scale;
+}
+
+template <typename T>
+int regrow_pair(T** dev, T** host, size_t bytes) {
+  if (*dev) CU(cudaFree(*dev));
+  if (*host) CU(cudaFreeHost(*host));
+  *dev = nullptr; *host = nullptr;
+  CU(cudaMalloc((void**)dev, bytes));
+  CU(cudaHostAlloc((void**)host, bytes, cudaHostAllocDefault));
+  return LFB_OK;
 }
 
 // Build + upload this shard's jobs unless the frame description is unchanged.
@@ -447,41 +519,49 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
   // launch order = list order.  (Measured on cfg2: sorting the ghosts longest-first, or interleaving long and short
   // ones, is 20 % SLOWER than the reference order; the sensor sums are integers, so the order never changes the result.)
   const int n = (int)ids.size();
+  const size_t prog_bytes = sizeof(StepD) * LFB_MAX_STEPS;  // per job, sized for the larger record
+  int rc;
   if (n > e->jobs_cap) {
-    if (e->d_jobs) CU(cudaFree(e->d_jobs));
-    if (e->h_jobs) CU(cudaFreeHost(e->h_jobs));
-    if (e->d_progs) CU(cudaFree(e->d_progs));
-    if (e->h_progs) CU(cudaFreeHost(e->h_progs));
-    e->d_jobs = nullptr; e->h_jobs = nullptr; e->d_progs = nullptr; e->h_progs = nullptr; e->jobs_cap = 0;
-    CU(cudaMalloc((void**)&e->d_jobs, sizeof(Job) * (size_t)n));
-    CU(cudaHostAlloc((void**)&e->h_jobs, sizeof(Job) * (size_t)n, cudaHostAllocDefault));
-    CU(cudaMalloc((void**)&e->d_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)n));
-    CU(cudaHostAlloc((void**)&e->h_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)n, cudaHostAllocDefault));
+    e->jobs_cap = 0;
+    if ((rc = regrow_pair(&e->d_jobs, &e->h_jobs, sizeof(Job) * (size_t)n))) return rc;
+    if ((rc = regrow_pair(&e->d_progs, &e->h_progs, prog_bytes * (size_t)n))) return rc;
     e->jobs_cap = n;
   }
-  // the previous frame's upload may still be reading h_jobs
+  // the previous frame's upload may still be reading the pinned staging buffers
   CU(cudaStreamSynchronize(e->stream));
-  const bool want_progs = P.mode == LFB_MODE_EXACT_GRID && P.precision == LFB_FP32;
+  const bool want_progs = is_exact_fast(P);
+  const bool strict = P.precision == LFB_STRICT;
+  e->frame_strict = strict;
+  const size_t step_bytes = strict ? sizeof(StepD) : sizeof(StepF);
+  const int parts = strict ? exact_prefix_parts<double>() : exact_prefix_parts<float>();
+  const bool want_family = e->opt.kernel_select != 1;
+  StepD prog[LFB_MAX_STEPS];
   // prefix cache: one slot per (light, lambda) that has ghost jobs in this shard
   std::vector<int> slot_of;   // [light * n_lambda + lambda] -> slot or -1
   std::vector<JobId> slot_ids;
   e->frame_has_prefix = false;
+  e->frame_has_prefix2 = false;
   e->frame_has_family = false;
-  if (want_progs && e->use_lut && e->use_prefix) {
+  e->n_fams = 0; e->n_slots = 0;
+  if (want_progs && e->opt.prefix_budget_bytes >= 0) {
     slot_of.assign((size_t)std::max(n_lights, 1) * e->lens.n_lambda, -1);
     for (int q = 0; q < n; q++)
-      if (ids[q].i >= 0 || e->use_family) {  // with families the direct path is splatted by the prefix kernel itself
+      if (ids[q].i >= 0 || want_family) {  // with families the direct path is splatted by the prefix kernel itself
         int& sl = slot_of[(size_t)ids[q].light * e->lens.n_lambda + ids[q].lambda];
         if (sl < 0) { sl = (int)slot_ids.size(); slot_ids.push_back({ids[q].light, -1, -1, ids[q].lambda}); }
       }
+    // The decision must not depend on the shard (a sharded frame and the whole frame pick the same kernels): it is made on
+    // the cache the UNSHARDED frame would need.  (The frames have the same bits either way -- a job without a cached sweep
+    // re-traces it with the same arithmetic -- this keeps the performance model simple.)
     const size_t half_rays = (size_t)P.grid_n * ((P.grid_n + 1) / 2);
-    const size_t need = slot_ids.size() * (size_t)e->lens.n_surfaces * 2 * half_rays * sizeof(float4);
-    if (!slot_ids.empty() && need <= e->prefix_budget) {
-      int rc = grow(&e->d_prefix, &e->prefix_cap, need);
+    const size_t per_slot = (size_t)e->lens.n_surfaces * parts * half_rays * sizeof(float4);
+    const size_t need_whole = (size_t)std::max(n_lights, 1) * e->lens.n_lambda * per_slot;
+    const size_t need = slot_ids.size() * per_slot;
+    if (!slot_ids.empty() && need_whole <= e->prefix_budget) {
+      rc = grow(&e->d_prefix, &e->prefix_cap, need);
       if (rc == LFB_OK) e->frame_has_prefix = true;
       else if (rc != LFB_ERR_NOMEM) return rc;
-      e->frame_has_prefix2 = false;
-      if (e->frame_has_prefix && e->prefix_overlap && e->prefix_stream && 2 * need <= e->prefix_budget) {
+      if (e->frame_has_prefix && e->opt.prefix_overlap >= 0 && e->prefix_stream && 2 * need_whole <= e->prefix_budget) {
         rc = grow(&e->d_prefix2, &e->prefix2_cap, need);
         if (rc == LFB_OK) e->frame_has_prefix2 = true;
         else if (rc != LFB_ERR_NOMEM) return rc;
@@ -491,25 +571,19 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
   if (e->frame_has_prefix) {
     const int ns = (int)slot_ids.size();
     if (ns > e->slots_cap) {
-      if (e->d_slots) CU(cudaFree(e->d_slots));
-      if (e->h_slots) CU(cudaFreeHost(e->h_slots));
-      if (e->d_slot_progs) CU(cudaFree(e->d_slot_progs));
-      if (e->h_slot_progs) CU(cudaFreeHost(e->h_slot_progs));
-      e->d_slots = nullptr; e->h_slots = nullptr; e->d_slot_progs = nullptr; e->h_slot_progs = nullptr; e->slots_cap = 0;
-      CU(cudaMalloc((void**)&e->d_slots, sizeof(Job) * (size_t)ns));
-      CU(cudaHostAlloc((void**)&e->h_slots, sizeof(Job) * (size_t)ns, cudaHostAllocDefault));
-      CU(cudaMalloc((void**)&e->d_slot_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)ns));
-      CU(cudaHostAlloc((void**)&e->h_slot_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)ns, cudaHostAllocDefault));
+      e->slots_cap = 0;
+      if ((rc = regrow_pair(&e->d_slots, &e->h_slots, sizeof(Job) * (size_t)ns))) return rc;
+      if ((rc = regrow_pair(&e->d_slot_progs, &e->h_slot_progs, prog_bytes * (size_t)ns))) return rc;
       e->slots_cap = ns;
     }
     for (int sl = 0; sl < ns; sl++) {
       fill_job(e, P, lights[slot_ids[sl].light], slot_ids[sl], &e->h_slots[sl]);
-      e->h_slots[sl].n_steps = build_program(e->lens, e->dev_lens, slot_ids[sl].lambda, -1, -1, e->h_slot_progs + (size_t)sl * LFB_MAX_STEPS, false, true);
+      e->h_slots[sl].n_steps = build_program(e, slot_ids[sl].lambda, -1, -1, prog, false, true);
+      put_steps(strict, e->h_slot_progs, (size_t)sl * LFB_MAX_STEPS, prog, e->h_slots[sl].n_steps + 1);
       e->h_slots[sl].i = 0;  // set to 1 below when this shard owns the slot's direct path
     }
     // ghost families: the pairs (i, j) of a slot grouped by their first reflection j
-    e->frame_has_family = false;
-    if (e->use_family) {
+    if (want_family) {
       struct Fam { int slot, j; unsigned mask; };
       std::vector<Fam> fams;
       std::vector<int> fam_of((size_t)ns * LFB_MAX_SURFACES, -1);
@@ -520,36 +594,28 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
         if (f < 0) { f = (int)fams.size(); fams.push_back({sl, ids[q].j, 0u}); }
         fams[f].mask |= 1u << ids[q].i;
       }
-      // LFB_FAMILY_SPLIT = m: at most m forks per family job (more, shorter CTAs for small frames; the part of the backward
-      // sweep above a chunk's forks is then repeated per chunk)
-      if (const char* env = getenv("LFB_FAMILY_SPLIT")) {
-        const int m = atoi(env);
-        if (m > 0) {
-          std::vector<Fam> split;
-          for (const Fam& f : fams) {
-            unsigned cur = 0;
-            int cnt = 0;
-            for (int k = f.j - 1; k >= 0; k--) {
-              if (!((f.mask >> k) & 1u)) continue;
-              cur |= 1u << k;
-              if (++cnt == m) { split.push_back({f.slot, f.j, cur}); cur = 0; cnt = 0; }
-            }
-            if (cnt) split.push_back({f.slot, f.j, cur});
+      // options.family_split = m: at most m forks per family job (more, shorter CTAs for small frames; the part of the
+      // backward sweep above a chunk's forks is then repeated per chunk)
+      if (e->opt.family_split > 0) {
+        const int m = e->opt.family_split;
+        std::vector<Fam> split;
+        for (const Fam& f : fams) {
+          unsigned cur = 0;
+          int cnt = 0;
+          for (int k = f.j - 1; k >= 0; k--) {
+            if (!((f.mask >> k) & 1u)) continue;
+            cur |= 1u << k;
+            if (++cnt == m) { split.push_back({f.slot, f.j, cur}); cur = 0; cnt = 0; }
           }
-          fams.swap(split);
+          if (cnt) split.push_back({f.slot, f.j, cur});
         }
+        fams.swap(split);
       }
       const int nf = (int)fams.size();
       if (nf > e->fams_cap) {
-        if (e->d_fams) CU(cudaFree(e->d_fams));
-        if (e->h_fams) CU(cudaFreeHost(e->h_fams));
-        if (e->d_fam_progs) CU(cudaFree(e->d_fam_progs));
-        if (e->h_fam_progs) CU(cudaFreeHost(e->h_fam_progs));
-        e->d_fams = nullptr; e->h_fams = nullptr; e->d_fam_progs = nullptr; e->h_fam_progs = nullptr; e->fams_cap = 0;
-        CU(cudaMalloc((void**)&e->d_fams, sizeof(Job) * (size_t)nf));
-        CU(cudaHostAlloc((void**)&e->h_fams, sizeof(Job) * (size_t)nf, cudaHostAllocDefault));
-        CU(cudaMalloc((void**)&e->d_fam_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)nf));
-        CU(cudaHostAlloc((void**)&e->h_fam_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)nf, cudaHostAllocDefault));
+        e->fams_cap = 0;
+        if ((rc = regrow_pair(&e->d_fams, &e->h_fams, sizeof(Job) * (size_t)nf))) return rc;
+        if ((rc = regrow_pair(&e->d_fam_progs, &e->h_fam_progs, prog_bytes * (size_t)nf))) return rc;
         e->fams_cap = nf;
       }
       for (int f = 0; f < nf; f++) {
@@ -560,36 +626,36 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
         FJ->j_first = fams[f].j;
         FJ->i = (int)fams[f].mask;
         FJ->j = fams[f].j;
-        FJ->n_steps = build_family_program(e->lens, e->dev_lens, sid.lambda, fams[f].j, fams[f].mask, e->h_fam_progs + (size_t)f * LFB_MAX_STEPS);
+        FJ->n_steps = build_family_program(e, sid.lambda, fams[f].j, fams[f].mask, prog);
+        put_steps(strict, e->h_fam_progs, (size_t)f * LFB_MAX_STEPS, prog, FJ->n_steps);
       }
       e->n_fams = nf;
       if (nf > 0) {
         CU(cudaMemcpyAsync(e->d_fams, e->h_fams, sizeof(Job) * (size_t)nf, cudaMemcpyHostToDevice, e->stream));
-        CU(cudaMemcpyAsync(e->d_fam_progs, e->h_fam_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)nf, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->d_fam_progs, e->h_fam_progs, step_bytes * LFB_MAX_STEPS * (size_t)nf, cudaMemcpyHostToDevice, e->stream));
       }
       e->frame_has_family = true;
     }
     e->n_slots = ns;
     CU(cudaMemcpyAsync(e->d_slots, e->h_slots, sizeof(Job) * (size_t)ns, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(e->d_slot_progs, e->h_slot_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)ns, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->d_slot_progs, e->h_slot_progs, step_bytes * LFB_MAX_STEPS * (size_t)ns, cudaMemcpyHostToDevice, e->stream));
   }
   for (int q = 0; q < n; q++) {
     fill_job(e, P, lights[ids[q].light], ids[q], &e->h_jobs[q]);
     e->h_jobs[q].slot = -1;
+    e->h_jobs[q].j_first = ids[q].j;  // jobs without a cached sweep re-trace it and canonicalise the state there
     if (want_progs) {
       const bool cached = e->frame_has_prefix && ids[q].i >= 0;
-      if (cached) {
-        e->h_jobs[q].slot = slot_of[(size_t)ids[q].light * e->lens.n_lambda + ids[q].lambda];
-        e->h_jobs[q].j_first = ids[q].j;
-      }
-      e->h_jobs[q].n_steps = build_program(e->lens, e->dev_lens, ids[q].lambda, ids[q].i, ids[q].j, e->h_progs + (size_t)q * LFB_MAX_STEPS, cached);
+      if (cached) e->h_jobs[q].slot = slot_of[(size_t)ids[q].light * e->lens.n_lambda + ids[q].lambda];
+      e->h_jobs[q].n_steps = build_program(e, ids[q].lambda, ids[q].i, ids[q].j, prog, cached);
+      put_steps(strict, e->h_progs, (size_t)q * LFB_MAX_STEPS, prog, e->h_jobs[q].n_steps);
     }
   }
   e->n_jobs = n;
   if (n > 0) {
     CU(cudaMemcpyAsync(e->d_jobs, e->h_jobs, sizeof(Job) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
     if (want_progs)
-      CU(cudaMemcpyAsync(e->d_progs, e->h_progs, sizeof(Step) * LFB_MAX_STEPS * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+      CU(cudaMemcpyAsync(e->d_progs, e->h_progs, step_bytes * LFB_MAX_STEPS * (size_t)n, cudaMemcpyHostToDevice, e->stream));
     if (P.mode == LFB_MODE_PARAXIAL_GRID) {
       CU(launch_paraxial_setup(e->d_jobs, n, P.physical_backward, e->stream));
       e->launches++;
@@ -600,27 +666,19 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
   return LFB_OK;
 }
 
-int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params& P,
-                       unsigned long long* accum, int clear_first) {
-  int rc = upload_constants(e);
-  if (rc) return rc;
-  rc = prepare_jobs(e, lights, n_lights, P);
-  if (rc) return rc;
-  FrameGeom g = make_geom(e, P);
-  // inside a CUDA-graph capture (a host may capture whole frames and replay them) the timing events are not recorded:
-  // they could not be read back anyway
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  CU(cudaStreamIsCapturing(e->stream, &cap));
-  const bool capturing = cap != cudaStreamCaptureStatusNone;
-  if (clear_first) CU(cudaMemsetAsync(accum, 0, lfb_accum_bytes(P.width, P.height), e->stream));
-  if (!capturing) CU(cudaEventRecord(e->ev_trace0, e->stream));
+// The EXACT_GRID throughput kernels of one frame, for geometry type T.
+template <typename T>
+int launch_exact_frame(lfb_engine* e, const lfb_params& P, FrameGeom& g, unsigned long long* accum, bool capturing) {
+  typedef StepT<T> S;
+  const bool stats = e->opt.collect_stats != 0;
   // Families do ~25 % less work but in 4x fewer, longer-lived CTAs: they win once the grid is many waves deep (cfg3 / cfg4:
   // x1.3), and lose ~8 % on a frame as small as cfg2 (5 376 CTAs = 3.6 waves), where the per-pair kernel keeps the SMs fuller.
   const long long fam_ctas = (long long)e->n_fams * ((P.grid_n + 15) / 16) * (((P.grid_n + 1) / 2 + 7) / 8);
-  const bool families = e->frame_has_prefix && e->frame_has_family && g.lut && (e->force_family || fam_ctas >= 16384);
+  const bool families = e->frame_has_prefix && e->frame_has_family && (e->opt.kernel_select == 2 || fam_ctas >= 16384);
+  e->last_families = families;
   int overlap_buf = -1;
-  if (e->n_jobs > 0 && e->frame_has_prefix && g.lut) {
-    if (!families && !capturing && e->frame_has_prefix2) {
+  if (e->n_slots > 0 && e->frame_has_prefix) {
+    if (!families && !capturing && !stats && e->frame_has_prefix2) {
       // forward sweeps on their own stream, alternating caches: they do not touch the sensor, so the sweeps of this frame may
       // run while the previous frame's ghost kernel (reading the other cache) is still draining
       const int b = e->prefix_flip;
@@ -632,30 +690,59 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
         e->upload_pending = false;
       }
       if (e->prefix_free_valid[b]) CU(cudaStreamWaitEvent(e->prefix_stream, e->ev_prefix_free[b], 0));
-      CU(launch_prefix_f32(e->d_slots, e->d_slot_progs, e->n_slots, g, e->d_tex, cache, nullptr, e->prefix_stream));
+      CU(launch_exact_prefix<T>(e->d_slots, (const S*)e->d_slot_progs, e->n_slots, g, e->d_tex, cache, nullptr, stats, e->prefix_stream));
       CU(cudaEventRecord(e->ev_prefix_done[b], e->prefix_stream));
       CU(cudaStreamWaitEvent(e->stream, e->ev_prefix_done[b], 0));
       g.prefix = cache;
       overlap_buf = b;
     } else {
-      CU(launch_prefix_f32(e->d_slots, e->d_slot_progs, e->n_slots, g, e->d_tex, e->d_prefix, families ? accum : nullptr, e->stream));
+      // cache 0 on the engine stream; a sweep still running on prefix_stream from an earlier (overlapped) frame writes its own
+      // cache and was already joined by that frame's ghost kernel, which precedes this launch in stream order
+      CU(launch_exact_prefix<T>(e->d_slots, (const S*)e->d_slot_progs, e->n_slots, g, e->d_tex, e->d_prefix, families ? accum : nullptr, stats, e->stream));
       g.prefix = e->d_prefix;
+      overlap_buf = 0;
     }
     e->launches++;
   }
-  if (families) {  // v7: one job per (light, lambda, first reflection); the direct path was splatted by the prefix kernel
+  if (families) {  // one job per (light, lambda, first reflection); the direct path was splatted by the prefix kernel
     if (e->n_fams > 0) {
-      CU(launch_family_f32(e->d_fams, e->d_fam_progs, e->n_fams, e->d_slots, e->d_slot_progs, g, e->d_tex, accum, e->stream));
+      CU(launch_exact_families<T>(e->d_fams, (const S*)e->d_fam_progs, e->n_fams, e->d_slots, (const S*)e->d_slot_progs, g, e->d_tex, accum, stats, e->stream));
       e->launches++;
     }
   } else if (e->n_jobs > 0) {
-    if (P.precision == LFB_FP64) CU(launch_trace_splat_f64(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
-    else CU(launch_trace_splat_f32(e->d_jobs, e->d_progs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
+    CU(launch_exact_ghosts<T>(e->d_jobs, (const S*)e->d_progs, e->n_jobs, g, e->d_tex, accum, e->opt.ctas_per_sm, stats, e->stream));
     e->launches++;
   }
-  if (overlap_buf >= 0) {  // the cache may be rewritten once this frame's ghost kernel is done with it
+  if (overlap_buf >= 0) {  // the cache may be rewritten once this frame's kernels are done with it
     CU(cudaEventRecord(e->ev_prefix_free[overlap_buf], e->stream));
     e->prefix_free_valid[overlap_buf] = true;
+  }
+  return LFB_OK;
+}
+
+int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params& P,
+                       unsigned long long* accum, int clear_first) {
+  int rc = upload_constants(e);
+  if (rc) return rc;
+  rc = prepare_jobs(e, lights, n_lights, P);
+  if (rc) return rc;
+  const AccumLayout lay = accum_layout(P.width, P.height);
+  FrameGeom g = make_geom(e, P, (unsigned*)((char*)accum + lay.bits_off));
+  // inside a CUDA-graph capture (a host may capture whole frames and replay them) the timing events are not recorded:
+  // they could not be read back anyway
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CU(cudaStreamIsCapturing(e->stream, &cap));
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
+  if (clear_first) CU(cudaMemsetAsync(accum, 0, lay.total, e->stream));
+  if (g.stats) CU(cudaMemsetAsync(e->d_stats, 0, 4 * sizeof(unsigned long long), e->stream));
+  if (!capturing) CU(cudaEventRecord(e->ev_trace0, e->stream));
+  if (is_exact_fast(P)) {
+    rc = P.precision == LFB_STRICT ? launch_exact_frame<double>(e, P, g, accum, capturing) : launch_exact_frame<float>(e, P, g, accum, capturing);
+    if (rc) return rc;
+  } else if (e->n_jobs > 0) {
+    if (P.precision == LFB_FP64) CU(launch_trace_splat_f64(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
+    else CU(launch_trace_splat_f32(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
+    e->launches++;
   }
   if (!capturing) {
     CU(cudaEventRecord(e->ev_trace1, e->stream));
@@ -713,9 +800,20 @@ extern "C" int lfb_abi_version(void) { return LFB_ABI_VERSION; }
 
 extern "C" const char* lfb_last_error(void) { return g_err.c_str(); }
 
-extern "C" int lfb_create(lfb_engine** out, int device_id) {
+extern "C" int lfb_create(lfb_engine** out, int device_id) { return lfb_create_ex(out, device_id, nullptr); }
+
+extern "C" int lfb_create_ex(lfb_engine** out, int device_id, const lfb_options* options) {
   if (!out) return fail(LFB_ERR_INVALID, "out is NULL");
   *out = nullptr;
+  lfb_options opt;
+  memset(&opt, 0, sizeof(opt));
+  if (options) {
+    if (options->struct_size < (int32_t)sizeof(int32_t) || options->struct_size > (int32_t)sizeof(lfb_options))
+      return fail(LFB_ERR_INVALID, "lfb_options.struct_size must be sizeof(lfb_options) of the caller's header");
+    memcpy(&opt, options, (size_t)options->struct_size);
+  }
+  opt.struct_size = (int32_t)sizeof(lfb_options);
+  if (opt.kernel_select < 0 || opt.kernel_select > 2) return fail(LFB_ERR_INVALID, "lfb_options.kernel_select must be 0, 1 or 2");
   int n = 0;
   cudaError_t err = cudaGetDeviceCount(&n);
   if (err != cudaSuccess || n < 1) {
@@ -732,12 +830,11 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   lfb_engine* e = new (std::nothrow) lfb_engine();
   if (!e) return fail(LFB_ERR_NOMEM, "out of host memory");
   e->device = device_id;
-  // LFB_STREAM_PRIORITY=high: for a second engine whose short kernels (finalize, peer reduce) must slip in between the
-  // CTAs of another engine's long trace kernel on the same device
+  e->opt = opt;
+  if (opt.prefix_budget_bytes > 0) e->prefix_budget = (size_t)opt.prefix_budget_bytes;
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  const char* prio_env = getenv("LFB_STREAM_PRIORITY");
-  const int prio = (prio_env && !strcmp(prio_env, "high")) ? prio_hi : prio_lo;
+  const int prio = opt.stream_priority == 1 ? prio_hi : prio_lo;
   cudaError_t rc = cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio);
   if (rc == cudaSuccess) rc = cudaStreamCreateWithPriority(&e->prefix_stream, cudaStreamNonBlocking, prio_hi);
   for (int k = 0; k < 2 && rc == cudaSuccess; k++) {
@@ -750,17 +847,12 @@ extern "C" int lfb_create(lfb_engine** out, int device_id) {
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_trace1);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_frame1);
   if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_dump_job, sizeof(Job));
-  if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_dump_prog, sizeof(Step) * LFB_MAX_STEPS);
+  if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_dump_prog, sizeof(StepD) * LFB_MAX_STEPS);
   if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_bbox, 4 * sizeof(int));
+  if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_stats, 4 * sizeof(unsigned long long));
+  if (rc == cudaSuccess) rc = cudaMemset(e->d_stats, 0, 4 * sizeof(unsigned long long));
   if (rc == cudaSuccess) rc = cudaHostAlloc((void**)&e->h_bbox, 8 * sizeof(int), cudaHostAllocDefault);
   if (rc == cudaSuccess) { e->h_bbox[0] = e->h_bbox[1] = 0x7fffffff; e->h_bbox[2] = e->h_bbox[3] = -0x7fffffff; }
-  if (const char* env = getenv("LFB_EXACT_PATCH")) e->patch = atoi(env);
-  if (const char* env = getenv("LFB_EXACT_MINB")) e->min_blocks = atoi(env);
-  if (const char* env = getenv("LFB_EXACT_WEIGHTS")) e->use_lut = strcmp(env, "closed") != 0;
-  if (const char* env = getenv("LFB_EXACT_PREFIX")) e->use_prefix = atoi(env) != 0;
-  if (const char* env = getenv("LFB_PREFIX_OVERLAP")) e->prefix_overlap = atoi(env) != 0;
-  if (const char* env = getenv("LFB_EXACT_FAMILY")) { e->use_family = atoi(env) != 0; e->force_family = e->use_family; }
-  if (const char* env = getenv("LFB_PREFIX_BUDGET_MB")) e->prefix_budget = (size_t)atoll(env) << 20;
   if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
   *out = e;
   return LFB_OK;
@@ -770,8 +862,11 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
-  cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox); cudaFree(e->d_lut);
+  {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
+  }
+  cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox); cudaFree(e->d_lut); cudaFree(e->d_stats);
   cudaFree(e->d_slots); cudaFree(e->d_slot_progs); cudaFree(e->d_prefix); cudaFree(e->d_prefix2);
   if (e->prefix_stream) { cudaStreamSynchronize(e->prefix_stream); cudaStreamDestroy(e->prefix_stream); }
   for (int k = 0; k < 2; k++) {
@@ -914,7 +1009,10 @@ extern "C" int lfb_set_lens(lfb_engine* e, const lfb_lens* L) {
   memcpy(D.ior, L->ior, sizeof(D.ior));
   memcpy(D.lambda_nm, L->lambda_nm, sizeof(D.lambda_nm));
   D.P = L->entrance_half_height; D.h_stop = L->stop_half_height; D.h_stop_neg = L->stop_half_height_neg;
-  if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
+  }
   // REF_QUADS tables: the reference's pair list and per-wavelength colour basis
   int pairs[LFB_MAX_SURFACES * LFB_MAX_SURFACES][2];
   const int np = list_pairs(*L, LFB_PAIRS_REF, pairs);
@@ -930,7 +1028,7 @@ extern "C" int lfb_set_lens(lfb_engine* e, const lfb_lens* L) {
   e->n_ref_pairs = np; e->n_ref_ghosts = 0;
   {
     std::vector<float2> lut;
-    build_reflectance_tables(*L, lut);
+    build_reflectance_tables(*L, lut, e->poly);
     cudaFree(e->d_lut);
     e->d_lut = nullptr;
     CU(cudaMalloc((void**)&e->d_lut, sizeof(float2) * lut.size()));
@@ -963,7 +1061,10 @@ extern "C" int lfb_set_aperture(lfb_engine* e, const float* texels, int w, int h
 // ---------------------------------------------------------------------------
 // the hot path
 // ---------------------------------------------------------------------------
-extern "C" size_t lfb_accum_bytes(int width, int height) { return sizeof(unsigned long long) * 3 * (size_t)width * (size_t)height; }
+extern "C" size_t lfb_accum_bytes(int width, int height) {
+  if (width < 1 || height < 1) return 0;
+  return accum_layout(width, height).total;
+}
 
 extern "C" void* lfb_stream(lfb_engine* e) { return e ? (void*)e->stream : nullptr; }
 
@@ -1049,7 +1150,7 @@ extern "C" int lfb_reduce_finalize_peers(lfb_engine* e, const void* const* accum
   const size_t npx = (size_t)P->width * P->height;
   const size_t p0 = npx * (size_t)rank / (size_t)n_ranks, p1 = npx * (size_t)(rank + 1) / (size_t)n_ranks;
   const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
-  CU(launch_reduce_finalize(A, (const unsigned long long*)multicast_accum, p0, p1, inv, out_dev, out_stride_bytes, out_elem, e->stream));
+  CU(launch_reduce_finalize(A, (const unsigned long long*)multicast_accum, p0, p1, inv, out_dev, out_stride_bytes, out_elem, e->opt.reduce_ctas, e->stream));
   e->launches++;
   return LFB_OK;
 }
@@ -1237,17 +1338,25 @@ extern "C" int lfb_dump_rays(lfb_engine* e, const lfb_light* light, const lfb_pa
   Job J;
   JobId id = {0, direct ? -1 : i, direct ? -1 : j, lambda};
   fill_job(e, *P, *light, id, &J);
-  Step prog[LFB_MAX_STEPS];
-  J.n_steps = build_program(e->lens, e->dev_lens, lambda, id.i, id.j, prog);
+  const bool fast = is_exact_fast(*P), strict = P->precision == LFB_STRICT;
+  if (fast) {
+    StepD prog[LFB_MAX_STEPS];
+    J.n_steps = build_program(e, lambda, id.i, id.j, prog);
+    std::vector<char> staged(sizeof(StepD) * LFB_MAX_STEPS);
+    put_steps(strict, staged.data(), 0, prog, J.n_steps);
+    CU(cudaMemcpyAsync(e->d_dump_prog, staged.data(), (strict ? sizeof(StepD) : sizeof(StepF)) * (size_t)J.n_steps, cudaMemcpyHostToDevice, e->stream));
+  }
   CU(cudaMemcpyAsync(e->d_dump_job, &J, sizeof(Job), cudaMemcpyHostToDevice, e->stream));
-  CU(cudaMemcpyAsync(e->d_dump_prog, prog, sizeof(Step) * (size_t)J.n_steps, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));  // J and the staged program live on this call's stack
   if (P->mode == LFB_MODE_PARAXIAL_GRID) {
     CU(launch_paraxial_setup(e->d_dump_job, 1, P->physical_backward, e->stream));
     e->launches++;
   }
-  const FrameGeom g = make_geom(e, *P);
-  if (P->precision == LFB_FP64) CU(launch_trace_dump_f64(e->d_dump_job, g, P->mode, e->d_tex, e->d_hits, e->stream));
-  else CU(launch_trace_dump_f32(e->d_dump_job, e->d_dump_prog, g, P->mode, e->d_tex, e->d_hits, e->stream));
+  const FrameGeom g = make_geom(e, *P, nullptr);
+  if (fast && strict) CU(launch_exact_dump<double>(e->d_dump_job, (const StepD*)e->d_dump_prog, g, e->d_tex, e->d_hits, e->stream));
+  else if (fast) CU(launch_exact_dump<float>(e->d_dump_job, (const StepF*)e->d_dump_prog, g, e->d_tex, e->d_hits, e->stream));
+  else if (P->precision == LFB_FP64) CU(launch_trace_dump_f64(e->d_dump_job, g, P->mode, e->d_tex, e->d_hits, e->stream));
+  else CU(launch_trace_dump_f32(e->d_dump_job, g, P->mode, e->d_tex, e->d_hits, e->stream));
   e->launches++;
   CU(cudaMemcpyAsync(out, e->d_hits, sizeof(lfb_ray_hit) * n, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
@@ -1319,10 +1428,9 @@ int starburst_device(lfb_engine* e, const lfb_light* lights, int n_lights, int w
   f.exponent = -flare_intensity + 3.0;  // :998-1001
   if (f.exponent <= 0) f.exponent = 2.0;
   // the pattern is periodic in the (integer) pixel offsets with period W_t (2 W_t for an odd W_t): evaluate one period
-  // when the frame is larger (LFB_STARBURST_LATTICE=0 forces one column / row per pixel)
+  // when the frame is larger (options.starburst_lattice = -1 forces one column / row per pixel)
   f.period = (e->star_w % 2 == 0) ? e->star_w : 2 * e->star_w;
-  const char* lat = getenv("LFB_STARBURST_LATTICE");
-  const bool lattice_ok = !(lat && atoi(lat) == 0);
+  const bool lattice_ok = e->opt.starburst_lattice >= 0;
   f.lattice_x = lattice_ok && width > f.period;
   f.lattice_y = lattice_ok && height > f.period;
   f.n_col = f.lattice_x ? f.period : width;
@@ -1470,6 +1578,18 @@ extern "C" int lfb_stats(lfb_engine* e, uint64_t* kernel_launches, float* last_t
     *last_trace_ms = e->last_trace_ms;
   }
   if (last_frame_ms) *last_frame_ms = e->last_frame_ms;
+  return LFB_OK;
+}
+
+extern "C" int lfb_exec_stats(lfb_engine* e, uint64_t out[4]) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!out) return fail(LFB_ERR_INVALID, "out is NULL");
+  if (!e->opt.collect_stats) return fail(LFB_ERR_STATE, "the engine was not created with lfb_options.collect_stats = 1");
+  CU(cudaStreamSynchronize(e->stream));
+  unsigned long long h[4];
+  CU(cudaMemcpy(h, e->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+  out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = e->last_families ? 1 : 0;
   return LFB_OK;
 }
 

@@ -1,0 +1,776 @@
+// exact_trace.cuh -- the throughput kernels of the ghost path: EXACT_GRID.
+//
+// Templated on the geometry type T:
+//   T = float   LFB_FP32    the FP32 kernels north_star asks for (exact_f32.cu)
+//   T = double  LFB_STRICT  the same kernels with FP64 positions / directions (exact_f64.cu): per-ray sensor hits within
+//                           1e-5 lens units of the double oracle (measured ~1e-9), which FP32 cannot give at |x| ~ 500
+// Weights (Fresnel / coating products, mask products) are FP32 in both.
+//
+// There is no memory stream to speak of (rays are generated from their grid index, a ghost's whole description is ~1.5 KB,
+// the 1 MB aperture mask is L2/L1 resident), so the design minimises instructions and stalls per ray (ncu, profiles/):
+//
+//  * STEP PROGRAM.  The host flattens each ghost (i, j, lambda) into a straight list of steps (refract / reflect / stop
+//    plane / sensor plane) with every ray-independent quantity already computed (lfb_internal.h: StepT).  A CTA stages
+//    its ghost's program in shared memory once; the per-ray loop has no "which surface / which direction / which glass"
+//    logic and no divisions by constants.
+//  * UNIFIED STEP.  Planes are c = 0 surfaces with an infinite clear radius; a missed surface or a total internal
+//    reflection turns the state into NaNs that the next clear-radius test catches: ONE death test per step.
+//  * FAST SCALAR MATH.  float: rcp.approx / sqrt.approx (one MUFU each).  double: the 20-bit MUFU seeds
+//    (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64) refined by two Newton steps, no IEEE division or square-root sequences.
+//  * POLYNOMIAL WEIGHTS.  The factor a surface multiplies the ray's weight by (R at a reflection, 1 - R at a refraction;
+//    bare Fresnel or the quarter-wave film) is a degree-7 polynomial in the cosine in the rarer medium, fitted per
+//    (wavelength, surface, direction) on the host in double: 9 FMAs in their own dependency chain and NO memory access in
+//    the surface loop (round 1's table lookups were 40 % of the kernel's stall cycles).  Rays steeper than acos(0.6)
+//    fall back to the 1024-interval table.
+//  * MIRROR SYMMETRY.  A light's bundle and the lens are symmetric about the meridional plane: ray (x, -y) is the mirror
+//    image of ray (x, y).  One trace serves both; only the (asymmetric) aperture mask is looked up twice.
+//  * PREFIX CACHE.  The forward sweep 0 .. j-1 shared by all ghosts of a (light, wavelength) is traced once
+//    (prefix_kernel) and the ray states on every surface cached in L2; ghost jobs start ON their first-reflection surface.
+//  * WARP-AUTONOMOUS SPLAT.  A warp owns its 32 ray pairs from trace to flush: survivors stay in registers, deposits go
+//    to a 64-pixel u64 fixed-point tile per warp in shared memory and each touched pixel is flushed with one global atomic
+//    (direct global atomics when the footprint exceeds the tile).  The only CTA barrier is the one after staging the
+//    program.  Integer accumulation keeps the frame bit-stable for any schedule, kernel or GPU count.
+//  * DIRTY TILES.  Every flush marks the 16 x 16 sensor tiles it touches in a bitmap (read first, atomicOr only when the
+//    bit is clear), so that finalize / read-back / the cross-GPU reduce visit the ~1 % of the frame that is not zero.
+//
+// Kernels: prefix_kernel (forward sweeps + the direct path), ghost_kernel (one job per ghost pair), family_kernel (one
+// thread follows every ghost sharing a first reflection; forks at each second reflection), dump_kernel (per-ray records).
+// Parity: per-ray and image tolerances against the double-precision oracle are in tests/test_gpu_parity.py; the FP64
+// kernels in ghost_grid_impl.cuh remain the oracle-order, bit-exact instruments.
+#pragma once
+#include <math_constants.h>
+
+#include "lfb_internal.h"
+
+namespace lfb {
+namespace xt {
+
+// ---------------------------------------------------------------------------------------------------------------
+// scalar math per geometry type
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct M;
+template <> struct M<float> {
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+  static __device__ __forceinline__ float rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+  }
+  static __device__ __forceinline__ float sqrt(float x) {  // NaN for x < 0
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+  }
+  static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+  static __device__ __forceinline__ float copysign(float m, float s) { return copysignf(m, s); }
+  static __device__ __forceinline__ float floor(float x) { return floorf(x); }
+  static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ float nan() { return CUDART_NAN_F; }
+  // g0 when nd carries a sign bit (the normal faces the ray), -g0 otherwise
+  static __device__ __forceinline__ float flip_unless_neg(float g0, float nd) {
+    return __int_as_float(__float_as_int(g0) ^ (~__float_as_int(nd) & 0x80000000));
+  }
+  static __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+};
+template <> struct M<double> {
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+  static __device__ __forceinline__ double rcp(double x) {  // 20-bit seed, two Newton steps: ~1e-16 relative
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = ::fma(-x, y, 1.0);
+    y = ::fma(y, e, y);
+    e = ::fma(-x, y, 1.0);
+    return ::fma(y, e, y);
+  }
+  static __device__ __forceinline__ double sqrt(double x) {  // NaN for x < 0; 0 for 0
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y;
+    double r = ::fma(-g, y, 1.0);
+    y = ::fma(0.5 * y, r, y);
+    g = x * y;
+    r = ::fma(-g, y, 1.0);
+    y = ::fma(0.5 * y, r, y);
+    g = x * y;
+    g = ::fma(::fma(-g, g, x), 0.5 * y, g);
+    return x == 0.0 ? 0.0 : g;
+  }
+  static __device__ __forceinline__ double abs(double x) { return fabs(x); }
+  static __device__ __forceinline__ double copysign(double m, double s) { return ::copysign(m, s); }
+  static __device__ __forceinline__ double floor(double x) { return ::floor(x); }
+  static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
+  static __device__ __forceinline__ double nan() { return CUDART_NAN; }
+  static __device__ __forceinline__ double flip_unless_neg(double g0, double nd) { return signbit(nd) ? g0 : -g0; }
+  static __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+};
+
+// The per-job constants in the geometry type (the host fills both copies, lfb_internal.h: Job).
+template <typename T> struct JobC;
+template <> struct JobC<float> {
+  float sin_t, cos_t, inv_d, sx, sy, cs, sn, ppu;
+  __device__ __forceinline__ explicit JobC(const Job& J)
+      : sin_t(J.f_sin_t), cos_t(J.f_cos_t), inv_d(J.f_inv_dist), sx(J.f_sx), sy(J.f_sy), cs(J.f_cs), sn(J.f_sn), ppu(J.f_ppu) {}
+};
+template <> struct JobC<double> {
+  double sin_t, cos_t, inv_d, sx, sy, cs, sn, ppu;
+  __device__ __forceinline__ explicit JobC(const Job& J)
+      : sin_t(J.sin_t), cos_t(J.cos_t), inv_d(J.inv_dist), sx(J.sx), sy(J.sy), cs(J.cs), sn(J.sn), ppu(J.ppu) {}
+};
+
+struct MaskGeom {
+  const float* tex;
+  int tw, th;
+  float su, sv, ou, ov;  // u = xa*su + ou ; v = ya*sv + ov
+  __device__ __forceinline__ explicit MaskGeom(const FrameGeom& g, const float* t)
+      : tex(t), tw(g.tex_w), th(g.tex_h), su(g.mask_su), sv(g.mask_sv), ou(g.mask_ou), ov(g.mask_ov) {}
+};
+
+template <typename T>
+__device__ __forceinline__ float mask_lookup(const MaskGeom& K, T xa, T ya) {
+  const T fu = M<T>::floor(M<T>::fma(xa, (T)K.su, (T)K.ou)), fv = M<T>::floor(M<T>::fma(ya, (T)K.sv, (T)K.ov));
+  if (!(fu >= (T)0 && fu < (T)K.tw && fv >= (T)0 && fv < (T)K.th)) return 0.f;
+  return __ldg(K.tex + ((unsigned)(int)fv * (unsigned)K.tw + (unsigned)(int)fu));  // in range, checked above
+}
+
+// Reflectance from the interface's table (rays steeper than acos(kPolyV0) only): R over v = the cosine of the ray's angle
+// in the RARER of the two media (in which R is analytic: R -> 1 linearly as v -> 0, i.e. at grazing incidence or at the
+// critical angle), 1024 intervals, linear interpolation of (R_i, R_{i+1} - R_i) pairs built on the host in double.
+__device__ __forceinline__ float reflectance_lut(const float2* __restrict__ lut, int table, float v) {
+  const float t = fminf(fmaxf(v, 0.f), 1.f) * (float)kLutSize;  // fmaxf(NaN, 0) = 0: beyond the critical angle R = 1
+  const int i = min((int)t, kLutSize - 1);
+  const float2 e = __ldg(lut + ((unsigned)table * (unsigned)kLutSize + (unsigned)i));
+  return fmaf(t - (float)i, e.y, e.x);
+}
+
+// The factor a step multiplies the weight by: the step's polynomial (Estrin: depth 4) on v >= kPolyV0, else the table.
+template <typename T>
+__device__ __forceinline__ float weight_factor(const StepT<T>& S, bool refl, const float2* __restrict__ lut, float v) {
+  if (v >= kPolyV0) {
+    const float x = fmaf(-v, kPolyScale, kPolyScale);  // (1 - v) / (1 - v0) in [0, 1]
+    const float x2 = x * x, x4 = x2 * x2;
+    const float a = fmaf(S.p[1], x, S.p[0]), b = fmaf(S.p[3], x, S.p[2]), c = fmaf(S.p[5], x, S.p[4]), d = fmaf(S.p[7], x, S.p[6]);
+    return fmaf(x4, fmaf(d, x2, c), fmaf(b, x2, a));
+  }
+  const float R = reflectance_lut(lut, S.lut, v);  // v NaN (total internal reflection) lands here: R = 1
+  return refl ? R : 1.f - R;
+}
+
+// A ray on (or heading for) a surface.  Position is relative to the current surface's vertex.
+template <typename T>
+struct RayState {
+  T ox, oy, oz, dx, dy, dz;
+  float w, ma, mb;  // Fresnel product; mask products of the ray and of its mirror image
+};
+
+struct RayDiag {  // parity-instrument variant only
+  unsigned flags;
+  double xa, ya;
+};
+
+// First half of a step: move the ray onto the step's surface (sphere or plane through its vertex) and test the clear
+// aperture.  False = the ray is dead (missed, vignetted, or NaN from a total internal reflection upstream).
+template <typename T, bool FLAGS>
+__device__ __forceinline__ bool propagate(const StepT<T>& S, RayState<T>& r, RayDiag& o) {
+  typedef M<T> m;
+  const T c = S.c;
+  const T pz = r.oz + S.dz;
+  const T pd = m::fma(r.ox, r.dx, m::fma(r.oy, r.dy, pz * r.dz));
+  const T pp = m::fma(r.ox, r.ox, m::fma(r.oy, r.oy, pz * pz));
+  const T B = m::fma(c, pd, -r.dz);
+  const T Cq = m::fma(c, pp, (T)-2 * pz);
+  const T disc = m::fma(B, B, -c * Cq);
+  if (FLAGS && disc < (T)0) { o.flags |= LFB_RAY_MISSED; return false; }
+  const T t = -Cq * m::rcp(B + m::copysign(m::sqrt(disc), B));
+  r.ox = m::fma(t, r.dx, r.ox); r.oy = m::fma(t, r.dy, r.oy); r.oz = m::fma(t, r.dz, pz);
+  if (!(m::fma(r.ox, r.ox, r.oy * r.oy) <= (T)S.semi2)) {  // outside the clear aperture, or NaN from a miss / TIR upstream
+    if (FLAGS) o.flags |= LFB_RAY_VIGNETTED;
+    return false;
+  }
+  return true;
+}
+
+// Second half: what the surface does to the ray (mask lookup at the stop; refraction or reflection + weight elsewhere).
+//   MIRROR  also look the mask up at (xa, -ya) for the mirror-image ray
+//   FLAGS   parity-instrument variant: classify the death, and let rays the mask stopped continue with weight 0 so that
+//           their positions stay comparable with the oracle
+template <typename T, bool MIRROR, bool FLAGS>
+__device__ __forceinline__ bool interact(const StepT<T>& S, const MaskGeom& K, const float2* __restrict__ lut, RayState<T>& r, RayDiag& o) {
+  typedef M<T> m;
+  const int op = S.op;
+  if (op >= STEP_PASS) {  // no change of direction: identical media, the stop, the sensor
+    if (op == STEP_STOP) {
+      const float mk = mask_lookup<T>(K, r.ox, r.oy);
+      r.ma *= mk;
+      if (MIRROR) r.mb *= mask_lookup<T>(K, r.ox, -r.oy);
+      if (FLAGS) { o.xa = (double)r.ox; o.ya = (double)r.oy; if (mk == 0.f) o.flags |= LFB_RAY_STOPPED; }
+      else if (MIRROR ? (r.ma == 0.f && r.mb == 0.f) : (r.ma == 0.f)) return false;
+    }
+    return true;
+  }
+  const T c = S.c, eta = S.eta;
+  const T nx = -c * r.ox, ny = -c * r.oy, nz = m::fma(-c, r.oz, (T)1);
+  const T nd = m::fma(nx, r.dx, m::fma(ny, r.dy, nz * r.dz));
+  const T c0 = m::abs(nd);
+  const T s2 = m::fma(-c0, c0, (T)1);
+  const T k2 = m::fma(-S.eta2, s2, (T)1);
+  const T c2 = m::sqrt(k2);  // NaN beyond the critical angle
+  const bool refl = op == STEP_REFLECT;
+  if (FLAGS && !refl && k2 < (T)0) { o.flags |= LFB_RAY_TIR; return false; }
+  // refract: d' = eta d + (eta c0 - c2) N with N = -sign(nd) n the normal facing the ray;  reflect: d' = d - 2 nd n
+  const T g = m::flip_unless_neg(m::fma(eta, c0, -c2), nd);
+  const T alpha = refl ? (T)1 : eta, beta = refl ? (T)-2 * nd : g;
+  r.dx = m::fma(alpha, r.dx, beta * nx); r.dy = m::fma(alpha, r.dy, beta * ny); r.dz = m::fma(alpha, r.dz, beta * nz);
+  r.w *= weight_factor<T>(S, refl, lut, (float)(eta > (T)1 ? c2 : c0));
+  return true;
+}
+
+// Entrance ray of grid point (x, y).  Directional light (inv_d = 0): the bundle's common direction.  Point light at
+// -D (sin t, 0, cos t): along v = (x/D + sin t, y/D, cos t), carrying the irradiance at the entrance point relative to the
+// vertex, |v|^-3 (lfb_light.distance).  The light lies in the plane y = 0, so the mirror pair (x, -y) stays a mirror pair.
+template <typename T>
+__device__ __forceinline__ void start_ray(RayState<T>& r, T x, T y, const JobC<T>& J) {
+  typedef M<T> m;
+  r.ox = x; r.oy = y; r.oz = (T)0; r.dx = J.sin_t; r.dy = (T)0; r.dz = J.cos_t; r.w = 1.f; r.ma = 1.f; r.mb = 1.f;
+  if (J.inv_d != (T)0) {  // uniform per job
+    const T vx = m::fma(x, J.inv_d, J.sin_t), vy = m::mul_rn(y, J.inv_d);
+    const T q = m::fma(vx, vx, m::fma(vy, vy, m::mul_rn(J.cos_t, J.cos_t)));
+    const T rl = m::rcp(m::sqrt(q));
+    r.dx = m::mul_rn(vx, rl); r.dy = m::mul_rn(vy, rl); r.dz = m::mul_rn(J.cos_t, rl);
+    r.w = (float)m::mul_rn(m::mul_rn(rl, rl), rl);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void grid_point(const FrameGeom& g, int a, int b, T& x, T& y) {
+  x = M<T>::fma((T)a + (T)0.5, (T)g.cell_d, -(T)g.P_d);
+  y = M<T>::fma((T)b + (T)0.5, (T)g.cell_d, -(T)g.P_d);
+}
+template <>
+__device__ __forceinline__ void grid_point<float>(const FrameGeom& g, int a, int b, float& x, float& y) {
+  x = fmaf((float)a + 0.5f, g.cell, -g.P);
+  y = fmaf((float)b + 0.5f, g.cell, -g.P);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PREFIX CACHE.  Every ghost (i, j) of a light and wavelength begins with the same forward sweep through surfaces
+// 0 .. j-1.  prefix_kernel traces that sweep ONCE per (light, wavelength) "slot" and caches each ray's state as it
+// arrives ON every surface (NaN = dead); a ghost job loads the state at its first-reflection surface j and starts with
+// the reflection.  Layout: prefix[((slot * n_surf + k) * PARTS + part) * half_rays + ray], 16-byte parts:
+//   float  (PARTS = 2)  (ox, oy, oz, w) (dx, dy, ma, mb); dz = +sqrt(1 - dx^2 - dy^2) on load (the sweep travels forward)
+//   double (PARTS = 4)  (ox, oy) (oz, dx) (dy, dz) (w, ma, mb, -)
+// canon(): what a load does to a state that was never stored -- applied by jobs that trace their own forward sweep (no
+// cache, e.g. over the memory budget), so that a frame has the same bits with or without the cache.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct PrefixIO;
+template <> struct PrefixIO<float> {
+  static constexpr int kParts = 2;
+  static __device__ __forceinline__ void store(float4* dst, size_t hr, const RayState<float>& r) {
+    dst[0] = make_float4(r.ox, r.oy, r.oz, r.w);
+    dst[hr] = make_float4(r.dx, r.dy, r.ma, r.mb);
+  }
+  static __device__ __forceinline__ void store_dead(float4* dst, size_t) { dst[0] = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ void canon(RayState<float>& r) {
+    r.dz = M<float>::sqrt(fmaxf(fmaf(-r.dx, r.dx, fmaf(-r.dy, r.dy, 1.f)), 0.f));
+  }
+  static __device__ __forceinline__ bool load(const float4* __restrict__ src, size_t hr, RayState<float>& r) {
+    const float4 s0 = __ldg(src);
+    if (!(s0.x == s0.x)) return false;  // NaN: the ray died in the forward sweep before reaching this surface
+    const float4 s1 = __ldg(src + hr);
+    r.ox = s0.x; r.oy = s0.y; r.oz = s0.z; r.w = s0.w;
+    r.dx = s1.x; r.dy = s1.y; r.ma = s1.z; r.mb = s1.w;
+    canon(r);
+    return true;
+  }
+};
+template <> struct PrefixIO<double> {
+  static constexpr int kParts = 4;
+  static __device__ __forceinline__ void store(float4* dst, size_t hr, const RayState<double>& r) {
+    double2* d = reinterpret_cast<double2*>(dst);
+    d[0] = make_double2(r.ox, r.oy);
+    d[hr] = make_double2(r.oz, r.dx);
+    d[2 * hr] = make_double2(r.dy, r.dz);
+    dst[3 * hr] = make_float4(r.w, r.ma, r.mb, 0.f);
+  }
+  static __device__ __forceinline__ void store_dead(float4* dst, size_t) {
+    reinterpret_cast<double2*>(dst)[0] = make_double2(CUDART_NAN, 0.0);
+  }
+  static __device__ __forceinline__ void canon(RayState<double>&) {}
+  static __device__ __forceinline__ bool load(const float4* __restrict__ src, size_t hr, RayState<double>& r) {
+    const double2* s = reinterpret_cast<const double2*>(src);
+    const double2 a = __ldg(s);
+    if (!(a.x == a.x)) return false;
+    const double2 b = __ldg(s + hr), c = __ldg(s + 2 * hr);
+    const float4 w = __ldg(src + 3 * hr);
+    r.ox = a.x; r.oy = a.y; r.oz = b.x; r.dx = b.y; r.dy = c.x; r.dz = c.y;
+    r.w = w.x; r.ma = w.y; r.mb = w.z;
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// landing: sensor point -> pixel taps -> per-warp shared-memory tile -> global atomics + dirty-tile marks
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWarpTilePx = 64;  // per-warp shared-memory sensor tile (pixels)
+
+struct Tap {  // one image of a ray on the sensor: top-left pixel of its footprint and the bilinear fractions
+  int ix, iy;
+  float fx, fy;
+};
+
+template <typename T>
+__device__ __forceinline__ Tap to_tap(const JobC<T>& J, bool bilinear, T xs, T ys) {
+  typedef M<T> m;
+  const T X = -J.ppu * xs, Y = J.ppu * ys;
+  const T px = J.sx + m::fma(X, J.cs, -m::mul_rn(Y, J.sn));
+  const T py = J.sy + m::fma(X, J.sn, m::mul_rn(Y, J.cs));
+  Tap t;
+  if (bilinear) {
+    const T qx = m::sub_rn(px, (T)0.5), qy = m::sub_rn(py, (T)0.5);
+    const T fx0 = m::floor(qx), fy0 = m::floor(qy);
+    t.fx = (float)m::sub_rn(qx, fx0); t.fy = (float)m::sub_rn(qy, fy0);
+    // NaN or far outside: park the tap where the footprint test rejects it (int conversion of huge values is undefined)
+    const bool sane = fx0 >= (T)-2 && fx0 < (T)65536 && fy0 >= (T)-2 && fy0 < (T)65536;
+    t.ix = sane ? (int)fx0 : -2; t.iy = sane ? (int)fy0 : -2;
+  } else {
+    const T fx0 = m::floor(px), fy0 = m::floor(py);
+    const bool sane = fx0 >= (T)-1 && fx0 < (T)65536 && fy0 >= (T)-1 && fy0 < (T)65536;
+    t.fx = t.fy = 0.f;
+    t.ix = sane ? (int)fx0 : -1; t.iy = sane ? (int)fy0 : -1;
+  }
+  return t;
+}
+
+// Footprint of one tap clipped to the sensor (bilinear: 2x2 pixels from (ix, iy); nearest: the pixel itself).
+__device__ __forceinline__ bool footprint(bool bilinear, const Tap& t, int W, int H, int& x0, int& y0, int& x1, int& y1) {
+  if (bilinear) {
+    if (!(t.ix >= -1 && t.ix < W && t.iy >= -1 && t.iy < H)) return false;
+    x0 = max(t.ix, 0); y0 = max(t.iy, 0); x1 = min(t.ix + 1, W - 1); y1 = min(t.iy + 1, H - 1);
+  } else {
+    if (!(t.ix >= 0 && t.ix < W && t.iy >= 0 && t.iy < H)) return false;
+    x0 = x1 = t.ix; y0 = y1 = t.iy;
+  }
+  return true;
+}
+
+struct WarpSplat {  // what a warp needs to deposit its lanes' results
+  unsigned long long* tile;   // this warp's shared-memory tile
+  unsigned long long* accum;  // global sensor accumulators
+  int* bbox;
+  unsigned* tile_bits;
+  int tiles_w;
+  int W, H;
+  float ch0, ch1, ch2;        // radiance * rgb_weight * ray area * 2^bits
+  bool bilinear;
+  __device__ __forceinline__ WarpSplat(const FrameGeom& g, const Job& J, unsigned long long* tile_, unsigned long long* accum_)
+      : tile(tile_), accum(accum_), bbox(g.bbox), tile_bits(g.tile_bits), tiles_w(g.tiles_w), W(g.W), H(g.H), ch0(J.f_chan[0]),
+        ch1(J.f_chan[1]), ch2(J.f_chan[2]), bilinear(g.splat == LFB_SPLAT_BILINEAR) {}
+};
+
+// The pixels of one tap into the shared-memory tile (origin (tx0, ty0), row pitch tw) or straight into the accumulators.
+// Explicit roundings: no FMA contraction, so every instantiation of every kernel produces the same bits.
+__device__ __forceinline__ void splat_tap(const WarpSplat& S, unsigned long long* tile, int tx0, int ty0, int tw, const Tap& t, float w) {
+  float wt[4];
+  if (S.bilinear) {
+    const float gx = __fsub_rn(1.f, t.fx), gy = __fsub_rn(1.f, t.fy);
+    wt[0] = __fmul_rn(w, __fmul_rn(gx, gy)); wt[1] = __fmul_rn(w, __fmul_rn(t.fx, gy));
+    wt[2] = __fmul_rn(w, __fmul_rn(gx, t.fy)); wt[3] = __fmul_rn(w, __fmul_rn(t.fx, t.fy));
+  } else {
+    wt[0] = w; wt[1] = wt[2] = wt[3] = 0.f;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int jx = t.ix + (q & 1), jy = t.iy + (q >> 1);
+    if (wt[q] == 0.f || jx < 0 || jx >= S.W || jy < 0 || jy >= S.H) continue;
+    unsigned long long* dst = tile ? tile + 3 * ((jy - ty0) * tw + (jx - tx0)) : S.accum + 3 * ((size_t)jx + (size_t)jy * S.W);
+    if (!tile && S.tile_bits) mark_tile(S.tile_bits, S.tiles_w, jx >> kTilePxLog2, jy >> kTilePxLog2);
+    // channels a wavelength does not feed (RGB lenses: two of three) are skipped without converting anything
+    if (S.ch0 != 0.f) { const long long v = __float2ll_rn(__fmul_rn(wt[q], S.ch0)); if (v) atomicAdd(dst + 0, (unsigned long long)v); }
+    if (S.ch1 != 0.f) { const long long v = __float2ll_rn(__fmul_rn(wt[q], S.ch1)); if (v) atomicAdd(dst + 1, (unsigned long long)v); }
+    if (S.ch2 != 0.f) { const long long v = __float2ll_rn(__fmul_rn(wt[q], S.ch2)); if (v) atomicAdd(dst + 2, (unsigned long long)v); }
+  }
+}
+
+// Deposit one (ray, mirror image) result per lane; warp-collective (all 32 lanes call it).  Only lanes whose ray (or its
+// mirror image) lands carry taps, weights and a footprint: nothing reads them on the other lanes.  Returns whether this
+// lane landed (statistics).
+template <typename T>
+__device__ __forceinline__ bool warp_land(const WarpSplat& S, const JobC<T>& J, bool alive, T xs, T ys, float wa, float wb, bool has_mirror,
+                                          int lane) {
+  int bx0, by0, bx1, by1;
+  Tap ta, tb;
+  float w0 = 0.f, w1 = 0.f;
+  bool lands = false;
+  if (alive) {
+    int x0, y0, x1, y1;
+    bx0 = by0 = 0x7fffffff; bx1 = by1 = -0x7fffffff;
+    ta.ix = ta.iy = tb.ix = tb.iy = 0; ta.fx = ta.fy = tb.fx = tb.fy = 0.f;
+    if (wa > 0.f) {
+      ta = to_tap<T>(J, S.bilinear, xs, ys);
+      if (footprint(S.bilinear, ta, S.W, S.H, x0, y0, x1, y1)) {
+        w0 = wa; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+      }
+    }
+    if (wb > 0.f && has_mirror) {
+      tb = to_tap<T>(J, S.bilinear, xs, -ys);
+      if (footprint(S.bilinear, tb, S.W, S.H, x0, y0, x1, y1)) {
+        w1 = wb; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
+      }
+    }
+    lands = w0 > 0.f || w1 > 0.f;
+  }
+  const unsigned landing = __ballot_sync(0xffffffffu, lands);
+  if (!landing) return false;  // nothing to deposit: the warp is done
+  if (lands) {  // the footprint of the warp's landing rays, reduced among those lanes only
+    bx0 = __reduce_min_sync(landing, bx0); by0 = __reduce_min_sync(landing, by0);
+    bx1 = __reduce_max_sync(landing, bx1); by1 = __reduce_max_sync(landing, by1);
+  }
+  const int leader = __ffs(landing) - 1;
+  bx0 = __shfl_sync(0xffffffffu, bx0, leader); by0 = __shfl_sync(0xffffffffu, by0, leader);
+  bx1 = __shfl_sync(0xffffffffu, bx1, leader); by1 = __shfl_sync(0xffffffffu, by1, leader);
+  if (lane == 0) grow_bbox(S.bbox, bx0, by0, bx1, by1);
+  const int tw = bx1 - bx0 + 1;
+  const int area = tw * (by1 - by0 + 1);
+  const bool use_tile = area <= kWarpTilePx;
+  unsigned long long* tile = use_tile ? S.tile : nullptr;
+  if (use_tile) {
+    for (int q = lane; q < 3 * area; q += 32) tile[q] = 0ull;
+    if (S.tile_bits) {  // the tiles under the warp's footprint (a 64-pixel box spans at most 5 x 1 or 2 x 2 ... tiles)
+      const int tx0 = bx0 >> kTilePxLog2, ty0 = by0 >> kTilePxLog2;
+      const int ntx = (bx1 >> kTilePxLog2) - tx0 + 1, nty = (by1 >> kTilePxLog2) - ty0 + 1;
+      for (int q = lane; q < ntx * nty; q += 32) mark_tile(S.tile_bits, S.tiles_w, tx0 + q % ntx, ty0 + q / ntx);
+    }
+    __syncwarp();
+  }
+  if (lands) {
+    if (w0 > 0.f) splat_tap(S, tile, bx0, by0, tw, ta, w0);
+    if (w1 > 0.f) splat_tap(S, tile, bx0, by0, tw, tb, w1);
+  }
+  if (!use_tile) return lands;
+  __syncwarp();
+  const float inv_tw = M<float>::rcp((float)tw);
+  for (int t = lane; t < area; t += 32) {
+    const int jy = (int)(((float)t + 0.5f) * inv_tw);  // t / tw, exact for these small integers
+    const int jx = t - jy * tw;
+    unsigned long long* dst = S.accum + 3 * ((size_t)(bx0 + jx) + (size_t)(by0 + jy) * S.W);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const unsigned long long v = tile[3 * t + c];
+      if (v) atomicAdd(dst + c, v);
+    }
+  }
+  __syncwarp();  // the tile is reused by the warp's next landing
+  return lands;
+}
+
+// statistics (STATS instantiations): executed surface steps / ray pairs started / ray pairs landed, one atomic each per warp
+__device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned steps, unsigned started, unsigned landed) {
+  steps = __reduce_add_sync(0xffffffffu, steps);
+  started = __reduce_add_sync(0xffffffffu, started);
+  landed = __reduce_add_sync(0xffffffffu, landed);
+  if ((threadIdx.x & 31) == 0 && stats) {
+    if (steps) atomicAdd(stats + 0, (unsigned long long)steps);
+    if (started) atomicAdd(stats + 1, (unsigned long long)started);
+    if (landed) atomicAdd(stats + 2, (unsigned long long)landed);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_program(StepT<T>* dst, const StepT<T>* __restrict__ src, int n_steps, int tid, int nthreads) {
+  constexpr int W16 = sizeof(StepT<T>) / 16;
+  const float4* s = reinterpret_cast<const float4*>(src);
+  float4* d = reinterpret_cast<float4*>(dst);
+  for (int q = tid; q < n_steps * W16; q += nthreads) d[q] = __ldg(s + q);
+}
+
+constexpr int kPrefixThreads = 256;
+
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(kPrefixThreads) prefix_kernel(const Job* __restrict__ slots, const StepT<T>* __restrict__ progs, FrameGeom g,
+                                                                const float* __restrict__ tex, float4* __restrict__ prefix,
+                                                                unsigned long long* __restrict__ accum) {
+  typedef PrefixIO<T> io;
+  __shared__ __align__(16) StepT<T> s_prog[LFB_MAX_SURFACES + 2];
+  __shared__ unsigned long long s_tile[(kPrefixThreads / 32) * kWarpTilePx * 3];
+  const int half_rows = (g.N + 1) / 2;
+  const int slot = blockIdx.z;  // 3-D grid (patch column, patch row, slot)
+  const Job& J = slots[slot];
+  const int n_steps = J.n_steps;  // forward refractions 0 .. n_surf-1 (the stop included); step n_surf is the sensor
+  const bool do_direct = accum != nullptr && J.i != 0;  // this shard owns the slot's direct (unreflected) path: splat it too
+  const int tid = threadIdx.x;
+  stage_program<T>(s_prog, progs + (size_t)slot * LFB_MAX_STEPS, n_steps + 1, tid, kPrefixThreads);
+  __syncthreads();
+  const int a = blockIdx.x * 16 + (tid & 15), bp = blockIdx.y * 16 + (tid >> 4);
+  const bool in_grid = a < g.N && bp < half_rows;
+  const int b = g.N - 1 - bp;
+  const size_t ray = (size_t)bp * g.N + a;
+  const size_t hr = (size_t)g.half_rays;
+  const MaskGeom K(g, tex);
+  const JobC<T> JC(J);
+  RayState<T> r;
+  {
+    T x, y;
+    grid_point<T>(g, a, b, x, y);
+    start_ray<T>(r, x, y, JC);
+  }
+  RayDiag o;
+  bool alive = in_grid;
+  unsigned n_exec = 0;
+  float4* base = prefix + (size_t)slot * g.n_surf * io::kParts * hr + ray;
+#pragma unroll 1
+  for (int s = 0; s < n_steps; s++) {
+    const StepT<T>& S = s_prog[s];
+    if (alive) { alive = propagate<T, false>(S, r, o); if (STATS) n_exec++; }
+    if (in_grid) {
+      float4* dst = base + (size_t)s * io::kParts * hr;
+      if (alive) io::store(dst, hr, r);
+      else io::store_dead(dst, hr);
+    }
+    if (alive) alive = interact<T, true, false>(S, K, g.lut, r, o);
+  }
+  bool landed = false;
+  if (do_direct) {  // the direct path: on to the sensor plane and splat, one warp at a time
+    if (alive) { alive = propagate<T, false>(s_prog[n_steps], r, o); if (STATS) n_exec++; }
+    const WarpSplat WS(g, J, s_tile + (tid >> 5) * (kWarpTilePx * 3), accum);
+    landed = warp_land<T>(WS, JC, alive, r.ox, r.oy, r.w * r.ma, r.w * r.mb, b != bp, tid & 31);
+  }
+  if (STATS) flush_stats(g.stats, n_exec, in_grid ? 1u : 0u, landed ? 1u : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GHOST KERNEL: one job per ghost pair (i, j).  BT threads = 16 x BT/16 ray pairs of the upper half grid.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, bool STATS>
+__device__ __forceinline__ void ghost_body(const Job& J, const StepT<T>* __restrict__ s_prog, const FrameGeom& g, const float* __restrict__ tex,
+                                           unsigned long long* tile, unsigned long long* __restrict__ accum, int a, int bp, int lane,
+                                           unsigned& n_exec, bool& started, bool& landed) {
+  typedef PrefixIO<T> io;
+  const int half_rows = (g.N + 1) / 2;
+  const int n_steps = J.n_steps;
+  const MaskGeom K(g, tex);
+  const JobC<T> JC(J);
+  const int b = g.N - 1 - bp;
+  RayState<T> r;
+  RayDiag o;
+  bool alive = false;
+  if (a < g.N && bp < half_rows) {
+    started = true;
+    int s = 0;
+    if (J.slot >= 0) {  // (uniform) the state ON the first-reflection surface comes from the prefix cache
+      const size_t hr = (size_t)g.half_rays;
+      const float4* src = g.prefix + ((size_t)(J.slot * g.n_surf + J.j_first) * io::kParts) * hr + ((size_t)bp * g.N + a);
+      alive = io::load(src, hr, r);
+      if (alive) alive = interact<T, true, false>(s_prog[0], K, g.lut, r, o);
+      s = 1;
+    } else {  // no cache (the direct path, or the cache is over its memory budget): from the entrance grid
+      T x, y;
+      grid_point<T>(g, a, b, x, y);
+      start_ray<T>(r, x, y, JC);
+      alive = true;
+      const int jc = J.i < 0 ? -1 : J.j_first;  // the step at which a cached state would have been loaded
+#pragma unroll 1
+      for (; alive && s <= jc; s++) {
+        const StepT<T>& S = s_prog[s];
+        alive = propagate<T, false>(S, r, o);
+        if (STATS) n_exec++;
+        if (alive && s == jc) io::canon(r);
+        if (alive) alive = interact<T, true, false>(S, K, g.lut, r, o);
+      }
+    }
+#pragma unroll 1
+    for (; alive && s < n_steps; s++) {
+      const StepT<T>& S = s_prog[s];
+      alive = propagate<T, false>(S, r, o);
+      if (STATS) n_exec++;
+      if (alive) alive = interact<T, true, false>(S, K, g.lut, r, o);
+    }
+  }
+  const WarpSplat WS(g, J, tile, accum);
+  landed = warp_land<T>(WS, JC, alive, r.ox, r.oy, r.w * r.ma, r.w * r.mb, b != bp, lane);
+}
+
+template <typename T, int MINB, int BT, bool STATS>
+__global__ void __launch_bounds__(BT, MINB) ghost_kernel(const Job* __restrict__ jobs, const StepT<T>* __restrict__ progs, FrameGeom g,
+                                                         const float* __restrict__ tex, unsigned long long* __restrict__ accum) {
+  constexpr int PH = BT / 16;
+  __shared__ __align__(16) StepT<T> s_prog[LFB_MAX_STEPS];
+  __shared__ unsigned long long s_tile[(BT / 32) * kWarpTilePx * 3];
+  // 3-D grid (patch column, patch row, job): no integer divisions in the prologue every warp pays
+  const Job& J = jobs[blockIdx.z];
+  const int tid = threadIdx.x;
+  stage_program<T>(s_prog, progs + (size_t)blockIdx.z * LFB_MAX_STEPS, J.n_steps, tid, BT);
+  __syncthreads();  // the only CTA-wide barrier
+  unsigned n_exec = 0;
+  bool started = false, landed = false;
+  ghost_body<T, STATS>(J, s_prog, g, tex, s_tile + (tid >> 5) * (kWarpTilePx * 3), accum, blockIdx.x * 16 + (tid & 15),
+                       blockIdx.y * PH + (tid >> 4), tid & 31, n_exec, started, landed);
+  if (STATS) flush_stats(g.stats, n_exec, started ? 1u : 0u, landed ? 1u : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GHOST FAMILIES.  After the forward sweep, the ghosts (i, j) of one (light, wavelength) with the same first reflection j
+// also share the BACKWARD sweep j-1, j-2, ... : ghost (i, j) leaves it at surface i.  One thread follows the whole
+// family: it starts ON surface j (prefix cache), reflects, and walks backward; at every candidate surface k it forks --
+// a copy of the ray reflects at k and runs the forward program k+1 .. n-1 to the sensor, where the warp splats it -- and
+// then continues backward through k.  28 ghost jobs per (light, wavelength) become 7 family jobs: the per-warp fixed
+// costs (launch prologue, state load, program staging) are paid once per family and the backward sweeps are not
+// repeated.  The arithmetic along every ghost path is unchanged, so the frame is bit-identical to the ghost kernel's.
+//
+// Family program (shared memory): [0] reflect at j; then for k = j-1 .. 0 two steps: (backward step at k: refraction or
+// the stop plane, fork step: reflection at k seen from behind, op < 0 when ghost (k, j) is not wanted).  The forward
+// program of the slot (refractions 0 .. n-1 + sensor) supplies the suffix k+1 .. n of every fork.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int MINB, int BT, bool STATS>
+__global__ void __launch_bounds__(BT, MINB) family_kernel(const Job* __restrict__ fams, const StepT<T>* __restrict__ fam_progs,
+                                                          const Job* __restrict__ slots, const StepT<T>* __restrict__ slot_progs, FrameGeom g,
+                                                          const float* __restrict__ tex, unsigned long long* __restrict__ accum) {
+  typedef PrefixIO<T> io;
+  constexpr int PH = BT / 16;
+  __shared__ __align__(16) StepT<T> s_fam[2 * LFB_MAX_SURFACES + 2];
+  __shared__ __align__(16) StepT<T> s_fwd[LFB_MAX_SURFACES + 2];
+  __shared__ unsigned long long s_tile[(BT / 32) * kWarpTilePx * 3];
+
+  const int half_rows = (g.N + 1) / 2;
+  const Job& J = fams[blockIdx.z];
+  const int slot = J.slot, j = J.j_first, n_fam = J.n_steps;
+  const int n_fwd = g.n_surf + 1;  // forward refractions 0 .. n-1 and the sensor
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int a = blockIdx.x * 16 + (tid & 15), bp = blockIdx.y * PH + (tid >> 4);
+  const int b = g.N - 1 - bp;
+  const bool in_grid = a < g.N && bp < half_rows;
+  stage_program<T>(s_fam, fam_progs + (size_t)blockIdx.z * LFB_MAX_STEPS, n_fam, tid, BT);
+  stage_program<T>(s_fwd, slot_progs + (size_t)slot * LFB_MAX_STEPS, n_fwd, tid, BT);
+  __syncthreads();  // the only CTA-wide barrier
+
+  const MaskGeom K(g, tex);
+  const JobC<T> JC(J);
+  const WarpSplat WS(g, J, s_tile + (tid >> 5) * (kWarpTilePx * 3), accum);
+  RayState<T> r;
+  RayDiag o;
+  bool alive = false;
+  unsigned n_exec = 0, n_landed = 0;
+  if (in_grid) {
+    const size_t hr = (size_t)g.half_rays;
+    const float4* src = g.prefix + ((size_t)(slot * g.n_surf + j) * io::kParts) * hr + ((size_t)bp * g.N + a);
+    alive = io::load(src, hr, r);
+    if (alive) alive = interact<T, true, false>(s_fam[0], K, g.lut, r, o);  // the first reflection, at j
+  }
+  const int n_back = (n_fam - 1) >> 1;  // backward surfaces in this job's program: j-1 .. down to its lowest fork
+#pragma unroll 1
+  for (int e = 0; e < n_back && __any_sync(0xffffffffu, alive); e++) {
+    const int k = j - 1 - e;
+    const StepT<T>& Sb = s_fam[1 + 2 * e];
+    const StepT<T>& Sf = s_fam[2 + 2 * e];
+    if (alive) { alive = propagate<T, false>(Sb, r, o); if (STATS) n_exec++; }  // onto surface k, travelling backward
+    if (Sf.op >= 0) {  // ghost (k, j): fork a copy that reflects here and runs forward to the sensor
+      RayState<T> q = r;
+      bool a2 = alive;
+      if (a2) a2 = interact<T, true, false>(Sf, K, g.lut, q, o);
+#pragma unroll 1
+      for (int s = k + 1; s < n_fwd; s++) {
+        if (a2) { a2 = propagate<T, false>(s_fwd[s], q, o); if (STATS) n_exec++; }
+        if (a2) a2 = interact<T, true, false>(s_fwd[s], K, g.lut, q, o);
+      }
+      if (warp_land<T>(WS, JC, a2, q.ox, q.oy, q.w * q.ma, q.w * q.mb, b != bp, lane)) n_landed++;
+    }
+    if (alive) alive = interact<T, true, false>(Sb, K, g.lut, r, o);  // on through surface k (or the stop's mask)
+  }
+  if (STATS) flush_stats(g.stats, n_exec, in_grid ? 1u : 0u, n_landed);
+}
+
+// Parity instrument for the same trace code: one record per ray (flags, positions, weight).
+template <typename T>
+__global__ void __launch_bounds__(256) dump_kernel(const Job* __restrict__ job, const StepT<T>* __restrict__ prog, FrameGeom g,
+                                                   const float* __restrict__ tex, lfb_ray_hit* __restrict__ out) {
+  __shared__ __align__(16) StepT<T> s_prog[LFB_MAX_STEPS];
+  const Job& J = *job;
+  const int n_steps = J.n_steps;
+  stage_program<T>(s_prog, prog, n_steps, threadIdx.x, 256);
+  __syncthreads();
+  const int tile = blockIdx.x;
+  const int a = (tile % g.tiles_x) * 16 + (threadIdx.x & 15);
+  const int b = (tile / g.tiles_x) * 16 + (threadIdx.x >> 4);
+  if (a >= g.N || b >= g.N) return;
+  const MaskGeom K(g, tex);
+  const JobC<T> JC(J);
+  RayState<T> r;
+  {
+    T x, y;
+    grid_point<T>(g, a, b, x, y);
+    start_ray<T>(r, x, y, JC);
+  }
+  RayDiag o;
+  o.flags = 0; o.xa = o.ya = CUDART_NAN;
+  bool alive = true;
+  for (int s = 0; alive && s < n_steps; s++) {
+    alive = propagate<T, true>(s_prog[s], r, o);
+    if (alive) alive = interact<T, false, true>(s_prog[s], K, g.lut, r, o);
+  }
+  lfb_ray_hit rec;
+  rec.x_ap = o.xa; rec.y_ap = o.ya; rec.flags = o.flags; rec.pad = 0;
+  if (alive) {
+    const T X = -JC.ppu * r.ox, Y = JC.ppu * r.oy;
+    const T px = JC.sx + M<T>::fma(X, JC.cs, -M<T>::mul_rn(Y, JC.sn));
+    const T py = JC.sy + M<T>::fma(X, JC.sn, M<T>::mul_rn(Y, JC.cs));
+    rec.x_s = (double)r.ox; rec.y_s = (double)r.oy; rec.weight = (double)(r.w * r.ma); rec.px = (double)px; rec.py = (double)py;
+    const T fx = M<T>::floor(px), fy = M<T>::floor(py);
+    if (!(fx >= (T)0 && fx < (T)g.W && fy >= (T)0 && fy < (T)g.H)) rec.flags |= LFB_RAY_OFF_SENSOR;
+  } else {
+    rec.x_s = rec.y_s = rec.px = rec.py = CUDART_NAN;
+    rec.weight = 0.0;
+  }
+  out[(size_t)b * g.N + a] = rec;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host launchers (instantiated per geometry type by exact_f32.cu / exact_f64.cu)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct Tune;  // CTAs per SM the register allocation targets: default / alternative
+template <> struct Tune<float> { static constexpr int kGhostA = 12, kGhostB = 10, kFamily = 10; };
+template <> struct Tune<double> { static constexpr int kGhostA = 6, kGhostB = 5, kFamily = 5; };
+
+template <typename T>
+cudaError_t launch_prefix_t(const Job* slots, const StepT<T>* progs, int n_slots, const FrameGeom& g, const float* tex, float4* prefix,
+                            unsigned long long* accum_for_direct, bool stats, cudaStream_t s) {
+  if (n_slots <= 0) return cudaSuccess;
+  const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + 15) / 16, n_slots);  // (patch column, patch row, slot)
+  if (nb.y > 65535u || nb.z > 65535u) return cudaErrorInvalidConfiguration;
+  if (stats) prefix_kernel<T, true><<<nb, kPrefixThreads, 0, s>>>(slots, progs, g, tex, prefix, accum_for_direct);
+  else prefix_kernel<T, false><<<nb, kPrefixThreads, 0, s>>>(slots, progs, g, tex, prefix, accum_for_direct);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_ghosts_t(const Job* jobs, const StepT<T>* progs, int n_jobs, const FrameGeom& g, const float* tex, unsigned long long* accum,
+                            int ctas_per_sm, bool stats, cudaStream_t s) {
+  if (n_jobs <= 0) return cudaSuccess;
+  constexpr int BT = 128;
+  const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + BT / 16 - 1) / (BT / 16), n_jobs);  // (patch column, patch row, job)
+  if (nb.y > 65535u || nb.z > 65535u) return cudaErrorInvalidConfiguration;
+  if (stats) ghost_kernel<T, Tune<T>::kGhostB, BT, true><<<nb, BT, 0, s>>>(jobs, progs, g, tex, accum);
+  else if (ctas_per_sm == Tune<T>::kGhostB) ghost_kernel<T, Tune<T>::kGhostB, BT, false><<<nb, BT, 0, s>>>(jobs, progs, g, tex, accum);
+  else ghost_kernel<T, Tune<T>::kGhostA, BT, false><<<nb, BT, 0, s>>>(jobs, progs, g, tex, accum);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_families_t(const Job* fams, const StepT<T>* fam_progs, int n_fams, const Job* slots, const StepT<T>* slot_progs,
+                              const FrameGeom& g, const float* tex, unsigned long long* accum, bool stats, cudaStream_t s) {
+  if (n_fams <= 0) return cudaSuccess;
+  constexpr int BT = 128;
+  const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + BT / 16 - 1) / (BT / 16), n_fams);  // (patch column, patch row, family)
+  if (nb.y > 65535u || nb.z > 65535u) return cudaErrorInvalidConfiguration;
+  if (stats) family_kernel<T, Tune<T>::kFamily, BT, true><<<nb, BT, 0, s>>>(fams, fam_progs, slots, slot_progs, g, tex, accum);
+  else family_kernel<T, Tune<T>::kFamily, BT, false><<<nb, BT, 0, s>>>(fams, fam_progs, slots, slot_progs, g, tex, accum);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_dump_t(const Job* job, const StepT<T>* prog, const FrameGeom& g, const float* tex, lfb_ray_hit* out, cudaStream_t s) {
+  dump_kernel<T><<<(unsigned)g.tiles_per_job, 256, 0, s>>>(job, prog, g, tex, out);
+  return cudaGetLastError();
+}
+
+}  // namespace xt
+}  // namespace lfb

@@ -5,7 +5,6 @@
 #define LFB_TU f64
 #include "ghost_grid_impl.cuh"
 #include "ref_abcd.cuh"
-#include <stdlib.h>
 
 namespace lfb {
 
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(PeerAccums P, cons
 }
 
 cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long* mc, size_t p0, size_t p1, double inv_scale,
-                                   void* out, size_t stride, int elem, cudaStream_t s) {
+                                   void* out, size_t stride, int elem, int ctas, cudaStream_t s) {
   if (p1 <= p0) return cudaSuccess;
   size_t e0 = 3 * p0, e1 = 3 * p1;
   if (e0 & 1) {  // keep the 16-byte loads aligned: the first (odd) value goes through the scalar tail of a 1-thread launch
@@ -256,13 +255,8 @@ cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // few, fat CTAs: the kernel is bound by NVLink latency, not by SM resources, and must leave the SMs to the trace
-  // kernel it overlaps with (LFB_REDUCE_CTAS overrides the CTA count for tuning)
-  static int ctas = 0;
-  if (!ctas) {
-    const char* env = getenv("LFB_REDUCE_CTAS");
-    ctas = env ? atoi(env) : sms;
-    if (ctas < 1) ctas = sms;
-  }
+  // kernel it overlaps with (lfb_options.reduce_ctas overrides the CTA count for tuning)
+  if (ctas < 1) ctas = sms;
   if (e1 > e0) reduce_finalize_kernel<8><<<ctas, 256, 0, s>>>(P, mc, e0, e1, inv_scale, (char*)out, stride, elem);
   return cudaGetLastError();
 }

@@ -262,6 +262,7 @@ __device__ __forceinline__ void deposit(unsigned long long* __restrict__ accum, 
                                         R wgt, const R* chan) {
   if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) return;
   grow_bbox(g.bbox, ix, iy, ix, iy);
+  if (g.tile_bits) mark_tile(g.tile_bits, g.tiles_w, ix >> kTilePxLog2, iy >> kTilePxLog2);
   unsigned long long* p = accum + 3 * ((size_t)ix + (size_t)iy * g.W);
 #pragma unroll
   for (int c = 0; c < 3; c++) {

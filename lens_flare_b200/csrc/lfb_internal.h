@@ -51,25 +51,64 @@ struct FrameGeom {
   double fp_scale;  // 2^fixed_point_bits
   float P, h_stop;  // entrance half height, stop half height
   float cell;       // 2P / N
+  double P_d, cell_d;  // the same in double (LFB_STRICT)
   float mask_su, mask_sv, mask_ou, mask_ov;  // aperture texel of a stop-plane point: u = x*su + ou, v = y*sv + ov
-  const float4* prefix;  // cached forward sweeps: [slot][surface][part 0|1][ray of the half grid], see exact_f32.cuh
+  const float4* prefix;  // cached forward sweeps: [slot][surface][part][ray of the half grid], see exact_trace.cuh
   int half_rays, n_surf;
-  const float2* lut;  // reflectance tables R(sin^2 theta0), one per (wavelength, surface, direction): (R_i, R_{i+1} - R_i)
+  const float2* lut;  // reflectance tables over the cosine in the rarer medium, one per (wavelength, surface, direction):
+                      // (R_i, R_{i+1} - R_i); the trace only reads them below kPolyV0 (steeper than ~53 degrees)
   int* bbox;        // device int[4] = {min_x, min_y, max_x, max_y} of every pixel the frame deposits into (or nullptr)
-  int patch, pad;   // FP32 EXACT_GRID tuning: rays per thread in pass 1 (1, 2 or 4); resident CTAs/SM target (0 -> 4)
+  unsigned* tile_bits;  // dirty-tile bitmap of the accumulators: bit t = 16x16 sensor tile t received a deposit (or nullptr)
+  int tiles_w, pad;     // tiles per sensor row
+  unsigned long long* stats;  // STATS instantiations only: [0] executed surface steps, [1] ray pairs started, [2] ray pairs landed
 };
 
-// FP32 EXACT_GRID step program (exact_f32.cuh): a ghost flattened into straight-line steps with every
-// ray-independent quantity precomputed on the host.  48 bytes = 3 x float4.
+constexpr int kTilePxLog2 = 4;  // the dirty-tile bitmap's tiles are 16 x 16 pixels
+constexpr int kTilePx1 = 1 << kTilePxLog2;
+inline int tiles_across(int px) { return (px + kTilePx1 - 1) >> kTilePxLog2; }
+
+// A sensor accumulator buffer (lfb_accum_bytes): W*H*3 u64 fixed-point sums, then the dirty-tile bitmap of those sums.
+struct AccumLayout {
+  int tiles_w, tiles_h, n_tiles, n_words;
+  size_t px_bytes, bits_off, total;
+};
+inline AccumLayout accum_layout(int W, int H) {
+  AccumLayout a;
+  a.tiles_w = tiles_across(W); a.tiles_h = tiles_across(H);
+  a.n_tiles = a.tiles_w * a.tiles_h;
+  a.n_words = (a.n_tiles + 31) / 32;
+  a.px_bytes = sizeof(unsigned long long) * 3 * (size_t)W * (size_t)H;
+  a.bits_off = (a.px_bytes + 255) & ~(size_t)255;
+  a.total = a.bits_off + (((size_t)a.n_words * 4 + 255) & ~(size_t)255);
+  return a;
+}
+// The state that goes with an OUTPUT buffer of the tile-sparse finalize (lfb_tile_state_bytes): which tiles the previous
+// frame left non-zero in it.  [0] ticket, [1] tiles written by the last frame, [2..3] pad, then n_words bitmap words.
+inline size_t tile_state_bytes(int W, int H) { return 16 + (((size_t)accum_layout(W, H).n_words * 4 + 255) & ~(size_t)255); }
+
+// EXACT_GRID step program (exact_trace.cuh): a ghost flattened into straight-line steps with every ray-independent
+// quantity precomputed on the host.  T = float (the FP32 throughput kernels, 64 B per step) or double (LFB_STRICT: FP64
+// geometry, 80 B).  The weight factor of a step -- R at a reflection, 1 - R at a refraction -- is a degree-7 polynomial in
+// x = (1 - v) * kPolyScale, v = the cosine of the ray's angle in the rarer medium, fitted on the host in double on
+// v in [kPolyV0, 1] (|error| <= 3e-8: tighter than any table, and no memory access in the surface loop); steeper rays fall
+// back to the interface's reflectance table.
 enum StepOp { STEP_REFRACT = 0, STEP_REFLECT = 1, STEP_PASS = 2, STEP_STOP = 3, STEP_SENSOR = 4 };
 #define LFB_MAX_STEPS (3 * LFB_MAX_SURFACES + 2)
 constexpr int kLutSize = 1024;  // intervals of the table variable (cosine in the rarer medium) on [0, 1]
-struct Step {
-  float c, dz, semi2, eta;   // curvature (0: plane); z of the previous vertex minus z of this one; clear radius^2; n0/n2
-  float eta2, phase;         // (n0/n2)^2; coating phase factor pi * lambda0 / lambda
-  int op, lut;               // StepOp; index of the interface's reflectance table (kLutSize float2 entries each)
-  float n0, n2, n1, e1sq;    // indices before/after along the ray; film index (0 = bare); (n0/n1)^2
+constexpr float kPolyV0 = 0.6f;
+constexpr float kPolyScale = 2.5f;  // 1 / (1 - kPolyV0)
+constexpr int kPolyN = 8;
+template <typename T>
+struct StepT {
+  T c, dz, eta, eta2;  // curvature (0: plane); z of the previous vertex minus z of this one; n0/n2; (n0/n2)^2
+  float semi2;         // clear radius^2
+  int op, lut;         // StepOp (-1: a fork the family does not take); index of the interface's reflectance table
+  float pad;
+  float p[kPolyN];     // weight-factor polynomial, lowest order first
 };
+typedef StepT<float> StepF;
+typedef StepT<double> StepD;
+static_assert(sizeof(StepF) == 64 && sizeof(StepD) == 80, "step programs are staged as 16-byte words");
 
 // REF_QUADS: one rasterisable triangle of a ghost quad (pathtracer.cpp:346-410 state
 // after the y-sort and the -0.5 shift), in draw order.
@@ -97,20 +136,33 @@ cudaError_t upload_lens_ref(const DevLens& h, cudaStream_t s);
 
 // kernels' host launchers (definitions in the .cu files)
 cudaError_t launch_paraxial_setup(Job* jobs, int n_jobs, int physical_backward, cudaStream_t s);
-cudaError_t launch_trace_splat_f32(const Job* jobs, const Step* progs, int n_jobs, const FrameGeom& g, int mode,
-                                   const float* tex, unsigned long long* accum, cudaStream_t s);
+// PARAXIAL_GRID in FP32 / FP64 and the FP64 oracle-order EXACT_GRID parity kernels (ghost_grid_impl.cuh)
+cudaError_t launch_trace_splat_f32(const Job* jobs, int n_jobs, const FrameGeom& g, int mode, const float* tex,
+                                   unsigned long long* accum, cudaStream_t s);
 cudaError_t launch_trace_splat_f64(const Job* jobs, int n_jobs, const FrameGeom& g, int mode, const float* tex,
                                    unsigned long long* accum, cudaStream_t s);
-// FP32 EXACT_GRID prefix pass: trace the forward sweep of every (light, lambda) slot once and cache the ray states
-cudaError_t launch_prefix_f32(const Job* slots, const Step* progs, int n_slots, const FrameGeom& g, const float* tex, float4* prefix,
-                              unsigned long long* accum_for_direct, cudaStream_t s);
-// FP32 EXACT_GRID ghost families (v7): one job per (light, lambda, first reflection j)
-cudaError_t launch_family_f32(const Job* fams, const Step* fam_progs, int n_fams, const Job* slots, const Step* slot_progs,
-                              const FrameGeom& g, const float* tex, unsigned long long* accum, cudaStream_t s);
-cudaError_t launch_trace_dump_f32(const Job* job, const Step* prog, const FrameGeom& g, int mode, const float* tex,
-                                  lfb_ray_hit* out, cudaStream_t s);
+cudaError_t launch_trace_dump_f32(const Job* job, const FrameGeom& g, int mode, const float* tex, lfb_ray_hit* out, cudaStream_t s);
 cudaError_t launch_trace_dump_f64(const Job* job, const FrameGeom& g, int mode, const float* tex, lfb_ray_hit* out,
                                   cudaStream_t s);
+// The EXACT_GRID throughput kernels (exact_trace.cuh), instantiated for T = float (exact_f32.cu, LFB_FP32) and T = double
+// (exact_f64.cu, LFB_STRICT: FP64 geometry, FP32 weights).  stats: the counting instantiation (FrameGeom::stats).
+//   prefix    the forward sweep of every (light, lambda) slot, traced once; each ray's state on every surface is cached
+//             (and the direct path splatted when accum_for_direct is given and the slot owns it)
+//   ghosts    one job per ghost pair (i, j), starting ON surface j from the cache (or from the entrance without one)
+//   families  one job per (light, lambda, first reflection j): forks at every second reflection
+//   dump      per-ray records of one ghost (parity instrument)
+template <typename T> int exact_prefix_parts();  // 16-byte words per cached ray state
+template <typename T>
+cudaError_t launch_exact_prefix(const Job* slots, const StepT<T>* progs, int n_slots, const FrameGeom& g, const float* tex, float4* prefix,
+                                unsigned long long* accum_for_direct, bool stats, cudaStream_t s);
+template <typename T>
+cudaError_t launch_exact_ghosts(const Job* jobs, const StepT<T>* progs, int n_jobs, const FrameGeom& g, const float* tex,
+                                unsigned long long* accum, int ctas_per_sm, bool stats, cudaStream_t s);
+template <typename T>
+cudaError_t launch_exact_families(const Job* fams, const StepT<T>* fam_progs, int n_fams, const Job* slots, const StepT<T>* slot_progs,
+                                  const FrameGeom& g, const float* tex, unsigned long long* accum, bool stats, cudaStream_t s);
+template <typename T>
+cudaError_t launch_exact_dump(const Job* job, const StepT<T>* prog, const FrameGeom& g, const float* tex, lfb_ray_hit* out, cudaStream_t s);
 cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,
                             size_t stride, int elem, int additive, cudaStream_t s);
 cudaError_t launch_finalize_clear(unsigned long long* accum, int W, int H, double inv_scale, void* out, size_t stride, int elem,
@@ -125,7 +177,7 @@ struct PeerFlags {  // every rank's barrier flag array (LFB_MAX_PEERS u64 each) 
 };
 cudaError_t launch_peer_barrier(const PeerFlags& F, int rank, unsigned long long epoch, cudaStream_t s);
 cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long* mc, size_t p0, size_t p1, double inv_scale,
-                                   void* out, size_t stride, int elem, cudaStream_t s);
+                                   void* out, size_t stride, int elem, int ctas, cudaStream_t s);
 // rect = {x0, y0, x1, y1} inclusive; out is PACKED: pixel (x, y) at ((y - y0) * (x1 - x0 + 1) + (x - x0)) * stride
 cudaError_t launch_finalize_rect(const unsigned long long* accum, int W, const int rect[4], double inv_scale, void* out,
                                  size_t stride, int elem, cudaStream_t s);
@@ -139,6 +191,14 @@ __device__ __forceinline__ void grow_bbox(int* bb, int x0, int y0, int x1, int y
   if (y0 < v[1]) atomicMin(bb + 1, y0);
   if (x1 > v[2]) atomicMax(bb + 2, x1);
   if (y1 > v[3]) atomicMax(bb + 3, y1);
+}
+// Mark the 16 x 16 sensor tile (tx, ty) dirty.  Read first: after the first few warps of a frame almost every bit a warp
+// wants is already set, so the atomics are rare.
+__device__ __forceinline__ void mark_tile(unsigned* bits, int tiles_w, int tx, int ty) {
+  const unsigned t = (unsigned)ty * (unsigned)tiles_w + (unsigned)tx;
+  const unsigned bit = 1u << (t & 31u);
+  unsigned* w = bits + (t >> 5);
+  if (!(*reinterpret_cast<volatile unsigned*>(w) & bit)) atomicOr(w, bit);
 }
 cudaError_t launch_ref_setup(const RefFrame& f, const int* pairs, const float* rgb_weight, RefTri* tris,
                              lfb_ref_ghost* ghosts, int* bbox, cudaStream_t s);

@@ -19,8 +19,16 @@ def shard_params(params, rank, world_size):
 
 
 def accum_tensor(params, device):
-    """The (H, W, 3) int64 fixed-point sensor accumulators the engine splats into."""
-    return torch.zeros((params.height, params.width, 3), dtype=torch.int64, device=device)
+    """A sensor accumulator buffer the engine splats into (lfb_accum_bytes: the H*W*3 int64 fixed-point sums followed by
+    the dirty-tile bitmap), as a flat int64 tensor; accum_pixels() views the sums."""
+    words = (capi.lib().lfb_accum_bytes(params.width, params.height) + 7) // 8
+    return torch.zeros((words,), dtype=torch.int64, device=device)
+
+
+def accum_pixels(accum, params):
+    """The (H, W, 3) int64 sums of an accumulator buffer."""
+    n = params.height * params.width * 3
+    return accum[:n].view(params.height, params.width, 3)
 
 
 def reduce_accum(accum, dst=None, group=None):
@@ -109,10 +117,11 @@ class ShardedFlare:
             self.C.wait_event(last)
             prev = torch.cuda.current_stream(self.device)
             torch.cuda.set_stream(self.C)  # cheaper than the context manager: this runs once per frame
+            px = accum_pixels(acc, self.full_params)  # the sums only: the dirty-tile bitmaps behind them are per rank
             if reduce_dst is None:
-                dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+                dist.all_reduce(px, op=dist.ReduceOp.SUM)
             else:
-                dist.reduce(acc, dst=reduce_dst, op=dist.ReduceOp.SUM)
+                dist.reduce(px, dst=reduce_dst, op=dist.ReduceOp.SUM)
             self.reduced[b].record(self.C)
             torch.cuda.set_stream(prev)
             last = self.reduced[b]
@@ -137,7 +146,7 @@ class ShardedFlare:
         self.begin()
         b = self.frame(lights, out=None, reduce_dst=reduce_dst, keep=True)
         self.join()
-        return self.accums[b]
+        return accum_pixels(self.accums[b], self.full_params)
 
     def finalize(self, out, elem=capi.F32x3):
         cur = torch.cuda.current_stream(self.device)
@@ -173,7 +182,8 @@ class PeerFlare:
         self.params = shard_params(params, rank, world_size)
         self.n_buffers = max(int(n_buffers), 3 if finalize_engine is not None else 2)
         H, W = params.height, params.width
-        self.accum_all = symm_mem.empty((self.n_buffers, H, W, 3), dtype=torch.int64, device=device)
+        acc_words = (capi.lib().lfb_accum_bytes(W, H) + 7) // 8
+        self.accum_all = symm_mem.empty((self.n_buffers, acc_words), dtype=torch.int64, device=device)
         self.out_all = symm_mem.empty((self.n_buffers, H, W, 3), dtype=out_dtype, device=device)
         self.h_acc = symm_mem.rendezvous(self.accum_all, group.group_name)
         self.h_out = symm_mem.rendezvous(self.out_all, group.group_name)
@@ -182,7 +192,7 @@ class PeerFlare:
         self.h_flags = symm_mem.rendezvous(self.flags, group.group_name)
         self.epoch = 0
         self.accum_all.zero_()
-        self.acc_bytes = H * W * 3 * 8
+        self.acc_bytes = acc_words * 8
         self.out_bytes = H * W * 3 * self.out_all.element_size()
         self.elem = capi.F32x3 if out_dtype == torch.float32 else capi.F64x3
         self.mc = int(self.h_acc.multicast_ptr) if (use_multicast and self.h_acc.has_multicast_support) else 0

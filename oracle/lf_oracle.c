@@ -418,10 +418,18 @@ typedef struct { double sx, sy, cs, sn, ppu; } pixmap;
 static pixmap make_pixmap(const lfb_light* lt, const lfb_params* P) {
   pixmap m;
   double dx = lt->ns_x - 0.5, dy = lt->ns_y - 0.5;
-  float ang = (dx == 0 && dy == 0) ? 0.f : (float)atan(dy / dx); /* shift_vertex :414 */
-  m.cs = cosf(ang); m.sn = sinf(ang);
-  m.sx = ceil(lt->ns_x * (double)P->width);  /* draw_ghost :462-463 */
-  m.sy = ceil(lt->ns_y * (double)P->height);
+  if (P->physical_mapping) {
+    /* ours (lfb_params.physical_mapping, no reference counterpart): origin at the image centre, meridional axis along the
+     * light's azimuth; the sign of to_pixel's X = -ppu xs is folded into the rotation */
+    double phi = (dx == 0 && dy == 0) ? 0.0 : atan2(dy * (double)P->height, dx * (double)P->width);
+    m.cs = -cos(phi); m.sn = -sin(phi);
+    m.sx = 0.5 * (double)P->width; m.sy = 0.5 * (double)P->height;
+  } else {
+    float ang = (dx == 0 && dy == 0) ? 0.f : (float)atan(dy / dx); /* shift_vertex :414 */
+    m.cs = cosf(ang); m.sn = sinf(ang);
+    m.sx = ceil(lt->ns_x * (double)P->width);  /* draw_ghost :462-463 */
+    m.sy = ceil(lt->ns_y * (double)P->height);
+  }
   m.ppu = P->px_per_unit > 0 ? P->px_per_unit : 0.4f;
   return m;
 }

@@ -33,6 +33,7 @@ def test_struct_layouts_match_header(native_lib):
     assert C.sizeof(capi.Lens) == 16 + 4 * 4 * 16 + 4 * 64 * 16 + 4 * 64 + 4 * 64 * 3 + 3 * 8
     assert C.sizeof(capi.Light) == 40
     assert C.sizeof(capi.Params) == 64
+    assert C.sizeof(capi.Options) == 80
     assert capi.RAY_HIT_DTYPE.itemsize == 64
     assert capi.REF_GHOST_DTYPE.itemsize == 72
 
@@ -258,6 +259,6 @@ def test_header_is_plain_c(native_lib, tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "tests", "c", "abi_from_c.c"), "-o", str(exe), "-L" + lib_dir, "-llfb200", "-Wl,-rpath," + lib_dir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
-    assert "abi 2 jobs 87 rays 5701632 interactions 95944704" in out
+    assert "abi 3 jobs 87 rays 5701632 interactions 95944704" in out
     assert "sizeof(lens)=5416 light=40 params=64 hit=64" in out
     assert "lfb_create -> 0" in out or "lfb_create -> -2" in out

@@ -71,13 +71,12 @@ def test_gpu_starburst_frame_vs_reference_golden(engine, port, apertures, case):
 
 
 @pytest.mark.gpu
-def test_gpu_starburst_lattice_equals_per_pixel_evaluation(apertures, monkeypatch):
+def test_gpu_starburst_lattice_equals_per_pixel_evaluation(apertures):
     """The P-periodic lattice evaluation (frames larger than the mask's period) equals one column / row per pixel."""
     lt = [capi.make_light(0.31, 0.64, radiance=(1.0, 0.5, 0.25))]
     frames = {}
     for mode in ("1", "0"):
-        monkeypatch.setenv("LFB_STARBURST_LATTICE", mode)
-        e = capi.Engine(0)
+        e = capi.Engine(0, starburst_lattice=0 if mode == "1" else -1)
         try:
             e.set_starburst_aperture(apertures["pent_11"])
             frames[mode] = [e.render_starburst(lt, W, H, 40.0, 1.5) for (W, H) in ((1280, 720), (700, 300), (333, 641))]
