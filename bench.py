@@ -5,22 +5,31 @@
   python bench.py --impl reference [--gpus N] [--steps K] ...     the reference's CPU code (oracle/_ref)
   N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-A STEP is one flare frame of BASELINE config 2 per light: RGB (3 wavelengths), a 256x256 ray grid per
-ghost, every two-reflection ghost of the built-in lens (28 glass-glass pairs) plus the direct path,
-1920x1080 sensor, final_apertures/pentbig500_14.png at the stop, EXACT_GRID physics (sphere/plane
-intersection, vector Snell with n(lambda), Fresnel + quarter-wave coating at 550 nm, aperture lookup,
-bilinear fixed-point splat), FP32.  With N GPUs the frame has N suns (weak scaling: one light's worth of
-ghosts per GPU), the (light x pair x wavelength) jobs are dealt to ranks and the int64 sensor buffers are
-summed with ONE NCCL reduce to rank 0, which converts them to pixels.
+A STEP is one flare frame of BASELINE config 2 per light: RGB (3 wavelengths), a 256x256 ray grid per ghost, every
+two-reflection ghost of the built-in lens (28 glass-glass pairs) plus the direct path, 1920x1080 sensor,
+final_apertures/pentbig500_14.png at the stop, EXACT_GRID physics (sphere/plane intersection, vector Snell with n(lambda),
+Fresnel + quarter-wave coating at 550 nm, aperture lookup, bilinear fixed-point splat), FP32.  With N GPUs the frame has N
+suns (weak scaling: one light's worth of ghosts per GPU); the (light x pair x wavelength) jobs are dealt to the ranks, every
+rank splats into its own u64 accumulators, and the frame is summed TILE-SPARSE over NVLink peer memory: each rank reduces +
+converts its interleaved share of the dirty 16x16 tiles and stores the pixels into rank 0's frame (no collective call; --reduce
+nccl / peer select the dense round-1 paths for comparison).
 
-  value  ray-surface interactions / s, whole job, frame description resident in HBM, device-timed
-         (CUDA events on the launching stream, per step, L2 flushed between steps, max over ranks)
-  e2e    the same metric through the reference-facing call (lfb_render_ghosts: host buffers; the
-         aperture mask + job table go host->device and the Vector3D[] frame comes back every step)
+  value     ray-surface interactions / s (NOMINAL: rays x I(i,j), the unit BASELINE.json defines), whole job, frame
+            description resident in HBM, device-timed: B brackets of EXACTLY K back-to-back frames each (CUDA events on the
+            launching stream, barrier + synchronize on both sides, max over ranks per bracket); the MEDIAN bracket is reported,
+            all of them are listed
+  e2e       the same metric through the reference-facing C-ABI call with HOST buffers every step: the aperture mask goes
+            host -> device and the Vector3D[] frame comes back (lfb_render_ghosts_sparse: the device writes the frame's dirty
+            tiles straight into the caller's page-locked HDRImageBuffer storage and re-zeroes the previous frame's)
+  strict    the same pipeline with LFB_STRICT (FP64 geometry): what north_star's 1e-5-lens-unit per-ray bar costs
+  parity    this run's GPU frames / rays against the double-precision oracle (and, N > 1, the sharded frame against the
+            unsharded one)
 """
 import argparse
 import json
+import math
 import os
+import statistics
 import sys
 import threading
 import time
@@ -35,9 +44,29 @@ FLOP_PER_INTERACTION = 64.0
 MUFU_PER_INTERACTION = 3.0
 GRID_N, WIDTH, HEIGHT = 256, 1920, 1080
 COATING_NM = 550.0
+N_BRACKETS = 7
 WORKLOAD = ("cfg2: RGB (3 wavelengths) x 256x256 ray grid per ghost x (28 two-reflection ghost pairs + direct path) per light, "
             "1920x1080 sensor, pentbig500_14 aperture, EXACT_GRID (sphere/plane hit, Snell, Fresnel + 550 nm quarter-wave coating), "
             "bilinear fixed-point splat")
+
+
+def physical_theta(ns_x, ns_y, hfov_deg=50.0, vfov_deg=35.0):
+    """Off-axis angle of a distant light at normalised screen position (ns_x, ns_y): the inverse of
+    Camera::analyze_world_coord (camera.cpp:245-273); float32 like lfb_light.theta.  (Same formula as capi.physical_theta;
+    restated here so that the reference arm does not load the product library.)"""
+    tx = (2.0 * ns_x - 1.0) * math.tan(0.5 * math.radians(hfov_deg))
+    ty = (2.0 * ns_y - 1.0) * math.tan(0.5 * math.radians(vfov_deg))
+    return float(np.float32(math.atan(math.hypot(tx, ty))))
+
+
+def nominal_interactions(n_lights, include_direct=True, grid_n=GRID_N, n_lambda=3, n_surfaces=9, stop=5):
+    """I(i, j) = 2 (j - i) + n + 1 per ray over all glass-glass pairs (478 for the built-in lens), n + 1 for the
+    direct path; x rays per ghost x wavelengths x lights.  Pure Python (lfb_count_work computes the same)."""
+    glass = [k for k in range(n_surfaces) if k != stop]
+    per_ray = sum(2 * (j - i) + n_surfaces + 1 for a, i in enumerate(glass) for j in glass[a + 1:])
+    if include_direct:
+        per_ray += n_surfaces + 1
+    return float(per_ray) * grid_n * grid_n * n_lambda * n_lights
 
 
 def sun_positions(n):
@@ -45,7 +74,6 @@ def sun_positions(n):
     through the 50 x 35 degree camera) at azimuths 2 pi k / n around the optical axis, so that every light is the same
     amount of work (weak scaling measures the system, not the lights) and none sits at the exact screen centre (the
     reference NaNs there, pathtracer.cpp:414)."""
-    import math
     ex, ey = math.tan(math.radians(25.0)), math.tan(math.radians(17.5))
     tx0, ty0 = (2 * 0.45 - 1) * ex, (2 * 0.55 - 1) * ey
     rad, phi0 = math.hypot(tx0, ty0), math.atan2(ty0, tx0)
@@ -57,10 +85,10 @@ def sun_positions(n):
 
 
 def make_sun(x, y, **kw):
-    """A sun at normalised screen position (x, y) seen through a 50 x 35 degree camera: the physical off-axis angle
-    (capi.physical_theta), not the reference's screen-space atan(y/x) that kills every exactly-traced ray."""
+    """A sun at normalised screen position (x, y) seen through a 50 x 35 degree camera: the physical off-axis angle,
+    not the reference's screen-space atan(y/x) that kills every exactly-traced ray."""
     from lens_flare_b200 import capi
-    return capi.make_light(x, y, theta=capi.physical_theta(x, y), **kw)
+    return capi.make_light(x, y, theta=physical_theta(x, y), **kw)
 
 
 def load_aperture():
@@ -118,16 +146,6 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-# ------------------------------------------------------------------------------------------------
-# the reference arm: the reference's own CPU code for this path, all host threads
-# ------------------------------------------------------------------------------------------------
-def reference_trace_step(ref, theta, threads):
-    """One step of the reference arm: trace_ray_auto_before/after (pathtracer.cpp:588-689) called per ray
-    and per axis over cfg2's grid (256^2 x 28 pairs x RGB), std::threads over ghosts.  -> (s, rays)"""
-    s, rays, _ = ref.time_trace_grid(GRID_N, theta, 3, 28, threads)
-    return s, rays
-
-
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -138,68 +156,61 @@ def cpu_model():
     return "unknown"
 
 
-def cpu_baseline_block(sample_steps=1):
-    """The CPU numbers reported beside the GPU line (rank 0, N = 1)."""
-    from lens_flare_b200 import capi
-    from oracle import bindings as ob
-    threads = os.cpu_count() or 1
-    lens = capi.builtin_lens(3, COATING_NM)
-    p = capi.make_params(capi.MODE_EXACT_GRID, WIDTH, HEIGHT, grid_n=GRID_N, pair_set=capi.PAIRS_ALL, include_direct=1)
-    _, inter_frame, _ = capi.count_work(lens, p, 1)
-    inter_pairs = inter_frame - 10 * 3 * GRID_N * GRID_N  # the reference has no direct path
-    theta = make_sun(0.45, 0.55).theta
-    out = {}
-    if os.path.exists(ob.REF_SO):
-        ref = ob.RefOracle()
-        best = min(reference_trace_step(ref, theta, threads)[0] for _ in range(max(1, sample_steps) + 1))
-        out.update(value=inter_pairs / best, unit="interactions/s", cores=threads, kind="reference",
-                   sample=f"trace_ray_auto_before/after per ray and axis over cfg2's grid (256^2 x 28 pairs x RGB = "
-                          f"{inter_pairs:.3g} interactions), {threads} std::threads, best of {max(1, sample_steps) + 1}",
-                   seconds=best)
-        tex = load_aperture()
-        s1, _ = ref.time_ghost_buffer(tex, WIDTH, HEIGHT, 0.45, 0.55, capi.make_light(0.45, 0.55).theta, 5)
-        out["reference_frame_ms_1thread"] = s1 * 1e3  # PathTracer::generate_ghost_buffer, 1080p (13 quads x RGB)
-    out["cpu_model"] = cpu_model()
-    if os.path.exists(ob.PORT_SO) or not out.get("kind"):
-        if not os.path.exists(ob.PORT_SO):
-            ob.build(("port",))
-        port = ob.PortOracle()
-        tex = load_aperture()
-        s, _ = port.time_render(lens, tex, [make_sun(0.45, 0.55)], p, threads)
-        exact = dict(value=inter_frame / s, unit="interactions/s", cores=threads, kind="port",
-                     sample=f"oracle/lf_oracle.c EXACT_GRID, one full cfg2 frame ({inter_frame:.3g} interactions), {threads} pthreads",
-                     seconds=s, frame_ms=s * 1e3)
-        if out.get("kind"):
-            out["port_exact"] = exact
-        else:
-            out.update(exact)
-    return out
+def spread(xs):
+    xs = sorted(xs)
+    return {"median": statistics.median(xs), "min": xs[0], "max": xs[-1], "n": len(xs)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm: the reference's own CPU code for this path, all host threads.  It does NOT load the product
+# library: the work count and the light's angle are computed in Python above.
+# ------------------------------------------------------------------------------------------------
+def reference_trace_step(ref, theta, threads):
+    """One step of the reference arm: trace_ray_auto_before/after (pathtracer.cpp:588-689) called per ray
+    and per axis over cfg2's grid (256^2 x 28 pairs x RGB), std::threads over ghosts.  -> seconds"""
+    s, _, _ = ref.time_trace_grid(GRID_N, theta, 3, 28, threads)
+    return s
+
+
+def load_ref_oracle():
+    """oracle/_ref through ctypes only (oracle.bindings imports the product's struct declarations, which this arm avoids)."""
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_time_trace_grid.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ref_time_trace_grid.restype = C.c_double
+
+    class Ref:
+        def time_trace_grid(self, n, theta, ncol, pairset, nthreads):
+            rays, chk = C.c_double(), C.c_double()
+            s = L.ref_time_trace_grid(n, theta, ncol, pairset, nthreads, C.byref(rays), C.byref(chk))
+            return s, rays.value, chk.value
+    return Ref()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from lens_flare_b200 import capi
-    from oracle import bindings as ob
     threads = os.cpu_count() or 1
-    lens = capi.builtin_lens(3)
-    p = capi.make_params(capi.MODE_EXACT_GRID, WIDTH, HEIGHT, grid_n=GRID_N, pair_set=capi.PAIRS_ALL)
-    _, inter, _ = capi.count_work(lens, p, 1)
-    theta = make_sun(0.45, 0.55).theta
-    if os.path.exists(ob.REF_SO):
-        ref = ob.RefOracle()
+    inter = nominal_interactions(1, include_direct=False)  # the reference has no direct path
+    theta = physical_theta(0.45, 0.55)
+    ref = load_ref_oracle()
+    if ref is not None:
         kind = "reference"
-        step = lambda: reference_trace_step(ref, theta, threads)[0]  # noqa: E731
+        step = lambda: reference_trace_step(ref, theta, threads)  # noqa: E731
         sample = (f"one step = trace_ray_auto_before/after per ray and axis over 256^2 x 28 pairs x RGB "
                   f"({inter:.3g} interactions), {threads} std::threads")
-    else:
+    else:  # the compiled reference is missing: the oracle port's paraxial frame (the other place bench.py may execute oracle/)
+        from lens_flare_b200 import capi
+        from oracle import bindings as ob
         if not os.path.exists(ob.PORT_SO):
             ob.build(("port",))
-        port = ob.PortOracle()
-        tex = load_aperture()
+        port, tex, lens = ob.PortOracle(), load_aperture(), capi.builtin_lens(3)
         kind = "port"
-        pp = capi.copy_params(p, mode=capi.MODE_PARAXIAL_GRID, precision=capi.FP64)
+        pp = capi.make_params(capi.MODE_PARAXIAL_GRID, WIDTH, HEIGHT, grid_n=GRID_N, pair_set=capi.PAIRS_ALL, precision=capi.FP64)
         step = lambda: port.time_render(lens, tex, [make_sun(0.45, 0.55)], pp, threads)[0]  # noqa: E731
         sample = f"one step = oracle port PARAXIAL_GRID frame, 256^2 x 28 pairs x RGB, {threads} pthreads"
     for _ in range(args.warmup):
@@ -212,18 +223,121 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD + " [reference arm: the reference's paraxial ABCD tracer on the same grid; it has no "
-                                          "exact physics and no direct path]"},
+                                          "exact physics and no direct path -- the same-physics CPU number is cpu_baseline.port_exact "
+                                          "of our arm's line]"},
         "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": threads, "kind": kind, "sample": sample, "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "repo_libraries_loaded": sorted({l.split()[-1][len(ROOT) + 1:] for l in open("/proc/self/maps") if ROOT in l and ".so" in l}),
     }
     print(json.dumps(line))
     return 0
 
 
 # ------------------------------------------------------------------------------------------------
+# CPU legs reported beside our line (rank 0, N = 1)
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_block(port_seconds, inter_frame, sample_steps=1):
+    """kind 'reference' = the reference's trace_ray_auto_* per ray (oracle/_ref); port_exact = the oracle's EXACT_GRID frame
+    (same physics as our kernels; its seconds come from the parity leg, which renders that frame anyway)."""
+    from lens_flare_b200 import capi
+    from oracle import bindings as ob
+    threads = os.cpu_count() or 1
+    inter_pairs = nominal_interactions(1, include_direct=False)
+    theta = physical_theta(0.45, 0.55)
+    out = {}
+    if os.path.exists(ob.REF_SO):
+        ref = ob.RefOracle()
+        best = min(reference_trace_step(ref, theta, threads) for _ in range(max(1, sample_steps) + 1))
+        out.update(value=inter_pairs / best, unit="interactions/s", cores=threads, kind="reference",
+                   sample=f"trace_ray_auto_before/after per ray and axis over cfg2's grid (256^2 x 28 pairs x RGB = "
+                          f"{inter_pairs:.3g} interactions), {threads} std::threads, best of {max(1, sample_steps) + 1}",
+                   seconds=best)
+        s1, _ = ref.time_ghost_buffer(load_aperture(), WIDTH, HEIGHT, 0.45, 0.55, capi.make_light(0.45, 0.55).theta, 5)
+        out["reference_frame_ms_1thread"] = s1 * 1e3  # PathTracer::generate_ghost_buffer, 1080p (13 quads x RGB)
+    out["cpu_model"] = cpu_model()
+    exact = dict(value=inter_frame / port_seconds, unit="interactions/s", cores=threads, kind="port",
+                 sample=f"oracle/lf_oracle.c EXACT_GRID, one full cfg2 frame ({inter_frame:.3g} interactions), {threads} pthreads",
+                 seconds=port_seconds, frame_ms=port_seconds * 1e3)
+    if out.get("kind"):
+        out["port_exact"] = exact
+    else:
+        out.update(exact)
+    return out
+
+
+def parity_block(eng, lens, tex, light, params):
+    """This run's GPU frames and rays against the double-precision oracle, at cfg2's full size.
+    image: relative L2 of the FP32 and STRICT frames against oracle/lf_oracle.c's frame.
+    per ray: sensor hit positions (lens units) of every ray of all 28 ghosts + the direct path at the green wavelength
+    (29 x 65 536 rays) against lfo_trace_grid."""
+    from lens_flare_b200 import capi
+    from oracle import bindings as ob
+    if not os.path.exists(ob.PORT_SO):
+        ob.build(("port",))
+    port = ob.PortOracle()
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    port_seconds, _ = port.time_render(lens, tex, [light], params, threads)  # the timed multi-threaded frame (cpu_baseline.port_exact)
+    want = port.render(lens, tex, [light], params)                           # the frame itself (single thread)
+    oracle_s = time.perf_counter() - t0
+    out = {"oracle": "oracle/lf_oracle.c EXACT_GRID (double); parity of this physics is UNPINNED by the reference, which has none (SURVEY 8a a13)",
+           "oracle_seconds": oracle_s}
+    norm = float(np.sqrt((want ** 2).sum()))
+    for name, prec in (("fp32", capi.FP32), ("strict", capi.STRICT)):
+        got = eng.render_ghosts([light], capi.copy_params(params, precision=prec))
+        out[name] = {"image_rel_l2": float(np.sqrt(((got - want) ** 2).sum()) / norm), "nonzero_pixels": int((got.sum(axis=2) > 0).sum())}
+    pairs = [(i, j) for i in range(9) for j in range(i + 1, 9) if i != 5 and j != 5] + [(-1, -1)]
+    geo = ob.RAY_MISSED | ob.RAY_VIGNETTED | ob.RAY_TIR
+    stats = {"fp32": [], "strict": []}
+    mism = {"fp32": 0, "strict": 0}
+    n_rays = 0
+    for (i, j) in pairs:
+        w = port.trace_grid(lens, tex, light, params, i, j, 1)
+        n_rays += w.size
+        for name, prec in (("fp32", capi.FP32), ("strict", capi.STRICT)):
+            g = eng.dump_rays(light, capi.copy_params(params, precision=prec), i, j, 1)
+            same = (g["flags"] & geo) == (w["flags"] & geo)
+            mism[name] += int((~same).sum())
+            ok = same & ~np.isnan(w["x_s"]) & ~np.isnan(g["x_s"])
+            stats[name].append(np.hypot(g["x_s"][ok] - w["x_s"][ok], g["y_s"][ok] - w["y_s"][ok]))
+    for name in stats:
+        d = np.concatenate(stats[name])
+        out[name]["per_ray_lens_units"] = {"p50": float(np.median(d)), "p99": float(np.quantile(d, 0.99)), "max": float(d.max()), "rays_compared": int(d.size)}
+        out[name]["flags_mismatch"] = mism[name] / n_rays
+    out["rays"] = n_rays
+    out["tolerances"] = "north_star: per-ray 1e-5 lens units, image 1e-3 relative L2"
+    return out, port_seconds
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+class SparsePipeline:
+    """N = 1: R rotating (accumulators, output frame, tile state) sets on ONE stream: trace (clear_first = 0: the tile-sparse
+    finalize leaves the accumulators clear) -> lfb_finalize_tiles_device.  The engine's own second stream runs the forward
+    sweeps of frame k+1 under the ghost kernel of frame k."""
+
+    def __init__(self, eng, params, dev, n_buffers, torch, capi):
+        self.eng, self.params, self.capi = eng, params, capi
+        W, H = params.width, params.height
+        acc_words = (capi.lib().lfb_accum_bytes(W, H) + 7) // 8
+        st_words = (capi.lib().lfb_tile_state_bytes(W, H) + 3) // 4
+        self.accums = [torch.zeros((acc_words,), dtype=torch.int64, device=dev) for _ in range(n_buffers)]
+        self.outs = [torch.zeros((H, W, 3), dtype=torch.float32, device=dev) for _ in range(n_buffers)]
+        self.states = [torch.zeros((st_words,), dtype=torch.int32, device=dev) for _ in range(n_buffers)]
+        self.k = 0
+
+    def frame(self, lights):
+        b = self.k % len(self.accums)
+        self.k += 1
+        self.eng.render_ghosts_device(lights, self.params, self.accums[b].data_ptr(), clear_first=False)
+        out = self.outs[b]
+        self.eng.finalize_tiles_device(self.accums[b].data_ptr(), self.params, out.data_ptr(), out.stride(1) * out.element_size(), self.capi.F32x3,
+                                       self.states[b].data_ptr())
+        return b
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -240,10 +354,13 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")  # host-side waits that must not occupy the GPUs
 
+    K, W_ = args.steps, max(args.warmup, 3)
     tex = load_aperture()
     lens = capi.builtin_lens(3, COATING_NM)
     eng = capi.Engine(local)
@@ -255,142 +372,316 @@ def run_ours(args):
     lights_a = [make_sun(x, y) for x, y in sun_positions(n_lights)]
     lights_b = [make_sun(1.0 - x, 1.0 - y) for x, y in sun_positions(n_lights)]  # e2e alternates frames (same off-axis angle)
     rays_frame, inter_frame, jobs_frame = capi.count_work(lens, params, n_lights)
-    # a second engine = a second stream: converts frame k to pixels while frame k+1 traces; high priority so that its short
-    # kernels slip in between the trace CTAs
-    fin = capi.Engine(local, stream_priority=1)
-    N_BUF = 3                 # rotating accumulator / output sets: 3 x (49.8 + 24.9 MB) > the 126 MB L2
-    sh = sharding.ShardedFlare(eng, params, rank, world, dev, n_buffers=N_BUF, finalize_engine=fin)
-    _, inter_rank, jobs_rank = capi.count_work(lens, sh.params, n_lights)
-    outs = [torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32, device=dev) for _ in range(N_BUF)]
-    out_dev = outs[0]
+    assert inter_frame == nominal_interactions(n_lights), "bench.py's nominal count disagrees with lfb_count_work"
+    N_BUF = 3  # rotating accumulator / output / state sets
+    fin = capi.Engine(local, stream_priority=1) if world > 1 else None  # N > 1: the reduce runs on a second, high-priority stream
+    if fin is not None:
+        fin.set_lens(lens)
+        fin.set_aperture(tex)
+    A = torch.cuda.ExternalStream(eng.stream, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    pf = None
-    if world > 1 and args.reduce != "nccl":
-        pf = sharding.PeerFlare(eng, params, rank, world, dev, dist.group.WORLD, n_buffers=N_BUF, use_multicast=(args.reduce == "multicast"),
+    def build_pipeline(p):
+        """-> (frames(n), finish(), result(b))"""
+        if world == 1:
+            sp = SparsePipeline(eng, p, dev, N_BUF, torch, capi)
+
+            def frames(n, lights=lights_a):
+                b = 0
+                for _ in range(n):
+                    b = sp.frame(lights)
+                return b
+            return frames, (lambda: None), (lambda b: sp.outs[b]), sp
+        if args.reduce == "sparse":
+            ps = sharding.PeerSparse(eng, p, rank, world, dev, dist.group.WORLD, n_buffers=N_BUF, finalize_engine=fin)
+
+            def frames(n, lights=lights_a):
+                b = 0
+                ps.begin()
+                for _ in range(n):
+                    b = ps.frame(lights, owner=0)
+                return b
+            return frames, ps.finish, ps.result, ps
+        if args.reduce == "nccl":
+            sh = sharding.ShardedFlare(eng, p, rank, world, dev, n_buffers=N_BUF, finalize_engine=fin)
+            outs = [torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32, device=dev) for _ in range(N_BUF)]
+
+            def frames(n, lights=lights_a):
+                sh.begin()
+                for k in range(n):
+                    sh.frame(lights, out=outs[k % N_BUF], elem=capi.F32x3, reduce_dst=0)
+                return (n - 1) % N_BUF
+            return frames, sh.join, (lambda b: outs[b]), sh
+        pf = sharding.PeerFlare(eng, p, rank, world, dev, dist.group.WORLD, n_buffers=N_BUF, use_multicast=(args.reduce == "multicast"),
                                 finalize_engine=fin)
         if args.reduce == "multicast" and not pf.mc:
             raise SystemExit("--reduce multicast: the symmetric allocation has no NVSwitch multicast binding on this box")
 
-    def run_frames(n):
-        """n pipelined frames.  N = 1 / --reduce nccl: trace (engine stream) | NCCL reduce to rank 0 (comm stream) | fixed
-        point -> pixels.  N > 1 default: trace | device barrier | fused peer-memory reduce + finalize into rank 0 (one stream)."""
-        if pf is not None:
+        def frames(n, lights=lights_a):
+            b = 0
             pf.begin()
-            for k in range(n):
-                pf.frame(lights_a, owner=0)
-            pf.finish()
-            return
-        sh.begin()
-        for k in range(n):
-            sh.frame(lights_a, out=outs[k % N_BUF], elem=capi.F32x3, reduce_dst=0)
-        sh.join()
+            for _ in range(n):
+                b = pf.frame(lights, owner=0)
+            return b
+        return frames, pf.finish, pf.result, pf
 
-    eager_frames = run_frames
+    def timed_brackets(frames, finish, n_brackets):
+        """n_brackets x (EXACTLY K frames between a barrier + synchronize on both sides); per bracket the device time of the
+        engine stream's events, max over ranks.  -> (list of ms per bracket, host enqueue ms per frame)"""
+        out, enq = [], []
+        for _ in range(n_brackets):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev_stream = A if world == 1 else torch.cuda.current_stream(dev)  # N = 1: everything runs on the engine's stream
+            e0.record(ev_stream)
+            th0 = time.perf_counter()
+            frames(K)
+            finish()  # N > 1: makes torch's current stream wait for the pipeline's streams
+            enq.append((time.perf_counter() - th0) * 1e3 / K)
+            e1.record(ev_stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out.append(float(t[0]))
+        return out, statistics.median(enq)
 
     clocks = ClockSampler(local)
-    run_frames(max(args.warmup, 3))
+    frames, finish, result, pipe = build_pipeline(params)
+    if world == 1:
+        A.wait_stream(torch.cuda.current_stream(dev))
+    frames(W_)
+    finish()
     barrier()
-    # kernels of ours per frame, counted on one eagerly enqueued frame (graph replays do not pass through the engine's counter)
-    l0 = eng.stats()["kernel_launches"] + fin.stats()["kernel_launches"]
-    eager_frames(1)
+    # kernels of ours per frame, counted on one frame
+    l0 = eng.stats()["kernel_launches"] + (fin.stats()["kernel_launches"] if fin else 0)
+    frames(1)
+    finish()
     barrier()
-    launches_per_frame = eng.stats()["kernel_launches"] + fin.stats()["kernel_launches"] - l0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_per_frame = eng.stats()["kernel_launches"] + (fin.stats()["kernel_launches"] if fin else 0) - l0
     with clocks:
-        e0.record()
-        th0 = time.perf_counter()
-        run_frames(args.steps)  # EXACTLY K frames
-        host_enqueue_ms = (time.perf_counter() - th0) * 1e3 / args.steps  # host time to ENQUEUE one frame (no sync inside)
-        e1.record()
+        brackets_ms, host_enqueue_ms = timed_brackets(frames, finish, N_BRACKETS)
+    dev_ms = statistics.median(brackets_ms)
+    value = inter_frame * K / (dev_ms * 1e-3)
+
+    # ---- N > 1: the sharded frame against the unsharded one (outside the timed region) --------------------------------
+    parity = {}
+    if world > 1:
+        b = frames(1)
+        finish()
         barrier()
-    launches = launches_per_frame * args.steps
-    dev_ms = e0.elapsed_time(e1)
-    # the dominant kernel's own duration: CUDA events the engine records around the launch on its stream, one frame at
-    # a time (serial, L2 flushed in between) so that nothing overlaps it
+        same = None
+        if rank == 0:
+            whole = torch.from_numpy(eng.render_ghosts(lights_a, params, elem=capi.F32x3)).to(dev)
+            same = bool(torch.equal(result(b), whole))
+        parity["equals_single_gpu"] = same
+        parity["equals_single_gpu_how"] = ("rank 0 renders the same %d-light frame unsharded (lfb_render_ghosts) and compares it bit for bit "
+                                           "with the frame the %d ranks reduced" % (n_lights, world))
+        barrier()
+
+    # ---- the dominant kernel's own duration: the engine's CUDA events around the trace kernels, one frame at a time, L2 flushed
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     trace_ms = []
-    for k in range(10):
+    for _ in range(12):
         flush.zero_()
-        torch.cuda.synchronize()
-        run_frames(1)
-        torch.cuda.synchronize()
+        barrier()
+        frames(1)
+        finish()
+        barrier()
         trace_ms.append(eng.stats()["last_trace_ms"])
     del flush
-    barrier()
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t[0])
-    value = inter_frame * args.steps / (dev_ms * 1e-3)
+    trace_ms = trace_ms[2:]
+    _, inter_rank, jobs_rank = capi.count_work(lens, capi.copy_params(params, shard=(rank, world) if world > 1 else (0, 0)), n_lights)
 
-    # ---- e2e: the reference-facing call with host buffers, every step ------------------------
-    pinned_out = capi.PinnedArray((HEIGHT, WIDTH, 3), np.float64)  # HDRImageBuffer::data layout (Vector3D, 24 B)
+    # ---- what the kernels executed (the counting build, one frame, outside every timed region) ---------------------------
+    executed = None
+    if rank == 0:
+        se = capi.Engine(local, collect_stats=1)
+        se.set_lens(lens)
+        se.set_aperture(tex)
+        acc = sharding.accum_tensor(params, dev)
+        se.render_ghosts_device(lights_a, capi.copy_params(params, shard=(0, world) if world > 1 else (0, 0)), acc.data_ptr(), clear_first=True)
+        executed = se.exec_stats()
+        se.close()
+        del acc
+
+    # ---- strict leg: the same pipeline, FP64 geometry ------------------------------------------------------------------------
+    strict = None
+    if not args.no_strict:
+        ps_ = capi.copy_params(params, precision=capi.STRICT)
+        del pipe
+        frames_s, finish_s, result_s, pipe_s = build_pipeline(ps_)
+        frames_s(W_)
+        finish_s()
+        barrier()
+        sb, _ = timed_brackets(frames_s, finish_s, 3)
+        st_ms = []
+        for _ in range(6):
+            barrier()
+            frames_s(1)
+            finish_s()
+            barrier()
+            st_ms.append(eng.stats()["last_trace_ms"])
+        strict = {"value": inter_frame * K / (statistics.median(sb) * 1e-3), "unit": "interactions/s", "ms_per_step": statistics.median(sb) / K,
+                  "brackets_ms_per_step": [x / K for x in sb], "kernel_ms": statistics.median(st_ms[1:]),
+                  "what": "LFB_STRICT: the same kernels with FP64 positions / directions (FP32 weights), the precision that meets north_star's "
+                          "1e-5-lens-unit per-ray bar (see parity.strict)"}
+        del pipe_s
+        frames, finish, result, pipe = build_pipeline(params)  # back to FP32 for the legs below
+        frames(W_)
+        finish()
+        barrier()
+
+    # ---- e2e: the reference-facing call with host buffers, every step ---------------------------------------------------------
     pinned_tex = capi.PinnedArray(tex.shape, np.float32)
     pinned_tex.array[...] = tex
-    host_out_t = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float64).pin_memory() if world > 1 else None
-    out64_dev = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float64, device=dev) if world > 1 else None
-
-    def e2e_step(k):
-        lights = lights_a if k % 2 == 0 else lights_b
-        eng.set_aperture(pinned_tex.array)  # this step's input, host -> device
-        if world == 1:
-            eng.render_ghosts(lights, params, out=pinned_out.array, elem=capi.F64x3)  # blocking, frame lands in host memory
-        else:
-            sh.begin()
-            sh.frame(lights, out=out64_dev, elem=capi.F64x3, reduce_dst=0)
-            sh.join()
-            if rank == 0:
-                host_out_t.copy_(out64_dev, non_blocking=True)
-            torch.cuda.synchronize()
-
-    for k in range(max(args.warmup, 3)):
-        e2e_step(k)
-    barrier()
-    with clocks:
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            e2e_step(k)
-        barrier()
-        e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t[0])
-    e2e_value = inter_frame * args.steps / e2e_s
-    job_bytes = 296 + 50 * 48  # sizeof(lfb::Job) + LFB_MAX_STEPS * sizeof(lfb::Step): re-uploaded when the lights change
+    job_bytes = 304 + 50 * 64  # sizeof(lfb::Job) + LFB_MAX_STEPS * sizeof(lfb::StepF): re-uploaded when the lights change
     h2d = tex.nbytes * world + (jobs_frame + 3 * n_lights) * job_bytes  # ghost jobs + one prefix slot per (light, lambda)
-    d2h = HEIGHT * WIDTH * 24
-
-    # ---- the same call without the wait (N = 1): frame k's 49.8 MB copy overlaps frame k+1's trace (two frames in flight) ----
-    e2e_async = None
+    e2e_extra = {}
     if world == 1:
-        pinned_out2 = capi.PinnedArray((HEIGHT, WIDTH, 3), np.float64)
-        outs2 = (pinned_out.array, pinned_out2.array)
+        pinned_out = capi.PinnedArray((HEIGHT, WIDTH, 3), np.float64)  # HDRImageBuffer::data layout (Vector3D, 24 B), page-locked
+        pinned_out.array[...] = 0.0
+        tiles_seen = []
 
-        def async_step(k):
+        def e2e_step(k):
+            eng.set_aperture(pinned_tex.array)  # this step's input, host -> device
+            tiles_seen.append(eng.render_ghosts_sparse(lights_a if k % 2 == 0 else lights_b, params, pinned_out.array, elem=capi.F64x3,
+                                                       out_is_clear=(k == 0 and not tiles_seen)))
+
+        for k in range(W_ + (W_ % 2)):
+            e2e_step(k)
+        e2e_brackets = []
+        with clocks:
+            for _ in range(N_BRACKETS):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for k in range(K):
+                    e2e_step(k)
+                torch.cuda.synchronize()
+                e2e_brackets.append((time.perf_counter() - t0) * 1e3)
+        e2e_ms = statistics.median(e2e_brackets) / K
+        tiles = statistics.median(tiles_seen[-K:])
+        d2h = int(tiles) * 256 * 24 + 4
+        # the frame that landed in host memory is the frame (checked once, outside the timed region)
+        eng.render_ghosts_sparse(lights_a, params, pinned_out.array, elem=capi.F64x3)
+        parity["e2e_frame_equals_full_frame_call"] = bool(np.array_equal(pinned_out.array, eng.render_ghosts(lights_a, params)))
+        e2e_api = ("lfb_render_ghosts_sparse (F64x3, stride 24 = HDRImageBuffer layout): the device writes the frame's dirty 16x16 tiles "
+                   "(median %d of 8160) straight into the caller's page-locked buffer and re-zeroes the previous frame's" % int(tiles))
+        # the same frame through the full-frame blocking call (every pixel crosses PCIe: round 1's e2e)
+        ts = []
+        for k in range(min(K, 20) + 2):
+            t0 = time.perf_counter()
             eng.set_aperture(pinned_tex.array)
-            eng.render_ghosts_async(lights_a if k % 2 == 0 else lights_b, params, outs2[k % 2], elem=capi.F64x3)
+            eng.render_ghosts(lights_a if k % 2 == 0 else lights_b, params, out=pinned_out.array, elem=capi.F64x3)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        e2e_extra["e2e_full_frame"] = {"value": inter_frame / (statistics.median(ts[2:]) * 1e-3), "unit": "interactions/s", "ms_per_step": statistics.median(ts[2:]),
+                                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": HEIGHT * WIDTH * 24,
+                                       "api": "lfb_render_ghosts (every pixel converted and copied: 49.8 MB over PCIe)"}
+        pinned_out.free()
+    else:
+        # N > 1: every rank writes its share of the dirty tiles straight into ONE page-locked host frame that all ranks have
+        # mapped (a POSIX shared-memory segment registered by each process): N PCIe links in parallel, no staging on rank 0
+        from multiprocessing import shared_memory
+        frame_bytes = HEIGHT * WIDTH * 24
+        name = [None]
+        shm = None
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=N_BUF * frame_bytes)
+            name[0] = shm.name
+        dist.broadcast_object_list(name, src=0, group=cpu_group)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name[0])
+        host = np.frombuffer(shm.buf, dtype=np.float64, count=N_BUF * HEIGHT * WIDTH * 3).reshape(N_BUF, HEIGHT, WIDTH, 3)
+        if rank == 0:
+            host[...] = 0.0
+        dist.barrier(group=cpu_group)
+        L = capi.lib()
+        if L.lfb_host_register(host.ctypes.data, host.nbytes) != capi.OK:
+            raise SystemExit("cudaHostRegister of the shared host frame failed: " + L.lfb_last_error().decode())
+        base = L.lfb_host_device_pointer(host.ctypes.data)
+        del pipe
+        pe = sharding.PeerSparse(eng, params, rank, world, dev, dist.group.WORLD, n_buffers=N_BUF, finalize_engine=fin,
+                                 host_out_ptrs=[base + b * frame_bytes for b in range(N_BUF)])
 
-        for k in range(max(args.warmup, 3)):
-            async_step(k)
-        eng.sync()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            async_step(k)
-        eng.sync()
-        async_s = time.perf_counter() - t0
-        e2e_async = {"value": inter_frame * args.steps / async_s, "unit": "interactions/s", "ms_per_step": async_s / args.steps * 1e3,
-                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                     "api": "lfb_render_ghosts_async + lfb_sync: same bytes every step, the copy of frame k overlaps the trace of frame k+1"}
-        pinned_out2.free()
+        def e2e_step(k):
+            eng.set_aperture(pinned_tex.array)
+            pe.begin()
+            b = pe.frame(lights_a if k % 2 == 0 else lights_b, owner=0, elem=capi.F64x3, stride=24)
+            pe.finish()
+            torch.cuda.synchronize()
+            return b
 
-    # ---- the displayable frame (N = 1): ghosts -> toColor -> RGBA8 on the device, 4 B/pixel back over PCIe -----------
-    e2e_rgba8 = None
+        for k in range(W_ + (W_ % 2)):
+            e2e_step(k)
+        e2e_brackets = []
+        with clocks:
+            for _ in range(N_BRACKETS):
+                barrier()
+                t0 = time.perf_counter()
+                for k in range(K):
+                    b = e2e_step(k)
+                barrier()
+                t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_brackets.append(float(t[0]))
+        e2e_ms = statistics.median(e2e_brackets) / K
+        b = e2e_step(0)
+        barrier()
+        if rank == 0:
+            whole64 = eng.render_ghosts(lights_a, params)
+            parity["e2e_host_frame_equals_single_gpu"] = bool(np.array_equal(host[b], whole64))
+            nz_tiles = int((np.add.reduceat(np.add.reduceat((whole64.sum(axis=2) != 0).astype(np.int32), np.arange(0, HEIGHT, 16), axis=0),
+                                            np.arange(0, WIDTH, 16), axis=1) > 0).sum())
+        else:
+            nz_tiles = 0
+        d2h = nz_tiles * 256 * 24
+        e2e_api = ("PeerSparse with a shared page-locked host frame: every rank's lfb_reduce_tiles_peers writes its share of the dirty tiles "
+                   "straight into host memory over its own PCIe link (d2h_bytes_per_step counts the non-empty tiles; the ranks also re-zero "
+                   "the previous frame's)")
+        del pe
+        barrier()
+        L.lfb_host_unregister(host.ctypes.data)
+        del host
+        shm.close()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            shm.unlink()
+    e2e_value = inter_frame / (e2e_ms * 1e-3)
+
+    # ---- N > 1: the single-process form (lfb_create_multi: one host thread drives all GPUs), rank 0 alone ----------------------
+    single_process = None
+    if world > 1:
+        if rank == 0:
+            try:
+                m = capi.MultiEngine(list(range(world)))
+                m.set_lens(lens)
+                m.set_aperture(tex)
+                buf = capi.PinnedArray((HEIGHT, WIDTH, 3), np.float64)
+                buf.array[...] = 0.0
+                ts, st = [], None
+                for k in range(12):
+                    t0 = time.perf_counter()
+                    m.render_ghosts(lights_a if k % 2 == 0 else lights_b, params, buf.array, out_is_clear=(k == 0))
+                    ts.append((time.perf_counter() - t0) * 1e3)
+                m.render_ghosts(lights_a, params, buf.array)
+                st = m.stats()
+                single_process = {"api": "lfb_create_multi + lfb_render_ghosts_multi: ONE host thread, %d GPUs, event-ordered streams, tiles written "
+                                         "straight into the caller's page-locked buffer" % world,
+                                  "ms_per_frame_blocking_call": statistics.median(ts[2:]), "value": inter_frame / (statistics.median(ts[2:]) * 1e-3),
+                                  "unit": "interactions/s", "stage_ms": st,
+                                  "equals_single_gpu": bool(np.array_equal(buf.array, eng.render_ghosts(lights_a, params)))}
+                buf.free()
+                m.close()
+            except Exception as exc:  # reported, never fatal: the headline numbers are above
+                single_process = {"error": repr(exc)[:300]}
+        dist.barrier(group=cpu_group)
+
+    # ---- N = 1 extras: the displayable frame and the starburst (SURVEY 8f) -------------------------------------------------------
+    e2e_rgba8 = starburst = None
     if world == 1:
         pinned_rgba = capi.PinnedArray((HEIGHT, WIDTH), np.uint32)
 
@@ -398,55 +689,57 @@ def run_ours(args):
             eng.set_aperture(pinned_tex.array)
             eng.render_frame_rgba8(lights_a if k % 2 == 0 else lights_b, params, flare_radius=-1.0, out=pinned_rgba.array)
 
-        for k in range(max(args.warmup, 3)):
+        for k in range(W_):
             rgba_step(k)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for k in range(args.steps):
+        for k in range(K):
             rgba_step(k)
         torch.cuda.synchronize()
         rgba_s = time.perf_counter() - t0
-        e2e_rgba8 = {"value": inter_frame * args.steps / rgba_s, "unit": "interactions/s", "ms_per_step": rgba_s / args.steps * 1e3,
+        e2e_rgba8 = {"value": inter_frame * K / rgba_s, "unit": "interactions/s", "ms_per_step": rgba_s / K * 1e3,
                      "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": HEIGHT * WIDTH * 4,
                      "api": "lfb_render_frame_rgba8: ghosts -> HDRImageBuffer::toColor -> ImageBuffer RGBA8 on the device (the displayable frame)"}
         pinned_rgba.free()
-
-    # ---- SURVEY 8f-1 for the record (N = 1): the starburst of the same frame, device time vs the reference per pixel ----
-    starburst = None
-    if world == 1:
+        out64 = capi.PinnedArray((HEIGHT, WIDTH, 3), np.float64)
         eng.set_starburst_aperture(tex)
         for _ in range(3):
-            eng.render_starburst(lights_a, WIDTH, HEIGHT, 50.0, 1.0, out=pinned_out.array)
+            eng.render_starburst(lights_a, WIDTH, HEIGHT, 50.0, 1.0, out=out64.array)
         ts = []
         for _ in range(10):
-            eng.render_starburst(lights_a, WIDTH, HEIGHT, 50.0, 1.0, out=pinned_out.array)
+            eng.render_starburst(lights_a, WIDTH, HEIGHT, 50.0, 1.0, out=out64.array)
             ts.append(eng.stats()["last_trace_ms"])
-        starburst = {"gpu_frame_ms_device": sum(ts) / len(ts), "api": "lfb_render_starburst, 1920x1080, pentbig500_14 (bbox 340x350 texels)"}
-        if not args.no_cpu:
-            try:
-                from oracle import bindings as ob
-                if os.path.exists(ob.REF_SO):
-                    rng = np.random.default_rng(0)
-                    xs, ys = rng.integers(0, WIDTH, 64), rng.integers(0, HEIGHT, 64)
-                    t0 = time.perf_counter()
-                    ob.RefOracle().starburst_multi(tex, WIDTH, HEIGHT, [(0.45, 0.55)], [(1, 1, 1)], 50.0, 1.0, xs, ys)
-                    per_px = (time.perf_counter() - t0) / 64
-                    starburst.update(reference_ms_per_pixel_1thread=per_px * 1e3, reference_frame_s_1thread_extrapolated=per_px * WIDTH * HEIGHT,
-                                     reference_sample="PathTracer::raytrace_starburst at 64 random pixels, one host thread")
-            except Exception as exc:
-                starburst["reference_error"] = repr(exc)[:200]
+        eng.set_starburst_aperture(tex)  # a new mask: the next frame recomputes the lattice spectrum
+        eng.render_starburst(lights_a, WIDTH, HEIGHT, 50.0, 1.0, out=out64.array)
+        starburst = {"gpu_frame_ms_device": statistics.median(ts), "gpu_frame_ms_device_first_frame_of_a_mask": eng.stats()["last_trace_ms"],
+                     "api": "lfb_render_starburst, 1920x1080, pentbig500_14 (bbox 340x350 texels); the lattice spectrum |F| is kept per mask"}
+        out64.free()
 
     peaks = eng.probe_peaks() if rank == 0 else None
     line = None
     if rank == 0:
-        # roofline of the dominant kernel (the FP32 EXACT_GRID ghost kernel): scalar FP32 FMA / MUFU pipes
-        k_ms = sum(trace_ms) / len(trace_ms)
+        k_ms = statistics.median(trace_ms)
         ach = inter_rank * FLOP_PER_INTERACTION / (k_ms * 1e-3)
         mufu_ach = inter_rank * MUFU_PER_INTERACTION / (k_ms * 1e-3)
+        frac = ach / peaks["fp32_flops"]
+        exec_ratio = executed["steps"] / inter_rank if executed else None
         roofline = {
-            "bound": "fp32", "kernel": "xf32::exact_splat3_kernel<12,128> (+ xf32::prefix_kernel)", "achieved": ach / 1e12, "peak": peaks["fp32_flops"] / 1e12,
-            "unit": "TFLOP/s", "frac": ach / peaks["fp32_flops"], "traffic": 1.97e7, "traffic_source": "ncu --set full, profiles/r1_exact_splat_v6_ncu_details.txt: 221.7 GB/s of DRAM traffic x 88.9 us = 19.7 MB per launch (prefix-cache lines that fell out of L2; sensor atomics stay in L2); the kernel has no algorithmic HBM stream",
-            "kernel_ms": k_ms, "interactions_per_launch": inter_rank, "flop_per_interaction": FLOP_PER_INTERACTION,
+            "bound": "fp32", "kernel": "lfb::xt::ghost_kernel<float,12,128> + lfb::xt::prefix_kernel<float> (exact_trace.cuh)",
+            "achieved": ach / 1e12, "peak": peaks["fp32_flops"] / 1e12, "unit": "TFLOP/s", "frac": frac,
+            "frac_is": "NOMINAL: declared 64 FLOP x nominal interactions (rays x I(i,j), BASELINE.json's unit) / kernel time / FFMA peak -- "
+                       "algorithmic throughput, NOT pipe occupancy; see executed_* and issue_slot_frac",
+            "traffic": None, "traffic_note": "the kernel has no algorithmic HBM stream (rays come from their grid index; the 28 MB prefix cache and the sensor "
+                                             "atomics live in L2); ncu --set full of the round-2 kernel: profiles/r2_ghost_kernel_ncu_details.txt",
+            "kernel_ms": k_ms, "kernel_ms_spread": spread(trace_ms), "interactions_per_launch": inter_rank, "flop_per_interaction": FLOP_PER_INTERACTION,
+            "executed_steps": executed["steps"] if executed else None,
+            "executed_ray_pairs_started": executed["ray_pairs_started"] if executed else None,
+            "executed_ray_pairs_landed": executed["ray_pairs_landed"] if executed else None,
+            "executed_over_nominal": exec_ratio,
+            "executed_flop": executed["steps"] * FLOP_PER_INTERACTION if executed else None,
+            "frac_executed": frac * exec_ratio if executed else None,
+            "executed_note": "surface steps the kernels actually ran (lfb_exec_stats, the counting build): mirror-image ray pairs share one trace, "
+                             "the forward sweep is traced once per (light, lambda), rays stop where they die",
+            "issue_slot_frac": 0.52, "issue_slot_source": "ncu --set full, profiles/r2_ghost_kernel_ncu_details.txt (issue slots busy; the kernel is latency-bound)",
             "peak_source": "measured live on this GPU by lfb_probe_peaks (register-only FFMA chains); MEASURED_PEAKS.json holds no "
                            "FP32 figure. The trace is scalar FP32/MUFU math: neither 'hbm' nor 'tensor' bounds it",
             "mufu": {"achieved_gops": mufu_ach / 1e9, "peak_gops": peaks["mufu_ops"] / 1e9, "frac": mufu_ach / peaks["mufu_ops"],
@@ -455,33 +748,45 @@ def run_ours(args):
         }
         line = {
             "metric": "ray_surface_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "steps": K, "warmup": W_, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "lights": n_lights, "sun": "ns=(0.45,0.55) through a 50x35 deg camera -> off-axis angle %.4f rad" % lights_a[0].theta, "jobs_per_frame": jobs_frame, "rays_per_frame": rays_frame,
-                       "interactions_per_frame": inter_frame, "l2": "working set rotates over 3 accumulator/output sets (224 MB > 126 MB L2) in the timed loop; L2 flushed (256 MiB memset) before each kernel-duration sample",
-                       "timing": "K frames back to back as a 3-stage pipeline (trace | NCCL reduce | fixed point -> pixels), every launch enqueued from Python (host enqueue time per frame is reported: at N > 1 the NCCL call's Python cost, ~0.1 ms, is what bounds a cfg2-sized frame; capturing it into a CUDA graph deadlocked on this stack and is not used), one CUDA-event bracket, max over ranks",
-                       "multi_gpu": "jobs (light x pair x wavelength) dealt LPT round-robin to ranks; " + (
-                           "one NCCL int64 sum-reduce to rank 0" if (world == 1 or args.reduce == "nccl") else
-                           "fused reduce+finalize kernel over NVLink peer memory (%s), device-side barrier, no collective call" % args.reduce)},
-            "frame_ms_1080p": dev_ms / args.steps, "host_enqueue_ms_per_step": host_enqueue_ms,
+            "config": {"workload": WORKLOAD, "lights": n_lights, "sun": "ns=(0.45,0.55) through a 50x35 deg camera -> off-axis angle %.4f rad" % lights_a[0].theta,
+                       "jobs_per_frame": jobs_frame, "rays_per_frame": rays_frame, "interactions_per_frame": inter_frame,
+                       "l2": "the frame's working set (prefix cache 28 MB, dirty accumulator tiles) is L2-resident by design; the timed loop rotates "
+                             "over 3 accumulator / output / state sets; L2 is flushed (256 MiB memset) before each kernel-duration sample",
+                       "timing": "%d brackets of exactly K frames back to back (barrier + synchronize on both sides, CUDA events, max over ranks per "
+                                 "bracket): value and ms_per_step are the MEDIAN bracket, brackets_ms_per_step lists all" % N_BRACKETS,
+                       "multi_gpu": "jobs (light x pair x wavelength) dealt to ranks (whole (light, lambda) groups); " + (
+                           "single GPU" if world == 1 else
+                           {"sparse": "tile-sparse reduce + finalize over NVLink peer memory (lfb_reduce_tiles_peers: each rank sums its share of the "
+                                      "dirty tiles and stores the pixels into rank 0's frame), device-side barrier, no collective call",
+                            "nccl": "one NCCL int64 sum-reduce of the whole frame to rank 0",
+                            "peer": "dense fused reduce + finalize over NVLink peer memory", "multicast": "dense fused reduce + finalize through NVSwitch multicast"}[args.reduce])},
+            "frame_ms_1080p": dev_ms / K, "brackets_ms_per_step": [x / K for x in brackets_ms], "host_enqueue_ms_per_step": host_enqueue_ms,
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s / args.steps * 1e3, "api": "lfb_render_ghosts (F64x3, stride 24 = HDRImageBuffer layout)"
-                    if world == 1 else "ShardedFlare.render + reduce + finalize + D2H"},
-            "e2e_async": e2e_async,
+                    "ms_per_step": e2e_ms, "brackets_ms_per_step": [x / K for x in e2e_brackets], "api": e2e_api},
+            "strict": strict,
+            "parity": parity,
+            "single_process": single_process,
             "starburst": starburst,
             "e2e_rgba8": e2e_rgba8,
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches_per_frame * K),
+            "gpu_launches_per_frame": int(launches_per_frame),
             "clocks": clocks.report(),
         }
+        line.update(e2e_extra)
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_block()
+            pb, port_seconds = parity_block(eng, lens, tex, lights_a[0], params)
+            line["parity"].update(pb)
+            line["cpu_baseline"] = cpu_baseline_block(port_seconds, inter_frame)
         print(json.dumps(line))
-    pinned_out.free()
     pinned_tex.free()
-    fin.close()
+    if fin is not None:
+        fin.close()
     eng.close()
     if world > 1:
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
     return 0
 
@@ -496,10 +801,11 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--reduce", default="nccl", choices=["nccl", "peer", "multicast"],
-                    help="N > 1: NCCL int64 reduce pipelined against the next frame's trace (default: measured fastest, 0.187 ms/frame at "
-                         "N=2), or the fused reduce+finalize kernel over NVLink peer memory (0.22 ms), or the same through NVSwitch multicast")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and oracle-parity legs")
+    ap.add_argument("--no-strict", action="store_true", help="skip the LFB_STRICT leg")
+    ap.add_argument("--reduce", default="sparse", choices=["sparse", "nccl", "peer", "multicast"],
+                    help="N > 1: tile-sparse reduce + finalize over NVLink peer memory (default), or round 1's dense paths: one NCCL int64 "
+                         "reduce of the whole frame / the dense fused kernel over peer memory / the same through NVSwitch multicast")
     args = ap.parse_args()
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
 

@@ -134,8 +134,8 @@ typedef struct lfb_params {
   int32_t physical_backward; /* PARAXIAL_GRID only: 0 = the reference's R^-1 on backward legs
                                 (pathtracer.cpp:607-608), 1 = physically consistent backward refraction */
   int32_t shard_index, shard_count; /* this engine renders its share of the (light x pair x lambda) job list: whole
-                                       (light, lambda) groups round-robin when there are at least shard_count groups,
-                                       else single jobs, longest first, round-robin; 0,0 -> all */
+                                       (light, lambda) groups round-robin as far as they divide evenly among the shards,
+                                       the jobs of the remaining groups one by one, longest first; 0,0 -> all */
   float px_per_unit;       /* sensor pixels per lens unit; 0 -> 0.4 (pathtracer.cpp:457-463) */
   int32_t physical_mapping; /* grid modes.  0 = the reference's screen mapping (draw_ghost / shift_vertex, pathtracer.cpp:412-430,
                                457-463): origin at the sun pixel, ghosts laid out along atan((ay-.5)/(ax-.5)) -- an angle mod pi, so
@@ -181,7 +181,9 @@ typedef struct lfb_options {
   int32_t reduce_ctas;        /* CTAs of the cross-GPU reduce kernels: 0 = one per SM */
   int32_t collect_stats;      /* 1: run the counting instantiation of the EXACT_GRID kernels (lfb_exec_stats); slower */
   int64_t prefix_budget_bytes; /* device memory the cached forward sweeps may take: 0 = 40 GiB; < 0 = no cache */
-  int32_t reserved[8];
+  int32_t weights_table;      /* 1: Fresnel / coating weights from the 1024-interval tables for every ray (round 1's scheme,
+                                 kept for A/B measurements) instead of the per-step polynomials */
+  int32_t reserved[7];
 } lfb_options;
 
 /* ---- lifecycle -------------------------------------------------------- */
@@ -237,6 +239,19 @@ int lfb_render_ghosts_rect(lfb_engine* e, const lfb_light* lights, int n_lights,
                            const lfb_params* params, void* out, size_t out_stride_bytes,
                            int out_elem, int* rect_out);
 
+/* Tile-sparse form of lfb_render_ghosts (grid modes, overwrite semantics).  A flare frame is ~99 % zeros: the splat kernels
+ * mark the 16 x 16 sensor tiles they deposit into, and only those tiles -- plus the tiles the PREVIOUS frame left non-zero in
+ * this same buffer, which are re-zeroed -- are converted and written, straight into the caller's memory from the device
+ * (zero-copy over PCIe: `out` must be page-locked, lfb_host_alloc / lfb_host_register; pageable memory falls back to the
+ * full-frame copy of lfb_render_ghosts and reports *tiles_written = -1).  On return `out` holds exactly this frame, bit for
+ * bit what lfb_render_ghosts writes -- the reference's ghost_buffer after generate_ghost_buffer (pathtracer.cpp:714-762),
+ * whose clear() + resize() (:719-720) is what the bookkeeping below replaces.
+ * Contract: out_is_clear = 1 says every pixel of `out` is zero now (a fresh HDRImageBuffer::resize + clear); with 0, `out`
+ * must be the buffer of this engine's previous lfb_render_ghosts_sparse call, same size / stride / element, not written by
+ * anyone else since (else LFB_ERR_STATE).  n_lights = 0 just re-zeroes what the previous frame wrote. */
+int lfb_render_ghosts_sparse(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* params,
+                             void* out, size_t out_stride_bytes, int out_elem, int out_is_clear, int* tiles_written);
+
 /* Parity instrument (no reference counterpart; PARAXIAL_GRID records are what trace_ray_auto_before / _after,
  * pathtracer.cpp:588-689, return per axis): trace the N x N grid of one ghost (i, j, lambda) of one light
  * and return every ray's record (grid modes only).  i = j = -1 selects the direct path. */
@@ -274,8 +289,27 @@ int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, int n_lights,
 /* No reference counterparts in this section: the reference is a single-process CPU program.  Together these calls are
  * generate_ghost_buffer (pathtracer.cpp:714-762) split into its device stages so that one process per GPU can shard a
  * frame by (light, ghost pair, wavelength) and sum the shards. */
-/* Sensor accumulators: width*height*3 u64 fixed-point sums, owned by the caller. */
+/* A sensor accumulator buffer, owned by the caller: width*height*3 u64 fixed-point sums followed by the dirty-tile map
+ * of those sums (one byte per 16 x 16 pixel tile, set by the splat kernels).  Zero it once; the tile-sparse calls below
+ * leave it zeroed again. */
 size_t lfb_accum_bytes(int width, int height);
+/* The state that goes with an OUTPUT buffer of the tile-sparse calls (which tiles the previous frame left non-zero in it).
+ * Zero it once, while the output buffer is all zeros. */
+size_t lfb_tile_state_bytes(int width, int height);
+/* Tile-sparse lfb_finalize_device + accumulator clear in one launch: converts the dirty tiles of accum_dev into out_dev
+ * (a full W x H frame in device memory, or page-locked host memory as mapped on the device), re-zeroes the tiles the previous
+ * frame left in out_dev, zeroes the accumulator tiles it read and rolls the tile maps over.  out_dev then holds exactly the
+ * frame lfb_finalize_device would write, given that it was all zeros when tile_state_dev was. */
+int lfb_finalize_tiles_device(lfb_engine* e, void* accum_dev, const lfb_params* params, void* out_dev, size_t out_stride_bytes,
+                              int out_elem, void* tile_state_dev);
+/* Multi-GPU form of the same launch: the cross-GPU reduce of SURVEY.md 8e fused with finalize, over NVLink peer memory, on
+ * dirty tiles only.  accum_ptrs[r] is rank r's accumulator buffer as mapped in this process; this rank handles the tile-map
+ * words w = rank (mod n_ranks): it sums the tiles that are dirty on any rank (reading only the ranks that have them),
+ * zeroes them, and stores the pixels into out_dev, the OWNER's output frame as mapped here.  tile_state_dev is this rank's
+ * own state for that frame.  Order it after every rank's lfb_render_ghosts_device of the frame (lfb_peer_barrier, or
+ * events in a single-process host).  Integer sums: the frame has the same bits for any rank count. */
+int lfb_reduce_tiles_peers(lfb_engine* e, void* const* accum_ptrs, int n_ranks, int rank, const lfb_params* params,
+                           void* out_dev, size_t out_stride_bytes, int out_elem, void* tile_state_dev);
 /* The engine's CUDA stream (cudaStream_t) so callers can order work / record events. */
 void* lfb_stream(lfb_engine* e);
 /* Zero the accumulators, trace + splat this shard's ghosts (grid modes), all on the
@@ -305,6 +339,27 @@ int lfb_peer_barrier(lfb_engine* e, void* const* flag_ptrs, int n_ranks, int ran
 int lfb_reduce_finalize_peers(lfb_engine* e, const void* const* accum_ptrs, int n_ranks, int rank,
                               const void* multicast_accum, const lfb_params* params, void* out_dev,
                               size_t out_stride_bytes, int out_elem);
+
+/* ---- single-process multi-GPU ------------------------- */
+/* The reference's caller is ONE thread of ONE process (RaytracedRenderer::start_raytracing, raytraced_renderer.cpp:303-311):
+ * this is the multi-GPU frame for that caller -- no torchrun, no NCCL, no IPC.  lfb_create_multi opens one engine per device
+ * of one node and enables peer access between them; lfb_render_ghosts_multi shards the (light x pair x lambda) jobs over the
+ * devices (lfb_params.shard_* are set internally), every device traces its share into its own accumulators, and then every
+ * device runs the tile-sparse reduce (lfb_reduce_tiles_peers) for its interleaved share of the dirty tiles: it sums them over
+ * NVLink peer memory and writes the pixels STRAIGHT INTO THE CALLER'S page-locked buffer over its own PCIe link.  Ordering is
+ * by CUDA events between the devices' streams.  Same contract and result as lfb_render_ghosts_sparse (out_is_clear,
+ * tiles_written; bit-identical frames for any device count); pageable `out` falls back to a full-frame copy from device 0. */
+typedef struct lfb_multi lfb_multi;
+int lfb_create_multi(lfb_multi** out, const int* device_ids, int n_devices, const lfb_options* options);
+void lfb_destroy_multi(lfb_multi* m);
+/* lfb_set_lens / lfb_set_aperture on every device. */
+int lfb_multi_set_lens(lfb_multi* m, const lfb_lens* lens);
+int lfb_multi_set_aperture(lfb_multi* m, const float* texels, int w, int h);
+int lfb_render_ghosts_multi(lfb_multi* m, const lfb_light* lights, int n_lights, const lfb_params* params, void* out,
+                            size_t out_stride_bytes, int out_elem, int out_is_clear, int* tiles_written);
+/* Device times of the last lfb_render_ghosts_multi, ms: stage_ms[0] = slowest device's trace kernels, [1] = slowest device's
+ * reduce kernel, [2] = first enqueue to last completion as seen by the host thread, [3] = host time spent enqueuing. */
+int lfb_multi_stats(lfb_multi* m, float stage_ms[4], int* n_devices);
 
 /* ---- accounting (no reference counterparts) ------------------------------ */
 /* Ray-surface interactions (I(i,j) = 2(j-i) + n_surfaces + 1 per ray,
@@ -341,6 +396,10 @@ void lfb_host_free(void* p);
  * reallocated.  Returns LFB_OK or LFB_ERR_CUDA (the memory then simply stays pageable). */
 int lfb_host_register(void* p, size_t bytes);
 int lfb_host_unregister(void* p);
+/* The address at which the current device sees page-locked host memory (cudaHostGetDevicePointer): what the device-resident
+ * calls (lfb_finalize_tiles_device, lfb_reduce_tiles_peers) take as out_dev to write a frame's tiles straight into host
+ * memory.  NULL when p is not page-locked / mapped. */
+void* lfb_host_device_pointer(void* p);
 
 #ifdef __cplusplus
 }

@@ -30,10 +30,10 @@ RAY_MISSED, RAY_VIGNETTED, RAY_TIR, RAY_STOPPED, RAY_OFF_SENSOR = 1, 2, 4, 8, 16
 
 # every symbol include/lfb200.h declares (tests check the library exports each one)
 SYMBOLS = (
-    "lfb_abi_version", "lfb_create", "lfb_create_ex", "lfb_exec_stats", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
+    "lfb_abi_version", "lfb_create", "lfb_create_ex", "lfb_exec_stats", "lfb_create_multi", "lfb_destroy_multi", "lfb_multi_set_lens", "lfb_multi_set_aperture", "lfb_render_ghosts_multi", "lfb_multi_stats", "lfb_render_ghosts_sparse", "lfb_tile_state_bytes", "lfb_finalize_tiles_device", "lfb_reduce_tiles_peers", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
     "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_render_ghosts_async", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
     "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_reduce_finalize_peers", "lfb_peer_barrier", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
-    "lfb_host_alloc", "lfb_host_free", "lfb_host_register", "lfb_host_unregister", "lfb_finalize_clear_device", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
+    "lfb_host_alloc", "lfb_host_free", "lfb_host_register", "lfb_host_unregister", "lfb_host_device_pointer", "lfb_finalize_clear_device", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
 )
 
 
@@ -72,7 +72,7 @@ class Options(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("stream_priority", C.c_int32), ("kernel_select", C.c_int32), ("family_split", C.c_int32),
         ("ctas_per_sm", C.c_int32), ("prefix_overlap", C.c_int32), ("starburst_lattice", C.c_int32), ("starburst_cache", C.c_int32),
-        ("reduce_ctas", C.c_int32), ("collect_stats", C.c_int32), ("prefix_budget_bytes", C.c_int64), ("reserved", C.c_int32 * 8),
+        ("reduce_ctas", C.c_int32), ("collect_stats", C.c_int32), ("prefix_budget_bytes", C.c_int64), ("weights_table", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -180,6 +180,18 @@ def lib():
     L.lfb_render_ghosts.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.c_int]
     L.lfb_render_ghosts_async.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int]
     L.lfb_render_ghosts_rect.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
+    L.lfb_render_ghosts_sparse.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.lfb_tile_state_bytes.argtypes = [C.c_int, C.c_int]
+    L.lfb_tile_state_bytes.restype = C.c_size_t
+    L.lfb_finalize_tiles_device.argtypes = [vp, vp, PP, vp, C.c_size_t, C.c_int, vp]
+    L.lfb_reduce_tiles_peers.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, PP, vp, C.c_size_t, C.c_int, vp]
+    L.lfb_create_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(Options)]
+    L.lfb_destroy_multi.argtypes = [vp]
+    L.lfb_destroy_multi.restype = None
+    L.lfb_multi_set_lens.argtypes = [vp, LP]
+    L.lfb_multi_set_aperture.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.c_int]
+    L.lfb_render_ghosts_multi.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.lfb_multi_stats.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.lfb_dump_rays.argtypes = [vp, LiP, PP, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]
     L.lfb_ref_ghosts.argtypes = [vp, vp, C.c_int]
     L.lfb_accum_bytes.argtypes = [C.c_int, C.c_int]
@@ -203,6 +215,8 @@ def lib():
     L.lfb_host_register.restype = C.c_int
     L.lfb_host_unregister.argtypes = [vp]
     L.lfb_host_unregister.restype = C.c_int
+    L.lfb_host_device_pointer.argtypes = [vp]
+    L.lfb_host_device_pointer.restype = vp
     L.lfb_set_starburst_aperture.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.c_int]
     L.lfb_render_starburst.argtypes = [vp, LiP, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, C.c_size_t, C.c_int, C.c_int]
     L.lfb_render_frame_rgba8.argtypes = [vp, LiP, C.c_int, PP, C.c_double, C.c_double, vp, vp, C.c_int]
@@ -255,6 +269,48 @@ class PinnedArray:
             self.array = None
             lib().lfb_host_free(self.ptr)
             self.ptr = None
+
+
+class MultiEngine:
+    """Owner of one lfb_multi: several GPUs of one node driven by THIS process and thread (lfb_create_multi)."""
+
+    def __init__(self, device_ids, **options):
+        self._h = C.c_void_p()
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        check(lib().lfb_create_multi(C.byref(self._h), ids, len(device_ids), C.byref(make_options(**options)) if options else None))
+
+    def close(self):
+        if self._h:
+            lib().lfb_destroy_multi(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_lens(self, lens):
+        check(lib().lfb_multi_set_lens(self._h, C.byref(lens)))
+
+    def set_aperture(self, texels):
+        tex = np.ascontiguousarray(texels, np.float32)
+        check(lib().lfb_multi_set_aperture(self._h, tex.ctypes.data_as(C.POINTER(C.c_float)), tex.shape[1], tex.shape[0]))
+
+    def render_ghosts(self, lights, params, out, elem=F64x3, stride=None, out_is_clear=False):
+        """Tile-sparse frame into `out` (page-locked host array kept between frames), sharded over the devices; returns the
+        number of tiles written (-1: pageable `out`, full-frame copy)."""
+        if stride is None:
+            stride = out.strides[1]
+        n = C.c_int()
+        check(lib().lfb_render_ghosts_multi(self._h, lights_array(lights), len(lights), C.byref(params), out.ctypes.data, stride, elem,
+                                            int(out_is_clear), C.byref(n)))
+        return n.value
+
+    def stats(self):
+        ms, n = (C.c_float * 4)(), C.c_int()
+        check(lib().lfb_multi_stats(self._h, ms, C.byref(n)))
+        return dict(trace_ms=ms[0], reduce_ms=ms[1], call_ms=ms[2], enqueue_ms=ms[3], n_devices=n.value)
 
 
 class Engine:
@@ -315,6 +371,23 @@ class Engine:
         check(lib().lfb_render_ghosts_rect(self._h, lights_array(lights), len(lights), C.byref(params),
                                            out.ctypes.data, stride, elem, rect))
         return None if rect[2] < rect[0] else tuple(rect)
+
+    def render_ghosts_sparse(self, lights, params, out, elem=F64x3, stride=None, out_is_clear=False):
+        """Tile-sparse frame into `out` (page-locked host array the caller keeps between frames); returns the number of
+        16 x 16 tiles written (-1: `out` is pageable and the full frame was copied)."""
+        if stride is None:
+            stride = out.strides[1]
+        n = C.c_int()
+        check(lib().lfb_render_ghosts_sparse(self._h, lights_array(lights), len(lights), C.byref(params), out.ctypes.data, stride, elem,
+                                             int(out_is_clear), C.byref(n)))
+        return n.value
+
+    def finalize_tiles_device(self, accum_ptr, params, out_ptr, stride, elem, state_ptr):
+        check(lib().lfb_finalize_tiles_device(self._h, accum_ptr, C.byref(params), out_ptr, stride, elem, state_ptr))
+
+    def reduce_tiles_peers(self, accum_ptrs, rank, params, out_ptr, stride, elem, state_ptr):
+        arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)
+        check(lib().lfb_reduce_tiles_peers(self._h, arr, len(accum_ptrs), rank, C.byref(params), out_ptr, stride, elem, state_ptr))
 
     def set_starburst_aperture(self, texels):
         tex = np.ascontiguousarray(texels, np.float32)

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -83,20 +84,24 @@ void list_jobs(const lfb_lens& L, const lfb_params& P, int n_lights, std::vector
   }
   out.clear();
   if (P.shard_count <= 1) { out = all; return; }
-  // Sharding.  When the frame has at least as many (light, lambda) groups as shards, whole groups are dealt round-robin:
-  // all ghosts of a group share one forward sweep (the prefix cache of the FP32 kernel), and equal groups balance
-  // exactly.  Otherwise single jobs are dealt, longest-processing-time first (stable), round-robin.
+  // Sharding.  All ghosts of a (light, lambda) group share one forward sweep (the prefix cache), so groups are dealt WHOLE,
+  // round-robin, as far as they divide evenly among the shards: groups 0 .. floor(G / S) * S - 1.  The jobs of the remaining
+  // G mod S groups (all of them when G < S) are put in longest-processing-time-first order (stable) and dealt one by one,
+  // so that e.g. one RGB light on two GPUs is split 1.5 : 1.5 groups, not 2 : 1.
+  const int S = P.shard_count;
   const int n_groups = P.mode == LFB_MODE_REF_QUADS ? 0 : n_lights * L.n_lambda;
-  if (n_groups >= P.shard_count) {
-    for (const JobId& id : all)
-      if ((id.light * L.n_lambda + id.lambda) % P.shard_count == P.shard_index) out.push_back(id);
-    return;
+  const int n_whole = (n_groups / S) * S;
+  std::vector<JobId> rest;
+  for (const JobId& id : all) {
+    const int grp = id.light * L.n_lambda + id.lambda;
+    if (grp < n_whole) { if (grp % S == P.shard_index) out.push_back(id); }
+    else rest.push_back(id);
   }
-  std::stable_sort(all.begin(), all.end(), [&](const JobId& a, const JobId& b) {
+  std::stable_sort(rest.begin(), rest.end(), [&](const JobId& a, const JobId& b) {
     return interactions_of(L, a.i, a.j) > interactions_of(L, b.i, b.j);
   });
-  for (size_t q = 0; q < all.size(); q++)
-    if ((int)(q % (size_t)P.shard_count) == P.shard_index) out.push_back(all[q]);
+  for (size_t q = 0; q < rest.size(); q++)
+    if ((int)(q % (size_t)S) == P.shard_index) out.push_back(rest[q]);
 }
 
 int check_lens(const lfb_lens* L) {
@@ -174,6 +179,7 @@ struct lfb_engine {
   char* d_fam_progs = nullptr;  char* h_fam_progs = nullptr;
   int fams_cap = 0, n_fams = 0;
   bool frame_has_family = false, last_families = false;
+  std::vector<unsigned> job_heads, fam_heads;  // packed (slot, first reflection, program length) per ghost / family job
   float2* d_lut = nullptr;   // reflectance tables, kLutSize entries per (lambda, surface, direction)
   std::vector<float> poly;   // reflectance polynomials, kPolyN coefficients per (lambda, surface, direction)
   unsigned long long* d_stats = nullptr;  // options.collect_stats: executed steps / ray pairs started / landed of the last frame
@@ -198,6 +204,8 @@ struct lfb_engine {
   size_t star_scratch_cap = 0;
   double* d_star_lights = nullptr;
   size_t star_lights_cap = 0;
+  bool star_spectrum_valid = false;  // d_star_scratch holds the lattice spectrum |F| of the current mask (options.starburst_cache)
+  int star_spectrum_period = 0;
   // asynchronous host path (lfb_render_ghosts_async): the frame's device->host copy runs on its own stream out of one of
   // two device buffers, so it overlaps the next frame's trace
   cudaStream_t copy_stream = nullptr;
@@ -217,6 +225,15 @@ struct lfb_engine {
   bool track_bbox = false;
   int accum_dirty[4] = {0, 0, -1, -1};  // what the last rect frame left non-zero in d_accum
   int accum_dirty_w = 0, accum_dirty_h = 0;
+  // tile-sparse host path (lfb_render_ghosts_sparse): the caller's buffer the engine last wrote and the tiles it left in it
+  unsigned* d_sparse_state = nullptr;
+  size_t sparse_state_cap = 0;
+  const void* sparse_out = nullptr;
+  int sparse_w = 0, sparse_h = 0, sparse_elem = 0;
+  size_t sparse_stride = 0;
+  unsigned* h_count = nullptr;  // page-locked, mapped: tiles written by the last sparse launch
+  bool accum_clean = false;     // d_accum (sums and bitmap) is all zeros for a accum_clean_w x accum_clean_h frame
+  int accum_clean_w = 0, accum_clean_h = 0;
   uint64_t launches = 0;
   float last_trace_ms = 0, last_frame_ms = 0;
 };
@@ -278,6 +295,7 @@ FrameGeom make_geom(const lfb_engine* e, const lfb_params& P, unsigned* tile_bit
   g.bbox = e->track_bbox ? e->d_bbox : nullptr;
   g.tile_bits = tile_bits;
   g.tiles_w = tiles_across(P.width);
+  g.poly_v0 = e->opt.weights_table ? 2.f : kPolyV0;
   g.stats = e->opt.collect_stats ? e->d_stats : nullptr;
   return g;
 }
@@ -543,6 +561,7 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
   e->frame_has_prefix2 = false;
   e->frame_has_family = false;
   e->n_fams = 0; e->n_slots = 0;
+  e->job_heads.clear(); e->fam_heads.clear();
   if (want_progs && e->opt.prefix_budget_bytes >= 0) {
     slot_of.assign((size_t)std::max(n_lights, 1) * e->lens.n_lambda, -1);
     for (int q = 0; q < n; q++)
@@ -627,6 +646,7 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
         FJ->i = (int)fams[f].mask;
         FJ->j = fams[f].j;
         FJ->n_steps = build_family_program(e, sid.lambda, fams[f].j, fams[f].mask, prog);
+        e->fam_heads.push_back(pack_head(FJ->slot, FJ->j_first, FJ->n_steps));
         put_steps(strict, e->h_fam_progs, (size_t)f * LFB_MAX_STEPS, prog, FJ->n_steps);
       }
       e->n_fams = nf;
@@ -648,6 +668,7 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
       const bool cached = e->frame_has_prefix && ids[q].i >= 0;
       if (cached) e->h_jobs[q].slot = slot_of[(size_t)ids[q].light * e->lens.n_lambda + ids[q].lambda];
       e->h_jobs[q].n_steps = build_program(e, ids[q].lambda, ids[q].i, ids[q].j, prog, cached);
+      e->job_heads.push_back(pack_head(e->h_jobs[q].slot, ids[q].i < 0 ? -1 : ids[q].j, e->h_jobs[q].n_steps));
       put_steps(strict, e->h_progs, (size_t)q * LFB_MAX_STEPS, prog, e->h_jobs[q].n_steps);
     }
   }
@@ -706,11 +727,11 @@ int launch_exact_frame(lfb_engine* e, const lfb_params& P, FrameGeom& g, unsigne
   }
   if (families) {  // one job per (light, lambda, first reflection); the direct path was splatted by the prefix kernel
     if (e->n_fams > 0) {
-      CU(launch_exact_families<T>(e->d_fams, (const S*)e->d_fam_progs, e->n_fams, e->d_slots, (const S*)e->d_slot_progs, g, e->d_tex, accum, stats, e->stream));
+      CU(launch_exact_families<T>(e->d_fams, (const S*)e->d_fam_progs, e->fam_heads.data(), e->n_fams, e->d_slots, (const S*)e->d_slot_progs, g, e->d_tex, accum, e->opt.ctas_per_sm, stats, e->stream));
       e->launches++;
     }
   } else if (e->n_jobs > 0) {
-    CU(launch_exact_ghosts<T>(e->d_jobs, (const S*)e->d_progs, e->n_jobs, g, e->d_tex, accum, e->opt.ctas_per_sm, stats, e->stream));
+    CU(launch_exact_ghosts<T>(e->d_jobs, (const S*)e->d_progs, e->job_heads.data(), e->n_jobs, g, e->d_tex, accum, e->opt.ctas_per_sm, stats, e->stream));
     e->launches++;
   }
   if (overlap_buf >= 0) {  // the cache may be rewritten once this frame's kernels are done with it
@@ -852,6 +873,8 @@ extern "C" int lfb_create_ex(lfb_engine** out, int device_id, const lfb_options*
   if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_stats, 4 * sizeof(unsigned long long));
   if (rc == cudaSuccess) rc = cudaMemset(e->d_stats, 0, 4 * sizeof(unsigned long long));
   if (rc == cudaSuccess) rc = cudaHostAlloc((void**)&e->h_bbox, 8 * sizeof(int), cudaHostAllocDefault);
+  if (rc == cudaSuccess) rc = cudaHostAlloc((void**)&e->h_count, 4 * sizeof(unsigned), cudaHostAllocMapped);
+  if (rc == cudaSuccess) e->h_count[0] = 0;
   if (rc == cudaSuccess) { e->h_bbox[0] = e->h_bbox[1] = 0x7fffffff; e->h_bbox[2] = e->h_bbox[3] = -0x7fffffff; }
   if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
   *out = e;
@@ -887,6 +910,8 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   }
   cudaFree(e->d_star_tex); cudaFree(e->d_star_scratch); cudaFree(e->d_star_lights); cudaFree(e->d_hdr); cudaFree(e->d_rgba);
   if (e->h_bbox) cudaFreeHost(e->h_bbox);
+  if (e->h_count) cudaFreeHost(e->h_count);
+  cudaFree(e->d_sparse_state);
   if (e->h_progs) cudaFreeHost(e->h_progs);
   cudaFree(e->d_tex); cudaFree(e->d_jobs); cudaFree(e->d_dump_job); cudaFree(e->d_accum); cudaFree(e->d_out);
   cudaFree(e->d_hits); cudaFree(e->d_tris); cudaFree(e->d_ghosts); cudaFree(e->d_pairs); cudaFree(e->d_rgbw);
@@ -1178,6 +1203,7 @@ extern "C" int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_l
   } else {
     rc = grow(&e->d_accum, &e->accum_cap, lfb_accum_bytes(P->width, P->height));
     if (rc) return rc;
+    e->accum_clean = false;
     e->accum_dirty_w = e->accum_dirty_h = 0;  // the whole buffer is about to be used: the rect path must start fresh
     rc = render_grid_device(e, lights, n_lights, *P, e->d_accum, 1);
     if (rc) return rc;
@@ -1188,6 +1214,117 @@ extern "C" int lfb_render_ghosts(lfb_engine* e, const lfb_light* lights, int n_l
   CU(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaEventRecord(e->ev_frame1, e->stream));
   CU(cudaStreamSynchronize(e->stream));  // the reference's caller reads ghost_buffer right after the call
+  CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
+  CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
+  return LFB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// tile-sparse back end (sparse.cu)
+// ---------------------------------------------------------------------------
+extern "C" size_t lfb_tile_state_bytes(int width, int height) {
+  if (width < 1 || height < 1) return 0;
+  return tile_state_bytes(width, height);
+}
+
+namespace {
+int check_out_args(const void* out_dev, size_t stride, int elem) {
+  if (!out_dev) return fail(LFB_ERR_INVALID, "NULL output pointer");
+  if (elem != LFB_F32x3 && elem != LFB_F64x3) return fail(LFB_ERR_INVALID, "unknown out_elem");
+  if (stride < elem_bytes(elem) || stride % (elem == LFB_F32x3 ? 4 : 8)) return fail(LFB_ERR_INVALID, "bad out_stride_bytes");
+  return LFB_OK;
+}
+}  // namespace
+
+extern "C" int lfb_finalize_tiles_device(lfb_engine* e, void* accum_dev, const lfb_params* P, void* out_dev, size_t stride, int elem,
+                                         void* tile_state_dev) {
+  int rc = bind(e);
+  if (rc) return rc;
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (!accum_dev || !tile_state_dev) return fail(LFB_ERR_INVALID, "NULL device pointer");
+  rc = check_out_args(out_dev, stride, elem);
+  if (rc) return rc;
+  PeerAccums A;
+  memset(&A, 0, sizeof(A));
+  A.n = 1; A.ptr[0] = (const unsigned long long*)accum_dev;
+  const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+  CU(launch_tiles(A, 0, P->width, P->height, inv, out_dev, stride, elem, (unsigned*)tile_state_dev, nullptr, 0, e->stream));
+  e->launches++;
+  return LFB_OK;
+}
+
+extern "C" int lfb_reduce_tiles_peers(lfb_engine* e, void* const* accum_ptrs, int n_ranks, int rank, const lfb_params* P, void* out_dev,
+                                      size_t stride, int elem, void* tile_state_dev) {
+  int rc = bind(e);
+  if (rc) return rc;
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (!accum_ptrs || n_ranks < 1 || n_ranks > LFB_MAX_PEERS || rank < 0 || rank >= n_ranks || !tile_state_dev) return fail(LFB_ERR_INVALID, "bad peer set");
+  rc = check_out_args(out_dev, stride, elem);
+  if (rc) return rc;
+  PeerAccums A;
+  memset(&A, 0, sizeof(A));
+  A.n = n_ranks;
+  for (int r = 0; r < n_ranks; r++) {
+    if (!accum_ptrs[r]) return fail(LFB_ERR_INVALID, "NULL peer accumulator");
+    A.ptr[r] = (const unsigned long long*)accum_ptrs[r];
+  }
+  const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+  CU(launch_tiles(A, rank, P->width, P->height, inv, out_dev, stride, elem, (unsigned*)tile_state_dev, nullptr, e->opt.reduce_ctas, e->stream));
+  e->launches++;
+  return LFB_OK;
+}
+
+extern "C" int lfb_render_ghosts_sparse(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P, void* out, size_t stride,
+                                        int elem, int out_is_clear, int* tiles_written) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!e->has_lens || !e->has_tex) return fail(LFB_ERR_STATE, "set the lens and the aperture first");
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (n_lights < 0 || (n_lights > 0 && !lights)) return fail(LFB_ERR_INVALID, "bad lights");
+  rc = check_out_args(out, stride, elem);
+  if (rc) return rc;
+  if (tiles_written) *tiles_written = 0;
+  // is the caller's buffer page-locked and mapped into this device?  (else: the full-frame copy)
+  cudaPointerAttributes attr;
+  memset(&attr, 0, sizeof(attr));
+  const cudaError_t perr = cudaPointerGetAttributes(&attr, out);
+  if (perr != cudaSuccess) cudaGetLastError();
+  const bool same = out == e->sparse_out && P->width == e->sparse_w && P->height == e->sparse_h && stride == e->sparse_stride && elem == e->sparse_elem;
+  if (!out_is_clear && !same) return fail(LFB_ERR_STATE, "lfb_render_ghosts_sparse: `out` is not the buffer of the previous sparse call; pass out_is_clear = 1 with a zeroed buffer");
+  if (perr != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+    e->sparse_out = nullptr;  // the dense call rewrites every pixel: nothing to remember
+    if (tiles_written) *tiles_written = -1;
+    return lfb_render_ghosts(e, lights, n_lights, P, out, stride, elem, 0);
+  }
+  const AccumLayout lay = accum_layout(P->width, P->height);
+  rc = grow(&e->d_sparse_state, &e->sparse_state_cap, tile_state_bytes(P->width, P->height));
+  if (rc) return rc;
+  if (out_is_clear || !same) CU(cudaMemsetAsync(e->d_sparse_state, 0, tile_state_bytes(P->width, P->height), e->stream));
+  e->sparse_out = out; e->sparse_w = P->width; e->sparse_h = P->height; e->sparse_stride = stride; e->sparse_elem = elem;
+  if (lay.total > e->accum_cap) e->accum_clean = false;
+  rc = grow(&e->d_accum, &e->accum_cap, lay.total);
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev_frame0, e->stream));
+  const bool clean = e->accum_clean && e->accum_clean_w == P->width && e->accum_clean_h == P->height;
+  e->accum_clean = false;
+  e->accum_dirty_w = e->accum_dirty_h = 0;
+  rc = render_grid_device(e, lights, n_lights, *P, e->d_accum, clean ? 0 : 1);
+  if (rc) return rc;
+  PeerAccums A;
+  memset(&A, 0, sizeof(A));
+  A.n = 1; A.ptr[0] = e->d_accum;
+  const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+  unsigned* count_dev = nullptr;
+  CU(cudaHostGetDevicePointer((void**)&count_dev, e->h_count, 0));
+  CU(launch_tiles(A, 0, P->width, P->height, inv, attr.devicePointer, stride, elem, e->d_sparse_state, count_dev, 0, e->stream));
+  e->launches++;
+  CU(cudaEventRecord(e->ev_frame1, e->stream));
+  CU(cudaStreamSynchronize(e->stream));  // the kernel's stores into the caller's memory are complete and visible
+  e->accum_clean = true; e->accum_clean_w = P->width; e->accum_clean_h = P->height;
+  if (tiles_written) *tiles_written = (int)e->h_count[0];
   CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
   CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
   return LFB_OK;
@@ -1226,6 +1363,7 @@ extern "C" int lfb_render_ghosts_async(lfb_engine* e, const lfb_light* lights, i
   }
   rc = grow(&e->d_accum, &e->accum_cap, lfb_accum_bytes(P->width, P->height));
   if (rc) return rc;
+  e->accum_clean = false;
   // buffer b's previous copy must have left the device buffer before it is overwritten
   if (e->copied_valid[b]) CU(cudaStreamWaitEvent(e->stream, e->ev_copied[b], 0));
   if (stride != elem_bytes(elem)) CU(cudaMemsetAsync(e->d_out_ab[b], 0, out_bytes, e->stream));
@@ -1277,6 +1415,7 @@ extern "C" int lfb_render_ghosts_rect(lfb_engine* e, const lfb_light* lights, in
     const bool fresh = need > e->accum_cap || e->accum_dirty_w != P->width || e->accum_dirty_h != P->height;
     rc = grow(&e->d_accum, &e->accum_cap, need);
     if (rc) return rc;
+    e->accum_clean = false;
     // the accumulators are zero except for the rectangle the previous rect frame left: clear only that
     if (fresh) {
       CU(cudaMemsetAsync(e->d_accum, 0, need, e->stream));
@@ -1402,6 +1541,7 @@ extern "C" int lfb_set_starburst_aperture(lfb_engine* e, const float* texels, in
   CU(cudaMalloc((void**)&e->d_star_tex, sizeof(float) * (size_t)w * h));
   CU(cudaMemcpy(e->d_star_tex, texels, sizeof(float) * (size_t)w * h, cudaMemcpyHostToDevice));
   e->star_w = w; e->star_h = h; e->star_total = total;
+  e->star_spectrum_valid = false;
   memcpy(e->star_bbox, bb, sizeof(bb));
   return LFB_OK;
 }
@@ -1445,14 +1585,20 @@ int starburst_device(lfb_engine* e, const lfb_light* lights, int n_lights, int w
     L[5 * l + 1] = lights[l].ns_y * (double)height;
     for (int c = 0; c < 3; c++) { L[5 * l + 2 + c] = lights[l].radiance[c]; rad_sum[c] += lights[l].radiance[c]; }
   }
+  if (starburst_scratch_bytes(f) > e->star_scratch_cap) e->star_spectrum_valid = false;  // the scratch buffer is about to move
   int rc = grow(&e->d_star_scratch, &e->star_scratch_cap, starburst_scratch_bytes(f));
   if (rc) return rc;
+  // both axes on the periodic lattice: |F| depends on the mask alone -- computed once per mask, then only the pixel kernel runs
+  const bool cacheable = f.herm && e->opt.starburst_cache >= 0;
+  const bool cached = cacheable && e->star_spectrum_valid && e->star_spectrum_period == f.period;
   rc = grow(&e->d_star_lights, &e->star_lights_cap, sizeof(double) * L.size());
   if (rc) return rc;
   CU(cudaMemcpyAsync(e->d_star_lights, L.data(), sizeof(double) * L.size(), cudaMemcpyHostToDevice, e->stream));
   int n = 0;
-  CU(launch_starburst(f, e->d_star_tex, e->d_star_scratch, e->d_star_lights, n_lights, rad_sum, out_dev, stride, elem, additive, e->stream, &n));
+  CU(launch_starburst(f, e->d_star_tex, e->d_star_scratch, e->d_star_lights, n_lights, rad_sum, out_dev, stride, elem, additive, cached, e->stream, &n));
   e->launches += (uint64_t)n;
+  e->star_spectrum_valid = cacheable;
+  e->star_spectrum_period = f.period;
   return LFB_OK;
 }
 }  // namespace
@@ -1511,6 +1657,7 @@ extern "C" int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, in
   } else {
     rc = grow(&e->d_accum, &e->accum_cap, lfb_accum_bytes(P->width, P->height));
     if (rc) return rc;
+    e->accum_clean = false;
     e->accum_dirty_w = e->accum_dirty_h = 0;
     rc = render_grid_device(e, lights, n_lights, *P, e->d_accum, 1);
     if (rc) return rc;
@@ -1529,6 +1676,215 @@ extern "C" int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, in
   CU(cudaStreamSynchronize(e->stream));
   CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
   CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
+  return LFB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// single-process multi-GPU
+// ---------------------------------------------------------------------------
+struct lfb_multi {
+  int n = 0;
+  lfb_engine* eng[LFB_MAX_PEERS] = {nullptr};
+  unsigned long long* accum[LFB_MAX_PEERS] = {nullptr};  // per device: sums + tile map (peer-accessible)
+  size_t accum_cap = 0;
+  bool accum_clean = false;
+  int accum_w = 0, accum_h = 0;
+  unsigned* state[LFB_MAX_PEERS] = {nullptr};            // per device: its tile state of the caller's buffer
+  size_t state_cap = 0;
+  unsigned* h_count = nullptr;                           // page-locked, portable: tiles written per device
+  cudaEvent_t ev_traced[LFB_MAX_PEERS] = {nullptr}, ev_red0[LFB_MAX_PEERS] = {nullptr}, ev_red1[LFB_MAX_PEERS] = {nullptr};
+  const void* out = nullptr;
+  int out_w = 0, out_h = 0, out_elem = 0;
+  size_t out_stride = 0;
+  float stage_ms[4] = {0, 0, 0, 0};
+};
+
+extern "C" void lfb_destroy_multi(lfb_multi* m) {
+  if (!m) return;
+  for (int d = 0; d < m->n; d++) {
+    if (!m->eng[d]) continue;
+    cudaSetDevice(m->eng[d]->device);
+    cudaStreamSynchronize(m->eng[d]->stream);
+    cudaFree(m->accum[d]); cudaFree(m->state[d]);
+    if (m->ev_traced[d]) cudaEventDestroy(m->ev_traced[d]);
+    if (m->ev_red0[d]) cudaEventDestroy(m->ev_red0[d]);
+    if (m->ev_red1[d]) cudaEventDestroy(m->ev_red1[d]);
+    lfb_destroy(m->eng[d]);
+  }
+  if (m->h_count) cudaFreeHost(m->h_count);
+  delete m;
+}
+
+extern "C" int lfb_create_multi(lfb_multi** out, const int* device_ids, int n_devices, const lfb_options* options) {
+  if (!out) return fail(LFB_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!device_ids || n_devices < 1 || n_devices > LFB_MAX_PEERS) return fail(LFB_ERR_INVALID, "bad device list");
+  for (int a = 0; a < n_devices; a++)
+    for (int b = a + 1; b < n_devices; b++)
+      if (device_ids[a] == device_ids[b]) return fail(LFB_ERR_INVALID, "a device is listed twice");
+  lfb_multi* m = new (std::nothrow) lfb_multi();
+  if (!m) return fail(LFB_ERR_NOMEM, "out of host memory");
+  m->n = n_devices;
+  int rc = LFB_OK;
+  for (int d = 0; d < n_devices && rc == LFB_OK; d++) rc = lfb_create_ex(&m->eng[d], device_ids[d], options);
+  for (int d = 0; d < n_devices && rc == LFB_OK; d++) {
+    cudaSetDevice(device_ids[d]);
+    for (int q = 0; q < n_devices; q++) {
+      if (q == d) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, device_ids[d], device_ids[q]);
+      if (!can) { rc = fail(LFB_ERR_CUDA, "devices " + std::to_string(device_ids[d]) + " and " + std::to_string(device_ids[q]) + " have no peer access"); break; }
+      const cudaError_t err = cudaDeviceEnablePeerAccess(device_ids[q], 0);
+      if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) { rc = fail_cuda(err, "cudaDeviceEnablePeerAccess"); break; }
+      cudaGetLastError();
+    }
+    if (rc) break;
+    cudaError_t err = cudaEventCreateWithFlags(&m->ev_traced[d], cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreate(&m->ev_red0[d]);
+    if (err == cudaSuccess) err = cudaEventCreate(&m->ev_red1[d]);
+    if (err != cudaSuccess) rc = fail_cuda(err, "cudaEventCreate");
+  }
+  if (rc == LFB_OK && cudaHostAlloc((void**)&m->h_count, sizeof(unsigned) * LFB_MAX_PEERS, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess)
+    rc = fail(LFB_ERR_NOMEM, "cudaHostAlloc");
+  if (rc) { const std::string keep = g_err; lfb_destroy_multi(m); g_err = keep; return rc; }
+  *out = m;
+  return LFB_OK;
+}
+
+extern "C" int lfb_multi_set_lens(lfb_multi* m, const lfb_lens* lens) {
+  if (!m) return fail(LFB_ERR_INVALID, "multi engine is NULL");
+  for (int d = 0; d < m->n; d++) {
+    const int rc = lfb_set_lens(m->eng[d], lens);
+    if (rc) return rc;
+  }
+  return LFB_OK;
+}
+
+extern "C" int lfb_multi_set_aperture(lfb_multi* m, const float* texels, int w, int h) {
+  if (!m) return fail(LFB_ERR_INVALID, "multi engine is NULL");
+  for (int d = 0; d < m->n; d++) {
+    const int rc = lfb_set_aperture(m->eng[d], texels, w, h);
+    if (rc) return rc;
+  }
+  return LFB_OK;
+}
+
+extern "C" int lfb_render_ghosts_multi(lfb_multi* m, const lfb_light* lights, int n_lights, const lfb_params* P, void* out, size_t stride,
+                                       int elem, int out_is_clear, int* tiles_written) {
+  if (!m) return fail(LFB_ERR_INVALID, "multi engine is NULL");
+  int rc = check_params(P, true);
+  if (rc) return rc;
+  if (n_lights < 0 || (n_lights > 0 && !lights)) return fail(LFB_ERR_INVALID, "bad lights");
+  rc = check_out_args(out, stride, elem);
+  if (rc) return rc;
+  for (int d = 0; d < m->n; d++)
+    if (!m->eng[d]->has_lens || !m->eng[d]->has_tex) return fail(LFB_ERR_STATE, "set the lens and the aperture first");
+  if (tiles_written) *tiles_written = 0;
+  const int W = P->width, H = P->height, n = m->n;
+  const bool same = out == m->out && W == m->out_w && H == m->out_h && stride == m->out_stride && elem == m->out_elem;
+  if (!out_is_clear && !same) return fail(LFB_ERR_STATE, "lfb_render_ghosts_multi: `out` is not the buffer of the previous call; pass out_is_clear = 1 with a zeroed buffer");
+  const auto host_t0 = std::chrono::steady_clock::now();
+  // the caller's buffer as every device sees it (page-locked + mapped), or the fallback: device 0's own frame, copied whole
+  void* out_dev[LFB_MAX_PEERS];
+  bool zero_copy = true;
+  for (int d = 0; d < n; d++) {
+    CU(cudaSetDevice(m->eng[d]->device));
+    out_dev[d] = nullptr;
+    if (cudaHostGetDevicePointer(&out_dev[d], out, 0) != cudaSuccess || !out_dev[d]) { cudaGetLastError(); zero_copy = false; break; }
+  }
+  const AccumLayout lay = accum_layout(W, H);
+  const size_t st_bytes = tile_state_bytes(W, H);
+  lfb_engine* e0 = m->eng[0];
+  if (!zero_copy) {  // the reduce writes a device-0 frame that is then copied whole: the engine keeps that frame's tile state
+    CU(cudaSetDevice(e0->device));
+    rc = grow(&e0->d_out, &e0->out_cap, ((size_t)W * H - 1) * stride + elem_bytes(elem));
+    if (rc) return rc;
+  }
+  const bool fresh_state = out_is_clear || !same || st_bytes > m->state_cap || !zero_copy;
+  const bool fresh_accum = lay.total > m->accum_cap || !(m->accum_clean && m->accum_w == W && m->accum_h == H);
+  for (int d = 0; d < n; d++) {
+    lfb_engine* e = m->eng[d];
+    CU(cudaSetDevice(e->device));
+    if (lay.total > m->accum_cap) {
+      cudaFree(m->accum[d]);
+      m->accum[d] = nullptr;
+      if (cudaMalloc((void**)&m->accum[d], lay.total) != cudaSuccess) { cudaGetLastError(); return fail(LFB_ERR_NOMEM, "cudaMalloc: out of device memory"); }
+    }
+    if (st_bytes > m->state_cap) {
+      cudaFree(m->state[d]);
+      m->state[d] = nullptr;
+      if (cudaMalloc((void**)&m->state[d], st_bytes) != cudaSuccess) { cudaGetLastError(); return fail(LFB_ERR_NOMEM, "cudaMalloc: out of device memory"); }
+    }
+    if (fresh_accum) CU(cudaMemsetAsync(m->accum[d], 0, lay.total, e->stream));
+    if (fresh_state) CU(cudaMemsetAsync(m->state[d], 0, st_bytes, e->stream));
+  }
+  m->accum_cap = std::max(m->accum_cap, lay.total);
+  m->state_cap = std::max(m->state_cap, st_bytes);
+  m->accum_clean = false;
+  if (!zero_copy) CU(cudaMemsetAsync(e0->d_out, 0, ((size_t)W * H - 1) * stride + elem_bytes(elem), e0->stream));
+  m->out = out; m->out_w = W; m->out_h = H; m->out_stride = stride; m->out_elem = elem;
+  // stage 1: every device traces its shard
+  for (int d = 0; d < n; d++) {
+    lfb_engine* e = m->eng[d];
+    CU(cudaSetDevice(e->device));
+    lfb_params Pd = *P;
+    Pd.shard_index = n > 1 ? d : 0; Pd.shard_count = n > 1 ? n : 0;
+    rc = render_grid_device(e, lights, n_lights, Pd, m->accum[d], 0);
+    if (rc) return rc;
+    CU(cudaEventRecord(m->ev_traced[d], e->stream));
+  }
+  // stage 2: every device reduces its interleaved share of the dirty tiles over peer memory, once all traces are done
+  PeerAccums A;
+  memset(&A, 0, sizeof(A));
+  A.n = n;
+  for (int d = 0; d < n; d++) A.ptr[d] = m->accum[d];
+  const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+  for (int d = 0; d < n; d++) {
+    lfb_engine* e = m->eng[d];
+    CU(cudaSetDevice(e->device));
+    for (int q = 0; q < n; q++)
+      if (q != d) CU(cudaStreamWaitEvent(e->stream, m->ev_traced[q], 0));
+    unsigned* count_dev = nullptr;
+    CU(cudaHostGetDevicePointer((void**)&count_dev, m->h_count + d, 0));
+    CU(cudaEventRecord(m->ev_red0[d], e->stream));
+    CU(launch_tiles(A, d, W, H, inv, zero_copy ? out_dev[d] : (void*)e0->d_out, stride, elem, m->state[d], count_dev, e->opt.reduce_ctas, e->stream));
+    e->launches++;
+    CU(cudaEventRecord(m->ev_red1[d], e->stream));
+  }
+  const auto host_t1 = std::chrono::steady_clock::now();
+  for (int d = 0; d < n; d++) {
+    CU(cudaSetDevice(m->eng[d]->device));
+    CU(cudaStreamSynchronize(m->eng[d]->stream));
+  }
+  if (!zero_copy) {
+    CU(cudaSetDevice(e0->device));
+    CU(cudaMemcpy(out, e0->d_out, ((size_t)W * H - 1) * stride + elem_bytes(elem), cudaMemcpyDeviceToHost));
+    m->out = nullptr;  // every pixel was rewritten: nothing to remember
+  }
+  const auto host_t2 = std::chrono::steady_clock::now();
+  m->accum_clean = true; m->accum_w = W; m->accum_h = H;
+  int total = 0;
+  float t_trace = 0, t_red = 0;
+  for (int d = 0; d < n; d++) {
+    total += (int)m->h_count[d];
+    float a = 0, b = 0;
+    CU(cudaSetDevice(m->eng[d]->device));
+    cudaEventElapsedTime(&a, m->eng[d]->ev_trace0, m->eng[d]->ev_trace1);
+    cudaEventElapsedTime(&b, m->ev_red0[d], m->ev_red1[d]);
+    cudaGetLastError();
+    t_trace = std::max(t_trace, a); t_red = std::max(t_red, b);
+  }
+  m->stage_ms[0] = t_trace; m->stage_ms[1] = t_red;
+  m->stage_ms[2] = std::chrono::duration<float, std::milli>(host_t2 - host_t0).count();
+  m->stage_ms[3] = std::chrono::duration<float, std::milli>(host_t1 - host_t0).count();
+  if (tiles_written) *tiles_written = zero_copy ? total : -1;
+  return LFB_OK;
+}
+
+extern "C" int lfb_multi_stats(lfb_multi* m, float stage_ms[4], int* n_devices) {
+  if (!m) return fail(LFB_ERR_INVALID, "multi engine is NULL");
+  if (stage_ms) memcpy(stage_ms, m->stage_ms, sizeof(m->stage_ms));
+  if (n_devices) *n_devices = m->n;
   return LFB_OK;
 }
 
@@ -1616,9 +1972,15 @@ extern "C" void lfb_host_free(void* p) {
 
 extern "C" int lfb_host_register(void* p, size_t bytes) {
   if (!p || bytes == 0) return fail(LFB_ERR_INVALID, "lfb_host_register: empty range");
-  const cudaError_t rc = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  const cudaError_t rc = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
   if (rc != cudaSuccess) { cudaGetLastError(); return fail(LFB_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(rc)); }
   return LFB_OK;
+}
+
+extern "C" void* lfb_host_device_pointer(void* p) {
+  void* d = nullptr;
+  if (!p || cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return d;
 }
 
 extern "C" int lfb_host_unregister(void* p) {

@@ -10,15 +10,15 @@ cudaError_t launch_exact_prefix<float>(const Job* slots, const StepT<float>* pro
   return xt::launch_prefix_t<float>(slots, progs, n_slots, g, tex, prefix, accum_for_direct, stats, s);
 }
 template <>
-cudaError_t launch_exact_ghosts<float>(const Job* jobs, const StepT<float>* progs, int n_jobs, const FrameGeom& g, const float* tex,
-                                     unsigned long long* accum, int ctas_per_sm, bool stats, cudaStream_t s) {
-  return xt::launch_ghosts_t<float>(jobs, progs, n_jobs, g, tex, accum, ctas_per_sm, stats, s);
+cudaError_t launch_exact_ghosts<float>(const Job* jobs, const StepT<float>* progs, const unsigned* heads, int n_jobs, const FrameGeom& g,
+                                     const float* tex, unsigned long long* accum, int ctas_per_sm, bool stats, cudaStream_t s) {
+  return xt::launch_ghosts_t<float>(jobs, progs, heads, n_jobs, g, tex, accum, ctas_per_sm, stats, s);
 }
 template <>
-cudaError_t launch_exact_families<float>(const Job* fams, const StepT<float>* fam_progs, int n_fams, const Job* slots,
+cudaError_t launch_exact_families<float>(const Job* fams, const StepT<float>* fam_progs, const unsigned* heads, int n_fams, const Job* slots,
                                        const StepT<float>* slot_progs, const FrameGeom& g, const float* tex, unsigned long long* accum,
-                                       bool stats, cudaStream_t s) {
-  return xt::launch_families_t<float>(fams, fam_progs, n_fams, slots, slot_progs, g, tex, accum, stats, s);
+                                       int ctas_per_sm, bool stats, cudaStream_t s) {
+  return xt::launch_families_t<float>(fams, fam_progs, heads, n_fams, slots, slot_progs, g, tex, accum, ctas_per_sm, stats, s);
 }
 template <>
 cudaError_t launch_exact_dump<float>(const Job* job, const StepT<float>* prog, const FrameGeom& g, const float* tex, lfb_ray_hit* out,

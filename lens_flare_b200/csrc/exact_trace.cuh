@@ -30,8 +30,8 @@
 //    to a 64-pixel u64 fixed-point tile per warp in shared memory and each touched pixel is flushed with one global atomic
 //    (direct global atomics when the footprint exceeds the tile).  The only CTA barrier is the one after staging the
 //    program.  Integer accumulation keeps the frame bit-stable for any schedule, kernel or GPU count.
-//  * DIRTY TILES.  Every flush marks the 16 x 16 sensor tiles it touches in a bitmap (read first, atomicOr only when the
-//    bit is clear), so that finalize / read-back / the cross-GPU reduce visit the ~1 % of the frame that is not zero.
+//  * DIRTY TILES.  Every flush marks the 16 x 16 sensor tiles it touches in a byte map (one plain store per tile: no read,
+//    no atomic), so that finalize / read-back / the cross-GPU reduce visit the ~1 % of the frame that is not zero.
 //
 // Kernels: prefix_kernel (forward sweeps + the direct path), ghost_kernel (one job per ghost pair), family_kernel (one
 // thread follows every ghost sharing a first reflection; forks at each second reflection), dump_kernel (per-ray records).
@@ -39,6 +39,7 @@
 // kernels in ghost_grid_impl.cuh remain the oracle-order, bit-exact instruments.
 #pragma once
 #include <math_constants.h>
+#include <string.h>
 
 #include "lfb_internal.h"
 
@@ -146,8 +147,8 @@ __device__ __forceinline__ float reflectance_lut(const float2* __restrict__ lut,
 
 // The factor a step multiplies the weight by: the step's polynomial (Estrin: depth 4) on v >= kPolyV0, else the table.
 template <typename T>
-__device__ __forceinline__ float weight_factor(const StepT<T>& S, bool refl, const float2* __restrict__ lut, float v) {
-  if (v >= kPolyV0) {
+__device__ __forceinline__ float weight_factor(const StepT<T>& S, bool refl, const float2* __restrict__ lut, float v0, float v) {
+  if (v >= v0) {
     const float x = fmaf(-v, kPolyScale, kPolyScale);  // (1 - v) / (1 - v0) in [0, 1]
     const float x2 = x * x, x4 = x2 * x2;
     const float a = fmaf(S.p[1], x, S.p[0]), b = fmaf(S.p[3], x, S.p[2]), c = fmaf(S.p[5], x, S.p[4]), d = fmaf(S.p[7], x, S.p[6]);
@@ -196,7 +197,7 @@ __device__ __forceinline__ bool propagate(const StepT<T>& S, RayState<T>& r, Ray
 //   FLAGS   parity-instrument variant: classify the death, and let rays the mask stopped continue with weight 0 so that
 //           their positions stay comparable with the oracle
 template <typename T, bool MIRROR, bool FLAGS>
-__device__ __forceinline__ bool interact(const StepT<T>& S, const MaskGeom& K, const float2* __restrict__ lut, RayState<T>& r, RayDiag& o) {
+__device__ __forceinline__ bool interact(const StepT<T>& S, const MaskGeom& K, const FrameGeom& g, RayState<T>& r, RayDiag& o) {
   typedef M<T> m;
   const int op = S.op;
   if (op >= STEP_PASS) {  // no change of direction: identical media, the stop, the sensor
@@ -219,10 +220,10 @@ __device__ __forceinline__ bool interact(const StepT<T>& S, const MaskGeom& K, c
   const bool refl = op == STEP_REFLECT;
   if (FLAGS && !refl && k2 < (T)0) { o.flags |= LFB_RAY_TIR; return false; }
   // refract: d' = eta d + (eta c0 - c2) N with N = -sign(nd) n the normal facing the ray;  reflect: d' = d - 2 nd n
-  const T g = m::flip_unless_neg(m::fma(eta, c0, -c2), nd);
-  const T alpha = refl ? (T)1 : eta, beta = refl ? (T)-2 * nd : g;
+  const T gg = m::flip_unless_neg(m::fma(eta, c0, -c2), nd);
+  const T alpha = refl ? (T)1 : eta, beta = refl ? (T)-2 * nd : gg;
   r.dx = m::fma(alpha, r.dx, beta * nx); r.dy = m::fma(alpha, r.dy, beta * ny); r.dz = m::fma(alpha, r.dz, beta * nz);
-  r.w *= weight_factor<T>(S, refl, lut, (float)(eta > (T)1 ? c2 : c0));
+  r.w *= weight_factor<T>(S, refl, g.lut, g.poly_v0, (float)(eta > (T)1 ? c2 : c0));
   return true;
 }
 
@@ -266,26 +267,34 @@ __device__ __forceinline__ void grid_point<float>(const FrameGeom& g, int a, int
 template <typename T> struct PrefixIO;
 template <> struct PrefixIO<float> {
   static constexpr int kParts = 2;
+  struct Raw { float4 a, b; };  // a cached state as loaded: nothing is decoded (no instruction waits on the loads) until take()
   static __device__ __forceinline__ void store(float4* dst, size_t hr, const RayState<float>& r) {
     dst[0] = make_float4(r.ox, r.oy, r.oz, r.w);
     dst[hr] = make_float4(r.dx, r.dy, r.ma, r.mb);
   }
-  static __device__ __forceinline__ void store_dead(float4* dst, size_t) { dst[0] = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ void store_dead(float4* dst, size_t hr) {
+    dst[0] = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+  }
   static __device__ __forceinline__ void canon(RayState<float>& r) {
     r.dz = M<float>::sqrt(fmaxf(fmaf(-r.dx, r.dx, fmaf(-r.dy, r.dy, 1.f)), 0.f));
   }
-  static __device__ __forceinline__ bool load(const float4* __restrict__ src, size_t hr, RayState<float>& r) {
-    const float4 s0 = __ldg(src);
-    if (!(s0.x == s0.x)) return false;  // NaN: the ray died in the forward sweep before reaching this surface
-    const float4 s1 = __ldg(src + hr);
-    r.ox = s0.x; r.oy = s0.y; r.oz = s0.z; r.w = s0.w;
-    r.dx = s1.x; r.dy = s1.y; r.ma = s1.z; r.mb = s1.w;
+  static __device__ __forceinline__ Raw issue(const float4* __restrict__ src, size_t hr) {
+    Raw q;
+    q.a = __ldg(src);
+    q.b = __ldg(src + hr);  // unconditionally: a dead ray's second part is stale, never used
+    return q;
+  }
+  static __device__ __forceinline__ bool take(const Raw& q, RayState<float>& r) {
+    if (!(q.a.x == q.a.x)) return false;  // NaN: the ray died in the forward sweep before reaching this surface
+    r.ox = q.a.x; r.oy = q.a.y; r.oz = q.a.z; r.w = q.a.w;
+    r.dx = q.b.x; r.dy = q.b.y; r.ma = q.b.z; r.mb = q.b.w;
     canon(r);
     return true;
   }
 };
 template <> struct PrefixIO<double> {
   static constexpr int kParts = 4;
+  struct Raw { double2 a, b, c; float4 w; };
   static __device__ __forceinline__ void store(float4* dst, size_t hr, const RayState<double>& r) {
     double2* d = reinterpret_cast<double2*>(dst);
     d[0] = make_double2(r.ox, r.oy);
@@ -297,14 +306,17 @@ template <> struct PrefixIO<double> {
     reinterpret_cast<double2*>(dst)[0] = make_double2(CUDART_NAN, 0.0);
   }
   static __device__ __forceinline__ void canon(RayState<double>&) {}
-  static __device__ __forceinline__ bool load(const float4* __restrict__ src, size_t hr, RayState<double>& r) {
+  static __device__ __forceinline__ Raw issue(const float4* __restrict__ src, size_t hr) {
     const double2* s = reinterpret_cast<const double2*>(src);
-    const double2 a = __ldg(s);
-    if (!(a.x == a.x)) return false;
-    const double2 b = __ldg(s + hr), c = __ldg(s + 2 * hr);
-    const float4 w = __ldg(src + 3 * hr);
-    r.ox = a.x; r.oy = a.y; r.oz = b.x; r.dx = b.y; r.dy = c.x; r.dz = c.y;
-    r.w = w.x; r.ma = w.y; r.mb = w.z;
+    Raw q;
+    q.a = __ldg(s); q.b = __ldg(s + hr); q.c = __ldg(s + 2 * hr);
+    q.w = __ldg(src + 3 * hr);
+    return q;
+  }
+  static __device__ __forceinline__ bool take(const Raw& q, RayState<double>& r) {
+    if (!(q.a.x == q.a.x)) return false;
+    r.ox = q.a.x; r.oy = q.a.y; r.oz = q.b.x; r.dx = q.b.y; r.dy = q.c.x; r.dz = q.c.y;
+    r.w = q.w.x; r.ma = q.w.y; r.mb = q.w.z;
     return true;
   }
 };
@@ -368,9 +380,21 @@ struct WarpSplat {  // what a warp needs to deposit its lanes' results
         ch1(J.f_chan[1]), ch2(J.f_chan[2]), bilinear(g.splat == LFB_SPLAT_BILINEAR) {}
 };
 
-// The pixels of one tap into the shared-memory tile (origin (tx0, ty0), row pitch tw) or straight into the accumulators.
-// Explicit roundings: no FMA contraction, so every instantiation of every kernel produces the same bits.
-__device__ __forceinline__ void splat_tap(const WarpSplat& S, unsigned long long* tile, int tx0, int ty0, int tw, const Tap& t, float w) {
+// Shared-memory accesses of the per-warp tile by 32-bit shared address: the tile pointer travels through structs and
+// selects, where the compiler loses the address space and would emit generic loads / atomics (L1TEX path, long scoreboard).
+__device__ __forceinline__ void sts_u64(unsigned addr, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long lds_u64(unsigned addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void reds_add_u64(unsigned addr, unsigned long long v) { asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+__device__ __forceinline__ void redg_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+// The pixels of one tap into the warp's shared-memory tile (TILE: origin (tx0, ty0), row pitch tw) or straight into the
+// accumulators.  Explicit roundings: no FMA contraction, so every instantiation of every kernel produces the same bits.
+template <bool TILE>
+__device__ __forceinline__ void splat_tap(const WarpSplat& S, unsigned tile, int tx0, int ty0, int tw, const Tap& t, float w) {
   float wt[4];
   if (S.bilinear) {
     const float gx = __fsub_rn(1.f, t.fx), gy = __fsub_rn(1.f, t.fy);
@@ -383,12 +407,22 @@ __device__ __forceinline__ void splat_tap(const WarpSplat& S, unsigned long long
   for (int q = 0; q < 4; q++) {
     const int jx = t.ix + (q & 1), jy = t.iy + (q >> 1);
     if (wt[q] == 0.f || jx < 0 || jx >= S.W || jy < 0 || jy >= S.H) continue;
-    unsigned long long* dst = tile ? tile + 3 * ((jy - ty0) * tw + (jx - tx0)) : S.accum + 3 * ((size_t)jx + (size_t)jy * S.W);
-    if (!tile && S.tile_bits) mark_tile(S.tile_bits, S.tiles_w, jx >> kTilePxLog2, jy >> kTilePxLog2);
     // channels a wavelength does not feed (RGB lenses: two of three) are skipped without converting anything
-    if (S.ch0 != 0.f) { const long long v = __float2ll_rn(__fmul_rn(wt[q], S.ch0)); if (v) atomicAdd(dst + 0, (unsigned long long)v); }
-    if (S.ch1 != 0.f) { const long long v = __float2ll_rn(__fmul_rn(wt[q], S.ch1)); if (v) atomicAdd(dst + 1, (unsigned long long)v); }
-    if (S.ch2 != 0.f) { const long long v = __float2ll_rn(__fmul_rn(wt[q], S.ch2)); if (v) atomicAdd(dst + 2, (unsigned long long)v); }
+    const long long v0 = S.ch0 != 0.f ? __float2ll_rn(__fmul_rn(wt[q], S.ch0)) : 0ll;
+    const long long v1 = S.ch1 != 0.f ? __float2ll_rn(__fmul_rn(wt[q], S.ch1)) : 0ll;
+    const long long v2 = S.ch2 != 0.f ? __float2ll_rn(__fmul_rn(wt[q], S.ch2)) : 0ll;
+    if (TILE) {
+      const unsigned dst = tile + 24u * (unsigned)((jy - ty0) * tw + (jx - tx0));
+      if (v0) reds_add_u64(dst, (unsigned long long)v0);
+      if (v1) reds_add_u64(dst + 8, (unsigned long long)v1);
+      if (v2) reds_add_u64(dst + 16, (unsigned long long)v2);
+    } else {
+      unsigned long long* dst = S.accum + 3 * ((size_t)jx + (size_t)jy * S.W);
+      if (S.tile_bits) mark_tile(S.tile_bits, S.tiles_w, jx >> kTilePxLog2, jy >> kTilePxLog2);
+      if (v0) redg_add_u64(dst, (unsigned long long)v0);
+      if (v1) redg_add_u64(dst + 1, (unsigned long long)v1);
+      if (v2) redg_add_u64(dst + 2, (unsigned long long)v2);
+    }
   }
 }
 
@@ -432,22 +466,31 @@ __device__ __forceinline__ bool warp_land(const WarpSplat& S, const JobC<T>& J, 
   if (lane == 0) grow_bbox(S.bbox, bx0, by0, bx1, by1);
   const int tw = bx1 - bx0 + 1;
   const int area = tw * (by1 - by0 + 1);
-  const bool use_tile = area <= kWarpTilePx;
-  unsigned long long* tile = use_tile ? S.tile : nullptr;
-  if (use_tile) {
-    for (int q = lane; q < 3 * area; q += 32) tile[q] = 0ull;
-    if (S.tile_bits) {  // the tiles under the warp's footprint (a 64-pixel box spans at most 5 x 1 or 2 x 2 ... tiles)
-      const int tx0 = bx0 >> kTilePxLog2, ty0 = by0 >> kTilePxLog2;
-      const int ntx = (bx1 >> kTilePxLog2) - tx0 + 1, nty = (by1 >> kTilePxLog2) - ty0 + 1;
-      for (int q = lane; q < ntx * nty; q += 32) mark_tile(S.tile_bits, S.tiles_w, tx0 + q % ntx, ty0 + q / ntx);
+  if (area > kWarpTilePx) {  // (uniform) the footprint exceeds the tile: straight to the accumulators
+    if (lands) {
+      if (w0 > 0.f) splat_tap<false>(S, 0u, bx0, by0, tw, ta, w0);
+      if (w1 > 0.f) splat_tap<false>(S, 0u, bx0, by0, tw, tb, w1);
     }
-    __syncwarp();
+    return lands;
   }
+  const unsigned tile = (unsigned)__cvta_generic_to_shared(S.tile);
+  // the dirty-tile bytes under the warp's footprint (a box of <= 64 pixels spans at most 5 x 1 ... 2 x 2 ... 1 x 5 tiles: lanes
+  // 0 .. 29 take a 6 x 5 patch): LOOK now, store after the splat, so that nothing waits for the look
+  unsigned char* mark = nullptr;
+  unsigned seen = 1;
+  if (S.tile_bits) {
+    const int tx = (bx0 >> kTilePxLog2) + lane % 6, ty = (by0 >> kTilePxLog2) + lane / 6;
+    if (tx <= (bx1 >> kTilePxLog2) && ty <= (by1 >> kTilePxLog2)) {
+      mark = tile_byte(S.tile_bits, S.tiles_w, tx, ty);
+      seen = tile_peek(mark);
+    }
+  }
+  for (int q = lane; q < 3 * area; q += 32) sts_u64(tile + 8u * (unsigned)q, 0ull);
+  __syncwarp();
   if (lands) {
-    if (w0 > 0.f) splat_tap(S, tile, bx0, by0, tw, ta, w0);
-    if (w1 > 0.f) splat_tap(S, tile, bx0, by0, tw, tb, w1);
+    if (w0 > 0.f) splat_tap<true>(S, tile, bx0, by0, tw, ta, w0);
+    if (w1 > 0.f) splat_tap<true>(S, tile, bx0, by0, tw, tb, w1);
   }
-  if (!use_tile) return lands;
   __syncwarp();
   const float inv_tw = M<float>::rcp((float)tw);
   for (int t = lane; t < area; t += 32) {
@@ -456,10 +499,11 @@ __device__ __forceinline__ bool warp_land(const WarpSplat& S, const JobC<T>& J, 
     unsigned long long* dst = S.accum + 3 * ((size_t)(bx0 + jx) + (size_t)(by0 + jy) * S.W);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      const unsigned long long v = tile[3 * t + c];
-      if (v) atomicAdd(dst + c, v);
+      const unsigned long long v = lds_u64(tile + 8u * (unsigned)(3 * t + c));
+      if (v) redg_add_u64(dst + c, v);
     }
   }
+  if (!seen) *mark = 1;
   __syncwarp();  // the tile is reused by the warp's next landing
   return lands;
 }
@@ -482,6 +526,28 @@ __device__ __forceinline__ void stage_program(StepT<T>* dst, const StepT<T>* __r
   const float4* s = reinterpret_cast<const float4*>(src);
   float4* d = reinterpret_cast<float4*>(dst);
   for (int q = tid; q < n_steps * W16; q += nthreads) d[q] = __ldg(s + q);
+}
+
+// Two-phase staging for the ghost / family kernels: the program's 16-byte words are requested into registers first (at most
+// two per thread: LFB_MAX_STEPS * sizeof(StepD) / 16 = 250 <= 2 * 128), other loads are issued, and only then are they
+// committed to shared memory -- so the wait for the program overlaps the wait for the job header and the ray state.
+struct Staged { float4 w0, w1; };
+template <typename T, int BT>
+__device__ __forceinline__ Staged stage_issue(const StepT<T>* __restrict__ src, int n_steps, int tid) {
+  static_assert(LFB_MAX_STEPS * (sizeof(StepT<T>) / 16) <= 2 * BT, "two staged words per thread");
+  const int nq = n_steps * (int)(sizeof(StepT<T>) / 16);
+  const float4* s = reinterpret_cast<const float4*>(src);
+  Staged q;
+  if (tid < nq) q.w0 = __ldg(s + tid);
+  if (tid + BT < nq) q.w1 = __ldg(s + tid + BT);
+  return q;
+}
+template <typename T, int BT>
+__device__ __forceinline__ void stage_commit(StepT<T>* dst, const Staged& q, int n_steps, int tid) {
+  const int nq = n_steps * (int)(sizeof(StepT<T>) / 16);
+  float4* d = reinterpret_cast<float4*>(dst);
+  if (tid < nq) d[tid] = q.w0;
+  if (tid + BT < nq) d[tid + BT] = q.w1;
 }
 
 constexpr int kPrefixThreads = 256;
@@ -527,7 +593,7 @@ __global__ void __launch_bounds__(kPrefixThreads) prefix_kernel(const Job* __res
       if (alive) io::store(dst, hr, r);
       else io::store_dead(dst, hr);
     }
-    if (alive) alive = interact<T, true, false>(S, K, g.lut, r, o);
+    if (alive) alive = interact<T, true, false>(S, K, g, r, o);
   }
   bool landed = false;
   if (do_direct) {  // the direct path: on to the sensor plane and splat, one warp at a time
@@ -541,71 +607,71 @@ __global__ void __launch_bounds__(kPrefixThreads) prefix_kernel(const Job* __res
 // ---------------------------------------------------------------------------------------------------------------
 // GHOST KERNEL: one job per ghost pair (i, j).  BT threads = 16 x BT/16 ray pairs of the upper half grid.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, bool STATS>
-__device__ __forceinline__ void ghost_body(const Job& J, const StepT<T>* __restrict__ s_prog, const FrameGeom& g, const float* __restrict__ tex,
-                                           unsigned long long* tile, unsigned long long* __restrict__ accum, int a, int bp, int lane,
-                                           unsigned& n_exec, bool& started, bool& landed) {
-  typedef PrefixIO<T> io;
-  const int half_rows = (g.N + 1) / 2;
-  const int n_steps = J.n_steps;
-  const MaskGeom K(g, tex);
-  const JobC<T> JC(J);
-  const int b = g.N - 1 - bp;
-  RayState<T> r;
-  RayDiag o;
-  bool alive = false;
-  if (a < g.N && bp < half_rows) {
-    started = true;
-    int s = 0;
-    if (J.slot >= 0) {  // (uniform) the state ON the first-reflection surface comes from the prefix cache
-      const size_t hr = (size_t)g.half_rays;
-      const float4* src = g.prefix + ((size_t)(J.slot * g.n_surf + J.j_first) * io::kParts) * hr + ((size_t)bp * g.N + a);
-      alive = io::load(src, hr, r);
-      if (alive) alive = interact<T, true, false>(s_prog[0], K, g.lut, r, o);
-      s = 1;
-    } else {  // no cache (the direct path, or the cache is over its memory budget): from the entrance grid
-      T x, y;
-      grid_point<T>(g, a, b, x, y);
-      start_ray<T>(r, x, y, JC);
-      alive = true;
-      const int jc = J.i < 0 ? -1 : J.j_first;  // the step at which a cached state would have been loaded
-#pragma unroll 1
-      for (; alive && s <= jc; s++) {
-        const StepT<T>& S = s_prog[s];
-        alive = propagate<T, false>(S, r, o);
-        if (STATS) n_exec++;
-        if (alive && s == jc) io::canon(r);
-        if (alive) alive = interact<T, true, false>(S, K, g.lut, r, o);
-      }
-    }
-#pragma unroll 1
-    for (; alive && s < n_steps; s++) {
-      const StepT<T>& S = s_prog[s];
-      alive = propagate<T, false>(S, r, o);
-      if (STATS) n_exec++;
-      if (alive) alive = interact<T, true, false>(S, K, g.lut, r, o);
-    }
-  }
-  const WarpSplat WS(g, J, tile, accum);
-  landed = warp_land<T>(WS, JC, alive, r.ox, r.oy, r.w * r.ma, r.w * r.mb, b != bp, lane);
-}
-
 template <typename T, int MINB, int BT, bool STATS>
-__global__ void __launch_bounds__(BT, MINB) ghost_kernel(const Job* __restrict__ jobs, const StepT<T>* __restrict__ progs, FrameGeom g,
-                                                         const float* __restrict__ tex, unsigned long long* __restrict__ accum) {
+__global__ void __launch_bounds__(BT, MINB) ghost_kernel(const Job* __restrict__ jobs, const StepT<T>* __restrict__ progs,
+                                                         const __grid_constant__ JobHeads heads, FrameGeom g, const float* __restrict__ tex,
+                                                         unsigned long long* __restrict__ accum) {
+  typedef PrefixIO<T> io;
   constexpr int PH = BT / 16;
   __shared__ __align__(16) StepT<T> s_prog[LFB_MAX_STEPS];
   __shared__ unsigned long long s_tile[(BT / 32) * kWarpTilePx * 3];
   // 3-D grid (patch column, patch row, job): no integer divisions in the prologue every warp pays
   const Job& J = jobs[blockIdx.z];
-  const int tid = threadIdx.x;
-  stage_program<T>(s_prog, progs + (size_t)blockIdx.z * LFB_MAX_STEPS, J.n_steps, tid, BT);
-  __syncthreads();  // the only CTA-wide barrier
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int half_rows = (g.N + 1) / 2;
+  const int a = blockIdx.x * 16 + (tid & 15), bp = blockIdx.y * PH + (tid >> 4);
+  const int b = g.N - 1 - bp;
+  const bool in_grid = a < g.N && bp < half_rows;
+  // The job's header comes from the kernel parameters (constant bank), so the program words and the ray's cached state on
+  // the first-reflection surface are requested at once, before the CTA's only barrier; the job's float constants (pixel
+  // mapping, channel weights) are not needed until a ray lands.
+  const unsigned head = heads.h[blockIdx.z];
+  const int slot = (int)(head & 0xffffu) - 1, j_first = (int)((head >> 16) & 31u), n_steps = (int)(head >> 21);
+  const Staged staged = stage_issue<T, BT>(progs + (size_t)blockIdx.z * LFB_MAX_STEPS, n_steps, tid);
+  typename io::Raw raw;
+  const bool cached = slot >= 0 && in_grid;  // (slot: uniform per CTA) the state ON the first-reflection surface comes from the prefix cache
+  if (cached) {
+    const size_t hr = (size_t)g.half_rays;
+    raw = io::issue(g.prefix + ((size_t)(slot * g.n_surf + j_first) * io::kParts) * hr + ((size_t)bp * g.N + a), hr);
+  }
+  stage_commit<T, BT>(s_prog, staged, n_steps, tid);
+  __syncthreads();  // the only CTA-wide barrier; nothing above waits for the state loads
+  const MaskGeom K(g, tex);
+  const JobC<T> JC(J);
+  RayState<T> r;
+  RayDiag o;
+  bool alive = false;
   unsigned n_exec = 0;
-  bool started = false, landed = false;
-  ghost_body<T, STATS>(J, s_prog, g, tex, s_tile + (tid >> 5) * (kWarpTilePx * 3), accum, blockIdx.x * 16 + (tid & 15),
-                       blockIdx.y * PH + (tid >> 4), tid & 31, n_exec, started, landed);
-  if (STATS) flush_stats(g.stats, n_exec, started ? 1u : 0u, landed ? 1u : 0u);
+  int s = 0;
+  if (slot >= 0) {
+    if (cached) alive = io::take(raw, r);
+    if (alive) alive = interact<T, true, false>(s_prog[0], K, g, r, o);
+    s = 1;
+  } else if (in_grid) {  // no cache (the direct path, or the cache is over its memory budget): from the entrance grid
+    T x, y;
+    grid_point<T>(g, a, b, x, y);
+    start_ray<T>(r, x, y, JC);
+    alive = true;
+    const int jc = J.i < 0 ? -1 : j_first;  // the step at which a cached state would have been loaded
+#pragma unroll 1
+    for (; alive && s <= jc; s++) {
+      const StepT<T>& S = s_prog[s];
+      alive = propagate<T, false>(S, r, o);
+      if (STATS) n_exec++;
+      if (alive && s == jc) io::canon(r);
+      if (alive) alive = interact<T, true, false>(S, K, g, r, o);
+    }
+  }
+#pragma unroll 1
+  for (; alive && s < n_steps; s++) {
+    const StepT<T>& S = s_prog[s];
+    alive = propagate<T, false>(S, r, o);
+    if (STATS) n_exec++;
+    if (alive) alive = interact<T, true, false>(S, K, g, r, o);
+  }
+  const WarpSplat WS(g, J, s_tile + (tid >> 5) * (kWarpTilePx * 3), accum);
+  const bool landed = warp_land<T>(WS, JC, alive, r.ox, r.oy, r.w * r.ma, r.w * r.mb, b != bp, lane);
+  if (STATS) flush_stats(g.stats, n_exec, in_grid ? 1u : 0u, landed ? 1u : 0u);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -623,8 +689,9 @@ __global__ void __launch_bounds__(BT, MINB) ghost_kernel(const Job* __restrict__
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MINB, int BT, bool STATS>
 __global__ void __launch_bounds__(BT, MINB) family_kernel(const Job* __restrict__ fams, const StepT<T>* __restrict__ fam_progs,
-                                                          const Job* __restrict__ slots, const StepT<T>* __restrict__ slot_progs, FrameGeom g,
-                                                          const float* __restrict__ tex, unsigned long long* __restrict__ accum) {
+                                                          const __grid_constant__ JobHeads heads, const Job* __restrict__ slots,
+                                                          const StepT<T>* __restrict__ slot_progs, FrameGeom g, const float* __restrict__ tex,
+                                                          unsigned long long* __restrict__ accum) {
   typedef PrefixIO<T> io;
   constexpr int PH = BT / 16;
   __shared__ __align__(16) StepT<T> s_fam[2 * LFB_MAX_SURFACES + 2];
@@ -633,15 +700,25 @@ __global__ void __launch_bounds__(BT, MINB) family_kernel(const Job* __restrict_
 
   const int half_rows = (g.N + 1) / 2;
   const Job& J = fams[blockIdx.z];
-  const int slot = J.slot, j = J.j_first, n_fam = J.n_steps;
+  const unsigned head = heads.h[blockIdx.z];  // from the kernel parameters: no global load before the prologue's loads
+  const int slot = (int)(head & 0xffffu) - 1, j = (int)((head >> 16) & 31u), n_fam = (int)(head >> 21);
   const int n_fwd = g.n_surf + 1;  // forward refractions 0 .. n-1 and the sensor
   const int tid = threadIdx.x, lane = tid & 31;
   const int a = blockIdx.x * 16 + (tid & 15), bp = blockIdx.y * PH + (tid >> 4);
   const int b = g.N - 1 - bp;
   const bool in_grid = a < g.N && bp < half_rows;
-  stage_program<T>(s_fam, fam_progs + (size_t)blockIdx.z * LFB_MAX_STEPS, n_fam, tid, BT);
-  stage_program<T>(s_fwd, slot_progs + (size_t)slot * LFB_MAX_STEPS, n_fwd, tid, BT);
-  __syncthreads();  // the only CTA-wide barrier
+  // both programs and the ray's cached state are requested at once, before the barrier
+  const int n_stage = n_fam;
+  const Staged st_fam = stage_issue<T, BT>(fam_progs + (size_t)blockIdx.z * LFB_MAX_STEPS, n_stage, tid);
+  const Staged st_fwd = stage_issue<T, BT>(slot_progs + (size_t)slot * LFB_MAX_STEPS, n_fwd, tid);
+  typename io::Raw raw;
+  if (in_grid) {
+    const size_t hr = (size_t)g.half_rays;
+    raw = io::issue(g.prefix + ((size_t)(slot * g.n_surf + j) * io::kParts) * hr + ((size_t)bp * g.N + a), hr);
+  }
+  stage_commit<T, BT>(s_fam, st_fam, n_stage, tid);
+  stage_commit<T, BT>(s_fwd, st_fwd, n_fwd, tid);
+  __syncthreads();  // the only CTA-wide barrier; nothing above waits for the state loads
 
   const MaskGeom K(g, tex);
   const JobC<T> JC(J);
@@ -650,12 +727,8 @@ __global__ void __launch_bounds__(BT, MINB) family_kernel(const Job* __restrict_
   RayDiag o;
   bool alive = false;
   unsigned n_exec = 0, n_landed = 0;
-  if (in_grid) {
-    const size_t hr = (size_t)g.half_rays;
-    const float4* src = g.prefix + ((size_t)(slot * g.n_surf + j) * io::kParts) * hr + ((size_t)bp * g.N + a);
-    alive = io::load(src, hr, r);
-    if (alive) alive = interact<T, true, false>(s_fam[0], K, g.lut, r, o);  // the first reflection, at j
-  }
+  if (in_grid) alive = io::take(raw, r);
+  if (alive) alive = interact<T, true, false>(s_fam[0], K, g, r, o);  // the first reflection, at j
   const int n_back = (n_fam - 1) >> 1;  // backward surfaces in this job's program: j-1 .. down to its lowest fork
 #pragma unroll 1
   for (int e = 0; e < n_back && __any_sync(0xffffffffu, alive); e++) {
@@ -666,15 +739,15 @@ __global__ void __launch_bounds__(BT, MINB) family_kernel(const Job* __restrict_
     if (Sf.op >= 0) {  // ghost (k, j): fork a copy that reflects here and runs forward to the sensor
       RayState<T> q = r;
       bool a2 = alive;
-      if (a2) a2 = interact<T, true, false>(Sf, K, g.lut, q, o);
+      if (a2) a2 = interact<T, true, false>(Sf, K, g, q, o);
 #pragma unroll 1
       for (int s = k + 1; s < n_fwd; s++) {
         if (a2) { a2 = propagate<T, false>(s_fwd[s], q, o); if (STATS) n_exec++; }
-        if (a2) a2 = interact<T, true, false>(s_fwd[s], K, g.lut, q, o);
+        if (a2) a2 = interact<T, true, false>(s_fwd[s], K, g, q, o);
       }
       if (warp_land<T>(WS, JC, a2, q.ox, q.oy, q.w * q.ma, q.w * q.mb, b != bp, lane)) n_landed++;
     }
-    if (alive) alive = interact<T, true, false>(Sb, K, g.lut, r, o);  // on through surface k (or the stop's mask)
+    if (alive) alive = interact<T, true, false>(Sb, K, g, r, o);  // on through surface k (or the stop's mask)
   }
   if (STATS) flush_stats(g.stats, n_exec, in_grid ? 1u : 0u, n_landed);
 }
@@ -705,7 +778,7 @@ __global__ void __launch_bounds__(256) dump_kernel(const Job* __restrict__ job, 
   bool alive = true;
   for (int s = 0; alive && s < n_steps; s++) {
     alive = propagate<T, true>(s_prog[s], r, o);
-    if (alive) alive = interact<T, false, true>(s_prog[s], K, g.lut, r, o);
+    if (alive) alive = interact<T, false, true>(s_prog[s], K, g, r, o);
   }
   lfb_ray_hit rec;
   rec.x_ap = o.xa; rec.y_ap = o.ya; rec.flags = o.flags; rec.pad = 0;
@@ -727,8 +800,9 @@ __global__ void __launch_bounds__(256) dump_kernel(const Job* __restrict__ job, 
 // host launchers (instantiated per geometry type by exact_f32.cu / exact_f64.cu)
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T> struct Tune;  // CTAs per SM the register allocation targets: default / alternative
-template <> struct Tune<float> { static constexpr int kGhostA = 12, kGhostB = 10, kFamily = 10; };
-template <> struct Tune<double> { static constexpr int kGhostA = 6, kGhostB = 5, kFamily = 5; };
+// (measured on B200, tools/kernel_ab.py: A is the faster of each pair at cfg2 / cfg3)
+template <> struct Tune<float> { static constexpr int kGhostA = 12, kGhostB = 10, kFamilyA = 8, kFamilyB = 10; };
+template <> struct Tune<double> { static constexpr int kGhostA = 8, kGhostB = 6, kFamilyA = 6, kFamilyB = 5; };
 
 template <typename T>
 cudaError_t launch_prefix_t(const Job* slots, const StepT<T>* progs, int n_slots, const FrameGeom& g, const float* tex, float4* prefix,
@@ -742,27 +816,41 @@ cudaError_t launch_prefix_t(const Job* slots, const StepT<T>* progs, int n_slots
 }
 
 template <typename T>
-cudaError_t launch_ghosts_t(const Job* jobs, const StepT<T>* progs, int n_jobs, const FrameGeom& g, const float* tex, unsigned long long* accum,
-                            int ctas_per_sm, bool stats, cudaStream_t s) {
-  if (n_jobs <= 0) return cudaSuccess;
+cudaError_t launch_ghosts_t(const Job* jobs, const StepT<T>* progs, const unsigned* heads, int n_jobs, const FrameGeom& g, const float* tex,
+                            unsigned long long* accum, int ctas_per_sm, bool stats, cudaStream_t s) {
   constexpr int BT = 128;
-  const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + BT / 16 - 1) / (BT / 16), n_jobs);  // (patch column, patch row, job)
-  if (nb.y > 65535u || nb.z > 65535u) return cudaErrorInvalidConfiguration;
-  if (stats) ghost_kernel<T, Tune<T>::kGhostB, BT, true><<<nb, BT, 0, s>>>(jobs, progs, g, tex, accum);
-  else if (ctas_per_sm == Tune<T>::kGhostB) ghost_kernel<T, Tune<T>::kGhostB, BT, false><<<nb, BT, 0, s>>>(jobs, progs, g, tex, accum);
-  else ghost_kernel<T, Tune<T>::kGhostA, BT, false><<<nb, BT, 0, s>>>(jobs, progs, g, tex, accum);
+  JobHeads H;
+  for (int z0 = 0; z0 < n_jobs; z0 += kHeadsPerLaunch) {  // kHeadsPerLaunch jobs per launch: their headers travel as kernel parameters
+    const int nz = n_jobs - z0 < kHeadsPerLaunch ? n_jobs - z0 : kHeadsPerLaunch;
+    memcpy(H.h, heads + z0, sizeof(unsigned) * (size_t)nz);
+    const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + BT / 16 - 1) / (BT / 16), nz);  // (patch column, patch row, job)
+    if (nb.y > 65535u) return cudaErrorInvalidConfiguration;
+    const Job* J = jobs + z0;
+    const StepT<T>* P = progs + (size_t)z0 * LFB_MAX_STEPS;
+    if (stats) ghost_kernel<T, Tune<T>::kGhostA, BT, true><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
+    else if (ctas_per_sm == 1) ghost_kernel<T, Tune<T>::kGhostB, BT, false><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
+    else ghost_kernel<T, Tune<T>::kGhostA, BT, false><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
+  }
   return cudaGetLastError();
 }
 
 template <typename T>
-cudaError_t launch_families_t(const Job* fams, const StepT<T>* fam_progs, int n_fams, const Job* slots, const StepT<T>* slot_progs,
-                              const FrameGeom& g, const float* tex, unsigned long long* accum, bool stats, cudaStream_t s) {
-  if (n_fams <= 0) return cudaSuccess;
+cudaError_t launch_families_t(const Job* fams, const StepT<T>* fam_progs, const unsigned* heads, int n_fams, const Job* slots,
+                              const StepT<T>* slot_progs, const FrameGeom& g, const float* tex, unsigned long long* accum, int ctas_per_sm,
+                              bool stats, cudaStream_t s) {
   constexpr int BT = 128;
-  const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + BT / 16 - 1) / (BT / 16), n_fams);  // (patch column, patch row, family)
-  if (nb.y > 65535u || nb.z > 65535u) return cudaErrorInvalidConfiguration;
-  if (stats) family_kernel<T, Tune<T>::kFamily, BT, true><<<nb, BT, 0, s>>>(fams, fam_progs, slots, slot_progs, g, tex, accum);
-  else family_kernel<T, Tune<T>::kFamily, BT, false><<<nb, BT, 0, s>>>(fams, fam_progs, slots, slot_progs, g, tex, accum);
+  JobHeads H;
+  for (int z0 = 0; z0 < n_fams; z0 += kHeadsPerLaunch) {
+    const int nz = n_fams - z0 < kHeadsPerLaunch ? n_fams - z0 : kHeadsPerLaunch;
+    memcpy(H.h, heads + z0, sizeof(unsigned) * (size_t)nz);
+    const dim3 nb((g.N + 15) / 16, ((g.N + 1) / 2 + BT / 16 - 1) / (BT / 16), nz);  // (patch column, patch row, family)
+    if (nb.y > 65535u) return cudaErrorInvalidConfiguration;
+    const Job* J = fams + z0;
+    const StepT<T>* P = fam_progs + (size_t)z0 * LFB_MAX_STEPS;
+    if (stats) family_kernel<T, Tune<T>::kFamilyA, BT, true><<<nb, BT, 0, s>>>(J, P, H, slots, slot_progs, g, tex, accum);
+    else if (ctas_per_sm == 1) family_kernel<T, Tune<T>::kFamilyB, BT, false><<<nb, BT, 0, s>>>(J, P, H, slots, slot_progs, g, tex, accum);
+    else family_kernel<T, Tune<T>::kFamilyA, BT, false><<<nb, BT, 0, s>>>(J, P, H, slots, slot_progs, g, tex, accum);
+  }
   return cudaGetLastError();
 }
 

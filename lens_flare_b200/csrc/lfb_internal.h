@@ -58,16 +58,30 @@ struct FrameGeom {
   const float2* lut;  // reflectance tables over the cosine in the rarer medium, one per (wavelength, surface, direction):
                       // (R_i, R_{i+1} - R_i); the trace only reads them below kPolyV0 (steeper than ~53 degrees)
   int* bbox;        // device int[4] = {min_x, min_y, max_x, max_y} of every pixel the frame deposits into (or nullptr)
-  unsigned* tile_bits;  // dirty-tile bitmap of the accumulators: bit t = 16x16 sensor tile t received a deposit (or nullptr)
-  int tiles_w, pad;     // tiles per sensor row
+  unsigned* tile_bits;  // dirty-tile map of the accumulators: byte t != 0 = 16x16 sensor tile t received a deposit (or nullptr)
+  int tiles_w;          // tiles per sensor row
+  float poly_v0;        // weights come from the step's polynomial for cosines >= this (kPolyV0; > 1 forces the tables)
+  int pad2, pad3;
   unsigned long long* stats;  // STATS instantiations only: [0] executed surface steps, [1] ray pairs started, [2] ray pairs landed
 };
 
-constexpr int kTilePxLog2 = 4;  // the dirty-tile bitmap's tiles are 16 x 16 pixels
+// Job headers of one launch of the ghost / family kernels, passed BY VALUE (kernel parameter space = constant bank): a CTA
+// knows its job's cache slot, first-reflection surface and program length without a global load, so the ray-state and
+// program loads of its prologue are issued at once -- one L2 round trip instead of two.  Launches take kHeadsPerLaunch jobs.
+constexpr int kHeadsPerLaunch = 1024;
+struct JobHeads {
+  unsigned h[kHeadsPerLaunch];  // bits 0-15 slot + 1 (0: no cached sweep), 16-20 first-reflection surface, 21-27 program length
+};
+inline unsigned pack_head(int slot, int j_first, int n_steps) {
+  return (unsigned)(slot + 1) | ((unsigned)(j_first < 0 ? 0 : j_first) << 16) | ((unsigned)n_steps << 21);
+}
+
+constexpr int kTilePxLog2 = 4;  // the dirty-tile map's tiles are 16 x 16 pixels
 constexpr int kTilePx1 = 1 << kTilePxLog2;
 inline int tiles_across(int px) { return (px + kTilePx1 - 1) >> kTilePxLog2; }
 
-// A sensor accumulator buffer (lfb_accum_bytes): W*H*3 u64 fixed-point sums, then the dirty-tile bitmap of those sums.
+// A sensor accumulator buffer (lfb_accum_bytes): W*H*3 u64 fixed-point sums, then the dirty-tile map of those sums: one
+// BYTE per 16 x 16 tile (non-zero = a splat deposited into it), handled four tiles to a 32-bit word.
 struct AccumLayout {
   int tiles_w, tiles_h, n_tiles, n_words;
   size_t px_bytes, bits_off, total;
@@ -76,14 +90,14 @@ inline AccumLayout accum_layout(int W, int H) {
   AccumLayout a;
   a.tiles_w = tiles_across(W); a.tiles_h = tiles_across(H);
   a.n_tiles = a.tiles_w * a.tiles_h;
-  a.n_words = (a.n_tiles + 31) / 32;
+  a.n_words = (a.n_tiles + 3) / 4;
   a.px_bytes = sizeof(unsigned long long) * 3 * (size_t)W * (size_t)H;
   a.bits_off = (a.px_bytes + 255) & ~(size_t)255;
   a.total = a.bits_off + (((size_t)a.n_words * 4 + 255) & ~(size_t)255);
   return a;
 }
 // The state that goes with an OUTPUT buffer of the tile-sparse finalize (lfb_tile_state_bytes): which tiles the previous
-// frame left non-zero in it.  [0] ticket, [1] tiles written by the last frame, [2..3] pad, then n_words bitmap words.
+// frame left non-zero in it.  [0] ticket, [1] tiles written by the last frame, [2..3] pad, then n_words tile-map words.
 inline size_t tile_state_bytes(int W, int H) { return 16 + (((size_t)accum_layout(W, H).n_words * 4 + 255) & ~(size_t)255); }
 
 // EXACT_GRID step program (exact_trace.cuh): a ghost flattened into straight-line steps with every ray-independent
@@ -156,11 +170,12 @@ template <typename T>
 cudaError_t launch_exact_prefix(const Job* slots, const StepT<T>* progs, int n_slots, const FrameGeom& g, const float* tex, float4* prefix,
                                 unsigned long long* accum_for_direct, bool stats, cudaStream_t s);
 template <typename T>
-cudaError_t launch_exact_ghosts(const Job* jobs, const StepT<T>* progs, int n_jobs, const FrameGeom& g, const float* tex,
+cudaError_t launch_exact_ghosts(const Job* jobs, const StepT<T>* progs, const unsigned* heads, int n_jobs, const FrameGeom& g, const float* tex,
                                 unsigned long long* accum, int ctas_per_sm, bool stats, cudaStream_t s);
 template <typename T>
-cudaError_t launch_exact_families(const Job* fams, const StepT<T>* fam_progs, int n_fams, const Job* slots, const StepT<T>* slot_progs,
-                                  const FrameGeom& g, const float* tex, unsigned long long* accum, bool stats, cudaStream_t s);
+cudaError_t launch_exact_families(const Job* fams, const StepT<T>* fam_progs, const unsigned* heads, int n_fams, const Job* slots,
+                                  const StepT<T>* slot_progs, const FrameGeom& g, const float* tex, unsigned long long* accum, int ctas_per_sm,
+                                  bool stats, cudaStream_t s);
 template <typename T>
 cudaError_t launch_exact_dump(const Job* job, const StepT<T>* prog, const FrameGeom& g, const float* tex, lfb_ray_hit* out, cudaStream_t s);
 cudaError_t launch_finalize(const unsigned long long* accum, int W, int H, double inv_scale, void* out,
@@ -175,6 +190,9 @@ struct PeerFlags {  // every rank's barrier flag array (LFB_MAX_PEERS u64 each) 
   unsigned long long* ptr[LFB_MAX_PEERS];
   int n, rank_self;
 };
+// sparse.cu: dirty tiles of the ranks' accumulators -> pixels of `out` (n = 1: this GPU's finalize)
+cudaError_t launch_tiles(const PeerAccums& P, int rank, int W, int H, double inv_scale, void* out, size_t stride, int elem,
+                         unsigned* state, unsigned* count_out, int ctas, cudaStream_t s);
 cudaError_t launch_peer_barrier(const PeerFlags& F, int rank, unsigned long long epoch, cudaStream_t s);
 cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long* mc, size_t p0, size_t p1, double inv_scale,
                                    void* out, size_t stride, int elem, int ctas, cudaStream_t s);
@@ -192,13 +210,19 @@ __device__ __forceinline__ void grow_bbox(int* bb, int x0, int y0, int x1, int y
   if (x1 > v[2]) atomicMax(bb + 2, x1);
   if (y1 > v[3]) atomicMax(bb + 3, y1);
 }
-// Mark the 16 x 16 sensor tile (tx, ty) dirty.  Read first: after the first few warps of a frame almost every bit a warp
-// wants is already set, so the atomics are rare.
-__device__ __forceinline__ void mark_tile(unsigned* bits, int tiles_w, int tx, int ty) {
-  const unsigned t = (unsigned)ty * (unsigned)tiles_w + (unsigned)tx;
-  const unsigned bit = 1u << (t & 31u);
-  unsigned* w = bits + (t >> 5);
-  if (!(*reinterpret_cast<volatile unsigned*>(w) & bit)) atomicOr(w, bit);
+// The dirty-tile map: one byte per 16 x 16 sensor tile, non-zero = a splat deposited into it.  Marking is "look, then store
+// the byte if it is still zero": no atomics (a lost race only repeats the store), and after the first few warps of a frame
+// almost every look finds the byte set.  Measured on B200 at cfg2, ghost kernel under ncu: a bit map with a volatile read
+// right before atomicOr 84 us (26 % of the stall samples on the read); unconditional atomicOr 1.5 ms (same-address atomics
+// serialise in L2); unconditional byte stores 152 us (the hot sectors back the store path up: drain / MIO stalls
+// everywhere).  The throughput kernels therefore issue the look early (tile_peek) and act on it after the splat (tile_mark_if).
+__device__ __forceinline__ unsigned char* tile_byte(unsigned* map, int tiles_w, int tx, int ty) {
+  return reinterpret_cast<unsigned char*>(map) + ((unsigned)ty * (unsigned)tiles_w + (unsigned)tx);
+}
+__device__ __forceinline__ unsigned tile_peek(const unsigned char* p) { return __ldcg(p); }  // L2, not L1: other SMs' marks are seen
+__device__ __forceinline__ void mark_tile(unsigned* map, int tiles_w, int tx, int ty) {
+  unsigned char* p = tile_byte(map, tiles_w, tx, ty);
+  if (!tile_peek(p)) *p = 1;
 }
 cudaError_t launch_ref_setup(const RefFrame& f, const int* pairs, const float* rgb_weight, RefTri* tris,
                              lfb_ref_ghost* ghosts, int* bbox, cudaStream_t s);
@@ -220,7 +244,8 @@ struct StarFrame {
 };
 size_t starburst_scratch_bytes(const StarFrame& f);
 cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch, const double* lights_dev, int n_lights,
-                             const double rad_sum[3], void* out, size_t stride, int elem, int additive, cudaStream_t s, int* launches);
+                             const double rad_sum[3], void* out, size_t stride, int elem, int additive, bool spectrum_cached, cudaStream_t s,
+                             int* launches);
 
 cudaError_t launch_to_color(const double* hdr, int W, int H, uint32_t* out, int flip, cudaStream_t s);
 

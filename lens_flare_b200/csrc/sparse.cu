@@ -1,0 +1,192 @@
+// sparse.cu -- the tile-sparse back end of the ghost path: fixed-point sums -> pixels for the DIRTY 16 x 16 sensor tiles only,
+// on one GPU or summed across GPUs over NVLink peer memory.
+//
+// A flare frame is ~99 % zeros (cfg2: 24 725 non-zero pixels of 2 073 600).  The splat kernels mark every tile they deposit
+// into in a byte map behind the accumulators (lfb_internal.h: AccumLayout, mark_tile: a plain store per tile); this kernel then
+//   * visits the tiles that are dirty NOW (convert, store) or were dirty in the output buffer's PREVIOUS frame (store zeros),
+//     so the output buffer always holds exactly this frame -- the reference's "ghost_buffer fully rewritten on return"
+//     (pathtracer.cpp:719-720) without touching the other 99 %;
+//   * zeroes the accumulator tiles it reads, so the next frame needs no 49.8 MB memset either;
+//   * with n_ranks > 1 is the cross-GPU reduce as well: rank r owns the map words w = r (mod n) -- interleaved strips of
+//     4 tiles -- ORs the ranks' marks for them, sums the dirty tiles of exactly those ranks that have them (peer loads),
+//     zeroes them (peer stores) and writes the pixels into the owner's output buffer (peer stores).  Integer sums: the frame
+//     has the same bits for any rank count.  This is the "reduce" of SURVEY 8e fused with finalize, moving ~1 % of the bytes
+//     an all-pixels reduce moves.
+// The output may be DEVICE memory or page-locked HOST memory mapped into the device (zero-copy): the stores of the dirty
+// tiles then ARE the device->host transfer -- no staging buffer, no host-side scatter, no second pass.
+//
+// One launch per frame; the CTA that finishes last rolls the tile maps over (previous = current, current = 0).
+#include "lfb_internal.h"
+
+namespace lfb {
+
+namespace {
+
+constexpr int kThreads = 256;  // one thread per pixel of a tile
+
+struct TileArgs {
+  PeerAccums acc;        // the ranks' accumulator buffers (pixel sums at offset 0)
+  size_t bits_off;       // byte offset of the dirty-tile map inside each
+  unsigned* state;       // THIS rank's tile state of the output buffer: [0] ticket, [1] tiles written, [2..3] pad, [4..] previous bits
+  int rank;              // this rank owns the tile-map words w with w % acc.n == rank
+  int W, H, tiles_w, n_words;
+  double inv_scale;
+  char* out;             // the output frame: pixel (x, y) at (x + y * W) * stride
+  size_t stride;
+  int elem;
+  unsigned* count_out;   // optional (mapped host memory): the number of tiles this launch wrote
+};
+
+__device__ __forceinline__ unsigned* bits_of(const TileArgs& A, int r) {
+  return reinterpret_cast<unsigned*>(reinterpret_cast<char*>(const_cast<unsigned long long*>(A.acc.ptr[r])) + A.bits_off);
+}
+
+// one bit (0, 8, 16, 24) per non-zero byte of a tile-map word
+__device__ __forceinline__ unsigned nonzero_bytes(unsigned m) { return __vcmpne4(m, 0u) & 0x01010101u; }
+
+__global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
+  extern __shared__ unsigned s_pre[];  // [n_words + 1] exclusive prefix of the per-word tile counts
+  __shared__ unsigned s_warp[kThreads / 32];
+  __shared__ unsigned s_total;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  unsigned* prev = A.state + 4;
+  const int n = A.acc.n;
+
+  // ---- 1. how many tiles does each word of the tile map hold (current of any rank, or previous)?  owned words only ----
+  const int per = (A.n_words + kThreads - 1) / kThreads;  // contiguous words per thread
+  const int w0 = tid * per, w1 = min(w0 + per, A.n_words);
+  unsigned mine = 0;
+  for (int w = w0; w < w1; w++) {
+    unsigned m = 0;
+    if (w % n == A.rank) {
+      m = prev[w];
+      for (int r = 0; r < n; r++) m |= bits_of(A, r)[w];
+    }
+    const unsigned c = __popc(nonzero_bytes(m));
+    s_pre[w] = c;
+    mine += c;
+  }
+  // block-exclusive scan of the per-thread sums
+  unsigned incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned v = lane < kThreads / 32 ? s_warp[lane] : 0, inc = v;
+#pragma unroll
+    for (int d = 1; d < kThreads / 32; d <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += u;
+    }
+    if (lane < kThreads / 32) s_warp[lane] = inc - v;
+    if (lane == kThreads / 32 - 1) s_total = inc;
+  }
+  __syncthreads();
+  unsigned run = s_warp[wid] + incl - mine;
+  for (int w = w0; w < w1; w++) {
+    const unsigned c = s_pre[w];
+    s_pre[w] = run;
+    run += c;
+  }
+  if (tid == kThreads - 1 || (w0 < A.n_words && w1 == A.n_words)) s_pre[A.n_words] = s_total;
+  __syncthreads();
+  const unsigned total = s_total;
+
+  // ---- 2. tiles q = blockIdx.x, + gridDim.x, ... in tile-map order ----
+  for (unsigned q = blockIdx.x; q < total; q += gridDim.x) {
+    int lo = 0, hi = A.n_words;  // the word w with s_pre[w] <= q < s_pre[w + 1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_pre[mid] <= q) lo = mid; else hi = mid;
+    }
+    const int w = lo;
+    unsigned have = 0;  // bit r set = rank r's tile is dirty
+    unsigned m = prev[w];
+    for (int r = 0; r < n; r++) m |= bits_of(A, r)[w];
+    const int byte = __fns(nonzero_bytes(m), 0, (int)(q - s_pre[w]) + 1) >> 3;  // the (q - s_pre[w])-th marked tile of the word
+    for (int r = 0; r < n; r++) have |= (((bits_of(A, r)[w] >> (8 * byte)) & 0xffu) ? 1u : 0u) << r;
+    const int t = w * 4 + byte;
+    const int ty = t / A.tiles_w, tx = t - ty * A.tiles_w;
+    const int x = tx * kTilePx1 + (tid & (kTilePx1 - 1)), y = ty * kTilePx1 + (tid >> kTilePxLog2);
+    if (x >= A.W || y >= A.H) continue;
+    const size_t p = (size_t)x + (size_t)y * A.W;
+    unsigned long long s0 = 0, s1 = 0, s2 = 0;
+    for (int r = 0; r < n; r++) {
+      if (!((have >> r) & 1u)) continue;
+      unsigned long long* a = const_cast<unsigned long long*>(A.acc.ptr[r]) + 3 * p;
+      s0 += a[0]; s1 += a[1]; s2 += a[2];
+      a[0] = 0ull; a[1] = 0ull; a[2] = 0ull;  // the next frame finds the accumulators clear
+    }
+    const double v0 = (double)(long long)s0 * A.inv_scale, v1 = (double)(long long)s1 * A.inv_scale, v2 = (double)(long long)s2 * A.inv_scale;
+    if (A.elem == LFB_F32x3) {
+      float* o = reinterpret_cast<float*>(A.out + p * A.stride);
+      o[0] = (float)v0; o[1] = (float)v1; o[2] = (float)v2;
+    } else {
+      double* o = reinterpret_cast<double*>(A.out + p * A.stride);
+      o[0] = v0; o[1] = v1; o[2] = v2;
+    }
+  }
+
+  // ---- 3. the CTA that finishes last rolls the tile maps over ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(A.state, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int w = tid; w < A.n_words; w += kThreads) {
+    if (w % n != A.rank) continue;
+    unsigned m = 0;
+    for (int r = 0; r < n; r++) {
+      unsigned* b = bits_of(A, r) + w;
+      m |= *b;
+      *b = 0u;
+    }
+    prev[w] = m;
+  }
+  if (tid == 0) {
+    A.state[0] = 0u;
+    A.state[1] = total;
+    if (A.count_out) *A.count_out = total;
+  }
+}
+
+}  // namespace
+
+// accum_ptrs[r]: rank r's accumulator buffer as mapped in this process (n_ranks = 1: this GPU's own); state: this rank's
+// tile state of `out` (tile_state_bytes, zero-initialised once while `out` is clear).
+cudaError_t launch_tiles(const PeerAccums& P, int rank, int W, int H, double inv_scale, void* out, size_t stride, int elem,
+                         unsigned* state, unsigned* count_out, int ctas, cudaStream_t s) {
+  const AccumLayout lay = accum_layout(W, H);
+  TileArgs A;
+  A.acc = P;
+  A.bits_off = lay.bits_off;
+  A.state = state;
+  A.rank = rank;
+  A.W = W; A.H = H; A.tiles_w = lay.tiles_w; A.n_words = lay.n_words;
+  A.inv_scale = inv_scale;
+  A.out = (char*)out; A.stride = stride; A.elem = elem;
+  A.count_out = count_out;
+  const size_t smem = sizeof(unsigned) * ((size_t)lay.n_words + 1);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // > 1.6 M tiles: use the dense finalize
+  if (smem > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+  }
+  if (ctas < 1) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ctas = 2 * sms;
+  }
+  if (ctas > lay.n_tiles) ctas = lay.n_tiles;
+  tiles_kernel<<<ctas, kThreads, smem, s>>>(A);
+  return cudaGetLastError();
+}
+
+}  // namespace lfb

@@ -329,17 +329,21 @@ size_t starburst_scratch_bytes(const StarFrame& f) {
 }
 
 cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch, const double* lights_dev, int n_lights,
-                             const double rad_sum[3], void* out, size_t stride, int elem, int additive, cudaStream_t s, int* launches) {
+                             const double rad_sum[3], void* out, size_t stride, int elem, int additive, bool spectrum_cached, cudaStream_t s,
+                             int* launches) {
   double2* E1 = (double2*)scratch;
   double2* E2 = E1 + (size_t)f.bw * f.n_col;
   double2* Ac = E2 + (size_t)f.n_row * f.bh;
   double2* G = Ac + (size_t)f.bh * f.bw;
   double* mag = (double*)(G + (size_t)f.bh * f.n_col);
   auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
-  twiddle_kernel<<<blocks((size_t)f.bw * f.n_col + (size_t)f.n_row * f.bh + (size_t)f.bh * f.bw), 256, 0, s>>>(f, tex, E1, E2, Ac);
   StarEpilogue E;
   E.out = (char*)out; E.stride = stride; E.elem = elem; E.additive = additive; E.n_lights = n_lights; E.lights = lights_dev;
   E.rad_sum[0] = rad_sum[0]; E.rad_sum[1] = rad_sum[1]; E.rad_sum[2] = rad_sum[2];
+  // On the periodic lattice of both axes the spectrum |F| is a property of the MASK alone (the light and the frame only
+  // decide which lattice class a pixel reads): the engine keeps it between frames and only the pixel kernel runs.
+  if (!spectrum_cached) {
+  twiddle_kernel<<<blocks((size_t)f.bw * f.n_col + (size_t)f.n_row * f.bh + (size_t)f.bh * f.bw), 256, 0, s>>>(f, tex, E1, E2, Ac);
   // tile size by problem size: 64 x 64 tiles once they fill the GPU twice over, 32 x 32 below that
   auto big = [](int m, int n) { return (size_t)((m + 63) / 64) * ((n + 63) / 64) >= 2 * 148; };
   {  // G = Ac . E1   (bh x bw) . (bw x n_col); Ac is real.  On the column lattice G[., P - c] = conj G[., c]: half the columns
@@ -361,8 +365,10 @@ cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch
       zgemm_kernel<32, 32, 4, false, true><<<grid, 256, 0, s>>>(E2, G, (double2*)mag, f.n_row, f.n_col, f.bh, f.n_col, f.n_col, 0);
     }
   }
+  if (launches) *launches += 3;
+  }
   star_pixels_kernel<<<dim3((unsigned)((f.W + 255) / 256), (unsigned)f.H), 256, 0, s>>>(f, E, mag);
-  if (launches) *launches += 4;
+  if (launches) *launches += 1;
   return cudaGetLastError();
 }
 

@@ -138,18 +138,19 @@ class PathTracer {
   lfb_params params;
   void set_lens(const lfb_lens& lens);  // default: the built-in prescription, RGB
   const lfb_lens& lens() const { return lens_; }
-  // Dirty-rectangle mode (used for REF_QUADS and PARAXIAL_GRID, whose ghosts are compact): ghost_buffer stays allocated
-  // between renders of the same size, only the rectangle the previous frame wrote is cleared on the host and only the
-  // rectangle the new frame deposits into comes back over PCIe (lfb_render_ghosts_rect) -- instead of zero-filling and
-  // copying W x H x 24 bytes every render.  ghost_buffer must then only be written by generate_ghost_buffer(); call
-  // ghost_buffer.clear() to force a full reset.  EXACT_GRID ghosts throw stray rays across the frame, so that mode
-  // always takes the full-frame path.
+  // ghost_buffer stays allocated between renders of the same size and the facade tracks what the last frame left in it, so
+  // a render clears only that instead of zero-filling W x H x 24 bytes (the reference's clear() + resize(), :719-720).
+  // ghost_buffer must then only be written by generate_ghost_buffer(); call invalidate_ghost_buffer() after touching it.
+  // Dirty-rectangle mode (REF_QUADS, whose ghosts are compact quads; grid modes when pinning is off): only the bounding
+  // rectangle of the frame's deposits is cleared / converted / copied (lfb_render_ghosts_rect).
   bool dirty_rect_mode = true;
-  // Full-frame renders (EXACT_GRID): page-lock ghost_buffer's storage once (lfb_host_register) so the 24 B/pixel frame comes
-  // back at PCIe rate, and skip the host-side zero fill of clear() + resize() when the size is unchanged -- the render
-  // overwrites every pixel.  The storage is unregistered when it moves, changes size, or the PathTracer dies; do not
-  // reallocate ghost_buffer.data behind the PathTracer's back while this is on.
+  // Grid modes: page-lock ghost_buffer's storage once (lfb_host_register) and render tile-sparse (lfb_render_ghosts_sparse):
+  // the device writes this frame's dirty 16 x 16 tiles straight into ghost_buffer.data and re-zeroes the previous frame's.
+  // The storage is unregistered when it moves, changes size, or the PathTracer dies; do not reallocate ghost_buffer.data
+  // behind the PathTracer's back while this is on.
   bool pin_ghost_buffer = true;
+  void invalidate_ghost_buffer() { buffer_state_ = kUnknown; }
+  int last_tiles_written() const { return last_tiles_; }  // tiles the last sparse render wrote (-1: full-frame fallback)
   // stats of the last generate_ghost_buffer(): device ms of the trace kernels and of the whole call
   float last_trace_ms() const;
   float last_frame_ms() const;
@@ -165,7 +166,13 @@ class PathTracer {
   std::vector<lfb_light> make_lights(bool for_ghosts) const;
   void upload_textures(bool ghost, bool star);
   size_t frame_w_ = 0, frame_h_ = 0;
-  int dirty_[4] = {0, 0, -1, -1};  // what the last frame wrote into ghost_buffer
+  int dirty_[4] = {0, 0, -1, -1};  // kRectDirty: what the last frame wrote into ghost_buffer
+  // what is known about ghost_buffer's content: all zeros / zeros outside dirty_ / the engine tracks the non-zero tiles of
+  // the storage at tracked_ / anything (a full-frame render, or the application wrote into it)
+  enum BufferState { kAllClear, kRectDirty, kTilesTracked, kUnknown };
+  BufferState buffer_state_ = kUnknown;
+  const void* tracked_ = nullptr;
+  int last_tiles_ = 0;
   void* pinned_ = nullptr;         // ghost_buffer storage currently page-locked
   size_t pinned_bytes_ = 0;
   void pin_storage();

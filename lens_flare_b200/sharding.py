@@ -20,7 +20,7 @@ def shard_params(params, rank, world_size):
 
 def accum_tensor(params, device):
     """A sensor accumulator buffer the engine splats into (lfb_accum_bytes: the H*W*3 int64 fixed-point sums followed by
-    the dirty-tile bitmap), as a flat int64 tensor; accum_pixels() views the sums."""
+    the dirty-tile map), as a flat int64 tensor; accum_pixels() views the sums."""
     words = (capi.lib().lfb_accum_bytes(params.width, params.height) + 7) // 8
     return torch.zeros((words,), dtype=torch.int64, device=device)
 
@@ -117,7 +117,7 @@ class ShardedFlare:
             self.C.wait_event(last)
             prev = torch.cuda.current_stream(self.device)
             torch.cuda.set_stream(self.C)  # cheaper than the context manager: this runs once per frame
-            px = accum_pixels(acc, self.full_params)  # the sums only: the dirty-tile bitmaps behind them are per rank
+            px = accum_pixels(acc, self.full_params)  # the sums only: the dirty-tile maps behind them are per rank
             if reduce_dst is None:
                 dist.all_reduce(px, op=dist.ReduceOp.SUM)
             else:
@@ -241,6 +241,105 @@ class PeerFlare:
             ev = torch.cuda.Event()
             ev.record(self.B)
             self.reduce_done[k] = ev
+        return b
+
+    def result(self, b):
+        """The owner's pixels of buffer b (valid after finish())."""
+        return self.out_all[b]
+
+
+class PeerSparse:
+    """The multi-GPU frame, tile-sparse: NO collective call and NO full-frame traffic.  Every rank's accumulator buffers
+    (sums + dirty-tile map) live in symmetric memory; after its trace each rank runs ONE kernel (lfb_reduce_tiles_peers) for
+    its interleaved share of the dirty tiles: it ORs the ranks' tile maps, sums the tiles that are dirty anywhere -- reading
+    only the ranks that have them, over NVLink peer memory -- zeroes them, and stores the pixels into the owner's output
+    frame (a peer store) -- or, when `host_out` is given, straight into a page-locked HOST buffer every rank has mapped
+    (a POSIX shared-memory segment each process registered): N GPUs then write the frame's dirty tiles over their own PCIe
+    links at the same time.  ~1 % of the bytes an all-pixels reduce moves; integer sums, so the frame has the same bits for
+    any rank count.
+
+    Two streams, R >= 3 rotating buffer sets (accumulators, output frame, tile state):
+        stream A (engine)           trace frame k into accum[k % R]; device-side barrier (symmetric-memory flags)
+        stream B (finalize engine)  tile reduce of frame k
+    Buffer safety is PeerFlare's: trace(k) first waits for this rank's own reduce(k-R+1); a peer can only pass
+    barrier(k+R-1) -- and then splat into accum[k % R] again in trace(k+R) -- after this rank arrived there, i.e. after this
+    rank's reduce(k) finished reading (and zeroing) it.  The owner's pixels of frame k are complete after finish()."""
+
+    def __init__(self, engine, params, rank, world_size, device, group, n_buffers=3, out_dtype=torch.float32, finalize_engine=None,
+                 host_out_ptrs=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.engine, self.rank, self.world, self.device = engine, rank, world_size, device
+        self.fin_engine = finalize_engine if finalize_engine is not None else engine
+        self.full_params = params
+        self.params = shard_params(params, rank, world_size)
+        self.n_buffers = max(int(n_buffers), 3 if finalize_engine is not None else 2)
+        H, W = params.height, params.width
+        acc_words = (capi.lib().lfb_accum_bytes(W, H) + 7) // 8
+        self.accum_all = symm_mem.empty((self.n_buffers, acc_words), dtype=torch.int64, device=device)
+        self.accum_all.zero_()
+        self.out_all = symm_mem.empty((self.n_buffers, H, W, 3), dtype=out_dtype, device=device)
+        self.out_all.zero_()
+        self.h_acc = symm_mem.rendezvous(self.accum_all, group.group_name)
+        self.h_out = symm_mem.rendezvous(self.out_all, group.group_name)
+        self.flags = symm_mem.empty((16,), dtype=torch.int64, device=device)
+        self.flags.zero_()
+        self.h_flags = symm_mem.rendezvous(self.flags, group.group_name)
+        st_words = (capi.lib().lfb_tile_state_bytes(W, H) + 3) // 4
+        self.state = torch.zeros((self.n_buffers, st_words), dtype=torch.int32, device=device)  # this rank's own, per output frame
+        self.epoch = 0
+        self.acc_bytes = acc_words * 8
+        self.out_bytes = H * W * 3 * self.out_all.element_size()
+        self.elem = capi.F32x3 if out_dtype == torch.float32 else capi.F64x3
+        self.host_out_ptrs = host_out_ptrs  # optional: per buffer, THIS rank's device mapping of a shared page-locked host frame
+        self.A = torch.cuda.ExternalStream(engine.stream, device=device)
+        self.B = torch.cuda.ExternalStream(self.fin_engine.stream, device=device)
+        self.two_streams = self.fin_engine is not engine
+        self.reduce_events = [torch.cuda.Event() for _ in range(self.n_buffers)]
+        self.reduce_valid = [False] * self.n_buffers
+        self.k = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    def begin(self, stream=None):
+        cur = stream or torch.cuda.current_stream(self.device)
+        self.A.wait_stream(cur)
+        self.B.wait_stream(cur)
+
+    def barrier(self):
+        self.epoch += 1
+        self.engine.peer_barrier([int(p) for p in self.h_flags.buffer_ptrs], self.rank, self.epoch)
+
+    def finish(self, stream=None):
+        """All frames enqueued so far are complete in the owner's buffers once `stream` passes this point."""
+        self.A.wait_stream(self.B)
+        self.barrier()
+        (stream or torch.cuda.current_stream(self.device)).wait_stream(self.A)
+
+    def frame(self, lights, owner=0, elem=None, stride=None):
+        """Enqueue one frame; returns its buffer index."""
+        k, R = self.k, self.n_buffers
+        b = k % R
+        self.k += 1
+        nb = (k + 1) % R  # the buffer trace(k) is about to reuse was read by reduce(k - R); frame k - R + 1 is the one PeerFlare's argument needs
+        if self.two_streams and self.reduce_valid[nb] and k - R + 1 >= 0:
+            self.A.wait_event(self.reduce_events[nb])
+        my_acc = int(self.h_acc.buffer_ptrs[self.rank]) + b * self.acc_bytes
+        self.engine.render_ghosts_device(lights, self.params, my_acc, clear_first=False)  # the reducers left it clear
+        self.barrier()  # every rank has finished splatting into buffer b
+        if self.two_streams:
+            self.B.wait_stream(self.A)
+        ptrs = [int(p) + b * self.acc_bytes for p in self.h_acc.buffer_ptrs]
+        if self.host_out_ptrs is not None:
+            out_ptr = self.host_out_ptrs[b]
+            self.fin_engine.reduce_tiles_peers(ptrs, self.rank, self.full_params, out_ptr, stride or 24, elem if elem is not None else capi.F64x3,
+                                               self.state[b].data_ptr())
+        else:
+            out_ptr = int(self.h_out.buffer_ptrs[owner]) + b * self.out_bytes
+            self.fin_engine.reduce_tiles_peers(ptrs, self.rank, self.full_params, out_ptr, 3 * self.out_all.element_size(), self.elem,
+                                               self.state[b].data_ptr())
+        if self.two_streams:
+            self.reduce_events[b].record(self.B)
+            self.reduce_valid[b] = True
         return b
 
     def result(self, b):

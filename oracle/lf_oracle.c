@@ -695,9 +695,9 @@ static int job_cost(const lfb_lens* L, const job_t* q) { /* ray-surface interact
   return q->i < 0 ? L->n_surfaces + 1 : 2 * (q->j - q->i) + L->n_surfaces + 1;
 }
 
-/* All jobs in (light, pair, lambda) order.  Sharding: whole (light, lambda) groups round-robin when there are at
- * least as many groups as shards; otherwise the list is put in longest-processing-time-first order (stable) and
- * single jobs are dealt round-robin (q % shard_count == shard_index). */
+/* All jobs in (light, pair, lambda) order.  Sharding: whole (light, lambda) groups round-robin as far as they divide evenly
+ * among the shards; the jobs of the remaining groups are put in longest-processing-time-first order (stable) and dealt
+ * one by one (q % shard_count == shard_index). */
 static int list_jobs(const lfb_lens* L, const lfb_params* P, int n_lights, job_t** out) {
   int pairs[LFB_MAX_SURFACES * LFB_MAX_SURFACES][2];
   int np = list_pairs(L, P->pair_set, pairs);
@@ -711,23 +711,29 @@ static int list_jobs(const lfb_lens* L, const lfb_params* P, int n_lights, job_t
         J[n++] = q;
       }
     }
-  if (P->shard_count > 1 && n_lights * L->n_lambda >= P->shard_count) {
-    /* at least as many (light, lambda) groups as shards: whole groups are dealt round-robin */
-    int m = 0;
-    for (int q = 0; q < n; q++)
-      if ((J[q].light * L->n_lambda + J[q].lambda) % P->shard_count == P->shard_index) J[m++] = J[q];
-    n = m;
-  } else if (P->shard_count > 1) {
-    for (int a = 1; a < n; a++) { /* stable insertion sort, decreasing cost */
-      job_t q = J[a];
-      int b = a - 1;
-      while (b >= 0 && job_cost(L, &J[b]) < job_cost(L, &q)) { J[b + 1] = J[b]; b--; }
-      J[b + 1] = q;
+  if (P->shard_count > 1) {
+    /* whole (light, lambda) groups round-robin as far as they divide evenly (groups 0 .. floor(G/S)*S - 1); the jobs of the
+     * remaining groups in longest-processing-time-first order (stable), dealt one by one */
+    const int S = P->shard_count, G = n_lights * L->n_lambda, n_whole = (G / S) * S;
+    job_t* keep = (job_t*)malloc(sizeof(job_t) * (n > 0 ? n : 1));
+    job_t* rest = (job_t*)malloc(sizeof(job_t) * (n > 0 ? n : 1));
+    int m = 0, nr = 0;
+    for (int q = 0; q < n; q++) {
+      int grp = J[q].light * L->n_lambda + J[q].lambda;
+      if (grp < n_whole) { if (grp % S == P->shard_index) keep[m++] = J[q]; }
+      else rest[nr++] = J[q];
     }
-    int m = 0;
-    for (int q = 0; q < n; q++)
-      if (q % P->shard_count == P->shard_index) J[m++] = J[q];
+    for (int a = 1; a < nr; a++) { /* stable insertion sort, decreasing cost */
+      job_t q = rest[a];
+      int b = a - 1;
+      while (b >= 0 && job_cost(L, &rest[b]) < job_cost(L, &q)) { rest[b + 1] = rest[b]; b--; }
+      rest[b + 1] = q;
+    }
+    for (int q = 0; q < nr; q++)
+      if (q % S == P->shard_index) keep[m++] = rest[q];
+    memcpy(J, keep, sizeof(job_t) * (size_t)m);
     n = m;
+    free(keep); free(rest);
   }
   *out = J;
   return n;

@@ -1,6 +1,6 @@
 """Multi-GPU parity check, launched with torchrun on a box with >= 2 GPUs (tests/test_multigpu.py does that when it can):
-the sharded frame -- NCCL reduce path (ShardedFlare) and fused peer-memory path (PeerFlare, with and without NVSwitch
-multicast) -- must equal the unsharded single-GPU frame bit for bit."""
+the sharded frame -- NCCL reduce path (ShardedFlare), fused peer-memory path (PeerFlare, with and without NVSwitch
+multicast) and the tile-sparse peer path (PeerSparse) -- must equal the unsharded single-GPU frame bit for bit."""
 import os
 import sys
 
@@ -58,6 +58,24 @@ def main():
         if rank == 0:
             same = all(torch.equal(pf.result(q), whole) for q in range(3))
             print(f"peer path (multicast={mc}, two streams={two}) == single GPU:", same)
+            ok &= same
+    # --- tile-sparse peer path (the default of bench.py at N > 1): moving suns, so tiles of earlier frames must be re-zeroed
+    suns = [[capi.make_light(0.3 + 0.05 * k, 0.4 + 0.03 * k, theta=0.05 + 0.01 * k, radiance=(1.0, 0.5 + 0.1 * k, 2.0 - 0.2 * k)),
+             capi.make_light(0.7, 0.3, theta=0.1, radiance=(0.5, 1.0, 2.0))] for k in range(7)]
+    wants = [torch.from_numpy(eng.render_ghosts(lt, params, elem=capi.F32x3)).to(dev) for lt in suns]
+    for two in (False, True):
+        ps = sharding.PeerSparse(eng, params, rank, world, dev, dist.group.WORLD, n_buffers=3, finalize_engine=fin if two else None)
+        got = []
+        ps.begin()
+        for k, lt in enumerate(suns):
+            b = ps.frame(lt, owner=0)
+            if k >= 4:  # read every frame of the tail (a buffer's content is final only after a finish)
+                ps.finish()
+                torch.cuda.synchronize()
+                got.append((k, ps.result(b).clone()))
+        if rank == 0:
+            same = all(torch.equal(g, wants[k]) for k, g in got)
+            print(f"tile-sparse peer path (two streams={two}) == single GPU:", same)
             ok &= same
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

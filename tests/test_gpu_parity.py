@@ -784,3 +784,97 @@ def test_async_render_equals_blocking_render(engine, apertures):
     finally:
         for b in bufs:
             b.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# tile-sparse back end: finalize / read-back of the dirty 16 x 16 tiles only
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,prec", [(capi.MODE_EXACT_GRID, capi.FP32), (capi.MODE_EXACT_GRID, capi.STRICT), (capi.MODE_EXACT_GRID, capi.FP64),
+                                       (capi.MODE_PARAXIAL_GRID, capi.FP32)])
+def test_sparse_render_equals_full_frame(apertures, mode, prec):
+    """lfb_render_ghosts_sparse into one page-locked buffer, frame after frame (the sun moves, leaves, comes back; two suns;
+    odd strides): after every call the buffer holds exactly what lfb_render_ghosts writes -- tiles the previous frame left
+    are re-zeroed, the accumulators are left clear -- and only a few per cent of the tiles travel."""
+    e = capi.Engine(0)
+    W, H = 1000, 562  # not multiples of the 16-pixel tile
+    bufs = [capi.PinnedArray((H, W, 3), np.float64), capi.PinnedArray((H, W, 4), np.float64)]
+    try:
+        e.set_lens(capi.builtin_lens(3, 550.0))
+        e.set_aperture(apertures["pentbig500_14"])
+        p = capi.make_params(mode, W, H, grid_n=80, pair_set=capi.PAIRS_ALL, include_direct=1, precision=prec)
+        mk = (lambda x, y, **kw: capi.make_light(x, y, theta=capi.physical_theta(x, y), **kw)) if mode == capi.MODE_EXACT_GRID else \
+             (lambda x, y, **kw: capi.make_light(x, y, theta=0.02 + 0.05 * x, **kw))
+        seq = [[mk(0.45, 0.55)], [mk(0.7, 0.3, radiance=(2.0, 1.0, 0.5))], [], [mk(0.45, 0.55), mk(0.3, 0.62)], [mk(0.52, 0.5)]]
+        for buf, stride in ((bufs[0], 24), (bufs[1], 32)):  # Vector3D and the AVX Vector3D (padding lane untouched)
+            buf.array[...] = 0.0
+            n_tiles_total = ((W + 15) // 16) * ((H + 15) // 16)
+            for k, lights in enumerate(seq):
+                want = e.render_ghosts(lights, p)
+                n = e.render_ghosts_sparse(lights, p, buf.array, stride=stride, out_is_clear=(k == 0))
+                assert np.array_equal(buf.array[..., :3], want), (k, stride)
+                if stride == 32:
+                    assert not buf.array[..., 3].any()
+                assert 0 <= n < 0.5 * n_tiles_total, (k, n)
+                if lights:
+                    assert want.any() and n > 0
+        # a buffer the engine has not seen needs out_is_clear = 1
+        with pytest.raises(capi.LfbError) as err:
+            e.render_ghosts_sparse(seq[0], p, bufs[0].array, stride=24, out_is_clear=False)
+        assert err.value.code == capi.ERR_STATE
+        # pageable memory: falls back to the full-frame copy, says so
+        mine = np.full((H, W, 3), -1.0)
+        assert e.render_ghosts_sparse(seq[0], p, mine, out_is_clear=True) == -1
+        assert np.array_equal(mine, e.render_ghosts(seq[0], p))
+    finally:
+        for b in bufs:
+            b.free()
+        e.close()
+
+
+def test_finalize_tiles_device_pipeline(apertures):
+    """The device-resident form: lfb_render_ghosts_device (clear_first = 0) + lfb_finalize_tiles_device over frames keeps the
+    accumulators clear and the output frame exact, F32x3 and F64x3."""
+    import torch
+    from lens_flare_b200 import sharding
+    dev = torch.device("cuda", 0)
+    e = capi.Engine(0)
+    try:
+        e.set_lens(capi.builtin_lens(3, 550.0))
+        e.set_aperture(apertures["pentbig500_14"])
+        p = capi.make_params(capi.MODE_EXACT_GRID, 1920, 1080, grid_n=96, pair_set=capi.PAIRS_ALL, include_direct=1)
+        acc = sharding.accum_tensor(p, dev)
+        for elem, dt in ((capi.F32x3, torch.float32), (capi.F64x3, torch.float64)):
+            out = torch.zeros((1080, 1920, 3), dtype=dt, device=dev)
+            state = torch.zeros((capi.lib().lfb_tile_state_bytes(1920, 1080) + 3) // 4, dtype=torch.int32, device=dev)
+            for k, (x, y) in enumerate(((0.45, 0.55), (0.6, 0.35), (0.3, 0.7), (0.45, 0.55))):
+                lt = [capi.make_light(x, y, theta=capi.physical_theta(x, y))]
+                e.render_ghosts_device(lt, p, acc.data_ptr(), clear_first=False)
+                e.finalize_tiles_device(acc.data_ptr(), p, out.data_ptr(), out.stride(1) * out.element_size(), elem, state.data_ptr())
+                e.sync()
+                want = e.render_ghosts(lt, p, elem=elem)
+                assert want.any() and np.array_equal(out.cpu().numpy(), want), (elem, k)
+                assert int(acc.abs().max()) == 0  # sums and bitmap left clear
+    finally:
+        e.close()
+
+
+def test_physical_mapping_vs_oracle(engine, port, apertures):
+    """lfb_params.physical_mapping = 1 (origin at the image centre, meridional axis along the light's azimuth): the FP64
+    parity kernel's integer sums equal the oracle's, FP32 / STRICT frames are within the usual image tolerances, for suns in
+    all four quadrants (the oracle side of this mapping is pinned by test_physical_mapping_puts_the_direct_image_on_the_light)."""
+    lens = capi.builtin_lens(3)
+    engine.set_lens(lens)
+    tex = apertures["pentbig500_14"]
+    engine.set_aperture(tex)
+    for ns in ((0.62, 0.58), (0.38, 0.58), (0.38, 0.42), (0.62, 0.40)):
+        lt = [capi.make_light(ns[0], ns[1], theta=capi.physical_theta(ns[0], ns[1]), radiance=(1.0, 0.7, 0.4))]
+        p = capi.make_params(capi.MODE_EXACT_GRID, 800, 450, grid_n=64, pair_set=capi.PAIRS_ALL, include_direct=1, precision=capi.FP64, px_per_unit=1.0)
+        p.physical_mapping = 1
+        want, acc = port.render(lens, tex, lt, p, want_accum=True)
+        assert np.count_nonzero(acc) > 500
+        assert np.array_equal(np.rint(engine.render_ghosts(lt, p) * 2.0 ** 40), acc), ns
+        assert rel_l2(engine.render_ghosts(lt, capi.copy_params(p, precision=capi.FP32)), want) <= 1e-3, ns
+        assert rel_l2(engine.render_ghosts(lt, capi.copy_params(p, precision=capi.STRICT)), want) <= 1e-4, ns
+        # and it is a different picture from the reference's mapping
+        q = capi.copy_params(p, physical_mapping=0)
+        assert rel_l2(engine.render_ghosts(lt, q), want) > 0.1

@@ -89,10 +89,14 @@ def test_job_list_order_and_sharding(native_lib):
             seen += [tuple(x) for x in sh]
             loads.append(sum(2 * (j - i) + 10 if i >= 0 else 10 for _, i, j, _ in sh))
         assert sorted(seen) == sorted(tuple(x) for x in full)          # a partition
-        if n <= 6:   # 2 lights x 3 wavelengths = 6 groups >= n: whole (light, lambda) groups, identical cost each
-            assert max(loads) - min(loads) <= (488 if 6 % n else 0)
-        else:        # fewer groups than shards: single jobs, longest first
-            assert max(loads) - min(loads) <= 26
+        # 6 (light, lambda) groups: whole groups as far as they divide evenly among the shards (identical cost each), the
+        # jobs of the remaining groups one by one, longest first -- never more than one job's worth of imbalance
+        assert max(loads) - min(loads) <= (0 if 6 % n == 0 else 26), (n, loads)
+    # one RGB light on two GPUs used to be dealt 2 groups : 1 group
+    loads = [sum(2 * (j - i) + 10 if i >= 0 else 10 for _, i, j, _ in capi.list_jobs(lens, capi.copy_params(p, shard=(r, 2)), 1)) for r in range(2)]
+    assert abs(loads[0] - loads[1]) <= 26 and sum(loads) == 3 * 488
+    groups0 = {(l, lam) for l, _, _, lam in capi.list_jobs(lens, capi.copy_params(p, shard=(0, 2)), 1)}
+    assert (0, 0) in groups0 and (0, 1) not in groups0  # group 0 whole on rank 0, group 1 whole on rank 1, group 2 split
     with pytest.raises(capi.LfbError):
         capi.list_jobs(lens, capi.copy_params(p, shard=(2, 2)), 1)
 

@@ -235,3 +235,35 @@ def test_point_light_exact_converges_to_paraxial(port):
         errs.append(worst)
     assert errs[0] < 0.15 and errs[2] < 0.01
     assert errs[1] < errs[0] / 3.0 and errs[2] < errs[1] / 3.0
+
+
+def test_physical_mapping_puts_the_direct_image_on_the_light(port, apertures):
+    """lfb_params.physical_mapping = 1 (ours; the reference's mapping -- origin at the sun pixel, rotation atan mod pi,
+    pathtracer.cpp:412-430 -- mirrors the ghosts of a sun left of centre through the sun): with px_per_unit matched to the
+    camera (W / (2 f tan(hFov/2)), f = the lens's focal length from its own ABCD system, square pixels) the direct,
+    unreflected image of a distant light lands on the light's own pixel (Camera::analyze_world_coord, camera.cpp:245-273),
+    in all four quadrants -- and with the reference's mapping it does not."""
+    import math
+    from lens_flare_b200 import capi
+    lens = port.builtin_lens(3)
+    tex = apertures["pentbig500_14"]
+    W, H, hfov = 1920, 1080, 50.0
+    vfov = 2 * math.degrees(math.atan(math.tan(math.radians(hfov / 2)) * H / W))  # square pixels
+    _, full = port.paraxial_system(lens, 1, -1, -1)
+    assert abs(full[0]) < 1e-3  # the sensor sits in the focal plane (green): x_s = f * theta
+    f = full[1]
+    ppu = W / (2 * f * math.tan(math.radians(hfov / 2)))
+    for ns in ((0.62, 0.58), (0.38, 0.58), (0.38, 0.42), (0.62, 0.40), (0.5, 0.6), (0.41, 0.5)):
+        lt = capi.make_light(ns[0], ns[1], theta=capi.physical_theta(ns[0], ns[1], hfov, vfov))
+        for phys, on_target in ((1, True), (0, False)):
+            p = capi.make_params(capi.MODE_EXACT_GRID, W, H, grid_n=24, precision=capi.FP64, px_per_unit=ppu)
+            p.physical_mapping = phys
+            hits = port.trace_grid(lens, tex, lt, p, -1, -1, 1)
+            ok = hits["weight"] > 0
+            assert ok.sum() > 50
+            px, py = hits["px"][ok].mean(), hits["py"][ok].mean()
+            err = math.hypot(px - ns[0] * W, py - ns[1] * H)
+            if on_target:
+                assert err < 1.5, (ns, px, py)       # within the lens's own aberrations / distortion (pixels)
+            else:
+                assert err > 20, (ns, px, py)
