@@ -19,6 +19,7 @@ int main(int argc, char** argv) {
   int mode = LFB_MODE_REF_QUADS, grid = 256;
   double flare_intensity = 1.0, flare_radius = 30.0;  // -i / -n, main.cpp:135-152
   int repeat = 0, pin = 1;                            // --repeat K: time K more generate_ghost_buffer() calls on the host clock
+  int gpus = 1;                                       // --gpus N: devices 0 .. N-1 behind the one PathTracer (lfb_create_multi)
   if (argc == 3 && std::string(argv[1]) == "--png-info") {  // host-only: what CameraApertureTexture::init decodes
     try {
       lfb::CameraApertureTexture t;
@@ -59,6 +60,7 @@ int main(int argc, char** argv) {
     else if (k == "-n" && a + 1 < argc) flare_radius = std::atof(argv[++a]);
     else if (k == "--repeat" && a + 1 < argc) repeat = std::atoi(argv[++a]);
     else if (k == "--no-pin") pin = 0;
+    else if (k == "--gpus" && a + 1 < argc) gpus = std::atoi(argv[++a]);
     else if (k == "-m" && a + 1 < argc) {
       const std::string m = argv[++a];
       mode = m == "exact" ? LFB_MODE_EXACT_GRID : (m == "paraxial" ? LFB_MODE_PARAXIAL_GRID : LFB_MODE_REF_QUADS);
@@ -79,7 +81,9 @@ int main(int argc, char** argv) {
     lfb::DirectionalLight sun(lfb::Vector3D(1, 1, 1), lfb::Vector3D(-(2 * sx - 1) * ex, -(2 * sy - 1) * ey, 1.0), lfb::Vector3D(0, 0, -1));
     lfb::Scene scene;
     scene.lights.push_back(&sun);
-    lfb::PathTracer pt(0);
+    std::vector<int> devices;
+    for (int d = 0; d < (gpus > 1 ? gpus : 1); d++) devices.push_back(d);
+    lfb::PathTracer pt(devices);
     pt.scene = &scene;
     pt.camera = &camera;
     pt.params.mode = mode;
@@ -103,9 +107,10 @@ int main(int argc, char** argv) {
       nz += (v.x != 0 || v.y != 0 || v.z != 0);
     }
     std::printf("{\"w\": %zu, \"h\": %zu, \"axis_ray\": [%.17g, %.17g], \"angle_to_sun\": %.9g, \"sum\": [%.17g, %.17g, %.17g], "
-                "\"l2\": %.17g, \"nonzero\": %zu, \"trace_ms\": %.4f, \"frame_ms\": %.4f, \"host_ms_per_render\": %.4f, \"tex_total\": %.17g}\n",
+                "\"l2\": %.17g, \"nonzero\": %zu, \"trace_ms\": %.4f, \"frame_ms\": %.4f, \"host_ms_per_render\": %.4f, \"tex_total\": %.17g, "
+                "\"tiles_written\": %d, \"gpus\": %d}\n",
                 W, H, pt.axis_ray.x, pt.axis_ray.y, pt.angle_to_sun, sum[0], sum[1], sum[2], std::sqrt(l2), nz, pt.last_trace_ms(),
-                pt.last_frame_ms(), host_ms, ghost_tex.total_value);
+                pt.last_frame_ms(), host_ms, ghost_tex.total_value, pt.last_tiles_written(), gpus > 1 ? gpus : 1);
     if (!star_png.empty()) {  // the rest of raytrace_pixel's flare terms (:881-891) and the displayable frame
       pt.flare_radius = flare_radius;
       pt.flare_intensity = flare_intensity;

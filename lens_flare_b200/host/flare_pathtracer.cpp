@@ -73,8 +73,13 @@ PathTracer::PathTracer(int device_id) : device_id_(device_id) {
   check(lfb_builtin_lens(&lens_, 3, 0.f), "lfb_builtin_lens");
 }
 
+PathTracer::PathTracer(const std::vector<int>& device_ids) : PathTracer(device_ids.empty() ? -1 : device_ids[0]) {
+  if (device_ids.size() > 1) device_ids_ = device_ids;
+}
+
 PathTracer::~PathTracer() {
   unpin_storage();
+  lfb_destroy_multi(multi_);
   lfb_destroy(engine_);
 }
 
@@ -95,6 +100,7 @@ void PathTracer::pin_storage() {
 void PathTracer::set_lens(const lfb_lens& lens) {
   lens_ = lens;
   lens_dirty_ = true;
+  multi_lens_dirty_ = true;
 }
 
 void PathTracer::ensure_engine() {
@@ -183,6 +189,18 @@ void PathTracer::generate_ghost_buffer() {
     pin_storage();
     int tiles = 0;
     const int was_clear = buffer_state_ == kAllClear ? 1 : 0;
+    if (!device_ids_.empty()) {  // several GPUs: one engine each, the same call
+      if (!multi_) check(lfb_create_multi(&multi_, device_ids_.data(), (int)device_ids_.size(), nullptr), "lfb_create_multi");
+      if (multi_lens_dirty_) { check(lfb_multi_set_lens(multi_, &lens_), "lfb_multi_set_lens"); multi_lens_dirty_ = false; }
+      const CameraApertureTexture* t = camera->ghost_aperture_texture;
+      if (sun && multi_uploaded_ != t) {
+        check(lfb_multi_set_aperture(multi_, t->aperture.data(), (int)t->width, (int)t->height), "lfb_multi_set_aperture");
+        multi_uploaded_ = t;
+      }
+      check(lfb_render_ghosts_multi(multi_, lights.data(), (int)lights.size(), &params, ghost_buffer.data.data(), sizeof(Vector3D), LFB_F64x3,
+                                    was_clear, &tiles),
+            "lfb_render_ghosts_multi");
+    } else
     check(lfb_render_ghosts_sparse(engine_, lights.data(), (int)lights.size(), &params, ghost_buffer.data.data(), sizeof(Vector3D), LFB_F64x3,
                                    was_clear, &tiles),
           "lfb_render_ghosts_sparse");

@@ -105,6 +105,10 @@ struct Scene {
 class PathTracer {
  public:
   explicit PathTracer(int device_id = -1);
+  // Several GPUs of one node behind the same single-threaded call surface (lfb_create_multi): generate_ghost_buffer() shards
+  // the grid modes' ghosts over them and every GPU writes its tiles into ghost_buffer.data.  REF_QUADS, the starburst and
+  // render_frame run on the first device.
+  explicit PathTracer(const std::vector<int>& device_ids);
   ~PathTracer();
   PathTracer(const PathTracer&) = delete;
   PathTracer& operator=(const PathTracer&) = delete;
@@ -158,6 +162,10 @@ class PathTracer {
  private:
   void ensure_engine();
   lfb_engine* engine_ = nullptr;
+  lfb_multi* multi_ = nullptr;
+  std::vector<int> device_ids_;
+  bool multi_lens_dirty_ = true;
+  const CameraApertureTexture* multi_uploaded_ = nullptr;
   int device_id_;
   lfb_lens lens_;
   bool lens_dirty_ = true;

@@ -215,6 +215,17 @@ class PortOracle:
         assert rc == 0
         return (out, acc) if want_accum else out
 
+    def render_mt(self, lens, tex, lights, params, nthreads=None):
+        """render() on all host threads (the same bits: integer sums)."""
+        tex = np.ascontiguousarray(tex, np.float32)
+        out = np.zeros((params.height, params.width, 3))
+        f = self.lib.lfo_render_mt
+        f.argtypes = [C.POINTER(Lens), C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(Light), C.c_int, C.POINTER(Params), C.c_int, C.POINTER(C.c_double)]
+        rc = f(C.byref(lens), _fp(tex), tex.shape[1], tex.shape[0], lights_array(lights), len(lights), C.byref(params), nthreads or os.cpu_count() or 1,
+               _dp(out))
+        assert rc == 0
+        return out
+
     def starburst_pixels(self, tex, W, H, origins, radiances, flare_radius, flare_intensity, xs, ys):
         """-> (dft scalar (n,), deterministic falloff (n, 3))"""
         tex = np.ascontiguousarray(tex, np.float32)

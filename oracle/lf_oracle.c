@@ -890,9 +890,11 @@ static void* worker(void* arg) {
   return NULL;
 }
 
-/* Wall-clock of lfo_render's ghost jobs on nthreads pthreads: bench.py's cpu_baseline "port" leg (no reference counterpart). */
-double lfo_time_render(const lfb_lens* L, const float* tex, int tw, int th, const lfb_light* lights,
-                       int n_lights, const lfb_params* P, int nthreads, double* checksum) {
+/* lfo_render's ghost jobs on nthreads pthreads (jobs dealt round-robin, one private accumulator buffer per thread, summed
+ * as integers: the same bits as the single-threaded lfo_render).  Returns the wall-clock seconds; acc_out (optional)
+ * receives the W*H*3 sums. */
+static double render_threads(const lfb_lens* L, const float* tex, int tw, int th, const lfb_light* lights, int n_lights,
+                             const lfb_params* P, int nthreads, int64_t* acc_out, double* checksum) {
   if (nthreads < 1) nthreads = 1;
   const size_t npx = (size_t)P->width * P->height;
   job_t* J;
@@ -914,7 +916,30 @@ double lfo_time_render(const lfb_lens* L, const float* tex, int tw, int th, cons
   double s = 0;
   for (size_t p = 0; p < 3 * npx; p++) s += (double)W[0].acc[p];
   if (checksum) *checksum = s;
+  if (acc_out) memcpy(acc_out, W[0].acc, sizeof(int64_t) * 3 * npx);
   for (int t = 0; t < nthreads; t++) free(W[t].acc);
   free(W); free(T); free(J);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* Wall-clock of lfo_render's ghost jobs on nthreads pthreads: bench.py's cpu_baseline "port" leg (no reference counterpart). */
+double lfo_time_render(const lfb_lens* L, const float* tex, int tw, int th, const lfb_light* lights,
+                       int n_lights, const lfb_params* P, int nthreads, double* checksum) {
+  return render_threads(L, tex, tw, th, lights, n_lights, P, nthreads, NULL, checksum);
+}
+
+/* lfo_render (grid modes) on nthreads pthreads, for the full-size parity tests: out = W*H*3 doubles, the same bits as
+ * lfo_render's. */
+int lfo_render_mt(const lfb_lens* L, const float* tex, int tw, int th, const lfb_light* lights, int n_lights,
+                  const lfb_params* P, int nthreads, double* out) {
+  if (P->mode != LFB_MODE_PARAXIAL_GRID && P->mode != LFB_MODE_EXACT_GRID) return LFB_ERR_INVALID;
+  const size_t npx = (size_t)P->width * P->height;
+  int64_t* acc = (int64_t*)malloc(sizeof(int64_t) * 3 * npx);
+  if (!acc) return LFB_ERR_NOMEM;
+  render_threads(L, tex, tw, th, lights, n_lights, P, nthreads, acc, NULL);
+  const int bits = P->fixed_point_bits > 0 ? P->fixed_point_bits : 40;
+  const double inv = ldexp(1.0, -bits);
+  for (size_t p = 0; p < 3 * npx; p++) out[p] = (double)acc[p] * inv;
+  free(acc);
+  return LFB_OK;
 }

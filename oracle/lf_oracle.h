@@ -81,6 +81,10 @@ double lfo_time_render(const lfb_lens* lens, const float* tex, int tw, int th,
                        const lfb_light* lights, int n_lights, const lfb_params* params,
                        int nthreads, double* checksum);
 
+/* lfo_render (grid modes) on nthreads pthreads: the same bits (integer sums), for the full-size parity tests. */
+int lfo_render_mt(const lfb_lens* lens, const float* tex, int tw, int th, const lfb_light* lights, int n_lights,
+                  const lfb_params* params, int nthreads, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,8 @@ golden vectors of the compiled reference.  Tolerances (stated per test):
                                     (FP32 ulp at |x| = 150 is 1.5e-5, so an absolute 1e-5 is only claimed for the FP64
                                     kernels); images <= 1e-3 relative L2
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -878,3 +880,89 @@ def test_physical_mapping_vs_oracle(engine, port, apertures):
         # and it is a different picture from the reference's mapping
         q = capi.copy_params(p, physical_mapping=0)
         assert rel_l2(engine.render_ghosts(lt, q), want) > 0.1
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs at FULL SIZE against the oracle (multi-threaded, the same bits as its single-threaded render),
+# through the DEFAULT kernel selection
+# ---------------------------------------------------------------------------------------------
+def _kernel_choice(lens, tex, lights, p):
+    """Which throughput kernel the default selection picks for this frame (the counting build reports it)."""
+    e = capi.Engine(0, collect_stats=1)
+    try:
+        e.set_lens(lens)
+        e.set_aperture(tex)
+        e.render_ghosts(lights, p, elem=capi.F32x3)
+        st = e.exec_stats()
+        assert st["steps"] > 0 and st["ray_pairs_landed"] > 0
+        return "families" if st["families"] else "pairs"
+    finally:
+        e.close()
+
+
+def test_full_size_cfg2_vs_oracle(engine, port, apertures):
+    """BASELINE config 2 as bench.py runs it (RGB, 256^2 rays per ghost, 28 pairs + direct, coated, 1920x1080,
+    pentbig500_14): the FP32 frame is within 1e-3 relative L2 of the double oracle's (north_star's image bar), the STRICT
+    frame within 1e-5; the default selection runs the per-pair kernel here."""
+    lens = capi.builtin_lens(3, 550.0)
+    tex = apertures["pentbig500_14"]
+    engine.set_lens(lens)
+    engine.set_aperture(tex)
+    lt = [capi.make_light(0.45, 0.55, theta=capi.physical_theta(0.45, 0.55))]
+    p = capi.make_params(capi.MODE_EXACT_GRID, 1920, 1080, grid_n=256, pair_set=capi.PAIRS_ALL, include_direct=1)
+    want = port.render_mt(lens, tex, lt, p)
+    assert np.count_nonzero(want.sum(axis=2)) > 10000
+    e32 = rel_l2(engine.render_ghosts(lt, p), want)
+    e64 = rel_l2(engine.render_ghosts(lt, capi.copy_params(p, precision=capi.STRICT)), want)
+    assert e32 <= 1e-3 and e64 <= 1e-5, (e32, e64)
+    assert e32 <= 1e-4, e32  # measured ~1e-5: far inside the bar
+    assert _kernel_choice(lens, tex, lt, p) == "pairs"
+
+
+def test_full_size_cfg3_vs_oracle(engine, port, apertures):
+    """BASELINE config 3: 32 wavelengths (Cauchy n(lambda)), 550 nm coating, 1080p, 512^2 rays per ghost (256^2 when the box
+    has fewer than 16 host threads, to keep the oracle under ~30 s): FP32 within 1e-3 of the oracle, through the DEFAULT
+    selection -- which is the ghost-family kernel at this size."""
+    lens = capi.builtin_lens(32, 550.0)
+    tex = apertures["pentbig500_14"]
+    engine.set_lens(lens)
+    engine.set_aperture(tex)
+    lt = [capi.make_light(0.45, 0.55, theta=capi.physical_theta(0.45, 0.55), radiance=(1.0, 0.9, 0.8))]
+    grid = 512 if (os.cpu_count() or 1) >= 16 else 256
+    p = capi.make_params(capi.MODE_EXACT_GRID, 1920, 1080, grid_n=grid, pair_set=capi.PAIRS_ALL, include_direct=1)
+    want = port.render_mt(lens, tex, lt, p)
+    assert np.count_nonzero(want.sum(axis=2)) > 10000
+    e32 = rel_l2(engine.render_ghosts(lt, p), want)
+    assert e32 <= 1e-3, e32
+    e64 = rel_l2(engine.render_ghosts(lt, capi.copy_params(p, precision=capi.STRICT)), want)
+    assert e64 <= 1e-5, e64
+    assert _kernel_choice(lens, tex, lt, p) == "families"
+    engine.set_lens(capi.builtin_lens(3))
+
+
+def test_full_size_cfg4_shape_vs_oracle(port, apertures):
+    """BASELINE config 4's shape on one GPU: 3840x2160 sensor, RGB, 1024^2 rays per ghost, several suns of the 8x8 lattice
+    (4; 2 on a box with fewer than 16 host threads -- the full 64 need ~10 minutes of oracle), default selection (families):
+    FP32 within 1e-3 of the oracle, and the frame equals the sum of its 8 shards bit for bit."""
+    lens = capi.builtin_lens(3, 550.0)
+    tex = apertures["pentbig500_14"]
+    n_l = 4 if (os.cpu_count() or 1) >= 16 else 2
+    lattice = [(0.1 + 0.8 * a / 7, 0.1 + 0.8 * b / 7) for a, b in ((2, 5), (5, 2), (3, 3), (6, 6))][:n_l]
+    lt = [capi.make_light(x, y, theta=capi.physical_theta(x, y), radiance=(1.0, 0.8 + 0.05 * k, 0.6)) for k, (x, y) in enumerate(lattice)]
+    p = capi.make_params(capi.MODE_EXACT_GRID, 3840, 2160, grid_n=1024, pair_set=capi.PAIRS_ALL, include_direct=1, px_per_unit=0.8)
+    want = port.render_mt(lens, tex, lt, p)
+    assert np.count_nonzero(want.sum(axis=2)) > 50000
+    e = capi.Engine(0)
+    try:
+        e.set_lens(lens)
+        e.set_aperture(tex)
+        got = e.render_ghosts(lt, p)
+        err = rel_l2(got, want)
+        assert err <= 1e-3, err
+        parts = np.zeros_like(got)
+        for r in range(8):
+            parts += e.render_ghosts(lt, capi.copy_params(p, shard=(r, 8)))
+        assert np.array_equal(parts, got)
+    finally:
+        e.close()
+    assert _kernel_choice(lens, tex, lt, p) == "families"
