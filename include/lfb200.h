@@ -285,6 +285,45 @@ int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, int n_lights,
                            double flare_radius, double flare_intensity, const double* base_hdr,
                            uint32_t* out_rgba8, int flip_vertical);
 
+/* ---- the path-traced scene pass (BASELINE config 5) ------- */
+/* A scene as plain arrays (the reference's COLLADA loader, GUI and tile pool are out of scope; the application hands over what
+ * it loaded).  Replaces what PathTracer::set_scene / build_accel give raytrace_pixel: the primitives of Scene::objects
+ * (Triangle, scene/triangle.h; Sphere, scene/sphere.h), their BSDFs (DiffuseBSDF / EmissionBSDF, pathtracer/bsdf.h) and
+ * Scene::lights (DirectionalLight / PointLight, scene/light.h; area lights are sampled randomly in the reference and are not
+ * supported).  The engine copies everything and builds its own BVH. */
+typedef struct lfb_scene {
+  const double* tri_pos;    /* [n_tri][3][3] vertex positions (Triangle::p1, p2, p3) */
+  const double* tri_nrm;    /* [n_tri][3][3] vertex normals (Triangle::n1, n2, n3) */
+  const int32_t* tri_mat;   /* [n_tri] material index */
+  int32_t n_tri, n_sph;
+  const double* spheres;    /* [n_sph][4] centre, radius */
+  const int32_t* sph_mat;   /* [n_sph] */
+  const double* materials;  /* [n_mat][6] reflectance rgb, emission rgb: any emission > 0 -> EmissionBSDF, else DiffuseBSDF */
+  const double* lights;     /* [n_lights][7] kind (0 directional: vec = the direction the light travels; 1 point: vec = position),
+                               radiance rgb, vec xyz */
+  int32_t n_mat, n_lights;
+} lfb_scene;
+/* The pinhole camera of Camera::generate_ray (camera.cpp:278-305): position, camera-to-world rotation (row-major; the camera
+ * looks down its -z), fields of view in degrees, clip distances. */
+typedef struct lfb_camera {
+  double pos[3];
+  double c2w[9];
+  double hfov_deg, vfov_deg, nclip, fclip;
+} lfb_camera;
+int lfb_set_scene(lfb_engine* e, const lfb_scene* scene);
+/* Replaces the path-traced term of PathTracer::raytrace_pixel (pathtracer.cpp:819-899) for the WHOLE frame:
+ * est_radiance_global_illumination (:279-302) as the reference has it -- the hit surface's emission plus direct lighting by
+ * light sampling with shadow rays (:136-231; the indirect bounces are commented out there) -- along the camera ray through
+ * every pixel CENTRE (the reference jitters ns_aa samples with its global RNG).  out: as lfb_render_ghosts; additive = 1 adds
+ * into the caller's sampleBuffer-like frame. */
+int lfb_render_scene(lfb_engine* e, const lfb_camera* camera, int width, int height, void* out, size_t out_stride_bytes,
+                     int out_elem, int additive);
+/* BASELINE config 5 in one call: scene pass + ghosts + [starburst] composited on the device exactly as raytrace_pixel sums them
+ * (:881-891), then HDRImageBuffer::toColor and the RGBA8 pack (as lfb_render_frame_rgba8, whose other arguments these are). */
+int lfb_render_composite_rgba8(lfb_engine* e, const lfb_camera* camera, const lfb_light* lights, int n_lights,
+                               const lfb_params* params, double flare_radius, double flare_intensity, uint32_t* out_rgba8,
+                               int flip_vertical);
+
 /* ---- device-resident API (multi-GPU sharding, benchmarking) ------------- */
 /* No reference counterparts in this section: the reference is a single-process CPU program.  Together these calls are
  * generate_ghost_buffer (pathtracer.cpp:714-762) split into its device stages so that one process per GPU can shard a

@@ -30,7 +30,7 @@ RAY_MISSED, RAY_VIGNETTED, RAY_TIR, RAY_STOPPED, RAY_OFF_SENSOR = 1, 2, 4, 8, 16
 
 # every symbol include/lfb200.h declares (tests check the library exports each one)
 SYMBOLS = (
-    "lfb_abi_version", "lfb_create", "lfb_create_ex", "lfb_exec_stats", "lfb_create_multi", "lfb_destroy_multi", "lfb_multi_set_lens", "lfb_multi_set_aperture", "lfb_render_ghosts_multi", "lfb_multi_stats", "lfb_render_ghosts_sparse", "lfb_tile_state_bytes", "lfb_finalize_tiles_device", "lfb_reduce_tiles_peers", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
+    "lfb_abi_version", "lfb_create", "lfb_create_ex", "lfb_exec_stats", "lfb_set_scene", "lfb_render_scene", "lfb_render_composite_rgba8", "lfb_create_multi", "lfb_destroy_multi", "lfb_multi_set_lens", "lfb_multi_set_aperture", "lfb_render_ghosts_multi", "lfb_multi_stats", "lfb_render_ghosts_sparse", "lfb_tile_state_bytes", "lfb_finalize_tiles_device", "lfb_reduce_tiles_peers", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
     "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_render_ghosts_async", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
     "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_reduce_finalize_peers", "lfb_peer_barrier", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
     "lfb_host_alloc", "lfb_host_free", "lfb_host_register", "lfb_host_unregister", "lfb_host_device_pointer", "lfb_finalize_clear_device", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
@@ -82,6 +82,29 @@ def make_options(**fields):
     for k, v in fields.items():
         setattr(o, k, v)
     return o
+
+
+class Scene(C.Structure):
+    """lfb_scene: plain arrays (layouts in include/lfb200.h)."""
+    _fields_ = [("tri_pos", C.POINTER(C.c_double)), ("tri_nrm", C.POINTER(C.c_double)), ("tri_mat", C.POINTER(C.c_int32)),
+                ("n_tri", C.c_int32), ("n_sph", C.c_int32), ("spheres", C.POINTER(C.c_double)), ("sph_mat", C.POINTER(C.c_int32)),
+                ("materials", C.POINTER(C.c_double)), ("lights", C.POINTER(C.c_double)), ("n_mat", C.c_int32), ("n_lights", C.c_int32)]
+
+
+class Camera(C.Structure):
+    """lfb_camera: the pinhole camera of Camera::generate_ray (camera.cpp:278-305)."""
+    _fields_ = [("pos", C.c_double * 3), ("c2w", C.c_double * 9), ("hfov_deg", C.c_double), ("vfov_deg", C.c_double),
+                ("nclip", C.c_double), ("fclip", C.c_double)]
+
+
+def make_camera(cam16):
+    """cam16 = pos xyz, c2w rows, hFov, vFov (degrees), nClip, fClip (tests/scene_fixtures.py, oracle/ref_shim.cpp)."""
+    c = Camera()
+    a = [float(v) for v in cam16]
+    c.pos[:] = a[0:3]
+    c.c2w[:] = a[3:12]
+    c.hfov_deg, c.vfov_deg, c.nclip, c.fclip = a[12:16]
+    return c
 
 
 RAY_HIT_DTYPE = np.dtype([("x_s", "f8"), ("y_s", "f8"), ("x_ap", "f8"), ("y_ap", "f8"), ("px", "f8"),
@@ -192,6 +215,9 @@ def lib():
     L.lfb_multi_set_aperture.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.c_int]
     L.lfb_render_ghosts_multi.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.lfb_multi_stats.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.lfb_set_scene.argtypes = [vp, C.POINTER(Scene)]
+    L.lfb_render_scene.argtypes = [vp, C.POINTER(Camera), C.c_int, C.c_int, vp, C.c_size_t, C.c_int, C.c_int]
+    L.lfb_render_composite_rgba8.argtypes = [vp, C.POINTER(Camera), LiP, C.c_int, PP, C.c_double, C.c_double, vp, C.c_int]
     L.lfb_dump_rays.argtypes = [vp, LiP, PP, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]
     L.lfb_ref_ghosts.argtypes = [vp, vp, C.c_int]
     L.lfb_accum_bytes.argtypes = [C.c_int, C.c_int]
@@ -388,6 +414,35 @@ class Engine:
     def reduce_tiles_peers(self, accum_ptrs, rank, params, out_ptr, stride, elem, state_ptr):
         arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)
         check(lib().lfb_reduce_tiles_peers(self._h, arr, len(accum_ptrs), rank, C.byref(params), out_ptr, stride, elem, state_ptr))
+
+    def set_scene(self, scene):
+        """scene: dict of arrays (tri_pos [n,3,3], tri_nrm [n,3,3], tri_mat [n], spheres [m,4], sph_mat [m], mats [k,6], lights [l,7])."""
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        tp = np.ascontiguousarray(scene["tri_pos"], np.float64)
+        tn = np.ascontiguousarray(scene["tri_nrm"], np.float64)
+        tm = np.ascontiguousarray(scene["tri_mat"], np.int32)
+        sp = np.ascontiguousarray(scene["spheres"], np.float64).reshape(-1, 4)
+        sm = np.ascontiguousarray(scene["sph_mat"], np.int32)
+        ma = np.ascontiguousarray(scene["mats"], np.float64).reshape(-1, 6)
+        li = np.ascontiguousarray(scene["lights"], np.float64).reshape(-1, 7)
+        sc = Scene(tp.ctypes.data_as(dp), tn.ctypes.data_as(dp), tm.ctypes.data_as(ip), tm.size, sm.size, sp.ctypes.data_as(dp), sm.ctypes.data_as(ip),
+                   ma.ctypes.data_as(dp), li.ctypes.data_as(dp), ma.shape[0], li.shape[0])
+        check(lib().lfb_set_scene(self._h, C.byref(sc)))
+
+    def render_scene(self, camera, width, height, out=None, elem=F64x3, additive=False):
+        """The path-traced scene pass (emission + direct lighting) for the whole frame: (H, W, 3)."""
+        if out is None:
+            out = np.zeros((height, width, 3), np.float64 if elem == F64x3 else np.float32)
+        check(lib().lfb_render_scene(self._h, C.byref(camera), width, height, out.ctypes.data, out.strides[1], elem, int(additive)))
+        return out
+
+    def render_composite_rgba8(self, camera, lights, params, flare_radius=-1.0, flare_intensity=1.0, out=None, flip=False):
+        """scene pass + ghosts + [starburst] -> toColor -> (H, W) uint32: BASELINE config 5 in one call."""
+        if out is None:
+            out = np.empty((params.height, params.width), np.uint32)
+        check(lib().lfb_render_composite_rgba8(self._h, C.byref(camera), lights_array(lights), len(lights), C.byref(params), flare_radius,
+                                               flare_intensity, out.ctypes.data, int(flip)))
+        return out
 
     def set_starburst_aperture(self, texels):
         tex = np.ascontiguousarray(texels, np.float32)

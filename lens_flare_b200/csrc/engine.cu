@@ -234,6 +234,7 @@ struct lfb_engine {
   unsigned* h_count = nullptr;  // page-locked, mapped: tiles written by the last sparse launch
   bool accum_clean = false;     // d_accum (sums and bitmap) is all zeros for a accum_clean_w x accum_clean_h frame
   int accum_clean_w = 0, accum_clean_h = 0;
+  SceneStore* scene = nullptr;  // lfb_set_scene
   uint64_t launches = 0;
   float last_trace_ms = 0, last_frame_ms = 0;
 };
@@ -911,6 +912,7 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   cudaFree(e->d_star_tex); cudaFree(e->d_star_scratch); cudaFree(e->d_star_lights); cudaFree(e->d_hdr); cudaFree(e->d_rgba);
   if (e->h_bbox) cudaFreeHost(e->h_bbox);
   if (e->h_count) cudaFreeHost(e->h_count);
+  scene_free(e->scene);
   cudaFree(e->d_sparse_state);
   if (e->h_progs) cudaFreeHost(e->h_progs);
   cudaFree(e->d_tex); cudaFree(e->d_jobs); cudaFree(e->d_dump_job); cudaFree(e->d_accum); cudaFree(e->d_out);
@@ -1635,24 +1637,29 @@ extern "C" int lfb_render_starburst(lfb_engine* e, const lfb_light* lights, int 
 // i.e. what raytrace_pixel (:881-891) + raytrace_tile's toColor + frameBuffer do for the flare terms.  base_hdr (optional,
 // host, W*H F64x3 packed) is the path-traced radiance to composite over; flare_radius < 0 skips the starburst;
 // flip_vertical = 1 applies save_image's row flip (raytraced_renderer.cpp:739-742).  4 bytes per pixel cross PCIe, not 24.
-extern "C" int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P,
-                                      double flare_radius, double flare_intensity, const double* base_hdr, uint32_t* out_rgba8,
-                                      int flip_vertical) {
-  int rc = bind(e);
-  if (rc) return rc;
+namespace {
+// [base | scene pass] + ghosts + [starburst] -> toColor -> RGBA8, everything device-resident until the 8-bit frame comes back
+int frame_rgba8(lfb_engine* e, const lfb_camera* cam, const lfb_light* lights, int n_lights, const lfb_params* P, double flare_radius,
+                double flare_intensity, const double* base_hdr, uint32_t* out_rgba8, int flip_vertical) {
   if (!e->has_lens || !e->has_tex) return fail(LFB_ERR_STATE, "set the lens and the aperture first");
-  rc = check_params(P, false);
+  int rc = check_params(P, false);
   if (rc) return rc;
   if (n_lights < 0 || (n_lights > 0 && !lights) || !out_rgba8) return fail(LFB_ERR_INVALID, "bad lights/out");
+  if (cam && !e->scene) return fail(LFB_ERR_STATE, "set the scene first (lfb_set_scene)");
   const size_t npx = (size_t)P->width * P->height;
   rc = grow(&e->d_hdr, &e->hdr_cap, npx * 24);
   if (rc) return rc;
   rc = grow(&e->d_rgba, &e->rgba_cap, npx * 4);
   if (rc) return rc;
   CU(cudaEventRecord(e->ev_frame0, e->stream));
+  const bool have_base = base_hdr || cam;
   if (base_hdr) CU(cudaMemcpyAsync(e->d_hdr, base_hdr, npx * 24, cudaMemcpyHostToDevice, e->stream));
+  if (cam) {
+    CU(launch_scene(e->scene, cam, P->width, P->height, e->d_hdr, 24, LFB_F64x3, base_hdr ? 1 : 0, e->stream));
+    e->launches++;
+  }
   if (P->mode == LFB_MODE_REF_QUADS) {
-    rc = render_ref_device(e, lights, n_lights, *P, e->d_hdr, 24, LFB_F64x3, base_hdr ? 1 : 0);
+    rc = render_ref_device(e, lights, n_lights, *P, e->d_hdr, 24, LFB_F64x3, have_base ? 1 : 0);
     if (rc) return rc;
   } else {
     rc = grow(&e->d_accum, &e->accum_cap, lfb_accum_bytes(P->width, P->height));
@@ -1662,7 +1669,7 @@ extern "C" int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, in
     rc = render_grid_device(e, lights, n_lights, *P, e->d_accum, 1);
     if (rc) return rc;
     const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
-    CU(launch_finalize(e->d_accum, P->width, P->height, inv, e->d_hdr, 24, LFB_F64x3, base_hdr ? 1 : 0, e->stream));
+    CU(launch_finalize(e->d_accum, P->width, P->height, inv, e->d_hdr, 24, LFB_F64x3, have_base ? 1 : 0, e->stream));
     e->launches++;
   }
   if (flare_radius >= 0 && n_lights > 0) {
@@ -1677,6 +1684,74 @@ extern "C" int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, in
   CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
   CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
   return LFB_OK;
+}
+}  // namespace
+
+extern "C" int lfb_render_frame_rgba8(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P,
+                                      double flare_radius, double flare_intensity, const double* base_hdr, uint32_t* out_rgba8,
+                                      int flip_vertical) {
+  int rc = bind(e);
+  if (rc) return rc;
+  return frame_rgba8(e, nullptr, lights, n_lights, P, flare_radius, flare_intensity, base_hdr, out_rgba8, flip_vertical);
+}
+
+// ---------------------------------------------------------------------------
+// the path-traced scene pass (scene.cu)
+// ---------------------------------------------------------------------------
+extern "C" int lfb_set_scene(lfb_engine* e, const lfb_scene* sc) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!sc) return fail(LFB_ERR_INVALID, "scene is NULL");
+  if (sc->n_tri < 0 || sc->n_sph < 0 || sc->n_mat < 1 || sc->n_lights < 0) return fail(LFB_ERR_INVALID, "negative counts (or no material)");
+  if ((sc->n_tri > 0 && (!sc->tri_pos || !sc->tri_nrm || !sc->tri_mat)) || (sc->n_sph > 0 && (!sc->spheres || !sc->sph_mat)) || !sc->materials ||
+      (sc->n_lights > 0 && !sc->lights))
+    return fail(LFB_ERR_INVALID, "NULL scene array");
+  CU(cudaStreamSynchronize(e->stream));
+  SceneStore* st = nullptr;
+  const char* msg = nullptr;
+  const cudaError_t err = scene_upload(sc, &st, &msg);
+  if (msg) return fail(LFB_ERR_INVALID, msg);
+  if (err == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(LFB_ERR_NOMEM, "cudaMalloc: out of device memory"); }
+  if (err != cudaSuccess) return fail_cuda(err, "lfb_set_scene");
+  scene_free(e->scene);
+  e->scene = st;
+  return LFB_OK;
+}
+
+extern "C" int lfb_render_scene(lfb_engine* e, const lfb_camera* cam, int width, int height, void* out, size_t stride, int elem, int additive) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!e->scene) return fail(LFB_ERR_STATE, "set the scene first (lfb_set_scene)");
+  if (!cam) return fail(LFB_ERR_INVALID, "camera is NULL");
+  if (width < 1 || height < 1 || width > 32768 || height > 32768) return fail(LFB_ERR_INVALID, "frame size out of range");
+  rc = check_out_args(out, stride, elem);
+  if (rc) return rc;
+  const size_t npx = (size_t)width * height;
+  const size_t out_bytes = (npx - 1) * stride + elem_bytes(elem);
+  rc = grow(&e->d_out, &e->out_cap, out_bytes);
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev_frame0, e->stream));
+  if (additive) CU(cudaMemcpyAsync(e->d_out, out, out_bytes, cudaMemcpyHostToDevice, e->stream));
+  else if (stride != elem_bytes(elem)) CU(cudaMemsetAsync(e->d_out, 0, out_bytes, e->stream));
+  CU(cudaEventRecord(e->ev_trace0, e->stream));
+  CU(launch_scene(e->scene, cam, width, height, e->d_out, stride, elem, additive, e->stream));
+  e->launches++;
+  CU(cudaEventRecord(e->ev_trace1, e->stream));
+  CU(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaEventRecord(e->ev_frame1, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
+  CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
+  e->timed = true;
+  return LFB_OK;
+}
+
+extern "C" int lfb_render_composite_rgba8(lfb_engine* e, const lfb_camera* cam, const lfb_light* lights, int n_lights, const lfb_params* P,
+                                          double flare_radius, double flare_intensity, uint32_t* out_rgba8, int flip_vertical) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (!cam) return fail(LFB_ERR_INVALID, "camera is NULL");
+  return frame_rgba8(e, cam, lights, n_lights, P, flare_radius, flare_intensity, nullptr, out_rgba8, flip_vertical);
 }
 
 // ---------------------------------------------------------------------------

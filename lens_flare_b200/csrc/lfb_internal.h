@@ -247,6 +247,12 @@ cudaError_t launch_starburst(const StarFrame& f, const float* tex, void* scratch
                              const double rad_sum[3], void* out, size_t stride, int elem, int additive, bool spectrum_cached, cudaStream_t s,
                              int* launches);
 
+// scene.cu: the path-traced scene pass
+struct SceneStore;
+cudaError_t scene_upload(const lfb_scene* sc, SceneStore** out, const char** err_msg);
+void scene_free(SceneStore* s);
+cudaError_t launch_scene(const SceneStore* s, const lfb_camera* cam, int W, int H, void* out, size_t stride, int elem, int additive, cudaStream_t st);
+
 cudaError_t launch_to_color(const double* hdr, int W, int H, uint32_t* out, int flip, cudaStream_t s);
 
 cudaError_t probe_peaks(int device, cudaStream_t s, double* fp32_flops, double* mufu_ops, double* sm_clock_hz);

@@ -82,6 +82,13 @@ class RefOracle:
           xs.ctypes.data_as(C.POINTER(C.c_int)), ys.ctypes.data_as(C.POINTER(C.c_int)), xs.size, _dp(out))
         return out
 
+    def scene_radiance(self, scene, cam, W, H):
+        """PathTracer::est_radiance_global_illumination of the compiled reference over its own BVH, per pixel centre."""
+        self.lib.ref_scene_radiance.argtypes = SCENE_ARGTYPES
+        keep, out, args = _scene_args(scene, cam, W, H)
+        assert self.lib.ref_scene_radiance(*args) == 0
+        return out
+
     def to_color(self, hdr):
         hdr = np.ascontiguousarray(hdr, np.float64)
         out = np.zeros(hdr.shape[:2], np.uint32)
@@ -149,8 +156,35 @@ class RefOracle:
         return out
 
 
+def _scene_args(scene, cam, W, H):
+    """ctypes arguments of ref_scene_radiance / lfo_scene_radiance (layouts: oracle/ref_shim.cpp)."""
+    tp = np.ascontiguousarray(scene["tri_pos"], np.float64)
+    tn = np.ascontiguousarray(scene["tri_nrm"], np.float64)
+    tm = np.ascontiguousarray(scene["tri_mat"], np.int32)
+    sp = np.ascontiguousarray(scene["spheres"], np.float64).reshape(-1, 4)
+    sm = np.ascontiguousarray(scene["sph_mat"], np.int32)
+    ma = np.ascontiguousarray(scene["mats"], np.float64)
+    li = np.ascontiguousarray(scene["lights"], np.float64)
+    ca = np.ascontiguousarray(cam, np.float64)
+    out = np.zeros((H, W, 3))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))  # noqa: E731
+    keep = (tp, tn, tm, sp, sm, ma, li, ca)
+    return keep, out, [_dp(tp), _dp(tn), ip(tm), tm.size, _dp(sp), ip(sm), sm.size, _dp(ma), ma.shape[0], _dp(li), li.shape[0], _dp(ca), W, H, _dp(out)]
+
+
+SCENE_ARGTYPES = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int,
+                  C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_double)]
+
+
 class PortOracle:
     """The C restatement (oracle/lf_oracle.c)."""
+
+    def scene_radiance(self, scene, cam, W, H):
+        """The path-traced scene pass (emission + direct lighting of delta lights) per pixel centre: (H, W, 3)."""
+        self.lib.lfo_scene_radiance.argtypes = SCENE_ARGTYPES
+        keep, out, args = _scene_args(scene, cam, W, H)
+        assert self.lib.lfo_scene_radiance(*args) == 0
+        return out
 
     def __init__(self, path=PORT_SO):
         self.lib = L = C.CDLL(path)

@@ -943,3 +943,159 @@ int lfo_render_mt(const lfb_lens* L, const float* tex, int tw, int th, const lfb
   free(acc);
   return LFB_OK;
 }
+
+/* ------------------------------------------------------------------------- */
+/* path-traced scene pass, restated                             */
+/* ------------------------------------------------------------------------- */
+/* PathTracer::est_radiance_global_illumination (pathtracer.cpp:279-302) as the reference has it TODAY: zero_bounce_radiance
+ * (:213-218, the surface's emission) + one_bounce_radiance (:220-231) = estimate_direct_lighting_importance (:136-211); the
+ * indirect bounces are commented out there (:299).  For delta lights (DirectionalLight / PointLight, scene/light.cpp:11-24,
+ * 49-60: one sample, pdf 1) the estimate is deterministic.  Primary rays: Camera::generate_ray (camera.cpp:278-305) through
+ * the pixel centres.  Nearest hit by brute force over Triangle::intersect (scene/triangle.cpp:26-113: Moeller-Trumbore, hits
+ * with t in [min_t, max_t], barycentrics in [0, 1], interpolated unit normal) and Sphere::intersect (scene/sphere.cpp:11-108);
+ * the reference's BVH (scene/bvh.cpp) only changes the order of equal-t ties.  DiffuseBSDF::f = reflectance / pi,
+ * EmissionBSDF::f = 0 (pathtracer/bsdf.cpp:58-61, 87-89).  Array layouts: oracle/ref_shim.cpp ref_scene_radiance.
+ * PINNED against the compiled reference (tests/test_scene_pass.py, tests/golden/scene.npz). */
+typedef struct { double o[3], d[3], min_t, max_t; } sray_t;
+typedef struct { double t, n[3]; int mat; } shit_t;
+
+static double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+static void unit3(const double* a, double* u) { /* vector3D.h:215-218: multiply by the reciprocal norm */
+  double r = 1. / sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  u[0] = a[0] * r; u[1] = a[1] * r; u[2] = a[2] * r;
+}
+
+static int tri_hit(const double* P, const double* N, sray_t* r, shit_t* h) { /* triangle.cpp:26-113 */
+  const double *p0 = P, *p1 = P + 3, *p2 = P + 6;
+  double e1[3], e2[3], s[3], s1[3], s2[3];
+  for (int a = 0; a < 3; a++) { e1[a] = p1[a] - p0[a]; e2[a] = p2[a] - p0[a]; s[a] = r->o[a] - p0[a]; }
+  cross3(r->d, e2, s1);
+  cross3(s, e1, s2);
+  double den = dot3(s1, e1);
+  double t = dot3(s2, e2) / den, b1 = dot3(s1, s) / den, b2 = dot3(s2, r->d) / den;
+  if (t < r->min_t || t > r->max_t) return 0;
+  if (b1 < 0 || b1 > 1) return 0;
+  if (b2 < 0 || b2 > 1) return 0;
+  if (b1 + b2 > 1) return 0;
+  if (!(t == t) || !(b1 == b1) || !(b2 == b2)) return 0; /* NaN (a ray parallel to a degenerate configuration): not a hit here */
+  if (!h) return 1;
+  double b0 = 1 - b1 - b2, n[3];
+  for (int a = 0; a < 3; a++) n[a] = b0 * N[a] + b1 * N[3 + a] + b2 * N[6 + a];
+  r->max_t = t;
+  h->t = t;
+  unit3(n, h->n);
+  return 1;
+}
+
+static int sph_hit(const double* S, sray_t* r, shit_t* h) { /* sphere.cpp:11-108 */
+  double oc[3] = {r->o[0] - S[0], r->o[1] - S[1], r->o[2] - S[2]};
+  double a = dot3(r->d, r->d), b = 2 * dot3(oc, r->d), c = dot3(oc, oc) - S[3] * S[3];
+  double t1;
+  if (b * b < 4.0 * a * c) return 0;
+  if (b * b == 4.0 * a * c) {
+    double root = (-b) / (2.0 * a);
+    if (root < r->min_t || root > r->max_t) return 0;
+    t1 = root;
+  } else {
+    double q = sqrt(b * b - 4.0 * a * c);
+    double r1 = (-b - q) / (2.0 * a), r2 = (-b + q) / (2.0 * a);
+    double lo = r1 < r2 ? r1 : r2, hi = r1 < r2 ? r2 : r1;
+    if (lo > r->max_t || hi < r->min_t) return 0;
+    if (lo < r->min_t) {
+      if (hi > r->max_t) return 0;
+      t1 = hi;
+    } else {
+      t1 = lo;
+    }
+  }
+  if (!h) return 1;
+  r->max_t = t1;
+  h->t = t1;
+  double p[3] = {r->o[0] + t1 * r->d[0] - S[0], r->o[1] + t1 * r->d[1] - S[1], r->o[2] + t1 * r->d[2] - S[2]};
+  unit3(p, h->n);
+  return 1;
+}
+
+typedef struct {
+  const double *tri_pos, *tri_nrm, *sph; const int *tri_mat, *sph_mat; int nt, ns;
+} sscene_t;
+
+static int scene_hit(const sscene_t* S, sray_t* r, shit_t* h) {
+  int hit = 0;
+  for (int t = 0; t < S->nt; t++)
+    if (tri_hit(S->tri_pos + 9 * t, S->tri_nrm + 9 * t, r, h)) { hit = 1; if (h) h->mat = S->tri_mat[t]; else return 1; }
+  for (int k = 0; k < S->ns; k++)
+    if (sph_hit(S->sph + 4 * k, r, h)) { hit = 1; if (h) h->mat = S->sph_mat[k]; else return 1; }
+  return hit;
+}
+
+int lfo_scene_radiance(const double* tri_pos, const double* tri_nrm, const int* tri_mat, int nt, const double* sph,
+                       const int* sph_mat, int ns, const double* mats, int nm, const double* lights, int nl,
+                       const double* cam, int W, int H, double* out) {
+  (void)nm;
+  const sscene_t S = {tri_pos, tri_nrm, sph, tri_mat, sph_mat, nt, ns};
+  const double pi = 3.14159265358979323846264338327950288; /* CGL's PI */
+  const double ex = tan(0.5 * (cam[12] * (pi / 180.0))), ey = tan(0.5 * (cam[13] * (pi / 180.0)));
+  const float eps_f = 0.00001f; /* EPS_F, CGL/misc.h:13 */
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      double* o = out + 3 * ((size_t)x + (size_t)y * W);
+      o[0] = o[1] = o[2] = 0;
+      /* Camera::generate_ray */
+      double cx = ex * (2 * ((x + 0.5) / (double)W) - 1), cy = ey * (2 * ((y + 0.5) / (double)H) - 1);
+      double dcam[3] = {cx, cy, -1}, du[3];
+      unit3(dcam, du);
+      sray_t r;
+      for (int a = 0; a < 3; a++) {
+        r.o[a] = cam[a];
+        r.d[a] = cam[3 + 3 * a] * du[0] + cam[3 + 3 * a + 1] * du[1] + cam[3 + 3 * a + 2] * du[2];
+      }
+      r.min_t = cam[14]; r.max_t = cam[15];
+      shit_t h;
+      if (!scene_hit(&S, &r, &h)) continue; /* envLight == NULL: black */
+      const double* M = mats + 6 * h.mat;
+      const int emissive = M[3] > 0 || M[4] > 0 || M[5] > 0;
+      double Lz[3] = {emissive ? M[3] : 0, emissive ? M[4] : 0, emissive ? M[5] : 0}; /* zero bounce */
+      /* make_coord_space (bsdf.cpp:20-43) */
+      double z[3] = {h.n[0], h.n[1], h.n[2]}, hh[3] = {h.n[0], h.n[1], h.n[2]}, xx[3], yy[3];
+      if (fabs(hh[0]) <= fabs(hh[1]) && fabs(hh[0]) <= fabs(hh[2])) hh[0] = 1.0;
+      else if (fabs(hh[1]) <= fabs(hh[0]) && fabs(hh[1]) <= fabs(hh[2])) hh[1] = 1.0;
+      else hh[2] = 1.0;
+      { double nz = sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]); z[0] /= nz; z[1] /= nz; z[2] /= nz; }
+      cross3(hh, z, yy);
+      { double ny = sqrt(yy[0] * yy[0] + yy[1] * yy[1] + yy[2] * yy[2]); yy[0] /= ny; yy[1] /= ny; yy[2] /= ny; }
+      cross3(z, yy, xx);
+      { double nx = sqrt(xx[0] * xx[0] + xx[1] * xx[1] + xx[2] * xx[2]); xx[0] /= nx; xx[1] /= nx; xx[2] /= nx; }
+      double hit_p[3] = {r.o[0] + r.d[0] * h.t, r.o[1] + r.d[1] * h.t, r.o[2] + r.d[2] * h.t};
+      double Ld[3] = {0, 0, 0};
+      for (int l = 0; l < nl; l++) {
+        const double* A = lights + 7 * l;
+        double wi[3], dist;
+        if (A[0] == 0) { /* DirectionalLight: dirToLight = -lightDir.unit() */
+          double u[3];
+          unit3(A + 4, u);
+          wi[0] = -u[0]; wi[1] = -u[1]; wi[2] = -u[2];
+          dist = INFINITY;
+        } else { /* PointLight */
+          double d[3] = {A[4] - hit_p[0], A[5] - hit_p[1], A[6] - hit_p[2]};
+          unit3(d, wi);
+          dist = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        }
+        double wo[3] = {dot3(xx, wi), dot3(yy, wi), dot3(z, wi)}; /* w2o * wi */
+        if (wo[2] < 0) continue;
+        sray_t sh;
+        for (int a = 0; a < 3; a++) { sh.o[a] = hit_p[a]; sh.d[a] = wi[a]; }
+        sh.min_t = eps_f; sh.max_t = dist - eps_f;
+        if (scene_hit(&S, &sh, NULL)) continue;
+        double wu[3];
+        unit3(wo, wu);
+        if (!emissive)
+          for (int c = 0; c < 3; c++) Ld[c] += (((1.0 / pi) * M[c]) * A[1 + c] * wu[2]) / 1.0;
+      }
+      for (int c = 0; c < 3; c++) o[c] = Lz[c] + (nl > 0 ? Ld[c] / (double)nl : 0.0);
+    }
+  return LFB_OK;
+}

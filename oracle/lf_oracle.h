@@ -85,6 +85,13 @@ double lfo_time_render(const lfb_lens* lens, const float* tex, int tw, int th,
 int lfo_render_mt(const lfb_lens* lens, const float* tex, int tw, int th, const lfb_light* lights, int n_lights,
                   const lfb_params* params, int nthreads, double* out);
 
+/* The path-traced scene pass as the reference computes it today (pathtracer.cpp:279-302: emission + direct lighting by
+ * light sampling; delta lights only -> deterministic), per pixel centre, brute-force nearest hit.  Layouts as
+ * oracle/ref_shim.cpp ref_scene_radiance.  PINNED against the compiled reference. */
+int lfo_scene_radiance(const double* tri_pos, const double* tri_nrm, const int* tri_mat, int nt, const double* sph,
+                       const int* sph_mat, int ns, const double* mats, int nm, const double* lights, int nl,
+                       const double* cam, int W, int H, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,12 @@
 #include "pathtracer/camera.h"
 #undef private
 #include "pathtracer/pathtracer.h"
+#include "pathtracer/bsdf.h"
+#include "scene/bvh.h"
 #include "scene/light.h"
+#include "scene/object.h"
+#include "scene/sphere.h"
+#include "scene/triangle.h"
 #include "util/image.h"
 
 #include <chrono>
@@ -31,11 +36,10 @@ extern float curvatures[], red_refr[], green_refr[], blue_refr[];
 Vector2D trace_ray_auto_before(float r, float theta, int i, int j, std::vector<Matrix3x3> color_R);
 Vector2D trace_ray_auto_after(float r, float theta, int i, int j, std::vector<Matrix3x3> color_R);
 
-// Three path-tracer symbols that pathtracer.o references but the ghost/starburst
-// path never calls (bsdf.cpp, bvh.cpp, environment_light.cpp are not linked).
-void make_coord_space(Matrix3x3&, Vector3D) { std::abort(); }
+// One path-tracer symbol that pathtracer.o references but no path here calls (environment_light.cpp is not linked; the
+// scene pass below runs with envLight == NULL).  The OpenGL / ImGui entry points the scene sources' draw() and debugger
+// methods reference are stubbed by oracle/Makefile (ref_stubs.S, generated from the link's own list of undefined symbols).
 namespace SceneObjects {
-bool BVHAccel::intersect(const Ray&, Intersection*, BVHNode*) const { std::abort(); }
 Vector3D EnvironmentLight::sample_dir(const Ray&) const { std::abort(); }
 }  // namespace SceneObjects
 }  // namespace CGL
@@ -318,6 +322,82 @@ double ref_time_trace_grid(int N, float theta, int ncol, int pairset, int nthrea
   *checksum = s;
   *rays = (double)jobs.size() * N * N;
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+
+// PathTracer::est_radiance_global_illumination (pathtracer.cpp:279-302: zero_bounce_radiance :213-218 + one_bounce_radiance
+// :220-231 = estimate_direct_lighting_importance :136-211) over the reference's own BVHAccel (scene/bvh.cpp:54-222),
+// Triangle (scene/triangle.cpp:9-113), Sphere (scene/sphere.cpp:11-108), DiffuseBSDF / EmissionBSDF (pathtracer/bsdf.cpp),
+// DirectionalLight / PointLight (scene/light.cpp), for the camera rays Camera::generate_ray (camera.cpp:278-305) makes
+// through the pixel CENTRES (raytrace_pixel :819-899 jitters them with the global RNG; its composite is covered
+// elsewhere).  The scene comes in as plain arrays (the COLLADA loader is out of scope):
+//   tri_pos / tri_nrm [nt][3][3], tri_mat [nt]; sph [ns][4] = centre, radius, sph_mat [ns];
+//   mats [nm][6] = reflectance rgb, emission rgb (any emission > 0: EmissionBSDF, else DiffuseBSDF);
+//   lights [nl][7] = kind (0 directional: vec = direction the light travels; 1 point: vec = position), radiance rgb, vec xyz;
+//   cam [16] = pos xyz, c2w rows, hFov, vFov (degrees), nClip, fClip.     out [H][W][3]
+int ref_scene_radiance(const double* tri_pos, const double* tri_nrm, const int* tri_mat, int nt, const double* sph, const int* sph_mat, int ns,
+                       const double* mats, int nm, const double* lights, int nl, const double* cam, int W, int H, double* out) {
+  Quiet q;
+  using namespace CGL::SceneObjects;
+  std::vector<BSDF*> bsdfs;
+  for (int m = 0; m < nm; m++) {
+    const double* a = mats + 6 * m;
+    if (a[3] > 0 || a[4] > 0 || a[5] > 0) bsdfs.push_back(new EmissionBSDF(Vector3D(a[3], a[4], a[5])));
+    else bsdfs.push_back(new DiffuseBSDF(Vector3D(a[0], a[1], a[2])));
+  }
+  // one Mesh per material: built from an empty HalfedgeMesh, then pointed at our vertex arrays (positions / normals are
+  // public members, scene/object.h); Triangle's constructor copies what it needs (scene/triangle.cpp:9-22)
+  std::vector<Vector3D> P((size_t)3 * nt), N((size_t)3 * nt);
+  for (int v = 0; v < 3 * nt; v++) {
+    P[v] = Vector3D(tri_pos[3 * v], tri_pos[3 * v + 1], tri_pos[3 * v + 2]);
+    N[v] = Vector3D(tri_nrm[3 * v], tri_nrm[3 * v + 1], tri_nrm[3 * v + 2]);
+  }
+  std::vector<Mesh*> meshes;
+  HalfedgeMesh empty;
+  for (int m = 0; m < nm; m++) {
+    Mesh* mesh = new Mesh(empty, bsdfs[m]);
+    mesh->positions = P.data();
+    mesh->normals = N.data();
+    meshes.push_back(mesh);
+  }
+  std::vector<Primitive*> prims;
+  for (int t = 0; t < nt; t++) prims.push_back(new Triangle(meshes[tri_mat[t]], 3 * t, 3 * t + 1, 3 * t + 2));
+  std::vector<SphereObject*> sobj;
+  for (int k = 0; k < ns; k++) {
+    sobj.push_back(new SphereObject(Vector3D(sph[4 * k], sph[4 * k + 1], sph[4 * k + 2]), sph[4 * k + 3], bsdfs[sph_mat[k]]));
+    for (Primitive* p : sobj.back()->get_primitives()) prims.push_back(p);
+  }
+  BVHAccel bvh(prims, 4);
+  std::vector<SceneLight*> L;
+  for (int l = 0; l < nl; l++) {
+    const double* a = lights + 7 * l;
+    const Vector3D rad(a[1], a[2], a[3]), v(a[4], a[5], a[6]);
+    if (a[0] == 0) L.push_back(new DirectionalLight(rad, Vector3D(), v));
+    else L.push_back(new PointLight(rad, v));
+  }
+  Scene scene(std::vector<SceneObject*>(), L);
+  Camera camera;
+  camera.pos = Vector3D(cam[0], cam[1], cam[2]);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) camera.c2w(r, c) = cam[3 + 3 * r + c];
+  camera.hFov = cam[12]; camera.vFov = cam[13]; camera.nClip = cam[14]; camera.fClip = cam[15];
+  PathTracer pt;
+  pt.bvh = &bvh;
+  pt.scene = &scene;
+  pt.camera = &camera;
+  pt.envLight = NULL;
+  pt.direct_hemisphere_sample = false;
+  pt.ns_area_light = 1;
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      Ray r = camera.generate_ray((x + 0.5) / (double)W, (y + 0.5) / (double)H);
+      r.depth = 1;
+      const Vector3D rad = pt.est_radiance_global_illumination(r);
+      double* o = out + 3 * ((size_t)x + (size_t)y * W);
+      o[0] = rad.x; o[1] = rad.y; o[2] = rad.z;
+    }
+  pt.bvh = NULL; pt.scene = NULL; pt.camera = NULL;
+  return 0;
 }
 
 }  // extern "C"

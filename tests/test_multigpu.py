@@ -54,7 +54,7 @@ def test_single_process_multi_gpu_api(apertures):
                         first = False
                         want = ref.render_ghosts(lights, p)
                         assert np.array_equal(buf.array, want), (n, prec, len(lights))
-                        assert tiles >= 0 and (tiles > 0) == bool(lights)
+                        assert tiles >= 0 and (tiles > 0 or not lights)  # an empty frame still re-zeroes the previous frame's tiles
                 st = m.stats()
                 assert st["n_devices"] == n and st["call_ms"] > 0
                 mine = np.full((H, W, 3), -1.0)  # pageable: full-frame fallback

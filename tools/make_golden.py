@@ -128,6 +128,15 @@ def main():
     sb["apertures"] = np.array([c[1] for c in cfgs])
     sb["far_origin"] = np.array([60.0, -45.0])
     np.savez_compressed(os.path.join(OUT, "starburst.npz"), **sb)
+    # the path-traced scene pass: PathTracer::est_radiance_global_illumination of the compiled reference (its own BVHAccel,
+    # Triangle, Sphere, BSDFs and lights) on the scenes of tests/scene_fixtures.py, through the pixel centres
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_scene_pass
+    sc = {}
+    for name, scene, cam, W, H in test_scene_pass.cases():
+        sc[name] = ref.scene_radiance(scene, cam, W, H)
+        print("scene", name, sc[name].shape, "lit", float((sc[name].sum(axis=2) > 0).mean()), "max", float(sc[name].max()))
+    np.savez_compressed(os.path.join(OUT, "scene.npz"), **sc)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
