@@ -314,28 +314,45 @@ def parity_block(eng, lens, tex, light, params):
 # our arm
 # ------------------------------------------------------------------------------------------------
 class SparsePipeline:
-    """N = 1: R rotating (accumulators, output frame, tile state) sets on ONE stream: trace (clear_first = 0: the tile-sparse
-    finalize leaves the accumulators clear) -> lfb_finalize_tiles_device.  The engine's own second stream runs the forward
-    sweeps of frame k+1 under the ghost kernel of frame k."""
+    """N = 1: R rotating (accumulators, output frame, tile state) sets on TWO streams:
+        stream A (engine)                       trace frame k into accum[k % R] (clear_first = 0: the finalize left it clear)
+        stream B (finalize engine, high prio)   lfb_finalize_tiles_device of frame k -> out[k % R]
+    so the tile kernel of frame k runs under the trace of frame k+1 (which also has the engine's own third stream running its
+    forward sweeps).  Stage B of frame k waits for stage A of frame k; stage A of frame k + R waits for stage B of frame k."""
 
-    def __init__(self, eng, params, dev, n_buffers, torch, capi):
-        self.eng, self.params, self.capi = eng, params, capi
+    def __init__(self, eng, fin, params, dev, n_buffers, torch, capi):
+        self.eng, self.fin, self.params, self.capi, self.torch = eng, fin, params, capi, torch
         W, H = params.width, params.height
         acc_words = (capi.lib().lfb_accum_bytes(W, H) + 7) // 8
         st_words = (capi.lib().lfb_tile_state_bytes(W, H) + 3) // 4
         self.accums = [torch.zeros((acc_words,), dtype=torch.int64, device=dev) for _ in range(n_buffers)]
         self.outs = [torch.zeros((H, W, 3), dtype=torch.float32, device=dev) for _ in range(n_buffers)]
         self.states = [torch.zeros((st_words,), dtype=torch.int32, device=dev) for _ in range(n_buffers)]
+        self.A = torch.cuda.ExternalStream(eng.stream, device=dev)
+        self.B = torch.cuda.ExternalStream(fin.stream, device=dev)
+        self.traced = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.finalized = [torch.cuda.Event() for _ in range(n_buffers)]
+        self.fin_valid = [False] * n_buffers
         self.k = 0
+        torch.cuda.synchronize(dev)
 
     def frame(self, lights):
         b = self.k % len(self.accums)
         self.k += 1
+        if self.fin_valid[b]:
+            self.A.wait_event(self.finalized[b])  # the buffer's previous frame has been converted (and the buffer left clear)
         self.eng.render_ghosts_device(lights, self.params, self.accums[b].data_ptr(), clear_first=False)
+        self.traced[b].record(self.A)
+        self.B.wait_event(self.traced[b])
         out = self.outs[b]
-        self.eng.finalize_tiles_device(self.accums[b].data_ptr(), self.params, out.data_ptr(), out.stride(1) * out.element_size(), self.capi.F32x3,
+        self.fin.finalize_tiles_device(self.accums[b].data_ptr(), self.params, out.data_ptr(), out.stride(1) * out.element_size(), self.capi.F32x3,
                                        self.states[b].data_ptr())
+        self.finalized[b].record(self.B)
+        self.fin_valid[b] = True
         return b
+
+    def finish(self):
+        self.A.wait_stream(self.B)  # the timing events are recorded on A
 
 
 def run_ours(args):
@@ -374,10 +391,9 @@ def run_ours(args):
     rays_frame, inter_frame, jobs_frame = capi.count_work(lens, params, n_lights)
     assert inter_frame == nominal_interactions(n_lights), "bench.py's nominal count disagrees with lfb_count_work"
     N_BUF = 3  # rotating accumulator / output / state sets
-    fin = capi.Engine(local, stream_priority=1) if world > 1 else None  # N > 1: the reduce runs on a second, high-priority stream
-    if fin is not None:
-        fin.set_lens(lens)
-        fin.set_aperture(tex)
+    fin = capi.Engine(local, stream_priority=1)  # the tile finalize / reduce runs on a second, high-priority stream
+    fin.set_lens(lens)
+    fin.set_aperture(tex)
     A = torch.cuda.ExternalStream(eng.stream, device=dev)
 
     def barrier():
@@ -388,14 +404,14 @@ def run_ours(args):
     def build_pipeline(p):
         """-> (frames(n), finish(), result(b))"""
         if world == 1:
-            sp = SparsePipeline(eng, p, dev, N_BUF, torch, capi)
+            sp = SparsePipeline(eng, fin, p, dev, N_BUF, torch, capi)
 
             def frames(n, lights=lights_a):
                 b = 0
                 for _ in range(n):
                     b = sp.frame(lights)
                 return b
-            return frames, (lambda: None), (lambda b: sp.outs[b]), sp
+            return frames, sp.finish, (lambda b: sp.outs[b]), sp
         if args.reduce == "sparse":
             ps = sharding.PeerSparse(eng, p, rank, world, dev, dist.group.WORLD, n_buffers=N_BUF, finalize_engine=fin)
 
@@ -429,7 +445,7 @@ def run_ours(args):
             return b
         return frames, pf.finish, pf.result, pf
 
-    def timed_brackets(frames, finish, n_brackets):
+    def timed_brackets(frames, finish, n_brackets, K=K, lights=None):
         """n_brackets x (EXACTLY K frames between a barrier + synchronize on both sides); per bracket the device time of the
         engine stream's events, max over ranks.  -> (list of ms per bracket, host enqueue ms per frame)"""
         out, enq = [], []
@@ -439,7 +455,10 @@ def run_ours(args):
             ev_stream = A if world == 1 else torch.cuda.current_stream(dev)  # N = 1: everything runs on the engine's stream
             e0.record(ev_stream)
             th0 = time.perf_counter()
-            frames(K)
+            if lights is None:
+                frames(K)
+            else:
+                frames(K, lights)
             finish()  # N > 1: makes torch's current stream wait for the pipeline's streams
             enq.append((time.perf_counter() - th0) * 1e3 / K)
             e1.record(ev_stream)
@@ -458,11 +477,11 @@ def run_ours(args):
     finish()
     barrier()
     # kernels of ours per frame, counted on one frame
-    l0 = eng.stats()["kernel_launches"] + (fin.stats()["kernel_launches"] if fin else 0)
+    l0 = eng.stats()["kernel_launches"] + (fin.stats()["kernel_launches"])
     frames(1)
     finish()
     barrier()
-    launches_per_frame = eng.stats()["kernel_launches"] + (fin.stats()["kernel_launches"] if fin else 0) - l0
+    launches_per_frame = eng.stats()["kernel_launches"] + (fin.stats()["kernel_launches"]) - l0
     with clocks:
         brackets_ms, host_enqueue_ms = timed_brackets(frames, finish, N_BRACKETS)
     dev_ms = statistics.median(brackets_ms)
@@ -564,6 +583,9 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 e2e_brackets.append((time.perf_counter() - t0) * 1e3)
         e2e_ms = statistics.median(e2e_brackets) / K
+        e2e_dev = eng.stats()  # device-side split of the last call: trace kernels | whole call (trace + tile kernel's writes into host memory)
+        e2e_extra["e2e_device_split_ms"] = {"trace_kernels": e2e_dev["last_trace_ms"], "whole_call_on_device": e2e_dev["last_frame_ms"],
+                                            "note": "the rest of e2e.ms_per_step is the 1 MB aperture upload + its synchronize, launch latency and the ctypes calls"}
         tiles = statistics.median(tiles_seen[-K:])
         d2h = int(tiles) * 256 * 24 + 4
         # the frame that landed in host memory is the frame (checked once, outside the timed region)
@@ -651,6 +673,44 @@ def run_ours(args):
         if rank == 0:
             shm.unlink()
     e2e_value = inter_frame / (e2e_ms * 1e-3)
+
+    # ---- BASELINE configs 3 and 4: ONE frame, strong-scaled over the N ranks through the same pipeline (device time, max over
+    # ranks; the reduced frame checked against the unsharded one on rank 0) -- north_star's "near-linear scaling on the
+    # spectral / many-light configs" as numbers the driver's 1/2/4/8-GPU runs carry
+    other_configs = None
+    if not args.no_configs and (world == 1 or args.reduce == "sparse"):
+        other_configs = {}
+        lattice = [(0.1 + 0.8 * a / 7, 0.1 + 0.8 * b / 7) for b in range(8) for a in range(8)]
+        try:
+            del pipe
+        except NameError:
+            pass
+        for cname, n_lam, grid_c, Wc, Hc, suns, ppu in (("cfg3", 32, 512, 1920, 1080, [(0.45, 0.55)], 0.0), ("cfg4", 3, 1024, 3840, 2160, lattice, 0.8)):
+            lens_c = capi.builtin_lens(n_lam, COATING_NM)
+            eng.set_lens(lens_c)
+            pc = capi.make_params(capi.MODE_EXACT_GRID, Wc, Hc, grid_n=grid_c, pair_set=capi.PAIRS_ALL, include_direct=1, px_per_unit=ppu)
+            lights_c = [make_sun(x, y) for x, y in suns]
+            _, inter_c, jobs_c = capi.count_work(lens_c, pc, len(lights_c))
+            frames_c, finish_c, result_c, pipe_c = build_pipeline(pc)
+            frames_c(2, lights_c)
+            finish_c()
+            barrier()
+            tb, _ = timed_brackets(frames_c, finish_c, 3, K=1, lights=lights_c)
+            b = frames_c(1, lights_c)
+            finish_c()
+            barrier()
+            same = None
+            if rank == 0:
+                whole = torch.from_numpy(eng.render_ghosts(lights_c, pc, elem=capi.F32x3)).to(dev)
+                same = bool(torch.equal(result_c(b), whole))
+                del whole
+            other_configs[cname] = {"ms_per_frame": statistics.median(tb), "interactions_per_s": inter_c / (statistics.median(tb) * 1e-3),
+                                    "interactions_per_frame": inter_c, "jobs": jobs_c, "lights": len(lights_c), "wavelengths": n_lam, "grid": grid_c,
+                                    "sensor": [Wc, Hc], "equals_single_gpu_frame": same, "scaling": "strong: ONE frame over %d GPU(s)" % world}
+            del pipe_c, frames_c, finish_c, result_c
+            torch.cuda.empty_cache()
+            barrier()
+        eng.set_lens(lens)
 
     # ---- N > 1: the single-process form (lfb_create_multi: one host thread drives all GPUs), rank 0 alone ----------------------
     single_process = None
@@ -769,6 +829,7 @@ def run_ours(args):
             "strict": strict,
             "parity": parity,
             "single_process": single_process,
+            "other_configs": other_configs,
             "starburst": starburst,
             "e2e_rgba8": e2e_rgba8,
             "gpu_launches": int(launches_per_frame * K),
@@ -782,8 +843,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline_block(port_seconds, inter_frame)
         print(json.dumps(line))
     pinned_tex.free()
-    if fin is not None:
-        fin.close()
+    fin.close()
     eng.close()
     if world > 1:
         dist.barrier(group=cpu_group)
@@ -803,6 +863,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and oracle-parity legs")
     ap.add_argument("--no-strict", action="store_true", help="skip the LFB_STRICT leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 3 / config 4 single-frame legs")
     ap.add_argument("--reduce", default="sparse", choices=["sparse", "nccl", "peer", "multicast"],
                     help="N > 1: tile-sparse reduce + finalize over NVLink peer memory (default), or round 1's dense paths: one NCCL int64 "
                          "reduce of the whole frame / the dense fused kernel over peer memory / the same through NVSwitch multicast")

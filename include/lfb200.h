@@ -174,7 +174,8 @@ typedef struct lfb_options {
   int32_t kernel_select;      /* EXACT_GRID throughput kernels: 0 = by frame size (one job per ghost pair for small frames,
                                  ghost families from 16 384 family CTAs up), 1 = always per pair, 2 = always families */
   int32_t family_split;       /* > 0: at most this many forks per family job */
-  int32_t ctas_per_sm;        /* register-allocation target of the ghost / family kernels: 0 = default, 1 = the alternative build */
+  int32_t ctas_per_sm;        /* build variant of the ghost / family kernels: 0 = default, 1 = the alternative register-allocation
+                                 target, 2 = per-pair kernel without program staging (no CTA barrier; an experiment) */
   int32_t prefix_overlap;     /* forward sweeps of frame k+1 overlap the ghost kernel of frame k: 0 = on, -1 = off */
   int32_t starburst_lattice;  /* starburst on the aperture's periodic lattice: 0 = when the frame is larger than the period, -1 = never */
   int32_t starburst_cache;    /* keep the lattice spectrum |F| between frames (it depends on the mask alone): 0 = on, -1 = off */

@@ -241,9 +241,14 @@ struct lfb_engine {
 
 namespace {
 
-// The lens tables live in __constant__ memory, one copy per device: the engine that last
-// uploaded them owns them, others re-upload before launching.
+// The parity kernels (PARAXIAL_GRID, the FP64 oracle-order EXACT_GRID, REF_QUADS) read the lens from __constant__ memory,
+// one copy per device shared by every engine on it: the engine that last uploaded owns it, others re-upload before launching.
+// Engines run on their own streams, so an upload must not overtake another engine's kernels that still read the previous
+// lens: every launch of a constant-reading kernel records g_const_used[device] on its stream (note_const_use), and an upload
+// by a non-owner first makes its stream wait for that event.  (The EXACT_GRID throughput kernels do not use the constants.)
 const lfb_engine* g_const_owner[64] = {nullptr};
+cudaEvent_t g_const_used[64] = {nullptr};
+bool g_const_used_valid[64] = {false};
 std::mutex g_const_mutex;  // engines are single-threaded, but two engines of one device may live on two threads
 
 int bind(lfb_engine* e) {
@@ -254,12 +259,23 @@ int bind(lfb_engine* e) {
 
 int upload_constants(lfb_engine* e) {
   std::lock_guard<std::mutex> lock(g_const_mutex);
-  if (e->device < 64 && g_const_owner[e->device] == e) return LFB_OK;
+  if (e->device >= 64) return fail(LFB_ERR_INVALID, "device index >= 64");
+  if (g_const_owner[e->device] == e) return LFB_OK;
+  if (g_const_used_valid[e->device]) CU(cudaStreamWaitEvent(e->stream, g_const_used[e->device], 0));
   CU(upload_lens_f32(e->dev_lens, e->stream));
   CU(upload_lens_f64(e->dev_lens, e->stream));
   CU(upload_lens_ref(e->dev_lens, e->stream));
-  if (e->device < 64) g_const_owner[e->device] = e;
+  g_const_owner[e->device] = e;
   e->upload_pending = true;
+  return LFB_OK;
+}
+
+// call after enqueuing kernels that read the __constant__ lens
+int note_const_use(lfb_engine* e) {
+  std::lock_guard<std::mutex> lock(g_const_mutex);
+  if (!g_const_used[e->device]) CU(cudaEventCreateWithFlags(&g_const_used[e->device], cudaEventDisableTiming));
+  CU(cudaEventRecord(g_const_used[e->device], e->stream));
+  g_const_used_valid[e->device] = true;
   return LFB_OK;
 }
 
@@ -681,6 +697,8 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
     if (P.mode == LFB_MODE_PARAXIAL_GRID) {
       CU(launch_paraxial_setup(e->d_jobs, n, P.physical_backward, e->stream));
       e->launches++;
+      const int rcu = note_const_use(e);
+      if (rcu) return rcu;
     }
   }
   e->job_key.swap(key);
@@ -765,6 +783,8 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
     if (P.precision == LFB_FP64) CU(launch_trace_splat_f64(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
     else CU(launch_trace_splat_f32(e->d_jobs, e->n_jobs, g, P.mode, e->d_tex, accum, e->stream));
     e->launches++;
+    rc = note_const_use(e);
+    if (rc) return rc;
   }
   if (!capturing) {
     CU(cudaEventRecord(e->ev_trace1, e->stream));
@@ -803,11 +823,13 @@ int render_ref_device(lfb_engine* e, const lfb_light* lights, int n_lights, cons
     CU(cudaMemcpyAsync(e->h_bbox + 4, e->d_bbox, 4 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     memcpy(rect, e->h_bbox + 4, sizeof(rect));
-    if (rect[2] < rect[0] || rect[3] < rect[1]) { CU(cudaEventRecord(e->ev_trace1, e->stream)); e->timed = true; return LFB_OK; }
+    if (rect[2] < rect[0] || rect[3] < rect[1]) { CU(cudaEventRecord(e->ev_trace1, e->stream)); e->timed = true; return note_const_use(e); }
   }
   CU(launch_ref_raster(f, e->d_tris, f.has_sun ? 2 * n_ghosts : 0, e->d_tex, out_dev, stride, elem, additive,
                        e->track_bbox ? rect : nullptr, e->stream));
   e->launches++;
+  rc = note_const_use(e);
+  if (rc) return rc;
   CU(cudaEventRecord(e->ev_trace1, e->stream));
   e->timed = true;
   return LFB_OK;
@@ -1498,6 +1520,7 @@ extern "C" int lfb_dump_rays(lfb_engine* e, const lfb_light* light, const lfb_pa
   else if (fast) CU(launch_exact_dump<float>(e->d_dump_job, (const StepF*)e->d_dump_prog, g, e->d_tex, e->d_hits, e->stream));
   else if (P->precision == LFB_FP64) CU(launch_trace_dump_f64(e->d_dump_job, g, P->mode, e->d_tex, e->d_hits, e->stream));
   else CU(launch_trace_dump_f32(e->d_dump_job, g, P->mode, e->d_tex, e->d_hits, e->stream));
+  if (!fast && (rc = note_const_use(e))) return rc;
   e->launches++;
   CU(cudaMemcpyAsync(out, e->d_hits, sizeof(lfb_ray_hit) * n, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));

@@ -391,7 +391,16 @@ __device__ __forceinline__ unsigned long long lds_u64(unsigned addr) {
   asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void reds_add_u64(unsigned addr, unsigned long long v) { asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(addr), "l"(v)); }
+// 64-bit add into the tile with NATIVE 32-bit shared atomics (a 64-bit shared-memory add compiles to a compare-and-swap spin
+// loop, ATOMS.CAST.SPIN): add the low word, carry into the high word.  The carries commute with everything else, so the
+// pair holds the exact sum mod 2^64 in any order; deposits are < 2^32 almost always, so this is one atomic.
+__device__ __forceinline__ void tile_add_u64(unsigned addr, unsigned long long v) {
+  const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+  unsigned old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(lo));
+  const unsigned up = hi + ((old + lo) < old ? 1u : 0u);
+  if (up) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr + 4u), "r"(up));
+}
 __device__ __forceinline__ void redg_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v)); }
 // Pull the cache line with a job's float constants (pixel mapping, channel weights: lfb_internal.h Job::f_*) into L1 at kernel
 // start: they are first needed when a ray lands, and must not cost an L2 round trip there.
@@ -409,6 +418,19 @@ __device__ __forceinline__ void splat_tap(const WarpSplat& S, unsigned tile, int
   } else {
     wt[0] = w; wt[1] = wt[2] = wt[3] = 0.f;
   }
+  unsigned char* mark[4];
+  unsigned seen[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {  // global path: LOOK at the four pixels' tile bytes first, so that the looks overlap
+    mark[q] = nullptr; seen[q] = 1;
+    if (!TILE && S.tile_bits) {
+      const int jx = t.ix + (q & 1), jy = t.iy + (q >> 1);
+      if (!(wt[q] == 0.f || jx < 0 || jx >= S.W || jy < 0 || jy >= S.H)) {
+        mark[q] = tile_byte(S.tile_bits, S.tiles_w, jx >> kTilePxLog2, jy >> kTilePxLog2);
+        seen[q] = tile_peek(mark[q]);
+      }
+    }
+  }
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     const int jx = t.ix + (q & 1), jy = t.iy + (q >> 1);
@@ -419,50 +441,32 @@ __device__ __forceinline__ void splat_tap(const WarpSplat& S, unsigned tile, int
     const long long v2 = S.ch2 != 0.f ? __float2ll_rn(__fmul_rn(wt[q], S.ch2)) : 0ll;
     if (TILE) {
       const unsigned dst = tile + 24u * (unsigned)((jy - ty0) * tw + (jx - tx0));
-      if (v0) reds_add_u64(dst, (unsigned long long)v0);
-      if (v1) reds_add_u64(dst + 8, (unsigned long long)v1);
-      if (v2) reds_add_u64(dst + 16, (unsigned long long)v2);
+      if (v0) tile_add_u64(dst, (unsigned long long)v0);
+      if (v1) tile_add_u64(dst + 8, (unsigned long long)v1);
+      if (v2) tile_add_u64(dst + 16, (unsigned long long)v2);
     } else {
       unsigned long long* dst = S.accum + 3 * ((size_t)jx + (size_t)jy * S.W);
-      if (S.tile_bits) mark_tile(S.tile_bits, S.tiles_w, jx >> kTilePxLog2, jy >> kTilePxLog2);
       if (v0) redg_add_u64(dst, (unsigned long long)v0);
       if (v1) redg_add_u64(dst + 1, (unsigned long long)v1);
       if (v2) redg_add_u64(dst + 2, (unsigned long long)v2);
     }
   }
+  if (!TILE) {
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (!seen[q]) *mark[q] = 1;
+  }
 }
 
-// Deposit one (ray, mirror image) result per lane; warp-collective (all 32 lanes call it).  Only lanes whose ray (or its
-// mirror image) lands carry taps, weights and a footprint: nothing reads them on the other lanes.  Returns whether this
-// lane landed (statistics).
-template <typename T>
-__device__ __forceinline__ bool warp_land(const WarpSplat& S, const JobC<T>& J, bool alive, T xs, T ys, float wa, float wb, bool has_mirror,
-                                          int lane) {
-  int bx0, by0, bx1, by1;
-  Tap ta, tb;
-  float w0 = 0.f, w1 = 0.f;
-  bool lands = false;
-  if (alive) {
-    int x0, y0, x1, y1;
-    bx0 = by0 = 0x7fffffff; bx1 = by1 = -0x7fffffff;
-    ta.ix = ta.iy = tb.ix = tb.iy = 0; ta.fx = ta.fy = tb.fx = tb.fy = 0.f;
-    if (wa > 0.f) {
-      ta = to_tap<T>(J, S.bilinear, xs, ys);
-      if (footprint(S.bilinear, ta, S.W, S.H, x0, y0, x1, y1)) {
-        w0 = wa; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
-      }
-    }
-    if (wb > 0.f && has_mirror) {
-      tb = to_tap<T>(J, S.bilinear, xs, -ys);
-      if (footprint(S.bilinear, tb, S.W, S.H, x0, y0, x1, y1)) {
-        w1 = wb; bx0 = min(bx0, x0); by0 = min(by0, y0); bx1 = max(bx1, x1); by1 = max(by1, y1);
-      }
-    }
-    lands = w0 > 0.f || w1 > 0.f;
-  }
+// Deposit one image per lane (`lands`: this lane has one, at tap t with weight w); warp-collective (all 32 lanes call it).
+// The footprint of the warp's landing lanes decides: <= 64 pixels -> the warp's shared-memory tile, flushed with one global
+// atomic per touched (pixel, channel); larger -> straight to the accumulators.
+__device__ __forceinline__ void land_image(const WarpSplat& S, bool lands, const Tap& t, float w, int lane) {
   const unsigned landing = __ballot_sync(0xffffffffu, lands);
-  if (!landing) return false;  // nothing to deposit: the warp is done
-  if (lands) {  // the footprint of the warp's landing rays, reduced among those lanes only
+  if (!landing) return;
+  int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
+  if (lands) {
+    footprint(S.bilinear, t, S.W, S.H, bx0, by0, bx1, by1);  // true: `lands` was decided by it
     bx0 = __reduce_min_sync(landing, bx0); by0 = __reduce_min_sync(landing, by0);
     bx1 = __reduce_max_sync(landing, bx1); by1 = __reduce_max_sync(landing, by1);
   }
@@ -473,15 +477,12 @@ __device__ __forceinline__ bool warp_land(const WarpSplat& S, const JobC<T>& J, 
   const int tw = bx1 - bx0 + 1;
   const int area = tw * (by1 - by0 + 1);
   if (area > kWarpTilePx) {  // (uniform) the footprint exceeds the tile: straight to the accumulators
-    if (lands) {
-      if (w0 > 0.f) splat_tap<false>(S, 0u, bx0, by0, tw, ta, w0);
-      if (w1 > 0.f) splat_tap<false>(S, 0u, bx0, by0, tw, tb, w1);
-    }
-    return lands;
+    if (lands) splat_tap<false>(S, 0u, bx0, by0, tw, t, w);
+    return;
   }
   const unsigned tile = (unsigned)__cvta_generic_to_shared(S.tile);
-  // the dirty-tile bytes under the warp's footprint (a box of <= 64 pixels spans at most 5 x 1 ... 2 x 2 ... 1 x 5 tiles: lanes
-  // 0 .. 29 take a 6 x 5 patch): LOOK now, store after the splat, so that nothing waits for the look
+  // the dirty-tile bytes under the footprint (a box of <= 64 pixels spans at most 5 x 1 ... 2 x 2 ... 1 x 5 tiles: lanes 0 .. 29 take
+  // a 6 x 5 patch): LOOK now, store after the splat, so that nothing waits for the look
   unsigned char* mark = nullptr;
   unsigned seen = 1;
   if (S.tile_bits) {
@@ -493,25 +494,44 @@ __device__ __forceinline__ bool warp_land(const WarpSplat& S, const JobC<T>& J, 
   }
   for (int q = lane; q < 3 * area; q += 32) sts_u64(tile + 8u * (unsigned)q, 0ull);
   __syncwarp();
-  if (lands) {
-    if (w0 > 0.f) splat_tap<true>(S, tile, bx0, by0, tw, ta, w0);
-    if (w1 > 0.f) splat_tap<true>(S, tile, bx0, by0, tw, tb, w1);
-  }
+  if (lands) splat_tap<true>(S, tile, bx0, by0, tw, t, w);
   __syncwarp();
   const float inv_tw = M<float>::rcp((float)tw);
-  for (int t = lane; t < area; t += 32) {
-    const int jy = (int)(((float)t + 0.5f) * inv_tw);  // t / tw, exact for these small integers
-    const int jx = t - jy * tw;
+  for (int q = lane; q < area; q += 32) {
+    const int jy = (int)(((float)q + 0.5f) * inv_tw);  // q / tw, exact for these small integers
+    const int jx = q - jy * tw;
     unsigned long long* dst = S.accum + 3 * ((size_t)(bx0 + jx) + (size_t)(by0 + jy) * S.W);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      const unsigned long long v = lds_u64(tile + 8u * (unsigned)(3 * t + c));
+      const unsigned long long v = lds_u64(tile + 8u * (unsigned)(3 * q + c));
       if (v) redg_add_u64(dst + c, v);
     }
   }
   if (!seen) *mark = 1;
   __syncwarp();  // the tile is reused by the warp's next landing
-  return lands;
+}
+
+// Deposit one (ray, mirror image) result per lane; warp-collective.  The two images land on opposite sides of the meridional
+// axis, far apart for most ghosts, so each gets its own footprint / tile pass (one box around both would exceed the tile and
+// send every tap to the accumulators one atomic at a time -- what round 1 did).  Returns whether this lane landed (statistics).
+template <typename T>
+__device__ __forceinline__ bool warp_land(const WarpSplat& S, const JobC<T>& J, bool alive, T xs, T ys, float wa, float wb, bool has_mirror,
+                                          int lane) {
+  Tap ta, tb;
+  ta.ix = ta.iy = tb.ix = tb.iy = 0; ta.fx = ta.fy = tb.fx = tb.fy = 0.f;
+  bool la = false, lb = false;
+  int x0, y0, x1, y1;
+  if (alive && wa > 0.f) {
+    ta = to_tap<T>(J, S.bilinear, xs, ys);
+    la = footprint(S.bilinear, ta, S.W, S.H, x0, y0, x1, y1);
+  }
+  if (alive && wb > 0.f && has_mirror) {
+    tb = to_tap<T>(J, S.bilinear, xs, -ys);
+    lb = footprint(S.bilinear, tb, S.W, S.H, x0, y0, x1, y1);
+  }
+  land_image(S, la, ta, wa, lane);
+  land_image(S, lb, tb, wb, lane);
+  return la || lb;
 }
 
 // statistics (STATS instantiations): executed surface steps / ray pairs started / ray pairs landed, one atomic each per warp
@@ -613,13 +633,34 @@ __global__ void __launch_bounds__(kPrefixThreads) prefix_kernel(const Job* __res
 // ---------------------------------------------------------------------------------------------------------------
 // GHOST KERNEL: one job per ghost pair (i, j).  BT threads = 16 x BT/16 ray pairs of the upper half grid.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int MINB, int BT, bool STATS>
+// STAGED = false (an experiment, lfb_options.ctas_per_sm = 2): the program is not staged in shared memory -- every warp reads
+// its steps straight from global memory (warp-uniform 16-byte loads, L1-resident: a program is ~1.5 KB and the CTAs of an SM
+// work on a handful of jobs), so the kernel has NO CTA barrier and no staging wait in its prologue.
+template <typename T, bool STAGED>
+struct StepFetch {
+  const StepT<T>* base;
+  __device__ __forceinline__ const StepT<T>& operator[](int s) const { return base[s]; }
+};
+template <typename T>
+struct StepFetch<T, false> {
+  const StepT<T>* base;
+  __device__ __forceinline__ StepT<T> operator[](int s) const {
+    StepT<T> S;
+    const float4* src = reinterpret_cast<const float4*>(base + s);
+    float4* dst = reinterpret_cast<float4*>(&S);
+#pragma unroll
+    for (int q = 0; q < (int)(sizeof(StepT<T>) / 16); q++) dst[q] = __ldg(src + q);
+    return S;
+  }
+};
+
+template <typename T, int MINB, int BT, bool STATS, bool STAGED = true>
 __global__ void __launch_bounds__(BT, MINB) ghost_kernel(const Job* __restrict__ jobs, const StepT<T>* __restrict__ progs,
                                                          const __grid_constant__ JobHeads heads, FrameGeom g, const float* __restrict__ tex,
                                                          unsigned long long* __restrict__ accum) {
   typedef PrefixIO<T> io;
   constexpr int PH = BT / 16;
-  __shared__ __align__(16) StepT<T> s_prog[LFB_MAX_STEPS];
+  __shared__ __align__(16) StepT<T> s_prog_mem[STAGED ? LFB_MAX_STEPS : 1];
   __shared__ unsigned long long s_tile[(BT / 32) * kWarpTilePx * 3];
   // 3-D grid (patch column, patch row, job): no integer divisions in the prologue every warp pays
   const Job& J = jobs[blockIdx.z];
@@ -634,15 +675,19 @@ __global__ void __launch_bounds__(BT, MINB) ghost_kernel(const Job* __restrict__
   const unsigned head = heads.h[blockIdx.z];
   const int slot = (int)(head & 0xffffu) - 1, j_first = (int)((head >> 16) & 31u), n_steps = (int)(head >> 21);
   prefetch_job_constants(J);
-  const Staged staged = stage_issue<T, BT>(progs + (size_t)blockIdx.z * LFB_MAX_STEPS, n_steps, tid);
+  Staged staged;
+  if (STAGED) staged = stage_issue<T, BT>(progs + (size_t)blockIdx.z * LFB_MAX_STEPS, n_steps, tid);
   typename io::Raw raw;
   const bool cached = slot >= 0 && in_grid;  // (slot: uniform per CTA) the state ON the first-reflection surface comes from the prefix cache
   if (cached) {
     const size_t hr = (size_t)g.half_rays;
     raw = io::issue(g.prefix + ((size_t)(slot * g.n_surf + j_first) * io::kParts) * hr + ((size_t)bp * g.N + a), hr);
   }
-  stage_commit<T, BT>(s_prog, staged, n_steps, tid);
-  __syncthreads();  // the only CTA-wide barrier; nothing above waits for the state loads
+  if (STAGED) {
+    stage_commit<T, BT>(s_prog_mem, staged, n_steps, tid);
+    __syncthreads();  // the only CTA-wide barrier; nothing above waits for the state loads
+  }
+  const StepFetch<T, STAGED> s_prog = {STAGED ? s_prog_mem : progs + (size_t)blockIdx.z * LFB_MAX_STEPS};
   const MaskGeom K(g, tex);
   const JobC<T> JC(J);
   RayState<T> r;
@@ -837,6 +882,7 @@ cudaError_t launch_ghosts_t(const Job* jobs, const StepT<T>* progs, const unsign
     const StepT<T>* P = progs + (size_t)z0 * LFB_MAX_STEPS;
     if (stats) ghost_kernel<T, Tune<T>::kGhostA, BT, true><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
     else if (ctas_per_sm == 1) ghost_kernel<T, Tune<T>::kGhostB, BT, false><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
+    else if (ctas_per_sm == 2) ghost_kernel<T, Tune<T>::kGhostA, BT, false, false><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
     else ghost_kernel<T, Tune<T>::kGhostA, BT, false><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
   }
   return cudaGetLastError();

@@ -46,12 +46,16 @@ __device__ __forceinline__ unsigned nonzero_bytes(unsigned m) { return __vcmpne4
 
 __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
   extern __shared__ unsigned s_pre[];  // [n_words + 1] exclusive prefix of the per-word tile counts
+  __shared__ __align__(16) char s_rows[kTilePx1 * kTilePx1 * 32];  // one tile's pixels as they go out, row by row (stride <= 32 B)
+  __shared__ ulonglong2 s_acc[kTilePx1 * kTilePx1 * 24 / 16];  // one tile's summed accumulators (6 KB)
   __shared__ unsigned s_warp[kThreads / 32];
   __shared__ unsigned s_total;
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   unsigned* prev = A.state + 4;
   const int n = A.acc.n;
+  const size_t row_bytes = (size_t)kTilePx1 * A.stride;  // a tile row in the output: 16 pixels, contiguous
+  const bool row_vec = A.stride <= 32 && ((size_t)A.out % 16) == 0 && (((size_t)A.W * A.stride) % 16) == 0;
 
   // ---- 1. how many tiles does each word of the tile map hold (current of any rank, or previous)?  owned words only ----
   const int per = (A.n_words + kThreads - 1) / kThreads;  // contiguous words per thread
@@ -112,23 +116,84 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
     for (int r = 0; r < n; r++) have |= (((bits_of(A, r)[w] >> (8 * byte)) & 0xffu) ? 1u : 0u) << r;
     const int t = w * 4 + byte;
     const int ty = t / A.tiles_w, tx = t - ty * A.tiles_w;
-    const int x = tx * kTilePx1 + (tid & (kTilePx1 - 1)), y = ty * kTilePx1 + (tid >> kTilePxLog2);
-    if (x >= A.W || y >= A.H) continue;
+    const int lx = tid & (kTilePx1 - 1), ly = tid >> kTilePxLog2;
+    const int x = tx * kTilePx1 + lx, y = ty * kTilePx1 + ly;
+    const bool inside = x < A.W && y < A.H;
     const size_t p = (size_t)x + (size_t)y * A.W;
     unsigned long long s0 = 0, s1 = 0, s2 = 0;
-    for (int r = 0; r < n; r++) {
-      if (!((have >> r) & 1u)) continue;
-      unsigned long long* a = const_cast<unsigned long long*>(A.acc.ptr[r]) + 3 * p;
-      s0 += a[0]; s1 += a[1]; s2 += a[2];
-      a[0] = 0ull; a[1] = 0ull; a[2] = 0ull;  // the next frame finds the accumulators clear
+    const bool whole = (tx + 1) * kTilePx1 <= A.W && (ty + 1) * kTilePx1 <= A.H;
+    if (whole && (A.W & 1) == 0) {
+      // a whole tile of an even-width frame: its 16 rows are 384 contiguous, 16-byte aligned bytes each in every rank's
+      // accumulators -> read (and zero) them as 16-byte chunks, 24 per row: full sectors over NVLink / out of L2.  Thread t
+      // owns chunks t and t + 256 for every rank, so the ranks' sums build up in registers.
+      constexpr int kChunks = kTilePx1 * (kTilePx1 * 24 / 16);  // 384
+      ulonglong2 c0 = make_ulonglong2(0ull, 0ull), c1 = c0;
+      const size_t row0 = 3 * ((size_t)tx * kTilePx1 + (size_t)ty * kTilePx1 * A.W);  // u64 index of the tile's first value
+      for (int r = 0; r < n; r++) {
+        if (!((have >> r) & 1u)) continue;
+        unsigned long long* base = const_cast<unsigned long long*>(A.acc.ptr[r]) + row0;
+        {
+          const int row = tid / 24, col = tid - row * 24;
+          ulonglong2* src = reinterpret_cast<ulonglong2*>(base + (size_t)row * 3 * A.W) + col;
+          const ulonglong2 v = *src;
+          *src = make_ulonglong2(0ull, 0ull);  // the next frame finds the accumulators clear
+          c0.x += v.x; c0.y += v.y;
+        }
+        if (tid + kThreads < kChunks) {
+          const int c = tid + kThreads, row = c / 24, col = c - row * 24;
+          ulonglong2* src = reinterpret_cast<ulonglong2*>(base + (size_t)row * 3 * A.W) + col;
+          const ulonglong2 v = *src;
+          *src = make_ulonglong2(0ull, 0ull);
+          c1.x += v.x; c1.y += v.y;
+        }
+      }
+      s_acc[tid] = c0;
+      if (tid + kThreads < kChunks) s_acc[tid + kThreads] = c1;
+      __syncthreads();
+      const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(s_acc) + (ly * kTilePx1 + lx) * 3;
+      s0 = mine[0]; s1 = mine[1]; s2 = mine[2];
+      __syncthreads();  // s_acc is reused by the CTA's next tile
+    } else if (inside) {
+      for (int r = 0; r < n; r++) {
+        if (!((have >> r) & 1u)) continue;
+        unsigned long long* a = const_cast<unsigned long long*>(A.acc.ptr[r]) + 3 * p;
+        s0 += a[0]; s1 += a[1]; s2 += a[2];
+        a[0] = 0ull; a[1] = 0ull; a[2] = 0ull;  // the next frame finds the accumulators clear
+      }
     }
     const double v0 = (double)(long long)s0 * A.inv_scale, v1 = (double)(long long)s1 * A.inv_scale, v2 = (double)(long long)s2 * A.inv_scale;
-    if (A.elem == LFB_F32x3) {
-      float* o = reinterpret_cast<float*>(A.out + p * A.stride);
-      o[0] = (float)v0; o[1] = (float)v1; o[2] = (float)v2;
-    } else {
-      double* o = reinterpret_cast<double*>(A.out + p * A.stride);
-      o[0] = v0; o[1] = v1; o[2] = v2;
+    // A full tile whose rows are 16-byte aligned in the output goes out as 16-byte chunks, row by row (16 pixels x stride bytes
+    // are contiguous): whole 128-byte lines per warp -- what a PCIe (zero-copy host frame) or NVLink (peer frame) write wants;
+    // 24-byte pixels stored 8 bytes per lane would go out as partial sectors (measured: 17 GB/s into host memory).
+    const bool full = whole && row_vec;
+    if (full) {
+      char* mine = s_rows + (size_t)ly * row_bytes + (size_t)lx * A.stride;
+      if (A.elem == LFB_F32x3) {
+        float* o = reinterpret_cast<float*>(mine);
+        o[0] = (float)v0; o[1] = (float)v1; o[2] = (float)v2;
+        for (size_t q = 3; q < A.stride / 4; q++) o[q] = 0.f;  // padding lanes read back as zero
+      } else {
+        double* o = reinterpret_cast<double*>(mine);
+        o[0] = v0; o[1] = v1; o[2] = v2;
+        for (size_t q = 3; q < A.stride / 8; q++) o[q] = 0.0;
+      }
+      __syncthreads();
+      const int chunks_per_row = (int)(row_bytes / 16);
+      char* base = A.out + ((size_t)tx * kTilePx1 + (size_t)ty * kTilePx1 * A.W) * A.stride;
+      for (int c = tid; c < kTilePx1 * chunks_per_row; c += kThreads) {
+        const int row = c / chunks_per_row, col = c - row * chunks_per_row;
+        *reinterpret_cast<uint4*>(base + (size_t)row * A.W * A.stride + (size_t)col * 16) =
+            *reinterpret_cast<const uint4*>(s_rows + (size_t)row * row_bytes + (size_t)col * 16);
+      }
+      __syncthreads();  // s_rows is reused by the CTA's next tile
+    } else if (inside) {
+      if (A.elem == LFB_F32x3) {
+        float* o = reinterpret_cast<float*>(A.out + p * A.stride);
+        o[0] = (float)v0; o[1] = (float)v1; o[2] = (float)v2;
+      } else {
+        double* o = reinterpret_cast<double*>(A.out + p * A.stride);
+        o[0] = v0; o[1] = v1; o[2] = v2;
+      }
     }
   }
 

@@ -47,5 +47,8 @@ def test_our_arm_contract():
     assert d["parity"]["e2e_frame_equals_full_frame_call"] is True
     assert d["e2e_full_frame"]["d2h_bytes_per_step"] == 1920 * 1080 * 24 and d["e2e_full_frame"]["value"] < e["value"]
     assert d["strict"]["ms_per_step"] < 5.0 and len(d["brackets_ms_per_step"]) == 7
+    oc = d["other_configs"]   # BASELINE configs 3 and 4, one frame each, checked against the unsharded frame
+    assert oc["cfg3"]["equals_single_gpu_frame"] is True and oc["cfg4"]["equals_single_gpu_frame"] is True
+    assert oc["cfg3"]["interactions_per_frame"] > 4e9 and oc["cfg4"]["interactions_per_frame"] > 9e10 and oc["cfg4"]["lights"] == 64
     assert d["gpu_launches"] == 3 * 5                             # prefix + ghost + tile-finalize kernels per frame
     assert d["clocks"]["sm_max_mhz"] and not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
