@@ -175,7 +175,8 @@ typedef struct lfb_options {
                                  ghost families from 16 384 family CTAs up), 1 = always per pair, 2 = always families */
   int32_t family_split;       /* > 0: at most this many forks per family job */
   int32_t ctas_per_sm;        /* build variant of the ghost / family kernels: 0 = default, 1 = the alternative register-allocation
-                                 target, 2 = per-pair kernel without program staging (no CTA barrier; an experiment) */
+                                 target, 2 = per-pair kernel without program staging (no CTA barrier; an experiment), 3 = per-pair kernel
+                                 with the landing code out of line (an experiment) */
   int32_t prefix_overlap;     /* forward sweeps of frame k+1 overlap the ghost kernel of frame k: 0 = on, -1 = off */
   int32_t starburst_lattice;  /* starburst on the aperture's periodic lattice: 0 = when the frame is larger than the period, -1 = never */
   int32_t starburst_cache;    /* keep the lattice spectrum |F| between frames (it depends on the mask alone): 0 = on, -1 = off */
@@ -184,7 +185,9 @@ typedef struct lfb_options {
   int64_t prefix_budget_bytes; /* device memory the cached forward sweeps may take: 0 = 40 GiB; < 0 = no cache */
   int32_t weights_table;      /* 1: Fresnel / coating weights from the 1024-interval tables for every ray (round 1's scheme,
                                  kept for A/B measurements) instead of the per-step polynomials */
-  int32_t reserved[7];
+  int32_t experiment;         /* bit mask of measurement switches that never change a frame's bits (tools/kernel_ab.py): 1 = look at the
+                                 dirty-tile bytes through L1 */
+  int32_t reserved[6];
 } lfb_options;
 
 /* ---- lifecycle -------------------------------------------------------- */

@@ -72,7 +72,7 @@ class Options(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("stream_priority", C.c_int32), ("kernel_select", C.c_int32), ("family_split", C.c_int32),
         ("ctas_per_sm", C.c_int32), ("prefix_overlap", C.c_int32), ("starburst_lattice", C.c_int32), ("starburst_cache", C.c_int32),
-        ("reduce_ctas", C.c_int32), ("collect_stats", C.c_int32), ("prefix_budget_bytes", C.c_int64), ("weights_table", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("reduce_ctas", C.c_int32), ("collect_stats", C.c_int32), ("prefix_budget_bytes", C.c_int64), ("weights_table", C.c_int32), ("experiment", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

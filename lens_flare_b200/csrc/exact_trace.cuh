@@ -375,9 +375,10 @@ struct WarpSplat {  // what a warp needs to deposit its lanes' results
   int W, H;
   float ch0, ch1, ch2;        // radiance * rgb_weight * ray area * 2^bits
   bool bilinear;
+  bool peek_l1;               // experiment: look at the tile bytes through L1
   __device__ __forceinline__ WarpSplat(const FrameGeom& g, const Job& J, unsigned long long* tile_, unsigned long long* accum_)
       : tile(tile_), accum(accum_), bbox(g.bbox), tile_bits(g.tile_bits), tiles_w(g.tiles_w), W(g.W), H(g.H), ch0(J.f_chan[0]),
-        ch1(J.f_chan[1]), ch2(J.f_chan[2]), bilinear(g.splat == LFB_SPLAT_BILINEAR) {}
+        ch1(J.f_chan[1]), ch2(J.f_chan[2]), bilinear(g.splat == LFB_SPLAT_BILINEAR), peek_l1((g.pad2 & 1) != 0) {}
 };
 
 // Shared-memory accesses of the per-warp tile by 32-bit shared address: the tile pointer travels through structs and
@@ -489,7 +490,7 @@ __device__ __forceinline__ void land_image(const WarpSplat& S, bool lands, const
     const int tx = (bx0 >> kTilePxLog2) + lane % 6, ty = (by0 >> kTilePxLog2) + lane / 6;
     if (tx <= (bx1 >> kTilePxLog2) && ty <= (by1 >> kTilePxLog2)) {
       mark = tile_byte(S.tile_bits, S.tiles_w, tx, ty);
-      seen = tile_peek(mark);
+      seen = S.peek_l1 ? (unsigned)__ldca(mark) : tile_peek(mark);
     }
   }
   for (int q = lane; q < 3 * area; q += 32) sts_u64(tile + 8u * (unsigned)q, 0ull);
@@ -511,10 +512,12 @@ __device__ __forceinline__ void land_image(const WarpSplat& S, bool lands, const
   __syncwarp();  // the tile is reused by the warp's next landing
 }
 
+static __device__ __noinline__ void land_image_call(const WarpSplat& S, bool lands, const Tap& t, float w, int lane) { land_image(S, lands, t, w, lane); }
+
 // Deposit one (ray, mirror image) result per lane; warp-collective.  The two images land on opposite sides of the meridional
 // axis, far apart for most ghosts, so each gets its own footprint / tile pass (one box around both would exceed the tile and
 // send every tap to the accumulators one atomic at a time -- what round 1 did).  Returns whether this lane landed (statistics).
-template <typename T>
+template <typename T, bool CALL = false>
 __device__ __forceinline__ bool warp_land(const WarpSplat& S, const JobC<T>& J, bool alive, T xs, T ys, float wa, float wb, bool has_mirror,
                                           int lane) {
   Tap ta, tb;
@@ -529,8 +532,13 @@ __device__ __forceinline__ bool warp_land(const WarpSplat& S, const JobC<T>& J, 
     tb = to_tap<T>(J, S.bilinear, xs, -ys);
     lb = footprint(S.bilinear, tb, S.W, S.H, x0, y0, x1, y1);
   }
-  land_image(S, la, ta, wa, lane);
-  land_image(S, lb, tb, wb, lane);
+  if (CALL) {  // experiment: one out-of-line copy of the landing code instead of two inlined ones
+    land_image_call(S, la, ta, wa, lane);
+    land_image_call(S, lb, tb, wb, lane);
+  } else {
+    land_image(S, la, ta, wa, lane);
+    land_image(S, lb, tb, wb, lane);
+  }
   return la || lb;
 }
 
@@ -654,7 +662,7 @@ struct StepFetch<T, false> {
   }
 };
 
-template <typename T, int MINB, int BT, bool STATS, bool STAGED = true>
+template <typename T, int MINB, int BT, bool STATS, bool STAGED = true, bool CALL = false>
 __global__ void __launch_bounds__(BT, MINB) ghost_kernel(const Job* __restrict__ jobs, const StepT<T>* __restrict__ progs,
                                                          const __grid_constant__ JobHeads heads, FrameGeom g, const float* __restrict__ tex,
                                                          unsigned long long* __restrict__ accum) {
@@ -722,7 +730,7 @@ __global__ void __launch_bounds__(BT, MINB) ghost_kernel(const Job* __restrict__
     if (alive) alive = interact<T, true, false>(S, K, g, r, o);
   }
   const WarpSplat WS(g, J, s_tile + (tid >> 5) * (kWarpTilePx * 3), accum);
-  const bool landed = warp_land<T>(WS, JC, alive, r.ox, r.oy, r.w * r.ma, r.w * r.mb, b != bp, lane);
+  const bool landed = warp_land<T, CALL>(WS, JC, alive, r.ox, r.oy, r.w * r.ma, r.w * r.mb, b != bp, lane);
   if (STATS) flush_stats(g.stats, n_exec, in_grid ? 1u : 0u, landed ? 1u : 0u);
 }
 
@@ -883,6 +891,7 @@ cudaError_t launch_ghosts_t(const Job* jobs, const StepT<T>* progs, const unsign
     if (stats) ghost_kernel<T, Tune<T>::kGhostA, BT, true><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
     else if (ctas_per_sm == 1) ghost_kernel<T, Tune<T>::kGhostB, BT, false><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
     else if (ctas_per_sm == 2) ghost_kernel<T, Tune<T>::kGhostA, BT, false, false><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
+    else if (ctas_per_sm == 3) ghost_kernel<T, Tune<T>::kGhostA, BT, false, true, true><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
     else ghost_kernel<T, Tune<T>::kGhostA, BT, false><<<nb, BT, 0, s>>>(J, P, H, g, tex, accum);
   }
   return cudaGetLastError();

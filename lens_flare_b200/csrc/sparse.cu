@@ -41,6 +41,19 @@ __device__ __forceinline__ unsigned* bits_of(const TileArgs& A, int r) {
   return reinterpret_cast<unsigned*>(reinterpret_cast<char*>(const_cast<unsigned long long*>(A.acc.ptr[r])) + A.bits_off);
 }
 
+// Word w of every rank's tile map, loaded with all (peer) loads in flight at once; ranks >= n read as 0.
+__device__ __forceinline__ void load_ranks(const TileArgs& A, int w, unsigned* words) {
+#pragma unroll
+  for (int r = 0; r < LFB_MAX_PEERS; r++) words[r] = r < A.acc.n ? bits_of(A, r)[w] : 0u;
+}
+__device__ __forceinline__ unsigned or_of_ranks(const TileArgs& A, int w) {
+  unsigned words[LFB_MAX_PEERS], m = 0;
+  load_ranks(A, w, words);
+#pragma unroll
+  for (int r = 0; r < LFB_MAX_PEERS; r++) m |= words[r];
+  return m;
+}
+
 // one bit (0, 8, 16, 24) per non-zero byte of a tile-map word
 __device__ __forceinline__ unsigned nonzero_bytes(unsigned m) { return __vcmpne4(m, 0u) & 0x01010101u; }
 
@@ -63,10 +76,7 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
   unsigned mine = 0;
   for (int w = w0; w < w1; w++) {
     unsigned m = 0;
-    if (w % n == A.rank) {
-      m = prev[w];
-      for (int r = 0; r < n; r++) m |= bits_of(A, r)[w];
-    }
+    if (w % n == A.rank) m = prev[w] | or_of_ranks(A, w);
     const unsigned c = __popc(nonzero_bytes(m));
     s_pre[w] = c;
     mine += c;
@@ -109,11 +119,15 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
       if (s_pre[mid] <= q) lo = mid; else hi = mid;
     }
     const int w = lo;
+    unsigned words[LFB_MAX_PEERS];  // every rank's map word, all loads in flight at once (peer loads: ~2 us each over NVLink)
+    load_ranks(A, w, words);
     unsigned have = 0;  // bit r set = rank r's tile is dirty
     unsigned m = prev[w];
-    for (int r = 0; r < n; r++) m |= bits_of(A, r)[w];
+#pragma unroll
+    for (int r = 0; r < LFB_MAX_PEERS; r++) m |= words[r];
     const int byte = __fns(nonzero_bytes(m), 0, (int)(q - s_pre[w]) + 1) >> 3;  // the (q - s_pre[w])-th marked tile of the word
-    for (int r = 0; r < n; r++) have |= (((bits_of(A, r)[w] >> (8 * byte)) & 0xffu) ? 1u : 0u) << r;
+#pragma unroll
+    for (int r = 0; r < LFB_MAX_PEERS; r++) have |= (((words[r] >> (8 * byte)) & 0xffu) ? 1u : 0u) << r;
     const int t = w * 4 + byte;
     const int ty = t / A.tiles_w, tx = t - ty * A.tiles_w;
     const int lx = tid & (kTilePx1 - 1), ly = tid >> kTilePxLog2;
@@ -206,12 +220,8 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
   __threadfence();
   for (int w = tid; w < A.n_words; w += kThreads) {
     if (w % n != A.rank) continue;
-    unsigned m = 0;
-    for (int r = 0; r < n; r++) {
-      unsigned* b = bits_of(A, r) + w;
-      m |= *b;
-      *b = 0u;
-    }
+    const unsigned m = or_of_ranks(A, w);
+    for (int r = 0; r < n; r++) bits_of(A, r)[w] = 0u;
     prev[w] = m;
   }
   if (tid == 0) {

@@ -443,7 +443,8 @@ def test_exact_kernel_variants_agree(engine, port, apertures):
     variants = (("families", dict(kernel_select=2)), ("pairs", dict(kernel_select=1)), ("nocache", dict(kernel_select=1, prefix_budget_bytes=-1)),
                 ("split2", dict(kernel_select=2, family_split=2)), ("alt_build", dict(kernel_select=1, ctas_per_sm=1)),
                 ("alt_build_fam", dict(kernel_select=2, ctas_per_sm=1)), ("no_overlap", dict(kernel_select=1, prefix_overlap=-1)),
-                ("unstaged", dict(kernel_select=1, ctas_per_sm=2)))
+                ("unstaged", dict(kernel_select=1, ctas_per_sm=2)), ("landing_out_of_line", dict(kernel_select=1, ctas_per_sm=3)),
+                ("peek_l1", dict(kernel_select=1, experiment=1)))
     frames = {}
     for name, opts in variants:
         e = capi.Engine(0, **opts)
