@@ -180,14 +180,18 @@ typedef struct lfb_options {
   int32_t prefix_overlap;     /* forward sweeps of frame k+1 overlap the ghost kernel of frame k: 0 = on, -1 = off */
   int32_t starburst_lattice;  /* starburst on the aperture's periodic lattice: 0 = when the frame is larger than the period, -1 = never */
   int32_t starburst_cache;    /* keep the lattice spectrum |F| between frames (it depends on the mask alone): 0 = on, -1 = off */
-  int32_t reduce_ctas;        /* CTAs of the cross-GPU reduce kernels: 0 = one per SM */
+  int32_t reduce_ctas;        /* CTAs of the cross-GPU reduce kernels (0 = one per SM) and of lfb_render_ghosts_sparse_begin's
+                                 host-drain kernel (0 = 16) */
   int32_t collect_stats;      /* 1: run the counting instantiation of the EXACT_GRID kernels (lfb_exec_stats); slower */
   int64_t prefix_budget_bytes; /* device memory the cached forward sweeps may take: 0 = 40 GiB; < 0 = no cache */
   int32_t weights_table;      /* 1: Fresnel / coating weights from the 1024-interval tables for every ray (round 1's scheme,
                                  kept for A/B measurements) instead of the per-step polynomials */
   int32_t experiment;         /* bit mask of measurement switches that never change a frame's bits (tools/kernel_ab.py): 1 = look at the
-                                 dirty-tile bytes through L1 */
-  int32_t reserved[6];
+                                 dirty-tile bytes in L2 (ld.global.cg) instead of through L1 (the default: 13 % faster at cfg2) */
+  int32_t host_write_mbps;    /* lfb_render_ghosts_sparse_begin: the pace, in MB/s, at which a frame's tiles are stored into host memory
+                                 while other frames are in flight: 0 = 85 % of what unpaced stores reach on this link (measured once,
+                                 at the first call); < 0 = unpaced (the next frame's kernels then wait for the stores: see sparse.cu) */
+  int32_t reserved[5];
 } lfb_options;
 
 /* ---- lifecycle -------------------------------------------------------- */
@@ -255,6 +259,26 @@ int lfb_render_ghosts_rect(lfb_engine* e, const lfb_light* lights, int n_lights,
  * anyone else since (else LFB_ERR_STATE).  n_lights = 0 just re-zeroes what the previous frame wrote. */
 int lfb_render_ghosts_sparse(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* params,
                              void* out, size_t out_stride_bytes, int out_elem, int out_is_clear, int* tiles_written);
+
+/* lfb_render_ghosts_sparse with SEVERAL FRAMES IN FLIGHT (no reference counterpart: the reference renders and shows one frame
+ * at a time, raytraced_renderer.cpp:303-311; this is for a host that keeps two or three ghost_buffers in rotation).  The tile
+ * kernel's stores into host memory are PCIe-bound (~0.11 ms for cfg2's 5.4 MB) and the trace is SM-bound (~0.09 ms): in flight
+ * together they cost the longer of the two, not the sum.  _begin(slot) enqueues the frame -- trace on the engine stream into the
+ * slot's own accumulator, tile kernel on a second, highest-priority stream -- and returns; _end(slot) blocks until that frame's
+ * pixels are in `out` and reports the tiles written.  slot is in [0, LFB_SPARSE_SLOTS); each slot remembers ITS `out` buffer
+ * (same contract as above: out_is_clear = 1 the first time, then the same buffer, untouched by others); a slot must be
+ * collected by _end before its next _begin (LFB_ERR_STATE).  Three slots keep the device busy while the host prepares the
+ * next frame (cfg2 with the sun moving every frame, 0.31 ms per blocking call, ~0.16 ms per frame in flight).  `out` must be page-locked and mapped
+ * (LFB_ERR_INVALID otherwise: there is no staged fallback here).  The frames are bit for bit those of lfb_render_ghosts. */
+#define LFB_SPARSE_SLOTS 4
+int lfb_render_ghosts_sparse_begin(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* params,
+                                   void* out, size_t out_stride_bytes, int out_elem, int out_is_clear, int slot);
+int lfb_render_ghosts_sparse_end(lfb_engine* e, int slot, int* tiles_written);
+/* Device timeline of the slot's last collected frame, in ms since the engine was created (CUDA events; no reference
+ * counterpart): ms[0] the engine stream reached the frame, ms[1] its trace kernels were done, ms[2] the tile kernel's stream
+ * reached it, ms[3] its tiles were staged (pixels, in device memory), ms[4] they were in `out`.  For benches and
+ * tools/e2e_probe.py. */
+int lfb_sparse_slot_times(lfb_engine* e, int slot, float ms[5]);
 
 /* Parity instrument (no reference counterpart; PARAXIAL_GRID records are what trace_ray_auto_before / _after,
  * pathtracer.cpp:588-689, return per axis): trace the N x N grid of one ghost (i, j, lambda) of one light

@@ -30,7 +30,7 @@ RAY_MISSED, RAY_VIGNETTED, RAY_TIR, RAY_STOPPED, RAY_OFF_SENSOR = 1, 2, 4, 8, 16
 
 # every symbol include/lfb200.h declares (tests check the library exports each one)
 SYMBOLS = (
-    "lfb_abi_version", "lfb_create", "lfb_create_ex", "lfb_exec_stats", "lfb_set_scene", "lfb_render_scene", "lfb_render_composite_rgba8", "lfb_create_multi", "lfb_destroy_multi", "lfb_multi_set_lens", "lfb_multi_set_aperture", "lfb_render_ghosts_multi", "lfb_multi_stats", "lfb_render_ghosts_sparse", "lfb_tile_state_bytes", "lfb_finalize_tiles_device", "lfb_reduce_tiles_peers", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
+    "lfb_abi_version", "lfb_create", "lfb_create_ex", "lfb_exec_stats", "lfb_set_scene", "lfb_render_scene", "lfb_render_composite_rgba8", "lfb_create_multi", "lfb_destroy_multi", "lfb_multi_set_lens", "lfb_multi_set_aperture", "lfb_render_ghosts_multi", "lfb_multi_stats", "lfb_render_ghosts_sparse", "lfb_render_ghosts_sparse_begin", "lfb_render_ghosts_sparse_end", "lfb_sparse_slot_times", "lfb_tile_state_bytes", "lfb_finalize_tiles_device", "lfb_reduce_tiles_peers", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
     "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_render_ghosts_async", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
     "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_reduce_finalize_peers", "lfb_peer_barrier", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
     "lfb_host_alloc", "lfb_host_free", "lfb_host_register", "lfb_host_unregister", "lfb_host_device_pointer", "lfb_finalize_clear_device", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
@@ -72,7 +72,7 @@ class Options(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("stream_priority", C.c_int32), ("kernel_select", C.c_int32), ("family_split", C.c_int32),
         ("ctas_per_sm", C.c_int32), ("prefix_overlap", C.c_int32), ("starburst_lattice", C.c_int32), ("starburst_cache", C.c_int32),
-        ("reduce_ctas", C.c_int32), ("collect_stats", C.c_int32), ("prefix_budget_bytes", C.c_int64), ("weights_table", C.c_int32), ("experiment", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("reduce_ctas", C.c_int32), ("collect_stats", C.c_int32), ("prefix_budget_bytes", C.c_int64), ("weights_table", C.c_int32), ("experiment", C.c_int32), ("host_write_mbps", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -204,6 +204,9 @@ def lib():
     L.lfb_render_ghosts_async.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int]
     L.lfb_render_ghosts_rect.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
     L.lfb_render_ghosts_sparse.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.lfb_render_ghosts_sparse_begin.argtypes = [vp, LiP, C.c_int, PP, vp, C.c_size_t, C.c_int, C.c_int, C.c_int]
+    L.lfb_render_ghosts_sparse_end.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+    L.lfb_sparse_slot_times.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.lfb_tile_state_bytes.argtypes = [C.c_int, C.c_int]
     L.lfb_tile_state_bytes.restype = C.c_size_t
     L.lfb_finalize_tiles_device.argtypes = [vp, vp, PP, vp, C.c_size_t, C.c_int, vp]
@@ -407,6 +410,25 @@ class Engine:
         check(lib().lfb_render_ghosts_sparse(self._h, lights_array(lights), len(lights), C.byref(params), out.ctypes.data, stride, elem,
                                              int(out_is_clear), C.byref(n)))
         return n.value
+
+    def render_ghosts_sparse_begin(self, lights, params, out, slot, elem=F64x3, stride=None, out_is_clear=False):
+        """Enqueue a tile-sparse frame into `out` (page-locked, the slot's own buffer) and return; collect it with
+        render_ghosts_sparse_end(slot).  Two slots: the tile writes of one frame overlap the trace of the next."""
+        if stride is None:
+            stride = out.strides[1]
+        check(lib().lfb_render_ghosts_sparse_begin(self._h, lights_array(lights), len(lights), C.byref(params), out.ctypes.data, stride, elem,
+                                                   int(out_is_clear), int(slot)))
+
+    def render_ghosts_sparse_end(self, slot):
+        n = C.c_int()
+        check(lib().lfb_render_ghosts_sparse_end(self._h, int(slot), C.byref(n)))
+        return n.value
+
+    def sparse_slot_times(self, slot):
+        """(reached, traced, tile kernel start, staged, done) of the slot's last collected frame, ms since the engine was created."""
+        ms = (C.c_float * 5)()
+        check(lib().lfb_sparse_slot_times(self._h, int(slot), ms))
+        return tuple(ms)
 
     def finalize_tiles_device(self, accum_ptr, params, out_ptr, stride, elem, state_ptr):
         check(lib().lfb_finalize_tiles_device(self._h, accum_ptr, C.byref(params), out_ptr, stride, elem, state_ptr))

@@ -146,23 +146,47 @@ struct lfb_engine {
   bool has_lens = false, has_tex = false, timed = false;
   lfb_lens lens;
   DevLens dev_lens;
-  float* d_tex = nullptr;
+  float* d_tex = nullptr;  // the aperture mask the next frame reads: d_tex_ab[tex_cur]
+  // lfb_set_aperture uploads into the OTHER of two textures on its own stream, so a host that changes the mask while earlier
+  // frames are still in flight waits for the 1 MB copy only, not for those frames (ev_tex_free[k]: the frames that read k are done)
+  float* d_tex_ab[2] = {nullptr, nullptr};
+  int tex_cur = 0;
+  cudaStream_t tex_stream = nullptr;
+  cudaEvent_t ev_tex_up = nullptr, ev_tex_free[2] = {nullptr, nullptr};
+  bool tex_free_valid[2] = {false, false};
   int tex_w = 0, tex_h = 0;
   // jobs of the current frame description (re-used while lights/params/lens do not change)
   Job* d_jobs = nullptr;
-  Job* h_jobs = nullptr;  // pinned staging
-  int jobs_cap = 0, n_jobs = 0;
-  std::vector<unsigned char> job_key;
+  Job* h_jobs = nullptr;  // pinned staging of the frame being built: alias of stage[stage_cur]
+  // Two sets of page-locked staging buffers, used in turn: a host that enqueues frames back to back (moving lights) builds
+  // frame k+1's tables while frame k's upload may still be queued behind frame k-1's kernels.  stage[b].ev = b's last upload done.
+  struct HostStage {
+    char* arena = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool valid = false;
+  } stage[2];
+  int stage_cur = 0;
+  char* d_arena = nullptr;  // all per-frame tables back to back (prepare_jobs): d_jobs, d_progs, d_slots, ... point into it
+  size_t rec_off[3] = {0, 0, 0}, rec_bytes = 0;  // jobs / slots / families inside a record region; its size
+  int rec_cur = 1;                                // the record region the current tables use
+  cudaEvent_t ev_rec_free[2] = {nullptr, nullptr};  // on `stream`: the frames that read region r are done
+  bool rec_free_valid[2] = {false, false};
+  bool sweeps_aside = false;  // this structure's frames run their forward sweeps on prefix_stream (launch_exact_frame)
+  size_t arena_cap = 0;
+  int n_jobs = 0;
+  std::vector<unsigned char> job_key;     // params + lights of the tables on the device
+  std::vector<unsigned char> struct_key;  // params + light COUNT: the part the job lists and step programs depend on
+  std::vector<char> job_tmpl;             // the job records of that structure (host copy)
   Job* d_dump_job = nullptr;
   // EXACT_GRID step programs, LFB_MAX_STEPS per job: StepF (LFB_FP32) or StepD (LFB_STRICT) records, buffers sized for StepD
   char* d_progs = nullptr;
-  char* h_progs = nullptr;   // pinned staging
+  char* h_progs = nullptr;   // alias of stage[stage_cur].progs
   char* d_dump_prog = nullptr;
   bool frame_strict = false;  // the current job table holds StepD programs
   // prefix cache: one slot per (light, lambda) of the frame
   Job* d_slots = nullptr;  Job* h_slots = nullptr;
   char* d_slot_progs = nullptr;  char* h_slot_progs = nullptr;
-  int slots_cap = 0, n_slots = 0;
+  int n_slots = 0;
   float4* d_prefix = nullptr;
   size_t prefix_cap = 0;
   // prefix overlap: the forward sweeps of frame k+1 run on their own (high-priority) stream into the other of two caches while
@@ -180,7 +204,7 @@ struct lfb_engine {
   // ghost families: one job per (light, lambda, first reflection j) of the frame
   Job* d_fams = nullptr;  Job* h_fams = nullptr;
   char* d_fam_progs = nullptr;  char* h_fam_progs = nullptr;
-  int fams_cap = 0, n_fams = 0;
+  int n_fams = 0;
   bool frame_has_family = false, last_families = false;
   std::vector<unsigned> job_heads, fam_heads;  // packed (slot, first reflection, program length) per ghost / family job
   float2* d_lut = nullptr;   // reflectance tables, kLutSize entries per (lambda, surface, direction)
@@ -234,7 +258,20 @@ struct lfb_engine {
   const void* sparse_out = nullptr;
   int sparse_w = 0, sparse_h = 0, sparse_elem = 0;
   size_t sparse_stride = 0;
-  unsigned* h_count = nullptr;  // page-locked, mapped: tiles written by the last sparse launch
+  unsigned* h_count = nullptr;  // page-locked, mapped: tiles written by the last sparse launch ([0]) / by slot s ([1 + s])
+  // lfb_render_ghosts_sparse_begin / _end: up to LFB_SPARSE_SLOTS frames in flight.  Each slot owns an accumulator and the tile state of ITS host
+  // frame; the tile kernel runs on fin_stream (highest priority), so its PCIe-bound stores overlap the next frame's trace.
+  struct SparseSlot {
+    unsigned long long* accum = nullptr; size_t accum_cap = 0; bool accum_clean = false; int accum_w = 0, accum_h = 0;
+    unsigned* state = nullptr; size_t state_cap = 0;
+    char* stage = nullptr; size_t stage_cap = 0;  // the frame's tiles on their way to host memory (sparse.cu: drain_kernel)
+    const void* out = nullptr; int w = 0, h = 0, elem = 0; size_t stride = 0;
+    cudaEvent_t ev_begin = nullptr, ev_traced = nullptr, ev_tile0 = nullptr, ev_staged = nullptr, ev_done = nullptr;  // timing events (lfb_sparse_slot_times)
+    bool pending = false, done_valid = false;
+  } slot[LFB_SPARSE_SLOTS];
+  cudaStream_t fin_stream = nullptr, drain_stream = nullptr;
+  float drain_gbps = -1.f;  // pace of the host-drain kernel; < 0: not decided yet (options.host_write_mbps)
+  cudaEvent_t ev_epoch = nullptr;  // recorded at creation: the zero of lfb_sparse_slot_times
   bool accum_clean = false;     // d_accum (sums and bitmap) is all zeros for a accum_clean_w x accum_clean_h frame
   int accum_clean_w = 0, accum_clean_h = 0;
   SceneStore* scene = nullptr;  // lfb_set_scene
@@ -506,72 +543,121 @@ int build_family_program(const lfb_engine* e, int lam, int j, unsigned mask, Ste
 
 // Frame constants of one job.  The libm calls (atan/cosf/sinf of frame constants,
 // pathtracer.cpp:414, and sin/cos of the light's angle) are made here once per job, not per ray.
-void fill_job(const lfb_engine* e, const lfb_params& P, const lfb_light& lt, const JobId& id, Job* J) {
-  memset(J, 0, sizeof(*J));
-  J->light = id.light; J->i = id.i; J->j = id.j; J->lambda = id.lambda;
-  J->theta = lt.theta;
+// The fields of a Job that depend on its LIGHT (and, through the colour weights, its wavelength): everything else is the
+// frame's structure (lens, pairs, grid, shard) and survives a change of the lights alone.
+struct LightFields {
+  float theta;
+  double cs, sn, sx, sy, ppu, sin_t, cos_t, inv_dist, area, scale;
+};
+LightFields light_fields(const lfb_engine* e, const lfb_params& P, const lfb_light& lt) {
+  LightFields F;
+  F.theta = lt.theta;
   const double dx = lt.ns_x - 0.5, dy = lt.ns_y - 0.5;
   if (P.physical_mapping) {
     // the flare axis runs from the image centre through the light: the rotation is the light's azimuth (atan2, not the
     // reference's atan, which folds left-of-centre suns onto the right) and the origin is the image centre, so that a ray
     // landing at local (xs, ys) is drawn at centre + ppu * R(phi) (xs, ys).  See lfb_params.physical_mapping.
     const double phi = (dx == 0 && dy == 0) ? 0.0 : atan2(dy * (double)P.height, dx * (double)P.width);
-    J->cs = -cos(phi); J->sn = -sin(phi);  // to_pixel maps X = -ppu xs: fold the sign into the rotation
-    J->sx = 0.5 * (double)P.width;
-    J->sy = 0.5 * (double)P.height;
+    F.cs = -cos(phi); F.sn = -sin(phi);  // to_pixel maps X = -ppu xs: fold the sign into the rotation
+    F.sx = 0.5 * (double)P.width;
+    F.sy = 0.5 * (double)P.height;
   } else {
     const float ang = (dx == 0 && dy == 0) ? 0.f : (float)atan(dy / dx);
-    J->cs = cosf(ang); J->sn = sinf(ang);
-    J->sx = ceil(lt.ns_x * (double)P.width);   // draw_ghost, pathtracer.cpp:462-463
-    J->sy = ceil(lt.ns_y * (double)P.height);
+    F.cs = cosf(ang); F.sn = sinf(ang);
+    F.sx = ceil(lt.ns_x * (double)P.width);   // draw_ghost, pathtracer.cpp:462-463
+    F.sy = ceil(lt.ns_y * (double)P.height);
   }
-  J->ppu = P.px_per_unit > 0 ? P.px_per_unit : 0.4f;
-  J->sin_t = sin((double)lt.theta); J->cos_t = cos((double)lt.theta);
-  J->inv_dist = (lt.distance > 0 && std::isfinite(lt.distance)) ? 1.0 / lt.distance : 0.0;  // 0: directional
+  F.ppu = P.px_per_unit > 0 ? P.px_per_unit : 0.4f;
+  F.sin_t = sin((double)lt.theta); F.cos_t = cos((double)lt.theta);
+  F.inv_dist = (lt.distance > 0 && std::isfinite(lt.distance)) ? 1.0 / lt.distance : 0.0;  // 0: directional
   const double cell = 2 * e->lens.entrance_half_height / P.grid_n;
-  const double area = cell * cell * J->ppu * J->ppu;
-  for (int c = 0; c < 3; c++) J->chan[c] = (double)lt.radiance[c] * (double)e->lens.rgb_weight[id.lambda][c] * area;
-  const double scale = ldexp(1.0, P.fixed_point_bits > 0 ? P.fixed_point_bits : 40);
+  F.area = cell * cell * F.ppu * F.ppu;
+  F.scale = ldexp(1.0, P.fixed_point_bits > 0 ? P.fixed_point_bits : 40);
+  return F;
+}
+void apply_light(const lfb_engine* e, const lfb_light& lt, const LightFields& F, Job* J) {
+  J->theta = F.theta;
+  J->cs = F.cs; J->sn = F.sn; J->sx = F.sx; J->sy = F.sy; J->ppu = F.ppu;
+  J->sin_t = F.sin_t; J->cos_t = F.cos_t; J->inv_dist = F.inv_dist;
+  for (int c = 0; c < 3; c++) J->chan[c] = (double)lt.radiance[c] * (double)e->lens.rgb_weight[J->lambda][c] * F.area;
   J->f_sin_t = (float)J->sin_t; J->f_cos_t = (float)J->cos_t; J->f_inv_dist = (float)J->inv_dist;
   J->f_sx = (float)J->sx; J->f_sy = (float)J->sy; J->f_cs = (float)J->cs; J->f_sn = (float)J->sn; J->f_ppu = (float)J->ppu;
-  for (int c = 0; c < 3; c++) J->f_chan[c] = (float)J->chan[c] * (float)scale;
+  for (int c = 0; c < 3; c++) J->f_chan[c] = (float)J->chan[c] * (float)F.scale;
+}
+void fill_job(const lfb_engine* e, const lfb_params& P, const lfb_light& lt, const JobId& id, Job* J) {
+  memset(J, 0, sizeof(*J));
+  J->light = id.light; J->i = id.i; J->j = id.j; J->lambda = id.lambda;
+  apply_light(e, lt, light_fields(e, P, lt), J);
 }
 
-template <typename T>
-int regrow_pair(T** dev, T** host, size_t bytes) {
-  if (*dev) CU(cudaFree(*dev));
-  if (*host) CU(cudaFreeHost(*host));
-  *dev = nullptr; *host = nullptr;
-  CU(cudaMalloc((void**)dev, bytes));
-  CU(cudaHostAlloc((void**)host, bytes, cudaHostAllocDefault));
-  return LFB_OK;
+// the job / slot / family records the next launches read: region r of the arena's two
+void set_record_region(lfb_engine* e, int r) {
+  char* base = e->d_arena + (size_t)r * e->rec_bytes;
+  e->d_jobs = (Job*)(base + e->rec_off[0]);
+  e->d_slots = (Job*)(base + e->rec_off[1]);
+  e->d_fams = (Job*)(base + e->rec_off[2]);
+  e->rec_cur = r;
 }
 
-// Build + upload this shard's jobs unless the frame description is unchanged.
-int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params& P) {
+// Build + upload this shard's tables unless the frame description is unchanged.  All tables of a frame -- ghost jobs and their
+// step programs, prefix slots and theirs, family jobs and theirs -- are laid out back to back in ONE arena and go up in ONE
+// copy: six separate small copies cost ~8 us of stream time each (measured: 0.05 ms of a 0.26 ms cfg2 frame with a moving sun).
+int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params& P, bool capturing) {
   std::vector<unsigned char> key(sizeof(lfb_params) + sizeof(lfb_light) * (size_t)n_lights);
   memcpy(key.data(), &P, sizeof(lfb_params));
   if (n_lights > 0) memcpy(key.data() + sizeof(lfb_params), lights, sizeof(lfb_light) * (size_t)n_lights);
   if (key == e->job_key) return LFB_OK;
+  // Only the lights moved (the usual frame-to-frame change): the structure -- job lists, step programs, kernel choice, arena
+  // layout -- stands, and so do the programs already on the device.  Refill the light-dependent fields of the job records
+  // from the saved templates and upload just those (cfg2: 27 KB instead of 300 KB, ~8 us of host time instead of ~50).
+  std::vector<unsigned char> skey(sizeof(lfb_params) + sizeof(int));
+  memcpy(skey.data(), &P, sizeof(lfb_params));
+  memcpy(skey.data() + sizeof(lfb_params), &n_lights, sizeof(int));
+  if (!e->job_key.empty() && skey == e->struct_key) {
+    e->stage_cur ^= 1;
+    lfb_engine::HostStage& st = e->stage[e->stage_cur];
+    if (st.valid) CU(cudaEventSynchronize(st.ev));
+    const size_t bytes = e->job_tmpl.size();
+    // With the forward sweeps on their own stream (launch_exact_frame), the records go up on THAT stream, into the record
+    // region the previous frame is not using: upload and sweeps of frame k+1 then run under the ghost kernel of frame k.
+    const bool aside = e->sweeps_aside && !capturing;
+    cudaStream_t up_stream = aside ? e->prefix_stream : e->stream;
+    if (bytes > 0) {
+      const int r = e->rec_cur ^ 1;
+      memcpy(st.arena, e->job_tmpl.data(), bytes);
+      std::vector<LightFields> LF((size_t)n_lights);
+      for (int l = 0; l < n_lights; l++) LF[l] = light_fields(e, P, lights[l]);
+      Job* const arrays[3] = {(Job*)(st.arena + e->rec_off[0]), (Job*)(st.arena + e->rec_off[1]), (Job*)(st.arena + e->rec_off[2])};
+      const int counts[3] = {e->n_jobs, e->n_slots, e->n_fams};
+      for (int a = 0; a < 3; a++)
+        for (int q = 0; q < counts[a]; q++) apply_light(e, lights[arrays[a][q].light], LF[arrays[a][q].light], &arrays[a][q]);
+      if (aside && e->rec_free_valid[r]) CU(cudaStreamWaitEvent(up_stream, e->ev_rec_free[r], 0));
+      CU(cudaMemcpyAsync(e->d_arena + (size_t)r * bytes, st.arena, bytes, cudaMemcpyHostToDevice, up_stream));
+      set_record_region(e, r);
+      if (e->n_jobs > 0 && P.mode == LFB_MODE_PARAXIAL_GRID) {
+        CU(launch_paraxial_setup(e->d_jobs, e->n_jobs, P.physical_backward, e->stream));
+        e->launches++;
+        const int rcu = note_const_use(e);
+        if (rcu) return rcu;
+      }
+    }
+    CU(cudaEventRecord(st.ev, up_stream));
+    st.valid = true;
+    e->job_key.swap(key);
+    if (!aside) e->upload_pending = true;
+    return LFB_OK;
+  }
   std::vector<JobId> ids;
   list_jobs(e->lens, P, n_lights, ids);
   // launch order = list order.  (Measured on cfg2: sorting the ghosts longest-first, or interleaving long and short
   // ones, is 20 % SLOWER than the reference order; the sensor sums are integers, so the order never changes the result.)
   const int n = (int)ids.size();
-  const size_t prog_bytes = sizeof(StepD) * LFB_MAX_STEPS;  // per job, sized for the larger record
   int rc;
-  if (n > e->jobs_cap) {
-    e->jobs_cap = 0;
-    if ((rc = regrow_pair(&e->d_jobs, &e->h_jobs, sizeof(Job) * (size_t)n))) return rc;
-    if ((rc = regrow_pair(&e->d_progs, &e->h_progs, prog_bytes * (size_t)n))) return rc;
-    e->jobs_cap = n;
-  }
-  // the previous frame's upload may still be reading the pinned staging buffers
-  CU(cudaStreamSynchronize(e->stream));
   const bool want_progs = is_exact_fast(P);
   const bool strict = P.precision == LFB_STRICT;
   e->frame_strict = strict;
   const size_t step_bytes = strict ? sizeof(StepD) : sizeof(StepF);
+  const size_t prog_bytes = step_bytes * LFB_MAX_STEPS;  // per job
   const int parts = strict ? exact_prefix_parts<double>() : exact_prefix_parts<float>();
   const bool want_family = e->opt.kernel_select != 1;
   StepD prog[LFB_MAX_STEPS];
@@ -581,7 +667,7 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
   e->frame_has_prefix = false;
   e->frame_has_prefix2 = false;
   e->frame_has_family = false;
-  e->n_fams = 0; e->n_slots = 0;
+  e->n_fams = 0; e->n_slots = 0; e->n_jobs = 0;
   e->job_heads.clear(); e->fam_heads.clear();
   if (want_progs && e->opt.prefix_budget_bytes >= 0) {
     slot_of.assign((size_t)std::max(n_lights, 1) * e->lens.n_lambda, -1);
@@ -608,80 +694,112 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
       }
     }
   }
-  if (e->frame_has_prefix) {
-    const int ns = (int)slot_ids.size();
-    if (ns > e->slots_cap) {
-      e->slots_cap = 0;
-      if ((rc = regrow_pair(&e->d_slots, &e->h_slots, sizeof(Job) * (size_t)ns))) return rc;
-      if ((rc = regrow_pair(&e->d_slot_progs, &e->h_slot_progs, prog_bytes * (size_t)ns))) return rc;
-      e->slots_cap = ns;
+  const int ns = e->frame_has_prefix ? (int)slot_ids.size() : 0;
+  // ghost families: the pairs (i, j) of a slot grouped by their first reflection j
+  struct Fam { int slot, j; unsigned mask; };
+  std::vector<Fam> fams;
+  std::vector<char> slot_direct((size_t)ns, 0);  // this shard owns the slot's direct path
+  bool use_fam = false;
+  if (e->frame_has_prefix && want_family) {
+    std::vector<int> fam_of((size_t)ns * LFB_MAX_SURFACES, -1);
+    for (int q = 0; q < n; q++) {
+      const int sl = slot_of[(size_t)ids[q].light * e->lens.n_lambda + ids[q].lambda];
+      if (ids[q].i < 0) { slot_direct[sl] = 1; continue; }
+      int& f = fam_of[(size_t)sl * LFB_MAX_SURFACES + ids[q].j];
+      if (f < 0) { f = (int)fams.size(); fams.push_back({sl, ids[q].j, 0u}); }
+      fams[f].mask |= 1u << ids[q].i;
     }
-    for (int sl = 0; sl < ns; sl++) {
-      fill_job(e, P, lights[slot_ids[sl].light], slot_ids[sl], &e->h_slots[sl]);
-      e->h_slots[sl].n_steps = build_program(e, slot_ids[sl].lambda, -1, -1, prog, false, true);
-      put_steps(strict, e->h_slot_progs, (size_t)sl * LFB_MAX_STEPS, prog, e->h_slots[sl].n_steps + 1);
-      e->h_slots[sl].i = 0;  // set to 1 below when this shard owns the slot's direct path
-    }
-    // ghost families: the pairs (i, j) of a slot grouped by their first reflection j
-    if (want_family) {
-      struct Fam { int slot, j; unsigned mask; };
-      std::vector<Fam> fams;
-      std::vector<int> fam_of((size_t)ns * LFB_MAX_SURFACES, -1);
-      for (int q = 0; q < n; q++) {
-        const int sl = slot_of[(size_t)ids[q].light * e->lens.n_lambda + ids[q].lambda];
-        if (ids[q].i < 0) { e->h_slots[sl].i = 1; continue; }
-        int& f = fam_of[(size_t)sl * LFB_MAX_SURFACES + ids[q].j];
-        if (f < 0) { f = (int)fams.size(); fams.push_back({sl, ids[q].j, 0u}); }
-        fams[f].mask |= 1u << ids[q].i;
-      }
-      // options.family_split = m: at most m forks per family job (more, shorter CTAs for small frames; the part of the
-      // backward sweep above a chunk's forks is then repeated per chunk)
-      if (e->opt.family_split > 0) {
-        const int m = e->opt.family_split;
-        std::vector<Fam> split;
-        for (const Fam& f : fams) {
-          unsigned cur = 0;
-          int cnt = 0;
-          for (int k = f.j - 1; k >= 0; k--) {
-            if (!((f.mask >> k) & 1u)) continue;
-            cur |= 1u << k;
-            if (++cnt == m) { split.push_back({f.slot, f.j, cur}); cur = 0; cnt = 0; }
-          }
-          if (cnt) split.push_back({f.slot, f.j, cur});
+    // options.family_split = m: at most m forks per family job (more, shorter CTAs for small frames; the part of the
+    // backward sweep above a chunk's forks is then repeated per chunk)
+    if (e->opt.family_split > 0) {
+      const int m = e->opt.family_split;
+      std::vector<Fam> split;
+      for (const Fam& f : fams) {
+        unsigned cur = 0;
+        int cnt = 0;
+        for (int k = f.j - 1; k >= 0; k--) {
+          if (!((f.mask >> k) & 1u)) continue;
+          cur |= 1u << k;
+          if (++cnt == m) { split.push_back({f.slot, f.j, cur}); cur = 0; cnt = 0; }
         }
-        fams.swap(split);
+        if (cnt) split.push_back({f.slot, f.j, cur});
       }
-      const int nf = (int)fams.size();
-      if (nf > e->fams_cap) {
-        e->fams_cap = 0;
-        if ((rc = regrow_pair(&e->d_fams, &e->h_fams, sizeof(Job) * (size_t)nf))) return rc;
-        if ((rc = regrow_pair(&e->d_fam_progs, &e->h_fam_progs, prog_bytes * (size_t)nf))) return rc;
-        e->fams_cap = nf;
-      }
-      for (int f = 0; f < nf; f++) {
-        const JobId& sid = slot_ids[fams[f].slot];
-        Job* FJ = &e->h_fams[f];
-        fill_job(e, P, lights[sid.light], sid, FJ);
-        FJ->slot = fams[f].slot;
-        FJ->j_first = fams[f].j;
-        FJ->i = (int)fams[f].mask;
-        FJ->j = fams[f].j;
-        FJ->n_steps = build_family_program(e, sid.lambda, fams[f].j, fams[f].mask, prog);
-        e->fam_heads.push_back(pack_head(FJ->slot, FJ->j_first, FJ->n_steps));
-        put_steps(strict, e->h_fam_progs, (size_t)f * LFB_MAX_STEPS, prog, FJ->n_steps);
-      }
-      e->n_fams = nf;
-      if (nf > 0) {
-        CU(cudaMemcpyAsync(e->d_fams, e->h_fams, sizeof(Job) * (size_t)nf, cudaMemcpyHostToDevice, e->stream));
-        CU(cudaMemcpyAsync(e->d_fam_progs, e->h_fam_progs, step_bytes * LFB_MAX_STEPS * (size_t)nf, cudaMemcpyHostToDevice, e->stream));
-      }
-      e->frame_has_family = true;
+      fams.swap(split);
     }
-    e->n_slots = ns;
-    CU(cudaMemcpyAsync(e->d_slots, e->h_slots, sizeof(Job) * (size_t)ns, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(e->d_slot_progs, e->h_slot_progs, step_bytes * LFB_MAX_STEPS * (size_t)ns, cudaMemcpyHostToDevice, e->stream));
+    // Families do ~25 % less work but in 4x fewer, longer-lived CTAs: they win once the grid is many waves deep (cfg3 / cfg4:
+    // x1.3), and lose ~8 % on a frame as small as cfg2 (5 376 CTAs = 3.6 waves), where the per-pair kernel keeps the SMs
+    // fuller.  Decided here so that only the tables of the kernel that will run are built and uploaded.
+    const long long fam_ctas = (long long)fams.size() * ((P.grid_n + 15) / 16) * (((P.grid_n + 1) / 2 + 7) / 8);
+    use_fam = e->opt.kernel_select == 2 || fam_ctas >= 16384;
   }
-  for (int q = 0; q < n; q++) {
+  const int nf = use_fam ? (int)fams.size() : 0;
+  const int n_build = use_fam ? 0 : n;  // a frame traced by families needs no per-pair jobs
+  // ---- the arena: [jobs | slots | families || programs | slot programs | family programs], each 256-byte aligned; the job
+  // records come first so that a change of the lights alone re-uploads only them ----
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  // (host staging: [records | programs]; device: [records 0 | records 1 | programs] -- two record regions, used in turn)
+  const size_t off_jobs = 0;
+  const size_t off_slots = up(off_jobs + sizeof(Job) * (size_t)n_build);
+  const size_t off_fams = up(off_slots + sizeof(Job) * (size_t)ns);
+  const size_t off_progs = up(off_fams + sizeof(Job) * (size_t)nf);  // = bytes of one record region
+  const size_t off_slot_progs = up(off_progs + (want_progs ? prog_bytes * (size_t)n_build : 0));
+  const size_t off_fam_progs = up(off_slot_progs + prog_bytes * (size_t)ns);
+  const size_t host_total = up(off_fam_progs + prog_bytes * (size_t)nf);
+  const size_t total = host_total + off_progs;
+  if (total > e->arena_cap) {
+    CU(cudaStreamSynchronize(e->stream));  // uploads out of the old staging buffers may still be queued, kernels may read the old tables
+    if (e->prefix_stream) CU(cudaStreamSynchronize(e->prefix_stream));
+    cudaFree(e->d_arena);
+    e->d_arena = nullptr; e->arena_cap = 0;
+    e->rec_free_valid[0] = e->rec_free_valid[1] = false;
+    for (int b = 0; b < 2; b++) {
+      if (e->stage[b].arena) cudaFreeHost(e->stage[b].arena);
+      e->stage[b].arena = nullptr;
+      e->stage[b].valid = false;
+    }
+    const size_t cap = total + total / 4;
+    cudaError_t err = cudaMalloc((void**)&e->d_arena, cap);
+    if (err == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(LFB_ERR_NOMEM, "cudaMalloc: out of device memory"); }
+    if (err != cudaSuccess) return fail_cuda(err, "cudaMalloc");
+    for (int b = 0; b < 2; b++) CU(cudaHostAlloc((void**)&e->stage[b].arena, cap, cudaHostAllocDefault));
+    e->arena_cap = cap;
+  }
+  // Two page-locked staging arenas, used in turn: a host that enqueues frames back to back (moving lights) builds frame k+1's
+  // tables while frame k's upload may still be queued behind frame k-1's kernels; the other arena's upload is two frames old.
+  e->stage_cur ^= 1;
+  lfb_engine::HostStage& st = e->stage[e->stage_cur];
+  if (st.valid) CU(cudaEventSynchronize(st.ev));
+  char* const h = st.arena;
+  e->rec_off[0] = off_jobs; e->rec_off[1] = off_slots; e->rec_off[2] = off_fams; e->rec_bytes = off_progs;
+  e->h_jobs = (Job*)(h + off_jobs); e->h_slots = (Job*)(h + off_slots); e->h_fams = (Job*)(h + off_fams);
+  e->h_progs = h + off_progs; e->h_slot_progs = h + off_slot_progs; e->h_fam_progs = h + off_fam_progs;
+  // a full build fills record region 1, so that [records | programs] of the staging arena go up as one contiguous copy
+  set_record_region(e, 1);
+  e->d_progs = e->d_arena + off_progs + off_progs;
+  e->d_slot_progs = e->d_arena + off_slot_progs + off_progs;
+  e->d_fam_progs = e->d_arena + off_fam_progs + off_progs;
+  for (int sl = 0; sl < ns; sl++) {
+    fill_job(e, P, lights[slot_ids[sl].light], slot_ids[sl], &e->h_slots[sl]);
+    e->h_slots[sl].n_steps = build_program(e, slot_ids[sl].lambda, -1, -1, prog, false, true);
+    put_steps(strict, e->h_slot_progs, (size_t)sl * LFB_MAX_STEPS, prog, e->h_slots[sl].n_steps + 1);
+    e->h_slots[sl].i = slot_direct[sl];  // 1: the prefix kernel of a family frame also splats the slot's direct path
+  }
+  for (int f = 0; f < nf; f++) {
+    const JobId& sid = slot_ids[fams[f].slot];
+    Job* FJ = &e->h_fams[f];
+    fill_job(e, P, lights[sid.light], sid, FJ);
+    FJ->slot = fams[f].slot;
+    FJ->j_first = fams[f].j;
+    FJ->i = (int)fams[f].mask;
+    FJ->j = fams[f].j;
+    FJ->n_steps = build_family_program(e, sid.lambda, fams[f].j, fams[f].mask, prog);
+    e->fam_heads.push_back(pack_head(FJ->slot, FJ->j_first, FJ->n_steps));
+    put_steps(strict, e->h_fam_progs, (size_t)f * LFB_MAX_STEPS, prog, FJ->n_steps);
+  }
+  e->n_fams = nf;
+  e->frame_has_family = use_fam;
+  e->n_slots = ns;
+  for (int q = 0; q < n_build; q++) {
     fill_job(e, P, lights[ids[q].light], ids[q], &e->h_jobs[q]);
     e->h_jobs[q].slot = -1;
     e->h_jobs[q].j_first = ids[q].j;  // jobs without a cached sweep re-trace it and canonicalise the state there
@@ -693,19 +811,20 @@ int prepare_jobs(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb
       put_steps(strict, e->h_progs, (size_t)q * LFB_MAX_STEPS, prog, e->h_jobs[q].n_steps);
     }
   }
-  e->n_jobs = n;
-  if (n > 0) {
-    CU(cudaMemcpyAsync(e->d_jobs, e->h_jobs, sizeof(Job) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
-    if (want_progs)
-      CU(cudaMemcpyAsync(e->d_progs, e->h_progs, step_bytes * LFB_MAX_STEPS * (size_t)n, cudaMemcpyHostToDevice, e->stream));
-    if (P.mode == LFB_MODE_PARAXIAL_GRID) {
-      CU(launch_paraxial_setup(e->d_jobs, n, P.physical_backward, e->stream));
-      e->launches++;
-      const int rcu = note_const_use(e);
-      if (rcu) return rcu;
-    }
+  e->n_jobs = n_build;
+  if (host_total > 0) CU(cudaMemcpyAsync(e->d_arena + off_progs, h, host_total, cudaMemcpyHostToDevice, e->stream));
+  if (n_build > 0 && P.mode == LFB_MODE_PARAXIAL_GRID) {
+    CU(launch_paraxial_setup(e->d_jobs, n_build, P.physical_backward, e->stream));
+    e->launches++;
+    const int rcu = note_const_use(e);
+    if (rcu) return rcu;
   }
+  CU(cudaEventRecord(st.ev, e->stream));
+  st.valid = true;
+  e->job_tmpl.assign(h, h + (host_total > 0 ? off_progs : 0));  // the job records, for the lights-only path above
+  e->sweeps_aside = e->n_slots > 0 && e->frame_has_prefix && e->frame_has_prefix2 && !e->frame_has_family && !e->opt.collect_stats;
   e->job_key.swap(key);
+  e->struct_key.swap(skey);
   e->upload_pending = true;
   return LFB_OK;
 }
@@ -715,10 +834,7 @@ template <typename T>
 int launch_exact_frame(lfb_engine* e, const lfb_params& P, FrameGeom& g, unsigned long long* accum, bool capturing) {
   typedef StepT<T> S;
   const bool stats = e->opt.collect_stats != 0;
-  // Families do ~25 % less work but in 4x fewer, longer-lived CTAs: they win once the grid is many waves deep (cfg3 / cfg4:
-  // x1.3), and lose ~8 % on a frame as small as cfg2 (5 376 CTAs = 3.6 waves), where the per-pair kernel keeps the SMs fuller.
-  const long long fam_ctas = (long long)e->n_fams * ((P.grid_n + 15) / 16) * (((P.grid_n + 1) / 2 + 7) / 8);
-  const bool families = e->frame_has_prefix && e->frame_has_family && (e->opt.kernel_select == 2 || fam_ctas >= 16384);
+  const bool families = e->frame_has_prefix && e->frame_has_family;  // decided by prepare_jobs
   e->last_families = families;
   int overlap_buf = -1;
   if (e->n_slots > 0 && e->frame_has_prefix) {
@@ -768,15 +884,15 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
                        unsigned long long* accum, int clear_first) {
   int rc = upload_constants(e);
   if (rc) return rc;
-  rc = prepare_jobs(e, lights, n_lights, P);
-  if (rc) return rc;
-  const AccumLayout lay = accum_layout(P.width, P.height);
-  FrameGeom g = make_geom(e, P, (unsigned*)((char*)accum + lay.bits_off));
   // inside a CUDA-graph capture (a host may capture whole frames and replay them) the timing events are not recorded:
   // they could not be read back anyway
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   CU(cudaStreamIsCapturing(e->stream, &cap));
   const bool capturing = cap != cudaStreamCaptureStatusNone;
+  rc = prepare_jobs(e, lights, n_lights, P, capturing);
+  if (rc) return rc;
+  const AccumLayout lay = accum_layout(P.width, P.height);
+  FrameGeom g = make_geom(e, P, (unsigned*)((char*)accum + lay.bits_off));
   if (clear_first) CU(cudaMemsetAsync(accum, 0, lay.total, e->stream));
   if (g.stats) CU(cudaMemsetAsync(e->d_stats, 0, 4 * sizeof(unsigned long long), e->stream));
   if (!capturing) CU(cudaEventRecord(e->ev_trace0, e->stream));
@@ -793,6 +909,8 @@ int render_grid_device(lfb_engine* e, const lfb_light* lights, int n_lights, con
   if (!capturing) {
     CU(cudaEventRecord(e->ev_trace1, e->stream));
     e->timed = true;
+    CU(cudaEventRecord(e->ev_rec_free[e->rec_cur], e->stream));  // (a lights-only upload into this region waits for it)
+    e->rec_free_valid[e->rec_cur] = true;
   }
   return LFB_OK;
 }
@@ -890,6 +1008,22 @@ extern "C" int lfb_create_ex(lfb_engine** out, int device_id, const lfb_options*
     if (rc == cudaSuccess) rc = cudaEventCreateWithFlags(&e->ev_prefix_free[k], cudaEventDisableTiming);
   }
   if (rc == cudaSuccess) rc = cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming);
+  for (int k = 0; k < 2 && rc == cudaSuccess; k++) rc = cudaEventCreateWithFlags(&e->stage[k].ev, cudaEventDisableTiming);
+  for (int k = 0; k < 2 && rc == cudaSuccess; k++) rc = cudaEventCreateWithFlags(&e->ev_rec_free[k], cudaEventDisableTiming);
+  if (rc == cudaSuccess) rc = cudaStreamCreateWithFlags(&e->tex_stream, cudaStreamNonBlocking);
+  if (rc == cudaSuccess) rc = cudaStreamCreateWithPriority(&e->fin_stream, cudaStreamNonBlocking, prio_hi);
+  if (rc == cudaSuccess) rc = cudaStreamCreateWithPriority(&e->drain_stream, cudaStreamNonBlocking, prio_hi);
+  for (int k = 0; k < LFB_SPARSE_SLOTS && rc == cudaSuccess; k++) {
+    rc = cudaEventCreate(&e->slot[k].ev_traced);
+    if (rc == cudaSuccess) rc = cudaEventCreate(&e->slot[k].ev_done);
+    if (rc == cudaSuccess) rc = cudaEventCreate(&e->slot[k].ev_begin);
+    if (rc == cudaSuccess) rc = cudaEventCreate(&e->slot[k].ev_tile0);
+    if (rc == cudaSuccess) rc = cudaEventCreate(&e->slot[k].ev_staged);
+  }
+  if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_epoch);
+  if (rc == cudaSuccess) rc = cudaEventRecord(e->ev_epoch, e->stream);
+  if (rc == cudaSuccess) rc = cudaEventCreateWithFlags(&e->ev_tex_up, cudaEventDisableTiming);
+  for (int k = 0; k < 2 && rc == cudaSuccess; k++) rc = cudaEventCreateWithFlags(&e->ev_tex_free[k], cudaEventDisableTiming);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_frame0);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_trace0);
   if (rc == cudaSuccess) rc = cudaEventCreate(&e->ev_trace1);
@@ -900,7 +1034,7 @@ extern "C" int lfb_create_ex(lfb_engine** out, int device_id, const lfb_options*
   if (rc == cudaSuccess) rc = cudaMalloc((void**)&e->d_stats, 4 * sizeof(unsigned long long));
   if (rc == cudaSuccess) rc = cudaMemset(e->d_stats, 0, 4 * sizeof(unsigned long long));
   if (rc == cudaSuccess) rc = cudaHostAlloc((void**)&e->h_bbox, 8 * sizeof(int), cudaHostAllocDefault);
-  if (rc == cudaSuccess) rc = cudaHostAlloc((void**)&e->h_count, 4 * sizeof(unsigned), cudaHostAllocMapped);
+  if (rc == cudaSuccess) rc = cudaHostAlloc((void**)&e->h_count, (1 + LFB_SPARSE_SLOTS) * sizeof(unsigned), cudaHostAllocMapped);
   if (rc == cudaSuccess) e->h_count[0] = 0;
   if (rc == cudaSuccess) { e->h_bbox[0] = e->h_bbox[1] = 0x7fffffff; e->h_bbox[2] = e->h_bbox[3] = -0x7fffffff; }
   if (rc != cudaSuccess) { lfb_destroy(e); return fail_cuda(rc, "lfb_create"); }
@@ -916,19 +1050,35 @@ extern "C" void lfb_destroy(lfb_engine* e) {
     std::lock_guard<std::mutex> lock(g_const_mutex);
     if (e->device < 64 && g_const_owner[e->device] == e) g_const_owner[e->device] = nullptr;
   }
-  cudaFree(e->d_progs); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox); cudaFree(e->d_lut); cudaFree(e->d_stats);
-  cudaFree(e->d_slots); cudaFree(e->d_slot_progs); cudaFree(e->d_prefix); cudaFree(e->d_prefix2);
+  cudaFree(e->d_arena); cudaFree(e->d_dump_prog); cudaFree(e->d_bbox); cudaFree(e->d_lut); cudaFree(e->d_stats);
+  cudaFree(e->d_prefix); cudaFree(e->d_prefix2);
   if (e->prefix_stream) { cudaStreamSynchronize(e->prefix_stream); cudaStreamDestroy(e->prefix_stream); }
   for (int k = 0; k < 2; k++) {
     if (e->ev_prefix_done[k]) cudaEventDestroy(e->ev_prefix_done[k]);
     if (e->ev_prefix_free[k]) cudaEventDestroy(e->ev_prefix_free[k]);
   }
   if (e->ev_upload) cudaEventDestroy(e->ev_upload);
-  cudaFree(e->d_fams); cudaFree(e->d_fam_progs);
-  if (e->h_fams) cudaFreeHost(e->h_fams);
-  if (e->h_fam_progs) cudaFreeHost(e->h_fam_progs);
-  if (e->h_slots) cudaFreeHost(e->h_slots);
-  if (e->h_slot_progs) cudaFreeHost(e->h_slot_progs);
+  if (e->tex_stream) { cudaStreamSynchronize(e->tex_stream); cudaStreamDestroy(e->tex_stream); }
+  if (e->fin_stream) { cudaStreamSynchronize(e->fin_stream); cudaStreamDestroy(e->fin_stream); }
+  if (e->drain_stream) { cudaStreamSynchronize(e->drain_stream); cudaStreamDestroy(e->drain_stream); }
+  for (int k = 0; k < LFB_SPARSE_SLOTS; k++) {
+    cudaFree(e->slot[k].accum); cudaFree(e->slot[k].state); cudaFree(e->slot[k].stage);
+    if (e->slot[k].ev_traced) cudaEventDestroy(e->slot[k].ev_traced);
+    if (e->slot[k].ev_done) cudaEventDestroy(e->slot[k].ev_done);
+    if (e->slot[k].ev_begin) cudaEventDestroy(e->slot[k].ev_begin);
+    if (e->slot[k].ev_tile0) cudaEventDestroy(e->slot[k].ev_tile0);
+    if (e->slot[k].ev_staged) cudaEventDestroy(e->slot[k].ev_staged);
+  }
+  if (e->ev_epoch) cudaEventDestroy(e->ev_epoch);
+  if (e->ev_tex_up) cudaEventDestroy(e->ev_tex_up);
+  for (int k = 0; k < 2; k++)
+    if (e->ev_tex_free[k]) cudaEventDestroy(e->ev_tex_free[k]);
+  for (int k = 0; k < 2; k++) {
+    lfb_engine::HostStage& st = e->stage[k];
+    if (st.arena) cudaFreeHost(st.arena);
+    if (st.ev) cudaEventDestroy(st.ev);
+    if (e->ev_rec_free[k]) cudaEventDestroy(e->ev_rec_free[k]);
+  }
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   for (int k = 0; k < 2; k++) {
     cudaFree(e->d_out_ab[k]);
@@ -940,10 +1090,8 @@ extern "C" void lfb_destroy(lfb_engine* e) {
   if (e->h_count) cudaFreeHost(e->h_count);
   scene_free(e->scene);
   cudaFree(e->d_sparse_state);
-  if (e->h_progs) cudaFreeHost(e->h_progs);
-  cudaFree(e->d_tex); cudaFree(e->d_jobs); cudaFree(e->d_dump_job); cudaFree(e->d_accum); cudaFree(e->d_out);
+  cudaFree(e->d_tex_ab[0]); cudaFree(e->d_tex_ab[1]); cudaFree(e->d_dump_job); cudaFree(e->d_accum); cudaFree(e->d_out);
   cudaFree(e->d_hits); cudaFree(e->d_tris); cudaFree(e->d_ghosts); cudaFree(e->d_pairs); cudaFree(e->d_rgbw);
-  if (e->h_jobs) cudaFreeHost(e->h_jobs);
   if (e->ev_frame0) cudaEventDestroy(e->ev_frame0);
   if (e->ev_trace0) cudaEventDestroy(e->ev_trace0);
   if (e->ev_trace1) cudaEventDestroy(e->ev_trace1);
@@ -1088,6 +1236,7 @@ extern "C" int lfb_set_lens(lfb_engine* e, const lfb_lens* L) {
     CU(cudaMemcpy(e->d_lut, lut.data(), sizeof(float2) * lut.size(), cudaMemcpyHostToDevice));
   }
   e->job_key.clear();
+  e->struct_key.clear();
   e->has_lens = true;
   return LFB_OK;
 }
@@ -1099,15 +1248,27 @@ extern "C" int lfb_set_aperture(lfb_engine* e, const float* texels, int w, int h
   const size_t bytes = sizeof(float) * (size_t)w * h;
   if (w != e->tex_w || h != e->tex_h) {
     CU(cudaStreamSynchronize(e->stream));
-    cudaFree(e->d_tex);
+    CU(cudaStreamSynchronize(e->tex_stream));
+    for (int k = 0; k < 2; k++) {
+      cudaFree(e->d_tex_ab[k]);
+      e->d_tex_ab[k] = nullptr;
+      e->tex_free_valid[k] = false;
+    }
     e->d_tex = nullptr; e->has_tex = false;
-    CU(cudaMalloc((void**)&e->d_tex, bytes));
+    for (int k = 0; k < 2; k++) CU(cudaMalloc((void**)&e->d_tex_ab[k], bytes));
     e->tex_w = w; e->tex_h = h;
   }
-  CU(cudaMemcpyAsync(e->d_tex, texels, bytes, cudaMemcpyHostToDevice, e->stream));
-  CU(cudaStreamSynchronize(e->stream));  // the caller may free texels on return
+  const int nb = e->tex_cur ^ 1;
+  if (e->tex_free_valid[nb]) CU(cudaStreamWaitEvent(e->tex_stream, e->ev_tex_free[nb], 0));
+  CU(cudaMemcpyAsync(e->d_tex_ab[nb], texels, bytes, cudaMemcpyHostToDevice, e->tex_stream));
+  CU(cudaEventRecord(e->ev_tex_up, e->tex_stream));
+  CU(cudaEventSynchronize(e->ev_tex_up));  // the caller may free texels on return; later launches need no device-side wait
+  // everything enqueued so far reads the current texture (sweeps on prefix_stream are joined into `stream` by their frame)
+  CU(cudaEventRecord(e->ev_tex_free[e->tex_cur], e->stream));
+  e->tex_free_valid[e->tex_cur] = true;
+  e->tex_cur = nb;
+  e->d_tex = e->d_tex_ab[nb];
   e->has_tex = true;
-  e->upload_pending = true;
   return LFB_OK;
 }
 
@@ -1126,6 +1287,8 @@ extern "C" int lfb_sync(lfb_engine* e) {
   if (rc) return rc;
   CU(cudaStreamSynchronize(e->stream));
   if (e->copy_stream) CU(cudaStreamSynchronize(e->copy_stream));
+  if (e->fin_stream) CU(cudaStreamSynchronize(e->fin_stream));
+  if (e->drain_stream) CU(cudaStreamSynchronize(e->drain_stream));
   return LFB_OK;
 }
 
@@ -1355,6 +1518,105 @@ extern "C" int lfb_render_ghosts_sparse(lfb_engine* e, const lfb_light* lights, 
   if (tiles_written) *tiles_written = (int)e->h_count[0];
   CU(cudaEventElapsedTime(&e->last_frame_ms, e->ev_frame0, e->ev_frame1));
   CU(cudaEventElapsedTime(&e->last_trace_ms, e->ev_trace0, e->ev_trace1));
+  return LFB_OK;
+}
+
+// Several frames in flight (include/lfb200.h).  begin(slot): trace on the engine stream into the slot's own accumulator, then the
+// tile kernel on fin_stream writes the dirty tiles into `out` (page-locked, mapped); end(slot): wait for exactly that.
+extern "C" int lfb_render_ghosts_sparse_begin(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P, void* out,
+                                              size_t stride, int elem, int out_is_clear, int slot) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (slot < 0 || slot >= LFB_SPARSE_SLOTS) return fail(LFB_ERR_INVALID, "slot must be in [0, LFB_SPARSE_SLOTS)");
+  if (!e->has_lens || !e->has_tex) return fail(LFB_ERR_STATE, "set the lens and the aperture first");
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (n_lights < 0 || (n_lights > 0 && !lights)) return fail(LFB_ERR_INVALID, "bad lights");
+  rc = check_out_args(out, stride, elem);
+  if (rc) return rc;
+  lfb_engine::SparseSlot& S = e->slot[slot];
+  if (S.pending) return fail(LFB_ERR_STATE, "lfb_render_ghosts_sparse_begin: the slot's previous frame was not collected (lfb_render_ghosts_sparse_end)");
+  cudaPointerAttributes attr;
+  memset(&attr, 0, sizeof(attr));
+  if (cudaPointerGetAttributes(&attr, out) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+    cudaGetLastError();
+    return fail(LFB_ERR_INVALID, "lfb_render_ghosts_sparse_begin: `out` must be page-locked host memory mapped into the device (lfb_host_alloc / lfb_host_register)");
+  }
+  const int W = P->width, H = P->height;
+  const bool same = out == S.out && W == S.w && H == S.h && stride == S.stride && elem == S.elem;
+  if (!out_is_clear && !same) return fail(LFB_ERR_STATE, "lfb_render_ghosts_sparse_begin: `out` is not the buffer of the slot's previous frame; pass out_is_clear = 1 with a zeroed buffer");
+  const AccumLayout lay = accum_layout(W, H);
+  const size_t st_bytes = tile_state_bytes(W, H);
+  const size_t stage_bytes = tile_stage_bytes(W, H, stride);
+  if (lay.total > S.accum_cap || st_bytes > S.state_cap || stage_bytes > S.stage_cap) {
+    CU(cudaStreamSynchronize(e->fin_stream));
+    CU(cudaStreamSynchronize(e->drain_stream));
+    if (lay.total > S.accum_cap) S.accum_clean = false;
+    if ((rc = grow(&S.accum, &S.accum_cap, lay.total))) return rc;
+    if ((rc = grow(&S.state, &S.state_cap, st_bytes))) return rc;
+    if ((rc = grow(&S.stage, &S.stage_cap, stage_bytes))) return rc;
+  }
+  if (e->drain_gbps < 0.f) {  // once per engine
+    if (e->opt.host_write_mbps > 0) e->drain_gbps = 1e-3f * (float)e->opt.host_write_mbps;
+    else if (e->opt.host_write_mbps < 0) e->drain_gbps = 0.f;  // unpaced
+    else {
+      float link = 0.f;
+      CU(measure_host_write_gbps(e->fin_stream, &link));
+      e->drain_gbps = link > 5.f ? 0.85f * link : 0.f;  // below what the drain kernel reaches unpaced (~0.88 of the 16-CTA fill this measures)
+    }
+  }
+  // the slot's previous tile kernel (which also re-zeroed its accumulator) precedes this frame's trace
+  if (S.done_valid) CU(cudaStreamWaitEvent(e->stream, S.ev_done, 0));
+  CU(cudaEventRecord(S.ev_begin, e->stream));
+  if (out_is_clear || !same) CU(cudaMemsetAsync(S.state, 0, st_bytes, e->stream));
+  S.out = out; S.w = W; S.h = H; S.stride = stride; S.elem = elem;
+  const bool clean = S.accum_clean && S.accum_w == W && S.accum_h == H;
+  S.accum_clean = false;
+  rc = render_grid_device(e, lights, n_lights, *P, S.accum, clean ? 0 : 1);
+  if (rc) return rc;
+  CU(cudaEventRecord(S.ev_traced, e->stream));
+  CU(cudaStreamWaitEvent(e->fin_stream, S.ev_traced, 0));
+  PeerAccums A;
+  memset(&A, 0, sizeof(A));
+  A.n = 1; A.ptr[0] = S.accum;
+  const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+  unsigned* count_dev = nullptr;
+  CU(cudaHostGetDevicePointer((void**)&count_dev, e->h_count + 1 + slot, 0));
+  CU(cudaEventRecord(S.ev_tile0, e->fin_stream));
+  // stage 1 (every SM, ~15 us): dirty tiles -> pixels in the slot's device staging; stage 2 (a few CTAs on their own stream,
+  // paced): staging -> the caller's host frame.  Stage 1 of the next frame runs while this frame drains.
+  CU(launch_tiles(A, 0, W, H, inv, attr.devicePointer, stride, elem, S.state, count_dev, 0, e->fin_stream, S.stage));
+  CU(cudaEventRecord(S.ev_staged, e->fin_stream));
+  CU(cudaStreamWaitEvent(e->drain_stream, S.ev_staged, 0));
+  CU(launch_tile_drain(W, H, attr.devicePointer, stride, S.state, S.stage, e->opt.reduce_ctas, e->drain_gbps, e->drain_stream));
+  e->launches += 2;
+  CU(cudaEventRecord(S.ev_done, e->drain_stream));
+  S.done_valid = true;
+  S.pending = true;
+  S.accum_clean = true; S.accum_w = W; S.accum_h = H;  // once ev_done has fired, which every later user of the slot waits for
+  return LFB_OK;
+}
+
+extern "C" int lfb_sparse_slot_times(lfb_engine* e, int slot, float ms[5]) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (slot < 0 || slot >= LFB_SPARSE_SLOTS || !ms) return fail(LFB_ERR_INVALID, "bad slot");
+  lfb_engine::SparseSlot& S = e->slot[slot];
+  if (!S.done_valid || S.pending) return fail(LFB_ERR_STATE, "lfb_sparse_slot_times: the slot has no collected frame");
+  cudaEvent_t evs[5] = {S.ev_begin, S.ev_traced, S.ev_tile0, S.ev_staged, S.ev_done};
+  for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&ms[k], e->ev_epoch, evs[k]));
+  return LFB_OK;
+}
+
+extern "C" int lfb_render_ghosts_sparse_end(lfb_engine* e, int slot, int* tiles_written) {
+  int rc = bind(e);
+  if (rc) return rc;
+  if (slot < 0 || slot >= LFB_SPARSE_SLOTS) return fail(LFB_ERR_INVALID, "slot must be in [0, LFB_SPARSE_SLOTS)");
+  lfb_engine::SparseSlot& S = e->slot[slot];
+  if (!S.pending) return fail(LFB_ERR_STATE, "lfb_render_ghosts_sparse_end: no frame in flight in this slot");
+  CU(cudaEventSynchronize(S.ev_done));  // the kernel's stores into the caller's memory are complete and visible
+  S.pending = false;
+  if (tiles_written) *tiles_written = (int)e->h_count[1 + slot];
   return LFB_OK;
 }
 

@@ -375,10 +375,10 @@ struct WarpSplat {  // what a warp needs to deposit its lanes' results
   int W, H;
   float ch0, ch1, ch2;        // radiance * rgb_weight * ray area * 2^bits
   bool bilinear;
-  bool peek_l1;               // experiment: look at the tile bytes through L1
+  bool peek_l1;               // look at the tile bytes through L1 (default; lfb_options.experiment bit 0 = in L2)
   __device__ __forceinline__ WarpSplat(const FrameGeom& g, const Job& J, unsigned long long* tile_, unsigned long long* accum_)
       : tile(tile_), accum(accum_), bbox(g.bbox), tile_bits(g.tile_bits), tiles_w(g.tiles_w), W(g.W), H(g.H), ch0(J.f_chan[0]),
-        ch1(J.f_chan[1]), ch2(J.f_chan[2]), bilinear(g.splat == LFB_SPLAT_BILINEAR), peek_l1((g.pad2 & 1) != 0) {}
+        ch1(J.f_chan[1]), ch2(J.f_chan[2]), bilinear(g.splat == LFB_SPLAT_BILINEAR), peek_l1((g.pad2 & 1) == 0) {}
 };
 
 // Shared-memory accesses of the per-warp tile by 32-bit shared address: the tile pointer travels through structs and

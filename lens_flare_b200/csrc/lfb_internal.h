@@ -192,7 +192,15 @@ struct PeerFlags {  // every rank's barrier flag array (LFB_MAX_PEERS u64 each) 
 };
 // sparse.cu: dirty tiles of the ranks' accumulators -> pixels of `out` (n = 1: this GPU's finalize)
 cudaError_t launch_tiles(const PeerAccums& P, int rank, int W, int H, double inv_scale, void* out, size_t stride, int elem,
-                         unsigned* state, unsigned* count_out, int ctas, cudaStream_t s);
+                         unsigned* state, unsigned* count_out, int ctas, cudaStream_t s, void* stage = nullptr);
+cudaError_t launch_tile_drain(int W, int H, void* out, size_t stride, const unsigned* state, const void* stage, int ctas, float gbps,
+                              cudaStream_t s);
+cudaError_t measure_host_write_gbps(cudaStream_t s, float* gbps);
+// bytes of the optional device staging buffer of launch_tiles: every tile's pixels + one word per tile
+inline size_t tile_stage_bytes(int W, int H, size_t stride) {
+  const AccumLayout lay = accum_layout(W, H);
+  return (size_t)lay.n_tiles * kTilePx1 * kTilePx1 * stride + sizeof(unsigned) * (size_t)lay.n_tiles;
+}
 cudaError_t launch_peer_barrier(const PeerFlags& F, int rank, unsigned long long epoch, cudaStream_t s);
 cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long* mc, size_t p0, size_t p1, double inv_scale,
                                    void* out, size_t stride, int elem, int ctas, cudaStream_t s);
@@ -216,6 +224,9 @@ __device__ __forceinline__ void grow_bbox(int* bb, int x0, int y0, int x1, int y
 // right before atomicOr 84 us (26 % of the stall samples on the read); unconditional atomicOr 1.5 ms (same-address atomics
 // serialise in L2); unconditional byte stores 152 us (the hot sectors back the store path up: drain / MIO stalls
 // everywhere).  The throughput kernels therefore issue the look early (tile_peek) and act on it after the splat (tile_mark_if).
+// The EXACT_GRID landing code looks through L1 (__ldca) by default: within a kernel a byte only goes 0 -> 1, so a stale L1 line can
+// only show 0 for a set byte (the store is repeated, harmless), never 1 for a clear one; the maps are cleared by earlier
+// operations of the stream, and L1 is invalidated at every kernel launch.  cfg2 ghost kernel 0.091 -> 0.079 ms (tools/kernel_ab.py).
 __device__ __forceinline__ unsigned char* tile_byte(unsigned* map, int tiles_w, int tx, int ty) {
   return reinterpret_cast<unsigned char*>(map) + ((unsigned)ty * (unsigned)tiles_w + (unsigned)tx);
 }

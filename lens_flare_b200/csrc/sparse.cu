@@ -35,6 +35,8 @@ struct TileArgs {
   size_t stride;
   int elem;
   unsigned* count_out;   // optional (mapped host memory): the number of tiles this launch wrote
+  char* stage;           // optional: whole tiles go HERE, tile q at q * 16 * 16 * stride, rows packed (see drain_kernel) ...
+  unsigned* stage_tiles; // ... and [q] = the tile's byte offset in `out` / 16 (0xffffffff: tile q was stored directly)
 };
 
 __device__ __forceinline__ unsigned* bits_of(const TileArgs& A, int r) {
@@ -180,6 +182,8 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
     // are contiguous): whole 128-byte lines per warp -- what a PCIe (zero-copy host frame) or NVLink (peer frame) write wants;
     // 24-byte pixels stored 8 bytes per lane would go out as partial sectors (measured: 17 GB/s into host memory).
     const bool full = whole && row_vec;
+    if (A.stage && tid == 0)  // where the staged tile goes in the output, in 16-byte chunks
+      A.stage_tiles[q] = full ? (unsigned)((((size_t)ty * kTilePx1 * A.W + (size_t)tx * kTilePx1) * A.stride) >> 4) : 0xffffffffu;
     if (full) {
       char* mine = s_rows + (size_t)ly * row_bytes + (size_t)lx * A.stride;
       if (A.elem == LFB_F32x3) {
@@ -193,10 +197,11 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
       }
       __syncthreads();
       const int chunks_per_row = (int)(row_bytes / 16);
-      char* base = A.out + ((size_t)tx * kTilePx1 + (size_t)ty * kTilePx1 * A.W) * A.stride;
+      char* base = A.stage ? A.stage + (size_t)q * kTilePx1 * row_bytes : A.out + ((size_t)tx * kTilePx1 + (size_t)ty * kTilePx1 * A.W) * A.stride;
+      const size_t pitch = A.stage ? row_bytes : (size_t)A.W * A.stride;
       for (int c = tid; c < kTilePx1 * chunks_per_row; c += kThreads) {
         const int row = c / chunks_per_row, col = c - row * chunks_per_row;
-        *reinterpret_cast<uint4*>(base + (size_t)row * A.W * A.stride + (size_t)col * 16) =
+        *reinterpret_cast<uint4*>(base + (size_t)row * pitch + (size_t)col * 16) =
             *reinterpret_cast<const uint4*>(s_rows + (size_t)row * row_bytes + (size_t)col * 16);
       }
       __syncthreads();  // s_rows is reused by the CTA's next tile
@@ -231,12 +236,92 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
   }
 }
 
+// The second stage of a frame that goes to HOST memory while other work runs: a FEW CTAs copy the staged tiles into the
+// caller's page-locked frame, PACED just below the link rate.  Measured on B200 (tools/pcie_write_probe.cu):
+//  * stores into host memory are posted PCIe writes; SMs issue them far faster than the link drains them (~50 GB/s), and the
+//    backlog sits in front of every PCIe READ the GPU makes -- reads may not pass posted writes -- which is how the GPU fetches
+//    its command stream: 20 back-to-back tiny kernels take 80 us alone and 315 us next to an unpaced writer (they complete when
+//    it does), i.e. the next frame's kernels cannot even be launched while this frame drains;
+//  * an SM whose store path is backed up is also all but lost to the other CTAs on it.
+// A few CTAs storing one 16-byte chunk per thread and round, each round released by the clock at ~85 % of the link rate, keep
+// the backlog at a microsecond or two: in the probe the same 20 kernels then take 110 us and the writer still gets 43 of the
+// 48 GB/s it gets unpaced; in the frame pipeline (tools/e2e_probe.py, cfg2, sun moving every frame) 0.155 ms per frame against
+// 0.19 unpaced and 0.31 for one blocking call per frame.
+constexpr int kDrainDepth = 8;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void __launch_bounds__(kThreads) drain_kernel(const char* __restrict__ stage, const unsigned* __restrict__ stage_tiles,
+                                                         const unsigned* __restrict__ state, char* __restrict__ out, int W, size_t stride,
+                                                         float gbps) {
+  __shared__ unsigned long long s_t0;
+  const unsigned total = state[1];  // tiles of this frame (tiles_kernel's last CTA)
+  const unsigned cpr = (unsigned)stride, cpt = kTilePx1 * cpr;  // 16-byte chunks per tile row (16 px * stride / 16) / per tile
+  const unsigned n_chunks = total * cpt;                         // < 2^32: launch_tiles checks
+  const uint4* src = reinterpret_cast<const uint4*>(stage);
+  const unsigned per_round = gridDim.x * kThreads;  // chunks per round: one per thread (16 CTAs: 64 KB)
+  const float ns_per_round = gbps > 0.f ? (float)per_round * 16.f / gbps : 0.f;
+  const bool paced = ns_per_round > 0.f;
+  const unsigned pitch16 = (unsigned)(((size_t)W * stride) >> 4);  // output row pitch in chunks
+  if (threadIdx.x == 0) s_t0 = global_ns();
+  __syncthreads();
+  const unsigned lane0 = blockIdx.x * kThreads + threadIdx.x;
+  // this thread's chunk as (tile q, row, col), advanced by one round per step without divisions
+  unsigned q = lane0 / cpt, row = (lane0 - q * cpt) / cpr, col = lane0 - q * cpt - row * cpr;
+  const unsigned dq = per_round / cpt, drow = (per_round - dq * cpt) / cpr, dcol = per_round - dq * cpt - drow * cpr;
+  uint4 cur[kDrainDepth], nxt[kDrainDepth];
+#pragma unroll
+  for (int d = 0; d < kDrainDepth; d++) {
+    const unsigned c = lane0 + (unsigned)d * per_round;
+    cur[d] = c < n_chunks ? __ldcg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  unsigned round = 0;
+  for (unsigned g = 0; g < n_chunks; g += per_round * kDrainDepth) {  // uniform over the CTA: it synchronises every round
+#pragma unroll
+    for (int d = 0; d < kDrainDepth; d++) {  // the next group's loads are in flight while this group drains
+      const unsigned c = g + lane0 + (unsigned)(kDrainDepth + d) * per_round;
+      nxt[d] = c < n_chunks ? __ldcg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int d = 0; d < kDrainDepth; d++) {
+      const unsigned c = g + lane0 + (unsigned)d * per_round;
+      if (c < n_chunks) {
+        const unsigned off16 = __ldca(stage_tiles + q);  // the tile's first chunk in the output, or ~0: stored directly (frame edge)
+        if (off16 != 0xffffffffu)
+          reinterpret_cast<uint4*>(out)[(size_t)off16 + (size_t)row * pitch16 + col] = cur[d];
+      }
+      col += dcol; row += drow; q += dq;
+      if (col >= cpr) { col -= cpr; row++; }
+      if (row >= (unsigned)kTilePx1) { row -= kTilePx1; q++; }
+      if (paced) {
+        round++;
+        if (threadIdx.x == 0) {
+          const unsigned long long due = s_t0 + (unsigned long long)((float)round * ns_per_round);
+          while (global_ns() < due) {}  // one spinning thread per CTA; __nanosleep overshoots by more than a round
+        }
+        __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < kDrainDepth; d++) cur[d] = nxt[d];
+  }
+}
+
+// calibration: how fast do unpaced stores from a few CTAs fill page-locked host memory?
+__global__ void __launch_bounds__(kThreads) host_fill_kernel(uint4* out, size_t n16, unsigned v) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n16; i += (size_t)gridDim.x * kThreads) out[i] = make_uint4(v, v, v, v);
+}
+
 }  // namespace
 
 // accum_ptrs[r]: rank r's accumulator buffer as mapped in this process (n_ranks = 1: this GPU's own); state: this rank's
 // tile state of `out` (tile_state_bytes, zero-initialised once while `out` is clear).
+// stage (optional, lfb_internal.h: tile_stage_bytes): whole tiles are staged there instead of stored into `out`; launch_tile_drain
+// copies them out -- for a host-memory `out` written while other kernels run.
 cudaError_t launch_tiles(const PeerAccums& P, int rank, int W, int H, double inv_scale, void* out, size_t stride, int elem,
-                         unsigned* state, unsigned* count_out, int ctas, cudaStream_t s) {
+                         unsigned* state, unsigned* count_out, int ctas, cudaStream_t s, void* stage) {
   const AccumLayout lay = accum_layout(W, H);
   TileArgs A;
   A.acc = P;
@@ -247,6 +332,8 @@ cudaError_t launch_tiles(const PeerAccums& P, int rank, int W, int H, double inv
   A.inv_scale = inv_scale;
   A.out = (char*)out; A.stride = stride; A.elem = elem;
   A.count_out = count_out;
+  A.stage = (char*)stage;
+  A.stage_tiles = stage ? reinterpret_cast<unsigned*>((char*)stage + (size_t)lay.n_tiles * kTilePx1 * kTilePx1 * stride) : nullptr;
   const size_t smem = sizeof(unsigned) * ((size_t)lay.n_words + 1);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // > 1.6 M tiles: use the dense finalize
   if (smem > 48 * 1024) {
@@ -261,7 +348,46 @@ cudaError_t launch_tiles(const PeerAccums& P, int rank, int W, int H, double inv
   }
   if (ctas > lay.n_tiles) ctas = lay.n_tiles;
   tiles_kernel<<<ctas, kThreads, smem, s>>>(A);
+  if (stage && (((size_t)W * H * stride) >> 4) >= 0xffffffffull) return cudaErrorInvalidConfiguration;  // chunk offsets are 32-bit
   return cudaGetLastError();
 }
 
+// The staged tiles of launch_tiles(..., stage) -> `out` (page-locked host memory), by `ctas` CTAs paced at gbps (<= 0: unpaced).
+// Any stream, ordered after that launch_tiles.
+cudaError_t launch_tile_drain(int W, int H, void* out, size_t stride, const unsigned* state, const void* stage, int ctas, float gbps,
+                              cudaStream_t s) {
+  const AccumLayout lay = accum_layout(W, H);
+  const char* st = (const char*)stage;
+  const unsigned* stage_tiles = reinterpret_cast<const unsigned*>(st + (size_t)lay.n_tiles * kTilePx1 * kTilePx1 * stride);
+  drain_kernel<<<ctas > 0 ? ctas : 16, kThreads, 0, s>>>(st, stage_tiles, state, (char*)out, W, stride, gbps);
+  return cudaGetLastError();
+}
+
+}  // namespace lfb
+
+namespace lfb {
+// GB/s that unpaced SM stores reach into page-locked host memory on this device's link (best of 3 fills of 8 MB).
+cudaError_t measure_host_write_gbps(cudaStream_t s, float* gbps) {
+  const size_t bytes = (size_t)8 << 20;
+  char *h = nullptr, *hd = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t err = cudaHostAlloc((void**)&h, bytes, cudaHostAllocMapped);
+  if (err != cudaSuccess) return err;
+  if ((err = cudaHostGetDevicePointer((void**)&hd, h, 0)) != cudaSuccess) { cudaFreeHost(h); return err; }
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 0.f;
+  for (int rep = 0; rep < 4 && err == cudaSuccess; rep++) {
+    cudaEventRecord(e0, s);
+    host_fill_kernel<<<16, kThreads, 0, s>>>(reinterpret_cast<uint4*>(hd), bytes / 16, (unsigned)rep);
+    cudaEventRecord(e1, s);
+    err = cudaStreamSynchronize(s);
+    float ms = 0.f;
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms > 0.f) best = fmaxf(best, (float)bytes / (ms * 1e6f));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFreeHost(h);
+  *gbps = best;
+  return err;
+}
 }  // namespace lfb

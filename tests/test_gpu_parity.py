@@ -444,7 +444,7 @@ def test_exact_kernel_variants_agree(engine, port, apertures):
                 ("split2", dict(kernel_select=2, family_split=2)), ("alt_build", dict(kernel_select=1, ctas_per_sm=1)),
                 ("alt_build_fam", dict(kernel_select=2, ctas_per_sm=1)), ("no_overlap", dict(kernel_select=1, prefix_overlap=-1)),
                 ("unstaged", dict(kernel_select=1, ctas_per_sm=2)), ("landing_out_of_line", dict(kernel_select=1, ctas_per_sm=3)),
-                ("peek_l1", dict(kernel_select=1, experiment=1)))
+                ("peek_l2", dict(kernel_select=1, experiment=1)))
     frames = {}
     for name, opts in variants:
         e = capi.Engine(0, **opts)
@@ -829,6 +829,62 @@ def test_sparse_render_equals_full_frame(apertures, mode, prec):
         mine = np.full((H, W, 3), -1.0)
         assert e.render_ghosts_sparse(seq[0], p, mine, out_is_clear=True) == -1
         assert np.array_equal(mine, e.render_ghosts(seq[0], p))
+    finally:
+        for b in bufs:
+            b.free()
+        e.close()
+
+
+def test_sparse_two_frames_in_flight(apertures):
+    """lfb_render_ghosts_sparse_begin / _end: frames enqueued two deep into two page-locked buffers (the sun moves every frame,
+    the aperture is re-uploaded between them) are, when collected, bit for bit the frames of the blocking calls."""
+    e = capi.Engine(0)
+    W, H = 1000, 562
+    bufs = [capi.PinnedArray((H, W, 3), np.float64), capi.PinnedArray((H, W, 3), np.float64)]
+    try:
+        e.set_lens(capi.builtin_lens(3, 550.0))
+        tex_a, tex_b = apertures["pentbig500_14"], np.ascontiguousarray(apertures["pentbig500_14"][::-1, :] * 0.5)
+        e.set_aperture(tex_a)
+        p = capi.make_params(capi.MODE_EXACT_GRID, W, H, grid_n=80, pair_set=capi.PAIRS_ALL, include_direct=1)
+        mk = lambda x, y, **kw: capi.make_light(x, y, theta=capi.physical_theta(x, y), **kw)  # noqa: E731
+        seq = [[mk(0.45, 0.55)], [mk(0.7, 0.3, radiance=(2.0, 1.0, 0.5))], [], [mk(0.45, 0.55), mk(0.3, 0.62)], [mk(0.52, 0.5)], [mk(0.6, 0.4)], [mk(0.45, 0.55)]]
+        texs = [tex_a, tex_a, tex_b, tex_b, tex_a, tex_b, tex_a]
+        want = []
+        for lights, tex in zip(seq, texs):
+            e.set_aperture(tex)
+            want.append(e.render_ghosts(lights, p))
+        assert not np.array_equal(want[0], want[5]) and np.array_equal(want[0], want[6])
+        for b in bufs:
+            b.array[...] = 0.0
+        got = [None] * len(seq)
+        for k, (lights, tex) in enumerate(zip(seq, texs)):
+            s = k % 2
+            if k >= 2:  # collect the slot's previous frame before reusing its buffer
+                n = e.render_ghosts_sparse_end(s)
+                assert n >= 0
+                got[k - 2] = bufs[s].array.copy()
+            e.set_aperture(tex)
+            e.render_ghosts_sparse_begin(lights, p, bufs[s].array, s, out_is_clear=(k < 2))
+        for k in (len(seq) - 2, len(seq) - 1):
+            e.render_ghosts_sparse_end(k % 2)
+            got[k] = bufs[k % 2].array.copy()
+        for k in range(len(seq)):
+            assert np.array_equal(got[k], want[k]), k
+        # a slot must be collected before it is used again; an empty slot cannot be collected
+        e.render_ghosts_sparse_begin(seq[0], p, bufs[0].array, 0)
+        with pytest.raises(capi.LfbError) as err:
+            e.render_ghosts_sparse_begin(seq[1], p, bufs[0].array, 0)
+        assert err.value.code == capi.ERR_STATE
+        e.render_ghosts_sparse_end(0)
+        with pytest.raises(capi.LfbError) as err:
+            e.render_ghosts_sparse_end(0)
+        assert err.value.code == capi.ERR_STATE
+        # pageable memory is refused (no staged fallback)
+        with pytest.raises(capi.LfbError) as err:
+            e.render_ghosts_sparse_begin(seq[0], p, np.zeros((H, W, 3)), 1, out_is_clear=True)
+        assert err.value.code == capi.ERR_INVALID
+        # the blocking calls still work on the same engine afterwards
+        assert np.array_equal(e.render_ghosts(seq[6], p), want[6])
     finally:
         for b in bufs:
             b.free()

@@ -21,8 +21,8 @@ VARIANTS = {
     "pairs_alt": dict(kernel_select=1, ctas_per_sm=1),
     "pairs_unstaged": dict(kernel_select=1, ctas_per_sm=2),
     "pairs_landcall": dict(kernel_select=1, ctas_per_sm=3),
-    "pairs_peek_l1": dict(kernel_select=1, experiment=1),
-    "families_peek_l1": dict(kernel_select=2, experiment=1),
+    "pairs_peek_l2": dict(kernel_select=1, experiment=1),
+    "families_peek_l2": dict(kernel_select=2, experiment=1),
     "pairs_table": dict(kernel_select=1, weights_table=1),
     "pairs_nooverlap": dict(kernel_select=1, prefix_overlap=-1),
     "pairs_nocache": dict(kernel_select=1, prefix_budget_bytes=-1),
