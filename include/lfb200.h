@@ -134,8 +134,9 @@ typedef struct lfb_params {
   int32_t physical_backward; /* PARAXIAL_GRID only: 0 = the reference's R^-1 on backward legs
                                 (pathtracer.cpp:607-608), 1 = physically consistent backward refraction */
   int32_t shard_index, shard_count; /* this engine renders its share of the (light x pair x lambda) job list: whole
-                                       (light, lambda) groups round-robin as far as they divide evenly among the shards,
-                                       the jobs of the remaining groups one by one, longest first; 0,0 -> all */
+                                       (light, lambda) groups in contiguous blocks (a shard gets all wavelengths of a few
+                                       lights) as far as they divide evenly among the shards, the jobs of the remaining
+                                       groups one by one, longest first; 0,0 -> all */
   float px_per_unit;       /* sensor pixels per lens unit; 0 -> 0.4 (pathtracer.cpp:457-463) */
   int32_t physical_mapping; /* grid modes.  0 = the reference's screen mapping (draw_ghost / shift_vertex, pathtracer.cpp:412-430,
                                457-463): origin at the sun pixel, ghosts laid out along atan((ay-.5)/(ax-.5)) -- an angle mod pi, so

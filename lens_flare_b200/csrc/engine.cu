@@ -87,17 +87,19 @@ void list_jobs(const lfb_lens& L, const lfb_params& P, int n_lights, std::vector
   }
   out.clear();
   if (P.shard_count <= 1) { out = all; return; }
-  // Sharding.  All ghosts of a (light, lambda) group share one forward sweep (the prefix cache), so groups are dealt WHOLE,
-  // round-robin, as far as they divide evenly among the shards: groups 0 .. floor(G / S) * S - 1.  The jobs of the remaining
-  // G mod S groups (all of them when G < S) are put in longest-processing-time-first order (stable) and dealt one by one,
-  // so that e.g. one RGB light on two GPUs is split 1.5 : 1.5 groups, not 2 : 1.
+  // Sharding.  All ghosts of a (light, lambda) group share one forward sweep (the prefix cache), so groups are dealt WHOLE, in
+  // CONTIGUOUS blocks (groups are light-major: a shard gets all wavelengths of a few lights, so its deposits -- and the tiles
+  // the cross-GPU reduce has to fetch from it -- stay near those lights), as far as they divide evenly among the shards:
+  // groups 0 .. floor(G / S) * S - 1.  The jobs of the remaining G mod S groups (all of them when G < S) are put in
+  // longest-processing-time-first order (stable) and dealt one by one, so that e.g. one RGB light on two GPUs is split
+  // 1.5 : 1.5 groups, not 2 : 1.
   const int S = P.shard_count;
   const int n_groups = P.mode == LFB_MODE_REF_QUADS ? 0 : n_lights * L.n_lambda;
   const int n_whole = (n_groups / S) * S;
   std::vector<JobId> rest;
   for (const JobId& id : all) {
     const int grp = id.light * L.n_lambda + id.lambda;
-    if (grp < n_whole) { if (grp % S == P.shard_index) out.push_back(id); }
+    if (grp < n_whole) { if (grp / (n_whole / S) == P.shard_index) out.push_back(id); }
     else rest.push_back(id);
   }
   std::stable_sort(rest.begin(), rest.end(), [&](const JobId& a, const JobId& b) {

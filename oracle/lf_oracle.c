@@ -712,7 +712,7 @@ static int list_jobs(const lfb_lens* L, const lfb_params* P, int n_lights, job_t
       }
     }
   if (P->shard_count > 1) {
-    /* whole (light, lambda) groups round-robin as far as they divide evenly (groups 0 .. floor(G/S)*S - 1); the jobs of the
+    /* whole (light, lambda) groups in contiguous blocks as far as they divide evenly (groups 0 .. floor(G/S)*S - 1); the jobs of the
      * remaining groups in longest-processing-time-first order (stable), dealt one by one */
     const int S = P->shard_count, G = n_lights * L->n_lambda, n_whole = (G / S) * S;
     job_t* keep = (job_t*)malloc(sizeof(job_t) * (n > 0 ? n : 1));
@@ -720,7 +720,7 @@ static int list_jobs(const lfb_lens* L, const lfb_params* P, int n_lights, job_t
     int m = 0, nr = 0;
     for (int q = 0; q < n; q++) {
       int grp = J[q].light * L->n_lambda + J[q].lambda;
-      if (grp < n_whole) { if (grp % S == P->shard_index) keep[m++] = J[q]; }
+      if (grp < n_whole) { if (grp / (n_whole / S) == P->shard_index) keep[m++] = J[q]; }
       else rest[nr++] = J[q];
     }
     for (int a = 1; a < nr; a++) { /* stable insertion sort, decreasing cost */
