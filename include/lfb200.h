@@ -190,7 +190,7 @@ typedef struct lfb_options {
   int32_t experiment;         /* bit mask of measurement switches that never change a frame's bits (tools/kernel_ab.py): 1 = look at the
                                  dirty-tile bytes in L2 (ld.global.cg) instead of through L1 (the default: 13 % faster at cfg2) */
   int32_t host_write_mbps;    /* lfb_render_ghosts_sparse_begin: the pace, in MB/s, at which a frame's tiles are stored into host memory
-                                 while other frames are in flight: 0 = 85 % of what unpaced stores reach on this link (measured once,
+                                 while other frames are in flight: 0 = 93 % of what unpaced stores reach on this link (measured once,
                                  at the first call); < 0 = unpaced (the next frame's kernels then wait for the stores: see sparse.cu) */
   int32_t reserved[5];
 } lfb_options;

@@ -1564,7 +1564,8 @@ extern "C" int lfb_render_ghosts_sparse_begin(lfb_engine* e, const lfb_light* li
     else {
       float link = 0.f;
       CU(measure_host_write_gbps(e->fin_stream, &link));
-      e->drain_gbps = link > 5.f ? 0.85f * link : 0.f;  // below what the drain kernel reaches unpaced (~0.88 of the 16-CTA fill this measures)
+      // measured (tools/e2e_probe.py, link ~50 GB/s): 0.146 ms / frame at 48 GB/s, 0.155 at 44, 0.19 at 32, 0.17 at 52, 0.19 unpaced
+      e->drain_gbps = link > 5.f ? 0.93f * link : 0.f;
     }
   }
   // the slot's previous tile kernel (which also re-zeroed its accumulator) precedes this frame's trace

@@ -243,10 +243,11 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
 //    its command stream: 20 back-to-back tiny kernels take 80 us alone and 315 us next to an unpaced writer (they complete when
 //    it does), i.e. the next frame's kernels cannot even be launched while this frame drains;
 //  * an SM whose store path is backed up is also all but lost to the other CTAs on it.
-// A few CTAs storing one 16-byte chunk per thread and round, each round released by the clock at ~85 % of the link rate, keep
+// A few CTAs storing one 16-byte chunk per thread and round, each round released by the clock just below the link rate, keep
 // the backlog at a microsecond or two: in the probe the same 20 kernels then take 110 us and the writer still gets 43 of the
-// 48 GB/s it gets unpaced; in the frame pipeline (tools/e2e_probe.py, cfg2, sun moving every frame) 0.155 ms per frame against
-// 0.19 unpaced and 0.31 for one blocking call per frame.
+// 48 GB/s it gets unpaced; in the frame pipeline (tools/e2e_probe.py, cfg2, sun moving every frame) 0.146 ms per frame at 48 GB/s
+// against 0.19 unpaced (and 0.17 at 52 GB/s, 0.19 at 32: the optimum sits right under the link rate) and 0.27 for one blocking
+// call per frame.
 constexpr int kDrainDepth = 8;
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -378,7 +379,7 @@ cudaError_t measure_host_write_gbps(cudaStream_t s, float* gbps) {
   float best = 0.f;
   for (int rep = 0; rep < 4 && err == cudaSuccess; rep++) {
     cudaEventRecord(e0, s);
-    host_fill_kernel<<<16, kThreads, 0, s>>>(reinterpret_cast<uint4*>(hd), bytes / 16, (unsigned)rep);
+    host_fill_kernel<<<64, kThreads, 0, s>>>(reinterpret_cast<uint4*>(hd), bytes / 16, (unsigned)rep);  // (16 CTAs reach only ~35 of the link's ~50 GB/s)
     cudaEventRecord(e1, s);
     err = cudaStreamSynchronize(s);
     float ms = 0.f;
