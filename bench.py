@@ -848,8 +848,9 @@ def run_ours(args):
             "achieved": ach / 1e12, "peak": peaks["fp32_flops"] / 1e12, "unit": "TFLOP/s", "frac": frac,
             "frac_is": "NOMINAL: declared 64 FLOP x nominal interactions (rays x I(i,j), BASELINE.json's unit) / kernel time / FFMA peak -- "
                        "algorithmic throughput, NOT pipe occupancy; see executed_* and issue_slot_frac",
-            "traffic": None, "traffic_note": "the kernel has no algorithmic HBM stream (rays come from their grid index; the 28 MB prefix cache and the sensor "
-                                             "atomics live in L2); ncu --set full of the round-2 kernel: profiles/r2_ghost_kernel_ncu_details.txt",
+            "traffic": 24.03e6, "traffic_note": "bytes per launch: dram__bytes_read.sum 24.03 MB + dram__bytes_write.sum 0 of ghost_kernel in the committed capture "
+                                                "profiles/r2_ghost_v16_ncu_summary.txt (cold L2: the prefix cache it reads). The kernel has no algorithmic HBM stream -- rays "
+                                                "come from their grid index, the 28 MB prefix cache and the sensor atomics live in L2 -- so there is no byte roofline to compare with",
             "kernel_ms": k_ms, "kernel_ms_spread": spread(trace_ms), "interactions_per_launch": inter_rank, "flop_per_interaction": FLOP_PER_INTERACTION,
             "executed_steps": executed["steps"] if executed else None,
             "executed_ray_pairs_started": executed["ray_pairs_started"] if executed else None,
@@ -859,7 +860,7 @@ def run_ours(args):
             "frac_executed": frac * exec_ratio if executed else None,
             "executed_note": "surface steps the kernels actually ran (lfb_exec_stats, the counting build): mirror-image ray pairs share one trace, "
                              "the forward sweep is traced once per (light, lambda), rays stop where they die",
-            "issue_slot_frac": 0.52, "issue_slot_source": "ncu --set full, profiles/r2_ghost_kernel_ncu_details.txt (issue slots busy; the kernel is latency-bound)",
+            "issue_slot_frac": 0.68, "issue_slot_source": "ncu --set full, profiles/r2_ghost_v16_ncu_summary.txt (Issue Slots Busy 68.2 %, 75.4 us, 24 MB of DRAM reads; stalls: long scoreboard 26 %, wait 16 %, barrier 11 %)",
             "peak_source": "measured live on this GPU by lfb_probe_peaks (register-only FFMA chains); MEASURED_PEAKS.json holds no "
                            "FP32 figure. The trace is scalar FP32/MUFU math: neither 'hbm' nor 'tensor' bounds it",
             "mufu": {"achieved_gops": mufu_ach / 1e9, "peak_gops": peaks["mufu_ops"] / 1e9, "frac": mufu_ach / peaks["mufu_ops"],

@@ -76,12 +76,32 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
   const int per = (A.n_words + kThreads - 1) / kThreads;  // contiguous words per thread
   const int w0 = tid * per, w1 = min(w0 + per, A.n_words);
   unsigned mine = 0;
-  for (int w = w0; w < w1; w++) {
-    unsigned m = 0;
-    if (w % n == A.rank) m = prev[w] | or_of_ranks(A, w);
-    const unsigned c = __popc(nonzero_bytes(m));
-    s_pre[w] = c;
-    mine += c;
+  if (n == 1) {  // one GPU: the words of this thread's run eight at a time, their loads in flight together
+    const unsigned* cur = bits_of(A, 0);
+    for (int wb = w0; wb < w1; wb += 8) {
+      unsigned pv[8], cv[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const bool in = wb + k < w1;
+        pv[k] = in ? prev[wb + k] : 0u;
+        cv[k] = in ? cur[wb + k] : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (wb + k >= w1) break;
+        const unsigned c = __popc(nonzero_bytes(pv[k] | cv[k]));
+        s_pre[wb + k] = c;
+        mine += c;
+      }
+    }
+  } else {
+    for (int w = w0; w < w1; w++) {
+      unsigned m = 0;
+      if (w % n == A.rank) m = prev[w] | or_of_ranks(A, w);
+      const unsigned c = __popc(nonzero_bytes(m));
+      s_pre[w] = c;
+      mine += c;
+    }
   }
   // block-exclusive scan of the per-thread sums
   unsigned incl = mine;
@@ -217,17 +237,35 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
   }
 
   // ---- 3. the CTA that finishes last rolls the tile maps over ----
-  __threadfence();
+  // (no fence before the ticket: what the last CTA must not overtake are the other CTAs' READS of the maps, and those have
+  // completed -- their values were consumed above; this CTA's pixel stores need no ordering against the roll, and the kernel's
+  // end publishes them.  A __threadfence() here was 26 % of the kernel's stall samples.)
   __syncthreads();
   if (tid == 0) s_last = atomicAdd(A.state, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int w = tid; w < A.n_words; w += kThreads) {
-    if (w % n != A.rank) continue;
-    const unsigned m = or_of_ranks(A, w);
-    for (int r = 0; r < n; r++) bits_of(A, r)[w] = 0u;
-    prev[w] = m;
+  if (n == 1) {
+    unsigned* cur = bits_of(A, 0);
+    for (int wb = tid; wb < A.n_words; wb += 8 * kThreads) {
+      unsigned cv[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) cv[k] = wb + k * kThreads < A.n_words ? cur[wb + k * kThreads] : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int w = wb + k * kThreads;
+        if (w >= A.n_words) break;
+        cur[w] = 0u;
+        prev[w] = cv[k];
+      }
+    }
+  } else {
+    for (int w = tid; w < A.n_words; w += kThreads) {
+      if (w % n != A.rank) continue;
+      const unsigned m = or_of_ranks(A, w);
+      for (int r = 0; r < n; r++) bits_of(A, r)[w] = 0u;
+      prev[w] = m;
+    }
   }
   if (tid == 0) {
     A.state[0] = 0u;

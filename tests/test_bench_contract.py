@@ -35,7 +35,7 @@ def test_reference_arm_contract(ref):
 @pytest.mark.gpu
 def test_our_arm_contract():
     d = run_bench("--steps", "5", "--warmup", "3", "--no-cpu")
-    assert BASE_KEYS | {"roofline", "clocks", "strict", "parity", "e2e_full_frame", "e2e_rgba8", "brackets_ms_per_step"} <= set(d)
+    assert BASE_KEYS | {"roofline", "clocks", "strict", "parity", "e2e_full_frame", "e2e_blocking_call", "e2e_rgba8", "brackets_ms_per_step"} <= set(d)
     assert d["metric"] == "ray_surface_interactions_per_s" and d["n_gpus"] == 1 and d["steps"] == 5 and d["dtype"] == "f32"
     assert d["config"]["interactions_per_frame"] == 95944704.0 and d["config"]["jobs_per_frame"] == 87
     assert d["value"] > 1e10 and d["ms_per_step"] < 5.0          # the north star's target: a 1080p RGB flare frame in < 5 ms
@@ -45,6 +45,8 @@ def test_our_arm_contract():
     e = d["e2e"]   # tile-sparse: only the dirty tiles cross PCIe, and the frame in host memory is the full-frame call's
     assert 0 < e["d2h_bytes_per_step"] < 0.2 * 1920 * 1080 * 24 and e["h2d_bytes_per_step"] > 1_000_000 and 0 < e["value"] < d["value"]
     assert d["parity"]["e2e_frame_equals_full_frame_call"] is True
+    assert all(d["parity"]["e2e_pipelined_frame_%d_equals_full_frame_call" % s] is True for s in range(4))   # the frames collected from flight
+    assert e["value"] > d["e2e_blocking_call"]["value"] > d["e2e_full_frame"]["value"]
     assert d["e2e_full_frame"]["d2h_bytes_per_step"] == 1920 * 1080 * 24 and d["e2e_full_frame"]["value"] < e["value"]
     assert d["strict"]["ms_per_step"] < 5.0 and len(d["brackets_ms_per_step"]) == 7
     oc = d["other_configs"]   # BASELINE configs 3 and 4, one frame each, checked against the unsharded frame
