@@ -677,6 +677,11 @@ def run_ours(args):
         dist.broadcast_object_list(name, src=0, group=cpu_group)
         if rank != 0:
             shm = shared_memory.SharedMemory(name=name[0])
+            try:  # rank 0 owns (and unlinks) the segment: keep this process's resource tracker from trying again at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         host = np.frombuffer(shm.buf, dtype=np.float64, count=N_BUF * HEIGHT * WIDTH * 3).reshape(N_BUF, HEIGHT, WIDTH, 3)
         if rank == 0:
             host[...] = 0.0
