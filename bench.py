@@ -391,7 +391,7 @@ def run_ours(args):
     rays_frame, inter_frame, jobs_frame = capi.count_work(lens, params, n_lights)
     assert inter_frame == nominal_interactions(n_lights), "bench.py's nominal count disagrees with lfb_count_work"
     N_BUF = 3  # rotating accumulator / output / state sets
-    fin = capi.Engine(local, stream_priority=1)  # the tile finalize / reduce runs on a second, high-priority stream
+    fin = capi.Engine(local, stream_priority=1, reduce_ctas=args.reduce_ctas)  # the tile finalize / reduce runs on a second, high-priority stream
     fin.set_lens(lens)
     fin.set_aperture(tex)
     A = torch.cuda.ExternalStream(eng.stream, device=dev)
@@ -694,29 +694,52 @@ def run_ours(args):
         pe = sharding.PeerSparse(eng, params, rank, world, dev, dist.group.WORLD, n_buffers=N_BUF, finalize_engine=fin,
                                  host_out_ptrs=[base + b * frame_bytes for b in range(N_BUF)])
 
+        # two frames in flight per rank: before frame k is enqueued, frame k - 2 is collected -- complete in the host frame on EVERY
+        # rank (PeerSparse.wait_frame: this rank passed the device-side barrier that each rank reaches after its reduce of that frame)
         def e2e_step(k):
+            if pe.k >= 2:
+                pe.wait_frame(pe.k - 2)
             eng.set_aperture(pinned_tex.array)
-            pe.begin()
-            b = pe.frame(lights_a if k % 2 == 0 else lights_b, owner=0, elem=capi.F64x3, stride=24)
+            return pe.frame(lights_a if k % 2 == 0 else lights_b, owner=0, elem=capi.F64x3, stride=24)
+
+        def e2e_drain():
             pe.finish()
             torch.cuda.synchronize()
-            return b
 
+        pe.begin()
         for k in range(W_ + (W_ % 2)):
             e2e_step(k)
-        e2e_brackets = []
+        e2e_drain()
+        e2e_brackets, blocking_brackets = [], []
         with clocks:
             for _ in range(N_BRACKETS):
                 barrier()
                 t0 = time.perf_counter()
                 for k in range(K):
                     b = e2e_step(k)
+                e2e_drain()
                 barrier()
                 t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 e2e_brackets.append(float(t[0]))
+            for _ in range(3):  # the same frames, one at a time (the previous rounds' e2e): every step waits for its own frame
+                barrier()
+                t0 = time.perf_counter()
+                for k in range(K):
+                    eng.set_aperture(pinned_tex.array)
+                    b = pe.frame(lights_a if k % 2 == 0 else lights_b, owner=0, elem=capi.F64x3, stride=24)
+                    e2e_drain()
+                barrier()
+                t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                blocking_brackets.append(float(t[0]))
         e2e_ms = statistics.median(e2e_brackets) / K
-        b = e2e_step(0)
+        e2e_extra["e2e_blocking_call"] = {"ms_per_step": statistics.median(blocking_brackets) / K, "unit": "interactions/s",
+                                          "value": inter_frame / (statistics.median(blocking_brackets) / K * 1e-3),
+                                          "api": "the same frames one at a time: every step waits for its own frame on every rank"}
+        eng.set_aperture(pinned_tex.array)
+        b = pe.frame(lights_a, owner=0, elem=capi.F64x3, stride=24)
+        e2e_drain()
         barrier()
         if rank == 0:
             whole64 = eng.render_ghosts(lights_a, params)
@@ -726,9 +749,10 @@ def run_ours(args):
         else:
             nz_tiles = 0
         d2h = nz_tiles * 256 * 24
-        e2e_api = ("PeerSparse with a shared page-locked host frame: every rank's lfb_reduce_tiles_peers writes its share of the dirty tiles "
-                   "straight into host memory over its own PCIe link (d2h_bytes_per_step counts the non-empty tiles; the ranks also re-zero "
-                   "the previous frame's)")
+        e2e_api = ("PeerSparse with shared page-locked host frames (3 in rotation, two frames in flight): every rank's lfb_reduce_tiles_peers "
+                   "writes its share of the dirty tiles straight into host memory over its own PCIe link; a frame is collected -- complete on "
+                   "every rank -- before the frame after next is enqueued (d2h_bytes_per_step counts the non-empty tiles; the ranks also "
+                   "re-zero the previous frame's)")
         del pe
         barrier()
         L.lfb_host_unregister(host.ctypes.data)
@@ -930,6 +954,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and oracle-parity legs")
     ap.add_argument("--no-strict", action="store_true", help="skip the LFB_STRICT leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 3 / config 4 single-frame legs")
+    ap.add_argument("--reduce-ctas", type=int, default=0, help="CTAs of the cross-GPU tile reduce kernel (0: the library default)")
     ap.add_argument("--reduce", default="sparse", choices=["sparse", "nccl", "peer", "multicast"],
                     help="N > 1: tile-sparse reduce + finalize over NVLink peer memory (default), or round 1's dense paths: one NCCL int64 "
                          "reduce of the whole frame / the dense fused kernel over peer memory / the same through NVSwitch multicast")

@@ -354,6 +354,14 @@ class PeerSparse:
             self.reduce_valid[b] = True
         return b
 
+    def wait_frame(self, j):
+        """Block the host until frame j (0-based, in enqueue order) is complete in its output buffer ON EVERY RANK: this rank has
+        passed barrier(j + 1), where each rank arrives only after its reduce(j).  Needs frame j + 1 enqueued and at most R frames
+        enqueued after j (two streams only)."""
+        if not self.two_streams or not (j + 1 < self.k <= j + 1 + self.n_buffers):
+            raise ValueError("wait_frame(%d): frame %d must be enqueued and recent (k = %d)" % (j, j + 1, self.k))
+        self.passed[(j + 1) % (self.n_buffers + 1)].synchronize()
+
     def result(self, b):
         """The owner's pixels of buffer b (valid after finish())."""
         return self.out_all[b]
