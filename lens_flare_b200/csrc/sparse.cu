@@ -165,38 +165,22 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
       constexpr int kChunks = kTilePx1 * (kTilePx1 * 24 / 16);  // 384
       ulonglong2 c0 = make_ulonglong2(0ull, 0ull), c1 = c0;
       const size_t row0 = 3 * ((size_t)tx * kTilePx1 + (size_t)ty * kTilePx1 * A.W);  // u64 index of the tile's first value
-      // all ranks' loads of a chunk are issued before any is consumed (peer loads: ~2.5 us each over NVLink -- one round trip
-      // per chunk, not one per rank)
-      {
-        const int row = tid / 24, col = tid - row * 24;
-        const size_t off = (size_t)row * 3 * A.W;
-        ulonglong2 v[LFB_MAX_PEERS];
-#pragma unroll
-        for (int r = 0; r < LFB_MAX_PEERS; r++) {
-          v[r] = make_ulonglong2(0ull, 0ull);
-          if (r < n && ((have >> r) & 1u)) v[r] = *(reinterpret_cast<const ulonglong2*>(A.acc.ptr[r] + row0 + off) + col);
+      for (int r = 0; r < n; r++) {
+        if (!((have >> r) & 1u)) continue;
+        unsigned long long* base = const_cast<unsigned long long*>(A.acc.ptr[r]) + row0;
+        {
+          const int row = tid / 24, col = tid - row * 24;
+          ulonglong2* src = reinterpret_cast<ulonglong2*>(base + (size_t)row * 3 * A.W) + col;
+          const ulonglong2 v = *src;
+          *src = make_ulonglong2(0ull, 0ull);  // the next frame finds the accumulators clear
+          c0.x += v.x; c0.y += v.y;
         }
-#pragma unroll
-        for (int r = 0; r < LFB_MAX_PEERS; r++) {
-          if (r < n && ((have >> r) & 1u))  // the next frame finds the accumulators clear
-            *(reinterpret_cast<ulonglong2*>(const_cast<unsigned long long*>(A.acc.ptr[r]) + row0 + off) + col) = make_ulonglong2(0ull, 0ull);
-          c0.x += v[r].x; c0.y += v[r].y;
-        }
-      }
-      if (tid + kThreads < kChunks) {
-        const int c = tid + kThreads, row = c / 24, col = c - row * 24;
-        const size_t off = (size_t)row * 3 * A.W;
-        ulonglong2 v[LFB_MAX_PEERS];
-#pragma unroll
-        for (int r = 0; r < LFB_MAX_PEERS; r++) {
-          v[r] = make_ulonglong2(0ull, 0ull);
-          if (r < n && ((have >> r) & 1u)) v[r] = *(reinterpret_cast<const ulonglong2*>(A.acc.ptr[r] + row0 + off) + col);
-        }
-#pragma unroll
-        for (int r = 0; r < LFB_MAX_PEERS; r++) {
-          if (r < n && ((have >> r) & 1u))
-            *(reinterpret_cast<ulonglong2*>(const_cast<unsigned long long*>(A.acc.ptr[r]) + row0 + off) + col) = make_ulonglong2(0ull, 0ull);
-          c1.x += v[r].x; c1.y += v[r].y;
+        if (tid + kThreads < kChunks) {
+          const int c = tid + kThreads, row = c / 24, col = c - row * 24;
+          ulonglong2* src = reinterpret_cast<ulonglong2*>(base + (size_t)row * 3 * A.W) + col;
+          const ulonglong2 v = *src;
+          *src = make_ulonglong2(0ull, 0ull);
+          c1.x += v.x; c1.y += v.y;
         }
       }
       s_acc[tid] = c0;
@@ -399,7 +383,7 @@ cudaError_t launch_tiles(const PeerAccums& P, int rank, int W, int H, double inv
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    ctas = P.n > 1 ? sms : 2 * sms;  // cross-GPU: its CTAs mostly wait for NVLink; fewer of them leave the co-running trace more of the SMs (N = 8: 0.1026 vs 0.1076 ms / step)
+    ctas = P.n > 1 ? sms : 2 * sms;  // cross-GPU: its CTAs mostly wait for NVLink; fewer of them leave the co-running trace more of the SMs (N = 8: 0.1026 vs 0.1076 ms / step; issuing all ranks' tile loads of a chunk before consuming any -- 80 registers -- was slower there: 0.1177)
   }
   if (ctas > lay.n_tiles) ctas = lay.n_tiles;
   tiles_kernel<<<ctas, kThreads, smem, s>>>(A);
