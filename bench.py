@@ -691,8 +691,9 @@ def run_ours(args):
             raise SystemExit("cudaHostRegister of the shared host frame failed: " + L.lfb_last_error().decode())
         base = L.lfb_host_device_pointer(host.ctypes.data)
         del pipe
+        drn = None if args.no_drain else capi.Engine(local, stream_priority=1)  # its stream carries the paced host writes
         pe = sharding.PeerSparse(eng, params, rank, world, dev, dist.group.WORLD, n_buffers=N_BUF, finalize_engine=fin,
-                                 host_out_ptrs=[base + b * frame_bytes for b in range(N_BUF)])
+                                 host_out_ptrs=[base + b * frame_bytes for b in range(N_BUF)], drain_engine=drn, host_stride=24)
 
         # two frames in flight per rank: before frame k is enqueued, frame k - 2 is collected -- complete in the host frame on EVERY
         # rank (PeerSparse.wait_frame: this rank passed the device-side barrier that each rank reaches after its reduce of that frame)
@@ -750,11 +751,14 @@ def run_ours(args):
             nz_tiles = 0
         d2h = nz_tiles * 256 * 24
         e2e_api = ("PeerSparse with shared page-locked host frames (3 in rotation, two frames in flight): every rank's lfb_reduce_tiles_peers "
-                   "writes its share of the dirty tiles straight into host memory over its own PCIe link; a frame is collected -- complete on "
-                   "every rank -- before the frame after next is enqueued (d2h_bytes_per_step counts the non-empty tiles; the ranks also "
+                   "leaves its share of the dirty tiles in a device staging buffer and lfb_drain_tiles copies it into host memory over the rank's "
+                   "own PCIe link, paced just under the link rate; a frame is collected -- complete on every rank -- before the frame after "
+                   "next is enqueued (d2h_bytes_per_step counts the non-empty tiles; the ranks also "
                    "re-zero the previous frame's)")
         del pe
         barrier()
+        if drn is not None:
+            drn.close()
         L.lfb_host_unregister(host.ctypes.data)
         del host
         shm.close()
@@ -954,6 +958,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and oracle-parity legs")
     ap.add_argument("--no-strict", action="store_true", help="skip the LFB_STRICT leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 3 / config 4 single-frame legs")
+    ap.add_argument("--no-drain", action="store_true", help="N > 1 e2e: the reduce kernels store into the host frame themselves (unpaced) instead of staging + paced drain")
     ap.add_argument("--reduce-ctas", type=int, default=0, help="CTAs of the cross-GPU tile reduce kernel (0: the library default)")
     ap.add_argument("--reduce", default="sparse", choices=["sparse", "nccl", "peer", "multicast"],
                     help="N > 1: tile-sparse reduce + finalize over NVLink peer memory (default), or round 1's dense paths: one NCCL int64 "

@@ -378,6 +378,17 @@ int lfb_finalize_tiles_device(lfb_engine* e, void* accum_dev, const lfb_params* 
  * events in a single-process host).  Integer sums: the frame has the same bits for any rank count. */
 int lfb_reduce_tiles_peers(lfb_engine* e, void* const* accum_ptrs, int n_ranks, int rank, const lfb_params* params,
                            void* out_dev, size_t out_stride_bytes, int out_elem, void* tile_state_dev);
+/* The same reduce for an output frame in page-locked HOST memory that is written while other frames are in flight (DESIGN.md
+ * 5b: stores into host memory must be paced, or the GPU cannot fetch its next commands while they drain).  Two launches:
+ * lfb_reduce_tiles_peers_staged leaves this rank's share of the frame's dirty tiles as pixels in stage_dev (device memory,
+ * lfb_tile_stage_bytes; only partial tiles at the frame's edge go to out_dev directly); lfb_drain_tiles -- on another engine's
+ * stream, ordered after it by the caller -- copies them into out_dev with a few CTAs paced just under the link rate
+ * (lfb_options.host_write_mbps).  tile_state_dev and stage_dev must not be reused before the drain has run. */
+size_t lfb_tile_stage_bytes(int width, int height, size_t out_stride_bytes);
+int lfb_reduce_tiles_peers_staged(lfb_engine* e, void* const* accum_ptrs, int n_ranks, int rank, const lfb_params* params,
+                                  void* out_dev, size_t out_stride_bytes, int out_elem, void* tile_state_dev, void* stage_dev);
+int lfb_drain_tiles(lfb_engine* e, const lfb_params* params, void* out_dev, size_t out_stride_bytes, const void* tile_state_dev,
+                    const void* stage_dev);
 /* The engine's CUDA stream (cudaStream_t) so callers can order work / record events. */
 void* lfb_stream(lfb_engine* e);
 /* Zero the accumulators, trace + splat this shard's ghosts (grid modes), all on the

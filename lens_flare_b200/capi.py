@@ -30,7 +30,7 @@ RAY_MISSED, RAY_VIGNETTED, RAY_TIR, RAY_STOPPED, RAY_OFF_SENSOR = 1, 2, 4, 8, 16
 
 # every symbol include/lfb200.h declares (tests check the library exports each one)
 SYMBOLS = (
-    "lfb_abi_version", "lfb_create", "lfb_create_ex", "lfb_exec_stats", "lfb_set_scene", "lfb_render_scene", "lfb_render_composite_rgba8", "lfb_create_multi", "lfb_destroy_multi", "lfb_multi_set_lens", "lfb_multi_set_aperture", "lfb_render_ghosts_multi", "lfb_multi_stats", "lfb_render_ghosts_sparse", "lfb_render_ghosts_sparse_begin", "lfb_render_ghosts_sparse_end", "lfb_sparse_slot_times", "lfb_tile_state_bytes", "lfb_finalize_tiles_device", "lfb_reduce_tiles_peers", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
+    "lfb_abi_version", "lfb_create", "lfb_create_ex", "lfb_exec_stats", "lfb_set_scene", "lfb_render_scene", "lfb_render_composite_rgba8", "lfb_create_multi", "lfb_destroy_multi", "lfb_multi_set_lens", "lfb_multi_set_aperture", "lfb_render_ghosts_multi", "lfb_multi_stats", "lfb_render_ghosts_sparse", "lfb_render_ghosts_sparse_begin", "lfb_render_ghosts_sparse_end", "lfb_sparse_slot_times", "lfb_tile_state_bytes", "lfb_finalize_tiles_device", "lfb_reduce_tiles_peers", "lfb_tile_stage_bytes", "lfb_reduce_tiles_peers_staged", "lfb_drain_tiles", "lfb_destroy", "lfb_last_error", "lfb_builtin_lens", "lfb_set_lens",
     "lfb_set_aperture", "lfb_render_ghosts", "lfb_render_ghosts_rect", "lfb_render_ghosts_async", "lfb_dump_rays", "lfb_ref_ghosts", "lfb_accum_bytes", "lfb_stream",
     "lfb_render_ghosts_device", "lfb_finalize_device", "lfb_sync", "lfb_reduce_finalize_peers", "lfb_peer_barrier", "lfb_count_work", "lfb_list_jobs", "lfb_stats",
     "lfb_host_alloc", "lfb_host_free", "lfb_host_register", "lfb_host_unregister", "lfb_host_device_pointer", "lfb_finalize_clear_device", "lfb_probe_peaks", "lfb_set_starburst_aperture", "lfb_render_starburst", "lfb_render_frame_rgba8",
@@ -209,6 +209,10 @@ def lib():
     L.lfb_sparse_slot_times.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.lfb_tile_state_bytes.argtypes = [C.c_int, C.c_int]
     L.lfb_tile_state_bytes.restype = C.c_size_t
+    L.lfb_tile_stage_bytes.restype = C.c_size_t
+    L.lfb_tile_stage_bytes.argtypes = [C.c_int, C.c_int, C.c_size_t]
+    L.lfb_reduce_tiles_peers_staged.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, PP, vp, C.c_size_t, C.c_int, vp, vp]
+    L.lfb_drain_tiles.argtypes = [vp, PP, vp, C.c_size_t, vp, vp]
     L.lfb_finalize_tiles_device.argtypes = [vp, vp, PP, vp, C.c_size_t, C.c_int, vp]
     L.lfb_reduce_tiles_peers.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, PP, vp, C.c_size_t, C.c_int, vp]
     L.lfb_create_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(Options)]
@@ -432,6 +436,13 @@ class Engine:
 
     def finalize_tiles_device(self, accum_ptr, params, out_ptr, stride, elem, state_ptr):
         check(lib().lfb_finalize_tiles_device(self._h, accum_ptr, C.byref(params), out_ptr, stride, elem, state_ptr))
+
+    def reduce_tiles_peers_staged(self, accum_ptrs, rank, params, out_ptr, stride, elem, state_ptr, stage_ptr):
+        arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)
+        check(lib().lfb_reduce_tiles_peers_staged(self._h, arr, len(accum_ptrs), rank, C.byref(params), out_ptr, stride, elem, state_ptr, stage_ptr))
+
+    def drain_tiles(self, params, out_ptr, stride, state_ptr, stage_ptr):
+        check(lib().lfb_drain_tiles(self._h, C.byref(params), out_ptr, stride, state_ptr, stage_ptr))
 
     def reduce_tiles_peers(self, accum_ptrs, rank, params, out_ptr, stride, elem, state_ptr):
         arr = (C.c_void_p * len(accum_ptrs))(*accum_ptrs)

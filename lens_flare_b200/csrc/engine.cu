@@ -1469,6 +1469,56 @@ extern "C" int lfb_reduce_tiles_peers(lfb_engine* e, void* const* accum_ptrs, in
   return LFB_OK;
 }
 
+// The two-stage form for an output frame in HOST memory written while other frames are in flight (include/lfb200.h):
+// lfb_reduce_tiles_peers_staged leaves this rank's share of the dirty tiles as pixels in stage_dev, lfb_drain_tiles copies them
+// into the host frame with a few clock-paced CTAs.
+extern "C" size_t lfb_tile_stage_bytes(int width, int height, size_t stride) {
+  if (width < 1 || height < 1 || stride < 12) return 0;
+  return tile_stage_bytes(width, height, stride);
+}
+
+extern "C" int lfb_reduce_tiles_peers_staged(lfb_engine* e, void* const* accum_ptrs, int n_ranks, int rank, const lfb_params* P, void* out_dev,
+                                             size_t stride, int elem, void* tile_state_dev, void* stage_dev) {
+  int rc = bind(e);
+  if (rc) return rc;
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (!accum_ptrs || n_ranks < 1 || n_ranks > LFB_MAX_PEERS || rank < 0 || rank >= n_ranks || !tile_state_dev || !stage_dev) return fail(LFB_ERR_INVALID, "bad peer set");
+  rc = check_out_args(out_dev, stride, elem);
+  if (rc) return rc;
+  PeerAccums A;
+  memset(&A, 0, sizeof(A));
+  A.n = n_ranks;
+  for (int r = 0; r < n_ranks; r++) {
+    if (!accum_ptrs[r]) return fail(LFB_ERR_INVALID, "NULL peer accumulator");
+    A.ptr[r] = (const unsigned long long*)accum_ptrs[r];
+  }
+  const double inv = ldexp(1.0, -(P->fixed_point_bits > 0 ? P->fixed_point_bits : 40));
+  CU(launch_tiles(A, rank, P->width, P->height, inv, out_dev, stride, elem, (unsigned*)tile_state_dev, nullptr, e->opt.reduce_ctas, e->stream, stage_dev));
+  e->launches++;
+  return LFB_OK;
+}
+
+extern "C" int lfb_drain_tiles(lfb_engine* e, const lfb_params* P, void* out_dev, size_t stride, const void* tile_state_dev, const void* stage_dev) {
+  int rc = bind(e);
+  if (rc) return rc;
+  rc = check_params(P, true);
+  if (rc) return rc;
+  if (!out_dev || !tile_state_dev || !stage_dev || stride < 12) return fail(LFB_ERR_INVALID, "NULL pointer");
+  if (e->drain_gbps < 0.f) {  // once per engine (as in lfb_render_ghosts_sparse_begin)
+    if (e->opt.host_write_mbps > 0) e->drain_gbps = 1e-3f * (float)e->opt.host_write_mbps;
+    else if (e->opt.host_write_mbps < 0) e->drain_gbps = 0.f;
+    else {
+      float link = 0.f;
+      CU(measure_host_write_gbps(e->stream, &link));
+      e->drain_gbps = link > 5.f ? 0.93f * link : 0.f;
+    }
+  }
+  CU(launch_tile_drain(P->width, P->height, out_dev, stride, (const unsigned*)tile_state_dev, stage_dev, e->opt.reduce_ctas > 0 && e->opt.reduce_ctas <= 64 ? e->opt.reduce_ctas : 0, e->drain_gbps, e->stream));
+  e->launches++;
+  return LFB_OK;
+}
+
 extern "C" int lfb_render_ghosts_sparse(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* P, void* out, size_t stride,
                                         int elem, int out_is_clear, int* tiles_written) {
   int rc = bind(e);

@@ -270,7 +270,12 @@ class PeerSparse:
     complete after finish()."""
 
     def __init__(self, engine, params, rank, world_size, device, group, n_buffers=3, out_dtype=torch.float32, finalize_engine=None,
-                 host_out_ptrs=None):
+                 host_out_ptrs=None, drain_engine=None, host_stride=24):
+        """drain_engine (with host_out_ptrs; every rank alike): a third engine whose stream C carries the host writes.  The reduce
+        then leaves this rank's tiles as pixels in a device staging buffer (lfb_reduce_tiles_peers_staged) and
+        lfb_drain_tiles copies them into the host frame with a few clock-paced CTAs -- unpaced stores into host memory keep
+        the GPU from fetching its next commands while they drain.  A frame is then complete on every rank once
+        this rank has passed the barrier on C that follows the drain (wait_frame)."""
         import torch.distributed._symmetric_memory as symm_mem
         self.engine, self.rank, self.world, self.device = engine, rank, world_size, device
         self.fin_engine = finalize_engine if finalize_engine is not None else engine
@@ -302,6 +307,19 @@ class PeerSparse:
         self.reduce_valid = [False] * self.n_buffers
         self.traced = [torch.cuda.Event() for _ in range(self.n_buffers)]
         self.passed = [torch.cuda.Event() for _ in range(self.n_buffers + 1)]  # [j % (R+1)]: this rank passed barrier(j) on B
+        self.drain_engine = drain_engine if (drain_engine is not None and host_out_ptrs is not None and self.two_streams) else None
+        if self.drain_engine is not None:
+            self.host_stride = host_stride
+            stage_bytes = capi.lib().lfb_tile_stage_bytes(W, H, host_stride)
+            self.stage = torch.zeros((self.n_buffers, (stage_bytes + 15) // 16 * 16), dtype=torch.uint8, device=device)
+            self.C = torch.cuda.ExternalStream(self.drain_engine.stream, device=device)
+            self.flags2 = symm_mem.empty((16,), dtype=torch.int64, device=device)  # the barriers on C have their own flags and epochs
+            self.flags2.zero_()
+            self.h_flags2 = symm_mem.rendezvous(self.flags2, group.group_name)
+            self.epoch2 = 0
+            self.drained = [torch.cuda.Event() for _ in range(self.n_buffers)]
+            self.drained_valid = [False] * self.n_buffers
+            self.done = [torch.cuda.Event() for _ in range(self.n_buffers + 1)]  # [j % (R+1)]: frame j is in host memory on every rank
         self.k = 0
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
@@ -310,6 +328,8 @@ class PeerSparse:
         cur = stream or torch.cuda.current_stream(self.device)
         self.A.wait_stream(cur)
         self.B.wait_stream(cur)
+        if self.drain_engine is not None:
+            self.C.wait_stream(cur)
 
     def barrier(self, engine=None):
         """Enqueue the device-side barrier on `engine`'s stream (default: the trace engine's)."""
@@ -319,8 +339,12 @@ class PeerSparse:
     def finish(self, stream=None):
         """All frames enqueued so far are complete in the owner's buffers once `stream` passes this point."""
         self.A.wait_stream(self.B)
-        self.barrier()  # on A, after everything on B: every rank's reduces are done
+        if self.drain_engine is not None:
+            self.A.wait_stream(self.C)
+        self.barrier()  # on A, after everything on B (and C): every rank's reduces (and drains) are done
         self.B.wait_stream(self.A)  # later barriers on B come after this one
+        if self.drain_engine is not None:
+            self.C.wait_stream(self.A)
         (stream or torch.cuda.current_stream(self.device)).wait_stream(self.A)
 
     def frame(self, lights, owner=0, elem=None, stride=None):
@@ -341,6 +365,23 @@ class PeerSparse:
             self.engine.render_ghosts_device(lights, self.params, my_acc, clear_first=False)
             self.barrier()
         ptrs = [int(p) + b * self.acc_bytes for p in self.h_acc.buffer_ptrs]
+        if self.drain_engine is not None:
+            out_ptr = self.host_out_ptrs[b]
+            el = elem if elem is not None else capi.F64x3
+            if self.drained_valid[b]:
+                self.B.wait_event(self.drained[b])  # the buffer's previous frame has left state[b] / stage[b]
+            self.fin_engine.reduce_tiles_peers_staged(ptrs, self.rank, self.full_params, out_ptr, self.host_stride, el, self.state[b].data_ptr(),
+                                                      self.stage[b].data_ptr())
+            self.reduce_events[b].record(self.B)
+            self.reduce_valid[b] = True
+            self.C.wait_event(self.reduce_events[b])
+            self.drain_engine.drain_tiles(self.full_params, out_ptr, self.host_stride, self.state[b].data_ptr(), self.stage[b].data_ptr())
+            self.drained[b].record(self.C)
+            self.drained_valid[b] = True
+            self.epoch2 += 1  # every rank arrives here after its drain of frame k
+            self.drain_engine.peer_barrier([int(p) for p in self.h_flags2.buffer_ptrs], self.rank, self.epoch2)
+            self.done[k % (R + 1)].record(self.C)
+            return b
         if self.host_out_ptrs is not None:
             out_ptr = self.host_out_ptrs[b]
             self.fin_engine.reduce_tiles_peers(ptrs, self.rank, self.full_params, out_ptr, stride or 24, elem if elem is not None else capi.F64x3,
@@ -358,6 +399,11 @@ class PeerSparse:
         """Block the host until frame j (0-based, in enqueue order) is complete in its output buffer ON EVERY RANK: this rank has
         passed barrier(j + 1), where each rank arrives only after its reduce(j).  Needs frame j + 1 enqueued and at most R frames
         enqueued after j (two streams only)."""
+        if self.drain_engine is not None:  # the barrier on C after the drain of frame j
+            if not (j < self.k <= j + 1 + self.n_buffers):
+                raise ValueError("wait_frame(%d): the frame must be enqueued and recent (k = %d)" % (j, self.k))
+            self.done[j % (self.n_buffers + 1)].synchronize()
+            return
         if not self.two_streams or not (j + 1 < self.k <= j + 1 + self.n_buffers):
             raise ValueError("wait_frame(%d): frame %d must be enqueued and recent (k = %d)" % (j, j + 1, self.k))
         self.passed[(j + 1) % (self.n_buffers + 1)].synchronize()

@@ -77,6 +77,61 @@ def main():
             same = all(torch.equal(g, wants[k]) for k, g in got)
             print(f"tile-sparse peer path (two streams={two}) == single GPU:", same)
             ok &= same
+    # --- the same into shared page-locked HOST frames, frames in flight: direct stores by the reduce kernels, and the staged
+    # reduce + paced drain (lfb_reduce_tiles_peers_staged / lfb_drain_tiles); a frame is read right after wait_frame()
+    from multiprocessing import shared_memory
+    cpu_group = dist.new_group(backend="gloo")
+    frame_bytes, R = H * W * 24, 3
+    name = [None]
+    if rank == 0:
+        shm = shared_memory.SharedMemory(create=True, size=R * frame_bytes)
+        name[0] = shm.name
+    dist.broadcast_object_list(name, src=0, group=cpu_group)
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=name[0])
+        try:
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:
+            pass
+    host = np.frombuffer(shm.buf, dtype=np.float64, count=R * H * W * 3).reshape(R, H, W, 3)
+    L = capi.lib()
+    assert L.lfb_host_register(host.ctypes.data, host.nbytes) == capi.OK
+    base = L.lfb_host_device_pointer(host.ctypes.data)
+    wants64 = [eng.render_ghosts(lt, params) for lt in suns] if rank == 0 else None
+    drn = capi.Engine(local, stream_priority=1)
+    for drain in (None, drn):
+        if rank == 0:
+            host[...] = 0.0
+        dist.barrier(group=cpu_group)
+        ps = sharding.PeerSparse(eng, params, rank, world, dev, dist.group.WORLD, n_buffers=R, finalize_engine=fin,
+                                 host_out_ptrs=[base + b * frame_bytes for b in range(R)], drain_engine=drain, host_stride=24)
+        same = True
+        ps.begin()
+        bufs = []
+        for k, lt in enumerate(suns):
+            if k >= 2:
+                ps.wait_frame(k - 2)  # frame k - 2 is complete on every rank
+                if rank == 0:
+                    same &= bool(np.array_equal(host[bufs[k - 2]], wants64[k - 2]))
+            bufs.append(ps.frame(lt, owner=0, elem=capi.F64x3, stride=24))
+        ps.finish()
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            for k in (len(suns) - 2, len(suns) - 1):
+                same &= bool(np.array_equal(host[bufs[k]], wants64[k]))
+            print("tile-sparse peer path into host frames, two in flight (%s) == single GPU:" % ("staged + paced drain" if drain else "direct stores"), same)
+            ok &= same
+        del ps
+        dist.barrier(group=cpu_group)
+    drn.close()
+    L.lfb_host_unregister(host.ctypes.data)
+    del host
+    shm.close()
+    dist.barrier(group=cpu_group)
+    if rank == 0:
+        shm.unlink()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     fin.close()
