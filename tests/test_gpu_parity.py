@@ -893,6 +893,51 @@ def test_sparse_two_frames_in_flight(apertures):
         e.close()
 
 
+@pytest.mark.parametrize("layout", ["f64_stride32", "f32_stride12", "f32_stride16", "f64_odd_width", "unpaced", "slow_pace"])
+def test_sparse_in_flight_layouts(apertures, layout):
+    """The staged tiles + paced drain of lfb_render_ghosts_sparse_begin / _end for the other output layouts (AVX Vector3D with
+    its padding lane, float pixels packed and padded, a frame whose rows are not 16-byte multiples: every tile then goes out
+    directly), unpaced and at a crawl: three slots, the sun moving, every collected frame bit for bit the blocking call's."""
+    opts = {"unpaced": dict(host_write_mbps=-1), "slow_pace": dict(host_write_mbps=2000)}.get(layout, {})
+    e = capi.Engine(0, **opts)
+    W, H = (999, 333) if layout == "f64_odd_width" else (1000, 562)
+    f32 = layout.startswith("f32")
+    lanes = {"f64_stride32": 4, "f32_stride16": 4}.get(layout, 3)
+    dt = np.float32 if f32 else np.float64
+    elem = capi.F32x3 if f32 else capi.F64x3
+    bufs = [capi.PinnedArray((H, W, lanes), dt) for _ in range(3)]
+    try:
+        e.set_lens(capi.builtin_lens(3, 550.0))
+        e.set_aperture(apertures["pentbig500_14"])
+        p = capi.make_params(capi.MODE_EXACT_GRID, W, H, grid_n=64, pair_set=capi.PAIRS_ALL, include_direct=1)
+        mk = lambda x, y, **kw: capi.make_light(x, y, theta=capi.physical_theta(x, y), **kw)  # noqa: E731
+        seq = [[mk(0.45, 0.55)], [mk(0.7, 0.3, radiance=(2.0, 1.0, 0.5))], [mk(0.3, 0.62)], [], [mk(0.45, 0.55), mk(0.3, 0.62)], [mk(0.52, 0.5)], [mk(0.6, 0.4)]]
+        want = [e.render_ghosts(lights, p, elem=elem) for lights in seq]
+        for b in bufs:
+            b.array[...] = 0
+        got = [None] * len(seq)
+        stride = lanes * np.dtype(dt).itemsize
+        for k, lights in enumerate(seq):
+            s = k % 3
+            if k >= 3:
+                assert e.render_ghosts_sparse_end(s) >= 0
+                got[k - 3] = bufs[s].array.copy()
+            e.render_ghosts_sparse_begin(lights, p, bufs[s].array, s, elem=elem, stride=stride, out_is_clear=(k < 3))
+        for k in range(len(seq) - 3, len(seq)):
+            e.render_ghosts_sparse_end(k % 3)
+            got[k] = bufs[k % 3].array.copy()
+        for k in range(len(seq)):
+            assert np.array_equal(got[k][..., :3], want[k]), (layout, k)
+            if lanes == 4:
+                assert not got[k][..., 3].any()
+        t = e.sparse_slot_times(0)
+        assert t[0] <= t[1] <= t[3] <= t[4] and t[2] <= t[3]
+    finally:
+        for b in bufs:
+            b.free()
+        e.close()
+
+
 def test_finalize_tiles_device_pipeline(apertures):
     """The device-resident form: lfb_render_ghosts_device (clear_first = 0) + lfb_finalize_tiles_device over frames keeps the
     accumulators clear and the output frame exact, F32x3 and F64x3."""
