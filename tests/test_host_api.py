@@ -97,6 +97,12 @@ def test_job_list_order_and_sharding(native_lib):
     assert abs(loads[0] - loads[1]) <= 26 and sum(loads) == 3 * 488
     groups0 = {(l, lam) for l, _, _, lam in capi.list_jobs(lens, capi.copy_params(p, shard=(0, 2)), 1)}
     assert (0, 0) in groups0 and (0, 1) not in groups0  # group 0 whole on rank 0, group 1 whole on rank 1, group 2 split
+    # contiguous blocks: with as many lights as shards every shard gets ALL wavelengths of exactly one light (its deposits, and
+    # the tiles the cross-GPU reduce fetches from it, then stay around that light), in the engine and in the oracle alike
+    for n in (2, 4, 8):
+        for r in range(n):
+            sh = capi.list_jobs(lens, capi.copy_params(p, shard=(r, n)), n)
+            assert {int(x[0]) for x in sh} == {r} and len(sh) == 29 * 3, (n, r)
     with pytest.raises(capi.LfbError):
         capi.list_jobs(lens, capi.copy_params(p, shard=(2, 2)), 1)
 
