@@ -391,7 +391,7 @@ def run_ours(args):
     rays_frame, inter_frame, jobs_frame = capi.count_work(lens, params, n_lights)
     assert inter_frame == nominal_interactions(n_lights), "bench.py's nominal count disagrees with lfb_count_work"
     N_BUF = 3  # rotating accumulator / output / state sets
-    fin = capi.Engine(local, stream_priority=1, reduce_ctas=args.reduce_ctas)  # the tile finalize / reduce runs on a second, high-priority stream
+    fin = capi.Engine(local, stream_priority=args.fin_priority, reduce_ctas=args.reduce_ctas)  # the tile finalize / reduce runs on a second, high-priority stream
     fin.set_lens(lens)
     fin.set_aperture(tex)
     A = torch.cuda.ExternalStream(eng.stream, device=dev)
@@ -958,6 +958,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and oracle-parity legs")
     ap.add_argument("--no-strict", action="store_true", help="skip the LFB_STRICT leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 3 / config 4 single-frame legs")
+    ap.add_argument("--fin-priority", type=int, default=1, help="stream priority of the tile finalize / reduce engine (1: highest, 0: default)")
     ap.add_argument("--no-drain", action="store_true", help="N > 1 e2e: the reduce kernels store into the host frame themselves (unpaced) instead of staging + paced drain")
     ap.add_argument("--reduce-ctas", type=int, default=0, help="CTAs of the cross-GPU tile reduce kernel (0: the library default)")
     ap.add_argument("--reduce", default="sparse", choices=["sparse", "nccl", "peer", "multicast"],
