@@ -313,6 +313,20 @@ def parity_block(eng, lens, tex, light, params):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def dirty_quadrants(*frames):
+    """8 x 8 sensor quadrants that hold a non-zero pixel in ANY of the (H, W, 3) frames: what the tile kernels write (a frame's own
+    non-zero quadrants plus those the output buffer's previous frame left)."""
+    nz = None
+    for f in frames:
+        m = f.sum(axis=2) != 0
+        H, W = m.shape
+        pad = np.zeros(((H + 7) // 8 * 8, (W + 7) // 8 * 8), bool)
+        pad[:H, :W] = m
+        q = pad.reshape(pad.shape[0] // 8, 8, pad.shape[1] // 8, 8).any(axis=(1, 3))
+        nz = q if nz is None else (nz | q)
+    return int(nz.sum())
+
+
 class SparsePipeline:
     """N = 1: R rotating (accumulators, output frame, tile state) sets on TWO streams:
         stream A (engine)                       trace frame k into accum[k % R] (clear_first = 0: the finalize left it clear)
@@ -588,7 +602,9 @@ def run_ours(args):
         e2e_extra["e2e_device_split_ms"] = {"trace_kernels": e2e_dev["last_trace_ms"], "whole_call_on_device": e2e_dev["last_frame_ms"],
                                             "note": "of one BLOCKING call; the rest of its ms_per_step is the 1 MB aperture upload + its synchronize, launch latency and the ctypes calls"}
         tiles = statistics.median(tiles_seen[-K:])
-        d2h = int(tiles) * 256 * 24 + 4
+        # bytes that cross PCIe per frame: the 8 x 8 quadrants (of the dirty 16 x 16 tiles) that are non-zero in this frame or were in
+        # the buffer's previous frame (the other sun), 24 bytes per pixel
+        d2h = dirty_quadrants(eng.render_ghosts(lights_a, params), eng.render_ghosts(lights_b, params)) * 64 * 24 + 4
         e2e_extra["e2e_blocking_call"] = {"value": inter_frame / (blocking_ms * 1e-3), "unit": "interactions/s", "ms_per_step": blocking_ms,
                                           "brackets_ms_per_step": [t / K for t in blocking_brackets], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                                           "api": "lfb_render_ghosts_sparse, one blocking call per frame (trace, then the tile kernel's PCIe-bound stores, then return)"}
@@ -636,7 +652,6 @@ def run_ours(args):
                 e2e_brackets.append((time.perf_counter() - t0) * 1e3)
         e2e_ms = statistics.median(e2e_brackets) / K
         tiles = statistics.median(tiles2[-K:])
-        d2h = int(tiles) * 256 * 24 + 4
         # every collected frame is the frame: the last two, against the full-frame call
         for s in range(R_SLOTS):
             kk = max(k for k in range(K) if k % R_SLOTS == s) if K > s else -1
@@ -650,8 +665,8 @@ def run_ours(args):
         eng.render_ghosts_sparse(lights_a, params, pinned_out.array, elem=capi.F64x3, out_is_clear=True)
         parity["e2e_frame_equals_full_frame_call"] = bool(np.array_equal(pinned_out.array, eng.render_ghosts(lights_a, params)))
         e2e_api = ("lfb_render_ghosts_sparse_begin / _end, %d frames in flight (F64x3, stride 24 = HDRImageBuffer layout, %d page-locked host "
-                   "frames in rotation): the device writes each frame's dirty 16x16 tiles (median %d of 8160, incl. the re-zeroed tiles of the "
-                   "buffer's previous frame) into the caller's memory, paced below the PCIe rate, while the next frames are traced; "
+                   "frames in rotation): the device writes the non-zero 8x8 quadrants of each frame's dirty 16x16 tiles (median %d tiles of 8160, incl. the re-zeroed "
+                   "ones of the buffer's previous frame) into the caller's memory, paced below the PCIe rate, while the next frames are traced; "
                    "e2e_blocking_call is the one-call-per-frame form" % (R_SLOTS, R_SLOTS, int(tiles)))
         # the same frame through the full-frame blocking call (every pixel crosses PCIe: round 1's e2e)
         ts = []
@@ -745,16 +760,15 @@ def run_ours(args):
         if rank == 0:
             whole64 = eng.render_ghosts(lights_a, params)
             parity["e2e_host_frame_equals_single_gpu"] = bool(np.array_equal(host[b], whole64))
-            nz_tiles = int((np.add.reduceat(np.add.reduceat((whole64.sum(axis=2) != 0).astype(np.int32), np.arange(0, HEIGHT, 16), axis=0),
-                                            np.arange(0, WIDTH, 16), axis=1) > 0).sum())
+            nz_quads = dirty_quadrants(whole64, eng.render_ghosts(lights_b, params))
         else:
-            nz_tiles = 0
-        d2h = nz_tiles * 256 * 24
+            nz_quads = 0
+        d2h = nz_quads * 64 * 24
         e2e_api = ("PeerSparse with shared page-locked host frames (3 in rotation, two frames in flight): every rank's lfb_reduce_tiles_peers "
                    "leaves its share of the dirty tiles in a device staging buffer and lfb_drain_tiles copies it into host memory over the rank's "
                    "own PCIe link, paced just under the link rate; a frame is collected -- complete on every rank -- before the frame after "
-                   "next is enqueued (d2h_bytes_per_step counts the non-empty tiles; the ranks also "
-                   "re-zero the previous frame's)")
+                   "next is enqueued (d2h_bytes_per_step counts the 8x8 quadrants that are non-zero in the frame or in "
+                   "the buffer's previous frame)")
         del pe
         barrier()
         if drn is not None:

@@ -249,8 +249,8 @@ int lfb_render_ghosts_rect(lfb_engine* e, const lfb_light* lights, int n_lights,
                            int out_elem, int* rect_out);
 
 /* Tile-sparse form of lfb_render_ghosts (grid modes, overwrite semantics).  A flare frame is ~99 % zeros: the splat kernels
- * mark the 16 x 16 sensor tiles they deposit into, and only those tiles -- plus the tiles the PREVIOUS frame left non-zero in
- * this same buffer, which are re-zeroed -- are converted and written, straight into the caller's memory from the device
+ * mark the 16 x 16 sensor tiles they deposit into, and only the non-zero 8 x 8 quadrants of those tiles -- plus the quadrants the
+ * PREVIOUS frame left non-zero in this same buffer, which are re-zeroed -- are converted and written, straight into the caller's memory from the device
  * (zero-copy over PCIe: `out` must be page-locked, lfb_host_alloc / lfb_host_register; pageable memory falls back to the
  * full-frame copy of lfb_render_ghosts and reports *tiles_written = -1).  On return `out` holds exactly this frame, bit for
  * bit what lfb_render_ghosts writes -- the reference's ghost_buffer after generate_ghost_buffer (pathtracer.cpp:714-762),
@@ -269,7 +269,7 @@ int lfb_render_ghosts_sparse(lfb_engine* e, const lfb_light* lights, int n_light
  * pixels are in `out` and reports the tiles written.  slot is in [0, LFB_SPARSE_SLOTS); each slot remembers ITS `out` buffer
  * (same contract as above: out_is_clear = 1 the first time, then the same buffer, untouched by others); a slot must be
  * collected by _end before its next _begin (LFB_ERR_STATE).  Three slots keep the device busy while the host prepares the
- * next frame (cfg2 with the sun moving every frame, 0.31 ms per blocking call, ~0.16 ms per frame in flight).  `out` must be page-locked and mapped
+ * next frame (cfg2 with the sun moving every frame, 0.23 ms per blocking call, 0.14 ms per frame in flight).  `out` must be page-locked and mapped
  * (LFB_ERR_INVALID otherwise: there is no staged fallback here).  The frames are bit for bit those of lfb_render_ghosts. */
 #define LFB_SPARSE_SLOTS 4
 int lfb_render_ghosts_sparse_begin(lfb_engine* e, const lfb_light* lights, int n_lights, const lfb_params* params,

@@ -97,8 +97,10 @@ inline AccumLayout accum_layout(int W, int H) {
   return a;
 }
 // The state that goes with an OUTPUT buffer of the tile-sparse finalize (lfb_tile_state_bytes): which tiles the previous
-// frame left non-zero in it.  [0] ticket, [1] tiles written by the last frame, [2..3] pad, then n_words tile-map words.
-inline size_t tile_state_bytes(int W, int H) { return 16 + (((size_t)accum_layout(W, H).n_words * 4 + 255) & ~(size_t)255); }
+// frame left non-zero in it.  [0] ticket, [1] tiles (staged units) of the last frame, [2] staging unit counter, [3] pad, then
+// n_words words of the PREVIOUS map (per tile one byte: the mask of its 8 x 8 quadrants the output holds non-zero pixels in) and
+// n_words words of the NEXT map (written during a launch, rolled over by its last CTA).
+inline size_t tile_state_bytes(int W, int H) { return 16 + (((size_t)accum_layout(W, H).n_words * 8 + 255) & ~(size_t)255); }
 
 // EXACT_GRID step program (exact_trace.cuh): a ghost flattened into straight-line steps with every ray-independent
 // quantity precomputed on the host.  T = float (the FP32 throughput kernels, 64 B per step) or double (LFB_STRICT: FP64
@@ -199,7 +201,7 @@ cudaError_t measure_host_write_gbps(cudaStream_t s, float* gbps);
 // bytes of the optional device staging buffer of launch_tiles: every tile's pixels + one word per tile
 inline size_t tile_stage_bytes(int W, int H, size_t stride) {
   const AccumLayout lay = accum_layout(W, H);
-  return (size_t)lay.n_tiles * kTilePx1 * kTilePx1 * stride + sizeof(unsigned) * (size_t)lay.n_tiles;
+  return (size_t)lay.n_tiles * kTilePx1 * kTilePx1 * stride + sizeof(unsigned) * 4 * (size_t)lay.n_tiles;  // pixels + one word per quadrant
 }
 cudaError_t launch_peer_barrier(const PeerFlags& F, int rank, unsigned long long epoch, cudaStream_t s);
 cudaError_t launch_reduce_finalize(const PeerAccums& P, const unsigned long long* mc, size_t p0, size_t p1, double inv_scale,

@@ -38,8 +38,8 @@ struct TileArgs {
   size_t stride;
   int elem;
   unsigned* count_out;   // optional (mapped host memory): the number of tiles this launch wrote
-  char* stage;           // optional: whole tiles go HERE, tile q at q * 16 * 16 * stride, rows packed (see drain_kernel) ...
-  unsigned* stage_tiles; // ... and [q] = the tile's byte offset in `out` / 16 (0xffffffff: tile q was stored directly)
+  char* stage;           // optional: the quadrants to write go HERE instead, unit u at u * 8 * 8 * stride, rows packed (see drain_kernel) ...
+  unsigned* stage_units; // ... and [u] = the quadrant's byte offset in `out` / 16
 };
 
 __device__ __forceinline__ unsigned* bits_of(const TileArgs& A, int r) {
@@ -69,8 +69,14 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
   __shared__ unsigned s_warp[kThreads / 32];
   __shared__ unsigned s_total;
   __shared__ bool s_last;
+  __shared__ unsigned s_quads;  // which 8 x 8 quadrants of the CTA's current tile hold a non-zero pixel (bit 2 * (y / 8) + x / 8)
+  __shared__ unsigned s_unit0;  // staging: the first unit of the CTA's current tile
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // Tile state: [0] ticket, [1] tiles (or staged units) of the last frame, [2] staging unit counter, [3] pad, then the PREVIOUS
+  // map -- per tile, one byte: the quadrants the output frame holds non-zero pixels in -- and the NEXT map being written by
+  // this launch (the last CTA rolls it over: the previous map is still being read by other CTAs until then).
   unsigned* prev = A.state + 4;
+  unsigned char* next = reinterpret_cast<unsigned char*>(A.state + 4 + A.n_words);
   const int n = A.acc.n;
   const size_t row_bytes = (size_t)kTilePx1 * A.stride;  // a tile row in the output: 16 pixels, contiguous
   const bool row_vec = A.stride <= 32 && ((size_t)A.out % 16) == 0 && (((size_t)A.W * A.stride) % 16) == 0;
@@ -201,12 +207,30 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
       }
     }
     const double v0 = (double)(long long)s0 * A.inv_scale, v1 = (double)(long long)s1 * A.inv_scale, v2 = (double)(long long)s2 * A.inv_scale;
+    // Quadrant sparsity: a dirty 16 x 16 tile is mostly zeros too (cfg2: 24 719 non-zero pixels lie in 128 512 pixels of dirty
+    // tiles, but in 76 288 pixels of dirty 8 x 8 quadrants).  Only the quadrants that hold a non-zero pixel now, or held one in
+    // the output's previous frame (the tile's byte in the previous map), are written: -41 % of the bytes that cross PCIe.
+    // A warp is two tile rows: lanes 0-7 / 16-23 are the left quadrant, 8-15 / 24-31 the right one; warps 0-3 the upper half.
+    __syncthreads();  // (every thread is done with the previous tile's s_quads / s_unit0)
+    if (tid == 0) s_quads = 0u;
+    __syncthreads();
+    {
+      const unsigned bal = __ballot_sync(0xffffffffu, inside && (s0 | s1 | s2) != 0ull);
+      if (lane == 0 && bal) atomicOr(&s_quads, (((bal & 0x00ff00ffu) ? 1u : 0u) | ((bal & 0xff00ff00u) ? 2u : 0u)) << (2 * (wid >> 2)));
+    }
+    __syncthreads();
+    const unsigned q_now = s_quads;
+    const unsigned q_prev = (prev[w] >> (8 * byte)) & 0xffu;
     // A full tile whose rows are 16-byte aligned in the output goes out as 16-byte chunks, row by row (16 pixels x stride bytes
     // are contiguous): whole 128-byte lines per warp -- what a PCIe (zero-copy host frame) or NVLink (peer frame) write wants;
     // 24-byte pixels stored 8 bytes per lane would go out as partial sectors (measured: 17 GB/s into host memory).
     const bool full = whole && row_vec;
-    if (A.stage && tid == 0)  // where the staged tile goes in the output, in 16-byte chunks
-      A.stage_tiles[q] = full ? (unsigned)((((size_t)ty * kTilePx1 * A.W + (size_t)tx * kTilePx1) * A.stride) >> 4) : 0xffffffffu;
+    // full tiles go out by quadrant; the others (frame edge, unaligned rows) whole, pixel by pixel -- their byte says "all four"
+    const unsigned q_write = full ? (q_now | (q_prev & 0xfu)) : 0xfu;
+    if (tid == 0) {
+      next[t] = (unsigned char)(full ? q_now : (q_now ? 0xfu : 0u));
+      if (A.stage) s_unit0 = full && q_write ? atomicAdd(A.state + 2, (unsigned)__popc(q_write)) : 0u;
+    }
     if (full) {
       char* mine = s_rows + (size_t)ly * row_bytes + (size_t)lx * A.stride;
       if (A.elem == LFB_F32x3) {
@@ -219,15 +243,26 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
         for (size_t q = 3; q < A.stride / 8; q++) o[q] = 0.0;
       }
       __syncthreads();
-      const int chunks_per_row = (int)(row_bytes / 16);
-      char* base = A.stage ? A.stage + (size_t)q * kTilePx1 * row_bytes : A.out + ((size_t)tx * kTilePx1 + (size_t)ty * kTilePx1 * A.W) * A.stride;
-      const size_t pitch = A.stage ? row_bytes : (size_t)A.W * A.stride;
+      const int chunks_per_row = (int)(row_bytes / 16), half = chunks_per_row / 2;  // (16 px * stride / 16 = stride: even)
+      const size_t tile_off = ((size_t)tx * kTilePx1 + (size_t)ty * kTilePx1 * A.W) * A.stride;
+      const size_t pitch = (size_t)A.W * A.stride;
+      const unsigned unit0 = s_unit0;
+      if (A.stage && tid < 4 && ((q_write >> tid) & 1u))  // where each staged quadrant goes in the output, in 16-byte chunks
+        A.stage_units[unit0 + __popc(q_write & ((1u << tid) - 1u))] =
+            (unsigned)((tile_off + (size_t)(tid >> 1) * 8 * pitch + (size_t)(tid & 1) * half * 16) >> 4);
       for (int c = tid; c < kTilePx1 * chunks_per_row; c += kThreads) {
         const int row = c / chunks_per_row, col = c - row * chunks_per_row;
-        *reinterpret_cast<uint4*>(base + (size_t)row * pitch + (size_t)col * 16) =
-            *reinterpret_cast<const uint4*>(s_rows + (size_t)row * row_bytes + (size_t)col * 16);
+        const int quad = 2 * (row >> 3) + (col >= half ? 1 : 0);
+        if (!((q_write >> quad) & 1u)) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(s_rows + (size_t)row * row_bytes + (size_t)col * 16);
+        if (A.stage) {  // unit = one quadrant: 8 rows of `half` chunks, packed
+          const unsigned u = unit0 + __popc(q_write & ((1u << quad) - 1u));
+          reinterpret_cast<uint4*>(A.stage)[(size_t)u * 8 * half + (size_t)(row & 7) * half + (col >= half ? col - half : col)] = v;
+        } else {
+          *reinterpret_cast<uint4*>(A.out + tile_off + (size_t)row * pitch + (size_t)col * 16) = v;
+        }
       }
-      __syncthreads();  // s_rows is reused by the CTA's next tile
+      __syncthreads();  // s_rows (and s_quads / s_unit0) are reused by the CTA's next tile
     } else if (inside) {
       if (A.elem == LFB_F32x3) {
         float* o = reinterpret_cast<float*>(A.out + p * A.stride);
@@ -240,39 +275,46 @@ __global__ void __launch_bounds__(kThreads) tiles_kernel(TileArgs A) {
   }
 
   // ---- 3. the CTA that finishes last rolls the tile maps over ----
-  // (no fence before the ticket: what the last CTA must not overtake are the other CTAs' READS of the maps, and those have
-  // completed -- their values were consumed above; this CTA's pixel stores need no ordering against the roll, and the kernel's
-  // end publishes them.  A __threadfence() here was 26 % of the kernel's stall samples.)
+  // (no CTA-wide fence before the ticket: what the last CTA must not overtake are the other CTAs' READS of the maps -- completed,
+  // their values were consumed above -- and their bytes of the NEXT map, which thread 0 wrote and fences itself; the pixel
+  // stores need no ordering against the roll, and the kernel's end publishes them.  A fence by all 256 threads here was 26 %
+  // of the kernel's stall samples.)
   __syncthreads();
-  if (tid == 0) s_last = atomicAdd(A.state, 1u) == gridDim.x - 1;
+  if (tid == 0) {
+    __threadfence();  // this thread's bytes of the next map, before the ticket
+    s_last = atomicAdd(A.state, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  unsigned* next_w = A.state + 4 + A.n_words;
   if (n == 1) {
     unsigned* cur = bits_of(A, 0);
     for (int wb = tid; wb < A.n_words; wb += 8 * kThreads) {
-      unsigned cv[8];
+      unsigned nv[8];  // eight words per thread, their loads in flight together
 #pragma unroll
-      for (int k = 0; k < 8; k++) cv[k] = wb + k * kThreads < A.n_words ? cur[wb + k * kThreads] : 0u;
+      for (int k = 0; k < 8; k++) nv[k] = wb + k * kThreads < A.n_words ? __ldcg(next_w + wb + k * kThreads) : 0u;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const int w = wb + k * kThreads;
         if (w >= A.n_words) break;
         cur[w] = 0u;
-        prev[w] = cv[k];
+        prev[w] = nv[k];
+        next_w[w] = 0u;
       }
     }
   } else {
     for (int w = tid; w < A.n_words; w += kThreads) {
       if (w % n != A.rank) continue;
-      const unsigned m = or_of_ranks(A, w);
       for (int r = 0; r < n; r++) bits_of(A, r)[w] = 0u;
-      prev[w] = m;
+      prev[w] = __ldcg(next_w + w);
+      next_w[w] = 0u;
     }
   }
   if (tid == 0) {
     A.state[0] = 0u;
-    A.state[1] = total;
+    A.state[1] = A.stage ? __ldcg(A.state + 2) : total;  // what drain_kernel copies: the staged units
+    A.state[2] = 0u;
     if (A.count_out) *A.count_out = total;
   }
 }
@@ -295,13 +337,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__global__ void __launch_bounds__(kThreads) drain_kernel(const char* __restrict__ stage, const unsigned* __restrict__ stage_tiles,
+__global__ void __launch_bounds__(kThreads) drain_kernel(const char* __restrict__ stage, const unsigned* __restrict__ stage_units,
                                                          const unsigned* __restrict__ state, char* __restrict__ out, int W, size_t stride,
                                                          float gbps) {
   __shared__ unsigned long long s_t0;
-  const unsigned total = state[1];  // tiles of this frame (tiles_kernel's last CTA)
-  const unsigned cpr = (unsigned)stride, cpt = kTilePx1 * cpr;  // 16-byte chunks per tile row (16 px * stride / 16) / per tile
-  const unsigned n_chunks = total * cpt;                         // < 2^32: launch_tiles checks
+  const unsigned total = state[1];  // staged units (8 x 8 quadrants) of this frame (tiles_kernel's last CTA)
+  const unsigned half = (unsigned)stride / 2u, cpu = 8u * half;  // 16-byte chunks per quadrant row (8 px * stride / 16) / per unit
+  const unsigned n_chunks = total * cpu;                          // < 2^32: launch_tiles checks
   const uint4* src = reinterpret_cast<const uint4*>(stage);
   const unsigned per_round = gridDim.x * kThreads;  // chunks per round: one per thread (16 CTAs: 64 KB)
   const float ns_per_round = gbps > 0.f ? (float)per_round * 16.f / gbps : 0.f;
@@ -310,9 +352,9 @@ __global__ void __launch_bounds__(kThreads) drain_kernel(const char* __restrict_
   if (threadIdx.x == 0) s_t0 = global_ns();
   __syncthreads();
   const unsigned lane0 = blockIdx.x * kThreads + threadIdx.x;
-  // this thread's chunk as (tile q, row, col), advanced by one round per step without divisions
-  unsigned q = lane0 / cpt, row = (lane0 - q * cpt) / cpr, col = lane0 - q * cpt - row * cpr;
-  const unsigned dq = per_round / cpt, drow = (per_round - dq * cpt) / cpr, dcol = per_round - dq * cpt - drow * cpr;
+  // this thread's chunk as (unit q, row, col), advanced by one round per step without divisions
+  unsigned q = lane0 / cpu, row = (lane0 - q * cpu) / half, col = lane0 - q * cpu - row * half;
+  const unsigned dq = per_round / cpu, drow = (per_round - dq * cpu) / half, dcol = per_round - dq * cpu - drow * half;
   uint4 cur[kDrainDepth], nxt[kDrainDepth];
 #pragma unroll
   for (int d = 0; d < kDrainDepth; d++) {
@@ -330,13 +372,12 @@ __global__ void __launch_bounds__(kThreads) drain_kernel(const char* __restrict_
     for (int d = 0; d < kDrainDepth; d++) {
       const unsigned c = g + lane0 + (unsigned)d * per_round;
       if (c < n_chunks) {
-        const unsigned off16 = __ldca(stage_tiles + q);  // the tile's first chunk in the output, or ~0: stored directly (frame edge)
-        if (off16 != 0xffffffffu)
-          reinterpret_cast<uint4*>(out)[(size_t)off16 + (size_t)row * pitch16 + col] = cur[d];
+        const unsigned off16 = __ldca(stage_units + q);  // the quadrant's first chunk in the output
+        reinterpret_cast<uint4*>(out)[(size_t)off16 + (size_t)row * pitch16 + col] = cur[d];
       }
       col += dcol; row += drow; q += dq;
-      if (col >= cpr) { col -= cpr; row++; }
-      if (row >= (unsigned)kTilePx1) { row -= kTilePx1; q++; }
+      if (col >= half) { col -= half; row++; }
+      if (row >= 8u) { row -= 8u; q++; }
       if (paced) {
         round++;
         if (threadIdx.x == 0) {
@@ -375,7 +416,7 @@ cudaError_t launch_tiles(const PeerAccums& P, int rank, int W, int H, double inv
   A.out = (char*)out; A.stride = stride; A.elem = elem;
   A.count_out = count_out;
   A.stage = (char*)stage;
-  A.stage_tiles = stage ? reinterpret_cast<unsigned*>((char*)stage + (size_t)lay.n_tiles * kTilePx1 * kTilePx1 * stride) : nullptr;
+  A.stage_units = stage ? reinterpret_cast<unsigned*>((char*)stage + (size_t)lay.n_tiles * kTilePx1 * kTilePx1 * stride) : nullptr;
   const size_t smem = sizeof(unsigned) * ((size_t)lay.n_words + 1);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // > 1.6 M tiles: use the dense finalize
   if (smem > 48 * 1024) {
@@ -400,8 +441,8 @@ cudaError_t launch_tile_drain(int W, int H, void* out, size_t stride, const unsi
                               cudaStream_t s) {
   const AccumLayout lay = accum_layout(W, H);
   const char* st = (const char*)stage;
-  const unsigned* stage_tiles = reinterpret_cast<const unsigned*>(st + (size_t)lay.n_tiles * kTilePx1 * kTilePx1 * stride);
-  drain_kernel<<<ctas > 0 ? ctas : 16, kThreads, 0, s>>>(st, stage_tiles, state, (char*)out, W, stride, gbps);
+  const unsigned* stage_units = reinterpret_cast<const unsigned*>(st + (size_t)lay.n_tiles * kTilePx1 * kTilePx1 * stride);
+  drain_kernel<<<ctas > 0 ? ctas : 16, kThreads, 0, s>>>(st, stage_units, state, (char*)out, W, stride, gbps);
   return cudaGetLastError();
 }
 
