@@ -181,15 +181,15 @@ typedef struct lfb_options {
   int32_t prefix_overlap;     /* forward sweeps of frame k+1 overlap the ghost kernel of frame k: 0 = on, -1 = off */
   int32_t starburst_lattice;  /* starburst on the aperture's periodic lattice: 0 = when the frame is larger than the period, -1 = never */
   int32_t starburst_cache;    /* keep the lattice spectrum |F| between frames (it depends on the mask alone): 0 = on, -1 = off */
-  int32_t reduce_ctas;        /* CTAs of the cross-GPU reduce kernels (0 = one per SM) and of lfb_render_ghosts_sparse_begin's
-                                 host-drain kernel (0 = 16) */
+  int32_t reduce_ctas;        /* CTAs of the cross-GPU tile reduce (0 = one per SM; the one-GPU finalize always runs two per SM) and
+                                 of the host-drain kernel of lfb_render_ghosts_sparse_begin / lfb_drain_tiles (0 = 16; at most 64) */
   int32_t collect_stats;      /* 1: run the counting instantiation of the EXACT_GRID kernels (lfb_exec_stats); slower */
   int64_t prefix_budget_bytes; /* device memory the cached forward sweeps may take: 0 = 40 GiB; < 0 = no cache */
   int32_t weights_table;      /* 1: Fresnel / coating weights from the 1024-interval tables for every ray (round 1's scheme,
                                  kept for A/B measurements) instead of the per-step polynomials */
   int32_t experiment;         /* bit mask of measurement switches that never change a frame's bits (tools/kernel_ab.py): 1 = look at the
                                  dirty-tile bytes in L2 (ld.global.cg) instead of through L1 (the default: 13 % faster at cfg2) */
-  int32_t host_write_mbps;    /* lfb_render_ghosts_sparse_begin: the pace, in MB/s, at which a frame's tiles are stored into host memory
+  int32_t host_write_mbps;    /* lfb_render_ghosts_sparse_begin, lfb_drain_tiles: the pace, in MB/s, at which a frame's tiles are stored into host memory
                                  while other frames are in flight: 0 = 93 % of what unpaced stores reach on this link (measured once,
                                  at the first call); < 0 = unpaced (the next frame's kernels then wait for the stores: see sparse.cu) */
   int32_t reserved[5];
