@@ -1,6 +1,7 @@
 // flare_demo.cpp -- the reference application's flare flags on top of the C++ facade:
 //   flare_demo -r W H -y ghost_aperture.png [-x starburst_aperture.png] [-s ns_x ns_y] [-m ref|paraxial|exact] [-g N] [-f out.pfm|out.png]
 // (-r, -x, -y, -f as in src/application/main.cpp:87, 135-152).  Prints frame statistics as one JSON line.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -19,6 +20,7 @@ int main(int argc, char** argv) {
   int mode = LFB_MODE_REF_QUADS, grid = 256;
   double flare_intensity = 1.0, flare_radius = 30.0;  // -i / -n, main.cpp:135-152
   int repeat = 0, pin = 1;                            // --repeat K: time K more generate_ghost_buffer() calls on the host clock
+  int frames = 0, in_flight = 3;                      // --frames N [--in-flight R]: an N-frame sweep of the sun, blocking and with R frames in flight
   int gpus = 1;                                       // --gpus N: devices 0 .. N-1 behind the one PathTracer (lfb_create_multi)
   if (argc == 3 && std::string(argv[1]) == "--png-info") {  // host-only: what CameraApertureTexture::init decodes
     try {
@@ -61,6 +63,8 @@ int main(int argc, char** argv) {
     else if (k == "--repeat" && a + 1 < argc) repeat = std::atoi(argv[++a]);
     else if (k == "--no-pin") pin = 0;
     else if (k == "--gpus" && a + 1 < argc) gpus = std::atoi(argv[++a]);
+    else if (k == "--frames" && a + 1 < argc) frames = std::atoi(argv[++a]);
+    else if (k == "--in-flight" && a + 1 < argc) in_flight = std::atoi(argv[++a]);
     else if (k == "-m" && a + 1 < argc) {
       const std::string m = argv[++a];
       mode = m == "exact" ? LFB_MODE_EXACT_GRID : (m == "paraxial" ? LFB_MODE_PARAXIAL_GRID : LFB_MODE_REF_QUADS);
@@ -124,6 +128,40 @@ int main(int argc, char** argv) {
       for (uint32_t px : rgba) bytes += (px & 0xFF) + ((px >> 8) & 0xFF) + ((px >> 16) & 0xFF);
       std::printf("{\"ghost_plus_starburst_sum\": [%.17g, %.17g, %.17g], \"starburst_ms\": %.4f, \"rgba8_byte_sum\": %llu, \"frame_ms\": %.4f}\n",
                   ssum[0], ssum[1], ssum[2], pt.last_trace_ms(), bytes, pt.last_frame_ms());
+    }
+    if (frames > 0 && mode != LFB_MODE_REF_QUADS && gpus <= 1) {
+      // a sequence: the sun moves on a small circle; every frame once through the blocking call, once through the ring of
+      // ghost buffers with `in_flight` frames in flight -- same pixels, less time per frame
+      if (in_flight < 1) in_flight = 1;
+      if (in_flight > LFB_SPARSE_SLOTS) in_flight = LFB_SPARSE_SLOTS;
+      auto place_sun = [&](int k) {
+        const double a = 2 * kPi * k / 16.0, x = sx + 0.03 * std::cos(a), y = sy + 0.03 * std::sin(a);
+        sun.posLight = lfb::Vector3D((2 * x - 1) * ex, (2 * y - 1) * ey, -1.0);  // (the constructor negates its argument)
+        pt.flare_origins.clear(); pt.flare_radiance.clear(); pt.flare_distance.clear();  // find_sun_pos() appends, as the reference's does
+        pt.find_sun_pos();
+      };
+      auto checksum = [](const lfb::HDRImageBuffer& b) {
+        double s = 0;
+        for (const lfb::Vector3D& v : b.data) s += v.x + 2 * v.y + 3 * v.z;
+        return s;
+      };
+      std::vector<double> want((size_t)frames), got((size_t)frames);
+      auto t0 = std::chrono::steady_clock::now();
+      for (int k = 0; k < frames; k++) { place_sun(k); pt.generate_ghost_buffer(); want[(size_t)k] = checksum(pt.ghost_buffer); }
+      const double blocking_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / frames;
+      t0 = std::chrono::steady_clock::now();
+      for (int k = 0; k < frames; k++) {
+        const int s = k % in_flight;
+        if (k >= in_flight) { pt.end_ghost_frame(s); got[(size_t)(k - in_flight)] = checksum(pt.ghost_ring[s]); }
+        place_sun(k);
+        pt.begin_ghost_frame(s);
+      }
+      for (int k = std::max(0, frames - in_flight); k < frames; k++) { pt.end_ghost_frame(k % in_flight); got[(size_t)k] = checksum(pt.ghost_ring[k % in_flight]); }
+      const double flight_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / frames;
+      int equal = 0;
+      for (int k = 0; k < frames; k++) equal += want[(size_t)k] == got[(size_t)k];
+      std::printf("{\"frames\": %d, \"in_flight\": %d, \"frames_equal\": %d, \"blocking_ms_per_frame_incl_checksum\": %.4f, "
+                  "\"in_flight_ms_per_frame_incl_checksum_and_ring_setup\": %.4f}\n", frames, in_flight, equal, blocking_ms, flight_ms);
     }
     const bool out_png = out.size() > 4 && out.compare(out.size() - 4, 4, ".png") == 0;
     if (out_png) {  // the tone-mapped flare frame, as save_image writes it (raytraced_renderer.cpp:717-755)

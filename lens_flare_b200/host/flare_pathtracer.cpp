@@ -78,9 +78,55 @@ PathTracer::PathTracer(const std::vector<int>& device_ids) : PathTracer(device_i
 }
 
 PathTracer::~PathTracer() {
+  for (int s = 0; s < LFB_SPARSE_SLOTS; s++)
+    if (ring_pending_[s] && engine_) lfb_render_ghosts_sparse_end(engine_, s, nullptr);  // nothing may still be writing into the ring
   unpin_storage();
   lfb_destroy_multi(multi_);
   lfb_destroy(engine_);
+  for (int s = 0; s < LFB_SPARSE_SLOTS; s++)
+    if (ring_pinned_[s]) lfb_host_unregister(ring_pinned_[s]);
+}
+
+void PathTracer::begin_ghost_frame(int slot) {
+  if (slot < 0 || slot >= LFB_SPARSE_SLOTS) throw Error(LFB_ERR_INVALID, "begin_ghost_frame: slot out of range");
+  if (params.mode == LFB_MODE_REF_QUADS) throw Error(LFB_ERR_STATE, "begin_ghost_frame: grid modes only (REF_QUADS frames are compact quads: generate_ghost_buffer)");
+  if (!device_ids_.empty()) throw Error(LFB_ERR_STATE, "begin_ghost_frame: one GPU only");
+  if (ring_pending_[slot]) throw Error(LFB_ERR_STATE, "begin_ghost_frame: the slot's previous frame was not collected (end_ghost_frame)");
+  HDRImageBuffer& B = ghost_ring[slot];
+  const size_t bytes = frame_w_ * frame_h_ * sizeof(Vector3D);
+  const bool same = B.w == frame_w_ && B.h == frame_h_ && B.data.size() == frame_w_ * frame_h_ && frame_w_ > 0 &&
+                    static_cast<void*>(B.data.data()) == ring_pinned_[slot] && bytes == ring_bytes_[slot];
+  int clear = 0;
+  if (!same) {  // (re)allocate, zero, page-lock: the engine's tile bookkeeping for this slot starts over
+    if (ring_pinned_[slot]) lfb_host_unregister(ring_pinned_[slot]);
+    ring_pinned_[slot] = nullptr;
+    B.clear();
+    B.resize(frame_w_, frame_h_);
+    if (B.data.empty()) throw Error(LFB_ERR_INVALID, "begin_ghost_frame: set_frame_size first");
+    ensure_engine();
+    check(lfb_host_register(B.data.data(), bytes), "lfb_host_register");
+    ring_pinned_[slot] = B.data.data();
+    ring_bytes_[slot] = bytes;
+    clear = 1;
+  }
+  const bool sun = !(axis_ray.x == 0 && axis_ray.y == 0);
+  if (sun) upload_textures(true, false);
+  else ensure_engine();
+  params.width = (int)frame_w_;
+  params.height = (int)frame_h_;
+  std::vector<lfb_light> lights = sun ? make_lights(true) : std::vector<lfb_light>();
+  check(lfb_render_ghosts_sparse_begin(engine_, lights.data(), (int)lights.size(), &params, B.data.data(), sizeof(Vector3D), LFB_F64x3, clear, slot),
+        "lfb_render_ghosts_sparse_begin");
+  ring_pending_[slot] = true;
+}
+
+int PathTracer::end_ghost_frame(int slot) {
+  if (slot < 0 || slot >= LFB_SPARSE_SLOTS) throw Error(LFB_ERR_INVALID, "end_ghost_frame: slot out of range");
+  if (!ring_pending_[slot]) throw Error(LFB_ERR_STATE, "end_ghost_frame: no frame in flight in this slot");
+  int tiles = 0;
+  check(lfb_render_ghosts_sparse_end(engine_, slot, &tiles), "lfb_render_ghosts_sparse_end");
+  ring_pending_[slot] = false;
+  return tiles;
 }
 
 void PathTracer::unpin_storage() {

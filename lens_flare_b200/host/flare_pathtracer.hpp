@@ -153,6 +153,14 @@ class PathTracer {
   // The storage is unregistered when it moves, changes size, or the PathTracer dies; do not reallocate ghost_buffer.data
   // behind the PathTracer's back while this is on.
   bool pin_ghost_buffer = true;
+  // Frames in flight (grid modes, one GPU; lfb_render_ghosts_sparse_begin / _end): a ring of ghost buffers for a host that
+  // renders a sequence.  begin_ghost_frame(slot) is generate_ghost_buffer() for ghost_ring[slot] -- current flare_origins /
+  // axis_ray from find_sun_pos(), page-locked on first use -- without the wait; end_ghost_frame(slot) blocks until that frame
+  // is complete in ghost_ring[slot] and returns the 16 x 16 tiles it wrote.  A slot is collected before it is begun again;
+  // ghost_ring[slot] must only be written through these calls (resize it, or the frame, and it starts clear again).
+  HDRImageBuffer ghost_ring[LFB_SPARSE_SLOTS];
+  void begin_ghost_frame(int slot);
+  int end_ghost_frame(int slot);
   void invalidate_ghost_buffer() { buffer_state_ = kUnknown; }
   int last_tiles_written() const { return last_tiles_; }  // tiles the last sparse render wrote (-1: full-frame fallback)
   // stats of the last generate_ghost_buffer(): device ms of the trace kernels and of the whole call
@@ -161,6 +169,9 @@ class PathTracer {
 
  private:
   void ensure_engine();
+  void* ring_pinned_[LFB_SPARSE_SLOTS] = {};
+  size_t ring_bytes_[LFB_SPARSE_SLOTS] = {};
+  bool ring_pending_[LFB_SPARSE_SLOTS] = {};
   lfb_engine* engine_ = nullptr;
   lfb_multi* multi_ = nullptr;
   std::vector<int> device_ids_;

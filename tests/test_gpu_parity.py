@@ -675,6 +675,12 @@ def test_cpp_facade_end_to_end(golden, apertures, port, tmp_path):
     p = capi.make_params(capi.MODE_EXACT_GRID, 640, 360, grid_n=64, pair_set=capi.PAIRS_ALL, include_direct=1)
     want = port.render(lens, apertures["pent_11"], lt, p)
     assert want.any() and np.allclose(info["sum"], want.reshape(-1, 3).sum(0), rtol=2e-3)
+    # a sequence through the facade's ring of ghost buffers (begin_ghost_frame / end_ghost_frame, three frames in flight): every
+    # frame has the pixels of the blocking generate_ghost_buffer()
+    out = subprocess.run([os.path.join(host, "flare_demo"), "-r", "640", "360", "-y", str(png), "-s", "0.45", "0.55", "-m", "exact", "-g", "64",
+                          "--frames", "13", "--in-flight", "3"], check=True, capture_output=True, text=True).stdout
+    seq = json.loads(out.strip().splitlines()[-1])
+    assert seq["frames"] == 13 and seq["in_flight"] == 3 and seq["frames_equal"] == 13, seq
 
 
 @pytest.mark.parametrize("mode", [capi.MODE_REF_QUADS, capi.MODE_PARAXIAL_GRID, capi.MODE_EXACT_GRID])
