@@ -149,6 +149,12 @@ def test_sharded_oracle_sums_to_whole(port, apertures):
             _, a = port.render(lens, apertures["pent_11"], lights, ob.copy_params(p, shard=(r, n)), want_accum=True)
             tot += a
         assert np.array_equal(tot, whole)
+    # contiguous blocks of (light, lambda) groups, like the engine's list (tests/test_host_api.py): with as many shards as lights,
+    # shard r is exactly light r's frame
+    for r in range(2):
+        _, a = port.render(lens, apertures["pent_11"], lights, ob.copy_params(p, shard=(r, 2)), want_accum=True)
+        _, alone = port.render(lens, apertures["pent_11"], [lights[r]], p, want_accum=True)
+        assert alone.any() and np.array_equal(a, alone), r
 
 
 # ---------------------------------------------------------------------------------------------
